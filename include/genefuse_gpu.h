@@ -1,0 +1,197 @@
+/*
+ * genefuse_gpu.h — C ABI of the B200-native fusion-matching hot path.
+ *
+ * This is the drop-in boundary for GeneFuseRust's per-read matching path.  The
+ * reference has no FFI of its own (pure Rust); the two call sites this library
+ * replaces are
+ *
+ *   Indexer::make_index            src/core/indexer.rs:122-177   -> gf_index_create
+ *   PairEndScanner::scan_pair_end  src/core/pescanner.rs:427-518 -> gf_map_pairs
+ *   SingleEndScanner::scan_single_end src/core/sescanner.rs:183-205 -> gf_map_pairs (seq2 == NULL)
+ *
+ * and the functions below them on the path (Indexer::map_read :252-538,
+ * in_required_direction :541-608, FusionMapper::map_read / make_match /
+ * calc_distance / calc_ed  src/core/fusion_mapper.rs:93-251, edit_distance
+ * src/core/edit_distance.rs:164-197, SequenceReadPair::fast_merge
+ * src/core/read.rs:313-440, reverse_complement src/core/sequence.rs:22-60).
+ *
+ * Everything is plain pointers and sizes.  All compute runs in hand-written
+ * sm_100a CUDA kernels; there is no CPU fallback: every entry point fails with
+ * GF_E_CUDA when no usable device is present.
+ *
+ * Threading: calls on DIFFERENT gf_index handles are independent.  Calls on
+ * the same handle are serialised internally (one mutex per handle).
+ */
+#ifndef GENEFUSE_GPU_H
+#define GENEFUSE_GPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GF_ABI_VERSION 1
+
+/* status codes (0 = ok, negative = error; text via gf_last_error()) */
+enum gf_status {
+    GF_OK = 0,
+    GF_E_INVALID = -1,   /* bad argument (NULL, inconsistent offsets, too long read, ...) */
+    GF_E_CUDA = -2,      /* CUDA runtime error / no device */
+    GF_E_CAPACITY = -3,  /* out_cap too small; *n_out = required count */
+    GF_E_LIMIT = -4,     /* input exceeds a documented limit of the index layout */
+    GF_E_REF_PANIC = -5  /* the reference would panic on this input (edit distance > 640 cols both sides,
+                            src/core/edit_distance.rs:94-100,177-196) */
+};
+
+/* Limits.  FASTQ lines longer than 1000 bytes make the reference panic
+ * (src/core/fastq_reader.rs:27, src/aux/limited_bufreader.rs:75-87). */
+#define GF_MAX_READ_LEN 1000u
+#define GF_MAX_SEQ_LEN 2048u /* >= 2*GF_MAX_READ_LEN - 30 (longest merged read) */
+#define GF_KMER 16           /* src/core/indexer.rs:35 */
+
+/* One fusion gene as Indexer::make_index sees it AFTER the host resolved the
+ * chromosome name and sliced + upper-cased contig[m_start..m_end]
+ * (src/core/indexer.rs:136-159).  len == 0 stands for an unresolved chromosome
+ * (the gene keeps its contig id, :148-151). */
+typedef struct gf_gene_span {
+    const uint8_t* seq;   /* upper-cased gene bytes, may contain N / IUPAC */
+    uint32_t len;
+    uint8_t reversed;     /* Gene::is_reversed(), src/core/gene.rs:98-107 */
+} gf_gene_span;
+
+/* GlobalSettings fields read on the path (src/aux/global_settings.rs:15-29). */
+typedef struct gf_params {
+    int32_t skip_key_dup_threshold;      /* 5  */
+    int32_t major_gene_key_requirement;  /* 40 */
+    int32_t minor_gene_key_requirement;  /* 20 */
+    int32_t mismatch_threshold;          /* 10 */
+} gf_params;
+
+/* A batch of read pairs (PE) or reads (SE: seq2 == qual2 == off2 == NULL) as
+ * byte arenas with n+1 offsets each.  Record i of arena k is
+ * seqk[offk[i] .. offk[i+1]) and its quality string qualk[offk[i] .. offk[i+1])
+ * (same offsets: FASTQ sequence and quality have equal length).
+ * For gf_map_pairs the pointers are HOST pointers (pinned memory makes the
+ * H2D copy faster but is not required); for gf_map_pairs_device they are
+ * DEVICE pointers. */
+typedef struct gf_batch {
+    uint64_t n;
+    const uint8_t* seq1;
+    const uint8_t* qual1;
+    const uint64_t* off1;
+    const uint8_t* seq2;
+    const uint8_t* qual2;
+    const uint64_t* off2;
+    uint64_t bytes1; /* == off1[n] */
+    uint64_t bytes2; /* == off2[n] (0 for SE) */
+} gf_batch;
+
+/* One fusion match = the integer content of a ReadMatch
+ * (src/core/read_match.rs:17-30) plus where it came from.  The host rebuilds
+ * the strings (fast_merge / reverse_complement on the few matched pairs).
+ * Records are emitted sorted by (pair_idx, source). */
+typedef struct gf_match {
+    uint64_t pair_idx;   /* index into the batch */
+    int32_t read_break;  /* m_read_break */
+    int32_t l_pos;       /* m_left_gp.position  (after make_match's shift) */
+    int32_t r_pos;       /* m_right_gp.position */
+    int32_t gap;         /* m_gap */
+    int32_t l_dist;      /* m_left_distance  (-1 / -2 sentinels of calc_ed kept) */
+    int32_t r_dist;      /* m_right_distance */
+    int32_t seq_len;     /* length of the sequence that matched (m_read.m_seq) */
+    int16_t l_contig;    /* m_left_gp.contig */
+    int16_t r_contig;    /* m_right_gp.contig */
+    int16_t merge_olen;  /* overlap length of fast_merge, -1 when the pair did not merge */
+    int16_t merge_diff;  /* the N of "merged_diff_N" (src/core/read.rs:372) */
+    uint8_t source;      /* 0 = merged read, 1 = R1, 2 = R2 */
+    uint8_t used_rc;     /* 1 = the match was found on the reverse complement (rc retry) */
+    uint8_t reversed;    /* m_reversed: set only for R1/R2 rc matches (pescanner.rs:483,506), never for merged */
+    uint8_t pad;
+} gf_match;
+
+typedef struct gf_index gf_index; /* opaque */
+
+typedef struct gf_index_info {
+    uint64_t n_sites;        /* valid indexed k-mer occurrences (both strands) */
+    uint64_t n_keys;         /* distinct k-mers (= set bits of the reference's bitmap) */
+    uint64_t n_unique;       /* keys with one site */
+    uint64_t n_normal;       /* keys with 2..skip_key_dup_threshold sites (DUPE_NORMAL_LEVEL) */
+    uint64_t n_high;         /* keys with more (DUPE_HIGH_LEVEL) */
+    uint64_t table_slots;    /* open-addressed slots allocated */
+    uint64_t table_bytes;
+    uint64_t max_displacement; /* worst (slot - home slot) */
+    uint64_t gene_bytes;     /* Σ gene lengths */
+    uint64_t device_bytes;   /* total HBM held by the handle */
+    double build_ms;         /* device time of the build */
+} gf_index_info;
+
+/* Result of a debug/parity lookup of one 16-mer (A=0,T=1,C=2,G=3, first base in
+ * the top bits; src/core/indexer.rs:852-913). */
+typedef struct gf_lookup {
+    int32_t kind;            /* 0 absent-or-HIGH, 1 unique, 2 NORMAL dupe */
+    int32_t n_sites;
+    int16_t contig[8];
+    int32_t position[8];
+} gf_lookup;
+
+/* Result of the device fast_merge for one pair (parity hook). */
+typedef struct gf_merge_info {
+    int32_t merged;          /* 0 / 1 */
+    int32_t olen;
+    int32_t diff;
+    int32_t merged_len;
+} gf_merge_info;
+
+/* Per-call device timing and counters of the last gf_map_pairs* on a handle. */
+typedef struct gf_map_stats {
+    uint64_t n_pairs;
+    uint64_t n_sequences;    /* sequences screened (merged or R1+R2) */
+    uint64_t n_probes_pass1; /* Σ P1(len) */
+    uint64_t n_survivors;    /* sequences sent to the exact path */
+    uint64_t n_matches;
+    uint64_t seq_bytes;      /* Σ len of the screened sequences */
+    uint64_t kernel_launches;
+    float ms_total;          /* device time, events on the call's stream */
+    float ms_merge;
+    float ms_screen;
+    float ms_exact;
+} gf_map_stats;
+
+const char* gf_last_error(void);
+int gf_abi_version(void);
+int gf_device_count(void);
+void gf_default_params(gf_params* p);
+
+/* Build the fusion-gene index on `device` (replaces Indexer::make_index rows:
+ * index_contig fwd + reverse complement, dedup 1 / 2..5 / >=6, membership). */
+int gf_index_create(const gf_gene_span* genes, uint32_t n_genes, const gf_params* params,
+                    int device, gf_index** out);
+void gf_index_destroy(gf_index* idx);
+int gf_index_get_info(const gf_index* idx, gf_index_info* out);
+int gf_index_lookup(gf_index* idx, const uint32_t* kmers, uint64_t n, gf_lookup* out);
+
+/* Map a batch held in HOST memory: H2D copy, merge, screen, exact path,
+ * verification, D2H of the match records.  SE when in->seq2 == NULL.
+ * Returns GF_E_CAPACITY (and *n_out = needed) when out_cap is too small. */
+int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_cap, uint64_t* n_out);
+
+/* Same on a batch already resident in DEVICE memory of the index's device.
+ * `d_out` / `d_n_out` are device pointers (capacity out_cap records / one
+ * uint64).  Work is enqueued on `cuda_stream` (a cudaStream_t, NULL = legacy
+ * default stream) and NOT synchronised: the caller owns the stream.  Records
+ * are in arbitrary order here; gf_sort_matches orders a host copy. */
+int gf_map_pairs_device(gf_index* idx, const gf_batch* in_dev, gf_match* d_out, uint64_t out_cap,
+                        uint64_t* d_n_out, void* cuda_stream);
+void gf_sort_matches(gf_match* m, uint64_t n); /* by (pair_idx, source), host */
+
+int gf_get_map_stats(const gf_index* idx, gf_map_stats* out);
+
+/* Parity hook: run only the device fast_merge on a HOST batch. */
+int gf_fast_merge(gf_index* idx, const gf_batch* in, gf_merge_info* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENEFUSE_GPU_H */
