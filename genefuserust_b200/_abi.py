@@ -45,6 +45,8 @@ class gf_batch(C.Structure):
         ("off2", C.c_void_p),
         ("bytes1", C.c_uint64),
         ("bytes2", C.c_uint64),
+        ("max_len", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 

@@ -31,6 +31,9 @@ class ReadBatch:
             self.seq2 = self.qual2 = self.off2 = None
         assert len(self.seq1) == len(self.qual1) == int(self.off1[-1])
         self.n = len(self.off1) - 1
+        self.max_len = int(np.diff(self.off1).max()) if self.n else 0
+        if self.paired and self.n:
+            self.max_len = max(self.max_len, int(np.diff(self.off2).max()))
 
     @classmethod
     def from_reads(cls, r1, r2=None):
@@ -66,6 +69,7 @@ class ReadBatch:
         b.qual1 = self.qual1.ctypes.data
         b.off1 = self.off1.ctypes.data
         b.bytes1 = int(self.off1[-1])
+        b.max_len = self.max_len
         if self.paired:
             b.seq2 = self.seq2.ctypes.data
             b.qual2 = self.qual2.ctypes.data

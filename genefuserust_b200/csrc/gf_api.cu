@@ -1,0 +1,396 @@
+/*
+ * gf_api.cu — the C ABI (include/genefuse_gpu.h): handles, host<->device staging, stream pipeline.
+ * No CPU fallback: every compute entry point needs a CUDA device and fails with GF_E_CUDA otherwise.
+ */
+#include <algorithm>
+#include <cstring>
+
+#include "gf_internal.h"
+
+static thread_local std::string g_last_error;
+void gf_set_error(const std::string& msg) { g_last_error = msg; }
+
+namespace {
+
+constexpr uint64_t CHUNK_TARGET_BYTES = 192ull << 20; /* sequence+quality bytes per pipeline chunk */
+
+int fail(int code, const std::string& msg) {
+    gf_set_error(msg);
+    return code;
+}
+
+void accumulate(gf_map_stats& st, const GfHostSlot& h) {
+    st.n_sequences += h.counters.n_sequences;
+    st.n_probes_pass1 += h.counters.n_probes;
+    st.n_survivors += h.counters.n_survivors;
+    st.n_matches += h.n_out;
+    st.seq_bytes += h.counters.seq_bytes;
+}
+
+int check_flags(const GfHostSlot& h) {
+    if (h.counters.error_flags & 1u)
+        return fail(GF_E_INVALID, "a read is longer than the kernel capacity (max_len hint too small, or > 1024 bases)");
+    if (h.counters.error_flags & 2u) return fail(GF_E_CUDA, "internal: survivor list overflow");
+    return GF_OK;
+}
+
+void destroy_handle(gf_index* idx) {
+    if (!idx) return;
+    cudaSetDevice(idx->device);
+    if (idx->stream) cudaStreamSynchronize(idx->stream);
+    if (idx->copy_stream) cudaStreamSynchronize(idx->copy_stream);
+    cudaFree(idx->d_table);
+    cudaFree(idx->d_dupes);
+    cudaFree(idx->d_gene_ascii);
+    cudaFree(idx->d_gene_start);
+    cudaFree(idx->d_gene_len);
+    cudaFree(idx->d_gene_rev);
+    idx->ws_survivors.release();
+    idx->ws_counters.release();
+    idx->ws_gtbl.release();
+    for (auto& s : idx->stage) {
+        s.seq1.release(); s.qual1.release(); s.off1.release();
+        s.seq2.release(); s.qual2.release(); s.off2.release();
+        s.out.release(); s.nout.release();
+        if (s.copied) cudaEventDestroy(s.copied);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    if (idx->h_slots) cudaFreeHost(idx->h_slots);
+    for (cudaEvent_t e : {idx->ev_start, idx->ev_screen, idx->ev_exact, idx->ev_end})
+        if (e) cudaEventDestroy(e);
+    if (idx->stream) cudaStreamDestroy(idx->stream);
+    if (idx->copy_stream) cudaStreamDestroy(idx->copy_stream);
+    delete idx;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gf_last_error(void) { return g_last_error.c_str(); }
+int gf_abi_version(void) { return GF_ABI_VERSION; }
+
+int gf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void gf_default_params(gf_params* p) {
+    /* src/aux/global_settings.rs:15-29 */
+    p->skip_key_dup_threshold = 5;
+    p->major_gene_key_requirement = 40;
+    p->minor_gene_key_requirement = 20;
+    p->mismatch_threshold = 10;
+}
+
+int gf_index_create(const gf_gene_span* genes, uint32_t n_genes, const gf_params* params, int device,
+                    gf_index** out) {
+    if (!out) return fail(GF_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_genes && !genes) return fail(GF_E_INVALID, "genes is NULL");
+    if (n_genes > 32767) return fail(GF_E_LIMIT, "more than 32767 genes: contig ids are i16 (src/core/common.rs:5)");
+    gf_params p;
+    if (params) p = *params; else gf_default_params(&p);
+    if (p.skip_key_dup_threshold < 0 || p.skip_key_dup_threshold > GF_MAX_DUPES)
+        return fail(GF_E_LIMIT, "skip_key_dup_threshold must be in [0, 7] (3-bit site count)");
+    for (uint32_t g = 0; g < n_genes; g++)
+        if (genes[g].len && !genes[g].seq) return fail(GF_E_INVALID, "gene with len > 0 and seq == NULL");
+    int ndev = gf_device_count();
+    if (ndev <= 0) return fail(GF_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(GF_E_INVALID, "device index out of range");
+    GF_CUDA_TRY(cudaSetDevice(device));
+
+    gf_index* idx = new gf_index();
+    idx->device = device;
+    idx->params = p;
+    int rc = GF_OK;
+    do {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { rc = fail(GF_E_CUDA, "cudaGetDeviceProperties failed"); break; }
+        idx->sm_count = prop.multiProcessorCount;
+        if (cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&idx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            rc = fail(GF_E_CUDA, "cudaStreamCreate failed");
+            break;
+        }
+        bool ok = cudaEventCreate(&idx->ev_start) == cudaSuccess && cudaEventCreate(&idx->ev_screen) == cudaSuccess &&
+                  cudaEventCreate(&idx->ev_exact) == cudaSuccess && cudaEventCreate(&idx->ev_end) == cudaSuccess;
+        for (auto& s : idx->stage)
+            ok = ok && cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaMallocHost((void**)&idx->h_slots, sizeof(GfHostSlot) * 3) == cudaSuccess;
+        if (!ok) { rc = fail(GF_E_CUDA, "event / pinned allocation failed"); break; }
+        memset(idx->h_slots, 0, sizeof(GfHostSlot) * 3);
+        rc = gf_build_index_device(idx, genes, n_genes);
+    } while (0);
+    if (rc != GF_OK) {
+        std::string keep = g_last_error;
+        destroy_handle(idx);
+        cudaGetLastError();
+        g_last_error = keep;
+        return rc;
+    }
+    *out = idx;
+    return GF_OK;
+}
+
+void gf_index_destroy(gf_index* idx) { destroy_handle(idx); }
+
+int gf_index_get_info(const gf_index* idx, gf_index_info* out) {
+    if (!idx || !out) return fail(GF_E_INVALID, "NULL argument");
+    *out = idx->info;
+    return GF_OK;
+}
+
+int gf_index_lookup(gf_index* idx, const uint32_t* kmers, uint64_t n, gf_lookup* out) {
+    if (!idx || (n && (!kmers || !out))) return fail(GF_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    GF_CUDA_TRY(cudaSetDevice(idx->device));
+    return gf_lookup_device(idx, kmers, n, out);
+}
+
+void gf_sort_matches(gf_match* m, uint64_t n) {
+    std::sort(m, m + n, [](const gf_match& a, const gf_match& b) {
+        if (a.pair_idx != b.pair_idx) return a.pair_idx < b.pair_idx;
+        return a.source < b.source;
+    });
+}
+
+static int validate_batch(const gf_batch* in) {
+    if (!in) return fail(GF_E_INVALID, "batch is NULL");
+    if (in->n == 0) return GF_OK;
+    if (!in->seq1 || !in->qual1 || !in->off1) return fail(GF_E_INVALID, "seq1/qual1/off1 must be set");
+    bool pe = in->seq2 != nullptr;
+    if (pe && (!in->qual2 || !in->off2)) return fail(GF_E_INVALID, "paired batch needs qual2 and off2");
+    return GF_OK;
+}
+
+/* Host batch: chunked double-buffered pipeline (H2D of chunk k+1 overlaps the kernels of chunk k). */
+int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_cap, uint64_t* n_out) {
+    if (!idx || !n_out) return fail(GF_E_INVALID, "NULL argument");
+    *n_out = 0;
+    int rc = validate_batch(in);
+    if (rc != GF_OK) return rc;
+    if (out_cap && !out) return fail(GF_E_INVALID, "out is NULL");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    GF_CUDA_TRY(cudaSetDevice(idx->device));
+    idx->stats = gf_map_stats{};
+    idx->stats.n_pairs = in->n;
+    idx->stats_pending = false;
+    if (in->n == 0) return GF_OK;
+    const bool pe = in->seq2 != nullptr;
+    const uint64_t n = in->n;
+    const uint64_t* off1 = in->off1;
+    const uint64_t* off2 = in->off2;
+    if (off1[n] < off1[0] || (pe && off2[n] < off2[0])) return fail(GF_E_INVALID, "offsets are not ascending");
+    const uint64_t total_bytes = (off1[n] - off1[0]) + (pe ? off2[n] - off2[0] : 0);
+    uint64_t n_chunks = std::max<uint64_t>(1, (2 * total_bytes + CHUNK_TARGET_BYTES - 1) / CHUNK_TARGET_BYTES);
+    n_chunks = std::min<uint64_t>(n_chunks, n);
+    const uint64_t per = (n + n_chunks - 1) / n_chunks;
+    n_chunks = (n + per - 1) / per;
+
+    const unsigned long long launches0 = idx->launches;
+    uint64_t total_out = 0;
+    bool panic = false;
+    GF_CUDA_TRY(cudaEventRecord(idx->ev_start, idx->stream));
+
+    auto issue = [&](uint64_t k) -> int {
+        GfStage& s = idx->stage[k & 1];
+        const uint64_t lo = k * per, hi = std::min(n, lo + per), cn = hi - lo;
+        const uint64_t b1 = off1[lo], e1 = off1[hi];
+        GF_CUDA_TRY(s.seq1.reserve(e1 - b1 + 16));
+        GF_CUDA_TRY(s.qual1.reserve(e1 - b1 + 16));
+        GF_CUDA_TRY(s.off1.reserve(sizeof(uint64_t) * (cn + 1)));
+        cudaStream_t cs = idx->copy_stream;
+        GF_CUDA_TRY(cudaMemcpyAsync(s.seq1.p, in->seq1 + b1, e1 - b1, cudaMemcpyHostToDevice, cs));
+        GF_CUDA_TRY(cudaMemcpyAsync(s.qual1.p, in->qual1 + b1, e1 - b1, cudaMemcpyHostToDevice, cs));
+        GF_CUDA_TRY(cudaMemcpyAsync(s.off1.p, off1 + lo, sizeof(uint64_t) * (cn + 1), cudaMemcpyHostToDevice, cs));
+        GfDevBatch db{};
+        db.n = cn;
+        db.seq1 = s.seq1.as<uint8_t>();
+        db.qual1 = s.qual1.as<uint8_t>();
+        db.off1 = s.off1.as<uint64_t>();
+        db.base1 = b1;
+        db.pair_base = lo;
+        db.max_len = in->max_len;
+        if (pe) {
+            const uint64_t b2 = off2[lo], e2 = off2[hi];
+            GF_CUDA_TRY(s.seq2.reserve(e2 - b2 + 16));
+            GF_CUDA_TRY(s.qual2.reserve(e2 - b2 + 16));
+            GF_CUDA_TRY(s.off2.reserve(sizeof(uint64_t) * (cn + 1)));
+            GF_CUDA_TRY(cudaMemcpyAsync(s.seq2.p, in->seq2 + b2, e2 - b2, cudaMemcpyHostToDevice, cs));
+            GF_CUDA_TRY(cudaMemcpyAsync(s.qual2.p, in->qual2 + b2, e2 - b2, cudaMemcpyHostToDevice, cs));
+            GF_CUDA_TRY(cudaMemcpyAsync(s.off2.p, off2 + lo, sizeof(uint64_t) * (cn + 1), cudaMemcpyHostToDevice, cs));
+            db.seq2 = s.seq2.as<uint8_t>();
+            db.qual2 = s.qual2.as<uint8_t>();
+            db.off2 = s.off2.as<uint64_t>();
+            db.base2 = b2;
+        }
+        GF_CUDA_TRY(cudaEventRecord(s.copied, cs));
+        s.n = cn;
+        s.pair_base = lo;
+        s.out_cap = (pe ? 2 : 1) * cn;
+        GF_CUDA_TRY(s.out.reserve(sizeof(gf_match) * s.out_cap));
+        GF_CUDA_TRY(s.nout.reserve(sizeof(unsigned long long)));
+        GF_CUDA_TRY(cudaStreamWaitEvent(idx->stream, s.copied, 0));
+        int r = gf_map_device_batch(idx, db, s.out.as<gf_match>(), s.out_cap, s.nout.as<unsigned long long>(),
+                                    idx->stream, false);
+        if (r != GF_OK) return r;
+        GfHostSlot* h = &idx->h_slots[k & 1];
+        GF_CUDA_TRY(cudaMemcpyAsync(&h->counters, idx->ws_counters.p, sizeof(GfMapCounters), cudaMemcpyDeviceToHost,
+                                    idx->stream));
+        GF_CUDA_TRY(cudaMemcpyAsync(&h->n_out, s.nout.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                    idx->stream));
+        GF_CUDA_TRY(cudaEventRecord(s.done, idx->stream));
+        return GF_OK;
+    };
+    auto collect = [&](uint64_t k) -> int {
+        GfStage& s = idx->stage[k & 1];
+        GfHostSlot* h = &idx->h_slots[k & 1];
+        GF_CUDA_TRY(cudaEventSynchronize(s.done));
+        int r = check_flags(*h);
+        if (r != GF_OK) return r;
+        accumulate(idx->stats, *h);
+        if (h->counters.n_ref_panic) panic = true;
+        const uint64_t cnt = h->n_out; /* <= s.out_cap by construction */
+        if (cnt && total_out + cnt <= out_cap)
+            GF_CUDA_TRY(cudaMemcpy(out + total_out, s.out.p, sizeof(gf_match) * cnt, cudaMemcpyDeviceToHost));
+        total_out += cnt;
+        return GF_OK;
+    };
+
+    rc = issue(0);
+    for (uint64_t k = 0; rc == GF_OK && k < n_chunks; k++) {
+        if (k + 1 < n_chunks) rc = issue(k + 1);
+        if (rc == GF_OK) rc = collect(k);
+    }
+    if (rc != GF_OK) {
+        cudaStreamSynchronize(idx->stream);
+        cudaStreamSynchronize(idx->copy_stream);
+        return rc;
+    }
+    GF_CUDA_TRY(cudaEventRecord(idx->ev_end, idx->stream));
+    GF_CUDA_TRY(cudaEventSynchronize(idx->ev_end));
+    float ms = 0;
+    GF_CUDA_TRY(cudaEventElapsedTime(&ms, idx->ev_start, idx->ev_end));
+    idx->stats.ms_total = ms;
+    idx->stats.kernel_launches = idx->launches - launches0;
+    *n_out = total_out;
+    if (total_out > out_cap) return fail(GF_E_CAPACITY, "out_cap too small; *n_out holds the required count");
+    gf_sort_matches(out, total_out);
+    if (panic)
+        return fail(GF_E_REF_PANIC,
+                    "a candidate needs an edit distance over more than 640 columns: the reference panics here "
+                    "(src/core/edit_distance.rs:94-100,177-196); records were still written with exact distances");
+    return GF_OK;
+}
+
+int gf_map_pairs_device(gf_index* idx, const gf_batch* in_dev, gf_match* d_out, uint64_t out_cap, uint64_t* d_n_out,
+                        void* cuda_stream) {
+    if (!idx || !d_n_out) return fail(GF_E_INVALID, "NULL argument");
+    int rc = validate_batch(in_dev);
+    if (rc != GF_OK) return rc;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    GF_CUDA_TRY(cudaSetDevice(idx->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    GfDevBatch db{};
+    db.n = in_dev->n;
+    db.seq1 = in_dev->seq1;
+    db.qual1 = in_dev->qual1;
+    db.off1 = in_dev->off1;
+    db.seq2 = in_dev->seq2;
+    db.qual2 = in_dev->qual2;
+    db.off2 = in_dev->off2;
+    db.base1 = db.base2 = 0;
+    db.pair_base = 0;
+    db.max_len = in_dev->max_len;
+    const unsigned long long launches0 = idx->launches;
+    rc = gf_map_device_batch(idx, db, d_out, out_cap, (unsigned long long*)d_n_out, st, true);
+    if (rc != GF_OK) return rc;
+    GfHostSlot* h = &idx->h_slots[2];
+    GF_CUDA_TRY(cudaMemcpyAsync(&h->counters, idx->ws_counters.p, sizeof(GfMapCounters), cudaMemcpyDeviceToHost, st));
+    GF_CUDA_TRY(cudaMemcpyAsync(&h->n_out, d_n_out, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    GF_CUDA_TRY(cudaEventRecord(idx->ev_end, st));
+    idx->stats = gf_map_stats{};
+    idx->stats.n_pairs = in_dev->n;
+    idx->stats.kernel_launches = idx->launches - launches0;
+    idx->stats_pending = true;
+    return GF_OK;
+}
+
+int gf_get_map_stats(const gf_index* cidx, gf_map_stats* out) {
+    gf_index* idx = const_cast<gf_index*>(cidx);
+    if (!idx || !out) return fail(GF_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    int rc = GF_OK;
+    if (idx->stats_pending) {
+        GF_CUDA_TRY(cudaSetDevice(idx->device));
+        GF_CUDA_TRY(cudaEventSynchronize(idx->ev_end));
+        const GfHostSlot& h = idx->h_slots[2];
+        accumulate(idx->stats, h);
+        float a = 0, b = 0, c = 0;
+        GF_CUDA_TRY(cudaEventElapsedTime(&a, idx->ev_start, idx->ev_screen));
+        GF_CUDA_TRY(cudaEventElapsedTime(&b, idx->ev_screen, idx->ev_exact));
+        GF_CUDA_TRY(cudaEventElapsedTime(&c, idx->ev_start, idx->ev_end));
+        idx->stats.ms_screen = a;
+        idx->stats.ms_exact = b;
+        idx->stats.ms_total = c;
+        idx->stats.ms_merge = 0; /* fast_merge is fused into the screen kernel */
+        idx->stats_pending = false;
+        rc = check_flags(h);
+        if (rc == GF_OK && h.counters.n_ref_panic)
+            rc = fail(GF_E_REF_PANIC, "a candidate needs an edit distance over more than 640 columns (reference panics)");
+    }
+    *out = idx->stats;
+    return rc;
+}
+
+int gf_fast_merge(gf_index* idx, const gf_batch* in, gf_merge_info* out) {
+    if (!idx || !out) return fail(GF_E_INVALID, "NULL argument");
+    int rc = validate_batch(in);
+    if (rc != GF_OK) return rc;
+    if (in->n == 0) return GF_OK;
+    if (!in->seq2) return fail(GF_E_INVALID, "gf_fast_merge needs a paired batch");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    GF_CUDA_TRY(cudaSetDevice(idx->device));
+    const uint64_t n = in->n;
+    const uint64_t b1 = in->off1[0], e1 = in->off1[n], b2 = in->off2[0], e2 = in->off2[n];
+    GfStage& s = idx->stage[0];
+    GF_CUDA_TRY(s.seq1.reserve(e1 - b1 + 16));
+    GF_CUDA_TRY(s.qual1.reserve(e1 - b1 + 16));
+    GF_CUDA_TRY(s.off1.reserve(sizeof(uint64_t) * (n + 1)));
+    GF_CUDA_TRY(s.seq2.reserve(e2 - b2 + 16));
+    GF_CUDA_TRY(s.qual2.reserve(e2 - b2 + 16));
+    GF_CUDA_TRY(s.off2.reserve(sizeof(uint64_t) * (n + 1)));
+    GF_CUDA_TRY(s.out.reserve(sizeof(gf_merge_info) * n));
+    cudaStream_t st = idx->stream;
+    GF_CUDA_TRY(cudaMemcpyAsync(s.seq1.p, in->seq1 + b1, e1 - b1, cudaMemcpyHostToDevice, st));
+    GF_CUDA_TRY(cudaMemcpyAsync(s.qual1.p, in->qual1 + b1, e1 - b1, cudaMemcpyHostToDevice, st));
+    GF_CUDA_TRY(cudaMemcpyAsync(s.off1.p, in->off1, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, st));
+    GF_CUDA_TRY(cudaMemcpyAsync(s.seq2.p, in->seq2 + b2, e2 - b2, cudaMemcpyHostToDevice, st));
+    GF_CUDA_TRY(cudaMemcpyAsync(s.qual2.p, in->qual2 + b2, e2 - b2, cudaMemcpyHostToDevice, st));
+    GF_CUDA_TRY(cudaMemcpyAsync(s.off2.p, in->off2, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, st));
+    GfDevBatch db{};
+    db.n = n;
+    db.seq1 = s.seq1.as<uint8_t>();
+    db.qual1 = s.qual1.as<uint8_t>();
+    db.off1 = s.off1.as<uint64_t>();
+    db.seq2 = s.seq2.as<uint8_t>();
+    db.qual2 = s.qual2.as<uint8_t>();
+    db.off2 = s.off2.as<uint64_t>();
+    db.base1 = b1;
+    db.base2 = b2;
+    rc = gf_fast_merge_device(idx, db, s.out.as<gf_merge_info>(), st);
+    if (rc != GF_OK) return rc;
+    GF_CUDA_TRY(cudaMemcpyAsync(out, s.out.p, sizeof(gf_merge_info) * n, cudaMemcpyDeviceToHost, st));
+    GfHostSlot* h = &idx->h_slots[0];
+    GF_CUDA_TRY(cudaMemcpyAsync(&h->counters, idx->ws_counters.p, sizeof(GfMapCounters), cudaMemcpyDeviceToHost, st));
+    GF_CUDA_TRY(cudaStreamSynchronize(st));
+    return check_flags(*h);
+}
+
+} /* extern "C" */

@@ -1,0 +1,167 @@
+/*
+ * gf_device.cuh — device-side data layout and helpers shared by the index-build and mapping kernels.
+ *
+ * Index layout in HBM (replaces Indexer::{m_kmer_pos, m_dupe_list, m_bloom_filter},
+ * /root/reference/src/core/indexer.rs:74-76):
+ *
+ *   table     open-addressed hash, buckets of 4 slots x {u32 key, u32 val} = 32 B = one HBM/L2 sector.
+ *             home bucket = (key * 0x9E3779B1) >> (32 - bucket_bits); overflow goes to the next bucket.
+ *             A probe that finds an EMPTY slot in a bucket stops there (no deletions ever happen).
+ *   key       "plane form" of the reference's 16-mer code (A=0 T=1 C=2 G=3, indexer.rs:889-900):
+ *             low 16 bits = the low code bit of base j at bit j, high 16 bits = the high code bit.  It is a
+ *             bijection of the reference's 32-bit code (the hash only needs membership/values).
+ *   val       [31:30] kind  0 unique  : [29] strand (1 = reverse-complement site) [28:0] goff
+ *                           1 NORMAL  : [29:3] offset into `dupes`, [2:0] number of sites (2..threshold)
+ *                           2 HIGH    : no payload (DUPE_HIGH_LEVEL, common.rs:32)
+ *                           3 EMPTY   : 0xFFFFFFFF
+ *   site      strand<<29 | goff, goff = gene_start[contig] + |position| into the padded gene arena.
+ *             A reverse-strand site has position = -(forward coordinate of the k-mer's LAST base)
+ *             (index_contig(rc, start = 1-len), indexer.rs:167-168,194-197).
+ *   genes     upper-cased ASCII, genes laid out with >= GF_GENE_PAD bytes between them so that
+ *             "goff -/+ read offset" diagonals of different genes can never collide.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define GF_GENE_PAD 2304u           /* > GF_MAX_SEQ_LEN */
+#define GF_EMPTY_VAL 0xFFFFFFFFu
+#define GF_HASH_MULT 0x9E3779B1u
+#define GF_KIND_UNIQUE 0u
+#define GF_KIND_NORMAL 1u
+#define GF_KIND_HIGH 2u
+#define GF_SITE_STRAND (1u << 29)
+#define GF_SITE_GOFF_MASK ((1u << 29) - 1u)
+#define GF_MAX_GOFF (1u << 29)
+#define GF_MAX_DUPES 7              /* count field is 3 bits */
+
+struct GfDevIndex {
+    const uint4* table;         /* 2 x uint4 per bucket */
+    const uint32_t* dupes;      /* site codes of NORMAL keys */
+    const uint8_t* gene_ascii;  /* padded arena, indexed by goff */
+    const uint32_t* gene_start; /* goff of base 0 of each gene [n_genes] (ascending) */
+    const uint32_t* gene_len;   /* [n_genes] */
+    const uint8_t* gene_rev;    /* Gene::is_reversed() per gene */
+    uint32_t n_genes;
+    uint32_t max_sites;         /* most sites a NORMAL key holds = max(skip_key_dup_threshold, 2) */
+    uint32_t bucket_shift;      /* 32 - bucket_bits */
+    uint32_t bucket_mask;
+    int32_t major_req, minor_req, mismatch_thr; /* gf_params */
+};
+
+/* base classification -------------------------------------------------------------------- */
+/* upper-case A,C,G,T only (make_kmer_bytes, indexer.rs:888-904: anything else invalidates the k-mer) */
+__device__ __forceinline__ bool gf_is_acgt_upper(uint32_t c) {
+    /* bit (c-64) of {A=1, C=3, G=7, T=20} */
+    return ((c & 0xE0u) == 0x40u) && ((0x0010008Au >> (c & 31u)) & 1u);
+}
+/* code bits for an upper-case ACGT char: A=0 T=1 C=2 G=3  ->  lo = bit 2 of c, hi = bit 1 of c */
+__device__ __forceinline__ uint32_t gf_code_lo(uint32_t c) { return (c >> 2) & 1u; }
+__device__ __forceinline__ uint32_t gf_code_hi(uint32_t c) { return (c >> 1) & 1u; }
+
+/* get_complement_base, src/core/sequence.rs:52-60 (case-insensitive, everything else -> 'N') */
+__device__ __forceinline__ uint8_t gf_complement_ascii(uint8_t b) {
+    switch (b) {
+        case 'A': case 'a': return 'T';
+        case 'T': case 't': return 'A';
+        case 'C': case 'c': return 'G';
+        case 'G': case 'g': return 'C';
+        default: return 'N';
+    }
+}
+
+/* 16-mer starting at s (ASCII) -> plane-form key; returns false when any base is not upper-case ACGT */
+__device__ __forceinline__ bool gf_kmer_from_ascii(const uint8_t* s, uint32_t* key) {
+    uint32_t lo = 0, hi = 0;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        uint32_t c = s[j];
+        ok = ok && gf_is_acgt_upper(c);
+        lo |= gf_code_lo(c) << j;
+        hi |= gf_code_hi(c) << j;
+    }
+    *key = (hi << 16) | lo;
+    return ok;
+}
+/* key of the reverse complement of the same window: base k of rc = complement(base 15-k); complement = code ^ 1 */
+__device__ __forceinline__ uint32_t gf_key_revcomp(uint32_t key) {
+    uint32_t lo = key & 0xFFFFu, hi = key >> 16;
+    lo = (__brev(lo) >> 16) ^ 0xFFFFu;
+    hi = __brev(hi) >> 16;
+    return (hi << 16) | lo;
+}
+/* reference code (first base in the top bits, indexer.rs:852-913) -> plane-form key */
+__device__ __forceinline__ uint32_t gf_key_from_refcode(uint32_t code) {
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        uint32_t c = (code >> (30 - 2 * j)) & 3u;
+        lo |= (c & 1u) << j;
+        hi |= (c >> 1) << j;
+    }
+    return (hi << 16) | lo;
+}
+
+/* table probe ------------------------------------------------------------------------------ */
+__device__ __forceinline__ uint32_t gf_home_bucket(uint32_t key, uint32_t shift) { return (key * GF_HASH_MULT) >> shift; }
+
+/* 32-byte (one sector) read-only bucket load */
+__device__ __forceinline__ void gf_load_bucket(const uint4* table, uint32_t b, uint4& a, uint4& c) {
+    const uint4* p = table + 2ull * b;
+    a = __ldg(p);
+    c = __ldg(p + 1);
+}
+/* match `key` inside a loaded bucket: returns val, or GF_EMPTY_VAL with *stop telling whether the probe ends */
+__device__ __forceinline__ uint32_t gf_match_bucket(const uint4& a, const uint4& c, uint32_t key, bool* stop) {
+    uint32_t v = GF_EMPTY_VAL;
+    if (a.x == key && a.y != GF_EMPTY_VAL) v = a.y;
+    if (a.z == key && a.w != GF_EMPTY_VAL) v = a.w;
+    if (c.x == key && c.y != GF_EMPTY_VAL) v = c.y;
+    if (c.z == key && c.w != GF_EMPTY_VAL) v = c.w;
+    *stop = (v != GF_EMPTY_VAL) || a.y == GF_EMPTY_VAL || a.w == GF_EMPTY_VAL || c.y == GF_EMPTY_VAL ||
+            c.w == GF_EMPTY_VAL;
+    return v;
+}
+/* full lookup: val of `key`, GF_EMPTY_VAL when absent */
+__device__ __forceinline__ uint32_t gf_table_find(const GfDevIndex& ix, uint32_t key) {
+    uint32_t b = gf_home_bucket(key, ix.bucket_shift);
+    for (;;) {
+        uint4 a, c;
+        gf_load_bucket(ix.table, b, a, c);
+        bool stop;
+        uint32_t v = gf_match_bucket(a, c, key, &stop);
+        if (stop) return v;
+        b = (b + 1) & ix.bucket_mask;
+    }
+}
+
+/* site decoding ---------------------------------------------------------------------------- */
+/* goff -> contig by binary search over gene_start (ascending) */
+__device__ __forceinline__ uint32_t gf_contig_of(const GfDevIndex& ix, uint32_t goff) {
+    uint32_t lo = 0, hi = ix.n_genes;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(ix.gene_start + mid) <= goff) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+/* site -> GenePos (contig, position) exactly as the reference stores it */
+__device__ __forceinline__ void gf_site_decode(const GfDevIndex& ix, uint32_t site, int32_t* contig, int32_t* position) {
+    uint32_t goff = site & GF_SITE_GOFF_MASK;
+    uint32_t c = gf_contig_of(ix, goff);
+    int32_t p = (int32_t)(goff - __ldg(ix.gene_start + c));
+    *contig = (int32_t)c;
+    *position = (site & GF_SITE_STRAND) ? -p : p;
+}
+/* gp_to_i64, src/core/indexer.rs:697-706 */
+__device__ __forceinline__ long long gf_gp_pack(int32_t contig, int32_t position) {
+    return (long long)(((unsigned long long)(long long)(int16_t)contig << 32) | (unsigned long long)(uint32_t)position);
+}
+
+__device__ __forceinline__ uint32_t gf_lane() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t gf_lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}

@@ -1,0 +1,113 @@
+/* gf_internal.h — host-side handle and helpers shared by the .cu translation units (not part of the ABI). */
+#pragma once
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/genefuse_gpu.h"
+#include "gf_device.cuh"
+
+void gf_set_error(const std::string& msg);
+
+#define GF_CUDA_TRY(expr)                                                                              \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            gf_set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                         ":" + std::to_string(__LINE__) + ")");                                        \
+            return GF_E_CUDA;                                                                          \
+        }                                                                                              \
+    } while (0)
+
+/* grow-only device buffer */
+struct GfBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return (T*)p; }
+};
+
+/* device-side counters of one mapping call (single 128-byte block, zeroed per call) */
+struct GfMapCounters {
+    unsigned long long n_sequences;   /* sequences screened */
+    unsigned long long n_probes;      /* pass-1 probes issued by the screen */
+    unsigned long long seq_bytes;     /* bytes of screened sequences */
+    unsigned long long n_merged;      /* pairs merged */
+    unsigned int n_survivors;         /* entries appended to the survivor list */
+    unsigned int n_candidates;        /* candidates appended by the exact kernel */
+    unsigned int n_ref_panic;         /* edit distances beyond the reference's 640-column limit */
+    unsigned int error_flags;         /* bit 0: a read is longer than the kernel capacity; bit 1: survivor list overflow */
+    unsigned long long pad[9];
+};
+
+struct GfStage { /* one in-flight chunk of a host batch */
+    GfBuf seq1, qual1, off1, seq2, qual2, off2, out, nout;
+    cudaEvent_t copied = nullptr, done = nullptr;
+    uint64_t n = 0, pair_base = 0, out_cap = 0;
+};
+struct GfHostSlot { /* pinned host memory the device writes results of one call/chunk into */
+    GfMapCounters counters;
+    unsigned long long n_out;
+    unsigned long long pad[15];
+};
+
+struct gf_index {
+    int device = 0;
+    gf_params params{};
+    GfDevIndex dev{};
+    gf_index_info info{};
+    uint32_t n_genes = 0;
+    std::vector<uint32_t> gene_start, gene_len;
+
+    void *d_table = nullptr, *d_dupes = nullptr, *d_gene_ascii = nullptr, *d_gene_start = nullptr,
+         *d_gene_len = nullptr, *d_gene_rev = nullptr;
+
+    std::mutex mu; /* serialises calls on one handle */
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_screen = nullptr, ev_exact = nullptr, ev_end = nullptr;
+    bool ev_valid = false;
+
+    /* mapping workspace (grow-only) */
+    GfBuf ws_survivors, ws_counters, ws_gtbl;
+    GfStage stage[2];
+    GfHostSlot* h_slots = nullptr; /* [3]: two pipeline stages + the device-batch path */
+    bool stats_pending = false;    /* h_slots[2] is being written by an unsynchronised device-batch call */
+    uint64_t pending_pairs = 0;
+    gf_map_stats stats{};
+    unsigned long long launches = 0;
+    int sm_count = 148;
+};
+
+/* gf_index.cu */
+int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_genes);
+int gf_lookup_device(gf_index* idx, const uint32_t* kmers, uint64_t n, gf_lookup* out);
+
+/* gf_map.cu */
+struct GfDevBatch {
+    uint64_t n;
+    const uint8_t *seq1, *qual1, *seq2, *qual2;
+    const uint64_t *off1, *off2;
+    uint64_t base1, base2;   /* value subtracted from every offset (chunked host batches) */
+    uint64_t pair_base;      /* added to the local pair index in emitted records */
+    uint32_t max_len;        /* upper bound of any read length (selects the kernel capacity) */
+};
+int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uint64_t out_cap,
+                        unsigned long long* d_n_out, cudaStream_t stream, bool record_events);
+int gf_fast_merge_device(gf_index* idx, const GfDevBatch& b, gf_merge_info* d_out, cudaStream_t stream);

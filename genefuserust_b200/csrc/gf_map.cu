@@ -1,0 +1,937 @@
+/*
+ * gf_map.cu — per-read fusion matching on the GPU.
+ *
+ * Replaces, for a whole batch of read pairs (paths relative to /root/reference):
+ *   PairEndScanner::scan_pair_end   src/core/pescanner.rs:427-518   (per-pair policy, rc retry)
+ *   SingleEndScanner::scan_single_end src/core/sescanner.rs:183-205
+ *   SequenceReadPair::fast_merge    src/core/read.rs:313-440
+ *   FusionMapper::map_read / make_match / calc_distance / calc_ed   src/core/fusion_mapper.rs:93-251
+ *   Indexer::map_read / in_required_direction / segment_mask       src/core/indexer.rs:252-679
+ *   edit_distance                   src/core/edit_distance.rs:12-197
+ *
+ * Three kernels:
+ *   k_screen  (warp per pair, every pair)   fast_merge decision + a CONSERVATIVE form of map_read's first pass.
+ *             Reads are turned into bit-planes with __ballot_sync (1 bit per base and plane), the overlap test
+ *             of fast_merge is 32 bases per funnel-shift/xor/popc, 16-mers are cut out of the planes with funnel
+ *             shifts, and every even-offset 16-mer is probed in the HBM table (one 32-byte sector per probe).
+ *             A sequence is dropped only when it provably fails the vote gate of indexer.rs:353-360:
+ *                 T = sum of sites voted, c_d = votes of unique keys on one diagonal d (any d)
+ *                 count1 >= c_d and count1 + count2 <= T   =>   count2 <= T - c_d
+ *             so "T < ceil(major/2)+ceil(minor/2)  or  T - c_d < ceil(minor/2)" can never pass the gate.
+ *             Everything else goes to the survivor list.
+ *   k_exact   (warp per survivor)           the literal algorithm: exact vote table, top-2 in BTreeMap order,
+ *             gate, second pass mask, mismatch gate, segment_mask, direction gate, make_match, and the
+ *             reverse-complement retry of scan_pair_end.  Emits candidate records.
+ *   k_verify  (warp per candidate)          calc_distance/calc_ed: bit-parallel (Myers/Hyyro) Levenshtein with
+ *             one 64-column block per lane, carries passed lane to lane in a systolic pipeline; exact for any
+ *             distance, so the -1/-2 sentinels and the ">= 5" filter downstream see the reference's values.
+ */
+#include <climits>
+#include <cstdio>
+
+#include "gf_internal.h"
+
+namespace {
+
+#define FULL 0xFFFFFFFFu
+
+__device__ __forceinline__ uint32_t fsr(const uint32_t* plane, uint32_t bitpos) {
+    uint32_t w = bitpos >> 5;
+    return __funnelshift_r(plane[w], plane[w + 1], bitpos & 31u);
+}
+__device__ __forceinline__ uint32_t lowmask(int nbits) { /* nbits >= 1 */
+    return nbits >= 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* per-warp shared state of the screen kernel: bit-planes, one bit per base                          */
+template <int MAXW>
+struct ScreenWarp {
+    /* R1 forward */
+    uint32_t r1lo[MAXW + 1], r1hi[MAXW + 1], r1v[MAXW + 1], r1n[MAXW + 1], q1hi[MAXW + 1], q1lo[MAXW + 1];
+    /* reverse complement of R2 (read.rs:314) and its reversed qualities */
+    uint32_t c2lo[MAXW + 1], c2hi[MAXW + 1], c2v[MAXW + 1], c2n[MAXW + 1], q2hi[MAXW + 1], q2lo[MAXW + 1];
+    /* overlap-resolved rc(R2) (x*) and the sequence that is mapped (m*) */
+    uint32_t xlo[MAXW + 1], xhi[MAXW + 1], xv[MAXW + 1];
+    uint32_t mlo[2 * MAXW + 2], mhi[2 * MAXW + 2], mv[2 * MAXW + 2];
+};
+
+/* forward planes of a read: lo/hi code bits, valid (upper-case ACGT), N, quality >= '?' and <= '0' */
+__device__ __forceinline__ void planes_forward(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ qual,
+                                               int len, uint32_t* lo, uint32_t* hi, uint32_t* v, uint32_t* n,
+                                               uint32_t* qh, uint32_t* ql) {
+    const uint32_t lane = gf_lane();
+    const int nw = (len + 31) >> 5;
+    for (int r = 0; r < nw; r++) {
+        int p = 32 * r + (int)lane;
+        bool inb = p < len;
+        uint32_t c = inb ? __ldg(seq + p) : 0u;
+        bool valid = inb && gf_is_acgt_upper(c);
+        uint32_t blo = __ballot_sync(FULL, valid && gf_code_lo(c));
+        uint32_t bhi = __ballot_sync(FULL, valid && gf_code_hi(c));
+        uint32_t bv = __ballot_sync(FULL, valid);
+        uint32_t bn = 0, bqh = 0, bql = 0;
+        if (n) bn = __ballot_sync(FULL, inb && c == 'N');
+        if (qh) {
+            uint32_t q = inb ? __ldg(qual + p) : 0u;
+            bqh = __ballot_sync(FULL, inb && q >= '?');
+            bql = __ballot_sync(FULL, inb && q <= '0');
+        }
+        if (lane == 0) {
+            lo[r] = blo; hi[r] = bhi; v[r] = bv;
+            if (n) n[r] = bn;
+            if (qh) { qh[r] = bqh; ql[r] = bql; }
+        }
+    }
+    if (lane == 0) {
+        lo[nw] = 0; hi[nw] = 0; v[nw] = 0;
+        if (n) n[nw] = 0;
+        if (qh) { qh[nw] = 0; ql[nw] = 0; }
+    }
+}
+/* planes of reverse_complement(R2) (sequence.rs:22-60: case-insensitive, non-ACGT -> 'N') + reversed quals */
+__device__ __forceinline__ void planes_revcomp(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ qual,
+                                               int len, uint32_t* lo, uint32_t* hi, uint32_t* v, uint32_t* n,
+                                               uint32_t* qh, uint32_t* ql) {
+    const uint32_t lane = gf_lane();
+    const int nw = (len + 31) >> 5;
+    for (int r = 0; r < nw; r++) {
+        int p = 32 * r + (int)lane;
+        bool inb = p < len;
+        uint32_t c = inb ? __ldg(seq + (len - 1 - p)) : 0u;
+        uint32_t q = inb ? __ldg(qual + (len - 1 - p)) : 0u;
+        uint32_t cu = c & 0xDFu;
+        bool valid = inb && gf_is_acgt_upper(cu);
+        uint32_t blo = __ballot_sync(FULL, valid && !gf_code_lo(cu)); /* complement = code ^ 1 */
+        uint32_t bhi = __ballot_sync(FULL, valid && gf_code_hi(cu));
+        uint32_t bv = __ballot_sync(FULL, valid);
+        uint32_t bn = __ballot_sync(FULL, inb && !valid);
+        uint32_t bqh = __ballot_sync(FULL, inb && q >= '?');
+        uint32_t bql = __ballot_sync(FULL, inb && q <= '0');
+        if (lane == 0) { lo[r] = blo; hi[r] = bhi; v[r] = bv; n[r] = bn; qh[r] = bqh; ql[r] = bql; }
+    }
+    if (lane == 0) { lo[nw] = 0; hi[nw] = 0; v[nw] = 0; n[nw] = 0; qh[nw] = 0; ql[nw] = 0; }
+}
+
+/* fast_merge's inner loop for one overlap length (read.rs:339-367), 32 bases per step.
+ * passes <=> every mismatch is a "low quality diff" and there are at most 2 of them. */
+template <int MAXW>
+__device__ __forceinline__ bool overlap_ok(const ScreenWarp<MAXW>& S, int len1, int olen, int* diff) {
+    const int offset = len1 - olen;
+    int cnt = 0;
+    for (int k = 0; 32 * k < olen; k++) {
+        uint32_t bp = (uint32_t)(offset + 32 * k);
+        uint32_t alo = fsr(S.r1lo, bp), ahi = fsr(S.r1hi, bp), an = fsr(S.r1n, bp), av = fsr(S.r1v, bp);
+        uint32_t m = lowmask(olen - 32 * k);
+        uint32_t mism = ((alo ^ S.c2lo[k]) | (ahi ^ S.c2hi[k]) | (an ^ S.c2n[k]) | (~av & ~an)) & m;
+        if (mism) {
+            cnt += __popc(mism);
+            if (cnt > 2) return false;
+            uint32_t lowq = (fsr(S.q1hi, bp) & S.q2lo[k]) | (fsr(S.q1lo, bp) & S.q2hi[k]);
+            if (mism & ~lowq) return false;
+        }
+    }
+    *diff = cnt;
+    return true;
+}
+/* smallest passing overlap length >= 30 (read.rs:323-367); -1 when the pair does not merge */
+template <int MAXW>
+__device__ __forceinline__ int find_overlap(const ScreenWarp<MAXW>& S, int len1, int len2, int* diff_out) {
+    const int minlen = min(len1, len2);
+    const uint32_t lane = gf_lane();
+    for (int base = 30; base <= minlen; base += 32) {
+        int o = base + (int)lane;
+        int diff = 0;
+        bool ok = o <= minlen && overlap_ok<MAXW>(S, len1, o, &diff);
+        uint32_t b = __ballot_sync(FULL, ok);
+        if (b) {
+            int first = __ffs(b) - 1;
+            *diff_out = __shfl_sync(FULL, diff, first);
+            return base + first;
+        }
+    }
+    *diff_out = 0;
+    return -1;
+}
+/* merged sequence planes (read.rs:369-428): R1[..offset] ++ rc(R2), overlap mismatches take the R1 base
+ * iff q1 >= '?' and q2 <= '0'.  Returns the merged length. */
+template <int MAXW>
+__device__ __forceinline__ int build_merged(ScreenWarp<MAXW>& S, int len1, int len2, int olen) {
+    const uint32_t lane = gf_lane();
+    const int offset = len1 - olen;
+    const int nw2 = (len2 + 31) >> 5;
+    for (int k = (int)lane; k <= nw2; k += 32) {
+        uint32_t lo = S.c2lo[k], hi = S.c2hi[k], v = S.c2v[k];
+        if (k < nw2 && 32 * k < olen) {
+            uint32_t bp = (uint32_t)(offset + 32 * k);
+            uint32_t alo = fsr(S.r1lo, bp), ahi = fsr(S.r1hi, bp), an = fsr(S.r1n, bp), av = fsr(S.r1v, bp);
+            uint32_t m = lowmask(olen - 32 * k);
+            uint32_t mism = ((alo ^ lo) | (ahi ^ hi) | (an ^ S.c2n[k]) | (~av & ~an)) & m;
+            uint32_t sel = mism & fsr(S.q1hi, bp) & S.q2lo[k];
+            lo = (lo & ~sel) | (alo & sel);
+            hi = (hi & ~sel) | (ahi & sel);
+            v = (v & ~sel) | (av & sel);
+        }
+        S.xlo[k] = lo; S.xhi[k] = hi; S.xv[k] = v;
+    }
+    __syncwarp();
+    const int mlen = offset + len2;
+    const int nwm = (mlen + 31) >> 5;
+    for (int w = (int)lane; w <= nwm; w += 32) {
+        uint32_t lo = 0, hi = 0, v = 0;
+        if (w < nwm) {
+            int pos0 = 32 * w;
+            if (pos0 < offset) {
+                uint32_t m = lowmask(offset - pos0);
+                lo = S.r1lo[w] & m; hi = S.r1hi[w] & m; v = S.r1v[w] & m;
+            }
+            int j0 = pos0 - offset;
+            if (j0 > -32) {
+                if (j0 < 0) {
+                    lo |= S.xlo[0] << (-j0); hi |= S.xhi[0] << (-j0); v |= S.xv[0] << (-j0);
+                } else {
+                    lo |= fsr(S.xlo, (uint32_t)j0); hi |= fsr(S.xhi, (uint32_t)j0); v |= fsr(S.xv, (uint32_t)j0);
+                }
+            }
+        }
+        S.mlo[w] = lo; S.mhi[w] = hi; S.mv[w] = v;
+    }
+    __syncwarp();
+    return mlen;
+}
+
+struct ScreenParams {
+    GfDevIndex ix;
+    GfDevBatch b;
+    uint2* survivors;
+    uint32_t survivors_cap;
+    GfMapCounters* counters;
+    int need_total, need_minor;
+};
+
+/* Conservative first pass over one sequence given as planes.  Returns true when the sequence may pass the
+ * vote gate (indexer.rs:353-360) and must go through the exact kernel. */
+constexpr int SCREEN_ROUNDS = 4;
+__device__ __forceinline__ bool screen_sequence(const GfDevIndex& ix, const uint32_t* lo, const uint32_t* hi,
+                                                const uint32_t* v, int len, int need_total, int need_minor,
+                                                unsigned long long* probes) {
+    const uint32_t lane = gf_lane();
+    const int nprobe = len >= 16 ? ((len - 16) >> 1) + 1 : 0; /* indexer.rs:277, step 2 */
+    *probes += (unsigned long long)nprobe;
+    int T = 0, cntd = 0;
+    bool have_d = false;
+    uint32_t d = 0;
+    for (int base = 0; base < nprobe; base += 32 * SCREEN_ROUNDS) {
+        uint32_t key[SCREEN_ROUNDS], bkt[SCREEN_ROUNDS];
+        bool ok[SCREEN_ROUNDS];
+        uint4 a[SCREEN_ROUNDS], c[SCREEN_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < SCREEN_ROUNDS; r++) {
+            int j = base + 32 * r + (int)lane;
+            ok[r] = j < nprobe;
+            uint32_t i = ok[r] ? 2u * (uint32_t)j : 0u;
+            uint32_t vb = fsr(v, i) & 0xFFFFu;
+            ok[r] = ok[r] && vb == 0xFFFFu;
+            key[r] = ((fsr(hi, i) & 0xFFFFu) << 16) | (fsr(lo, i) & 0xFFFFu);
+            bkt[r] = gf_home_bucket(key[r], ix.bucket_shift);
+            if (ok[r]) gf_load_bucket(ix.table, bkt[r], a[r], c[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < SCREEN_ROUNDS; r++) {
+            if (base + 32 * r >= nprobe) break; /* warp-uniform */
+            uint32_t val = GF_EMPTY_VAL;
+            if (ok[r]) {
+                bool stop;
+                val = gf_match_bucket(a[r], c[r], key[r], &stop);
+                uint32_t bb = bkt[r];
+                while (!stop) {
+                    bb = (bb + 1) & ix.bucket_mask;
+                    uint4 a2, c2;
+                    gf_load_bucket(ix.table, bb, a2, c2);
+                    val = gf_match_bucket(a2, c2, key[r], &stop);
+                }
+            }
+            bool is_u = false;
+            uint32_t dcode = 0xC0000000u | lane; /* never equals a real diagonal code (< 2^30) */
+            if (val != GF_EMPTY_VAL) {
+                uint32_t kind = val >> 30;
+                if (kind == GF_KIND_UNIQUE) {
+                    uint32_t i = 2u * (uint32_t)(base + 32 * r + (int)lane);
+                    uint32_t goff = val & GF_SITE_GOFF_MASK;
+                    /* forward site: position - i ; reverse site: -(P) - i = -(P + i) */
+                    dcode = (val & GF_SITE_STRAND) ? (GF_SITE_STRAND | ((goff + i) & GF_SITE_GOFF_MASK))
+                                                   : ((goff - i) & GF_SITE_GOFF_MASK);
+                    is_u = true;
+                    T += 1;
+                } else if (kind == GF_KIND_NORMAL) {
+                    T += (int)(val & 7u);
+                }
+            }
+            if (!have_d) {
+                uint32_t um = __ballot_sync(FULL, is_u);
+                if (um) {
+                    uint32_t peers = __match_any_sync(FULL, dcode);
+                    uint32_t score = is_u ? (((uint32_t)__popc(peers) << 5) | (31u - lane)) : 0u;
+                    uint32_t best = __reduce_max_sync(FULL, score);
+                    d = __shfl_sync(FULL, dcode, 31 - (int)(best & 31u));
+                    have_d = true;
+                }
+            }
+            if (have_d) cntd += __popc(__ballot_sync(FULL, is_u && dcode == d));
+        }
+    }
+    T = (int)__reduce_add_sync(FULL, (unsigned)T);
+    return T >= need_total && (T - cntd) >= need_minor;
+}
+
+template <int MAXW, bool PAIRED>
+__global__ void __launch_bounds__(256, 3) k_screen(ScreenParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScreenWarp<MAXW>* Sall = reinterpret_cast<ScreenWarp<MAXW>*>(smem_raw);
+    const uint32_t lane = gf_lane();
+    const uint32_t warp_in_block = threadIdx.x >> 5;
+    ScreenWarp<MAXW>& S = Sall[warp_in_block];
+    const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    const uint64_t gwarp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+    const GfDevBatch& B = P.b;
+
+    unsigned long long c_seq = 0, c_probes = 0, c_bytes = 0, c_merged = 0;
+    uint32_t err = 0;
+
+    for (uint64_t p = gwarp; p < B.n; p += n_warps) {
+        const uint64_t o1 = __ldg(B.off1 + p), e1 = __ldg(B.off1 + p + 1);
+        const int len1 = (int)(e1 - o1);
+        const uint8_t* s1 = B.seq1 + (o1 - B.base1);
+        const uint8_t* q1 = B.qual1 + (o1 - B.base1);
+        int len2 = 0;
+        const uint8_t *s2 = nullptr, *q2 = nullptr;
+        if (PAIRED) {
+            const uint64_t o2 = __ldg(B.off2 + p), e2 = __ldg(B.off2 + p + 1);
+            len2 = (int)(e2 - o2);
+            s2 = B.seq2 + (o2 - B.base2);
+            q2 = B.qual2 + (o2 - B.base2);
+        }
+        if (len1 > 32 * MAXW || len2 > 32 * MAXW || len1 < 0 || len2 < 0) {
+            err |= 1u;
+            continue;
+        }
+        __syncwarp();
+        planes_forward(s1, q1, len1, S.r1lo, S.r1hi, S.r1v, S.r1n, S.q1hi, S.q1lo);
+        int olen = -1, diff = 0;
+        if (PAIRED) {
+            planes_revcomp(s2, q2, len2, S.c2lo, S.c2hi, S.c2v, S.c2n, S.q2hi, S.q2lo);
+            __syncwarp();
+            olen = find_overlap<MAXW>(S, len1, len2, &diff);
+        }
+        __syncwarp();
+        /* merged: only the merged read is searched (pescanner.rs:446-470); else R1, then R2 (:472-514) */
+        int mlen = 0;
+        if (olen >= 0) {
+            mlen = build_merged<MAXW>(S, len1, len2, olen);
+            c_merged++;
+        }
+        const int nseq = olen >= 0 ? 1 : (PAIRED ? 2 : 1);
+        for (int sq = 0; sq < nseq; sq++) {
+            const uint32_t *plo = S.mlo, *phi = S.mhi, *pv = S.mv;
+            int len = mlen;
+            uint32_t meta = 0u | ((uint32_t)max(olen, 0) << 2) | ((uint32_t)diff << 14);
+            if (olen < 0) {
+                if (sq == 0) {
+                    plo = S.r1lo; phi = S.r1hi; pv = S.r1v;
+                    len = len1;
+                    meta = 1u;
+                } else {
+                    __syncwarp();
+                    planes_forward(s2, nullptr, len2, S.mlo, S.mhi, S.mv, nullptr, nullptr, nullptr);
+                    __syncwarp();
+                    len = len2;
+                    meta = 2u;
+                }
+            }
+            c_seq++;
+            c_bytes += (unsigned long long)len;
+            bool sv = screen_sequence(P.ix, plo, phi, pv, len, P.need_total, P.need_minor, &c_probes);
+            if (sv && lane == 0) {
+                uint32_t slot = atomicAdd(&P.counters->n_survivors, 1u);
+                if (slot < P.survivors_cap) P.survivors[slot] = make_uint2((uint32_t)p, meta);
+                else err |= 2u;
+            }
+        }
+    }
+    if (lane == 0) {
+        if (c_seq) atomicAdd(&P.counters->n_sequences, c_seq);
+        if (c_probes) atomicAdd(&P.counters->n_probes, c_probes);
+        if (c_bytes) atomicAdd(&P.counters->seq_bytes, c_bytes);
+        if (c_merged) atomicAdd(&P.counters->n_merged, c_merged);
+    }
+    err = __reduce_or_sync(FULL, err);
+    if (err && lane == 0) atomicOr(&P.counters->error_flags, err);
+}
+
+/* parity hook: fast_merge only */
+template <int MAXW>
+__global__ void __launch_bounds__(256) k_merge_only(GfDevBatch B, gf_merge_info* __restrict__ out, GfMapCounters* counters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScreenWarp<MAXW>* Sall = reinterpret_cast<ScreenWarp<MAXW>*>(smem_raw);
+    const uint32_t lane = gf_lane();
+    ScreenWarp<MAXW>& S = Sall[threadIdx.x >> 5];
+    const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t p = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < B.n; p += n_warps) {
+        const uint64_t o1 = B.off1[p], o2 = B.off2[p];
+        const int len1 = (int)(B.off1[p + 1] - o1), len2 = (int)(B.off2[p + 1] - o2);
+        if (len1 > 32 * MAXW || len2 > 32 * MAXW) {
+            if (lane == 0) atomicOr(&counters->error_flags, 1u);
+            continue;
+        }
+        __syncwarp();
+        planes_forward(B.seq1 + (o1 - B.base1), B.qual1 + (o1 - B.base1), len1, S.r1lo, S.r1hi, S.r1v, S.r1n, S.q1hi, S.q1lo);
+        planes_revcomp(B.seq2 + (o2 - B.base2), B.qual2 + (o2 - B.base2), len2, S.c2lo, S.c2hi, S.c2v, S.c2n, S.q2hi, S.q2lo);
+        __syncwarp();
+        int diff = 0;
+        int olen = find_overlap<MAXW>(S, len1, len2, &diff);
+        if (lane == 0) {
+            gf_merge_info mi;
+            mi.merged = olen >= 0;
+            mi.olen = olen >= 0 ? olen : 0;
+            mi.diff = diff;
+            mi.merged_len = olen >= 0 ? len1 - olen + len2 : 0;
+            out[p] = mi;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* raw (ASCII) sequence reconstruction for the exact / verify kernels                                */
+
+/* Loads the sequence a survivor stands for into `seq` (shared memory), returns its length.
+ * source 0 = merged read (literal read.rs:369-428 given the overlap length), 1 = R1, 2 = R2. */
+__device__ int load_sequence(const GfDevBatch& B, uint32_t pair, uint32_t source, int olen, uint8_t* seq) {
+    const uint32_t lane = gf_lane();
+    const uint64_t o1 = B.off1[pair];
+    const int len1 = (int)(B.off1[pair + 1] - o1);
+    const uint8_t* s1 = B.seq1 + (o1 - B.base1);
+    int len;
+    if (source == 1) {
+        for (int j = (int)lane; j < len1; j += 32) seq[j] = s1[j];
+        len = len1;
+    } else {
+        const uint64_t o2 = B.off2[pair];
+        const int len2 = (int)(B.off2[pair + 1] - o2);
+        const uint8_t* s2 = B.seq2 + (o2 - B.base2);
+        if (source == 2) {
+            for (int j = (int)lane; j < len2; j += 32) seq[j] = s2[j];
+            len = len2;
+        } else {
+            const uint8_t* q1 = B.qual1 + (o1 - B.base1);
+            const uint8_t* q2 = B.qual2 + (o2 - B.base2);
+            const int offset = len1 - olen;
+            for (int j = (int)lane; j < offset; j += 32) seq[j] = s1[j];
+            for (int i = (int)lane; i < len2; i += 32) {
+                uint8_t c2 = gf_complement_ascii(s2[len2 - 1 - i]);
+                uint8_t ch = c2;
+                if (i < olen) {
+                    uint8_t c1 = s1[offset + i];
+                    if (c1 != c2 && q1[offset + i] >= '?' && q2[len2 - 1 - i] <= '0') ch = c1;
+                }
+                seq[offset + i] = ch;
+            }
+            len = offset + len2;
+        }
+    }
+    __syncwarp();
+    return len;
+}
+/* SequenceRead::reverse_complement (read.rs:243-261) in place */
+__device__ void revcomp_inplace(uint8_t* seq, int len) {
+    const uint32_t lane = gf_lane();
+    for (int j = (int)lane; 2 * j < len; j += 32) {
+        int k = len - 1 - j;
+        uint8_t a = seq[j], b = seq[k];
+        seq[j] = gf_complement_ascii(b);
+        if (k != j) seq[k] = gf_complement_ascii(a);
+    }
+    __syncwarp();
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* k_exact                                                                                           */
+constexpr int EX_SEQ_CAP = 2048 + 64;
+constexpr int EX_TBL_SMEM = 2048;       /* vote-table slots in shared memory */
+constexpr int EX_TBL_GLOBAL = 8192;     /* per-warp global fallback (long reads / many dupes) */
+constexpr int EX_WARPS = 2;
+constexpr long long EX_EMPTY_KEY = LLONG_MIN;
+
+struct ExactWarp {
+    long long tkeys[EX_TBL_SMEM];
+    int tcnt[EX_TBL_SMEM];
+    uint8_t seq[EX_SEQ_CAP];
+    uint8_t flag[EX_SEQ_CAP];
+    uint8_t mask[EX_SEQ_CAP];
+};
+
+struct ExactParams {
+    GfDevIndex ix;
+    GfDevBatch b;
+    const uint2* survivors;
+    uint32_t survivors_cap;
+    GfMapCounters* counters;
+    gf_match* out;
+    unsigned long long out_cap;
+    unsigned long long* n_out;
+    long long* gtbl_keys; /* [n_warps_total][EX_TBL_GLOBAL] */
+    int* gtbl_cnt;
+};
+
+struct Top2 { long long k1, k2; int c1, c2; };
+
+/* "better" in the order the reference's ascending BTreeMap scan with strict '>' produces
+ * (indexer.rs:336-346): higher count first, ties -> smaller key */
+__device__ __forceinline__ bool vote_better(int ca, long long ka, int cb, long long kb) {
+    return ca > cb || (ca == cb && ca > 0 && ka < kb);
+}
+__device__ __forceinline__ void vote_insert(long long* tk, int* tc, uint32_t tmask, long long g) {
+    if (g == 0) return; /* key 0 is the "no hit" bucket and is never a candidate (k != 0, indexer.rs:337) */
+    uint32_t h = (uint32_t)(((unsigned long long)g * 0x9E3779B97F4A7C15ull) >> 40) & tmask;
+    for (;;) {
+        long long old = (long long)atomicCAS((unsigned long long*)&tk[h], (unsigned long long)EX_EMPTY_KEY,
+                                             (unsigned long long)g);
+        if (old == EX_EMPTY_KEY || old == g) {
+            atomicAdd(&tc[h], 1);
+            return;
+        }
+        h = (h + 1) & tmask;
+    }
+}
+/* visit every (contig, position) the k-mer at seq[i..i+16) maps to */
+template <class F>
+__device__ __forceinline__ void for_each_site(const GfDevIndex& ix, const uint8_t* seq, int i, F f) {
+    uint32_t key;
+    if (!gf_kmer_from_ascii(seq + i, &key)) return;
+    uint32_t val = gf_table_find(ix, key);
+    if (val == GF_EMPTY_VAL) return;
+    uint32_t kind = val >> 30;
+    if (kind == GF_KIND_UNIQUE) {
+        int32_t c, p;
+        gf_site_decode(ix, val & 0x3FFFFFFFu, &c, &p);
+        f(c, p);
+    } else if (kind == GF_KIND_NORMAL) {
+        uint32_t cnt = val & 7u, off = (val >> 3) & 0x07FFFFFFu;
+        for (uint32_t j = 0; j < cnt; j++) {
+            int32_t c, p;
+            gf_site_decode(ix, __ldg(ix.dupes + off + j), &c, &p);
+            f(c, p);
+        }
+    }
+}
+
+struct SegResult { int n; int s0, e0, s1, e1; long long gp0, gp1; }; /* entries in TOP, SECOND order */
+
+/* Indexer::map_read (indexer.rs:252-538) on the ASCII sequence in W.seq.  All lanes return the same result. */
+__device__ SegResult exact_map_read(const GfDevIndex& ix, ExactWarp& W, int len, long long* gkeys, int* gcnt) {
+    const uint32_t lane = gf_lane();
+    SegResult R;
+    R.n = 0; R.s0 = R.e0 = R.s1 = R.e1 = 0; R.gp0 = R.gp1 = 0;
+    if (len < 16) return R;
+    const int nprobe = ((len - 16) >> 1) + 1;
+    long long* tk = W.tkeys;
+    int* tc = W.tcnt;
+    uint32_t tsize = EX_TBL_SMEM;
+    /* at most nprobe * max_sites distinct votes: shared-memory table while it stays <= 75% full */
+    if ((uint32_t)nprobe * ix.max_sites * 4u > 3u * EX_TBL_SMEM) { tk = gkeys; tc = gcnt; tsize = EX_TBL_GLOBAL; }
+    const uint32_t tmask = tsize - 1;
+    for (uint32_t s = lane; s < tsize; s += 32) { tk[s] = EX_EMPTY_KEY; tc[s] = 0; }
+    __syncwarp();
+    /* first pass: every 2nd offset votes for pack(contig, position - i)  (:277-321) */
+    for (int j = (int)lane; j < nprobe; j += 32) {
+        int i = 2 * j;
+        for_each_site(ix, W.seq, i, [&](int32_t c, int32_t p) { vote_insert(tk, tc, tmask, gf_gp_pack(c, p - i)); });
+    }
+    __syncwarp();
+    /* top-2 (:324-346) */
+    long long k1 = 0, k2 = 0;
+    int c1 = 0, c2 = 0;
+    for (uint32_t s = lane; s < tsize; s += 32) {
+        long long k = tk[s];
+        if (k == EX_EMPTY_KEY) continue;
+        int c = tc[s];
+        if (vote_better(c, k, c1, k1)) { k2 = k1; c2 = c1; k1 = k; c1 = c; }
+        else if (vote_better(c, k, c2, k2)) { k2 = k; c2 = c; }
+    }
+    long long bk = k1; int bc = c1;
+    for (int o = 16; o > 0; o >>= 1) {
+        long long ok_ = __shfl_xor_sync(FULL, bk, o);
+        int oc = __shfl_xor_sync(FULL, bc, o);
+        if (vote_better(oc, ok_, bc, bk)) { bk = ok_; bc = oc; }
+    }
+    long long sk = (k1 == bk && c1 == bc) ? k2 : k1;
+    int sc = (k1 == bk && c1 == bc) ? c2 : c1;
+    for (int o = 16; o > 0; o >>= 1) {
+        long long ok_ = __shfl_xor_sync(FULL, sk, o);
+        int oc = __shfl_xor_sync(FULL, sc, o);
+        if (vote_better(oc, ok_, sc, sk)) { sk = ok_; sc = oc; }
+    }
+    const long long gp1 = bc > 0 ? bk : 0, gp2 = sc > 0 ? sk : 0;
+    const int count1 = bc, count2 = sc;
+    if (count1 * 2 < ix.major_req || count2 * 2 < ix.minor_req) return R; /* :353-360 */
+
+    /* second pass: per-offset flag, then mask[p] = max over the 16 windows covering p  (:362-521, :716-732) */
+    const int nwin = len - 15;
+    for (int i = (int)lane; i < nwin; i += 32) {
+        int f = 0;
+        for_each_site(ix, W.seq, i, [&](int32_t c, int32_t p) {
+            long long g = gf_gp_pack(c, p - i);
+            long long d1 = g - gp1, d2 = g - gp2;
+            if (d1 < 0) d1 = -d1;
+            if (d2 < 0) d2 = -d2;
+            int ff = d1 <= 1 ? 3 : (d2 <= 1 ? 2 : (g == 0 ? 1 : 0));
+            f = max(f, ff);
+        });
+        W.flag[i] = (uint8_t)f;
+    }
+    __syncwarp();
+    int mism = 0;
+    for (int p = (int)lane; p < len; p += 32) {
+        int lo = max(0, p - 15), hi = min(p, nwin - 1);
+        int m = 0;
+        for (int i = lo; i <= hi; i++) m = max(m, (int)W.flag[i]);
+        W.mask[p] = (uint8_t)m;
+        if (m <= 1) mism++; /* MATCH_NONE or MATCH_UNKNOWN (:523-528) */
+    }
+    mism = (int)__reduce_add_sync(FULL, (unsigned)mism);
+    __syncwarp();
+    if (mism > ix.mismatch_thr) return R; /* :530-535 */
+
+    /* segment_mask (:616-679): every start s < len-1 with mask[s]==target is tried; the longest run wins,
+     * the first one on ties (strict '>'), and only if end-start > 20 */
+    for (int t = 0; t < 2; t++) {
+        const int target = t == 0 ? 3 : 2;
+        uint32_t best = 0;
+        for (int s = (int)lane; s < len - 1; s += 32) {
+            if (W.mask[s] != target) continue;
+            int end = s + 1, g = 0;
+            while (g < 10 && end + g < len) {
+                int m = W.mask[end + g];
+                if (m > target) break;
+                if (m == target) { end += g + 1; g = 0; continue; }
+                g++;
+            }
+            end -= 1;
+            uint32_t sc_ = ((uint32_t)(end - s) << 16) | (0xFFFFu - (uint32_t)s);
+            best = max(best, sc_);
+        }
+        best = __reduce_max_sync(FULL, best);
+        int seglen = (int)(best >> 16), s = (int)(0xFFFFu - (best & 0xFFFFu));
+        if (seglen > 20) {
+            if (R.n == 0) { R.s0 = s; R.e0 = s + seglen; R.gp0 = t == 0 ? gp1 : gp2; }
+            else { R.s1 = s; R.e1 = s + seglen; R.gp1 = t == 0 ? gp1 : gp2; }
+            R.n++;
+        }
+    }
+    return R;
+}
+
+/* i64_to_gp (indexer.rs:708-714) */
+__device__ __forceinline__ void gp_unpack(long long v, int32_t* contig, int32_t* position) {
+    *contig = (int32_t)(int16_t)(v >> 32);
+    *position = (int32_t)(uint32_t)(v & 0xFFFFFFFFll);
+}
+
+/* Indexer::in_required_direction (indexer.rs:541-608), left/right already ordered by seq_start */
+__device__ bool in_required_direction(const GfDevIndex& ix, int32_t lc, int32_t lp, int32_t rc, int32_t rp) {
+    if (lp > 0 && rp > 0) return true;
+    if (lp < 0 && rp < 0) return false;
+    bool lrev = ix.gene_rev[lc] != 0, rrev = ix.gene_rev[rc] != 0;
+    if (lrev && !rrev) return false;
+    if (!lrev && rrev) return true;
+    if (lc < rc) return true;
+    return false; /* :597-599 compares left with left -> never true */
+}
+
+__global__ void __launch_bounds__(EX_WARPS * 32) k_exact(ExactParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ExactWarp* Wall = reinterpret_cast<ExactWarp*>(smem_raw);
+    const uint32_t lane = gf_lane();
+    const uint32_t wib = threadIdx.x >> 5;
+    ExactWarp& W = Wall[wib];
+    const uint64_t gwarp = (uint64_t)blockIdx.x * EX_WARPS + wib;
+    const uint64_t n_warps = (uint64_t)gridDim.x * EX_WARPS;
+    long long* gkeys = P.gtbl_keys + gwarp * EX_TBL_GLOBAL;
+    int* gcnt = P.gtbl_cnt + gwarp * EX_TBL_GLOBAL;
+    const uint32_t n_surv = min(P.counters->n_survivors, P.survivors_cap);
+
+    for (uint64_t sidx = gwarp; sidx < n_surv; sidx += n_warps) {
+        const uint2 sv = P.survivors[sidx];
+        const uint32_t pair = sv.x, source = sv.y & 3u;
+        const int olen = (int)((sv.y >> 2) & 0xFFFu), diff = (int)((sv.y >> 14) & 3u);
+        __syncwarp();
+        int len = load_sequence(P.b, pair, source, olen, W.seq);
+        if (len + 16 > EX_SEQ_CAP) continue;
+        if (lane == 0) for (int k = 0; k < 16; k++) W.seq[len + k] = 0;
+        __syncwarp();
+        for (int attempt = 0; attempt < 2; attempt++) {
+            SegResult R = exact_map_read(P.ix, W, len, gkeys, gcnt);
+            if (R.n < 2) break; /* mapable = false (fusion_mapper.rs:107-113): no retry */
+            /* order by seq_start (fusion_mapper.rs:163-165 / indexer.rs:549-551) */
+            int ls = R.s0, le = R.e0, rs = R.s1, re = R.e1;
+            long long lg = R.gp0, rg = R.gp1;
+            if (ls > rs) { int t; t = ls; ls = rs; rs = t; t = le; le = re; re = t; long long tg = lg; lg = rg; rg = tg; }
+            int32_t lc, lp, rc, rp;
+            gp_unpack(lg, &lc, &lp);
+            gp_unpack(rg, &rc, &rp);
+            (void)re; (void)ls;
+            if (in_required_direction(P.ix, lc, lp, rc, rp)) {
+                /* make_match (fusion_mapper.rs:154-194) */
+                int read_break = (le + rs) / 2;
+                if (lane == 0) {
+                    unsigned long long slot = atomicAdd(P.n_out, 1ull);
+                    if (slot < P.out_cap) {
+                        gf_match m;
+                        m.pair_idx = P.b.pair_base + pair;
+                        m.read_break = read_break;
+                        m.l_pos = lp + read_break;
+                        m.r_pos = rp + read_break + 1;
+                        m.gap = rs - le - 1;
+                        m.l_dist = 0;
+                        m.r_dist = 0;
+                        m.seq_len = len;
+                        m.l_contig = (int16_t)lc;
+                        m.r_contig = (int16_t)rc;
+                        m.merge_olen = source == 0 ? (int16_t)olen : (int16_t)-1;
+                        m.merge_diff = source == 0 ? (int16_t)diff : (int16_t)0;
+                        m.source = (uint8_t)source;
+                        m.used_rc = (uint8_t)attempt;
+                        /* set_reversed(true) only on the R1/R2 retries (pescanner.rs:483,506), never merged (:455-469) */
+                        m.reversed = (uint8_t)(attempt == 1 && source != 0);
+                        m.pad = 0;
+                        P.out[slot] = m;
+                    }
+                }
+                break;
+            }
+            if (attempt == 0) {
+                revcomp_inplace(W.seq, len); /* "else if mapable" retry on the reverse complement */
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* k_verify: calc_distance / calc_ed / edit_distance                                                 */
+constexpr int VF_WARPS = 4;
+struct VerifyWarp { uint8_t seq[EX_SEQ_CAP]; };
+
+struct VerifyParams {
+    GfDevIndex ix;
+    GfDevBatch b;
+    GfMapCounters* counters;
+    gf_match* out;
+    unsigned long long out_cap;
+    const unsigned long long* n_out;
+};
+
+/* Levenshtein distance of pattern a[0..m) and text b[0..m) (equal lengths, m >= 1, m <= 2048), the
+ * recurrences of edit_distance_bpv (edit_distance.rs:12-92) with block r in lane r.  `a_rc`: the pattern is
+ * the reverse complement of part[0..m) (calc_ed start<0 branch, fusion_mapper.rs:237-246). */
+__device__ int warp_edit_distance(const uint8_t* part, int m, bool a_rc, const uint8_t* __restrict__ text) {
+    const uint32_t lane = gf_lane();
+    const int nb = ((m - 1) >> 6) + 1, tmax = nb - 1, tlen = m - 64 * tmax;
+    auto a_at = [&](int k) -> uint8_t { return a_rc ? gf_complement_ascii(part[m - 1 - k]) : part[k]; };
+    unsigned long long pA = 0, pC = 0, pG = 0, pT = 0, pN = 0, pO = 0; /* match masks of this lane's block */
+    if ((int)lane < nb) {
+        for (int j = 0; j < 64; j++) {
+            int k = 64 * (int)lane + j;
+            if (k >= m) break;
+            uint8_t ch = a_at(k);
+            unsigned long long bit = 1ull << j;
+            if (ch == 'A') pA |= bit; else if (ch == 'C') pC |= bit; else if (ch == 'G') pG |= bit;
+            else if (ch == 'T') pT |= bit; else if (ch == 'N') pN |= bit; else pO |= bit;
+        }
+    }
+    unsigned long long vp = 0, vn = 0;
+    if ((int)lane < tmax) vp = ~0ull;
+    else if ((int)lane == tmax) vp = tlen >= 64 ? ~0ull : ((1ull << tlen) - 1ull);
+    const unsigned long long top = 1ull << (tlen - 1), lmb = 1ull << 63;
+    int d = m;
+    uint32_t hp_out = 0, hn_out = 0;
+    const int steps = m + nb - 1;
+    for (int t = 0; t < steps; t++) {
+        uint32_t hp_in = __shfl_up_sync(FULL, hp_out, 1);
+        uint32_t hn_in = __shfl_up_sync(FULL, hn_out, 1);
+        int j = t - (int)lane;
+        if ((int)lane < nb && j >= 0 && j < m) {
+            uint8_t ch = __ldg(text + j);
+            unsigned long long x;
+            if (ch == 'A') x = pA; else if (ch == 'C') x = pC; else if (ch == 'G') x = pG;
+            else if (ch == 'T') x = pT; else if (ch == 'N') x = pN;
+            else {
+                x = 0;
+                if (pO) for (int q = 0; q < 64; q++) { int k = 64 * (int)lane + q; if (k < m && ((pO >> q) & 1ull) && a_at(k) == ch) x |= 1ull << q; }
+            }
+            if (lane > 0 && hn_in) x |= 1ull;
+            unsigned long long d0 = (((x & vp) + vp) ^ vp) | x | vn;
+            unsigned long long hp = vn | ~(d0 | vp);
+            unsigned long long hn = d0 & vp;
+            unsigned long long x2 = hp << 1;
+            if (lane == 0 || hp_in) x2 |= 1ull;
+            vp = (hn << 1) | ~(d0 | x2);
+            if (lane > 0 && hn_in) vp |= 1ull;
+            vn = d0 & x2;
+            hp_out = (hp & lmb) ? 1u : 0u;
+            hn_out = (hn & lmb) ? 1u : 0u;
+            if ((int)lane == tmax) {
+                if (hp & top) d++;
+                else if (hn & top) d--;
+            }
+        }
+    }
+    return __shfl_sync(FULL, d, tmax);
+}
+
+/* FusionMapper::calc_ed (fusion_mapper.rs:224-251) */
+__device__ int calc_ed(const GfDevIndex& ix, const uint8_t* part, int plen, int32_t contig, int32_t start, int32_t end,
+                       uint32_t* panic) {
+    if ((start >= 0 && end <= 0) || (start <= 0 && end >= 0)) return -1;
+    const int32_t glen = (int32_t)ix.gene_len[contig];
+    const int32_t as = start < 0 ? -start : start, ae = end < 0 ? -end : end;
+    if (as >= glen || ae >= glen) return -2;
+    bool rc = start < 0;
+    if (rc) { int32_t tmp = start; start = -end; end = -tmp; }
+    const int reflen = end - start + 1;
+    if (plen == 0) return reflen;      /* edit_distance: asize == 0 -> bsize */
+    if (reflen == 0) return plen;
+    /* plen == reflen by construction (calc_distance, fusion_mapper.rs:196-222) */
+    if (((plen - 1) >> 6) + 1 > 10) *panic = 1; /* the reference falls into its panicking DP branch (>640) */
+    return warp_edit_distance(part, plen, rc, ix.gene_ascii + ix.gene_start[contig] + start);
+}
+
+__global__ void __launch_bounds__(VF_WARPS * 32) k_verify(VerifyParams P) {
+    __shared__ VerifyWarp Wall[VF_WARPS];
+    const uint32_t lane = gf_lane();
+    const uint32_t wib = threadIdx.x >> 5;
+    VerifyWarp& W = Wall[wib];
+    const uint64_t n_warps = (uint64_t)gridDim.x * VF_WARPS;
+    unsigned long long n = *P.n_out;
+    if (n > P.out_cap) n = P.out_cap;
+    for (uint64_t ci = (uint64_t)blockIdx.x * VF_WARPS + wib; ci < n; ci += n_warps) {
+        gf_match m = P.out[ci];
+        __syncwarp();
+        int len = load_sequence(P.b, (uint32_t)(m.pair_idx - P.b.pair_base), m.source, m.merge_olen, W.seq);
+        if (m.used_rc) revcomp_inplace(W.seq, len);
+        const int rb = m.read_break;
+        const int left_len = rb + 1, right_len = len - (rb + 1);
+        uint32_t panic = 0;
+        int ld = calc_ed(P.ix, W.seq, left_len, m.l_contig, m.l_pos - left_len + 1, m.l_pos, &panic);
+        int rd = calc_ed(P.ix, W.seq + rb + 1, right_len, m.r_contig, m.r_pos, m.r_pos + right_len - 1, &panic);
+        if (lane == 0) {
+            P.out[ci].l_dist = ld;
+            P.out[ci].r_dist = rd;
+            if (panic) atomicAdd(&P.counters->n_ref_panic, 1u);
+        }
+    }
+}
+
+template <class K>
+cudaError_t set_smem(K kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+}  // namespace
+
+/* ================================================================================================== */
+int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uint64_t out_cap,
+                        unsigned long long* d_n_out, cudaStream_t st, bool record_events) {
+    const bool paired = b.seq2 != nullptr;
+    if (b.n > 0xFFFFFFFFull) {
+        gf_set_error("batch too large (n > 2^32-1 pairs): split it");
+        return GF_E_LIMIT;
+    }
+    /* workspace */
+    const uint64_t surv_cap64 = (paired ? 2 : 1) * b.n + 1;
+    const uint32_t surv_cap = (uint32_t)(surv_cap64 > 0xFFFFFFFFull ? 0xFFFFFFFFull : surv_cap64);
+    GF_CUDA_TRY(idx->ws_survivors.reserve(sizeof(uint2) * (size_t)surv_cap));
+    GF_CUDA_TRY(idx->ws_counters.reserve(sizeof(GfMapCounters)));
+    GfMapCounters* d_cnt = idx->ws_counters.as<GfMapCounters>();
+    GF_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(GfMapCounters), st));
+    GF_CUDA_TRY(cudaMemsetAsync(d_n_out, 0, sizeof(unsigned long long), st));
+    if (record_events) GF_CUDA_TRY(cudaEventRecord(idx->ev_start, st));
+
+    const int need_major = (idx->params.major_gene_key_requirement + 1) / 2;
+    const int need_minor = (idx->params.minor_gene_key_requirement + 1) / 2;
+    ScreenParams sp;
+    sp.ix = idx->dev;
+    sp.b = b;
+    sp.survivors = idx->ws_survivors.as<uint2>();
+    sp.survivors_cap = surv_cap;
+    sp.counters = d_cnt;
+    sp.need_total = need_major + need_minor;
+    sp.need_minor = need_minor;
+
+    if (b.n) {
+        const int threads = 256, warps = threads / 32;
+        const bool small = b.max_len != 0 && b.max_len <= 256;
+        const size_t smem = (small ? sizeof(ScreenWarp<8>) : sizeof(ScreenWarp<32>)) * warps;
+        const int blocks_per_sm = 3; /* 80 registers x 256 threads -> 3 resident blocks per SM */
+        uint64_t want = (b.n + warps - 1) / warps;
+        unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)idx->sm_count * blocks_per_sm);
+        if (small) {
+            if (paired) { GF_CUDA_TRY(set_smem(k_screen<8, true>, smem)); k_screen<8, true><<<grid, threads, smem, st>>>(sp); }
+            else { GF_CUDA_TRY(set_smem(k_screen<8, false>, smem)); k_screen<8, false><<<grid, threads, smem, st>>>(sp); }
+        } else {
+            if (paired) { GF_CUDA_TRY(set_smem(k_screen<32, true>, smem)); k_screen<32, true><<<grid, threads, smem, st>>>(sp); }
+            else { GF_CUDA_TRY(set_smem(k_screen<32, false>, smem)); k_screen<32, false><<<grid, threads, smem, st>>>(sp); }
+        }
+        GF_CUDA_TRY(cudaGetLastError());
+        idx->launches++;
+    }
+    if (record_events) GF_CUDA_TRY(cudaEventRecord(idx->ev_screen, st));
+
+    if (b.n) {
+        /* exact path over the (device-side) survivor count: fixed persistent grid, no host round trip */
+        const unsigned ex_grid = (unsigned)idx->sm_count * 3;
+        const size_t n_ex_warps = (size_t)ex_grid * EX_WARPS;
+        static_assert(sizeof(long long) == 8, "");
+        GfBuf& gt = idx->ws_gtbl; /* per-warp global vote tables (long reads only) */
+        GF_CUDA_TRY(gt.reserve(n_ex_warps * EX_TBL_GLOBAL * (sizeof(long long) + sizeof(int))));
+        ExactParams ep;
+        ep.ix = idx->dev;
+        ep.b = b;
+        ep.survivors = idx->ws_survivors.as<uint2>();
+        ep.survivors_cap = surv_cap;
+        ep.counters = d_cnt;
+        ep.out = d_out;
+        ep.out_cap = out_cap;
+        ep.n_out = d_n_out;
+        ep.gtbl_keys = gt.as<long long>();
+        ep.gtbl_cnt = (int*)(gt.as<long long>() + n_ex_warps * EX_TBL_GLOBAL);
+        const size_t ex_smem = sizeof(ExactWarp) * EX_WARPS;
+        GF_CUDA_TRY(set_smem(k_exact, ex_smem));
+        k_exact<<<ex_grid, EX_WARPS * 32, ex_smem, st>>>(ep);
+        GF_CUDA_TRY(cudaGetLastError());
+        VerifyParams vp;
+        vp.ix = idx->dev;
+        vp.b = b;
+        vp.counters = d_cnt;
+        vp.out = d_out;
+        vp.out_cap = out_cap;
+        vp.n_out = d_n_out;
+        k_verify<<<(unsigned)idx->sm_count * 2, VF_WARPS * 32, 0, st>>>(vp);
+        GF_CUDA_TRY(cudaGetLastError());
+        idx->launches += 2;
+    }
+    if (record_events) GF_CUDA_TRY(cudaEventRecord(idx->ev_exact, st));
+    return GF_OK;
+}
+
+int gf_fast_merge_device(gf_index* idx, const GfDevBatch& b, gf_merge_info* d_out, cudaStream_t st) {
+    if (!b.n) return GF_OK;
+    GF_CUDA_TRY(idx->ws_counters.reserve(sizeof(GfMapCounters)));
+    GF_CUDA_TRY(cudaMemsetAsync(idx->ws_counters.p, 0, sizeof(GfMapCounters), st));
+    const int threads = 256, warps = 8;
+    const size_t smem = sizeof(ScreenWarp<32>) * warps;
+    GF_CUDA_TRY(set_smem(k_merge_only<32>, smem));
+    unsigned grid = (unsigned)std::min<uint64_t>((b.n + warps - 1) / warps, (uint64_t)idx->sm_count * 4);
+    k_merge_only<32><<<grid, threads, smem, st>>>(b, d_out, idx->ws_counters.as<GfMapCounters>());
+    GF_CUDA_TRY(cudaGetLastError());
+    return GF_OK;
+}

@@ -1,0 +1,325 @@
+"""Host-side mirror of the reference's interface for the hot path, on top of the C ABI.
+
+Names follow /root/reference/src/core: Fusion::parse_csv (fusion.rs:23-91), FastaReader (fasta_reader.rs),
+FastqReader / FastqReaderPair (fastq_reader.rs:75-147), Indexer::make_index (indexer.rs:122-177),
+FusionMapper (fusion_mapper.rs:23-87, 253-275, 379-392), PairEndScanner::scan_pair_end (pescanner.rs:427-518),
+SingleEndScanner::scan_single_end (sescanner.rs:183-205).  Everything that computes runs in the CUDA library;
+this file only loads inputs, owns buffers and regroups records — there is no CPU fallback.
+"""
+import ctypes as C
+import gzip
+import os
+
+import numpy as np
+
+from ._abi import (GF_E_CAPACITY, GF_E_REF_PANIC, GF_OK, gf_index_info, gf_lookup, gf_map_stats, gf_match,
+                   gf_merge_info, gf_gene_span, gf_params, load_library)
+from .batch import ReadBatch
+
+
+class GeneFuseError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"genefuse_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _check(lib, rc, allow=()):
+    if rc != GF_OK and rc not in allow:
+        raise GeneFuseError(rc, lib.gf_last_error().decode(errors="replace"))
+    return rc
+
+
+# ---------------------------------------------------------------------------------------------- loaders
+class Gene:
+    """src/core/gene.rs: name, chr, [start, end), exons; reversed iff exon[0].start > exon[1].start (:98-107)."""
+
+    def __init__(self, name, chrom, start, end):
+        self.name, self.chr, self.start, self.end = name, chrom, start, end
+        self.exons = []
+        self.reversed = False
+
+    def add_exon(self, eid, start, end):
+        self.exons.append((eid, start, end))
+        if len(self.exons) > 1 and self.exons[0][1] > self.exons[1][1]:
+            self.reversed = True
+
+    def valid(self):
+        # gene.rs:40-42
+        return self.name != "invalid" and self.start != 0 and self.end != 0
+
+    def is_reversed(self):
+        return self.reversed
+
+
+class Fusion:
+    def __init__(self, gene):
+        self.gene = gene
+
+    def is_reversed(self):
+        return self.gene.reversed
+
+    @staticmethod
+    def parse_csv(path):
+        """fusion.rs:23-91: '>NAME,chr:start-end' gene lines, 'id,start,end' exon lines, '#' comments."""
+        fusions = []
+        cur = None
+        with open(path, "r") as f:
+            for raw in f:
+                line = raw.strip()
+                sp = line.split(",")
+                if len(sp) < 2 or sp[0].startswith("#"):
+                    continue
+                if sp[0].startswith(">"):
+                    if cur is not None and cur.valid():
+                        fusions.append(Fusion(cur))
+                    name = sp[0][1:].strip()
+                    chrom, rng = sp[1].split(":")
+                    a, b = rng.split("-")
+                    cur = Gene(name, chrom.strip(), int(a), int(b))
+                    continue
+                if len(sp) < 3 or cur is None:
+                    continue
+                cur.add_exon(int(sp[0]), int(sp[1]), int(sp[2]))
+        if cur is not None and cur.valid():
+            fusions.append(Fusion(cur))
+        return fusions
+
+
+def _open_maybe_gz(path):
+    return gzip.open(path, "rb") if path.endswith(".gz") else open(path, "rb")
+
+
+class FastaReader:
+    """fasta_reader.rs:121-201: name = header up to the first space or newline; everything after a space on
+    the header line is filtered into the sequence like any other line (:155-178); contigs sorted by name."""
+
+    def __init__(self, path):
+        self.m_fasta_file = path
+        self.m_all_contigs = {}
+
+    def read_all(self):
+        contigs = {}
+        with _open_maybe_gz(self.m_fasta_file) as f:
+            data = f.read()
+        for rec in data.split(b">")[1:]:
+            cut = len(rec)
+            for ch in (b"\n", b" "):
+                k = rec.find(ch)
+                if k >= 0:
+                    cut = min(cut, k)
+            name = rec[:cut].decode()
+            body = rec[cut:]
+            # the reference keeps every byte that is not whitespace/CR (:155-178)
+            seq = bytes(c for c in body if c not in b"\n\r \t")
+            contigs[name] = seq
+        self.m_all_contigs = dict(sorted(contigs.items()))
+        return self
+
+
+class FastqReader:
+    """fastq_reader.rs:75-147: four lines per record, one trailing '\\n' stripped (no '\\r' strip)."""
+
+    def __init__(self, path):
+        self.path = path
+
+    def read_all(self):
+        with _open_maybe_gz(self.path) as f:
+            lines = f.read().split(b"\n")
+        names, reads = [], []
+        for i in range(0, len(lines) - 3, 4):
+            if not lines[i]:
+                break
+            names.append(lines[i])
+            reads.append((lines[i + 1], lines[i + 3]))
+        return names, reads
+
+
+class FastqReaderPair:
+    def __init__(self, path1, path2):
+        self.left, self.right = FastqReader(path1), FastqReader(path2)
+
+    def read_all(self):
+        n1, r1 = self.left.read_all()
+        n2, r2 = self.right.read_all()
+        n = min(len(r1), len(r2))
+        return (n1[:n], n2[:n]), ReadBatch.from_reads(r1[:n], r2[:n])
+
+
+# ---------------------------------------------------------------------------------------------- index
+def resolve_gene_spans(reference, fusions):
+    """Indexer::make_index's host half (indexer.rs:136-159): chromosome-name resolution (exact, 'chr'+name,
+    name without 'chr'), slice contig[m_start..m_end], upper-case.  Unresolved -> empty gene that keeps its id."""
+    contigs = reference.m_all_contigs
+    spans = []
+    for fu in fusions:
+        g = fu.gene
+        chrom = g.chr
+        if chrom not in contigs:
+            if ("chr" + chrom) in contigs:
+                chrom = "chr" + chrom
+            elif chrom.replace("chr", "") in contigs:
+                chrom = chrom.replace("chr", "")
+            else:
+                spans.append((b"", g.reversed))
+                continue
+        seq = contigs[chrom]
+        if g.start > g.end or g.end > len(seq):
+            # the reference's `.get(start..end).unwrap()` panics here (indexer.rs:154-158)
+            raise GeneFuseError(-1, f"gene {g.name}: span {g.start}..{g.end} outside contig {chrom} (reference panics)")
+        spans.append((seq[g.start:g.end].upper(), g.reversed))
+    return spans
+
+
+class Indexer:
+    """Device index handle (replaces Indexer::{m_kmer_pos, m_dupe_list, m_bloom_filter})."""
+
+    def __init__(self, gene_spans, params=None, device=0):
+        self.lib = load_library()
+        self.params = params or gf_params.default()
+        self.device = device
+        self.m_fusion_seq = [s for s, _ in gene_spans]   # kept on the host like the reference (cluster_matches)
+        self.reversed = [bool(r) for _, r in gene_spans]
+        arr = (gf_gene_span * max(1, len(gene_spans)))()
+        keep = []
+        for i, (seq, rev) in enumerate(gene_spans):
+            buf = C.create_string_buffer(seq, len(seq)) if len(seq) else None
+            keep.append(buf)
+            arr[i].seq = C.cast(buf, C.c_void_p).value if buf is not None else None
+            arr[i].len = len(seq)
+            arr[i].reversed = 1 if rev else 0
+        h = C.c_void_p()
+        _check(self.lib, self.lib.gf_index_create(arr, len(gene_spans), C.byref(self.params), device, C.byref(h)))
+        self.h = h
+
+    @classmethod
+    def make_index(cls, reference, fusions, params=None, device=0):
+        return cls(resolve_gene_spans(reference, fusions), params, device)
+
+    def info(self):
+        out = gf_index_info()
+        _check(self.lib, self.lib.gf_index_get_info(self.h, C.byref(out)))
+        return out
+
+    def lookup(self, kmers):
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint32)
+        out = (gf_lookup * max(1, len(kmers)))()
+        _check(self.lib, self.lib.gf_index_lookup(self.h, kmers.ctypes.data, len(kmers), out))
+        return [(o.kind, o.n_sites, tuple((o.contig[j], o.position[j]) for j in range(o.n_sites)))
+                for o in out[:len(kmers)]]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gf_index_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------- mapper
+class FusionMapper:
+    """fusion_mapper.rs:23-87.  Owns the index and the n_genes^2 match buckets."""
+
+    def __init__(self, indexer, fusion_list=None):
+        self.m_indexer = indexer
+        self.lib = indexer.lib
+        self.fusion_list = fusion_list
+        self.n_genes = len(indexer.m_fusion_seq)
+        self.fusion_matches = {}   # bucket index -> [gf_match]; sparse form of the n_genes^2 Vec (:47-49)
+        self.last_rc = GF_OK
+
+    @classmethod
+    def from_ref_and_fusion_files(cls, ref_file, fusion_file, params=None, device=0):
+        fusions = Fusion.parse_csv(fusion_file)
+        ref = FastaReader(ref_file).read_all()
+        return cls(Indexer.make_index(ref, fusions, params, device), fusions)
+
+    @classmethod
+    def from_fasta_reader_and_fusion_files(cls, fasta_reader, fusion_file, params=None, device=0):
+        fusions = Fusion.parse_csv(fusion_file)
+        return cls(Indexer.make_index(fasta_reader, fusions, params, device), fusions)
+
+    @classmethod
+    def from_gene_spans(cls, gene_spans, params=None, device=0):
+        return cls(Indexer(gene_spans, params, device))
+
+    # -- the batch calls that replace the per-pack loops
+    def _map(self, batch, cap=None):
+        cap = cap or max(1024, (2 if batch.paired else 1) * batch.n // 8)
+        st = batch.as_struct()
+        while True:
+            out = (gf_match * cap)()
+            n = C.c_uint64(0)
+            rc = self.lib.gf_map_pairs(self.m_indexer.h, C.byref(st), out, cap, C.byref(n))
+            if rc == GF_E_CAPACITY:
+                cap = int(n.value)
+                continue
+            _check(self.lib, rc, allow=(GF_E_REF_PANIC,))
+            self.last_rc = rc
+            return [out[i] for i in range(n.value)]
+
+    def scan_pair_end(self, batch):
+        """PairEndScanner::scan_pair_end over a whole batch; records sorted by (pair_idx, source)."""
+        assert batch.paired
+        return self._map(batch)
+
+    def scan_single_end(self, batch):
+        assert not batch.paired
+        return self._map(batch)
+
+    def fast_merge(self, batch):
+        out = (gf_merge_info * max(1, batch.n))()
+        st = batch.as_struct()
+        _check(self.lib, self.lib.gf_fast_merge(self.m_indexer.h, C.byref(st), out))
+        return [(o.merged, o.olen, o.diff, o.merged_len) for o in out[:batch.n]]
+
+    def map_stats(self):
+        out = gf_map_stats()
+        _check(self.lib, self.lib.gf_get_map_stats(self.m_indexer.h, C.byref(out)), allow=(GF_E_REF_PANIC,))
+        return out
+
+    # -- fusion_mapper.rs:253-275 / 379-392
+    def add_match(self, m):
+        index = self.n_genes * m.r_contig + m.l_contig
+        self.fusion_matches.setdefault(index, []).append(m)
+
+    def sort_matches(self, read_name_of):
+        """sort_by(|a, b| b.partial_cmp(a)) with ReadMatch's order (read_match.rs:203-229): read_break desc,
+        read length asc, read name desc; stable.  `read_name_of(m)` supplies m_read.m_name."""
+        import functools
+
+        def cmp(a, b):
+            # partial_cmp(self=b, other=a): break asc on (b, a) -> desc on (a, b); len compared other-vs-self
+            if a.read_break != b.read_break:
+                return -1 if b.read_break < a.read_break else 1
+            if a.seq_len != b.seq_len:
+                return -1 if a.seq_len < b.seq_len else 1
+            na, nb = read_name_of(a), read_name_of(b)
+            if na != nb:
+                return -1 if nb < na else 1
+            return 0
+
+        for v in self.fusion_matches.values():
+            v.sort(key=functools.cmp_to_key(cmp))
+
+    def close(self):
+        self.m_indexer.close()
+
+
+class PairEndScanner:
+    """pescanner.rs: scan() = build mapper, map all pairs, push matches into the mapper's buckets."""
+
+    def __init__(self, fusion_file, ref_file, read1, read2, device=0):
+        self.fusion_file, self.ref_file, self.read1, self.read2, self.device = fusion_file, ref_file, read1, read2, device
+        self.mapper = None
+
+    def scan(self):
+        self.mapper = FusionMapper.from_ref_and_fusion_files(self.ref_file, self.fusion_file, device=self.device)
+        (names1, _names2), batch = FastqReaderPair(self.read1, self.read2).read_all()
+        matches = self.mapper.scan_pair_end(batch)
+        for m in matches:
+            self.mapper.add_match(m)
+        return matches

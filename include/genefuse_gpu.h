@@ -84,8 +84,12 @@ typedef struct gf_batch {
     const uint8_t* seq2;
     const uint8_t* qual2;
     const uint64_t* off2;
-    uint64_t bytes1; /* == off1[n] */
-    uint64_t bytes2; /* == off2[n] (0 for SE) */
+    uint64_t bytes1; /* == off1[n] - off1[0] */
+    uint64_t bytes2; /* == off2[n] - off2[0] (0 for SE) */
+    uint32_t max_len; /* hint: upper bound of any read's length in this batch, 0 = unknown.  Selects the
+                         kernel capacity (<= 256: 8-word bit-planes, else 32-word).  A read longer than the
+                         hint (or than 1024) makes the call fail with GF_E_INVALID; it is never truncated. */
+    uint32_t reserved;
 } gf_batch;
 
 /* One fusion match = the integer content of a ReadMatch
@@ -130,7 +134,7 @@ typedef struct gf_index_info {
 /* Result of a debug/parity lookup of one 16-mer (A=0,T=1,C=2,G=3, first base in
  * the top bits; src/core/indexer.rs:852-913). */
 typedef struct gf_lookup {
-    int32_t kind;            /* 0 absent-or-HIGH, 1 unique, 2 NORMAL dupe */
+    int32_t kind;            /* 0 absent, 1 unique, 2 NORMAL dupe (sites sorted by contig, position), 3 HIGH */
     int32_t n_sites;
     int16_t contig[8];
     int32_t position[8];
@@ -181,7 +185,10 @@ int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_
  * `d_out` / `d_n_out` are device pointers (capacity out_cap records / one
  * uint64).  Work is enqueued on `cuda_stream` (a cudaStream_t, NULL = legacy
  * default stream) and NOT synchronised: the caller owns the stream.  Records
- * are in arbitrary order here; gf_sort_matches orders a host copy. */
+ * are in arbitrary order here; gf_sort_matches orders a host copy.  *d_n_out
+ * may exceed out_cap (records beyond the capacity are counted, not written).
+ * Input errors detected on the device (a read longer than the capacity) are
+ * reported by the next gf_get_map_stats on the handle. */
 int gf_map_pairs_device(gf_index* idx, const gf_batch* in_dev, gf_match* d_out, uint64_t out_cap,
                         uint64_t* d_n_out, void* cuda_stream);
 void gf_sort_matches(gf_match* m, uint64_t n); /* by (pair_idx, source), host */

@@ -2,7 +2,7 @@
  * gf_oracle.h — C API of the CPU oracle.
  *
  * TEST INFRASTRUCTURE, NOT PRODUCT.  This is a literal CPU restatement of the
- * reference's per-read fusion-matching path (GeneFuseRust, src/core/*.rs — each
+ * reference's per-read fusion-matching path (GeneFuseRust, src/core/ — each
  * function in gf_oracle.cpp cites the lines it follows).  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load it, and only as the checker / the CPU baseline.  The product library

