@@ -3,6 +3,7 @@
  * No CPU fallback: every compute entry point needs a CUDA device and fails with GF_E_CUDA otherwise.
  */
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "gf_internal.h"
@@ -103,6 +104,17 @@ int gf_index_create(const gf_gene_span* genes, uint32_t n_genes, const gf_params
     if (ndev <= 0) return fail(GF_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(GF_E_INVALID, "device index out of range");
     GF_CUDA_TRY(cudaSetDevice(device));
+
+    /* Index probes are random 32-byte sectors.  The default L2 fetch granularity pulls the whole 128-byte line
+     * from HBM on a miss (ncu: 4 DRAM sectors per probe, profiles/r01_screen_v1_summary.md); ask for 32 bytes.
+     * It is a per-context performance hint only.  GF_L2_FETCH_GRANULARITY=0 leaves the limit untouched. */
+    {
+        size_t gran = 32;
+        if (const char* e = getenv("GF_L2_FETCH_GRANULARITY")) gran = (size_t)atoi(e);
+        if (gran == 32 || gran == 64 || gran == 128) {
+            if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) cudaGetLastError();
+        }
+    }
 
     gf_index* idx = new gf_index();
     idx->device = device;
