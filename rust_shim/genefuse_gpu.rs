@@ -1,0 +1,92 @@
+//! genefuse_gpu.rs — Rust FFI binding of include/genefuse_gpu.h.  SOURCE ONLY: this image has no cargo/rustc, so
+//! the file is shipped for a maintainer to drop into GeneFuseRust as `src/core/genefuse_gpu.rs`
+//! (add `pub(crate) mod genefuse_gpu;` to src/core/mod.rs and `println!("cargo:rustc-link-lib=genefuse_b200")`
+//! + a search path to build.rs).  It replaces two call sites and nothing else:
+//!   Indexer::make_index             src/core/indexer.rs:122-177      -> GpuIndex::build
+//!   PairEndScanner::scan_pair_end   src/core/pescanner.rs:427-518    -> GpuIndex::map_pairs
+//!   SingleEndScanner::scan_single_end src/core/sescanner.rs:183-205  -> GpuIndex::map_pairs (seq2 = null)
+#![allow(non_camel_case_types, dead_code)]
+use std::ffi::CStr;
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct gf_gene_span { pub seq: *const u8, pub len: u32, pub reversed: u8 }
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct gf_params {
+    pub skip_key_dup_threshold: i32,
+    pub major_gene_key_requirement: i32,
+    pub minor_gene_key_requirement: i32,
+    pub mismatch_threshold: i32,
+}
+
+#[repr(C)]
+pub struct gf_batch {
+    pub n: u64,
+    pub seq1: *const u8, pub qual1: *const u8, pub off1: *const u64,
+    pub seq2: *const u8, pub qual2: *const u8, pub off2: *const u64,
+    pub bytes1: u64, pub bytes2: u64,
+    pub max_len: u32, pub reserved: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default, Debug)]
+pub struct gf_match {
+    pub pair_idx: u64,
+    pub read_break: i32, pub l_pos: i32, pub r_pos: i32, pub gap: i32,
+    pub l_dist: i32, pub r_dist: i32, pub seq_len: i32,
+    pub l_contig: i16, pub r_contig: i16, pub merge_olen: i16, pub merge_diff: i16,
+    pub source: u8, pub used_rc: u8, pub reversed: u8, pub pad: u8,
+}
+
+#[repr(C)] pub struct gf_index { _private: [u8; 0] }
+
+extern "C" {
+    fn gf_last_error() -> *const c_char;
+    fn gf_index_create(genes: *const gf_gene_span, n_genes: u32, params: *const gf_params, device: c_int,
+                       out: *mut *mut gf_index) -> c_int;
+    fn gf_index_destroy(idx: *mut gf_index);
+    fn gf_map_pairs(idx: *mut gf_index, batch: *const gf_batch, out: *mut gf_match, out_cap: u64,
+                    n_out: *mut u64) -> c_int;
+}
+
+pub const GF_E_CAPACITY: c_int = -3;
+
+fn last_error() -> String {
+    unsafe { CStr::from_ptr(gf_last_error()).to_string_lossy().into_owned() }
+}
+
+/// Owns one device index (one per FusionMapper; list mode: one per CSV, handles are independent).
+pub struct GpuIndex { h: *mut gf_index }
+unsafe impl Send for GpuIndex {}
+unsafe impl Sync for GpuIndex {} // calls on one handle are serialised inside the library
+
+impl GpuIndex {
+    /// `genes[i]` = (upper-cased contig[m_start..m_end] or "" when the chromosome is unresolved, is_reversed),
+    /// i.e. exactly what Indexer::make_index computes at src/core/indexer.rs:136-159 before index_contig.
+    pub fn build(genes: &[(&[u8], bool)], params: gf_params, device: i32) -> Result<Self, String> {
+        let spans: Vec<gf_gene_span> = genes.iter()
+            .map(|(s, r)| gf_gene_span { seq: s.as_ptr(), len: s.len() as u32, reversed: *r as u8 }).collect();
+        let mut h: *mut gf_index = std::ptr::null_mut();
+        let rc = unsafe { gf_index_create(spans.as_ptr(), spans.len() as u32, &params, device, &mut h) };
+        if rc != 0 { return Err(last_error()); }
+        Ok(Self { h })
+    }
+
+    /// Maps a batch held in byte arenas (offsets have n+1 entries; seq and qual share them).
+    pub fn map_pairs(&self, batch: &gf_batch) -> Result<Vec<gf_match>, String> {
+        let mut cap = (batch.n as usize / 8).max(1024);
+        loop {
+            let mut out = vec![gf_match::default(); cap];
+            let mut n: u64 = 0;
+            let rc = unsafe { gf_map_pairs(self.h, batch, out.as_mut_ptr(), cap as u64, &mut n) };
+            if rc == GF_E_CAPACITY { cap = n as usize; continue; }
+            if rc != 0 { return Err(last_error()); } // upstream unwraps -> same abort behaviour as a panic
+            out.truncate(n as usize);
+            return Ok(out);
+        }
+    }
+}
+
+impl Drop for GpuIndex { fn drop(&mut self) { unsafe { gf_index_destroy(self.h) } } }
