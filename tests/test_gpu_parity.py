@@ -251,3 +251,21 @@ def test_testdata_config1(host):
     merged = sc.mapper.fast_merge(host.FastqReaderPair(os.path.join(td, "R1.fq"), os.path.join(td, "R2.fq")).read_all()[1])
     assert [x[3] for x in merged] == [178, 161, 161]
     sc.mapper.close()
+
+
+def test_golden_fixture_matches(host):
+    """the committed golden records (tests/golden/synth_small_matches.json) through the CUDA path"""
+    import hashlib
+    import json
+    g = json.load(open(os.path.join(GOLD, "synth_small_matches.json")))
+    panel = synth.make_panel(scale=g["panel_scale"], max_genes=g["max_genes"])
+    batch = synth.generate_pairs(panel, g["n_pairs"], read_len=g["read_len"], seed=g["seed"], p_fusion=g["p_fusion"],
+                                 threads=2)
+    assert hashlib.sha256(batch.seq1.tobytes() + batch.seq2.tobytes()).hexdigest() == g["reads_sha256"]
+    m = host.FusionMapper.from_gene_spans(panel.genes(), device=0)
+    info = m.m_indexer.info()
+    assert {"n_sites": info.n_sites, "n_keys": info.n_keys, "n_unique": info.n_unique, "n_normal": info.n_normal,
+            "n_high": info.n_high} == g["index_counts"]
+    got = [list(r.astuple()) for r in m.scan_pair_end(batch)]
+    assert got == g["matches"]
+    m.close()
