@@ -46,6 +46,8 @@ void destroy_handle(gf_index* idx) {
     cudaFree(idx->d_gene_start);
     cudaFree(idx->d_gene_len);
     cudaFree(idx->d_gene_rev);
+    cudaFree(idx->d_planes);
+    cudaFree(idx->d_filter);
     idx->ws_survivors.release();
     idx->ws_counters.release();
     idx->ws_gtbl.release();
@@ -119,6 +121,7 @@ int gf_index_create(const gf_gene_span* genes, uint32_t n_genes, const gf_params
     gf_index* idx = new gf_index();
     idx->device = device;
     idx->params = p;
+    if (const char* e = getenv("GF_SCREEN")) idx->screen_version = atoi(e) == 1 ? 1 : 2;
     int rc = GF_OK;
     do {
         cudaDeviceProp prop;
@@ -227,6 +230,7 @@ int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_
         db.qual1 = s.qual1.as<uint8_t>();
         db.off1 = s.off1.as<uint64_t>();
         db.base1 = b1;
+        db.bytes1 = e1 - b1;
         db.pair_base = lo;
         db.max_len = in->max_len;
         if (pe) {
@@ -241,6 +245,7 @@ int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_
             db.qual2 = s.qual2.as<uint8_t>();
             db.off2 = s.off2.as<uint64_t>();
             db.base2 = b2;
+            db.bytes2 = e2 - b2;
         }
         GF_CUDA_TRY(cudaEventRecord(s.copied, cs));
         s.n = cn;
@@ -318,6 +323,8 @@ int gf_map_pairs_device(gf_index* idx, const gf_batch* in_dev, gf_match* d_out, 
     db.qual2 = in_dev->qual2;
     db.off2 = in_dev->off2;
     db.base1 = db.base2 = 0;
+    db.bytes1 = in_dev->bytes1;
+    db.bytes2 = in_dev->bytes2;
     db.pair_base = 0;
     db.max_len = in_dev->max_len;
     const unsigned long long launches0 = idx->launches;
@@ -396,6 +403,8 @@ int gf_fast_merge(gf_index* idx, const gf_batch* in, gf_merge_info* out) {
     db.off2 = s.off2.as<uint64_t>();
     db.base1 = b1;
     db.base2 = b2;
+    db.bytes1 = e1 - b1;
+    db.bytes2 = e2 - b2;
     rc = gf_fast_merge_device(idx, db, s.out.as<gf_merge_info>(), st);
     if (rc != GF_OK) return rc;
     GF_CUDA_TRY(cudaMemcpyAsync(out, s.out.p, sizeof(gf_merge_info) * n, cudaMemcpyDeviceToHost, st));
@@ -406,3 +415,16 @@ int gf_fast_merge(gf_index* idx, const gf_batch* in, gf_merge_info* out) {
 }
 
 } /* extern "C" */
+
+/* debug hook (not part of the ABI header): survivor list of the last mapping call on this handle */
+extern "C" int gf_debug_get_survivors(gf_index* idx, uint32_t* out_pairs_meta, uint64_t cap, uint64_t* n) {
+    std::lock_guard<std::mutex> lk(idx->mu);
+    GF_CUDA_TRY(cudaSetDevice(idx->device));
+    GF_CUDA_TRY(cudaDeviceSynchronize());
+    GfMapCounters c;
+    GF_CUDA_TRY(cudaMemcpy(&c, idx->ws_counters.p, sizeof(c), cudaMemcpyDeviceToHost));
+    *n = c.n_survivors;
+    uint64_t m = std::min<uint64_t>(cap, c.n_survivors);
+    if (m) GF_CUDA_TRY(cudaMemcpy(out_pairs_meta, idx->ws_survivors.p, sizeof(uint32_t) * 2 * m, cudaMemcpyDeviceToHost));
+    return GF_OK;
+}

@@ -42,6 +42,17 @@ struct GfDevIndex {
     const uint32_t* gene_start; /* goff of base 0 of each gene [n_genes] (ascending) */
     const uint32_t* gene_len;   /* [n_genes] */
     const uint8_t* gene_rev;    /* Gene::is_reversed() per gene */
+    /* L2-resident screen structures (gf_index.cu: k_gene_planes, k_window_class, filter bits in k_build_table) */
+    const uint32_t* g_lo;       /* gene arena as bit-planes, bit (goff & 31) of word (goff >> 5): low code bit */
+    const uint32_t* g_hi;       /* high code bit */
+    const uint32_t* g_v;        /* base is upper-case ACGT */
+    const uint32_t* g_cf;       /* 3 planes (stride g_cstride): bit b of the number of sites (1..7) the forward k-mer
+                                   of the window starting at goff votes for, 0 when that window is not an indexed
+                                   site or its key is HIGH */
+    const uint32_t* g_cr;       /* same for the reverse-complement k-mer of that window */
+    uint32_t g_cstride;
+    const unsigned long long* filter; /* blocked Bloom filter over all non-HIGH keys, 64-bit blocks */
+    uint32_t filter_words;
     uint32_t n_genes;
     uint32_t max_sites;         /* most sites a NORMAL key holds = max(skip_key_dup_threshold, 2) */
     uint32_t bucket_shift;      /* 32 - bucket_bits */
@@ -134,6 +145,30 @@ __device__ __forceinline__ uint32_t gf_table_find(const GfDevIndex& ix, uint32_t
         if (stop) return v;
         b = (b + 1) & ix.bucket_mask;
     }
+}
+
+/* membership filter (one-sided: no false negatives) -------------------------------------------------- */
+/* word index + bit masks of a key: 4 "present" bits, 3 more "multi" bits set only for NORMAL (dupe) keys */
+__device__ __forceinline__ uint32_t gf_filter_word(uint32_t key, uint32_t n_words) {
+    return (uint32_t)(((unsigned long long)(key * GF_HASH_MULT) * n_words) >> 32);
+}
+/* 64-bit block = two 32-bit halves; a key sets 2 "present" bits in each half, NORMAL (dupe) keys one more
+ * "multi" bit per half.  All 32-bit arithmetic. */
+__device__ __forceinline__ void gf_filter_masks(uint32_t key, uint32_t* any_lo, uint32_t* any_hi, uint32_t* multi_lo,
+                                                uint32_t* multi_hi) {
+    const uint32_t g1 = key * 0xC2B2AE35u, g2 = key * 0x27D4EB2Fu;
+    *any_lo = (1u << (g1 >> 27)) | (1u << ((g1 >> 22) & 31u));
+    *any_hi = (1u << (g2 >> 27)) | (1u << ((g2 >> 22) & 31u));
+    *multi_lo = 1u << ((g1 >> 17) & 31u);
+    *multi_hi = 1u << ((g2 >> 17) & 31u);
+}
+/* upper bound of the number of sites the key votes for: 0 absent/HIGH, 1 unique, max_sites dupes */
+__device__ __forceinline__ uint32_t gf_filter_sites(unsigned long long w, uint32_t key, uint32_t max_sites) {
+    uint32_t al, ah, ml, mh;
+    gf_filter_masks(key, &al, &ah, &ml, &mh);
+    const uint32_t wl = (uint32_t)w, wh = (uint32_t)(w >> 32);
+    if ((wl & al) != al || (wh & ah) != ah) return 0u;
+    return ((wl & ml) && (wh & mh)) ? max_sites : 1u;
 }
 
 /* site decoding ---------------------------------------------------------------------------- */

@@ -237,7 +237,8 @@ __global__ void k_classify(const unsigned long long* __restrict__ items, uint64_
 __global__ void k_build_table(const unsigned long long* __restrict__ items, uint64_t n, uint32_t thr,
                               const uint32_t* __restrict__ dupe_off, uint32_t* __restrict__ dupes,
                               unsigned long long* __restrict__ table, uint32_t bucket_shift, uint32_t bucket_mask,
-                              unsigned int* __restrict__ max_disp) {
+                              unsigned int* __restrict__ max_disp, unsigned long long* __restrict__ filter,
+                              uint32_t filter_words) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t key = (uint32_t)(items[i] >> 32);
@@ -254,6 +255,12 @@ __global__ void k_build_table(const unsigned long long* __restrict__ items, uint
     } else {
         val = (GF_KIND_HIGH << 30);
     }
+    if (len <= thr) { /* unique and NORMAL keys vote; HIGH keys never do and stay out of the filter */
+        uint32_t al, ah, ml, mh;
+        gf_filter_masks(key, &al, &ah, &ml, &mh);
+        if (len > 1) { al |= ml; ah |= mh; }
+        atomicOr(filter + gf_filter_word(key, filter_words), ((unsigned long long)ah << 32) | al);
+    }
     unsigned long long entry = ((unsigned long long)val << 32) | key;
     uint32_t b = gf_home_bucket(key, bucket_shift);
     uint32_t disp = 0;
@@ -268,6 +275,48 @@ __global__ void k_build_table(const unsigned long long* __restrict__ items, uint
         disp++;
     }
     if (disp) atomicMax(max_disp, disp);
+}
+
+/* ---- L2-resident screen structures ------------------------------------------------------------------ */
+/* gene arena -> bit-planes (thread per 32-base word) */
+__global__ void k_gene_planes(const uint8_t* __restrict__ arena, uint64_t arena_len, uint32_t n_words,
+                              uint32_t* __restrict__ lo, uint32_t* __restrict__ hi, uint32_t* __restrict__ v) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint32_t blo = 0, bhi = 0, bv = 0;
+    for (int j = 0; j < 32; j++) {
+        uint64_t g = 32ull * w + j;
+        uint32_t c = g < arena_len ? arena[g] : 0u;
+        if (gf_is_acgt_upper(c)) {
+            bv |= 1u << j;
+            blo |= gf_code_lo(c) << j;
+            bhi |= gf_code_hi(c) << j;
+        }
+    }
+    lo[w] = blo; hi[w] = bhi; v[w] = bv;
+}
+/* per window and strand: number of sites its k-mer votes for if the window is an indexed site (0 otherwise / HIGH) */
+__device__ __forceinline__ uint32_t window_sites(const GfDevIndex& ix, uint32_t key) {
+    uint32_t val = gf_table_find(ix, key);
+    if (val == GF_EMPTY_VAL) return 0u;
+    uint32_t kind = val >> 30;
+    return kind == GF_KIND_UNIQUE ? 1u : (kind == GF_KIND_NORMAL ? (val & 7u) : 0u);
+}
+__global__ void k_window_class(GfDevIndex ix, const uint8_t* __restrict__ arena, uint64_t arena_len,
+                               uint32_t* __restrict__ cf, uint32_t* __restrict__ cr, uint32_t stride) {
+    __shared__ uint8_t tile[EX_THREADS + 32];
+    uint64_t g0 = (uint64_t)blockIdx.x * EX_THREADS;
+    load_tile(arena, arena_len, g0, tile);
+    uint64_t g = g0 + threadIdx.x;
+    uint32_t key = 0;
+    bool f = false, r = false;
+    if (g < arena_len) extract_window(tile, threadIdx.x, &key, &f, &r);
+    uint32_t nf = f ? window_sites(ix, key) : 0u;
+    uint32_t nr = r ? window_sites(ix, gf_key_revcomp(key)) : 0u;
+    for (int b = 0; b < 3; b++) {
+        uint32_t mf = __ballot_sync(0xFFFFFFFFu, (nf >> b) & 1u), mr = __ballot_sync(0xFFFFFFFFu, (nr >> b) & 1u);
+        if ((threadIdx.x & 31) == 0) { cf[(size_t)b * stride + (g >> 5)] = mf; cr[(size_t)b * stride + (g >> 5)] = mr; }
+    }
 }
 
 /* ---- parity hook: lookups ---------------------------------------------------------------------------- */
@@ -445,21 +494,21 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     GF_CUDA_TRY(cudaMemsetAsync(idx->d_table, 0xFF, n_buckets * 32, st));
     GF_CUDA_TRY(cudaMalloc(&idx->d_dupes, sizeof(uint32_t) * ((size_t)n_dupes + 8)));
     unsigned int* d_maxdisp = (unsigned int*)(d_stats + 6);
+    /* blocked Bloom filter, ~12 bits per key (rounded up to whole 64-bit words, at least 1024 words) */
+    const uint32_t filter_words = (uint32_t)std::max<uint64_t>(1024, (n_keys * 12 + 63) / 64);
+    GF_CUDA_TRY(cudaMalloc(&idx->d_filter, sizeof(unsigned long long) * filter_words));
+    GF_CUDA_TRY(cudaMemsetAsync(idx->d_filter, 0, sizeof(unsigned long long) * filter_words, st));
     if (n_items) {
         const unsigned cb = (unsigned)((n_items + 255) / 256);
         k_build_table<<<cb, 256, 0, st>>>(d_items, n_items, thr, d_doff, (uint32_t*)idx->d_dupes,
                                           (unsigned long long*)idx->d_table, 32 - bucket_bits,
-                                          (uint32_t)(n_buckets - 1), d_maxdisp);
+                                          (uint32_t)(n_buckets - 1), d_maxdisp, (unsigned long long*)idx->d_filter,
+                                          filter_words);
         GF_CUDA_TRY(cudaGetLastError());
     }
     unsigned int h_maxdisp = 0;
     GF_CUDA_TRY(cudaMemcpyAsync(&h_maxdisp, d_maxdisp, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-    GF_CUDA_TRY(cudaEventRecord(e1, st));
     GF_CUDA_TRY(cudaStreamSynchronize(st));
-    float ms = 0;
-    GF_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     GF_CUDA_TRY(cudaFree(d_items));
     GF_CUDA_TRY(cudaFree(d_ncnt));
     GF_CUDA_TRY(cudaFree(d_doff));
@@ -479,6 +528,33 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     idx->dev.major_req = idx->params.major_gene_key_requirement;
     idx->dev.minor_req = idx->params.minor_gene_key_requirement;
     idx->dev.mismatch_thr = idx->params.mismatch_threshold;
+    idx->dev.filter = (const unsigned long long*)idx->d_filter;
+    idx->dev.filter_words = filter_words;
+
+    /* gene bit-planes (lo, hi, valid) + per-window site-count planes (3 bits x 2 strands) */
+    const uint32_t n_pw = (uint32_t)((arena_len + 31) / 32);
+    const size_t plane_stride = (size_t)n_pw + 72;
+    GF_CUDA_TRY(cudaMalloc(&idx->d_planes, sizeof(uint32_t) * plane_stride * 9));
+    GF_CUDA_TRY(cudaMemsetAsync(idx->d_planes, 0, sizeof(uint32_t) * plane_stride * 9, st));
+    uint32_t* pl = (uint32_t*)idx->d_planes;
+    idx->dev.g_lo = pl;
+    idx->dev.g_hi = pl + plane_stride;
+    idx->dev.g_v = pl + 2 * plane_stride;
+    idx->dev.g_cf = pl + 3 * plane_stride;
+    idx->dev.g_cr = pl + 6 * plane_stride;
+    idx->dev.g_cstride = (uint32_t)plane_stride;
+    k_gene_planes<<<(n_pw + 255) / 256, 256, 0, st>>>((const uint8_t*)idx->d_gene_ascii, arena_len, n_pw, pl,
+                                                      pl + plane_stride, pl + 2 * plane_stride);
+    k_window_class<<<ex_blocks, EX_THREADS, 0, st>>>(idx->dev, (const uint8_t*)idx->d_gene_ascii, arena_len,
+                                                     pl + 3 * plane_stride, pl + 6 * plane_stride,
+                                                     (uint32_t)plane_stride);
+    GF_CUDA_TRY(cudaGetLastError());
+    GF_CUDA_TRY(cudaEventRecord(e1, st));
+    GF_CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0;
+    GF_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
 
     gf_index_info& inf = idx->info;
     inf.n_sites = n_items;
@@ -490,7 +566,8 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     inf.table_bytes = n_buckets * 32;
     inf.max_displacement = h_maxdisp;
     inf.gene_bytes = gene_bytes;
-    inf.device_bytes = n_buckets * 32 + sizeof(uint32_t) * ((size_t)n_dupes + 8) + arena_len + 9ull * (n_genes + 1);
+    inf.device_bytes = n_buckets * 32 + sizeof(uint32_t) * ((size_t)n_dupes + 8) + arena_len + 9ull * (n_genes + 1) +
+                       sizeof(uint32_t) * plane_stride * 9 + sizeof(unsigned long long) * (size_t)filter_words;
     inf.build_ms = ms;
     return GF_OK;
 }

@@ -77,7 +77,7 @@ struct gf_index {
     std::vector<uint32_t> gene_start, gene_len;
 
     void *d_table = nullptr, *d_dupes = nullptr, *d_gene_ascii = nullptr, *d_gene_start = nullptr,
-         *d_gene_len = nullptr, *d_gene_rev = nullptr;
+         *d_gene_len = nullptr, *d_gene_rev = nullptr, *d_planes = nullptr, *d_filter = nullptr;
 
     std::mutex mu; /* serialises calls on one handle */
     cudaStream_t stream = nullptr, copy_stream = nullptr;
@@ -93,6 +93,7 @@ struct gf_index {
     gf_map_stats stats{};
     unsigned long long launches = 0;
     int sm_count = 148;
+    int screen_version = 2; /* 1 = HBM hash probe per k-mer, 2 = L2-resident filter + gene planes (GF_SCREEN) */
 };
 
 /* gf_index.cu */
@@ -105,6 +106,7 @@ struct GfDevBatch {
     const uint8_t *seq1, *qual1, *seq2, *qual2;
     const uint64_t *off1, *off2;
     uint64_t base1, base2;   /* value subtracted from every offset (chunked host batches) */
+    uint64_t bytes1, bytes2; /* readable extent of the seq/qual arenas (0 = unknown: no bounds guard) */
     uint64_t pair_base;      /* added to the local pair index in emitted records */
     uint32_t max_len;        /* upper bound of any read length (selects the kernel capacity) */
 };

@@ -54,63 +54,160 @@ struct ScreenWarp {
     /* overlap-resolved rc(R2) (x*) and the sequence that is mapped (m*) */
     uint32_t xlo[MAXW + 1], xhi[MAXW + 1], xv[MAXW + 1];
     uint32_t mlo[2 * MAXW + 2], mhi[2 * MAXW + 2], mv[2 * MAXW + 2];
+    /* screen v2: reverse-complement planes of the mapped sequence, gene planes along the seed diagonal,
+     * per-chunk equality / hit words and the list of offsets that still need a filter probe */
+    uint32_t rlo[2 * MAXW + 2], rhi[2 * MAXW + 2], rv[2 * MAXW + 2];
+    uint32_t glo[2 * MAXW + 3], ghi[2 * MAXW + 3], gv[2 * MAXW + 3], gc[3][2 * MAXW + 3];
+    uint32_t eq[2 * MAXW + 2], hit[2 * MAXW + 2];
+    uint16_t others[32 * MAXW + 32];
+    /* forward planes of R2 (mapped when the pair does not merge) */
+    uint32_t f2lo[MAXW + 1], f2hi[MAXW + 1], f2v[MAXW + 1];
+    /* SWAR scratch: 6 byte-granular planes, bit (p + a) of plane j <-> base p of the read being converted,
+     * a = misalignment (0..7) of the read's first byte w.r.t. the 8-byte loads */
+    uint32_t sp[6][MAXW + 4];
 };
 
-/* forward planes of a read: lo/hi code bits, valid (upper-case ACGT), N, quality >= '?' and <= '0' */
-__device__ __forceinline__ void planes_forward(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ qual,
-                                               int len, uint32_t* lo, uint32_t* hi, uint32_t* v, uint32_t* n,
-                                               uint32_t* qh, uint32_t* ql) {
-    const uint32_t lane = gf_lane();
-    const int nw = (len + 31) >> 5;
-    for (int r = 0; r < nw; r++) {
-        int p = 32 * r + (int)lane;
-        bool inb = p < len;
-        uint32_t c = inb ? __ldg(seq + p) : 0u;
-        bool valid = inb && gf_is_acgt_upper(c);
-        uint32_t blo = __ballot_sync(FULL, valid && gf_code_lo(c));
-        uint32_t bhi = __ballot_sync(FULL, valid && gf_code_hi(c));
-        uint32_t bv = __ballot_sync(FULL, valid);
-        uint32_t bn = 0, bqh = 0, bql = 0;
-        if (n) bn = __ballot_sync(FULL, inb && c == 'N');
-        if (qh) {
-            uint32_t q = inb ? __ldg(qual + p) : 0u;
-            bqh = __ballot_sync(FULL, inb && q >= '?');
-            bql = __ballot_sync(FULL, inb && q <= '0');
-        }
-        if (lane == 0) {
-            lo[r] = blo; hi[r] = bhi; v[r] = bv;
-            if (n) n[r] = bn;
-            if (qh) { qh[r] = bqh; ql[r] = bql; }
-        }
-    }
-    if (lane == 0) {
-        lo[nw] = 0; hi[nw] = 0; v[nw] = 0;
-        if (n) n[nw] = 0;
-        if (qh) { qh[nw] = 0; ql[nw] = 0; }
-    }
+/* ---- SWAR plane construction: 8 ASCII bytes per lane and load --------------------------------------- */
+__device__ __forceinline__ uint32_t gather4(uint32_t t) { /* bits 0,8,16,24 -> bits 0..3 */
+    return ((t * 0x01020408u) >> 24) & 0xFu;
 }
-/* planes of reverse_complement(R2) (sequence.rs:22-60: case-insensitive, non-ACGT -> 'N') + reversed quals */
-__device__ __forceinline__ void planes_revcomp(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ qual,
-                                               int len, uint32_t* lo, uint32_t* hi, uint32_t* v, uint32_t* n,
-                                               uint32_t* qh, uint32_t* ql) {
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t y) { /* bit 7 of every byte that is 0 */
+    return ~(((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y) & 0x80808080u;
+}
+/* 4 bases -> 4-bit masks: code bits (A0 T1 C2 G3), valid = one of ACGT (upper case, or either case when ci) */
+__device__ __forceinline__ void classify4(uint32_t x, bool ci, uint32_t* lo, uint32_t* hi, uint32_t* v) {
+    const uint32_t xu = ci ? (x & 0xDFDFDFDFu) : x;
+    const uint32_t t = (xu >> 1) & 0x03030303u; /* A0 C1 T2 G3 per byte */
+    const uint32_t u = t | (t >> 4);
+    const uint32_t sel = (u & 0xFFu) | ((u >> 8) & 0xFF00u);
+    const uint32_t expect = __byte_perm(0x47544341u, 0u, sel); /* 'A','C','T','G' */
+    const uint32_t vv = gather4(zero_bytes(xu ^ expect) >> 7);
+    *v = vv;
+    *lo = gather4((xu >> 2) & 0x01010101u) & vv;
+    *hi = gather4((xu >> 1) & 0x01010101u) & vv;
+}
+__device__ __forceinline__ uint32_t ge4(uint32_t q, uint32_t thr4) { /* per byte: (q & 0x7F) >= thr */
+    return gather4((((q | 0x80808080u) - thr4) & 0x80808080u) >> 7);
+}
+/* 8 bytes at the 8-aligned address `p`; bytes outside [lo, hi) read as 0 (never touches memory outside) */
+__device__ __forceinline__ uint2 load8_guarded(const uint8_t* p, const uint8_t* lo, const uint8_t* hi) {
+    if (p >= lo && p + 8 <= hi) return __ldg(reinterpret_cast<const uint2*>(p));
+    uint32_t w[2] = {0u, 0u};
+    for (int t = 0; t < 8; t++)
+        if (p + t >= lo && p + t < hi) w[t >> 2] |= (uint32_t)__ldg(p + t) << (8 * (t & 3));
+    return make_uint2(w[0], w[1]);
+}
+/* Converts one read into the 6 scratch planes S.sp[0..5] (byte L of each plane = bases 8L-a .. 8L-a+7):
+ *   0 lo, 1 hi, 2 valid (case-insensitive when ci), 3 extra (R1: is 'N'; R2: valid upper-case only), 4 q>='?', 5 q<='0'
+ * Returns the bit shifts (a_seq, a_qual) to apply when reading the scratch planes. */
+template <int MAXW>
+__device__ __forceinline__ void swar_convert(ScreenWarp<MAXW>& S, const uint8_t* seq, const uint8_t* qual, int len,
+                                             const uint8_t* seq_lo, const uint8_t* seq_hi, const uint8_t* qual_lo,
+                                             const uint8_t* qual_hi, bool is_r2, int* a_seq, int* a_qual) {
     const uint32_t lane = gf_lane();
-    const int nw = (len + 31) >> 5;
-    for (int r = 0; r < nw; r++) {
-        int p = 32 * r + (int)lane;
-        bool inb = p < len;
-        uint32_t c = inb ? __ldg(seq + (len - 1 - p)) : 0u;
-        uint32_t q = inb ? __ldg(qual + (len - 1 - p)) : 0u;
-        uint32_t cu = c & 0xDFu;
-        bool valid = inb && gf_is_acgt_upper(cu);
-        uint32_t blo = __ballot_sync(FULL, valid && !gf_code_lo(cu)); /* complement = code ^ 1 */
-        uint32_t bhi = __ballot_sync(FULL, valid && gf_code_hi(cu));
-        uint32_t bv = __ballot_sync(FULL, valid);
-        uint32_t bn = __ballot_sync(FULL, inb && !valid);
-        uint32_t bqh = __ballot_sync(FULL, inb && q >= '?');
-        uint32_t bql = __ballot_sync(FULL, inb && q <= '0');
-        if (lane == 0) { lo[r] = blo; hi[r] = bhi; v[r] = bv; n[r] = bn; qh[r] = bqh; ql[r] = bql; }
+    const int as = (int)((uintptr_t)seq & 7u), aq = (int)((uintptr_t)qual & 7u);
+    const uint8_t* s0 = seq - as;
+    const uint8_t* q0 = qual - aq;
+    uint8_t* b0 = reinterpret_cast<uint8_t*>(S.sp[0]);
+    uint8_t* b1 = reinterpret_cast<uint8_t*>(S.sp[1]);
+    uint8_t* b2 = reinterpret_cast<uint8_t*>(S.sp[2]);
+    uint8_t* b3 = reinterpret_cast<uint8_t*>(S.sp[3]);
+    uint8_t* b4 = reinterpret_cast<uint8_t*>(S.sp[4]);
+    uint8_t* b5 = reinterpret_cast<uint8_t*>(S.sp[5]);
+    const int nbytes = 4 * (((len + 31) >> 5) + 3); /* scratch bytes that later reads may touch */
+    for (int L = (int)lane; L < nbytes; L += 32) {
+        uint32_t lo = 0, hi = 0, v = 0, ex = 0, qh = 0, ql = 0;
+        /* sequence planes: base p = 8L - as + t */
+        {
+            int p0 = 8 * L - as;
+            if (p0 < len && p0 + 8 > 0) {
+                uint2 x = load8_guarded(s0 + 8 * L, seq_lo, seq_hi);
+                uint32_t l0, h0, v0, l1, h1, v1;
+                classify4(x.x, is_r2, &l0, &h0, &v0);
+                classify4(x.y, is_r2, &l1, &h1, &v1);
+                lo = l0 | (l1 << 4); hi = h0 | (h1 << 4); v = v0 | (v1 << 4);
+                if (is_r2) {
+                    uint32_t c0, c1, c2, c3, c4, c5;
+                    classify4(x.x, false, &c0, &c1, &c2);
+                    classify4(x.y, false, &c3, &c4, &c5);
+                    ex = c2 | (c5 << 4);
+                } else {
+                    ex = gather4(zero_bytes(x.x ^ 0x4E4E4E4Eu) >> 7) | (gather4(zero_bytes(x.y ^ 0x4E4E4E4Eu) >> 7) << 4);
+                }
+                int tlo = max(0, -p0), thi = min(8, len - p0);
+                uint32_t pm = ((1u << thi) - 1u) & ~((1u << tlo) - 1u);
+                lo &= pm; hi &= pm; v &= pm; ex &= pm;
+            }
+        }
+        if (qual) {
+            int p0 = 8 * L - aq;
+            if (p0 < len && p0 + 8 > 0) {
+                uint2 q = load8_guarded(q0 + 8 * L, qual_lo, qual_hi);
+                qh = ge4(q.x, 0x3F3F3F3Fu) | (ge4(q.y, 0x3F3F3F3Fu) << 4);               /* >= '?' */
+                ql = (~(ge4(q.x, 0x31313131u) | (ge4(q.y, 0x31313131u) << 4))) & 0xFFu;  /* <= '0' */
+                int tlo = max(0, -p0), thi = min(8, len - p0);
+                uint32_t pm = ((1u << thi) - 1u) & ~((1u << tlo) - 1u);
+                qh &= pm; ql &= pm;
+            }
+        }
+        b0[L] = (uint8_t)lo; b1[L] = (uint8_t)hi; b2[L] = (uint8_t)v; b3[L] = (uint8_t)ex;
+        b4[L] = (uint8_t)qh; b5[L] = (uint8_t)ql;
     }
-    if (lane == 0) { lo[nw] = 0; hi[nw] = 0; v[nw] = 0; n[nw] = 0; qh[nw] = 0; ql[nw] = 0; }
+    *a_seq = as;
+    *a_qual = aq;
+    __syncwarp();
+}
+/* 32 bits of a scratch plane starting at (possibly negative) bit position pos */
+__device__ __forceinline__ uint32_t win32(const uint32_t* pl, int pos) {
+    if (pos >= 0) return fsr(pl, (uint32_t)pos);
+    if (pos > -32) return pl[0] << (-pos);
+    return 0u;
+}
+/* R1 planes (forward) from the scratch */
+template <int MAXW>
+__device__ __forceinline__ void planes_r1(ScreenWarp<MAXW>& S, const uint8_t* seq, const uint8_t* qual, int len,
+                                          const uint8_t* slo, const uint8_t* shi, const uint8_t* qlo, const uint8_t* qhi) {
+    int as, aq;
+    swar_convert<MAXW>(S, seq, qual, len, slo, shi, qlo, qhi, false, &as, &aq);
+    const int nw = (len + 31) >> 5;
+    for (int k = (int)gf_lane(); k <= nw; k += 32) {
+        const bool in = k < nw;
+        S.r1lo[k] = in ? fsr(S.sp[0], (uint32_t)(32 * k + as)) : 0u;
+        S.r1hi[k] = in ? fsr(S.sp[1], (uint32_t)(32 * k + as)) : 0u;
+        S.r1v[k] = in ? fsr(S.sp[2], (uint32_t)(32 * k + as)) : 0u;
+        S.r1n[k] = in ? fsr(S.sp[3], (uint32_t)(32 * k + as)) : 0u;
+        S.q1hi[k] = in ? fsr(S.sp[4], (uint32_t)(32 * k + aq)) : 0u;
+        S.q1lo[k] = in ? fsr(S.sp[5], (uint32_t)(32 * k + aq)) : 0u;
+    }
+    __syncwarp();
+}
+/* R2: forward planes (f2*, upper-case validity) and the planes of reverse_complement(R2) (c2*, sequence.rs:22-60:
+ * case-insensitive, everything else 'N') with reversed qualities */
+template <int MAXW>
+__device__ __forceinline__ void planes_r2(ScreenWarp<MAXW>& S, const uint8_t* seq, const uint8_t* qual, int len,
+                                          const uint8_t* slo, const uint8_t* shi, const uint8_t* qlo, const uint8_t* qhi) {
+    int as, aq;
+    swar_convert<MAXW>(S, seq, qual, len, slo, shi, qlo, qhi, true, &as, &aq);
+    const int nw = (len + 31) >> 5;
+    for (int k = (int)gf_lane(); k <= nw; k += 32) {
+        const bool in = k < nw;
+        uint32_t fv = in ? fsr(S.sp[3], (uint32_t)(32 * k + as)) : 0u;
+        S.f2v[k] = fv;
+        S.f2lo[k] = in ? (fsr(S.sp[0], (uint32_t)(32 * k + as)) & fv) : 0u;
+        S.f2hi[k] = in ? (fsr(S.sp[1], (uint32_t)(32 * k + as)) & fv) : 0u;
+        uint32_t clo = 0, chi = 0, cv = 0, cn = 0, cqh = 0, cql = 0;
+        if (in) {
+            const int pos = len - 32 * k - 32; /* out bit b = src[len-1-(32k+b)] */
+            cv = __brev(win32(S.sp[2], pos + as));
+            clo = ~__brev(win32(S.sp[0], pos + as)) & cv; /* complement = code ^ 1 */
+            chi = __brev(win32(S.sp[1], pos + as));
+            cn = lowmask(len - 32 * k) & ~cv;
+            cqh = __brev(win32(S.sp[4], pos + aq));
+            cql = __brev(win32(S.sp[5], pos + aq));
+        }
+        S.c2lo[k] = clo; S.c2hi[k] = chi; S.c2v[k] = cv; S.c2n[k] = cn; S.q2hi[k] = cqh; S.q2lo[k] = cql;
+    }
+    __syncwarp();
 }
 
 /* fast_merge's inner loop for one overlap length (read.rs:339-367), 32 bases per step.
@@ -284,7 +381,205 @@ __device__ __forceinline__ bool screen_sequence(const GfDevIndex& ix, const uint
     return T >= need_total && (T - cntd) >= need_minor;
 }
 
-template <int MAXW, bool PAIRED>
+
+/* ---- screen v2: L2-resident working set ------------------------------------------------------------
+ * Same conservative bound as screen_sequence (count2 <= T - c_d), but T and c_d are obtained without
+ * touching the HBM table for every k-mer:
+ *   1. seed: up to 8 spread k-mers are tested in the Bloom filter (L2); the first present one is looked up
+ *      in the HBM table; a UNIQUE key gives a site, i.e. a diagonal d of the read against one gene strand.
+ *   2. the whole read is compared with the 2-bit gene planes along d (32 bases per xor), a 16-wide run
+ *      detector yields every offset whose 16-mer equals the gene window; where that window is an indexed
+ *      voting site (site-count planes g_cf / g_cr) the votes are known exactly: +nsites to T, +1 to c_d.
+ *   3. every other valid even offset is probed in the filter: contributes an UPPER bound of its votes to T.
+ * No false negatives anywhere => T_ub >= T and c_d <= true votes on d => the drop rule stays safe. */
+__device__ __forceinline__ uint32_t run16(uint32_t w0, uint32_t w1) {
+    /* bit b set <=> bits [b, b+16) of the 64-bit concatenation are all ones */
+    unsigned long long x = (unsigned long long)w0 | ((unsigned long long)w1 << 32);
+    x &= x >> 1;
+    x &= x >> 2;
+    x &= x >> 4;
+    x &= x >> 8;
+    return (uint32_t)x;
+}
+/* L2 residency: filter and gene planes are loaded with an evict_last policy, so the 6 GB of reads that stream
+ * through the same L2 do not push them out */
+__device__ __forceinline__ unsigned long long make_policy_keep() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long ldg_filter(const unsigned long long* p, unsigned long long pol) {
+    unsigned long long v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg_plane(const uint32_t* p, unsigned long long pol) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
+template <int MAXW>
+__device__ __forceinline__ bool screen_sequence2(const GfDevIndex& ix, ScreenWarp<MAXW>& S, const uint32_t* lo,
+                                                 const uint32_t* hi, const uint32_t* v, int len, int need_total,
+                                                 int need_minor, unsigned long long* probes) {
+    const uint32_t lane = gf_lane();
+    const int nprobe = len >= 16 ? ((len - 16) >> 1) + 1 : 0;
+    *probes += (unsigned long long)nprobe;
+    if (need_total <= 0 || need_minor <= 0) return nprobe > 0 || need_total <= 0; /* degenerate params: keep */
+    if (nprobe == 0) return false;
+    const int nch = (len + 31) >> 5;
+    const unsigned long long pol = make_policy_keep();
+
+    /* 1. seed */
+    uint32_t seed_val = GF_EMPTY_VAL;
+    int seed_i = 0;
+    {
+        int i = (int)(((long long)(lane & 7u) * nprobe) >> 3) * 2;
+        bool ok = lane < 8 && (fsr(v, (uint32_t)i) & 0xFFFFu) == 0xFFFFu;
+        uint32_t key = ((fsr(hi, (uint32_t)i) & 0xFFFFu) << 16) | (fsr(lo, (uint32_t)i) & 0xFFFFu);
+        bool present = false;
+        if (ok) present = gf_filter_sites(ldg_filter(ix.filter + gf_filter_word(key, ix.filter_words), pol), key, 2u) == 1u;
+        uint32_t pm = __ballot_sync(FULL, present);
+        while (pm) {
+            int src = __ffs(pm) - 1;
+            pm &= pm - 1;
+            uint32_t k = __shfl_sync(FULL, key, src);
+            uint32_t val = gf_table_find(ix, k);
+            if (val != GF_EMPTY_VAL && (val >> 30) == GF_KIND_UNIQUE) {
+                seed_val = val;
+                seed_i = __shfl_sync(FULL, i, src);
+                break;
+            }
+        }
+    }
+
+    int T = 0, c_d = 0;
+    const uint32_t *plo = lo, *phi = hi, *pv = v; /* planes the "other" offsets are enumerated on */
+    bool rc = false;
+    uint32_t parity = 0x55555555u;
+    if (seed_val != GF_EMPTY_VAL) {
+        rc = (seed_val & GF_SITE_STRAND) != 0;
+        const uint32_t goff = seed_val & GF_SITE_GOFF_MASK;
+        uint32_t D;
+        if (!rc) {
+            D = goff - (uint32_t)seed_i;
+        } else {
+            /* compare revcomp(read) with the forward gene: read'[y] = comp(read[len-1-y]) */
+            for (int k = (int)lane; k <= nch; k += 32) {
+                uint32_t a = 0, b = 0, c = 0;
+                if (k < nch) {
+                    int pos = len - 32 * k - 32;
+                    if (pos >= 0) { a = fsr(lo, (uint32_t)pos); b = fsr(hi, (uint32_t)pos); c = fsr(v, (uint32_t)pos); }
+                    else if (pos > -32) { a = lo[0] << (-pos); b = hi[0] << (-pos); c = v[0] << (-pos); }
+                    a = __brev(a); b = __brev(b); c = __brev(c);
+                    a = (a ^ c) & c; /* complement = code ^ 1 on valid bases */
+                }
+                S.rlo[k] = a; S.rhi[k] = b; S.rv[k] = c;
+            }
+            plo = S.rlo; phi = S.rhi; pv = S.rv;
+            D = goff + (uint32_t)seed_i - (uint32_t)len + 1u;
+            if (len & 1) parity = 0xAAAAAAAAu; /* i' = len-16-i: even i <=> i' has the parity of len */
+            __syncwarp();
+        }
+        /* 2. gene planes along the diagonal */
+        const uint32_t wbase = D >> 5, sh = D & 31u;
+        const uint32_t* gc = rc ? ix.g_cr : ix.g_cf;
+        for (int k = (int)lane; k <= nch + 1; k += 32) {
+            S.glo[k] = ldg_plane(ix.g_lo + wbase + k, pol);
+            S.ghi[k] = ldg_plane(ix.g_hi + wbase + k, pol);
+            S.gv[k] = ldg_plane(ix.g_v + wbase + k, pol);
+            S.gc[0][k] = ldg_plane(gc + wbase + k, pol);
+            S.gc[1][k] = ldg_plane(gc + ix.g_cstride + wbase + k, pol);
+            S.gc[2][k] = ldg_plane(gc + 2 * ix.g_cstride + wbase + k, pol);
+        }
+        __syncwarp();
+        for (int k = (int)lane; k <= nch; k += 32) {
+            uint32_t e = 0;
+            if (k < nch) {
+                uint32_t glo = __funnelshift_r(S.glo[k], S.glo[k + 1], sh);
+                uint32_t ghi = __funnelshift_r(S.ghi[k], S.ghi[k + 1], sh);
+                uint32_t gvv = __funnelshift_r(S.gv[k], S.gv[k + 1], sh);
+                e = ~((plo[k] ^ glo) | (phi[k] ^ ghi)) & pv[k] & gvv;
+            }
+            S.eq[k] = e;
+        }
+        __syncwarp();
+        int c = 0, t = 0;
+        for (int k = (int)lane; k < nch; k += 32) {
+            uint32_t m = run16(S.eq[k], S.eq[k + 1]) & parity;
+            uint32_t c0 = __funnelshift_r(S.gc[0][k], S.gc[0][k + 1], sh) & m;
+            uint32_t c1 = __funnelshift_r(S.gc[1][k], S.gc[1][k + 1], sh) & m;
+            uint32_t c2 = __funnelshift_r(S.gc[2][k], S.gc[2][k + 1], sh) & m;
+            uint32_t h = c0 | c1 | c2; /* equal to an indexed, voting window: votes are known exactly */
+            S.hit[k] = h;
+            c += __popc(h);
+            t += __popc(c0) + 2 * __popc(c1) + 4 * __popc(c2);
+        }
+        c_d = (int)__reduce_add_sync(FULL, (unsigned)c);
+        T = (int)__reduce_add_sync(FULL, (unsigned)t);
+    }
+    __syncwarp();
+
+    /* 3. every other valid even offset -> filter probe (upper bound of its votes) */
+    int t_local = 0;
+    if (seed_val == GF_EMPTY_VAL) {
+        /* no diagonal: all even offsets, straight from the planes */
+        for (int j0 = 0; j0 < nprobe; j0 += 64) {
+            uint32_t key[2];
+            unsigned long long w[2];
+            bool ok[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                int j = j0 + 32 * u + (int)lane;
+                uint32_t off = 2u * (uint32_t)min(j, nprobe - 1);
+                ok[u] = j < nprobe && (fsr(pv, off) & 0xFFFFu) == 0xFFFFu;
+                key[u] = ((fsr(phi, off) & 0xFFFFu) << 16) | (fsr(plo, off) & 0xFFFFu);
+                w[u] = 0;
+                if (ok[u]) w[u] = ldg_filter(ix.filter + gf_filter_word(key[u], ix.filter_words), pol);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+                if (ok[u]) t_local += (int)gf_filter_sites(w[u], key[u], ix.max_sites);
+        }
+    } else {
+        /* offsets not explained by the diagonal: compact them into a list, then spread over the lanes */
+        int total = 0;
+        for (int k0 = 0; k0 < nch; k0 += 32) {
+            int k = k0 + (int)lane;
+            uint32_t om = 0;
+            if (k < nch) om = run16(pv[k], pv[k + 1]) & parity & ~S.hit[k];
+            if (__ballot_sync(FULL, om != 0u) == 0u) continue;
+            int cnt = __popc(om);
+            int incl = cnt;
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(FULL, incl, o);
+                if ((int)lane >= o) incl += t;
+            }
+            int pos = total + incl - cnt;
+            while (om) {
+                int b = __ffs(om) - 1;
+                om &= om - 1;
+                S.others[pos++] = (uint16_t)(32 * k + b);
+            }
+            total += __shfl_sync(FULL, incl, 31);
+        }
+        __syncwarp();
+        for (int j = (int)lane; j - (int)lane < total; j += 32) {
+            if (j < total) {
+                uint32_t off = S.others[j];
+                uint32_t kk = ((fsr(phi, off) & 0xFFFFu) << 16) | (fsr(plo, off) & 0xFFFFu);
+                uint32_t key = rc ? gf_key_revcomp(kk) : kk;
+                t_local += (int)gf_filter_sites(ldg_filter(ix.filter + gf_filter_word(key, ix.filter_words), pol), key,
+                                                ix.max_sites);
+            }
+        }
+    }
+    T += (int)__reduce_add_sync(FULL, (unsigned)t_local);
+    return T >= need_total && (T - c_d) >= need_minor;
+}
+
+template <int MAXW, bool PAIRED, int VERSION>
 __global__ void __launch_bounds__(256, 3) k_screen(ScreenParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScreenWarp<MAXW>* Sall = reinterpret_cast<ScreenWarp<MAXW>*>(smem_raw);
@@ -297,6 +592,11 @@ __global__ void __launch_bounds__(256, 3) k_screen(ScreenParams P) {
 
     unsigned long long c_seq = 0, c_probes = 0, c_bytes = 0, c_merged = 0;
     uint32_t err = 0;
+    const uint8_t* const NOBOUND = reinterpret_cast<const uint8_t*>(~(uintptr_t)0);
+    const uint8_t* bound1 = B.bytes1 ? B.seq1 + B.bytes1 : NOBOUND;
+    const uint8_t* qbound1 = B.bytes1 ? B.qual1 + B.bytes1 : NOBOUND;
+    const uint8_t* bound2 = (PAIRED && B.bytes2) ? B.seq2 + B.bytes2 : NOBOUND;
+    const uint8_t* qbound2 = (PAIRED && B.bytes2) ? B.qual2 + B.bytes2 : NOBOUND;
 
     for (uint64_t p = gwarp; p < B.n; p += n_warps) {
         const uint64_t o1 = __ldg(B.off1 + p), e1 = __ldg(B.off1 + p + 1);
@@ -316,11 +616,10 @@ __global__ void __launch_bounds__(256, 3) k_screen(ScreenParams P) {
             continue;
         }
         __syncwarp();
-        planes_forward(s1, q1, len1, S.r1lo, S.r1hi, S.r1v, S.r1n, S.q1hi, S.q1lo);
+        planes_r1<MAXW>(S, s1, q1, len1, B.seq1, bound1, B.qual1, qbound1);
         int olen = -1, diff = 0;
         if (PAIRED) {
-            planes_revcomp(s2, q2, len2, S.c2lo, S.c2hi, S.c2v, S.c2n, S.q2hi, S.q2lo);
-            __syncwarp();
+            planes_r2<MAXW>(S, s2, q2, len2, B.seq2, bound2, B.qual2, qbound2);
             olen = find_overlap<MAXW>(S, len1, len2, &diff);
         }
         __syncwarp();
@@ -341,16 +640,16 @@ __global__ void __launch_bounds__(256, 3) k_screen(ScreenParams P) {
                     len = len1;
                     meta = 1u;
                 } else {
-                    __syncwarp();
-                    planes_forward(s2, nullptr, len2, S.mlo, S.mhi, S.mv, nullptr, nullptr, nullptr);
-                    __syncwarp();
+                    plo = S.f2lo; phi = S.f2hi; pv = S.f2v;
                     len = len2;
                     meta = 2u;
                 }
             }
             c_seq++;
             c_bytes += (unsigned long long)len;
-            bool sv = screen_sequence(P.ix, plo, phi, pv, len, P.need_total, P.need_minor, &c_probes);
+            bool sv = VERSION == 1
+                          ? screen_sequence(P.ix, plo, phi, pv, len, P.need_total, P.need_minor, &c_probes)
+                          : screen_sequence2<MAXW>(P.ix, S, plo, phi, pv, len, P.need_total, P.need_minor, &c_probes);
             if (sv && lane == 0) {
                 uint32_t slot = atomicAdd(&P.counters->n_survivors, 1u);
                 if (slot < P.survivors_cap) P.survivors[slot] = make_uint2((uint32_t)p, meta);
@@ -384,8 +683,10 @@ __global__ void __launch_bounds__(256) k_merge_only(GfDevBatch B, gf_merge_info*
             continue;
         }
         __syncwarp();
-        planes_forward(B.seq1 + (o1 - B.base1), B.qual1 + (o1 - B.base1), len1, S.r1lo, S.r1hi, S.r1v, S.r1n, S.q1hi, S.q1lo);
-        planes_revcomp(B.seq2 + (o2 - B.base2), B.qual2 + (o2 - B.base2), len2, S.c2lo, S.c2hi, S.c2v, S.c2n, S.q2hi, S.q2lo);
+        planes_r1<MAXW>(S, B.seq1 + (o1 - B.base1), B.qual1 + (o1 - B.base1), len1, B.seq1, B.seq1 + B.bytes1, B.qual1,
+                        B.qual1 + B.bytes1);
+        planes_r2<MAXW>(S, B.seq2 + (o2 - B.base2), B.qual2 + (o2 - B.base2), len2, B.seq2, B.seq2 + B.bytes2, B.qual2,
+                        B.qual2 + B.bytes2);
         __syncwarp();
         int diff = 0;
         int olen = find_overlap<MAXW>(S, len1, len2, &diff);
@@ -874,13 +1175,19 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
         const int blocks_per_sm = 3; /* 80 registers x 256 threads -> 3 resident blocks per SM */
         uint64_t want = (b.n + warps - 1) / warps;
         unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)idx->sm_count * blocks_per_sm);
-        if (small) {
-            if (paired) { GF_CUDA_TRY(set_smem(k_screen<8, true>, smem)); k_screen<8, true><<<grid, threads, smem, st>>>(sp); }
-            else { GF_CUDA_TRY(set_smem(k_screen<8, false>, smem)); k_screen<8, false><<<grid, threads, smem, st>>>(sp); }
+#define GF_LAUNCH_SCREEN(W, PE, VER)                                         \
+    do {                                                                     \
+        GF_CUDA_TRY(set_smem(k_screen<W, PE, VER>, smem));                   \
+        k_screen<W, PE, VER><<<grid, threads, smem, st>>>(sp);               \
+    } while (0)
+        if (idx->screen_version == 1) {
+            if (small) { if (paired) GF_LAUNCH_SCREEN(8, true, 1); else GF_LAUNCH_SCREEN(8, false, 1); }
+            else { if (paired) GF_LAUNCH_SCREEN(32, true, 1); else GF_LAUNCH_SCREEN(32, false, 1); }
         } else {
-            if (paired) { GF_CUDA_TRY(set_smem(k_screen<32, true>, smem)); k_screen<32, true><<<grid, threads, smem, st>>>(sp); }
-            else { GF_CUDA_TRY(set_smem(k_screen<32, false>, smem)); k_screen<32, false><<<grid, threads, smem, st>>>(sp); }
+            if (small) { if (paired) GF_LAUNCH_SCREEN(8, true, 2); else GF_LAUNCH_SCREEN(8, false, 2); }
+            else { if (paired) GF_LAUNCH_SCREEN(32, true, 2); else GF_LAUNCH_SCREEN(32, false, 2); }
         }
+#undef GF_LAUNCH_SCREEN
         GF_CUDA_TRY(cudaGetLastError());
         idx->launches++;
     }
