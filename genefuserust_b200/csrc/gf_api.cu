@@ -121,7 +121,7 @@ int gf_index_create(const gf_gene_span* genes, uint32_t n_genes, const gf_params
     gf_index* idx = new gf_index();
     idx->device = device;
     idx->params = p;
-    if (const char* e = getenv("GF_SCREEN")) idx->screen_version = atoi(e) == 1 ? 1 : 2;
+    if (const char* e = getenv("GF_SCREEN")) { int v = atoi(e); if (v >= 1 && v <= 3) idx->screen_version = v; }
     int rc = GF_OK;
     do {
         cudaDeviceProp prop;
@@ -405,6 +405,7 @@ int gf_fast_merge(gf_index* idx, const gf_batch* in, gf_merge_info* out) {
     db.base2 = b2;
     db.bytes1 = e1 - b1;
     db.bytes2 = e2 - b2;
+    db.max_len = in->max_len;
     rc = gf_fast_merge_device(idx, db, s.out.as<gf_merge_info>(), st);
     if (rc != GF_OK) return rc;
     GF_CUDA_TRY(cudaMemcpyAsync(out, s.out.p, sizeof(gf_merge_info) * n, cudaMemcpyDeviceToHost, st));

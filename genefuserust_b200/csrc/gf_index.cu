@@ -17,6 +17,7 @@
  */
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "gf_internal.h"
@@ -494,8 +495,10 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     GF_CUDA_TRY(cudaMemsetAsync(idx->d_table, 0xFF, n_buckets * 32, st));
     GF_CUDA_TRY(cudaMalloc(&idx->d_dupes, sizeof(uint32_t) * ((size_t)n_dupes + 8)));
     unsigned int* d_maxdisp = (unsigned int*)(d_stats + 6);
-    /* blocked Bloom filter, ~12 bits per key (rounded up to whole 64-bit words, at least 1024 words) */
-    const uint32_t filter_words = (uint32_t)std::max<uint64_t>(1024, (n_keys * 12 + 63) / 64);
+    /* blocked Bloom filter, GF_FILTER_BITS (default 8: the filter must stay L2-resident next to the gene planes) bits per key, whole 64-bit words, at least 1024 words */
+    int filter_bits = 8;
+    if (const char* e = getenv("GF_FILTER_BITS")) { int v = atoi(e); if (v >= 4 && v <= 32) filter_bits = v; }
+    const uint32_t filter_words = (uint32_t)std::max<uint64_t>(1024, (n_keys * (uint64_t)filter_bits + 63) / 64);
     GF_CUDA_TRY(cudaMalloc(&idx->d_filter, sizeof(unsigned long long) * filter_words));
     GF_CUDA_TRY(cudaMemsetAsync(idx->d_filter, 0, sizeof(unsigned long long) * filter_words, st));
     if (n_items) {

@@ -93,7 +93,8 @@ struct gf_index {
     gf_map_stats stats{};
     unsigned long long launches = 0;
     int sm_count = 148;
-    int screen_version = 2; /* 1 = HBM hash probe per k-mer, 2 = L2-resident filter + gene planes (GF_SCREEN) */
+    int screen_version = 3; /* GF_SCREEN: 1 = HBM hash probe per k-mer (warp per pair), 2 = L2-resident filter + gene
+                               planes (warp per pair), 3 = same, thread per pair for reads <= 256 bases (else falls back to 2) */
 };
 
 /* gf_index.cu */

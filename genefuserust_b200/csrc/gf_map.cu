@@ -579,6 +579,8 @@ __device__ __forceinline__ bool screen_sequence2(const GfDevIndex& ix, ScreenWar
     return T >= need_total && (T - c_d) >= need_minor;
 }
 
+#include "gf_screen_tpp.cuh"
+
 template <int MAXW, bool PAIRED, int VERSION>
 __global__ void __launch_bounds__(256, 3) k_screen(ScreenParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1180,7 +1182,21 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
         GF_CUDA_TRY(set_smem(k_screen<W, PE, VER>, smem));                   \
         k_screen<W, PE, VER><<<grid, threads, smem, st>>>(sp);               \
     } while (0)
-        if (idx->screen_version == 1) {
+        if (idx->screen_version == 3 && small) {
+            /* thread per pair: 4 warps x (81 | 123) private words x 32 lanes of shared memory per block */
+            const bool w5 = b.max_len <= 160;
+            const size_t tsm = sizeof(uint32_t) * tpp::WARPS * (w5 ? tpp::Lay<5>::NWORDS : tpp::Lay<8>::NWORDS) * 32;
+            const uint64_t want_b = (b.n + tpp::WARPS * 32 - 1) / (tpp::WARPS * 32);
+            const unsigned tgrid = (unsigned)std::min<uint64_t>(want_b, (uint64_t)idx->sm_count * (w5 ? 5 : 3));
+#define GF_LAUNCH_TPP(WW, PE)                                                              \
+    do {                                                                                   \
+        GF_CUDA_TRY(set_smem(tpp::k_screen_tpp<WW, PE>, tsm));                             \
+        tpp::k_screen_tpp<WW, PE><<<tgrid, tpp::WARPS * 32, tsm, st>>>(sp);                \
+    } while (0)
+            if (w5) { if (paired) GF_LAUNCH_TPP(5, true); else GF_LAUNCH_TPP(5, false); }
+            else { if (paired) GF_LAUNCH_TPP(8, true); else GF_LAUNCH_TPP(8, false); }
+#undef GF_LAUNCH_TPP
+        } else if (idx->screen_version == 1) {
             if (small) { if (paired) GF_LAUNCH_SCREEN(8, true, 1); else GF_LAUNCH_SCREEN(8, false, 1); }
             else { if (paired) GF_LAUNCH_SCREEN(32, true, 1); else GF_LAUNCH_SCREEN(32, false, 1); }
         } else {
@@ -1234,6 +1250,20 @@ int gf_fast_merge_device(gf_index* idx, const GfDevBatch& b, gf_merge_info* d_ou
     if (!b.n) return GF_OK;
     GF_CUDA_TRY(idx->ws_counters.reserve(sizeof(GfMapCounters)));
     GF_CUDA_TRY(cudaMemsetAsync(idx->ws_counters.p, 0, sizeof(GfMapCounters), st));
+    if (idx->screen_version == 3 && b.max_len != 0 && b.max_len <= 256) {
+        const bool w5 = b.max_len <= 160;
+        const size_t tsm = sizeof(uint32_t) * tpp::WARPS * (w5 ? tpp::Lay<5>::NWORDS : tpp::Lay<8>::NWORDS) * 32;
+        unsigned tgrid = (unsigned)std::min<uint64_t>((b.n + tpp::WARPS * 32 - 1) / (tpp::WARPS * 32), (uint64_t)idx->sm_count * 3);
+        if (w5) {
+            GF_CUDA_TRY(set_smem(tpp::k_merge_only_tpp<5>, tsm));
+            tpp::k_merge_only_tpp<5><<<tgrid, tpp::WARPS * 32, tsm, st>>>(b, d_out, idx->ws_counters.as<GfMapCounters>());
+        } else {
+            GF_CUDA_TRY(set_smem(tpp::k_merge_only_tpp<8>, tsm));
+            tpp::k_merge_only_tpp<8><<<tgrid, tpp::WARPS * 32, tsm, st>>>(b, d_out, idx->ws_counters.as<GfMapCounters>());
+        }
+        GF_CUDA_TRY(cudaGetLastError());
+        return GF_OK;
+    }
     const int threads = 256, warps = 8;
     const size_t smem = sizeof(ScreenWarp<32>) * warps;
     GF_CUDA_TRY(set_smem(k_merge_only<32>, smem));
