@@ -16,6 +16,7 @@
  * so "bitmap hit" == "key present in the table".
  */
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -363,7 +364,23 @@ __global__ void k_lookup(GfDevIndex ix, const uint32_t* __restrict__ kmers, uint
 }  // namespace
 
 /* ======================================================================================================= */
+namespace {
+struct PhaseTimer { /* GF_DEBUG_TIMING=1: host wall clock per build phase on stderr */
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    PhaseTimer() : on(getenv("GF_DEBUG_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[gf build] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+}  // namespace
+
 int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_genes) {
+    PhaseTimer pt;
     /* index_contig (:202-239): the 2nd occurrence always opens a dupe list of 2; occurrence n >= 3 is pushed
      * while the list holds < threshold sites  =>  NORMAL iff 2 <= n <= max(threshold, 2), HIGH beyond */
     const uint32_t thr = (uint32_t)std::max(idx->params.skip_key_dup_threshold, 2);
@@ -400,6 +417,7 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
         }
     }
 
+    pt.mark("host arena");
     cudaEvent_t e0, e1;
     GF_CUDA_TRY(cudaEventCreate(&e0));
     GF_CUDA_TRY(cudaEventCreate(&e1));
@@ -417,6 +435,7 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     }
     GF_CUDA_TRY(cudaEventRecord(e0, st));
 
+    pt.mark("upload genes");
     /* 1. flags -> positions -> compacted (key, site) items */
     const uint64_t n_flags = 2 * arena_len;
     uint32_t *d_flags = nullptr, *d_pos = nullptr, *d_tmp = nullptr;
@@ -439,6 +458,7 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     GF_CUDA_TRY(cudaFree(d_pos));
     GF_CUDA_TRY(cudaFree(d_tmp));
 
+    pt.mark("extract k-mers");
     /* 2. radix sort by key */
     if (n_items > 1) {
         const uint32_t n_tiles = (uint32_t)((n_items + RS_TILE - 1) / RS_TILE);
@@ -463,6 +483,7 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     }
     GF_CUDA_TRY(cudaFree(d_items2));
 
+    pt.mark("radix sort");
     /* 3. classify runs */
     uint32_t *d_ncnt = nullptr, *d_doff = nullptr, *d_tmp2 = nullptr;
     unsigned long long* d_stats = nullptr;
@@ -486,6 +507,7 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
         return GF_E_LIMIT;
     }
 
+    pt.mark("classify");
     /* 4. table */
     const uint64_t n_keys = h_stats[0];
     uint32_t bucket_bits = 6;
@@ -518,6 +540,7 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     GF_CUDA_TRY(cudaFree(d_tmp2));
     GF_CUDA_TRY(cudaFree(d_stats));
 
+    pt.mark("table + filter");
     idx->dev.table = (const uint4*)idx->d_table;
     idx->dev.dupes = (const uint32_t*)idx->d_dupes;
     idx->dev.gene_ascii = (const uint8_t*)idx->d_gene_ascii;
@@ -559,6 +582,7 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
 
+    pt.mark("gene planes + window class");
     gf_index_info& inf = idx->info;
     inf.n_sites = n_items;
     inf.n_keys = n_keys;

@@ -759,9 +759,9 @@ __device__ void revcomp_inplace(uint8_t* seq, int len) {
 /* ------------------------------------------------------------------------------------------------ */
 /* k_exact                                                                                           */
 constexpr int EX_SEQ_CAP = 2048 + 64;
-constexpr int EX_TBL_SMEM = 2048;       /* vote-table slots in shared memory */
+constexpr int EX_TBL_SMEM = 1024;       /* vote-table slots in shared memory (reads up to ~320 bases) */
 constexpr int EX_TBL_GLOBAL = 8192;     /* per-warp global fallback (long reads / many dupes) */
-constexpr int EX_WARPS = 2;
+constexpr int EX_WARPS = 4;
 constexpr long long EX_EMPTY_KEY = LLONG_MIN;
 
 struct ExactWarp {
@@ -1187,7 +1187,9 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
             const bool w5 = b.max_len <= 160;
             const size_t tsm = sizeof(uint32_t) * tpp::WARPS * (w5 ? tpp::Lay<5>::NWORDS : tpp::Lay<8>::NWORDS) * 32;
             const uint64_t want_b = (b.n + tpp::WARPS * 32 - 1) / (tpp::WARPS * 32);
-            const unsigned tgrid = (unsigned)std::min<uint64_t>(want_b, (uint64_t)idx->sm_count * (w5 ? 5 : 3));
+            int bps = w5 ? 5 : 3; /* resident blocks per SM the shared-memory columns allow */
+            if (const char* e = getenv("GF_TPP_BLOCKS")) { int v = atoi(e); if (v >= 1 && v <= bps) bps = v; }
+            const unsigned tgrid = (unsigned)std::min<uint64_t>(want_b, (uint64_t)idx->sm_count * bps);
 #define GF_LAUNCH_TPP(WW, PE)                                                              \
     do {                                                                                   \
         GF_CUDA_TRY(set_smem(tpp::k_screen_tpp<WW, PE>, tsm));                             \

@@ -57,68 +57,121 @@ __device__ __forceinline__ uint32_t load4_guarded(const uint8_t* p, const uint8_
 __device__ __forceinline__ uint32_t rev4(uint32_t n) { return __brev(n) >> 28; }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+/* 16-aligned 128-bit load, streaming (evict_first: the reads must not push the filter / gene planes out of L2);
+ * bytes outside [lo, hi) read as 0 */
+__device__ __forceinline__ uint4 load16_guarded(const uint8_t* p, const uint8_t* lo, const uint8_t* hi, unsigned long long pol_stream) {
+    if (p >= lo && p + 16 <= hi) {
+        uint4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol_stream));
+        return v;
+    }
+    return make_uint4(load4_guarded(p, lo, hi), load4_guarded(p + 4, lo, hi), load4_guarded(p + 8, lo, hi),
+                      load4_guarded(p + 12, lo, hi));
+}
+__device__ __forceinline__ unsigned long long make_policy_stream() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+/* Both converters read 16 aligned bytes per step.  With a = misalignment of the read w.r.t. the 16-byte blocks,
+ * a = 4q + r: the r bytes are removed by funnel-shifting adjacent words, the 4q bases by building the planes at
+ * bit position u = p + 4q and emitting word w of the aligned plane as funnelshift(U[w], U[w+1], 4q). */
+
 /* R1 -> forward planes lo, hi, valid (upper-case ACGT), N */
 template <int W>
-__device__ __forceinline__ void convert_r1(const Col& c, const uint8_t* seq, int len, const uint8_t* lo, const uint8_t* hi) {
-    const uint32_t a4 = (uint32_t)((uintptr_t)seq & 3u);
-    const uint8_t* wp = seq - a4;
-    uint32_t cur = load4_guarded(wp, lo, hi);
-    uint32_t alo = 0, ahi = 0, av = 0, an = 0;
-    const int ng = (len + 3) >> 2;
-    int w = 0;
+__device__ __forceinline__ void convert_r1(const Col& c, const uint8_t* seq, int len, const uint8_t* lo, const uint8_t* hi,
+                                           unsigned long long pol_stream) {
+    const uint32_t a = (uint32_t)((uintptr_t)seq & 15u), q4 = a & ~3u /* 4q */, r8 = 8u * (a & 3u);
+    const uint8_t* bp = seq - a;
+    const int nu = len + (int)q4;           /* u positions in use: [4q, nu) */
+    const int nblocks = (nu + 15) >> 4;
+    uint4 cur = load16_guarded(bp, lo, hi, pol_stream);
+    uint32_t alo = 0, ahi = 0, av = 0, an = 0; /* U word being filled */
+    uint32_t plo = 0, phi = 0, pv = 0, pn = 0; /* previous U word */
+    int m = 0;                                 /* index of the U word being filled */
 #pragma unroll 1
-    for (int g = 0; g < ng; g++) {
-        uint32_t nxt = load4_guarded(wp + 4 * g + 4, lo, hi);
-        uint32_t x = __funnelshift_r(cur, nxt, 8u * a4);
+    for (int b = 0; b < nblocks; b++) {
+        uint4 nxt = load16_guarded(bp + 16 * (b + 1), lo, hi, pol_stream);
+        uint32_t x[4] = {__funnelshift_r(cur.x, cur.y, r8), __funnelshift_r(cur.y, cur.z, r8),
+                         __funnelshift_r(cur.z, cur.w, r8), __funnelshift_r(cur.w, nxt.x, r8)};
         cur = nxt;
-        uint32_t l, h, v;
-        classify4(x, false, &l, &h, &v);
-        uint32_t n = gather4(zero_bytes(x ^ 0x4E4E4E4Eu) >> 7);
-        int rem = len - 4 * g;
-        if (rem < 4) { uint32_t m = (1u << rem) - 1u; l &= m; h &= m; v &= m; n &= m; }
-        uint32_t sh = (4u * (uint32_t)g) & 31u;
-        alo |= l << sh; ahi |= h << sh; av |= v << sh; an |= n << sh;
-        if (sh == 28u || g == ng - 1) {
-            c(Lay<W>::R1LO, w) = alo; c(Lay<W>::R1HI, w) = ahi; c(Lay<W>::R1V, w) = av; c(Lay<W>::R1N, w) = an;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int u0 = 16 * b + 4 * j; /* u of the first base of this group */
+            uint32_t l, h, v;
+            classify4(x[j], false, &l, &h, &v);
+            uint32_t n = gather4(zero_bytes(x[j] ^ 0x4E4E4E4Eu) >> 7);
+            int rem = nu - u0;
+            uint32_t msk = u0 < (int)q4 ? 0u : (rem >= 4 ? 0xFu : (rem > 0 ? (1u << rem) - 1u : 0u));
+            uint32_t sh = (uint32_t)u0 & 31u;
+            alo |= (l & msk) << sh; ahi |= (h & msk) << sh; av |= (v & msk) << sh; an |= (n & msk) << sh;
+        }
+        if ((b & 1) || b == nblocks - 1) { /* U word m complete */
+            if (m > 0 && m - 1 <= W) {
+                c(Lay<W>::R1LO, m - 1) = __funnelshift_r(plo, alo, q4); c(Lay<W>::R1HI, m - 1) = __funnelshift_r(phi, ahi, q4);
+                c(Lay<W>::R1V, m - 1) = __funnelshift_r(pv, av, q4);    c(Lay<W>::R1N, m - 1) = __funnelshift_r(pn, an, q4);
+            }
+            plo = alo; phi = ahi; pv = av; pn = an;
             alo = ahi = av = an = 0;
-            w++;
+            m++;
         }
     }
-    for (; w <= W; w++) { c(Lay<W>::R1LO, w) = 0; c(Lay<W>::R1HI, w) = 0; c(Lay<W>::R1V, w) = 0; c(Lay<W>::R1N, w) = 0; }
+    if (m > 0 && m - 1 <= W) {
+        c(Lay<W>::R1LO, m - 1) = plo >> q4; c(Lay<W>::R1HI, m - 1) = phi >> q4; c(Lay<W>::R1V, m - 1) = pv >> q4; c(Lay<W>::R1N, m - 1) = pn >> q4;
+    }
+    for (int w = m; w <= W; w++) { c(Lay<W>::R1LO, w) = 0; c(Lay<W>::R1HI, w) = 0; c(Lay<W>::R1V, w) = 0; c(Lay<W>::R1N, w) = 0; }
 }
 
 /* R2 -> planes of reverse_complement(R2) (case-insensitive, sequence.rs:52-60) + the case-sensitive validity of
- * the same bases (Lay<W>::VCS, in rc orientation), produced by walking R2 from its last base backwards */
+ * the same bases (VCS, in rc orientation), produced by walking R2 from its last byte downwards */
 template <int W>
-__device__ __forceinline__ void convert_r2_rc(const Col& c, const uint8_t* seq, int len, const uint8_t* lo, const uint8_t* hi) {
-    const uint8_t* p0 = seq + len - 4; /* bytes of rc group 0 = R2[len-4 .. len-1] */
-    const uint32_t a4 = (uint32_t)((uintptr_t)p0 & 3u);
-    const uint8_t* wp = p0 - a4;
-    uint32_t up = a4 ? load4_guarded(wp + 4, lo, hi) : 0u; /* word above the current one */
-    uint32_t alo = 0, ahi = 0, av = 0, ac = 0;
-    const int ng = (len + 3) >> 2;
-    int w = 0;
+__device__ __forceinline__ void convert_r2_rc(const Col& c, const uint8_t* seq, int len, const uint8_t* lo, const uint8_t* hi,
+                                              unsigned long long pol_stream) {
+    const uint8_t* end = seq + len;
+    const uint32_t pad = (uint32_t)((16u - ((uintptr_t)end & 15u)) & 15u); /* garbage bytes above the last base */
+    const uint32_t q4 = pad & ~3u, r = pad & 3u;
+    const uint8_t* top = end + pad;           /* 16-aligned */
+    const int nu = len + (int)q4;
+    const int nblocks = (nu + 15) >> 4;
+    uint4 cur = load16_guarded(top - 16, lo, hi, pol_stream);
+    uint32_t alo = 0, ahi = 0, av = 0, ac = 0, plo = 0, phi = 0, pv = 0, pc = 0;
+    int m = 0;
+    const uint32_t s8 = 8u * (4u - r); /* 32 when r == 0: __funnelshift_rc clamps and returns the upper word */
 #pragma unroll 1
-    for (int g = 0; g < ng; g++) {
-        uint32_t cur = load4_guarded(wp - 4 * g, lo, hi);
-        uint32_t x = __funnelshift_r(cur, up, 8u * a4);
-        up = cur;
-        uint32_t l, h, v, l2, h2, vcs;
-        classify4(x, true, &l, &h, &v);
-        classify4(x, false, &l2, &h2, &vcs);
-        /* byte t of x is R2[len-4-4g+t] = rc position 4g+3-t: reverse the nibbles; complement = code ^ 1 */
-        uint32_t rv = rev4(v), rl = ~rev4(l) & rv, rh = rev4(h), rc = rev4(vcs);
-        int rem = len - 4 * g;
-        if (rem < 4) { uint32_t m = (1u << rem) - 1u; rl &= m; rh &= m; rv &= m; rc &= m; }
-        uint32_t sh = (4u * (uint32_t)g) & 31u;
-        alo |= rl << sh; ahi |= rh << sh; av |= rv << sh; ac |= rc << sh;
-        if (sh == 28u || g == ng - 1) {
-            c(Lay<W>::C2LO, w) = alo; c(Lay<W>::C2HI, w) = ahi; c(Lay<W>::C2V, w) = av; c(Lay<W>::VCS, w) = ac;
+    for (int b = 0; b < nblocks; b++) {
+        uint4 nxt = load16_guarded(top - 16 * (b + 2), lo, hi, pol_stream);
+        uint32_t x[4] = {__funnelshift_rc(cur.z, cur.w, s8), __funnelshift_rc(cur.y, cur.z, s8),
+                         __funnelshift_rc(cur.x, cur.y, s8), __funnelshift_rc(nxt.w, cur.x, s8)};
+        cur = nxt;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int u0 = 16 * b + 4 * j;
+            uint32_t l, h, v, l2, h2, vcs;
+            classify4(x[j], true, &l, &h, &v);
+            classify4(x[j], false, &l2, &h2, &vcs);
+            /* byte t of x[j] has u = u0 + 3 - t: reverse the nibbles; complement = code ^ 1 */
+            uint32_t rv = rev4(v), rl = ~rev4(l) & rv, rh = rev4(h), rcs = rev4(vcs);
+            int rem = nu - u0;
+            uint32_t msk = u0 < (int)q4 ? 0u : (rem >= 4 ? 0xFu : (rem > 0 ? (1u << rem) - 1u : 0u));
+            uint32_t sh = (uint32_t)u0 & 31u;
+            alo |= (rl & msk) << sh; ahi |= (rh & msk) << sh; av |= (rv & msk) << sh; ac |= (rcs & msk) << sh;
+        }
+        if ((b & 1) || b == nblocks - 1) {
+            if (m > 0 && m - 1 <= W) {
+                c(Lay<W>::C2LO, m - 1) = __funnelshift_r(plo, alo, q4); c(Lay<W>::C2HI, m - 1) = __funnelshift_r(phi, ahi, q4);
+                c(Lay<W>::C2V, m - 1) = __funnelshift_r(pv, av, q4);    c(Lay<W>::VCS, m - 1) = __funnelshift_r(pc, ac, q4);
+            }
+            plo = alo; phi = ahi; pv = av; pc = ac;
             alo = ahi = av = ac = 0;
-            w++;
+            m++;
         }
     }
-    for (; w <= W; w++) { c(Lay<W>::C2LO, w) = 0; c(Lay<W>::C2HI, w) = 0; c(Lay<W>::C2V, w) = 0; c(Lay<W>::VCS, w) = 0; }
+    if (m > 0 && m - 1 <= W) {
+        c(Lay<W>::C2LO, m - 1) = plo >> q4; c(Lay<W>::C2HI, m - 1) = phi >> q4; c(Lay<W>::C2V, m - 1) = pv >> q4; c(Lay<W>::VCS, m - 1) = pc >> q4;
+    }
+    for (int w = m; w <= W; w++) { c(Lay<W>::C2LO, w) = 0; c(Lay<W>::C2HI, w) = 0; c(Lay<W>::C2V, w) = 0; c(Lay<W>::VCS, w) = 0; }
 }
 
 /* mismatch mask of overlap chunk k for overlap length olen (read.rs:346) */
@@ -340,7 +393,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_screen_tpp(ScreenParams P) {
     c.base = sm + (size_t)wib * Lay<W>::NWORDS * 32 + lane;
     const GfDevBatch& B = P.b;
     const uint64_t n_warps = (uint64_t)gridDim.x * WARPS;
-    const unsigned long long pol = make_policy_keep();
+    const unsigned long long pol = make_policy_keep(), pol_stream = make_policy_stream();
     const uint8_t* const NOBOUND = reinterpret_cast<const uint8_t*>(~(uintptr_t)0);
     const uint8_t* bound1 = B.bytes1 ? B.seq1 + B.bytes1 : NOBOUND;
     const uint8_t* bound2 = (PAIRED && B.bytes2) ? B.seq2 + B.bytes2 : NOBOUND;
@@ -377,10 +430,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_screen_tpp(ScreenParams P) {
             if (len1 > 32 * W || len2 > 32 * W || len1 < 0 || len2 < 0) {
                 err |= 1u;
             } else {
-                convert_r1<W>(c, s1, len1, B.seq1, bound1);
+                convert_r1<W>(c, s1, len1, B.seq1, bound1, pol_stream);
                 int olen = -1, diff = 0;
                 if (PAIRED) {
-                    convert_r2_rc<W>(c, s2, len2, B.seq2, bound2);
+                    convert_r2_rc<W>(c, s2, len2, B.seq2, bound2, pol_stream);
                     olen = find_overlap<W>(c, len1, len2, q1, q2, &diff);
                 }
                 const int nseq = olen >= 0 ? 1 : (PAIRED ? 2 : 1);
@@ -442,8 +495,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_merge_only_tpp(GfDevBatch B, gf_
         const uint64_t o1 = B.off1[p], o2 = B.off2[p];
         const int len1 = (int)(B.off1[p + 1] - o1), len2 = (int)(B.off2[p + 1] - o2);
         if (len1 > 32 * W || len2 > 32 * W) { atomicOr(&counters->error_flags, 1u); continue; }
-        convert_r1<W>(c, B.seq1 + (o1 - B.base1), len1, B.seq1, B.seq1 + B.bytes1);
-        convert_r2_rc<W>(c, B.seq2 + (o2 - B.base2), len2, B.seq2, B.seq2 + B.bytes2);
+        convert_r1<W>(c, B.seq1 + (o1 - B.base1), len1, B.seq1, B.seq1 + B.bytes1, make_policy_stream());
+        convert_r2_rc<W>(c, B.seq2 + (o2 - B.base2), len2, B.seq2, B.seq2 + B.bytes2, make_policy_stream());
         int diff = 0;
         int olen = find_overlap<W>(c, len1, len2, B.qual1 + (o1 - B.base1), B.qual2 + (o2 - B.base2), &diff);
         gf_merge_info mi;

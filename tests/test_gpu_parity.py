@@ -269,3 +269,32 @@ def test_golden_fixture_matches(host):
     got = [list(r.astuple()) for r in m.scan_pair_end(batch)]
     assert got == g["matches"]
     m.close()
+
+
+def test_full_size_properties(host):
+    """BASELINE-size check: 4 M pairs of the bench workload against the full-size panel — the whole record set is
+    compared with the oracle (it is tiny), plus size-independent properties: mapping twice gives the same records,
+    mapping two halves separately gives the union, every record satisfies the structural invariants."""
+    panel = synth.make_panel(scale=1.0)
+    n = 4_000_000
+    b = synth.generate_pairs(panel, n, read_len=150, seed=12)
+    m = host.FusionMapper.from_gene_spans(panel.genes(), device=0)
+    got = [r.astuple() for r in m.scan_pair_end(b)]
+    assert got == [r.astuple() for r in m.scan_pair_end(b)]                       # idempotent
+    half = n // 2
+    lo = [r.astuple() for r in m.scan_pair_end(b.slice(0, half))]
+    hi = [r.astuple() for r in m.scan_pair_end(b.slice(half, n))]
+    assert got == lo + [(r[0] + half,) + r[1:] for r in hi]                       # shard-invariant
+    assert got == sorted(got, key=lambda r: (r[0], r[1]))                         # (pair_idx, source) order
+    for r in got:
+        pair, source, used_rc, reversed_, rb, lc, lp, rc, rp, gap, ld, rd, slen, olen, diff = r
+        assert 0 <= pair < n and source in (0, 1, 2) and 0 <= rb < slen
+        assert reversed_ == (1 if (used_rc and source != 0) else 0)
+        assert (olen >= 30) == (source == 0) and 0 <= diff <= 2
+        assert 0 <= lc < panel.n_genes and 0 <= rc < panel.n_genes
+    o = orc.OracleIndex(panel.genes())
+    want = o.scan(b, threads=os.cpu_count() or 8)
+    assert len(want) > 1000
+    assert got == want
+    m.close()
+    o.close()
