@@ -309,8 +309,12 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         assert int(n_out.value) == n_matches, (n_out.value, n_matches)
+        hs = gf_map_stats()
+        lib.gf_get_map_stats(h, C.byref(hs))
         e2e = {"value": world * P * e2e_steps / float(tt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": 4 * P * L + 2 * 8 * (P + 1), "d2h_bytes_per_step": int(n_out.value) * 48 + 2 * 160,
+               "h2d_bytes_per_step": int(hs.h2d_bytes), "d2h_bytes_per_step": int(hs.d2h_bytes),
+               "zero_copy_qualities": bool(hs.zero_copy_qual),
+               "host_buffer_bytes_per_step": 4 * P * L + 2 * 8 * (P + 1),
                "steps": e2e_steps, "timing": "host wall clock around the synchronous C-ABI call, max over ranks"}
 
     if rank != 0:

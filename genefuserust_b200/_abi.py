@@ -124,6 +124,10 @@ class gf_map_stats(C.Structure):
         ("ms_merge", C.c_float),
         ("ms_screen", C.c_float),
         ("ms_exact", C.c_float),
+        ("h2d_bytes", C.c_uint64),
+        ("d2h_bytes", C.c_uint64),
+        ("zero_copy_qual", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 

@@ -209,25 +209,48 @@ int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_
     n_chunks = (n + per - 1) / per;
 
     const unsigned long long launches0 = idx->launches;
-    uint64_t total_out = 0;
+    uint64_t total_out = 0, h2d = 0, d2h = 0;
     bool panic = false;
     GF_CUDA_TRY(cudaEventRecord(idx->ev_start, idx->stream));
+
+    /* qualities: zero-copy when they live in pinned host memory and the on-demand kernel (thread per pair) runs */
+    const uint8_t *zq1 = nullptr, *zq2 = nullptr;
+    {
+        const char* e = getenv("GF_ZEROCOPY_QUAL");
+        bool want = !(e && atoi(e) == 0) && idx->screen_version == 3 && in->max_len != 0 && in->max_len <= 256;
+        auto mapped = [](const void* p) -> const uint8_t* {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            return at.type == cudaMemoryTypeHost ? (const uint8_t*)at.devicePointer : nullptr;
+        };
+        if (want) {
+            zq1 = mapped(in->qual1);
+            zq2 = pe ? mapped(in->qual2) : nullptr;
+            if (!zq1 || (pe && !zq2)) zq1 = zq2 = nullptr;
+        }
+    }
+    const bool zc = zq1 != nullptr;
+    idx->stats.zero_copy_qual = zc ? 1u : 0u;
 
     auto issue = [&](uint64_t k) -> int {
         GfStage& s = idx->stage[k & 1];
         const uint64_t lo = k * per, hi = std::min(n, lo + per), cn = hi - lo;
         const uint64_t b1 = off1[lo], e1 = off1[hi];
         GF_CUDA_TRY(s.seq1.reserve(e1 - b1 + 16));
-        GF_CUDA_TRY(s.qual1.reserve(e1 - b1 + 16));
         GF_CUDA_TRY(s.off1.reserve(sizeof(uint64_t) * (cn + 1)));
         cudaStream_t cs = idx->copy_stream;
         GF_CUDA_TRY(cudaMemcpyAsync(s.seq1.p, in->seq1 + b1, e1 - b1, cudaMemcpyHostToDevice, cs));
-        GF_CUDA_TRY(cudaMemcpyAsync(s.qual1.p, in->qual1 + b1, e1 - b1, cudaMemcpyHostToDevice, cs));
+        if (!zc) {
+            GF_CUDA_TRY(s.qual1.reserve(e1 - b1 + 16));
+            GF_CUDA_TRY(cudaMemcpyAsync(s.qual1.p, in->qual1 + b1, e1 - b1, cudaMemcpyHostToDevice, cs));
+            h2d += e1 - b1;
+        }
         GF_CUDA_TRY(cudaMemcpyAsync(s.off1.p, off1 + lo, sizeof(uint64_t) * (cn + 1), cudaMemcpyHostToDevice, cs));
+        h2d += (e1 - b1) + sizeof(uint64_t) * (cn + 1);
         GfDevBatch db{};
         db.n = cn;
         db.seq1 = s.seq1.as<uint8_t>();
-        db.qual1 = s.qual1.as<uint8_t>();
+        db.qual1 = zc ? zq1 + b1 : s.qual1.as<uint8_t>(); /* kernels address it as qual1 + (off - base1) */
         db.off1 = s.off1.as<uint64_t>();
         db.base1 = b1;
         db.bytes1 = e1 - b1;
@@ -236,13 +259,17 @@ int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_
         if (pe) {
             const uint64_t b2 = off2[lo], e2 = off2[hi];
             GF_CUDA_TRY(s.seq2.reserve(e2 - b2 + 16));
-            GF_CUDA_TRY(s.qual2.reserve(e2 - b2 + 16));
             GF_CUDA_TRY(s.off2.reserve(sizeof(uint64_t) * (cn + 1)));
             GF_CUDA_TRY(cudaMemcpyAsync(s.seq2.p, in->seq2 + b2, e2 - b2, cudaMemcpyHostToDevice, cs));
-            GF_CUDA_TRY(cudaMemcpyAsync(s.qual2.p, in->qual2 + b2, e2 - b2, cudaMemcpyHostToDevice, cs));
+            if (!zc) {
+                GF_CUDA_TRY(s.qual2.reserve(e2 - b2 + 16));
+                GF_CUDA_TRY(cudaMemcpyAsync(s.qual2.p, in->qual2 + b2, e2 - b2, cudaMemcpyHostToDevice, cs));
+                h2d += e2 - b2;
+            }
             GF_CUDA_TRY(cudaMemcpyAsync(s.off2.p, off2 + lo, sizeof(uint64_t) * (cn + 1), cudaMemcpyHostToDevice, cs));
+            h2d += (e2 - b2) + sizeof(uint64_t) * (cn + 1);
             db.seq2 = s.seq2.as<uint8_t>();
-            db.qual2 = s.qual2.as<uint8_t>();
+            db.qual2 = zc ? zq2 + b2 : s.qual2.as<uint8_t>();
             db.off2 = s.off2.as<uint64_t>();
             db.base2 = b2;
             db.bytes2 = e2 - b2;
@@ -274,8 +301,11 @@ int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_
         accumulate(idx->stats, *h);
         if (h->counters.n_ref_panic) panic = true;
         const uint64_t cnt = h->n_out; /* <= s.out_cap by construction */
-        if (cnt && total_out + cnt <= out_cap)
+        if (cnt && total_out + cnt <= out_cap) {
             GF_CUDA_TRY(cudaMemcpy(out + total_out, s.out.p, sizeof(gf_match) * cnt, cudaMemcpyDeviceToHost));
+            d2h += sizeof(gf_match) * cnt;
+        }
+        d2h += sizeof(GfMapCounters) + sizeof(unsigned long long);
         total_out += cnt;
         return GF_OK;
     };
@@ -296,6 +326,8 @@ int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_
     GF_CUDA_TRY(cudaEventElapsedTime(&ms, idx->ev_start, idx->ev_end));
     idx->stats.ms_total = ms;
     idx->stats.kernel_launches = idx->launches - launches0;
+    idx->stats.h2d_bytes = h2d;
+    idx->stats.d2h_bytes = d2h;
     *n_out = total_out;
     if (total_out > out_cap) return fail(GF_E_CAPACITY, "out_cap too small; *n_out holds the required count");
     gf_sort_matches(out, total_out);

@@ -161,6 +161,11 @@ typedef struct gf_map_stats {
     float ms_merge;
     float ms_screen;
     float ms_exact;
+    uint64_t h2d_bytes;      /* bytes gf_map_pairs copied host -> device (0 for gf_map_pairs_device) */
+    uint64_t d2h_bytes;      /* bytes copied device -> host */
+    uint32_t zero_copy_qual; /* 1 = the quality arenas were pinned host memory and were NOT copied: the kernels
+                                read the few quality bytes fast_merge depends on directly over PCIe */
+    uint32_t reserved;
 } gf_map_stats;
 
 const char* gf_last_error(void);
@@ -178,7 +183,12 @@ int gf_index_lookup(gf_index* idx, const uint32_t* kmers, uint64_t n, gf_lookup*
 
 /* Map a batch held in HOST memory: H2D copy, merge, screen, exact path,
  * verification, D2H of the match records.  SE when in->seq2 == NULL.
- * Returns GF_E_CAPACITY (and *n_out = needed) when out_cap is too small. */
+ * Returns GF_E_CAPACITY (and *n_out = needed) when out_cap is too small.
+ * Pinned (page-locked) arenas make the copies asynchronous; when the quality
+ * arenas are pinned and reads are <= 256 bases they are not copied at all
+ * (fast_merge reads a quality byte only where R1 and rc(R2) disagree inside a
+ * candidate overlap; those bytes are fetched on demand).  GF_ZEROCOPY_QUAL=0
+ * in the environment disables this. */
 int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_cap, uint64_t* n_out);
 
 /* Same on a batch already resident in DEVICE memory of the index's device.

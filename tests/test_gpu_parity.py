@@ -298,3 +298,22 @@ def test_full_size_properties(host):
     assert got == want
     m.close()
     o.close()
+
+
+def test_zero_copy_qualities_pinned(mappers, small_panel):
+    """pinned host arenas: qualities are not copied, the kernels fetch the few bytes fast_merge needs over PCIe;
+    results must be identical to the staged path and to the oracle"""
+    import torch
+    m, o = mappers
+    b = synth.generate_pairs(small_panel, 50000, read_len=150, seed=41, p_fusion=0.05, sub_rate=0.01)
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    bp = ReadBatch(pin(b.seq1), pin(b.qual1), pin(b.off1.view(np.int64)).view(np.uint64),
+                   pin(b.seq2), pin(b.qual2), pin(b.off2.view(np.int64)).view(np.uint64))
+    want = o.scan(b, threads=8)
+    got_staged = m.scan_pair_end(b)
+    assert m.map_stats().zero_copy_qual == 0
+    got_zc = m.scan_pair_end(bp)
+    st = m.map_stats()
+    assert st.zero_copy_qual == 1 and st.h2d_bytes < 0.6 * (4 * b.n * 150)
+    assert_same_matches(got_staged, want, "staged")
+    assert_same_matches(got_zc, want, "zero-copy")
