@@ -317,3 +317,31 @@ def test_zero_copy_qualities_pinned(mappers, small_panel):
     assert st.zero_copy_qual == 1 and st.h2d_bytes < 0.6 * (4 * b.n * 150)
     assert_same_matches(got_staged, want, "staged")
     assert_same_matches(got_zc, want, "zero-copy")
+
+
+def test_list_mode_concurrent_handles(host, small_panel):
+    """multi-CSV list mode (fusion_scan.rs:62-188): one index per CSV, used concurrently from different host
+    threads over the same reads; handles are independent, every result must equal the oracle's for its panel"""
+    import threading
+    genes = small_panel.genes()
+    panels = [genes, genes[:40], genes[20:90], genes[::2]]
+    b = synth.generate_pairs(small_panel, 40000, read_len=150, seed=52, p_fusion=0.05)
+    mappers = [host.FusionMapper.from_gene_spans(p, device=0) for p in panels]
+    results = [None] * len(panels)
+
+    def work(k):
+        for _ in range(3):
+            results[k] = [r.astuple() for r in mappers[k].scan_pair_end(b)]
+    ths = [threading.Thread(target=work, args=(k,)) for k in range(len(panels))]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    for k, p in enumerate(panels):
+        o = orc.OracleIndex(p)
+        want = o.scan(b, threads=8)
+        assert results[k] == want, k
+        o.close()
+    assert len({len(r) for r in results}) > 1   # the panels really give different answers
+    for m in mappers:
+        m.close()

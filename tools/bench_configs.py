@@ -1,0 +1,134 @@
+#!/usr/bin/env python3
+"""Secondary configs of BASELINE.json (not the bench.py contract): the read-length sweep (config 5) and the
+multi-CSV list mode (config 4), device-timed on one B200, each checked against the CPU oracle on a sample.
+
+  python tools/bench_configs.py --sweep 75:50000000 250:50000000     # read_len:pairs
+  python tools/bench_configs.py --list 16 --pairs 10000000
+Prints one JSON line per config."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def device_batch(torch, synth, panel, P, L, seed, threads):
+    pinned = [torch.empty(P * L, dtype=torch.uint8, pin_memory=True) for _ in range(4)]
+    batch = synth.generate_pairs(panel, P, read_len=L, seed=seed, threads=threads, out=tuple(t.numpy() for t in pinned))
+    d = [t.cuda(non_blocking=True) for t in pinned]
+    off = torch.arange(P + 1, dtype=torch.int64) * L
+    d_off = off.cuda()
+    torch.cuda.synchronize()
+    return batch, d, d_off
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sweep", nargs="*", default=[])
+    ap.add_argument("--list", type=int, default=0)
+    ap.add_argument("--pairs", type=int, default=10_000_000)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--oracle-sample", type=int, default=300_000)
+    a = ap.parse_args()
+    import torch
+    import __graft_entry__ as ge
+    ge.build()
+    import _oracle
+    from genefuserust_b200 import synth
+    from genefuserust_b200._abi import gf_batch, gf_map_stats, gf_match
+    from genefuserust_b200.host import FusionMapper
+    threads = os.cpu_count() or 8
+    panel = synth.make_panel(scale=1.0)
+    genes = panel.genes()
+    FusionMapper.from_gene_spans(genes[:4]).close()   # CUDA init / module load
+    seeds = {75: 11, 150: 12, 250: 13}
+
+    def run(mappers, d, d_off, P, L, steps):
+        out_cap = max(1 << 16, P // 4)
+        d_out = torch.empty(out_cap * C.sizeof(gf_match), dtype=torch.uint8, device="cuda")
+        d_n = torch.zeros(1, dtype=torch.int64, device="cuda")
+        db = gf_batch()
+        db.n = P
+        db.seq1, db.qual1, db.seq2, db.qual2 = (t.data_ptr() for t in d)
+        db.off1 = db.off2 = d_off.data_ptr()
+        db.bytes1 = db.bytes2 = P * L
+        db.max_len = L
+        st = torch.cuda.current_stream()
+        lib = mappers[0].lib
+
+        def one_pass():
+            n = 0
+            for m in mappers:
+                rc = lib.gf_map_pairs_device(m.m_indexer.h, C.byref(db), d_out.data_ptr(), out_cap, d_n.data_ptr(),
+                                             C.c_void_p(st.cuda_stream))
+                assert rc == 0, lib.gf_last_error()
+            return n
+        for _ in range(3):
+            one_pass()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(steps):
+            one_pass()
+        e1.record(st)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        s = gf_map_stats()
+        lib.gf_get_map_stats(mappers[-1].m_indexer.h, C.byref(s))
+        return ms, s, int(d_n.item())
+
+    for item in a.sweep:
+        L, P = (int(x) for x in item.split(":"))
+        batch, d, d_off = device_batch(torch, synth, panel, P, L, seeds.get(L, 12), threads)
+        m = FusionMapper.from_gene_spans(genes)
+        ms, s, n_matches = run([m], d, d_off, P, L, a.steps)
+        # parity + CPU rate on a sample
+        sample = batch.slice(0, min(a.oracle_sample, P))
+        o = _oracle.OracleIndex(genes)
+        t0 = time.perf_counter()
+        want = o.scan(sample, threads=threads)
+        cpu_dt = time.perf_counter() - t0
+        got = [r.astuple() for r in m.scan_pair_end(sample)]
+        alg = s.seq_bytes + 32 * s.n_probes_pass1
+        print(json.dumps({"config": f"read-length sweep 2x{L}bp, {P} pairs, cancer-shaped panel, 1 B200", "pairs_per_s": P / (ms / 1e3),
+                          "ms_per_step": ms, "screen_ms": s.ms_screen, "exact_verify_ms": s.ms_exact, "matches": n_matches,
+                          "survivors": int(s.n_survivors), "roofline_frac_of_6538.3": alg / (s.ms_screen / 1e3) / 1e9 / 6538.3,
+                          "parity_sample_pairs": sample.n, "parity_ok": got == want, "parity_matches": len(want),
+                          "cpu_oracle_pairs_per_s": sample.n / cpu_dt, "cpu_cores": threads}), flush=True)
+        assert got == want
+        m.close()
+        o.close()
+        del d, d_off, batch
+        torch.cuda.empty_cache()
+
+    if a.list:
+        # list mode: K fusion CSVs = K independent indices over the same reads (fusion_scan.rs:62-188); alternate the
+        # full panel and a 40-gene subset like benchmark_res/hg38_fusion_csv_list.txt alternates cancer/druggable
+        L, P = 150, a.pairs
+        batch, d, d_off = device_batch(torch, synth, panel, P, L, 12, threads)
+        sub = genes[:40]
+        mappers = [FusionMapper.from_gene_spans(genes if k % 2 == 0 else sub) for k in range(a.list)]
+        ms, s, _ = run(mappers, d, d_off, P, L, a.steps)
+        sample = batch.slice(0, min(a.oracle_sample, P))
+        ok = True
+        t0 = time.perf_counter()
+        for gset, m in ((genes, mappers[0]), (sub, mappers[1] if a.list > 1 else mappers[0])):
+            o = _oracle.OracleIndex(gset)
+            ok = ok and [r.astuple() for r in m.scan_pair_end(sample)] == o.scan(sample, threads=threads)
+            o.close()
+        print(json.dumps({"config": f"list mode: {a.list} fusion CSVs (alternating 136-gene / 40-gene panels) x {P} pairs 2x150, 1 B200",
+                          "ms_per_list_job": ms, "pairs_per_s_whole_list": P / (ms / 1e3),
+                          "pair_x_csv_per_s": P * a.list / (ms / 1e3), "parity_ok_on_sample": ok,
+                          "index_bytes_total": sum(int(m.m_indexer.info().device_bytes) for m in mappers)}), flush=True)
+        assert ok
+        for m in mappers:
+            m.close()
+
+
+if __name__ == "__main__":
+    main()
