@@ -51,6 +51,10 @@ void destroy_handle(gf_index* idx) {
     idx->ws_survivors.release();
     idx->ws_counters.release();
     idx->ws_gtbl.release();
+    idx->ws_seq_words.release();
+    idx->ws_seq_meta.release();
+    idx->ws_seq_seed.release();
+    idx->ws_seq_lists.release();
     for (auto& s : idx->stage) {
         s.seq1.release(); s.qual1.release(); s.off1.release();
         s.seq2.release(); s.qual2.release(); s.off2.release();
@@ -121,7 +125,7 @@ int gf_index_create(const gf_gene_span* genes, uint32_t n_genes, const gf_params
     gf_index* idx = new gf_index();
     idx->device = device;
     idx->params = p;
-    if (const char* e = getenv("GF_SCREEN")) { int v = atoi(e); if (v >= 1 && v <= 3) idx->screen_version = v; }
+    if (const char* e = getenv("GF_SCREEN")) { int v = atoi(e); if (v >= 1 && v <= 4) idx->screen_version = v; }
     int rc = GF_OK;
     do {
         cudaDeviceProp prop;
@@ -217,7 +221,7 @@ int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_
     const uint8_t *zq1 = nullptr, *zq2 = nullptr;
     {
         const char* e = getenv("GF_ZEROCOPY_QUAL");
-        bool want = !(e && atoi(e) == 0) && idx->screen_version == 3 && in->max_len != 0 && in->max_len <= 256;
+        bool want = !(e && atoi(e) == 0) && idx->screen_version >= 3 && in->max_len != 0 && in->max_len <= 256;
         auto mapped = [](const void* p) -> const uint8_t* {
             cudaPointerAttributes at;
             if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }

@@ -86,6 +86,7 @@ struct gf_index {
 
     /* mapping workspace (grow-only) */
     GfBuf ws_survivors, ws_counters, ws_gtbl;
+    GfBuf ws_seq_words, ws_seq_meta, ws_seq_seed, ws_seq_lists; /* split screen pipeline (gf_screen_split.cuh) */
     GfStage stage[2];
     GfHostSlot* h_slots = nullptr; /* [3]: two pipeline stages + the device-batch path */
     bool stats_pending = false;    /* h_slots[2] is being written by an unsynchronised device-batch call */
@@ -93,8 +94,9 @@ struct gf_index {
     gf_map_stats stats{};
     unsigned long long launches = 0;
     int sm_count = 148;
-    int screen_version = 3; /* GF_SCREEN: 1 = HBM hash probe per k-mer (warp per pair), 2 = L2-resident filter + gene
-                               planes (warp per pair), 3 = same, thread per pair for reads <= 256 bases (else falls back to 2) */
+    int screen_version = 4; /* GF_SCREEN: 1 = HBM hash probe per k-mer (warp per pair), 2 = L2-resident filter + gene
+                               planes (warp per pair), 3 = same, thread per pair for reads <= 256 bases (else falls back to 2),
+                               4 = thread per pair split into prep / seed / diag / scan kernels (default) */
 };
 
 /* gf_index.cu */

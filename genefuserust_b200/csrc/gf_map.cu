@@ -580,6 +580,7 @@ __device__ __forceinline__ bool screen_sequence2(const GfDevIndex& ix, ScreenWar
 }
 
 #include "gf_screen_tpp.cuh"
+#include "gf_screen_split.cuh"
 
 template <int MAXW, bool PAIRED, int VERSION>
 __global__ void __launch_bounds__(256, 3) k_screen(ScreenParams P) {
@@ -1182,7 +1183,65 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
         GF_CUDA_TRY(set_smem(k_screen<W, PE, VER>, smem));                   \
         k_screen<W, PE, VER><<<grid, threads, smem, st>>>(sp);               \
     } while (0)
-        if (idx->screen_version == 3 && small) {
+        if (idx->screen_version == 4 && small) {
+            /* split pipeline: prep -> seed -> diag / scan (gf_screen_split.cuh) */
+            const bool w5 = b.max_len <= 160;
+            const int NW3 = w5 ? split::SL<5>::NW3 : split::SL<8>::NW3;
+            const uint32_t cap = surv_cap;
+            const size_t groups = ((size_t)cap + 31) / 32;
+            GF_CUDA_TRY(idx->ws_seq_words.reserve(groups * NW3 * 32 * sizeof(uint32_t)));
+            GF_CUDA_TRY(idx->ws_seq_meta.reserve((size_t)cap * sizeof(uint4)));
+            GF_CUDA_TRY(idx->ws_seq_seed.reserve((size_t)cap * sizeof(uint2)));
+            GF_CUDA_TRY(idx->ws_seq_lists.reserve((size_t)cap * 2 * sizeof(uint32_t) + 64));
+            split::SeqStore ss;
+            ss.words = idx->ws_seq_words.as<uint32_t>();
+            ss.meta = idx->ws_seq_meta.as<uint4>();
+            ss.seed = idx->ws_seq_seed.as<uint2>();
+            ss.counters = idx->ws_seq_lists.as<unsigned int>();
+            ss.list_seeded = idx->ws_seq_lists.as<uint32_t>() + 16;
+            ss.list_unseeded = ss.list_seeded + cap;
+            ss.cap = cap;
+            GF_CUDA_TRY(cudaMemsetAsync(ss.counters, 0, 64, st));
+            split::PrepParams pp;
+            pp.b = b;
+            pp.st = ss;
+            pp.counters = d_cnt;
+            const size_t psm = sizeof(uint32_t) * tpp::WARPS * (w5 ? tpp::Lay<5>::MLO : tpp::Lay<8>::MLO) * 32;
+            const uint64_t want_b = (b.n + tpp::WARPS * 32 - 1) / (tpp::WARPS * 32);
+            const unsigned pgrid = (unsigned)std::min<uint64_t>(want_b, (uint64_t)idx->sm_count * (w5 ? 8 : 5));
+#define GF_LAUNCH_PREP(WW, PE)                                                             \
+    do {                                                                                   \
+        GF_CUDA_TRY(set_smem(split::k_prep<WW, PE>, psm));                                 \
+        split::k_prep<WW, PE><<<pgrid, tpp::WARPS * 32, psm, st>>>(pp);                    \
+    } while (0)
+            if (w5) { if (paired) GF_LAUNCH_PREP(5, true); else GF_LAUNCH_PREP(5, false); }
+            else { if (paired) GF_LAUNCH_PREP(8, true); else GF_LAUNCH_PREP(8, false); }
+#undef GF_LAUNCH_PREP
+            split::SeedParams sdp;
+            sdp.ix = idx->dev;
+            sdp.st = ss;
+            sdp.need_total = sp.need_total;
+            sdp.need_minor = sp.need_minor;
+            split::ClassParams cp;
+            cp.ix = idx->dev;
+            cp.st = ss;
+            cp.survivors = sp.survivors;
+            cp.survivors_cap = sp.survivors_cap;
+            cp.counters = d_cnt;
+            cp.need_total = sp.need_total;
+            cp.need_minor = sp.need_minor;
+            const unsigned cgrid = (unsigned)idx->sm_count * 8;
+            if (w5) {
+                split::k_seed<5><<<cgrid, 256, 0, st>>>(sdp);
+                split::k_diag<5><<<cgrid, 256, 0, st>>>(cp);
+                split::k_scan<5><<<cgrid, 256, 0, st>>>(cp);
+            } else {
+                split::k_seed<8><<<cgrid, 256, 0, st>>>(sdp);
+                split::k_diag<8><<<cgrid, 256, 0, st>>>(cp);
+                split::k_scan<8><<<cgrid, 256, 0, st>>>(cp);
+            }
+            idx->launches += 3;
+        } else if (idx->screen_version >= 3 && small) {
             /* thread per pair: 4 warps x (81 | 123) private words x 32 lanes of shared memory per block */
             const bool w5 = b.max_len <= 160;
             const size_t tsm = sizeof(uint32_t) * tpp::WARPS * (w5 ? tpp::Lay<5>::NWORDS : tpp::Lay<8>::NWORDS) * 32;
@@ -1252,7 +1311,7 @@ int gf_fast_merge_device(gf_index* idx, const GfDevBatch& b, gf_merge_info* d_ou
     if (!b.n) return GF_OK;
     GF_CUDA_TRY(idx->ws_counters.reserve(sizeof(GfMapCounters)));
     GF_CUDA_TRY(cudaMemsetAsync(idx->ws_counters.p, 0, sizeof(GfMapCounters), st));
-    if (idx->screen_version == 3 && b.max_len != 0 && b.max_len <= 256) {
+    if (idx->screen_version >= 3 && b.max_len != 0 && b.max_len <= 256) {
         const bool w5 = b.max_len <= 160;
         const size_t tsm = sizeof(uint32_t) * tpp::WARPS * (w5 ? tpp::Lay<5>::NWORDS : tpp::Lay<8>::NWORDS) * 32;
         unsigned tgrid = (unsigned)std::min<uint64_t>((b.n + tpp::WARPS * 32 - 1) / (tpp::WARPS * 32), (uint64_t)idx->sm_count * 3);

@@ -1,0 +1,404 @@
+/*
+ * gf_screen_split.cuh — screen v4: the thread-per-pair screen of gf_screen_tpp.cuh cut into four kernels so that every
+ * warp runs ONE class of work (profiles/r01_final_summary.md: the fused kernel averages 15 of 32 active threads because
+ * merged/unmerged, seeded/unseeded and forward/reverse pairs diverge inside a warp).
+ *
+ *   k_prep   thread per pair      convert R1 / rc(R2) to bit-planes, fast_merge (read.rs:313-440), write the 1-2 sequences
+ *                                 that will be mapped (merged, or R1 and R2) as bit-planes into a sequence store
+ *   k_seed   thread per sequence  8 spread 16-mers -> L2 filter -> first unique one -> ONE HBM table lookup;
+ *                                 appends the sequence to the "seeded" or the "unseeded" list
+ *   k_diag   thread per seeded sequence    compare with the gene planes along the seed diagonal (exact votes), filter
+ *                                          probes for the offsets the diagonal does not explain
+ *   k_scan   thread per unseeded sequence  filter probe for every valid even offset
+ *
+ * The drop rule is the one documented in gf_map.cu (count2 <= T - c_d).  Sequence store layout: slot s, plane word k
+ * (lo: 0..NW-1, hi: NW.., valid: 2NW..) at words[((s >> 5) * 3*NW + k) * 32 + (s & 31)] — column-major per group of 32
+ * slots, so a warp reading consecutive slots is coalesced; meta[s] = {pair, source|olen<<2|diff<<14, len, 0}.
+ */
+#pragma once
+
+namespace split {
+
+using tpp::Col;
+using tpp::Lay;
+
+struct SeqStore {
+    uint32_t* words;
+    uint4* meta;
+    uint2* seed;              /* per slot: {seed_val, seed_i} */
+    uint32_t* list_seeded;    /* slot indices */
+    uint32_t* list_unseeded;
+    unsigned int* counters;   /* [0] slots, [1] seeded, [2] unseeded */
+    uint32_t cap;
+};
+template <int W>
+struct SL {
+    static constexpr int NW = 2 * W + 1;   /* plane words per sequence (merged reads, + zero pad word) */
+    static constexpr int NW3 = 3 * NW;
+};
+template <int W>
+__device__ __forceinline__ uint32_t* slot_words(const SeqStore& st, uint32_t s) {
+    return st.words + (size_t)(s >> 5) * SL<W>::NW3 * 32 + (s & 31u);
+}
+
+struct PrepParams {
+    GfDevBatch b;
+    SeqStore st;
+    GfMapCounters* counters;
+};
+
+/* ---------------------------------------------------------------------------------------------- k_prep */
+template <int W, bool PAIRED>
+__global__ void __launch_bounds__(tpp::WARPS * 32) k_prep(PrepParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* sm = reinterpret_cast<uint32_t*>(smem_raw);
+    const uint32_t lane = gf_lane(), wib = threadIdx.x >> 5;
+    constexpr int PW = Lay<W>::MLO; /* private words actually used here: R1 + C2 arrays only */
+    Col c;
+    c.base = sm + (size_t)wib * PW * 32 + lane;
+    const GfDevBatch& B = P.b;
+    const uint64_t n_warps = (uint64_t)gridDim.x * tpp::WARPS;
+    const unsigned long long pol_stream = tpp::make_policy_stream();
+    const uint8_t* const NOBOUND = reinterpret_cast<const uint8_t*>(~(uintptr_t)0);
+    const uint8_t* bound1 = B.bytes1 ? B.seq1 + B.bytes1 : NOBOUND;
+    const uint8_t* bound2 = (PAIRED && B.bytes2) ? B.seq2 + B.bytes2 : NOBOUND;
+    constexpr int NW = SL<W>::NW;
+    unsigned c_seq = 0, c_probes = 0, c_bytes = 0, c_merged = 0;
+    uint32_t err = 0;
+
+    for (uint64_t base = ((uint64_t)blockIdx.x * tpp::WARPS + wib) * 32; base < B.n; base += n_warps * 32) {
+        const uint64_t p = base + lane;
+        {   /* pull the bases of the pair this thread converts NEXT into L2 */
+            const uint64_t pn = p + n_warps * 32;
+            if (pn < B.n) {
+                const uint64_t a = __ldg(B.off1 + pn), e = __ldg(B.off1 + pn + 1);
+                for (uint64_t x = a & ~31ull; x < e; x += 32) tpp::prefetch_l2(B.seq1 + (x > B.base1 ? x - B.base1 : 0));
+                if (PAIRED) {
+                    const uint64_t a2 = __ldg(B.off2 + pn), e2 = __ldg(B.off2 + pn + 1);
+                    for (uint64_t x = a2 & ~31ull; x < e2; x += 32) tpp::prefetch_l2(B.seq2 + (x > B.base2 ? x - B.base2 : 0));
+                }
+            }
+        }
+        int len1 = 0, len2 = 0, olen = -1, diff = 0, nseq = 0;
+        const uint8_t *q1 = nullptr, *q2 = nullptr;
+        if (p < B.n) {
+            const uint64_t o1 = __ldg(B.off1 + p);
+            len1 = (int)(__ldg(B.off1 + p + 1) - o1);
+            const uint8_t* s1 = B.seq1 + (o1 - B.base1);
+            q1 = B.qual1 + (o1 - B.base1);
+            const uint8_t* s2 = nullptr;
+            if (PAIRED) {
+                const uint64_t o2 = __ldg(B.off2 + p);
+                len2 = (int)(__ldg(B.off2 + p + 1) - o2);
+                s2 = B.seq2 + (o2 - B.base2);
+                q2 = B.qual2 + (o2 - B.base2);
+            }
+            if (len1 > 32 * W || len2 > 32 * W || len1 < 0 || len2 < 0) {
+                err |= 1u;
+            } else {
+                tpp::convert_r1<W>(c, s1, len1, B.seq1, bound1, pol_stream);
+                if (PAIRED) {
+                    tpp::convert_r2_rc<W>(c, s2, len2, B.seq2, bound2, pol_stream);
+                    olen = tpp::find_overlap<W>(c, len1, len2, q1, q2, &diff);
+                }
+                nseq = olen >= 0 ? 1 : (PAIRED ? 2 : 1);
+            }
+        }
+        /* slots: warp-aggregated allocation, one atomic per warp (all lanes take part) */
+        int incl = nseq;
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(FULL, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        uint32_t slot0 = 0;
+        if (total) {
+            if (lane == 0) slot0 = atomicAdd(&P.st.counters[0], (unsigned)total);
+            slot0 = __shfl_sync(FULL, slot0, 0) + (uint32_t)(incl - nseq);
+        }
+        if (nseq && slot0 + (uint32_t)nseq > P.st.cap) { err |= 2u; nseq = 0; }
+        for (int sq = 0; sq < nseq; sq++) {
+            const uint32_t s = slot0 + (uint32_t)sq;
+            uint32_t* w = slot_words<W>(P.st, s);
+            int len;
+            uint32_t info;
+            if (olen >= 0) {
+                /* merged read (read.rs:369-428): R1[..offset] ++ rc(R2); overlap mismatches keep the R1 base iff
+                 * q1 >= '?' and q2 <= '0' */
+                const int offset = len1 - olen;
+                len = offset + len2;
+                const int nwm = (len + 31) >> 5;
+                /* positions (<= 2) where the R1 base wins */
+                int fix0 = -1, fix1 = -1;
+                for (int k = 0; 32 * k < olen; k++) {
+                    uint32_t mism = tpp::overlap_mism<W>(c, offset, olen, len2, k);
+                    while (mism) {
+                        int b = __ffs(mism) - 1;
+                        mism &= mism - 1;
+                        bool r1w;
+                        tpp::low_qual_pair(q1, q2, offset, len2, 32 * k + b, &r1w);
+                        if (r1w) { if (fix0 < 0) fix0 = offset + 32 * k + b; else fix1 = offset + 32 * k + b; }
+                    }
+                }
+                for (int k = 0; k < NW; k++) {
+                    uint32_t lo = 0, hi = 0, v = 0;
+                    if (k < nwm) {
+                        int pos0 = 32 * k;
+                        if (pos0 < offset) {
+                            uint32_t m = lowmask(offset - pos0);
+                            lo = c(Lay<W>::R1LO, k) & m; hi = c(Lay<W>::R1HI, k) & m; v = c(Lay<W>::R1V, k) & m;
+                        }
+                        int j0 = pos0 - offset;
+                        if (j0 > -32) { lo |= c.win(Lay<W>::C2LO, j0); hi |= c.win(Lay<W>::C2HI, j0); v |= c.win(Lay<W>::C2V, j0); }
+                        for (int f = 0; f < 2; f++) {
+                            int fp = f ? fix1 : fix0;
+                            if (fp >= 0 && (fp >> 5) == k) {
+                                uint32_t bit = 1u << (fp & 31);
+                                lo = (lo & ~bit) | (c(Lay<W>::R1LO, k) & bit);
+                                hi = (hi & ~bit) | (c(Lay<W>::R1HI, k) & bit);
+                                v = (v & ~bit) | (c(Lay<W>::R1V, k) & bit);
+                            }
+                        }
+                    }
+                    w[(size_t)k * 32] = lo; w[(size_t)(NW + k) * 32] = hi; w[(size_t)(2 * NW + k) * 32] = v;
+                }
+                info = 0u | ((uint32_t)olen << 2) | ((uint32_t)diff << 14);
+                c_merged++;
+            } else if (sq == 0) {
+                len = len1;
+                for (int k = 0; k < NW; k++) {
+                    bool in = k <= W;
+                    w[(size_t)k * 32] = in ? c(Lay<W>::R1LO, k) : 0u;
+                    w[(size_t)(NW + k) * 32] = in ? c(Lay<W>::R1HI, k) : 0u;
+                    w[(size_t)(2 * NW + k) * 32] = in ? c(Lay<W>::R1V, k) : 0u;
+                }
+                info = 1u;
+            } else {
+                /* forward R2 (upper-case validity) from the rc planes */
+                len = len2;
+                const int nw = (len2 + 31) >> 5;
+                for (int k = 0; k < NW; k++) {
+                    uint32_t lo = 0, hi = 0, v = 0;
+                    if (k < nw) {
+                        int pos = len2 - 32 * k - 32;
+                        v = __brev(c.win(Lay<W>::VCS, pos));
+                        lo = ~__brev(c.win(Lay<W>::C2LO, pos)) & v;
+                        hi = __brev(c.win(Lay<W>::C2HI, pos)) & v;
+                    }
+                    w[(size_t)k * 32] = lo; w[(size_t)(NW + k) * 32] = hi; w[(size_t)(2 * NW + k) * 32] = v;
+                }
+                info = 2u;
+            }
+            P.st.meta[s] = make_uint4((uint32_t)p, info, (uint32_t)len, 0u);
+            c_seq++;
+            c_bytes += (unsigned)len;
+            c_probes += (unsigned)(len >= 16 ? ((len - 16) >> 1) + 1 : 0);
+        }
+        __syncwarp();
+    }
+    c_seq = __reduce_add_sync(FULL, c_seq);
+    c_merged = __reduce_add_sync(FULL, c_merged);
+    c_probes = __reduce_add_sync(FULL, c_probes);
+    c_bytes = __reduce_add_sync(FULL, c_bytes);
+    if (lane == 0) {
+        if (c_seq) atomicAdd(&P.counters->n_sequences, (unsigned long long)c_seq);
+        if (c_probes) atomicAdd(&P.counters->n_probes, (unsigned long long)c_probes);
+        if (c_bytes) atomicAdd(&P.counters->seq_bytes, (unsigned long long)c_bytes);
+        if (c_merged) atomicAdd(&P.counters->n_merged, (unsigned long long)c_merged);
+    }
+    err = __reduce_or_sync(FULL, err);
+    if (err && lane == 0) atomicOr(&P.counters->error_flags, err);
+}
+
+/* ---------------------------------------------------------------------------------------------- k_seed */
+struct SeedParams {
+    GfDevIndex ix;
+    SeqStore st;
+    int need_total, need_minor;
+};
+__device__ __forceinline__ uint32_t fs_col(const uint32_t* col, int arr_base, uint32_t bitpos) {
+    uint32_t wi = bitpos >> 5;
+    return __funnelshift_r(col[(size_t)(arr_base + (int)wi) * 32], col[(size_t)(arr_base + (int)wi + 1) * 32], bitpos & 31u);
+}
+template <int W>
+__global__ void __launch_bounds__(256) k_seed(SeedParams P) {
+    constexpr int NW = SL<W>::NW;
+    const uint32_t lane = gf_lane();
+    const uint32_t n_slots = min(P.st.counters[0], P.st.cap);
+    const unsigned long long pol = make_policy_keep();
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t s0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); s0 < n_slots; s0 += stride) {
+        const uint32_t s = s0 + lane;
+        bool have = s < n_slots, seeded = false;
+        uint32_t seed_val = GF_EMPTY_VAL, seed_i = 0;
+        if (have) {
+            const uint4 m = P.st.meta[s];
+            const int len = (int)m.z;
+            const int nprobe = len >= 16 ? ((len - 16) >> 1) + 1 : 0;
+            const uint32_t* col = slot_words<W>(P.st, s);
+            if (nprobe == 0 && P.need_total > 0) have = false; /* cannot reach the gate: dropped here */
+#pragma unroll 1
+            for (int t = 0; have && t < 8 && nprobe > 0; t++) {
+                uint32_t i = (uint32_t)(((long long)t * nprobe) >> 3) * 2u;
+                if ((fs_col(col, 2 * NW, i) & 0xFFFFu) != 0xFFFFu) continue;
+                uint32_t key = ((fs_col(col, NW, i) & 0xFFFFu) << 16) | (fs_col(col, 0, i) & 0xFFFFu);
+                if (tpp::filter_sites(P.ix, key, pol, 2u) != 1u) continue;
+                uint32_t val = gf_table_find(P.ix, key);
+                if (val != GF_EMPTY_VAL && (val >> 30) == GF_KIND_UNIQUE) { seed_val = val; seed_i = i; seeded = true; break; }
+            }
+            if (have) P.st.seed[s] = make_uint2(seed_val, seed_i);
+        }
+        /* class lists, warp-aggregated */
+        const uint32_t ms = __ballot_sync(FULL, have && seeded), mu = __ballot_sync(FULL, have && !seeded);
+        uint32_t bs = 0, bu = 0;
+        if (lane == 0) {
+            if (ms) bs = atomicAdd(&P.st.counters[1], (unsigned)__popc(ms));
+            if (mu) bu = atomicAdd(&P.st.counters[2], (unsigned)__popc(mu));
+        }
+        bs = __shfl_sync(FULL, bs, 0);
+        bu = __shfl_sync(FULL, bu, 0);
+        if (have && seeded) P.st.list_seeded[bs + __popc(ms & gf_lanemask_lt())] = s;
+        if (have && !seeded) P.st.list_unseeded[bu + __popc(mu & gf_lanemask_lt())] = s;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------- k_diag / k_scan */
+struct ClassParams {
+    GfDevIndex ix;
+    SeqStore st;
+    uint2* survivors;
+    uint32_t survivors_cap;
+    GfMapCounters* counters;
+    int need_total, need_minor;
+};
+__device__ __forceinline__ void push_survivor(const ClassParams& P, const uint4& m) {
+    uint32_t slot = atomicAdd(&P.counters->n_survivors, 1u);
+    if (slot < P.survivors_cap) P.survivors[slot] = make_uint2(m.x, m.y);
+    else atomicOr(&P.counters->error_flags, 2u);
+}
+/* filter probes for the set bits of `om` (offsets inside the current chunk), 4 in flight; returns the vote bound */
+__device__ __forceinline__ int probe_offsets(const GfDevIndex& ix, uint32_t om, uint32_t lo_cur, uint32_t lo_nxt, uint32_t hi_cur,
+                                             uint32_t hi_nxt, bool rc, unsigned long long pol) {
+    int T = 0;
+    while (om) {
+        uint32_t key[4];
+        unsigned long long w[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            ok[u] = om != 0u;
+            uint32_t b = ok[u] ? (uint32_t)(__ffs(om) - 1) : 0u;
+            om &= om - 1u;
+            uint32_t kk = ((__funnelshift_r(hi_cur, hi_nxt, b) & 0xFFFFu) << 16) | (__funnelshift_r(lo_cur, lo_nxt, b) & 0xFFFFu);
+            key[u] = rc ? gf_key_revcomp(kk) : kk;
+            w[u] = 0;
+            if (ok[u]) w[u] = ldg_filter(ix.filter + gf_filter_word(key[u], ix.filter_words), pol);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (ok[u]) T += (int)gf_filter_sites(w[u], key[u], ix.max_sites);
+    }
+    return T;
+}
+
+/* unseeded sequences: every valid even offset gets a filter probe; survive iff the bound reaches the gate */
+template <int W>
+__global__ void __launch_bounds__(256) k_scan(ClassParams P) {
+    constexpr int NW = SL<W>::NW;
+    const uint32_t n = P.st.counters[2];
+    const unsigned long long pol = make_policy_keep();
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const uint32_t s = P.st.list_unseeded[t];
+        const uint4 m = P.st.meta[s];
+        const int len = (int)m.z, nch = (len + 31) >> 5;
+        const uint32_t* col = slot_words<W>(P.st, s);
+        uint32_t lo = col[0], hi = col[(size_t)NW * 32], v = col[(size_t)2 * NW * 32];
+        int T = 0;
+#pragma unroll 1
+        for (int k = 0; k < nch; k++) {
+            uint32_t nlo = col[(size_t)(k + 1) * 32], nhi = col[(size_t)(NW + k + 1) * 32], nv = col[(size_t)(2 * NW + k + 1) * 32];
+            T += probe_offsets(P.ix, run16(v, nv) & 0x55555555u, lo, nlo, hi, nhi, false, pol);
+            lo = nlo; hi = nhi; v = nv;
+        }
+        if (P.need_total <= 0 || (T >= P.need_total && T >= P.need_minor)) push_survivor(P, m);
+    }
+}
+
+/* seeded sequences: compare with the gene along the seed diagonal; exact votes where the 16-mer equals an indexed window */
+template <int W>
+__global__ void __launch_bounds__(256) k_diag(ClassParams P) {
+    constexpr int NW = SL<W>::NW;
+    const uint32_t n = P.st.counters[1];
+    const unsigned long long pol = make_policy_keep();
+    const GfDevIndex& ix = P.ix;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const uint32_t s = P.st.list_seeded[t];
+        const uint4 m = P.st.meta[s];
+        const uint2 sd = P.st.seed[s];
+        const int len = (int)m.z, nch = (len + 31) >> 5;
+        const uint32_t* col = slot_words<W>(P.st, s);
+        const bool rc = (sd.x & GF_SITE_STRAND) != 0;
+        const uint32_t goff = sd.x & GF_SITE_GOFF_MASK;
+        const uint32_t D = rc ? goff + sd.y - (uint32_t)len + 1u : goff - sd.y;
+        const uint32_t parity = (rc && (len & 1)) ? 0xAAAAAAAAu : 0x55555555u;
+        const uint32_t wbase = D >> 5, sh = D & 31u;
+        const uint32_t* gc = rc ? ix.g_cr : ix.g_cf;
+        /* read chunk k in the orientation of the comparison */
+        auto read_chunk = [&](int k, uint32_t* lo, uint32_t* hi, uint32_t* v) {
+            if (k >= nch) { *lo = *hi = *v = 0; return; }
+            if (!rc) { *lo = col[(size_t)k * 32]; *hi = col[(size_t)(NW + k) * 32]; *v = col[(size_t)(2 * NW + k) * 32]; return; }
+            int pos = len - 32 * k - 32;
+            uint32_t a, b, cc;
+            if (pos >= 0) { a = fs_col(col, 0, (uint32_t)pos); b = fs_col(col, NW, (uint32_t)pos); cc = fs_col(col, 2 * NW, (uint32_t)pos); }
+            else { a = col[0] << (-pos); b = col[(size_t)NW * 32] << (-pos); cc = col[(size_t)2 * NW * 32] << (-pos); }
+            uint32_t vv = __brev(cc);
+            *v = vv;
+            *lo = ~__brev(a) & vv;
+            *hi = __brev(b);
+        };
+        uint32_t glo0 = ldg_plane(ix.g_lo + wbase, pol), ghi0 = ldg_plane(ix.g_hi + wbase, pol), gv0 = ldg_plane(ix.g_v + wbase, pol);
+        uint32_t gca0 = ldg_plane(gc + wbase, pol), gcb0 = ldg_plane(gc + ix.g_cstride + wbase, pol),
+                 gcc0 = ldg_plane(gc + 2 * ix.g_cstride + wbase, pol);
+        uint32_t lo_cur, hi_cur, v_cur;
+        read_chunk(0, &lo_cur, &hi_cur, &v_cur);
+        uint32_t e_cur, cnt_a, cnt_b, cnt_c;
+        {
+            uint32_t glo1 = ldg_plane(ix.g_lo + wbase + 1, pol), ghi1 = ldg_plane(ix.g_hi + wbase + 1, pol),
+                     gv1 = ldg_plane(ix.g_v + wbase + 1, pol);
+            uint32_t gca1 = ldg_plane(gc + wbase + 1, pol), gcb1 = ldg_plane(gc + ix.g_cstride + wbase + 1, pol),
+                     gcc1 = ldg_plane(gc + 2 * ix.g_cstride + wbase + 1, pol);
+            e_cur = ~((lo_cur ^ __funnelshift_r(glo0, glo1, sh)) | (hi_cur ^ __funnelshift_r(ghi0, ghi1, sh))) & v_cur &
+                    __funnelshift_r(gv0, gv1, sh);
+            cnt_a = __funnelshift_r(gca0, gca1, sh); cnt_b = __funnelshift_r(gcb0, gcb1, sh); cnt_c = __funnelshift_r(gcc0, gcc1, sh);
+            glo0 = glo1; ghi0 = ghi1; gv0 = gv1; gca0 = gca1; gcb0 = gcb1; gcc0 = gcc1;
+        }
+        int T = 0, c_d = 0;
+#pragma unroll 1
+        for (int k = 0; k < nch; k++) {
+            uint32_t nlo, nhi, nv;
+            read_chunk(k + 1, &nlo, &nhi, &nv);
+            uint32_t e_nxt = 0, na = 0, nb = 0, nc = 0;
+            if (k + 1 < nch) {
+                uint32_t glo1 = ldg_plane(ix.g_lo + wbase + k + 2, pol), ghi1 = ldg_plane(ix.g_hi + wbase + k + 2, pol),
+                         gv1 = ldg_plane(ix.g_v + wbase + k + 2, pol);
+                uint32_t gca1 = ldg_plane(gc + wbase + k + 2, pol), gcb1 = ldg_plane(gc + ix.g_cstride + wbase + k + 2, pol),
+                         gcc1 = ldg_plane(gc + 2 * ix.g_cstride + wbase + k + 2, pol);
+                e_nxt = ~((nlo ^ __funnelshift_r(glo0, glo1, sh)) | (nhi ^ __funnelshift_r(ghi0, ghi1, sh))) & nv &
+                        __funnelshift_r(gv0, gv1, sh);
+                na = __funnelshift_r(gca0, gca1, sh); nb = __funnelshift_r(gcb0, gcb1, sh); nc = __funnelshift_r(gcc0, gcc1, sh);
+                glo0 = glo1; ghi0 = ghi1; gv0 = gv1; gca0 = gca1; gcb0 = gcb1; gcc0 = gcc1;
+            }
+            uint32_t mm = run16(e_cur, e_nxt) & parity;
+            uint32_t c0 = cnt_a & mm, c1 = cnt_b & mm, c2 = cnt_c & mm;
+            uint32_t hit = c0 | c1 | c2;
+            c_d += __popc(hit);
+            T += __popc(c0) + 2 * __popc(c1) + 4 * __popc(c2);
+            T += probe_offsets(ix, run16(v_cur, nv) & parity & ~hit, lo_cur, nlo, hi_cur, nhi, rc, pol);
+            e_cur = e_nxt; cnt_a = na; cnt_b = nb; cnt_c = nc;
+            v_cur = nv; lo_cur = nlo; hi_cur = nhi;
+        }
+        if (P.need_total <= 0 || P.need_minor <= 0 || (T >= P.need_total && (T - c_d) >= P.need_minor)) push_survivor(P, m);
+    }
+}
+
+}  // namespace split
