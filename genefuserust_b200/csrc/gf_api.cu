@@ -48,6 +48,7 @@ void destroy_handle(gf_index* idx) {
     cudaFree(idx->d_gene_rev);
     cudaFree(idx->d_planes);
     cudaFree(idx->d_filter);
+    cudaFree(idx->d_granule);
     idx->ws_survivors.release();
     idx->ws_counters.release();
     idx->ws_gtbl.release();

@@ -42,6 +42,8 @@ struct GfDevIndex {
     const uint32_t* gene_start; /* goff of base 0 of each gene [n_genes] (ascending) */
     const uint32_t* gene_len;   /* [n_genes] */
     const uint8_t* gene_rev;    /* Gene::is_reversed() per gene */
+    const uint16_t* granule_contig; /* contig owning arena granule (goff >> 11); genes are >= 2304 bytes apart, so a
+                                       2048-byte granule never holds bases of two genes */
     /* L2-resident screen structures (gf_index.cu: k_gene_planes, k_window_class, filter bits in k_build_table) */
     const uint32_t* g_lo;       /* gene arena as bit-planes, bit (goff & 31) of word (goff >> 5): low code bit */
     const uint32_t* g_hi;       /* high code bit */
@@ -172,14 +174,9 @@ __device__ __forceinline__ uint32_t gf_filter_sites(unsigned long long w, uint32
 }
 
 /* site decoding ---------------------------------------------------------------------------- */
-/* goff -> contig by binary search over gene_start (ascending) */
+/* goff -> contig: one table load */
 __device__ __forceinline__ uint32_t gf_contig_of(const GfDevIndex& ix, uint32_t goff) {
-    uint32_t lo = 0, hi = ix.n_genes;
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(ix.gene_start + mid) <= goff) lo = mid; else hi = mid;
-    }
-    return lo;
+    return (uint32_t)__ldg(ix.granule_contig + (goff >> 11));
 }
 /* site -> GenePos (contig, position) exactly as the reference stores it */
 __device__ __forceinline__ void gf_site_decode(const GfDevIndex& ix, uint32_t site, int32_t* contig, int32_t* position) {

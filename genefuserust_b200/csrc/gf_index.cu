@@ -418,6 +418,12 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     }
 
     pt.mark("host arena");
+    /* granule -> contig table (site decoding) */
+    std::vector<uint16_t> granule((arena_len >> 11) + 2, 0);
+    for (uint32_t g = 0; g < n_genes; g++)
+        if (genes[g].len)
+            for (uint64_t q = idx->gene_start[g] >> 11; q <= ((uint64_t)idx->gene_start[g] + genes[g].len - 1) >> 11; q++)
+                granule[q] = (uint16_t)g;
     cudaEvent_t e0, e1;
     GF_CUDA_TRY(cudaEventCreate(&e0));
     GF_CUDA_TRY(cudaEventCreate(&e1));
@@ -425,6 +431,9 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     GF_CUDA_TRY(cudaMalloc(&idx->d_gene_start, sizeof(uint32_t) * (n_genes + 1)));
     GF_CUDA_TRY(cudaMalloc(&idx->d_gene_len, sizeof(uint32_t) * (n_genes + 1)));
     GF_CUDA_TRY(cudaMalloc(&idx->d_gene_rev, n_genes + 1));
+    GF_CUDA_TRY(cudaMalloc(&idx->d_granule, sizeof(uint16_t) * granule.size()));
+    GF_CUDA_TRY(cudaMemcpyAsync(idx->d_granule, granule.data(), sizeof(uint16_t) * granule.size(), cudaMemcpyHostToDevice, st));
+    idx->dev.granule_contig = (const uint16_t*)idx->d_granule;
     GF_CUDA_TRY(cudaMemcpyAsync(idx->d_gene_ascii, arena.data(), arena_len, cudaMemcpyHostToDevice, st));
     if (n_genes) {
         GF_CUDA_TRY(cudaMemcpyAsync(idx->d_gene_start, idx->gene_start.data(), sizeof(uint32_t) * n_genes,

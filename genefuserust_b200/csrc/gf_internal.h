@@ -77,7 +77,7 @@ struct gf_index {
     std::vector<uint32_t> gene_start, gene_len;
 
     void *d_table = nullptr, *d_dupes = nullptr, *d_gene_ascii = nullptr, *d_gene_start = nullptr,
-         *d_gene_len = nullptr, *d_gene_rev = nullptr, *d_planes = nullptr, *d_filter = nullptr;
+         *d_gene_len = nullptr, *d_gene_rev = nullptr, *d_planes = nullptr, *d_filter = nullptr, *d_granule = nullptr;
 
     std::mutex mu; /* serialises calls on one handle */
     cudaStream_t stream = nullptr, copy_stream = nullptr;

@@ -27,6 +27,7 @@
  *             distance, so the -1/-2 sentinels and the ">= 5" filter downstream see the reference's values.
  */
 #include <climits>
+#include <cstdlib>
 #include <cstdio>
 
 #include "gf_internal.h"
@@ -1206,6 +1207,10 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
             pp.b = b;
             pp.st = ss;
             pp.counters = d_cnt;
+            pp.stream_policy = 0; /* measured: evict_first on the read bytes and L2 prefetch both cost ~2 % (gpurun_out) */
+            pp.prefetch = 0;
+            if (const char* e = getenv("GF_STREAM_POLICY")) pp.stream_policy = atoi(e) != 0;
+            if (const char* e = getenv("GF_PREFETCH")) pp.prefetch = atoi(e) != 0;
             const size_t psm = sizeof(uint32_t) * tpp::WARPS * (w5 ? tpp::Lay<5>::MLO : tpp::Lay<8>::MLO) * 32;
             const uint64_t want_b = (b.n + tpp::WARPS * 32 - 1) / (tpp::WARPS * 32);
             const unsigned pgrid = (unsigned)std::min<uint64_t>(want_b, (uint64_t)idx->sm_count * (w5 ? 8 : 5));

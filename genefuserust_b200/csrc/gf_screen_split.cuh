@@ -45,6 +45,8 @@ struct PrepParams {
     GfDevBatch b;
     SeqStore st;
     GfMapCounters* counters;
+    int stream_policy; /* 0 = evict_normal, 1 = evict_first for the read bytes (GF_STREAM_POLICY) */
+    int prefetch;      /* 1 = prefetch the next pair's bases into L2 (GF_PREFETCH) */
 };
 
 /* ---------------------------------------------------------------------------------------------- k_prep */
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(tpp::WARPS * 32) k_prep(PrepParams P) {
     c.base = sm + (size_t)wib * PW * 32 + lane;
     const GfDevBatch& B = P.b;
     const uint64_t n_warps = (uint64_t)gridDim.x * tpp::WARPS;
-    const unsigned long long pol_stream = tpp::make_policy_stream();
+    const unsigned long long pol_stream = P.stream_policy ? tpp::make_policy_stream() : tpp::make_policy_normal();
     const uint8_t* const NOBOUND = reinterpret_cast<const uint8_t*>(~(uintptr_t)0);
     const uint8_t* bound1 = B.bytes1 ? B.seq1 + B.bytes1 : NOBOUND;
     const uint8_t* bound2 = (PAIRED && B.bytes2) ? B.seq2 + B.bytes2 : NOBOUND;
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(tpp::WARPS * 32) k_prep(PrepParams P) {
         const uint64_t p = base + lane;
         {   /* pull the bases of the pair this thread converts NEXT into L2 */
             const uint64_t pn = p + n_warps * 32;
-            if (pn < B.n) {
+            if (P.prefetch && pn < B.n) {
                 const uint64_t a = __ldg(B.off1 + pn), e = __ldg(B.off1 + pn + 1);
                 for (uint64_t x = a & ~31ull; x < e; x += 32) tpp::prefetch_l2(B.seq1 + (x > B.base1 ? x - B.base1 : 0));
                 if (PAIRED) {
@@ -237,14 +239,27 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
             const int nprobe = len >= 16 ? ((len - 16) >> 1) + 1 : 0;
             const uint32_t* col = slot_words<W>(P.st, s);
             if (nprobe == 0 && P.need_total > 0) have = false; /* cannot reach the gate: dropped here */
-#pragma unroll 1
-            for (int t = 0; have && t < 8 && nprobe > 0; t++) {
-                uint32_t i = (uint32_t)(((long long)t * nprobe) >> 3) * 2u;
-                if ((fs_col(col, 2 * NW, i) & 0xFFFFu) != 0xFFFFu) continue;
-                uint32_t key = ((fs_col(col, NW, i) & 0xFFFFu) << 16) | (fs_col(col, 0, i) & 0xFFFFu);
-                if (tpp::filter_sites(P.ix, key, pol, 2u) != 1u) continue;
-                uint32_t val = gf_table_find(P.ix, key);
-                if (val != GF_EMPTY_VAL && (val >> 30) == GF_KIND_UNIQUE) { seed_val = val; seed_i = i; seeded = true; break; }
+            if (have && nprobe > 0) {
+                /* all 8 candidate k-mers go to the filter at once (independent L2 loads); the HBM table is asked only
+                 * for candidates the filter calls present-and-unique, in read order */
+                uint32_t key[8], off[8];
+                unsigned long long fw[8];
+                uint32_t okm = 0;
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    off[t] = (uint32_t)(((long long)t * nprobe) >> 3) * 2u;
+                    bool ok = (fs_col(col, 2 * NW, off[t]) & 0xFFFFu) == 0xFFFFu;
+                    key[t] = ((fs_col(col, NW, off[t]) & 0xFFFFu) << 16) | (fs_col(col, 0, off[t]) & 0xFFFFu);
+                    fw[t] = 0;
+                    if (ok) { fw[t] = ldg_filter(P.ix.filter + gf_filter_word(key[t], P.ix.filter_words), pol); okm |= 1u << t; }
+                }
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    if (seeded || !((okm >> t) & 1u)) continue;
+                    if (gf_filter_sites(fw[t], key[t], 2u) != 1u) continue;
+                    uint32_t val = gf_table_find(P.ix, key[t]);
+                    if (val != GF_EMPTY_VAL && (val >> 30) == GF_KIND_UNIQUE) { seed_val = val; seed_i = off[t]; seeded = true; }
+                }
             }
             if (have) P.st.seed[s] = make_uint2(seed_val, seed_i);
         }

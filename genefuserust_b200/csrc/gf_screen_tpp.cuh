@@ -69,6 +69,11 @@ __device__ __forceinline__ uint4 load16_guarded(const uint8_t* p, const uint8_t*
     return make_uint4(load4_guarded(p, lo, hi), load4_guarded(p + 4, lo, hi), load4_guarded(p + 8, lo, hi),
                       load4_guarded(p + 12, lo, hi));
 }
+__device__ __forceinline__ unsigned long long make_policy_normal() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ unsigned long long make_policy_stream() {
     unsigned long long pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -148,9 +153,10 @@ __device__ __forceinline__ void convert_r2_rc(const Col& c, const uint8_t* seq, 
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int u0 = 16 * b + 4 * j;
-            uint32_t l, h, v, l2, h2, vcs;
+            uint32_t l, h, v;
             classify4(x[j], true, &l, &h, &v);
-            classify4(x[j], false, &l2, &h2, &vcs);
+            /* case-sensitive validity: a valid letter is upper case iff bit 5 of its byte is clear */
+            uint32_t vcs = v & ~gather4((x[j] >> 5) & 0x01010101u);
             /* byte t of x[j] has u = u0 + 3 - t: reverse the nibbles; complement = code ^ 1 */
             uint32_t rv = rev4(v), rl = ~rev4(l) & rv, rh = rev4(h), rcs = rev4(vcs);
             int rem = nu - u0;
