@@ -135,7 +135,7 @@ class gf_map_stats(C.Structure):
 EXPORTS = (
     "gf_last_error", "gf_abi_version", "gf_device_count", "gf_default_params", "gf_index_create",
     "gf_index_destroy", "gf_index_get_info", "gf_index_lookup", "gf_map_pairs", "gf_map_pairs_device",
-    "gf_sort_matches", "gf_get_map_stats", "gf_fast_merge",
+    "gf_sort_matches", "gf_get_map_stats", "gf_fast_merge", "gf_map_fastq",
 )
 
 _lib = None
@@ -174,6 +174,9 @@ def load_library():
     lib.gf_sort_matches.restype = None
     lib.gf_get_map_stats.argtypes = [C.c_void_p, P(gf_map_stats)]
     lib.gf_get_map_stats.restype = C.c_int
+    lib.gf_map_fastq.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, P(gf_match), C.c_uint64,
+                                 P(C.c_uint64), P(C.c_uint64)]
+    lib.gf_map_fastq.restype = C.c_int
     lib.gf_fast_merge.argtypes = [C.c_void_p, P(gf_batch), P(gf_merge_info)]
     lib.gf_fast_merge.restype = C.c_int
     _lib = lib

@@ -56,6 +56,8 @@ void destroy_handle(gf_index* idx) {
     idx->ws_seq_meta.release();
     idx->ws_seq_seed.release();
     idx->ws_seq_lists.release();
+    idx->fq[0].release();
+    idx->fq[1].release();
     for (auto& s : idx->stage) {
         s.seq1.release(); s.qual1.release(); s.off1.release();
         s.seq2.release(); s.qual2.release(); s.off2.release();
@@ -256,7 +258,7 @@ int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_
         db.n = cn;
         db.seq1 = s.seq1.as<uint8_t>();
         db.qual1 = zc ? zq1 + b1 : s.qual1.as<uint8_t>(); /* kernels address it as qual1 + (off - base1) */
-        db.off1 = s.off1.as<uint64_t>();
+        db.s1 = s.off1.as<uint64_t>(); db.e1 = db.s1 + 1; db.qs1 = db.s1;
         db.base1 = b1;
         db.bytes1 = e1 - b1;
         db.pair_base = lo;
@@ -275,7 +277,7 @@ int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_
             h2d += (e2 - b2) + sizeof(uint64_t) * (cn + 1);
             db.seq2 = s.seq2.as<uint8_t>();
             db.qual2 = zc ? zq2 + b2 : s.qual2.as<uint8_t>();
-            db.off2 = s.off2.as<uint64_t>();
+            db.s2 = s.off2.as<uint64_t>(); db.e2 = db.s2 ? db.s2 + 1 : nullptr; db.qs2 = db.s2;
             db.base2 = b2;
             db.bytes2 = e2 - b2;
         }
@@ -355,10 +357,10 @@ int gf_map_pairs_device(gf_index* idx, const gf_batch* in_dev, gf_match* d_out, 
     db.n = in_dev->n;
     db.seq1 = in_dev->seq1;
     db.qual1 = in_dev->qual1;
-    db.off1 = in_dev->off1;
+    db.s1 = in_dev->off1; db.e1 = db.s1 + 1; db.qs1 = db.s1;
     db.seq2 = in_dev->seq2;
     db.qual2 = in_dev->qual2;
-    db.off2 = in_dev->off2;
+    db.s2 = in_dev->off2; db.e2 = db.s2 ? db.s2 + 1 : nullptr; db.qs2 = db.s2;
     db.base1 = db.base2 = 0;
     db.bytes1 = in_dev->bytes1;
     db.bytes2 = in_dev->bytes2;
@@ -375,6 +377,81 @@ int gf_map_pairs_device(gf_index* idx, const gf_batch* in_dev, gf_match* d_out, 
     idx->stats.n_pairs = in_dev->n;
     idx->stats.kernel_launches = idx->launches - launches0;
     idx->stats_pending = true;
+    return GF_OK;
+}
+
+int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8_t* fq2, uint64_t bytes2, gf_match* out,
+                 uint64_t out_cap, uint64_t* n_out, uint64_t* n_records) {
+    if (!idx || !n_out || !n_records) return fail(GF_E_INVALID, "NULL argument");
+    *n_out = 0;
+    *n_records = 0;
+    if ((bytes1 && !fq1) || (bytes2 && !fq2)) return fail(GF_E_INVALID, "NULL FASTQ buffer");
+    if (out_cap && !out) return fail(GF_E_INVALID, "out is NULL");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    GF_CUDA_TRY(cudaSetDevice(idx->device));
+    idx->stats = gf_map_stats{};
+    idx->stats_pending = false;
+    const bool pe = fq2 != nullptr;
+    cudaStream_t st = idx->stream;
+    GfStage& sg = idx->stage[0];
+    GF_CUDA_TRY(cudaEventRecord(idx->ev_start, st));
+    /* raw text -> device (the sequence and quality "arenas" are the text itself) */
+    GF_CUDA_TRY(sg.seq1.reserve(bytes1 + 32));
+    GF_CUDA_TRY(cudaMemcpyAsync(sg.seq1.p, fq1, bytes1, cudaMemcpyHostToDevice, st));
+    if (pe) {
+        GF_CUDA_TRY(sg.seq2.reserve(bytes2 + 32));
+        GF_CUDA_TRY(cudaMemcpyAsync(sg.seq2.p, fq2, bytes2, cudaMemcpyHostToDevice, st));
+    }
+    int rc = gf_fastq_parse_device(sg.seq1.as<uint8_t>(), bytes1, &idx->fq[0], st);
+    if (rc == GF_OK && pe) rc = gf_fastq_parse_device(sg.seq2.as<uint8_t>(), bytes2, &idx->fq[1], st);
+    if (rc != GF_OK) return rc;
+    const uint64_t n = pe ? std::min(idx->fq[0].n_records, idx->fq[1].n_records) : idx->fq[0].n_records;
+    *n_records = n;
+    idx->stats.n_pairs = n;
+    idx->stats.h2d_bytes = bytes1 + (pe ? bytes2 : 0);
+    if (n == 0) return GF_OK;
+    GfDevBatch db{};
+    db.n = n;
+    db.seq1 = db.qual1 = sg.seq1.as<uint8_t>();
+    db.s1 = idx->fq[0].s.as<uint64_t>();
+    db.e1 = idx->fq[0].e.as<uint64_t>();
+    db.qs1 = idx->fq[0].qs.as<uint64_t>();
+    db.bytes1 = bytes1;
+    db.max_len = idx->fq[0].max_len;
+    if (pe) {
+        db.seq2 = db.qual2 = sg.seq2.as<uint8_t>();
+        db.s2 = idx->fq[1].s.as<uint64_t>();
+        db.e2 = idx->fq[1].e.as<uint64_t>();
+        db.qs2 = idx->fq[1].qs.as<uint64_t>();
+        db.bytes2 = bytes2;
+        db.max_len = std::max(db.max_len, idx->fq[1].max_len);
+    }
+    if (db.max_len == 0) db.max_len = 1;
+    const uint64_t cap = (pe ? 2 : 1) * n;
+    GF_CUDA_TRY(sg.out.reserve(sizeof(gf_match) * cap));
+    GF_CUDA_TRY(sg.nout.reserve(sizeof(unsigned long long)));
+    const unsigned long long launches0 = idx->launches;
+    rc = gf_map_device_batch(idx, db, sg.out.as<gf_match>(), cap, sg.nout.as<unsigned long long>(), st, false);
+    if (rc != GF_OK) return rc;
+    GfHostSlot* h = &idx->h_slots[0];
+    GF_CUDA_TRY(cudaMemcpyAsync(&h->counters, idx->ws_counters.p, sizeof(GfMapCounters), cudaMemcpyDeviceToHost, st));
+    GF_CUDA_TRY(cudaMemcpyAsync(&h->n_out, sg.nout.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    GF_CUDA_TRY(cudaEventRecord(idx->ev_end, st));
+    GF_CUDA_TRY(cudaEventSynchronize(idx->ev_end));
+    rc = check_flags(*h);
+    if (rc != GF_OK) return rc;
+    accumulate(idx->stats, *h);
+    float ms = 0;
+    GF_CUDA_TRY(cudaEventElapsedTime(&ms, idx->ev_start, idx->ev_end));
+    idx->stats.ms_total = ms;
+    idx->stats.kernel_launches = idx->launches - launches0 + 3;
+    *n_out = h->n_out;
+    if (h->n_out > out_cap) return fail(GF_E_CAPACITY, "out_cap too small; *n_out holds the required count");
+    if (h->n_out) GF_CUDA_TRY(cudaMemcpy(out, sg.out.p, sizeof(gf_match) * h->n_out, cudaMemcpyDeviceToHost));
+    idx->stats.d2h_bytes = sizeof(gf_match) * h->n_out + sizeof(GfMapCounters) + 8;
+    gf_sort_matches(out, h->n_out);
+    if (h->counters.n_ref_panic)
+        return fail(GF_E_REF_PANIC, "a candidate needs an edit distance over more than 640 columns (reference panics)");
     return GF_OK;
 }
 
@@ -434,10 +511,10 @@ int gf_fast_merge(gf_index* idx, const gf_batch* in, gf_merge_info* out) {
     db.n = n;
     db.seq1 = s.seq1.as<uint8_t>();
     db.qual1 = s.qual1.as<uint8_t>();
-    db.off1 = s.off1.as<uint64_t>();
+    db.s1 = s.off1.as<uint64_t>(); db.e1 = db.s1 + 1; db.qs1 = db.s1;
     db.seq2 = s.seq2.as<uint8_t>();
     db.qual2 = s.qual2.as<uint8_t>();
-    db.off2 = s.off2.as<uint64_t>();
+    db.s2 = s.off2.as<uint64_t>(); db.e2 = db.s2 ? db.s2 + 1 : nullptr; db.qs2 = db.s2;
     db.base1 = b1;
     db.base2 = b2;
     db.bytes1 = e1 - b1;

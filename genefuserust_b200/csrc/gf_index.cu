@@ -363,6 +363,12 @@ __global__ void k_lookup(GfDevIndex ix, const uint32_t* __restrict__ kmers, uint
 
 }  // namespace
 
+/* exported to the other translation units (gf_fastq.cu) */
+size_t gf_scan_tmp_elems(uint64_t n) { return scan_tmp_elems(n); }
+cudaError_t gf_exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* tmp, cudaStream_t st) {
+    return exclusive_scan(in, out, n, tmp, st);
+}
+
 /* ======================================================================================================= */
 namespace {
 struct PhaseTimer { /* GF_DEBUG_TIMING=1: host wall clock per build phase on stderr */

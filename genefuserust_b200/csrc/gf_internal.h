@@ -68,6 +68,14 @@ struct GfHostSlot { /* pinned host memory the device writes results of one call/
     unsigned long long pad[15];
 };
 
+/* gf_fastq.cu: FASTQ text already on the device -> per-record start/end/quality-start tables */
+struct GfFastqTable {
+    uint64_t n_records = 0;
+    uint32_t max_len = 0;
+    GfBuf nl, s, e, qs; /* newline positions; sequence start / end; quality start (u64 each) */
+    void release() { nl.release(); s.release(); e.release(); qs.release(); }
+};
+
 struct gf_index {
     int device = 0;
     gf_params params{};
@@ -86,6 +94,7 @@ struct gf_index {
 
     /* mapping workspace (grow-only) */
     GfBuf ws_survivors, ws_counters, ws_gtbl;
+    GfFastqTable fq[2];
     GfBuf ws_seq_words, ws_seq_meta, ws_seq_seed, ws_seq_lists; /* split screen pipeline (gf_screen_split.cuh) */
     GfStage stage[2];
     GfHostSlot* h_slots = nullptr; /* [3]: two pipeline stages + the device-batch path */
@@ -103,11 +112,18 @@ struct gf_index {
 int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_genes);
 int gf_lookup_device(gf_index* idx, const uint32_t* kmers, uint64_t n, gf_lookup* out);
 
+size_t gf_scan_tmp_elems(uint64_t n);
+cudaError_t gf_exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* tmp, cudaStream_t st);
+
+int gf_fastq_parse_device(const uint8_t* d_text, uint64_t bytes, GfFastqTable* out, cudaStream_t st);
+
 /* gf_map.cu */
 struct GfDevBatch {
     uint64_t n;
     const uint8_t *seq1, *qual1, *seq2, *qual2;
-    const uint64_t *off1, *off2;
+    /* per record: start / end of the sequence and start of the quality string, relative to base1/base2.
+     * Arena batches: s = off, e = off + 1, qs = off.  FASTQ text: all three point into the parsed line table. */
+    const uint64_t *s1, *e1, *qs1, *s2, *e2, *qs2;
     uint64_t base1, base2;   /* value subtracted from every offset (chunked host batches) */
     uint64_t bytes1, bytes2; /* readable extent of the seq/qual arenas (0 = unknown: no bounds guard) */
     uint64_t pair_base;      /* added to the local pair index in emitted records */

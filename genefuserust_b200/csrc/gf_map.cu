@@ -603,17 +603,17 @@ __global__ void __launch_bounds__(256, 3) k_screen(ScreenParams P) {
     const uint8_t* qbound2 = (PAIRED && B.bytes2) ? B.qual2 + B.bytes2 : NOBOUND;
 
     for (uint64_t p = gwarp; p < B.n; p += n_warps) {
-        const uint64_t o1 = __ldg(B.off1 + p), e1 = __ldg(B.off1 + p + 1);
+        const uint64_t o1 = __ldg(B.s1 + p), e1 = __ldg(B.e1 + p);
         const int len1 = (int)(e1 - o1);
         const uint8_t* s1 = B.seq1 + (o1 - B.base1);
-        const uint8_t* q1 = B.qual1 + (o1 - B.base1);
+        const uint8_t* q1 = B.qual1 + (B.qs1[p] - B.base1);
         int len2 = 0;
         const uint8_t *s2 = nullptr, *q2 = nullptr;
         if (PAIRED) {
-            const uint64_t o2 = __ldg(B.off2 + p), e2 = __ldg(B.off2 + p + 1);
+            const uint64_t o2 = __ldg(B.s2 + p), e2 = __ldg(B.e2 + p);
             len2 = (int)(e2 - o2);
             s2 = B.seq2 + (o2 - B.base2);
-            q2 = B.qual2 + (o2 - B.base2);
+            q2 = B.qual2 + (B.qs2[p] - B.base2);
         }
         if (len1 > 32 * MAXW || len2 > 32 * MAXW || len1 < 0 || len2 < 0) {
             err |= 1u;
@@ -680,16 +680,16 @@ __global__ void __launch_bounds__(256) k_merge_only(GfDevBatch B, gf_merge_info*
     ScreenWarp<MAXW>& S = Sall[threadIdx.x >> 5];
     const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
     for (uint64_t p = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < B.n; p += n_warps) {
-        const uint64_t o1 = B.off1[p], o2 = B.off2[p];
-        const int len1 = (int)(B.off1[p + 1] - o1), len2 = (int)(B.off2[p + 1] - o2);
+        const uint64_t o1 = B.s1[p], o2 = B.s2[p];
+        const int len1 = (int)(B.e1[p] - o1), len2 = (int)(B.e2[p] - o2);
         if (len1 > 32 * MAXW || len2 > 32 * MAXW) {
             if (lane == 0) atomicOr(&counters->error_flags, 1u);
             continue;
         }
         __syncwarp();
-        planes_r1<MAXW>(S, B.seq1 + (o1 - B.base1), B.qual1 + (o1 - B.base1), len1, B.seq1, B.seq1 + B.bytes1, B.qual1,
+        planes_r1<MAXW>(S, B.seq1 + (o1 - B.base1), B.qual1 + (B.qs1[p] - B.base1), len1, B.seq1, B.seq1 + B.bytes1, B.qual1,
                         B.qual1 + B.bytes1);
-        planes_r2<MAXW>(S, B.seq2 + (o2 - B.base2), B.qual2 + (o2 - B.base2), len2, B.seq2, B.seq2 + B.bytes2, B.qual2,
+        planes_r2<MAXW>(S, B.seq2 + (o2 - B.base2), B.qual2 + (B.qs2[p] - B.base2), len2, B.seq2, B.seq2 + B.bytes2, B.qual2,
                         B.qual2 + B.bytes2);
         __syncwarp();
         int diff = 0;
@@ -712,23 +712,23 @@ __global__ void __launch_bounds__(256) k_merge_only(GfDevBatch B, gf_merge_info*
  * source 0 = merged read (literal read.rs:369-428 given the overlap length), 1 = R1, 2 = R2. */
 __device__ int load_sequence(const GfDevBatch& B, uint32_t pair, uint32_t source, int olen, uint8_t* seq) {
     const uint32_t lane = gf_lane();
-    const uint64_t o1 = B.off1[pair];
-    const int len1 = (int)(B.off1[pair + 1] - o1);
+    const uint64_t o1 = B.s1[pair];
+    const int len1 = (int)(B.e1[pair] - o1);
     const uint8_t* s1 = B.seq1 + (o1 - B.base1);
     int len;
     if (source == 1) {
         for (int j = (int)lane; j < len1; j += 32) seq[j] = s1[j];
         len = len1;
     } else {
-        const uint64_t o2 = B.off2[pair];
-        const int len2 = (int)(B.off2[pair + 1] - o2);
+        const uint64_t o2 = B.s2[pair];
+        const int len2 = (int)(B.e2[pair] - o2);
         const uint8_t* s2 = B.seq2 + (o2 - B.base2);
         if (source == 2) {
             for (int j = (int)lane; j < len2; j += 32) seq[j] = s2[j];
             len = len2;
         } else {
-            const uint8_t* q1 = B.qual1 + (o1 - B.base1);
-            const uint8_t* q2 = B.qual2 + (o2 - B.base2);
+            const uint8_t* q1 = B.qual1 + (B.qs1[pair] - B.base1);
+            const uint8_t* q2 = B.qual2 + (B.qs2[pair] - B.base2);
             const int offset = len1 - olen;
             for (int j = (int)lane; j < offset; j += 32) seq[j] = s1[j];
             for (int i = (int)lane; i < len2; i += 32) {

@@ -70,30 +70,19 @@ __global__ void __launch_bounds__(tpp::WARPS * 32) k_prep(PrepParams P) {
 
     for (uint64_t base = ((uint64_t)blockIdx.x * tpp::WARPS + wib) * 32; base < B.n; base += n_warps * 32) {
         const uint64_t p = base + lane;
-        {   /* pull the bases of the pair this thread converts NEXT into L2 */
-            const uint64_t pn = p + n_warps * 32;
-            if (P.prefetch && pn < B.n) {
-                const uint64_t a = __ldg(B.off1 + pn), e = __ldg(B.off1 + pn + 1);
-                for (uint64_t x = a & ~31ull; x < e; x += 32) tpp::prefetch_l2(B.seq1 + (x > B.base1 ? x - B.base1 : 0));
-                if (PAIRED) {
-                    const uint64_t a2 = __ldg(B.off2 + pn), e2 = __ldg(B.off2 + pn + 1);
-                    for (uint64_t x = a2 & ~31ull; x < e2; x += 32) tpp::prefetch_l2(B.seq2 + (x > B.base2 ? x - B.base2 : 0));
-                }
-            }
-        }
         int len1 = 0, len2 = 0, olen = -1, diff = 0, nseq = 0;
         const uint8_t *q1 = nullptr, *q2 = nullptr;
         if (p < B.n) {
-            const uint64_t o1 = __ldg(B.off1 + p);
-            len1 = (int)(__ldg(B.off1 + p + 1) - o1);
+            const uint64_t o1 = __ldg(B.s1 + p);
+            len1 = (int)(__ldg(B.e1 + p) - o1);
             const uint8_t* s1 = B.seq1 + (o1 - B.base1);
-            q1 = B.qual1 + (o1 - B.base1);
+            q1 = B.qual1 + (B.qs1[p] - B.base1);
             const uint8_t* s2 = nullptr;
             if (PAIRED) {
-                const uint64_t o2 = __ldg(B.off2 + p);
-                len2 = (int)(__ldg(B.off2 + p + 1) - o2);
+                const uint64_t o2 = __ldg(B.s2 + p);
+                len2 = (int)(__ldg(B.e2 + p) - o2);
                 s2 = B.seq2 + (o2 - B.base2);
-                q2 = B.qual2 + (o2 - B.base2);
+                q2 = B.qual2 + (B.qs2[p] - B.base2);
             }
             if (len1 > 32 * W || len2 > 32 * W || len1 < 0 || len2 < 0) {
                 err |= 1u;

@@ -409,29 +409,18 @@ __global__ void __launch_bounds__(WARPS * 32) k_screen_tpp(ScreenParams P) {
 
     for (uint64_t base = ((uint64_t)blockIdx.x * WARPS + wib) * 32; base < B.n; base += n_warps * 32) {
         const uint64_t p = base + lane;
-        {   /* pull the bases of the pair this thread maps NEXT into L2 while it works on the current one */
-            const uint64_t pn = p + n_warps * 32;
-            if (pn < B.n) {
-                const uint64_t a = __ldg(B.off1 + pn), e = __ldg(B.off1 + pn + 1);
-                for (uint64_t x = a & ~31ull; x < e; x += 32) prefetch_l2(B.seq1 + (x > B.base1 ? x - B.base1 : 0));
-                if (PAIRED) {
-                    const uint64_t a2 = __ldg(B.off2 + pn), e2 = __ldg(B.off2 + pn + 1);
-                    for (uint64_t x = a2 & ~31ull; x < e2; x += 32) prefetch_l2(B.seq2 + (x > B.base2 ? x - B.base2 : 0));
-                }
-            }
-        }
         if (p < B.n) {
-            const uint64_t o1 = __ldg(B.off1 + p);
-            const int len1 = (int)(__ldg(B.off1 + p + 1) - o1);
+            const uint64_t o1 = __ldg(B.s1 + p);
+            const int len1 = (int)(__ldg(B.e1 + p) - o1);
             const uint8_t* s1 = B.seq1 + (o1 - B.base1);
-            const uint8_t* q1 = B.qual1 + (o1 - B.base1);
+            const uint8_t* q1 = B.qual1 + (B.qs1[p] - B.base1);
             int len2 = 0;
             const uint8_t *s2 = nullptr, *q2 = nullptr;
             if (PAIRED) {
-                const uint64_t o2 = __ldg(B.off2 + p);
-                len2 = (int)(__ldg(B.off2 + p + 1) - o2);
+                const uint64_t o2 = __ldg(B.s2 + p);
+                len2 = (int)(__ldg(B.e2 + p) - o2);
                 s2 = B.seq2 + (o2 - B.base2);
-                q2 = B.qual2 + (o2 - B.base2);
+                q2 = B.qual2 + (B.qs2[p] - B.base2);
             }
             if (len1 > 32 * W || len2 > 32 * W || len1 < 0 || len2 < 0) {
                 err |= 1u;
@@ -498,13 +487,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_merge_only_tpp(GfDevBatch B, gf_
     c.base = sm + (size_t)wib * Lay<W>::NWORDS * 32 + lane;
     const uint64_t stride = (uint64_t)gridDim.x * WARPS * 32;
     for (uint64_t p = ((uint64_t)blockIdx.x * WARPS + wib) * 32 + lane; p < B.n; p += stride) {
-        const uint64_t o1 = B.off1[p], o2 = B.off2[p];
-        const int len1 = (int)(B.off1[p + 1] - o1), len2 = (int)(B.off2[p + 1] - o2);
+        const uint64_t o1 = B.s1[p], o2 = B.s2[p];
+        const int len1 = (int)(B.e1[p] - o1), len2 = (int)(B.e2[p] - o2);
         if (len1 > 32 * W || len2 > 32 * W) { atomicOr(&counters->error_flags, 1u); continue; }
         convert_r1<W>(c, B.seq1 + (o1 - B.base1), len1, B.seq1, B.seq1 + B.bytes1, make_policy_stream());
         convert_r2_rc<W>(c, B.seq2 + (o2 - B.base2), len2, B.seq2, B.seq2 + B.bytes2, make_policy_stream());
         int diff = 0;
-        int olen = find_overlap<W>(c, len1, len2, B.qual1 + (o1 - B.base1), B.qual2 + (o2 - B.base2), &diff);
+        int olen = find_overlap<W>(c, len1, len2, B.qual1 + (B.qs1[p] - B.base1), B.qual2 + (B.qs2[p] - B.base2), &diff);
         gf_merge_info mi;
         mi.merged = olen >= 0;
         mi.olen = olen >= 0 ? olen : 0;

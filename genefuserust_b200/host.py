@@ -270,6 +270,21 @@ class FusionMapper:
         assert not batch.paired
         return self._map(batch)
 
+    def scan_fastq(self, fq1, fq2=None):
+        """raw FASTQ text (bytes) -> matches; the records are split on the device (gf_map_fastq)"""
+        cap = 4096
+        while True:
+            out = (gf_match * cap)()
+            n, nrec = C.c_uint64(0), C.c_uint64(0)
+            rc = self.lib.gf_map_fastq(self.m_indexer.h, fq1, len(fq1), fq2, len(fq2) if fq2 is not None else 0, out, cap,
+                                       C.byref(n), C.byref(nrec))
+            if rc == GF_E_CAPACITY:
+                cap = int(n.value)
+                continue
+            _check(self.lib, rc, allow=(GF_E_REF_PANIC,))
+            self.last_rc = rc
+            return [out[i] for i in range(n.value)], int(nrec.value)
+
     def fast_merge(self, batch):
         out = (gf_merge_info * max(1, batch.n))()
         st = batch.as_struct()

@@ -203,6 +203,15 @@ int gf_map_pairs_device(gf_index* idx, const gf_batch* in_dev, gf_match* d_out, 
                         uint64_t* d_n_out, void* cuda_stream);
 void gf_sort_matches(gf_match* m, uint64_t n); /* by (pair_idx, source), host */
 
+/* Map reads given as raw FASTQ text in HOST memory (replaces FastqReader::read + the pack loop,
+ * src/core/fastq_reader.rs:75-147, src/core/pescanner.rs:190-249): the text is copied to the device, split
+ * into records there (four lines per record, one trailing '\n' stripped per line, nothing validated, an
+ * incomplete trailing record is ignored) and mapped without repacking.  fq2 == NULL for single end; for pairs
+ * the number of records is the smaller of the two files', like FastqReaderPair.  pair_idx in the output
+ * counts records from the start of the buffers.  *n_records = records (pairs) mapped. */
+int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8_t* fq2, uint64_t bytes2,
+                 gf_match* out, uint64_t out_cap, uint64_t* n_out, uint64_t* n_records);
+
 int gf_get_map_stats(const gf_index* idx, gf_map_stats* out);
 
 /* Parity hook: run only the device fast_merge on a HOST batch. */

@@ -345,3 +345,79 @@ def test_list_mode_concurrent_handles(host, small_panel):
     assert len({len(r) for r in results}) > 1   # the panels really give different answers
     for m in mappers:
         m.close()
+
+
+def _fastq_reader_reference(text):
+    """FastqReader::read restated (src/core/fastq_reader.rs:75-147): four read_line calls per record, each line loses
+    one trailing '\\n'; a record is returned only if all four reads returned > 0 bytes"""
+    recs = []
+    pos = 0
+
+    def read_line():
+        nonlocal pos
+        if pos >= len(text):
+            return None
+        k = text.find(b"\n", pos)
+        line = text[pos:] if k < 0 else text[pos:k + 1]
+        pos += len(line)
+        return line[:-1] if line.endswith(b"\n") else line
+    while True:
+        four = [read_line() for _ in range(4)]
+        if any(x is None for x in four):
+            break
+        recs.append((four[1], four[3]))
+    return recs
+
+
+def _to_fastq(batch, mate, rng, eol=b"\n", final_newline=True, extra_tail=b""):
+    out = []
+    for i in range(batch.n):
+        s, q = batch.read(i, mate)
+        name = b"@SYN:%d:%d %d:N:0:ACGT" % (i, rng.randint(0, 99999), mate)
+        out.append(name + eol + s + eol + b"+" + eol + q + eol)
+    text = b"".join(out)
+    if not final_newline and text.endswith(b"\n"):
+        text = text[:-1]
+    return text + extra_tail
+
+
+@pytest.mark.parametrize("variant", ["plain", "no_final_newline", "crlf", "truncated_tail"])
+def test_fastq_ingest_parity(mappers, small_panel, variant):
+    """device FASTQ record splitting (gf_map_fastq) vs the reference reader's semantics + the oracle"""
+    m, o = mappers
+    rng = random.Random(9)
+    b = synth.generate_pairs(small_panel, 20000, read_len=150, seed=61, p_fusion=0.05)
+    kw = {}
+    if variant == "no_final_newline":
+        kw = dict(final_newline=False)
+    elif variant == "crlf":
+        kw = dict(eol=b"\r\n")          # '\r' is NOT stripped by the reference: it stays in sequence and quality
+    elif variant == "truncated_tail":
+        kw = dict(extra_tail=b"@incomplete\nACGTACGT\n+\n")   # dropped at EOF
+    fq1, fq2 = _to_fastq(b, 1, rng, **kw), _to_fastq(b, 2, rng, **kw)
+    r1, r2 = _fastq_reader_reference(fq1), _fastq_reader_reference(fq2)
+    n = min(len(r1), len(r2))
+    assert n == b.n
+    ref_batch = ReadBatch.from_reads(r1[:n], r2[:n])
+    want = o.scan(ref_batch, threads=8)
+    got, nrec = m.scan_fastq(fq1, fq2)
+    assert nrec == n
+    assert_same_matches(got, want, variant)
+    if variant != "crlf":
+        assert len(want) > 50
+    # single end
+    got_se, nrec = m.scan_fastq(fq1, None)
+    want_se = o.scan(ReadBatch.from_reads(r1), threads=8)
+    assert nrec == len(r1)
+    assert_same_matches(got_se, want_se, variant + " SE")
+
+
+def test_fastq_ingest_testdata(host):
+    """the reference's own testdata R1.fq / R2.fq through the device FASTQ path: 3 records, 0 matches, merge lengths"""
+    td = os.path.join(GOLD, "testdata")
+    fq1, fq2 = open(os.path.join(td, "R1.fq"), "rb").read(), open(os.path.join(td, "R2.fq"), "rb").read()
+    m = host.FusionMapper.from_ref_and_fusion_files(os.path.join(td, "tinyref.fa"), os.path.join(td, "fusions.csv"))
+    got, nrec = m.scan_fastq(fq1, fq2)
+    assert (got, nrec) == ([], 3)
+    assert len(_fastq_reader_reference(fq1)) == 3
+    m.close()
