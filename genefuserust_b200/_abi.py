@@ -26,12 +26,13 @@ class gf_params(C.Structure):
         ("major_gene_key_requirement", C.c_int32),
         ("minor_gene_key_requirement", C.c_int32),
         ("mismatch_threshold", C.c_int32),
+        ("deletion_threshold", C.c_int32),
     ]
 
     @classmethod
     def default(cls):
         # src/aux/global_settings.rs:15-29
-        return cls(5, 40, 20, 10)
+        return cls(5, 40, 20, 10, 50)
 
 
 class gf_batch(C.Structure):
@@ -67,12 +68,12 @@ class gf_match(C.Structure):
         ("source", C.c_uint8),
         ("used_rc", C.c_uint8),
         ("reversed", C.c_uint8),
-        ("pad", C.c_uint8),
+        ("filter_flags", C.c_uint8),
     ]
 
     FIELDS = (
         "pair_idx", "source", "used_rc", "reversed", "read_break", "l_contig", "l_pos", "r_contig", "r_pos",
-        "gap", "l_dist", "r_dist", "seq_len", "merge_olen", "merge_diff",
+        "gap", "l_dist", "r_dist", "seq_len", "merge_olen", "merge_diff", "filter_flags",
     )
 
     def astuple(self):

@@ -95,6 +95,7 @@ void gf_default_params(gf_params* p) {
     p->major_gene_key_requirement = 40;
     p->minor_gene_key_requirement = 20;
     p->mismatch_threshold = 10;
+    p->deletion_threshold = 50;
 }
 
 int gf_index_create(const gf_gene_span* genes, uint32_t n_genes, const gf_params* params, int device,

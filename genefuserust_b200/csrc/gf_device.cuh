@@ -59,7 +59,7 @@ struct GfDevIndex {
     uint32_t max_sites;         /* most sites a NORMAL key holds = max(skip_key_dup_threshold, 2) */
     uint32_t bucket_shift;      /* 32 - bucket_bits */
     uint32_t bucket_mask;
-    int32_t major_req, minor_req, mismatch_thr; /* gf_params */
+    int32_t major_req, minor_req, mismatch_thr, deletion_thr; /* gf_params */
 };
 
 /* base classification -------------------------------------------------------------------- */

@@ -569,6 +569,7 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     idx->dev.major_req = idx->params.major_gene_key_requirement;
     idx->dev.minor_req = idx->params.minor_gene_key_requirement;
     idx->dev.mismatch_thr = idx->params.mismatch_threshold;
+    idx->dev.deletion_thr = idx->params.deletion_threshold;
     idx->dev.filter = (const unsigned long long*)idx->d_filter;
     idx->dev.filter_words = filter_words;
 

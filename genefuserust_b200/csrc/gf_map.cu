@@ -1007,7 +1007,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) k_exact(ExactParams P) {
                         m.used_rc = (uint8_t)attempt;
                         /* set_reversed(true) only on the R1/R2 retries (pescanner.rs:483,506), never merged (:455-469) */
                         m.reversed = (uint8_t)(attempt == 1 && source != 0);
-                        m.pad = 0;
+                        m.filter_flags = 0;
                         P.out[slot] = m;
                     }
                 }
@@ -1127,9 +1127,22 @@ __global__ void __launch_bounds__(VF_WARPS * 32) k_verify(VerifyParams P) {
         uint32_t panic = 0;
         int ld = calc_ed(P.ix, W.seq, left_len, m.l_contig, m.l_pos - left_len + 1, m.l_pos, &panic);
         int rd = calc_ed(P.ix, W.seq + rb + 1, right_len, m.r_contig, m.r_pos, m.r_pos + right_len - 1, &panic);
+        /* what filter_matches would decide (fusion_mapper.rs:298-377); the record is kept either way */
+        int chg_l = 0, chg_r = 0; /* dis_connected_count (src/utils/mod.rs:48-56) of both sides of the break */
+        for (int i = (int)lane; i + 1 < left_len; i += 32) chg_l += W.seq[i] != W.seq[i + 1];
+        for (int i = (int)lane; i + 1 < right_len; i += 32) chg_r += W.seq[rb + 1 + i] != W.seq[rb + 2 + i];
+        chg_l = (int)__reduce_add_sync(FULL, (unsigned)chg_l);
+        chg_r = (int)__reduce_add_sync(FULL, (unsigned)chg_r);
         if (lane == 0) {
+            uint32_t ff = 0;
+            if (left_len < 20 || chg_l < 7 || right_len < 20 || chg_r < 7) ff |= GF_FILTER_COMPLEXITY;
+            if (ld + rd >= 5) ff |= GF_FILTER_DISTANCE;
+            int dpos = m.l_pos - m.r_pos;
+            if (dpos < 0) dpos = -dpos;
+            if (m.l_contig == m.r_contig && dpos < P.ix.deletion_thr) ff |= GF_FILTER_INDEL;
             P.out[ci].l_dist = ld;
             P.out[ci].r_dist = rd;
+            P.out[ci].filter_flags = (uint8_t)ff;
             if (panic) atomicAdd(&P.counters->n_ref_panic, 1u);
         }
     }

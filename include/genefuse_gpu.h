@@ -67,6 +67,7 @@ typedef struct gf_params {
     int32_t major_gene_key_requirement;  /* 40 */
     int32_t minor_gene_key_requirement;  /* 20 */
     int32_t mismatch_threshold;          /* 10 */
+    int32_t deletion_threshold;          /* 50, CLI -d (src/argparse.rs:66-73); only used for GF_FILTER_INDEL */
 } gf_params;
 
 /* A batch of read pairs (PE) or reads (SE: seq2 == qual2 == off2 == NULL) as
@@ -112,8 +113,13 @@ typedef struct gf_match {
     uint8_t source;      /* 0 = merged read, 1 = R1, 2 = R2 */
     uint8_t used_rc;     /* 1 = the match was found on the reverse complement (rc retry) */
     uint8_t reversed;    /* m_reversed: set only for R1/R2 rc matches (pescanner.rs:483,506), never for merged */
-    uint8_t pad;
+    uint8_t filter_flags; /* what FusionMapper::filter_matches would do with this record (src/core/fusion_mapper.rs:298-377):
+                             GF_FILTER_COMPLEXITY | GF_FILTER_DISTANCE | GF_FILTER_INDEL; 0 = survives all three.
+                             Records are never dropped by the library: the host filters run unchanged. */
 } gf_match;
+#define GF_FILTER_COMPLEXITY 1u /* remove_by_complexity: a side of the break is < 20 chars or has < 7 base changes */
+#define GF_FILTER_DISTANCE 2u   /* remove_by_distance: l_dist + r_dist >= 5 */
+#define GF_FILTER_INDEL 4u      /* remove_indels: same contig and |l_pos - r_pos| < deletion_threshold */
 
 typedef struct gf_index gf_index; /* opaque */
 

@@ -477,6 +477,21 @@ struct orc_index {
         m->l_dist = calc_ed(seq, left_len, m->l_contig, m->l_pos - left_len + 1, m->l_pos, would_panic);
         m->r_dist = calc_ed(seq + read_break + 1, right_len, m->r_contig, m->r_pos, m->r_pos + right_len - 1,
                             would_panic);
+        /* what filter_matches would decide for this record (src/core/fusion_mapper.rs:298-377) */
+        auto is_low_complexity = [](const uint8_t* s, int32_t n) { /* :559-569 + src/utils/mod.rs:48-56 */
+            if (n < 20) return true;
+            int32_t diff = 0;
+            for (int32_t i = 0; i < n - 1; i++)
+                if (s[i] != s[i + 1]) diff++;
+            return diff < 7;
+        };
+        uint8_t ff = 0;
+        if (is_low_complexity(seq, read_break + 1) || is_low_complexity(seq + read_break + 1, seqlen - (read_break + 1)))
+            ff |= GF_FILTER_COMPLEXITY;                                                   /* remove_by_complexity :298-321 */
+        if (m->l_dist + m->r_dist >= 5) ff |= GF_FILTER_DISTANCE;                         /* remove_by_distance :323-348 */
+        if (m->l_contig == m->r_contig && std::abs(m->l_pos - m->r_pos) < p.deletion_threshold)
+            ff |= GF_FILTER_INDEL;                                                        /* remove_indels :350-377 */
+        m->filter_flags = ff;
         return 1;
     }
 };

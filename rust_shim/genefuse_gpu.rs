@@ -19,6 +19,7 @@ pub struct gf_params {
     pub major_gene_key_requirement: i32,
     pub minor_gene_key_requirement: i32,
     pub mismatch_threshold: i32,
+    pub deletion_threshold: i32,
 }
 
 #[repr(C)]
@@ -37,7 +38,7 @@ pub struct gf_match {
     pub read_break: i32, pub l_pos: i32, pub r_pos: i32, pub gap: i32,
     pub l_dist: i32, pub r_dist: i32, pub seq_len: i32,
     pub l_contig: i16, pub r_contig: i16, pub merge_olen: i16, pub merge_diff: i16,
-    pub source: u8, pub used_rc: u8, pub reversed: u8, pub pad: u8,
+    pub source: u8, pub used_rc: u8, pub reversed: u8, pub filter_flags: u8,
 }
 
 #[repr(C)] pub struct gf_index { _private: [u8; 0] }

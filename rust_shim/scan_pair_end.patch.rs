@@ -49,5 +49,6 @@ fn scan_pair_end(&self, pack: ReadPairPack<'s>) -> Result<bool, Error> {
 //         .map(|(s, f)| (s.as_bytes(), f.is_reversed())).collect();
 //     self.gpu = GpuIndex::build(&genes, gf_params { skip_key_dup_threshold: gs.skip_key_dup_threshold as i32,
 //         major_gene_key_requirement: gs.major_gene_key_requirement, minor_gene_key_requirement:
-//         gs.minor_gene_key_requirement, mismatch_threshold: gs.mismatch_threshold }, device).unwrap();
+//         gs.minor_gene_key_requirement, mismatch_threshold: gs.mismatch_threshold,
+//         deletion_threshold: gs.deletion_threshold as i32 }, device).unwrap();
 // m_kmer_pos / m_dupe_list / m_bloom_filter (indexer.rs:74-76) and the 512 MiB allocation (:94,108) disappear.

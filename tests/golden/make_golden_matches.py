@@ -21,6 +21,6 @@ cfg["reads_sha256"] = hashlib.sha256(batch.seq1.tobytes() + batch.seq2.tobytes()
 cfg["index_counts"] = idx.counts()
 cfg["matches"] = [list(r) for r in idx.scan(batch, threads=4)]
 cfg["fields"] = ["pair_idx", "source", "used_rc", "reversed", "read_break", "l_contig", "l_pos", "r_contig", "r_pos",
-                 "gap", "l_dist", "r_dist", "seq_len", "merge_olen", "merge_diff"]
+                 "gap", "l_dist", "r_dist", "seq_len", "merge_olen", "merge_diff", "filter_flags"]
 json.dump(cfg, open(os.path.join(HERE, "synth_small_matches.json"), "w"))
 print(len(cfg["matches"]), "matches")

@@ -161,7 +161,6 @@ def test_scan_pair_end_noisy_fusions(mappers, small_panel):
     assert len(want) > 2000
     assert any(w[10] > 0 or w[11] > 0 for w in want)       # non-zero distances
     assert any(w[2] == 1 for w in want)                     # rc retries
-    assert any(w[10] < 0 or w[11] < 0 for w in want) or True
     assert_same_matches(got, want, "noisy")
 
 
@@ -287,7 +286,8 @@ def test_full_size_properties(host):
     assert got == lo + [(r[0] + half,) + r[1:] for r in hi]                       # shard-invariant
     assert got == sorted(got, key=lambda r: (r[0], r[1]))                         # (pair_idx, source) order
     for r in got:
-        pair, source, used_rc, reversed_, rb, lc, lp, rc, rp, gap, ld, rd, slen, olen, diff = r
+        pair, source, used_rc, reversed_, rb, lc, lp, rc, rp, gap, ld, rd, slen, olen, diff, ff = r
+        assert (ff & 2) == (2 if ld + rd >= 5 else 0) and ff < 8
         assert 0 <= pair < n and source in (0, 1, 2) and 0 <= rb < slen
         assert reversed_ == (1 if (used_rc and source != 0) else 0)
         assert (olen >= 30) == (source == 0) and 0 <= diff <= 2
@@ -421,3 +421,42 @@ def test_fastq_ingest_testdata(host):
     assert (got, nrec) == ([], 3)
     assert len(_fastq_reader_reference(fq1)) == 3
     m.close()
+
+
+def test_filter_flags(host):
+    """filter_matches predicates (fusion_mapper.rs:298-377) as flags on the records: low complexity, distance >= 5,
+    indel; crafted so that every flag occurs"""
+    rng = random.Random(4)
+    rnd = lambda n: bytes(rng.choice(b"ACGT") for _ in range(n))
+    lowc = b"A" * 12 + b"C" * 13 + b"G" * 14 + b"T" * 15 + b"A" * 16          # 70 bases, 4 changes, unique 16-mers
+    gene_a = rnd(400) + lowc + rnd(400)
+    gene_b = rnd(1000)
+    genes = [(gene_a, False), (gene_b, False)]
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    reads = []
+    for k in range(400):
+        kind = k % 4
+        if kind == 0:      # clean fusion B | A-lowc : right side is low complexity
+            frag = gene_b[300:400] + gene_a[400:400 + 50]
+        elif kind == 1:    # fusion with many substitutions -> distance flag
+            frag = bytearray(gene_b[100:180] + gene_a[100:170])
+            for _ in range(6):
+                frag[rng.randrange(20, 130)] = rng.choice(b"ACGT")
+            frag = bytes(frag)
+        elif kind == 2:    # same-gene "fusion" 30 bases apart -> indel flag
+            frag = gene_b[500:575] + gene_b[605:680]
+        else:              # plain fusion
+            frag = gene_a[50:125] + gene_b[600:675]
+        if rng.random() < 0.5:
+            frag = frag[::-1].translate(comp)
+        reads.append((frag, b"E" * len(frag)))
+    b = ReadBatch.from_reads(reads)
+    m = host.FusionMapper.from_gene_spans(genes, device=0)
+    o = orc.OracleIndex(genes)
+    got = m.scan_single_end(b)
+    want = o.scan(b, threads=4)
+    assert_same_matches(got, want, "flags")
+    flags = {w[15] for w in want}
+    assert any(f & 1 for f in flags) and any(f & 2 for f in flags) and any(f & 4 for f in flags) and 0 in flags, flags
+    m.close()
+    o.close()

@@ -33,13 +33,13 @@ def test_library_exports_every_declared_symbol(built):
     p = _abi.gf_params()
     built.gf_default_params(C.byref(p))
     assert (p.skip_key_dup_threshold, p.major_gene_key_requirement, p.minor_gene_key_requirement,
-            p.mismatch_threshold) == (5, 40, 20, 10)   # src/aux/global_settings.rs:15-29
+            p.mismatch_threshold, p.deletion_threshold) == (5, 40, 20, 10, 50)   # src/aux/global_settings.rs:15-29
 
 
 def test_struct_sizes_match_header():
     assert C.sizeof(_abi.gf_match) == 48
     assert C.sizeof(_abi.gf_batch) == 80
-    assert C.sizeof(_abi.gf_params) == 16
+    assert C.sizeof(_abi.gf_params) == 20
 
 
 def test_no_device_fails_loudly(built):
