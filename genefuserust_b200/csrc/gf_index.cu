@@ -385,6 +385,24 @@ struct PhaseTimer { /* GF_DEBUG_TIMING=1: host wall clock per build phase on std
 };
 }  // namespace
 
+namespace {
+/* one device allocation for every temporary of the build (cudaMalloc/cudaFree are slow, synchronising calls) */
+struct BuildWorkspace {
+    char* base = nullptr;
+    size_t cap = 0, used = 0;
+    ~BuildWorkspace() { if (base) cudaFree(base); }
+    cudaError_t init(size_t bytes) { cap = bytes; return cudaMalloc((void**)&base, bytes); }
+    template <class T>
+    T* take(size_t n) {
+        size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+        if (used + bytes > cap) return nullptr;
+        T* p = reinterpret_cast<T*>(base + used);
+        used += bytes;
+        return p;
+    }
+};
+}  // namespace
+
 int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_genes) {
     PhaseTimer pt;
     /* index_contig (:202-239): the 2nd occurrence always opens a dupe list of 2; occurrence n >= 3 is pushed
@@ -453,10 +471,17 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     pt.mark("upload genes");
     /* 1. flags -> positions -> compacted (key, site) items */
     const uint64_t n_flags = 2 * arena_len;
-    uint32_t *d_flags = nullptr, *d_pos = nullptr, *d_tmp = nullptr;
-    GF_CUDA_TRY(cudaMalloc(&d_flags, sizeof(uint32_t) * n_flags));
-    GF_CUDA_TRY(cudaMalloc(&d_pos, sizeof(uint32_t) * (n_flags + 1)));
-    GF_CUDA_TRY(cudaMalloc(&d_tmp, sizeof(uint32_t) * scan_tmp_elems(n_flags)));
+    const uint64_t max_tiles = (n_flags + RS_TILE - 1) / RS_TILE, max_hist = 256ull * max_tiles;
+    BuildWorkspace ws;
+    {
+        size_t need = 4 * (n_flags + 64) * 4 /* flags, pos, ncnt, doff */ + 8 * (n_flags + 64) * 2 /* items x2 */ +
+                      4 * (max_hist + 64) * 2 + 4 * (scan_tmp_elems(n_flags + 1) * 2 + scan_tmp_elems(max_hist)) + 4096 +
+                      256 * 16;
+        GF_CUDA_TRY(ws.init(need));
+    }
+    uint32_t* d_flags = ws.take<uint32_t>(n_flags);
+    uint32_t* d_pos = ws.take<uint32_t>(n_flags + 1);
+    uint32_t* d_tmp = ws.take<uint32_t>(scan_tmp_elems(n_flags));
     const unsigned ex_blocks = (unsigned)((arena_len + EX_THREADS - 1) / EX_THREADS);
     k_extract_flags<<<ex_blocks, EX_THREADS, 0, st>>>((const uint8_t*)idx->d_gene_ascii, arena_len, d_flags);
     GF_CUDA_TRY(exclusive_scan(d_flags, d_pos, n_flags, d_tmp, st));
@@ -464,24 +489,20 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     GF_CUDA_TRY(cudaMemcpyAsync(&n_items32, d_pos + n_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     GF_CUDA_TRY(cudaStreamSynchronize(st));
     const uint64_t n_items = n_items32;
-    unsigned long long *d_items = nullptr, *d_items2 = nullptr;
-    GF_CUDA_TRY(cudaMalloc(&d_items, sizeof(unsigned long long) * (n_items + 1)));
-    GF_CUDA_TRY(cudaMalloc(&d_items2, sizeof(unsigned long long) * (n_items + 1)));
+    unsigned long long* d_items = ws.take<unsigned long long>(n_items + 1);
+    unsigned long long* d_items2 = ws.take<unsigned long long>(n_items + 1);
     k_extract_items<<<ex_blocks, EX_THREADS, 0, st>>>((const uint8_t*)idx->d_gene_ascii, arena_len, d_pos, d_items);
     GF_CUDA_TRY(cudaGetLastError());
-    GF_CUDA_TRY(cudaFree(d_flags));
-    GF_CUDA_TRY(cudaFree(d_pos));
-    GF_CUDA_TRY(cudaFree(d_tmp));
 
     pt.mark("extract k-mers");
     /* 2. radix sort by key */
     if (n_items > 1) {
         const uint32_t n_tiles = (uint32_t)((n_items + RS_TILE - 1) / RS_TILE);
         const uint64_t n_hist = 256ull * n_tiles;
-        uint32_t *d_hist = nullptr, *d_offs = nullptr, *d_stmp = nullptr;
-        GF_CUDA_TRY(cudaMalloc(&d_hist, sizeof(uint32_t) * n_hist));
-        GF_CUDA_TRY(cudaMalloc(&d_offs, sizeof(uint32_t) * (n_hist + 1)));
-        GF_CUDA_TRY(cudaMalloc(&d_stmp, sizeof(uint32_t) * scan_tmp_elems(n_hist)));
+        uint32_t* d_hist = ws.take<uint32_t>(n_hist);
+        uint32_t* d_offs = ws.take<uint32_t>(n_hist + 1);
+        uint32_t* d_stmp = ws.take<uint32_t>(scan_tmp_elems(n_hist));
+        if (!d_hist || !d_offs || !d_stmp) { gf_set_error("internal: build workspace too small"); return GF_E_CUDA; }
         const unsigned rs_blocks = (n_tiles + RS_WARPS - 1) / RS_WARPS;
         for (int pass = 0; pass < 4; pass++) {
             int shift = 32 + 8 * pass;
@@ -492,20 +513,18 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
         }
         GF_CUDA_TRY(cudaGetLastError());
         GF_CUDA_TRY(cudaStreamSynchronize(st));
-        GF_CUDA_TRY(cudaFree(d_hist));
-        GF_CUDA_TRY(cudaFree(d_offs));
-        GF_CUDA_TRY(cudaFree(d_stmp));
     }
-    GF_CUDA_TRY(cudaFree(d_items2));
 
     pt.mark("radix sort");
     /* 3. classify runs */
-    uint32_t *d_ncnt = nullptr, *d_doff = nullptr, *d_tmp2 = nullptr;
-    unsigned long long* d_stats = nullptr;
-    GF_CUDA_TRY(cudaMalloc(&d_ncnt, sizeof(uint32_t) * (n_items + 1)));
-    GF_CUDA_TRY(cudaMalloc(&d_doff, sizeof(uint32_t) * (n_items + 2)));
-    GF_CUDA_TRY(cudaMalloc(&d_tmp2, sizeof(uint32_t) * scan_tmp_elems(n_items + 1)));
-    GF_CUDA_TRY(cudaMalloc(&d_stats, sizeof(unsigned long long) * 8));
+    uint32_t* d_ncnt = ws.take<uint32_t>(n_items + 1);
+    uint32_t* d_doff = ws.take<uint32_t>(n_items + 2);
+    uint32_t* d_tmp2 = ws.take<uint32_t>(scan_tmp_elems(n_items + 1));
+    unsigned long long* d_stats = ws.take<unsigned long long>(8);
+    if (!d_flags || !d_pos || !d_tmp || !d_items || !d_items2 || !d_ncnt || !d_doff || !d_tmp2 || !d_stats) {
+        gf_set_error("internal: build workspace too small");
+        return GF_E_CUDA;
+    }
     GF_CUDA_TRY(cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * 8, st));
     unsigned long long h_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t n_dupes = 0;
@@ -549,11 +568,6 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     unsigned int h_maxdisp = 0;
     GF_CUDA_TRY(cudaMemcpyAsync(&h_maxdisp, d_maxdisp, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     GF_CUDA_TRY(cudaStreamSynchronize(st));
-    GF_CUDA_TRY(cudaFree(d_items));
-    GF_CUDA_TRY(cudaFree(d_ncnt));
-    GF_CUDA_TRY(cudaFree(d_doff));
-    GF_CUDA_TRY(cudaFree(d_tmp2));
-    GF_CUDA_TRY(cudaFree(d_stats));
 
     pt.mark("table + filter");
     idx->dev.table = (const uint4*)idx->d_table;
