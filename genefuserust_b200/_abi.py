@@ -136,7 +136,8 @@ class gf_map_stats(C.Structure):
 EXPORTS = (
     "gf_last_error", "gf_abi_version", "gf_device_count", "gf_default_params", "gf_index_create",
     "gf_index_destroy", "gf_index_get_info", "gf_index_lookup", "gf_map_pairs", "gf_map_pairs_device",
-    "gf_sort_matches", "gf_get_map_stats", "gf_fast_merge", "gf_map_fastq",
+    "gf_sort_matches", "gf_get_map_stats", "gf_fast_merge", "gf_map_fastq", "gf_multi_create", "gf_multi_destroy",
+    "gf_multi_map_pairs",
 )
 
 _lib = None
@@ -178,6 +179,12 @@ def load_library():
     lib.gf_map_fastq.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, P(gf_match), C.c_uint64,
                                  P(C.c_uint64), P(C.c_uint64)]
     lib.gf_map_fastq.restype = C.c_int
+    lib.gf_multi_create.argtypes = [P(gf_gene_span), C.c_uint32, P(gf_params), P(C.c_int), C.c_int, P(C.c_void_p)]
+    lib.gf_multi_create.restype = C.c_int
+    lib.gf_multi_destroy.argtypes = [C.c_void_p]
+    lib.gf_multi_destroy.restype = None
+    lib.gf_multi_map_pairs.argtypes = [C.c_void_p, P(gf_batch), P(gf_match), C.c_uint64, P(C.c_uint64)]
+    lib.gf_multi_map_pairs.restype = C.c_int
     lib.gf_fast_merge.argtypes = [C.c_void_p, P(gf_batch), P(gf_merge_info)]
     lib.gf_fast_merge.restype = C.c_int
     _lib = lib

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "gf_internal.h"
 
@@ -531,6 +532,99 @@ int gf_fast_merge(gf_index* idx, const gf_batch* in, gf_merge_info* out) {
 }
 
 } /* extern "C" */
+
+/* ---- multi-device handle ------------------------------------------------------------------------------ */
+struct gf_multi {
+    std::vector<gf_index*> idx;
+};
+
+extern "C" int gf_multi_create(const gf_gene_span* genes, uint32_t n_genes, const gf_params* params, const int* devices,
+                               int n_devices, gf_multi** out) {
+    if (!out) return fail(GF_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_devices <= 0 || !devices) return fail(GF_E_INVALID, "no devices given");
+    gf_multi* m = new gf_multi();
+    m->idx.assign((size_t)n_devices, nullptr);
+    std::vector<int> rcs((size_t)n_devices, GF_OK);
+    std::vector<std::string> errs((size_t)n_devices);
+    std::vector<std::thread> th;
+    for (int k = 0; k < n_devices; k++)
+        th.emplace_back([&, k] {
+            rcs[(size_t)k] = gf_index_create(genes, n_genes, params, devices[k], &m->idx[(size_t)k]);
+            if (rcs[(size_t)k] != GF_OK) errs[(size_t)k] = gf_last_error();
+        });
+    for (auto& t : th) t.join();
+    for (int k = 0; k < n_devices; k++)
+        if (rcs[(size_t)k] != GF_OK) {
+            int rc = rcs[(size_t)k];
+            std::string e = errs[(size_t)k];
+            for (gf_index* h : m->idx) if (h) gf_index_destroy(h);
+            delete m;
+            return fail(rc, "device " + std::to_string(devices[k]) + ": " + e);
+        }
+    *out = m;
+    return GF_OK;
+}
+
+extern "C" void gf_multi_destroy(gf_multi* m) {
+    if (!m) return;
+    for (gf_index* h : m->idx) if (h) gf_index_destroy(h);
+    delete m;
+}
+
+extern "C" int gf_multi_map_pairs(gf_multi* m, const gf_batch* in, gf_match* out, uint64_t out_cap, uint64_t* n_out) {
+    if (!m || !n_out) return fail(GF_E_INVALID, "NULL argument");
+    *n_out = 0;
+    int rc0 = validate_batch(in);
+    if (rc0 != GF_OK) return rc0;
+    const size_t nd = m->idx.size();
+    const uint64_t n = in->n;
+    const bool pe = in->seq2 != nullptr;
+    std::vector<std::vector<gf_match>> parts(nd);
+    std::vector<int> rcs(nd, GF_OK);
+    std::vector<std::string> errs(nd);
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < nd; k++)
+        th.emplace_back([&, k] {
+            /* contiguous shard [lo, hi): sizes differ by at most one pair */
+            const uint64_t base = n / nd, rem = n % nd;
+            const uint64_t lo = k * base + std::min<uint64_t>(k, rem), hi = lo + base + (k < rem ? 1 : 0);
+            if (hi == lo) return;
+            gf_batch sb = *in;
+            sb.n = hi - lo;
+            sb.off1 = in->off1 + lo; /* offsets stay absolute into the shared arenas */
+            sb.bytes1 = in->off1[hi] - in->off1[lo];
+            if (pe) { sb.off2 = in->off2 + lo; sb.bytes2 = in->off2[hi] - in->off2[lo]; }
+            uint64_t cap = std::max<uint64_t>(4096, sb.n / 64), got = 0; /* matches are << 1 % of pairs; grown on GF_E_CAPACITY */
+            for (;;) {
+                parts[k].resize(cap);
+                int rc = gf_map_pairs(m->idx[k], &sb, parts[k].data(), cap, &got);
+                if (rc == GF_E_CAPACITY) { cap = got; continue; }
+                rcs[k] = rc;
+                if (rc != GF_OK) errs[k] = gf_last_error();
+                break;
+            }
+            parts[k].resize(rcs[k] == GF_OK || rcs[k] == GF_E_REF_PANIC ? got : 0);
+            for (auto& r : parts[k]) r.pair_idx += lo;
+        });
+    for (auto& t : th) t.join();
+    int rc = GF_OK;
+    uint64_t total = 0;
+    for (size_t k = 0; k < nd; k++) {
+        if (rcs[k] != GF_OK && rcs[k] != GF_E_REF_PANIC) return fail(rcs[k], "shard " + std::to_string(k) + ": " + errs[k]);
+        if (rcs[k] == GF_E_REF_PANIC) rc = GF_E_REF_PANIC;
+        total += parts[k].size();
+    }
+    *n_out = total;
+    if (total > out_cap) return fail(GF_E_CAPACITY, "out_cap too small; *n_out holds the required count");
+    uint64_t w = 0;
+    for (size_t k = 0; k < nd; k++) {
+        if (!parts[k].empty()) memcpy(out + w, parts[k].data(), sizeof(gf_match) * parts[k].size());
+        w += parts[k].size();
+    }
+    if (rc == GF_E_REF_PANIC) gf_set_error("a candidate needs an edit distance over more than 640 columns (reference panics)");
+    return rc;
+}
 
 /* debug hook (not part of the ABI header): survivor list of the last mapping call on this handle */
 extern "C" int gf_debug_get_survivors(gf_index* idx, uint32_t* out_pairs_meta, uint64_t cap, uint64_t* n) {

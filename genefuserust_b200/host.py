@@ -248,7 +248,7 @@ class FusionMapper:
 
     # -- the batch calls that replace the per-pack loops
     def _map(self, batch, cap=None):
-        cap = cap or max(1024, (2 if batch.paired else 1) * batch.n // 8)
+        cap = cap or max(4096, batch.n // 64)   # matches are << 1 % of pairs; grown on GF_E_CAPACITY
         st = batch.as_struct()
         while True:
             out = (gf_match * cap)()
@@ -338,3 +338,42 @@ class PairEndScanner:
         for m in matches:
             self.mapper.add_match(m)
         return matches
+
+
+class MultiGpuMapper:
+    """One process, several GPUs (gf_multi_*): index replicated, every batch sharded by pairs, records gathered on the
+    host in (pair_idx, source) order — the same answer as FusionMapper on one device."""
+
+    def __init__(self, gene_spans, devices, params=None):
+        self.lib = load_library()
+        self.params = params or gf_params.default()
+        arr = (gf_gene_span * max(1, len(gene_spans)))()
+        keep = []
+        for i, (seq, rev) in enumerate(gene_spans):
+            buf = C.create_string_buffer(seq, len(seq)) if len(seq) else None
+            keep.append(buf)
+            arr[i].seq = C.cast(buf, C.c_void_p).value if buf is not None else None
+            arr[i].len = len(seq)
+            arr[i].reversed = 1 if rev else 0
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        _check(self.lib, self.lib.gf_multi_create(arr, len(gene_spans), C.byref(self.params), devs, len(devices), C.byref(h)))
+        self.h = h
+
+    def scan(self, batch):
+        cap = max(4096, batch.n // 64)
+        st = batch.as_struct()
+        while True:
+            out = (gf_match * cap)()
+            n = C.c_uint64(0)
+            rc = self.lib.gf_multi_map_pairs(self.h, C.byref(st), out, cap, C.byref(n))
+            if rc == GF_E_CAPACITY:
+                cap = int(n.value)
+                continue
+            _check(self.lib, rc, allow=(GF_E_REF_PANIC,))
+            return [out[i] for i in range(n.value)]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gf_multi_destroy(self.h)
+            self.h = None

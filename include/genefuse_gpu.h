@@ -223,6 +223,18 @@ int gf_get_map_stats(const gf_index* idx, gf_map_stats* out);
 /* Parity hook: run only the device fast_merge on a HOST batch. */
 int gf_fast_merge(gf_index* idx, const gf_batch* in, gf_merge_info* out);
 
+/* ---- several GPUs of one box from ONE process (what the Rust binary needs; bench.py uses one process per GPU) ----
+ * The index is replicated on every listed device (built there, ~12 ms each, in parallel); every batch is cut into
+ * n_devices contiguous shards of pairs, each mapped by its own host thread on its own device (no device-to-device
+ * traffic: reads are independent, map_read(&self), src/core/fusion_mapper.rs:93), and the records are gathered on
+ * the host.  The result is identical to a single-device gf_map_pairs on the whole batch, including the order.
+ * A device may be listed more than once (two streams of work on one GPU). */
+typedef struct gf_multi gf_multi;
+int gf_multi_create(const gf_gene_span* genes, uint32_t n_genes, const gf_params* params, const int* devices,
+                    int n_devices, gf_multi** out);
+void gf_multi_destroy(gf_multi* m);
+int gf_multi_map_pairs(gf_multi* m, const gf_batch* in, gf_match* out, uint64_t out_cap, uint64_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

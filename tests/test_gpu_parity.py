@@ -460,3 +460,20 @@ def test_filter_flags(host):
     assert any(f & 1 for f in flags) and any(f & 2 for f in flags) and any(f & 4 for f in flags) and 0 in flags, flags
     m.close()
     o.close()
+
+
+def test_multi_device_handle(host, small_panel):
+    """gf_multi_*: shards of one batch mapped by several handles from one process (device 0 listed three times on a
+    1-GPU box, all visible devices otherwise); the gathered records must equal the single-handle result"""
+    import torch
+    genes = small_panel.genes()
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0, 0]
+    b = synth.generate_pairs(small_panel, 100001, read_len=150, seed=71, p_fusion=0.03)
+    mm = host.MultiGpuMapper(genes, devices)
+    got = [r.astuple() for r in mm.scan(b)]
+    o = orc.OracleIndex(genes)
+    want = o.scan(b, threads=8)
+    assert len(want) > 100 and got == want
+    mm.close()
+    o.close()
