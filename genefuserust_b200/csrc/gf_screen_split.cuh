@@ -41,6 +41,11 @@ __device__ __forceinline__ uint32_t* slot_words(const SeqStore& st, uint32_t s) 
     return st.words + (size_t)(s >> 5) * SL<W>::NW3 * 32 + (s & 31u);
 }
 
+__device__ __forceinline__ uint32_t fs_col(const uint32_t* col, int arr_base, uint32_t bitpos) {
+    uint32_t wi = bitpos >> 5;
+    return __funnelshift_r(col[(size_t)(arr_base + (int)wi) * 32], col[(size_t)(arr_base + (int)wi + 1) * 32], bitpos & 31u);
+}
+
 struct PrepParams {
     GfDevBatch b;
     SeqStore st;
@@ -207,10 +212,6 @@ struct SeedParams {
     SeqStore st;
     int need_total, need_minor;
 };
-__device__ __forceinline__ uint32_t fs_col(const uint32_t* col, int arr_base, uint32_t bitpos) {
-    uint32_t wi = bitpos >> 5;
-    return __funnelshift_r(col[(size_t)(arr_base + (int)wi) * 32], col[(size_t)(arr_base + (int)wi + 1) * 32], bitpos & 31u);
-}
 template <int W>
 __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
     constexpr int NW = SL<W>::NW;
@@ -226,28 +227,34 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
             const uint4 m = P.st.meta[s];
             const int len = (int)m.z;
             const int nprobe = len >= 16 ? ((len - 16) >> 1) + 1 : 0;
-            const uint32_t* col = slot_words<W>(P.st, s);
             if (nprobe == 0 && P.need_total > 0) have = false; /* cannot reach the gate: dropped here */
             if (have && nprobe > 0) {
-                /* all 8 candidate k-mers go to the filter at once (independent L2 loads); the HBM table is asked only
-                 * for candidates the filter calls present-and-unique, in read order */
-                uint32_t key[8], off[8];
-                unsigned long long fw[8];
-                uint32_t okm = 0;
+                /* all 8 candidate k-mers go to the filter at once (independent L2 loads); the
+                 * HBM table is asked only for candidates the filter calls present-and-unique, in read order */
+                const uint32_t* col = slot_words<W>(P.st, s);
+                uint32_t key[8], okm = 0;
 #pragma unroll
                 for (int t = 0; t < 8; t++) {
-                    off[t] = (uint32_t)(((long long)t * nprobe) >> 3) * 2u;
-                    bool ok = (fs_col(col, 2 * NW, off[t]) & 0xFFFFu) == 0xFFFFu;
-                    key[t] = ((fs_col(col, NW, off[t]) & 0xFFFFu) << 16) | (fs_col(col, 0, off[t]) & 0xFFFFu);
+                    uint32_t i = (uint32_t)(((long long)t * nprobe) >> 3) * 2u;
+                    if ((fs_col(col, 2 * NW, i) & 0xFFFFu) == 0xFFFFu) okm |= 1u << t;
+                    key[t] = ((fs_col(col, NW, i) & 0xFFFFu) << 16) | (fs_col(col, 0, i) & 0xFFFFu);
+                }
+                unsigned long long fw[8];
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
                     fw[t] = 0;
-                    if (ok) { fw[t] = ldg_filter(P.ix.filter + gf_filter_word(key[t], P.ix.filter_words), pol); okm |= 1u << t; }
+                    if ((okm >> t) & 1u) fw[t] = ldg_filter(P.ix.filter + gf_filter_word(key[t], P.ix.filter_words), pol);
                 }
 #pragma unroll
                 for (int t = 0; t < 8; t++) {
                     if (seeded || !((okm >> t) & 1u)) continue;
                     if (gf_filter_sites(fw[t], key[t], 2u) != 1u) continue;
                     uint32_t val = gf_table_find(P.ix, key[t]);
-                    if (val != GF_EMPTY_VAL && (val >> 30) == GF_KIND_UNIQUE) { seed_val = val; seed_i = off[t]; seeded = true; }
+                    if (val != GF_EMPTY_VAL && (val >> 30) == GF_KIND_UNIQUE) {
+                        seed_val = val;
+                        seed_i = (uint32_t)(((long long)t * nprobe) >> 3) * 2u;
+                        seeded = true;
+                    }
                 }
             }
             if (have) P.st.seed[s] = make_uint2(seed_val, seed_i);
@@ -328,18 +335,25 @@ __global__ void __launch_bounds__(256) k_scan(ClassParams P) {
     }
 }
 
-/* seeded sequences: compare with the gene along the seed diagonal; exact votes where the 16-mer equals an indexed window */
+/* seeded sequences: compare with the gene along the seed diagonal; exact votes where the 16-mer equals an indexed window.
+ * The few offsets the diagonal does not explain (reads with a sequencing error) are queued per warp and probed by all
+ * 32 lanes together, so the probe code does not run at 1-2 active threads. */
 template <int W>
 __global__ void __launch_bounds__(256) k_diag(ClassParams P) {
     constexpr int NW = SL<W>::NW;
+    __shared__ uint32_t q_key[8][512];
+    __shared__ uint8_t q_own[8][512];
+    __shared__ int t_sh[8][32];
+    const uint32_t lane = gf_lane(), wib = threadIdx.x >> 5;
     const uint32_t n = P.st.counters[1];
     const unsigned long long pol = make_policy_keep();
     const GfDevIndex& ix = P.ix;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-        const uint32_t s = P.st.list_seeded[t];
-        const uint4 m = P.st.meta[s];
-        const uint2 sd = P.st.seed[s];
-        const int len = (int)m.z, nch = (len + 31) >> 5;
+    for (uint32_t t0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); t0 < n; t0 += gridDim.x * blockDim.x) {
+        const bool have = t0 + lane < n;
+        const uint32_t s = have ? P.st.list_seeded[t0 + lane] : 0u;
+        const uint4 m = have ? P.st.meta[s] : make_uint4(0, 0, 0, 0);
+        const uint2 sd = have ? P.st.seed[s] : make_uint2(0, 0);
+        const int len = (int)m.z, nch = have ? (len + 31) >> 5 : 0;
         const uint32_t* col = slot_words<W>(P.st, s);
         const bool rc = (sd.x & GF_SITE_STRAND) != 0;
         const uint32_t goff = sd.x & GF_SITE_GOFF_MASK;
@@ -347,6 +361,7 @@ __global__ void __launch_bounds__(256) k_diag(ClassParams P) {
         const uint32_t parity = (rc && (len & 1)) ? 0xAAAAAAAAu : 0x55555555u;
         const uint32_t wbase = D >> 5, sh = D & 31u;
         const uint32_t* gc = rc ? ix.g_cr : ix.g_cf;
+        t_sh[wib][lane] = 0;
         /* read chunk k in the orientation of the comparison */
         auto read_chunk = [&](int k, uint32_t* lo, uint32_t* hi, uint32_t* v) {
             if (k >= nch) { *lo = *hi = *v = 0; return; }
@@ -360,13 +375,13 @@ __global__ void __launch_bounds__(256) k_diag(ClassParams P) {
             *lo = ~__brev(a) & vv;
             *hi = __brev(b);
         };
-        uint32_t glo0 = ldg_plane(ix.g_lo + wbase, pol), ghi0 = ldg_plane(ix.g_hi + wbase, pol), gv0 = ldg_plane(ix.g_v + wbase, pol);
-        uint32_t gca0 = ldg_plane(gc + wbase, pol), gcb0 = ldg_plane(gc + ix.g_cstride + wbase, pol),
-                 gcc0 = ldg_plane(gc + 2 * ix.g_cstride + wbase, pol);
-        uint32_t lo_cur, hi_cur, v_cur;
-        read_chunk(0, &lo_cur, &hi_cur, &v_cur);
-        uint32_t e_cur, cnt_a, cnt_b, cnt_c;
-        {
+        uint32_t glo0 = 0, ghi0 = 0, gv0 = 0, gca0 = 0, gcb0 = 0, gcc0 = 0;
+        uint32_t lo_cur = 0, hi_cur = 0, v_cur = 0, e_cur = 0, cnt_a = 0, cnt_b = 0, cnt_c = 0;
+        if (have) {
+            glo0 = ldg_plane(ix.g_lo + wbase, pol); ghi0 = ldg_plane(ix.g_hi + wbase, pol); gv0 = ldg_plane(ix.g_v + wbase, pol);
+            gca0 = ldg_plane(gc + wbase, pol); gcb0 = ldg_plane(gc + ix.g_cstride + wbase, pol);
+            gcc0 = ldg_plane(gc + 2 * ix.g_cstride + wbase, pol);
+            read_chunk(0, &lo_cur, &hi_cur, &v_cur);
             uint32_t glo1 = ldg_plane(ix.g_lo + wbase + 1, pol), ghi1 = ldg_plane(ix.g_hi + wbase + 1, pol),
                      gv1 = ldg_plane(ix.g_v + wbase + 1, pol);
             uint32_t gca1 = ldg_plane(gc + wbase + 1, pol), gcb1 = ldg_plane(gc + ix.g_cstride + wbase + 1, pol),
@@ -377,31 +392,62 @@ __global__ void __launch_bounds__(256) k_diag(ClassParams P) {
             glo0 = glo1; ghi0 = ghi1; gv0 = gv1; gca0 = gca1; gcb0 = gcb1; gcc0 = gcc1;
         }
         int T = 0, c_d = 0;
+        const int max_nch = (int)__reduce_max_sync(FULL, (unsigned)nch);
 #pragma unroll 1
-        for (int k = 0; k < nch; k++) {
-            uint32_t nlo, nhi, nv;
-            read_chunk(k + 1, &nlo, &nhi, &nv);
-            uint32_t e_nxt = 0, na = 0, nb = 0, nc = 0;
-            if (k + 1 < nch) {
-                uint32_t glo1 = ldg_plane(ix.g_lo + wbase + k + 2, pol), ghi1 = ldg_plane(ix.g_hi + wbase + k + 2, pol),
-                         gv1 = ldg_plane(ix.g_v + wbase + k + 2, pol);
-                uint32_t gca1 = ldg_plane(gc + wbase + k + 2, pol), gcb1 = ldg_plane(gc + ix.g_cstride + wbase + k + 2, pol),
-                         gcc1 = ldg_plane(gc + 2 * ix.g_cstride + wbase + k + 2, pol);
-                e_nxt = ~((nlo ^ __funnelshift_r(glo0, glo1, sh)) | (nhi ^ __funnelshift_r(ghi0, ghi1, sh))) & nv &
-                        __funnelshift_r(gv0, gv1, sh);
-                na = __funnelshift_r(gca0, gca1, sh); nb = __funnelshift_r(gcb0, gcb1, sh); nc = __funnelshift_r(gcc0, gcc1, sh);
-                glo0 = glo1; ghi0 = ghi1; gv0 = gv1; gca0 = gca1; gcb0 = gcb1; gcc0 = gcc1;
+        for (int k = 0; k < max_nch; k++) {
+            uint32_t om = 0, nlo = 0, nhi = 0, nv = 0;
+            if (k < nch) {
+                read_chunk(k + 1, &nlo, &nhi, &nv);
+                uint32_t e_nxt = 0, na = 0, nb = 0, nc = 0;
+                if (k + 1 < nch) {
+                    uint32_t glo1 = ldg_plane(ix.g_lo + wbase + k + 2, pol), ghi1 = ldg_plane(ix.g_hi + wbase + k + 2, pol),
+                             gv1 = ldg_plane(ix.g_v + wbase + k + 2, pol);
+                    uint32_t gca1 = ldg_plane(gc + wbase + k + 2, pol), gcb1 = ldg_plane(gc + ix.g_cstride + wbase + k + 2, pol),
+                             gcc1 = ldg_plane(gc + 2 * ix.g_cstride + wbase + k + 2, pol);
+                    e_nxt = ~((nlo ^ __funnelshift_r(glo0, glo1, sh)) | (nhi ^ __funnelshift_r(ghi0, ghi1, sh))) & nv &
+                            __funnelshift_r(gv0, gv1, sh);
+                    na = __funnelshift_r(gca0, gca1, sh); nb = __funnelshift_r(gcb0, gcb1, sh); nc = __funnelshift_r(gcc0, gcc1, sh);
+                    glo0 = glo1; ghi0 = ghi1; gv0 = gv1; gca0 = gca1; gcb0 = gcb1; gcc0 = gcc1;
+                }
+                uint32_t mm = run16(e_cur, e_nxt) & parity;
+                uint32_t c0 = cnt_a & mm, c1 = cnt_b & mm, c2 = cnt_c & mm;
+                uint32_t hit = c0 | c1 | c2;
+                c_d += __popc(hit);
+                T += __popc(c0) + 2 * __popc(c1) + 4 * __popc(c2);
+                om = run16(v_cur, nv) & parity & ~hit;
+                e_cur = e_nxt; cnt_a = na; cnt_b = nb; cnt_c = nc;
             }
-            uint32_t mm = run16(e_cur, e_nxt) & parity;
-            uint32_t c0 = cnt_a & mm, c1 = cnt_b & mm, c2 = cnt_c & mm;
-            uint32_t hit = c0 | c1 | c2;
-            c_d += __popc(hit);
-            T += __popc(c0) + 2 * __popc(c1) + 4 * __popc(c2);
-            T += probe_offsets(ix, run16(v_cur, nv) & parity & ~hit, lo_cur, nlo, hi_cur, nhi, rc, pol);
-            e_cur = e_nxt; cnt_a = na; cnt_b = nb; cnt_c = nc;
-            v_cur = nv; lo_cur = nlo; hi_cur = nhi;
+            /* queue this chunk's unexplained offsets of all lanes, then probe them with the whole warp */
+            int cnt = __popc(om), incl = cnt;
+            for (int o = 1; o < 32; o <<= 1) {
+                int tt = __shfl_up_sync(FULL, incl, o);
+                if ((int)lane >= o) incl += tt;
+            }
+            const int total = __shfl_sync(FULL, incl, 31);
+            if (total) {
+                int pos = incl - cnt;
+                while (om) {
+                    uint32_t b = (uint32_t)(__ffs(om) - 1);
+                    om &= om - 1u;
+                    uint32_t kk = ((__funnelshift_r(hi_cur, nhi, b) & 0xFFFFu) << 16) | (__funnelshift_r(lo_cur, nlo, b) & 0xFFFFu);
+                    q_key[wib][pos] = rc ? gf_key_revcomp(kk) : kk;
+                    q_own[wib][pos] = (uint8_t)lane;
+                    pos++;
+                }
+                __syncwarp();
+                for (int j = (int)lane; j < total; j += 32) {
+                    uint32_t key = q_key[wib][j];
+                    int nsites = (int)gf_filter_sites(ldg_filter(ix.filter + gf_filter_word(key, ix.filter_words), pol), key, ix.max_sites);
+                    if (nsites) atomicAdd(&t_sh[wib][q_own[wib][j]], nsites);
+                }
+                __syncwarp();
+            }
+            if (k < nch) { v_cur = nv; lo_cur = nlo; hi_cur = nhi; }
         }
-        if (P.need_total <= 0 || P.need_minor <= 0 || (T >= P.need_total && (T - c_d) >= P.need_minor)) push_survivor(P, m);
+        __syncwarp();
+        T += t_sh[wib][lane];
+        if (have && (P.need_total <= 0 || P.need_minor <= 0 || (T >= P.need_total && (T - c_d) >= P.need_minor))) push_survivor(P, m);
+        __syncwarp();
     }
 }
 
