@@ -82,7 +82,8 @@ __device__ __forceinline__ void classify4(uint32_t x, bool ci, uint32_t* lo, uin
     const uint32_t u = t | (t >> 4);
     const uint32_t sel = (u & 0xFFu) | ((u >> 8) & 0xFF00u);
     const uint32_t expect = __byte_perm(0x47544341u, 0u, sel); /* 'A','C','T','G' */
-    const uint32_t vv = gather4(zero_bytes(xu ^ expect) >> 7);
+    /* common case: all four bytes are ACGT -> one compare instead of the per-byte zero test */
+    const uint32_t vv = xu == expect ? 0xFu : gather4(zero_bytes(xu ^ expect) >> 7);
     *v = vv;
     *lo = gather4((xu >> 2) & 0x01010101u) & vv;
     *hi = gather4((xu >> 1) & 0x01010101u) & vv;

@@ -105,13 +105,16 @@ __device__ __forceinline__ void convert_r1(const Col& c, const uint8_t* seq, int
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int u0 = 16 * b + 4 * j; /* u of the first base of this group */
-            uint32_t l, h, v;
+            uint32_t l, h, v, n = 0;
             classify4(x[j], false, &l, &h, &v);
-            uint32_t n = gather4(zero_bytes(x[j] ^ 0x4E4E4E4Eu) >> 7);
-            int rem = nu - u0;
-            uint32_t msk = u0 < (int)q4 ? 0u : (rem >= 4 ? 0xFu : (rem > 0 ? (1u << rem) - 1u : 0u));
+            if (v != 0xFu) n = gather4(zero_bytes(x[j] ^ 0x4E4E4E4Eu) >> 7); /* an 'N' can only sit in an invalid slot */
+            if (b == 0 || b == nblocks - 1) { /* only the first / last block holds positions outside the read */
+                int rem = nu - u0;
+                uint32_t msk = u0 < (int)q4 ? 0u : (rem >= 4 ? 0xFu : (rem > 0 ? (1u << rem) - 1u : 0u));
+                l &= msk; h &= msk; v &= msk; n &= msk;
+            }
             uint32_t sh = (uint32_t)u0 & 31u;
-            alo |= (l & msk) << sh; ahi |= (h & msk) << sh; av |= (v & msk) << sh; an |= (n & msk) << sh;
+            alo |= l << sh; ahi |= h << sh; av |= v << sh; an |= n << sh;
         }
         if ((b & 1) || b == nblocks - 1) { /* U word m complete */
             if (m > 0 && m - 1 <= W) {
@@ -159,10 +162,13 @@ __device__ __forceinline__ void convert_r2_rc(const Col& c, const uint8_t* seq, 
             uint32_t vcs = v & ~gather4((x[j] >> 5) & 0x01010101u);
             /* byte t of x[j] has u = u0 + 3 - t: reverse the nibbles; complement = code ^ 1 */
             uint32_t rv = rev4(v), rl = ~rev4(l) & rv, rh = rev4(h), rcs = rev4(vcs);
-            int rem = nu - u0;
-            uint32_t msk = u0 < (int)q4 ? 0u : (rem >= 4 ? 0xFu : (rem > 0 ? (1u << rem) - 1u : 0u));
+            if (b == 0 || b == nblocks - 1) {
+                int rem = nu - u0;
+                uint32_t msk = u0 < (int)q4 ? 0u : (rem >= 4 ? 0xFu : (rem > 0 ? (1u << rem) - 1u : 0u));
+                rl &= msk; rh &= msk; rv &= msk; rcs &= msk;
+            }
             uint32_t sh = (uint32_t)u0 & 31u;
-            alo |= (rl & msk) << sh; ahi |= (rh & msk) << sh; av |= (rv & msk) << sh; ac |= (rcs & msk) << sh;
+            alo |= rl << sh; ahi |= rh << sh; av |= rv << sh; ac |= rcs << sh;
         }
         if ((b & 1) || b == nblocks - 1) {
             if (m > 0 && m - 1 <= W) {
