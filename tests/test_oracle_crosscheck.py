@@ -1,0 +1,90 @@
+"""The C++ oracle against a second, independently written Python restatement of the same reference code
+(tests/ref_port.py) on randomised fusion reads — including repeats, N, lower case, reversed genes and noisy reads."""
+import random
+
+import _oracle as orc
+import ref_port
+from genefuserust_b200._abi import gf_params
+
+COMP = bytes.maketrans(b"ACGTacgt", b"TGCAtgca")
+
+
+def _genes(rng, n=5):
+    rnd = lambda k: bytes(rng.choice(b"ACGT") for _ in range(k))
+    genes = []
+    shared = rnd(120)                                    # NORMAL dupes across genes
+    many = rnd(60)                                       # HIGH dupes (7 copies)
+    for g in range(n):
+        s = bytearray(rnd(rng.randint(400, 900)))
+        if g < 3:
+            s[100:220] = shared
+        for k in range(2 if g < 4 else 0):
+            p = 250 + 70 * k
+            s[p:p + 60] = many
+        if g == 1:
+            s[300:330] = b"N" * 30
+        genes.append((bytes(s), bool(g % 2)))
+    return genes
+
+
+def _reads(rng, genes, n):
+    out = []
+    for _ in range(n):
+        (a, _), (b, _) = rng.choice(genes), rng.choice(genes)
+        x, y = rng.randint(30, 110), rng.randint(30, 110)
+        pa, pb = rng.randrange(0, len(a) - x), rng.randrange(0, len(b) - y)
+        left, right = a[pa:pa + x], b[pb:pb + y]
+        if rng.random() < 0.5:
+            left = left[::-1].translate(COMP)
+        if rng.random() < 0.5:
+            right = right[::-1].translate(COMP)
+        frag = bytearray(left + right)
+        for _ in range(rng.choice((0, 0, 0, 1, 2, 6))):
+            frag[rng.randrange(len(frag))] = rng.choice(b"ACGTNacgt")
+        if rng.random() < 0.15:
+            p = rng.randrange(len(frag))
+            frag[p:p] = bytes(rng.choice(b"ACGT") for _ in range(rng.randint(1, 3)))   # insertion
+        if rng.random() < 0.5:
+            frag = bytearray(bytes(frag[::-1]).translate(COMP))
+        out.append(bytes(frag))
+    return out
+
+
+def test_cpp_oracle_equals_python_port():
+    rng = random.Random(20240201)
+    n_match = n_mapable_only = 0
+    for rep in range(6):
+        genes = _genes(rng)
+        ref = ref_port.RefIndexer(genes)
+        idx = orc.OracleIndex(genes)
+        c = idx.counts()
+        kinds = [v[0] for v in ref.kmer_pos.values()]
+        assert c["n_keys"] == len(ref.kmer_pos)
+        assert c["n_high"] == sum(1 for k in kinds if k == -2) and c["n_normal"] == sum(1 for k in kinds if k == -1)
+        for seq in _reads(rng, genes, 250):
+            want_segs = [(s, e, gp[0], gp[1]) for (s, e, gp) in ref.map_read(seq)]
+            assert idx.map_read(seq) == want_segs, seq
+            want, want_mapable = ref.fusion_map_read(seq)
+            m, mapable = idx.fusion_map_read(seq)
+            assert mapable == want_mapable
+            got = None if m is None else (m.read_break, m.l_contig, m.l_pos, m.r_contig, m.r_pos, m.gap, m.l_dist,
+                                          m.r_dist, m.seq_len)
+            assert got == want, (seq, got, want)
+            n_match += want is not None
+            n_mapable_only += want is None and want_mapable
+        idx.close()
+    assert n_match > 100 and n_mapable_only > 30, (n_match, n_mapable_only)
+
+
+def test_thresholds_in_both_restatements():
+    rng = random.Random(5)
+    genes = _genes(rng)
+    for thr in (1, 2, 5, 7):
+        p = gf_params.default()
+        p.skip_key_dup_threshold = thr
+        ref = ref_port.RefIndexer(genes, dup_threshold=thr)
+        idx = orc.OracleIndex(genes, params=p)
+        c = idx.counts()
+        kinds = [v[0] for v in ref.kmer_pos.values()]
+        assert (c["n_keys"], c["n_high"], c["n_normal"]) == (len(kinds), kinds.count(-2), kinds.count(-1)), thr
+        idx.close()
