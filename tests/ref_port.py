@@ -224,3 +224,60 @@ def levenshtein(a: bytes, b: bytes) -> int:
             cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
         prev = cur
     return prev[-1]
+
+
+def fast_merge(s1: bytes, q1: bytes, s2: bytes, q2: bytes):
+    """SequenceReadPair::fast_merge (read.rs:313-440) -> (merged_seq, olen, diff) or None"""
+    str2, qual2 = reverse_complement(s2), q2[::-1]
+    len1, len2 = len(s1), len(s2)
+    olen, overlapped, diff = 30, False, 0
+    while olen <= min(len1, len2):
+        diff = low = 0
+        ok = True
+        offset = len1 - olen
+        for i in range(olen):
+            if s1[offset + i] != str2[i]:
+                diff += 1
+                a, b = q1[offset + i], qual2[i]
+                if (a >= ord("?") and b <= ord("0")) or (a <= ord("0") and b >= ord("?")):
+                    low += 1
+                if diff > low or low >= 3:
+                    ok = False
+                    break
+        if ok:
+            overlapped = True
+            break
+        olen += 1
+    if not overlapped:
+        return None
+    offset = len1 - olen
+    merged = bytearray(s1[:offset] + str2)
+    for i in range(olen):
+        if s1[offset + i] != str2[i]:
+            if q1[offset + i] >= ord("?") and qual2[i] <= ord("0"):
+                merged[offset + i] = s1[offset + i]
+            else:
+                merged[offset + i] = str2[i]
+    return bytes(merged), olen, diff
+
+
+def scan_pair(ix: "RefIndexer", s1, q1, s2, q2):
+    """PairEndScanner::scan_pair_end for one pair (pescanner.rs:427-518) -> list of
+    (source, used_rc, reversed, read_break, lc, lp, rc, rp, gap, ld, rd, seq_len)"""
+    out = []
+
+    def try_read(seq, source, set_reversed):
+        m, mapable = ix.fusion_map_read(seq)
+        if m is not None:
+            out.append((source, 0, 0) + m)
+        elif mapable:
+            m2, _ = ix.fusion_map_read(reverse_complement(seq))
+            if m2 is not None:
+                out.append((source, 1, 1 if set_reversed else 0) + m2)
+    merged = fast_merge(s1, q1, s2, q2)
+    if merged is not None:
+        try_read(merged[0], 0, False)       # merged rc matches are NOT flagged reversed (:455-469)
+        return out
+    try_read(s1, 1, True)
+    try_read(s2, 2, True)
+    return out

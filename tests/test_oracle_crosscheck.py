@@ -88,3 +88,30 @@ def test_thresholds_in_both_restatements():
         kinds = [v[0] for v in ref.kmer_pos.values()]
         assert (c["n_keys"], c["n_high"], c["n_normal"]) == (len(kinds), kinds.count(-2), kinds.count(-1)), thr
         idx.close()
+
+
+def test_scan_pair_end_policy_in_both_restatements():
+    """merge -> map -> rc retry -> reversed flag (pescanner.rs:427-518): the C++ oracle's batch scan against the Python port"""
+    from genefuserust_b200 import ReadBatch
+    rng = random.Random(77)
+    genes = _genes(rng, n=6)
+    ref = ref_port.RefIndexer(genes)
+    idx = orc.OracleIndex(genes)
+    r1s, r2s = [], []
+    for frag in _reads(rng, genes, 400):
+        L = rng.choice((75, 100, 150))
+        s1 = frag[:L]
+        s2 = frag[::-1].translate(COMP)[:L]
+        q = lambda n: bytes(rng.choice(b"EEEEEA/?0") for _ in range(n))
+        r1s.append((s1, q(len(s1))))
+        r2s.append((s2, q(len(s2))))
+    b = ReadBatch.from_reads(r1s, r2s)
+    got = idx.scan(b, threads=2)
+    want = []
+    for i, ((s1, q1), (s2, q2)) in enumerate(zip(r1s, r2s)):
+        for rec in ref_port.scan_pair(ref, s1, q1, s2, q2):
+            want.append((i,) + rec)
+    # oracle tuple: pair, source, used_rc, reversed, read_break, lc, lp, rc, rp, gap, ld, rd, seq_len, olen, diff, flags
+    assert [g[:13] for g in got] == want
+    assert len(want) > 60 and any(w[2] for w in want) and any(w[1] == 0 for w in want) and any(w[1] == 2 for w in want)
+    idx.close()
