@@ -55,6 +55,8 @@ struct GfDevIndex {
     uint32_t g_cstride;
     const unsigned long long* filter; /* blocked Bloom filter over all non-HIGH keys, 64-bit blocks */
     uint32_t filter_words;
+    const unsigned long long* filter_multi; /* second-level filter: NORMAL (dupe) keys only */
+    uint32_t filter_multi_words;
     uint32_t n_genes;
     uint32_t max_sites;         /* most sites a NORMAL key holds = max(skip_key_dup_threshold, 2) */
     uint32_t bucket_shift;      /* 32 - bucket_bits */
@@ -154,23 +156,31 @@ __device__ __forceinline__ uint32_t gf_table_find(const GfDevIndex& ix, uint32_t
 __device__ __forceinline__ uint32_t gf_filter_word(uint32_t key, uint32_t n_words) {
     return (uint32_t)(((unsigned long long)(key * GF_HASH_MULT) * n_words) >> 32);
 }
-/* 64-bit block = two 32-bit halves; a key sets 2 "present" bits in each half, NORMAL (dupe) keys one more
- * "multi" bit per half.  All 32-bit arithmetic. */
-__device__ __forceinline__ void gf_filter_masks(uint32_t key, uint32_t* any_lo, uint32_t* any_hi, uint32_t* multi_lo,
-                                                uint32_t* multi_hi) {
+/* main filter: 64-bit block = two 32-bit halves, a key sets 2 bits in each half (all 32-bit arithmetic).
+ * multi filter: a second, tiny filter (16 bits per key, 4 bits per key) holding only the NORMAL (dupe) keys; it is
+ * consulted only for k-mers the main filter calls present, so a false "dupe" (which would count max_sites votes)
+ * needs a false positive in BOTH filters. */
+__device__ __forceinline__ void gf_filter_masks(uint32_t key, uint32_t* any_lo, uint32_t* any_hi) {
     const uint32_t g1 = key * 0xC2B2AE35u, g2 = key * 0x27D4EB2Fu;
     *any_lo = (1u << (g1 >> 27)) | (1u << ((g1 >> 22) & 31u));
     *any_hi = (1u << (g2 >> 27)) | (1u << ((g2 >> 22) & 31u));
-    *multi_lo = 1u << ((g1 >> 17) & 31u);
-    *multi_hi = 1u << ((g2 >> 17) & 31u);
+}
+__device__ __forceinline__ uint32_t gf_multi_word(uint32_t key, uint32_t n_words) {
+    return (uint32_t)(((unsigned long long)(key * 0x85EBCA6Bu) * n_words) >> 32);
+}
+__device__ __forceinline__ unsigned long long gf_multi_mask(uint32_t key) {
+    const uint32_t g = key * 0x165667B1u;
+    return (1ull << (g >> 26)) | (1ull << ((g >> 20) & 63u)) | (1ull << ((g >> 14) & 63u)) | (1ull << ((g >> 8) & 63u));
 }
 /* upper bound of the number of sites the key votes for: 0 absent/HIGH, 1 unique, max_sites dupes */
-__device__ __forceinline__ uint32_t gf_filter_sites(unsigned long long w, uint32_t key, uint32_t max_sites) {
-    uint32_t al, ah, ml, mh;
-    gf_filter_masks(key, &al, &ah, &ml, &mh);
+__device__ __forceinline__ uint32_t gf_filter_sites(const GfDevIndex& ix, unsigned long long w, uint32_t key, uint32_t max_sites) {
+    uint32_t al, ah;
+    gf_filter_masks(key, &al, &ah);
     const uint32_t wl = (uint32_t)w, wh = (uint32_t)(w >> 32);
     if ((wl & al) != al || (wh & ah) != ah) return 0u;
-    return ((wl & ml) && (wh & mh)) ? max_sites : 1u;
+    const unsigned long long mm = gf_multi_mask(key);
+    const unsigned long long mw = __ldg(ix.filter_multi + gf_multi_word(key, ix.filter_multi_words));
+    return (mw & mm) == mm ? max_sites : 1u;
 }
 
 /* site decoding ---------------------------------------------------------------------------- */

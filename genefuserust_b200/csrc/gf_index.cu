@@ -240,7 +240,8 @@ __global__ void k_build_table(const unsigned long long* __restrict__ items, uint
                               const uint32_t* __restrict__ dupe_off, uint32_t* __restrict__ dupes,
                               unsigned long long* __restrict__ table, uint32_t bucket_shift, uint32_t bucket_mask,
                               unsigned int* __restrict__ max_disp, unsigned long long* __restrict__ filter,
-                              uint32_t filter_words) {
+                              uint32_t filter_words, unsigned long long* __restrict__ filter_multi,
+                              uint32_t filter_multi_words) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t key = (uint32_t)(items[i] >> 32);
@@ -258,10 +259,10 @@ __global__ void k_build_table(const unsigned long long* __restrict__ items, uint
         val = (GF_KIND_HIGH << 30);
     }
     if (len <= thr) { /* unique and NORMAL keys vote; HIGH keys never do and stay out of the filter */
-        uint32_t al, ah, ml, mh;
-        gf_filter_masks(key, &al, &ah, &ml, &mh);
-        if (len > 1) { al |= ml; ah |= mh; }
+        uint32_t al, ah;
+        gf_filter_masks(key, &al, &ah);
         atomicOr(filter + gf_filter_word(key, filter_words), ((unsigned long long)ah << 32) | al);
+        if (len > 1) atomicOr(filter_multi + gf_multi_word(key, filter_multi_words), gf_multi_mask(key));
     }
     unsigned long long entry = ((unsigned long long)val << 32) | key;
     uint32_t b = gf_home_bucket(key, bucket_shift);
@@ -555,14 +556,17 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     int filter_bits = 8;
     if (const char* e = getenv("GF_FILTER_BITS")) { int v = atoi(e); if (v >= 4 && v <= 32) filter_bits = v; }
     const uint32_t filter_words = (uint32_t)std::max<uint64_t>(1024, (n_keys * (uint64_t)filter_bits + 63) / 64);
-    GF_CUDA_TRY(cudaMalloc(&idx->d_filter, sizeof(unsigned long long) * filter_words));
-    GF_CUDA_TRY(cudaMemsetAsync(idx->d_filter, 0, sizeof(unsigned long long) * filter_words, st));
+    /* + the multi filter behind it: 16 bits per NORMAL key */
+    const uint32_t filter_multi_words = (uint32_t)std::max<uint64_t>(1024, (h_stats[2] * 16 + 63) / 64);
+    GF_CUDA_TRY(cudaMalloc(&idx->d_filter, sizeof(unsigned long long) * ((size_t)filter_words + filter_multi_words)));
+    GF_CUDA_TRY(cudaMemsetAsync(idx->d_filter, 0, sizeof(unsigned long long) * ((size_t)filter_words + filter_multi_words), st));
+    unsigned long long* d_filter_multi = (unsigned long long*)idx->d_filter + filter_words;
     if (n_items) {
         const unsigned cb = (unsigned)((n_items + 255) / 256);
         k_build_table<<<cb, 256, 0, st>>>(d_items, n_items, thr, d_doff, (uint32_t*)idx->d_dupes,
                                           (unsigned long long*)idx->d_table, 32 - bucket_bits,
                                           (uint32_t)(n_buckets - 1), d_maxdisp, (unsigned long long*)idx->d_filter,
-                                          filter_words);
+                                          filter_words, d_filter_multi, filter_multi_words);
         GF_CUDA_TRY(cudaGetLastError());
     }
     unsigned int h_maxdisp = 0;
@@ -586,6 +590,8 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     idx->dev.deletion_thr = idx->params.deletion_threshold;
     idx->dev.filter = (const unsigned long long*)idx->d_filter;
     idx->dev.filter_words = filter_words;
+    idx->dev.filter_multi = d_filter_multi;
+    idx->dev.filter_multi_words = filter_multi_words;
 
     /* gene bit-planes (lo, hi, valid) + per-window site-count planes (3 bits x 2 strands) */
     const uint32_t n_pw = (uint32_t)((arena_len + 31) / 32);
@@ -624,7 +630,7 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     inf.max_displacement = h_maxdisp;
     inf.gene_bytes = gene_bytes;
     inf.device_bytes = n_buckets * 32 + sizeof(uint32_t) * ((size_t)n_dupes + 8) + arena_len + 9ull * (n_genes + 1) +
-                       sizeof(uint32_t) * plane_stride * 9 + sizeof(unsigned long long) * (size_t)filter_words;
+                       sizeof(uint32_t) * plane_stride * 9 + sizeof(unsigned long long) * ((size_t)filter_words + filter_multi_words);
     inf.build_ms = ms;
     return GF_OK;
 }

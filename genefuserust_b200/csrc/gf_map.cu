@@ -441,7 +441,7 @@ __device__ __forceinline__ bool screen_sequence2(const GfDevIndex& ix, ScreenWar
         bool ok = lane < 8 && (fsr(v, (uint32_t)i) & 0xFFFFu) == 0xFFFFu;
         uint32_t key = ((fsr(hi, (uint32_t)i) & 0xFFFFu) << 16) | (fsr(lo, (uint32_t)i) & 0xFFFFu);
         bool present = false;
-        if (ok) present = gf_filter_sites(ldg_filter(ix.filter + gf_filter_word(key, ix.filter_words), pol), key, 2u) == 1u;
+        if (ok) present = gf_filter_sites(ix, ldg_filter(ix.filter + gf_filter_word(key, ix.filter_words), pol), key, 2u) == 1u;
         uint32_t pm = __ballot_sync(FULL, present);
         while (pm) {
             int src = __ffs(pm) - 1;
@@ -542,7 +542,7 @@ __device__ __forceinline__ bool screen_sequence2(const GfDevIndex& ix, ScreenWar
             }
 #pragma unroll
             for (int u = 0; u < 2; u++)
-                if (ok[u]) t_local += (int)gf_filter_sites(w[u], key[u], ix.max_sites);
+                if (ok[u]) t_local += (int)gf_filter_sites(ix, w[u], key[u], ix.max_sites);
         }
     } else {
         /* offsets not explained by the diagonal: compact them into a list, then spread over the lanes */
@@ -572,7 +572,7 @@ __device__ __forceinline__ bool screen_sequence2(const GfDevIndex& ix, ScreenWar
                 uint32_t off = S.others[j];
                 uint32_t kk = ((fsr(phi, off) & 0xFFFFu) << 16) | (fsr(plo, off) & 0xFFFFu);
                 uint32_t key = rc ? gf_key_revcomp(kk) : kk;
-                t_local += (int)gf_filter_sites(ldg_filter(ix.filter + gf_filter_word(key, ix.filter_words), pol), key,
+                t_local += (int)gf_filter_sites(ix, ldg_filter(ix.filter + gf_filter_word(key, ix.filter_words), pol), key,
                                                 ix.max_sites);
             }
         }

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
 #pragma unroll
                 for (int t = 0; t < 8; t++) {
                     if (seeded || !((okm >> t) & 1u)) continue;
-                    if (gf_filter_sites(fw[t], key[t], 2u) != 1u) continue;
+                    if (gf_filter_sites(P.ix, fw[t], key[t], 2u) != 1u) continue;
                     uint32_t val = gf_table_find(P.ix, key[t]);
                     if (val != GF_EMPTY_VAL && (val >> 30) == GF_KIND_UNIQUE) {
                         seed_val = val;
@@ -307,7 +307,7 @@ __device__ __forceinline__ int probe_offsets(const GfDevIndex& ix, uint32_t om, 
         }
 #pragma unroll
         for (int u = 0; u < 4; u++)
-            if (ok[u]) T += (int)gf_filter_sites(w[u], key[u], ix.max_sites);
+            if (ok[u]) T += (int)gf_filter_sites(ix, w[u], key[u], ix.max_sites);
     }
     return T;
 }
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(256) k_diag(ClassParams P) {
                 __syncwarp();
                 for (int j = (int)lane; j < total; j += 32) {
                     uint32_t key = q_key[wib][j];
-                    int nsites = (int)gf_filter_sites(ldg_filter(ix.filter + gf_filter_word(key, ix.filter_words), pol), key, ix.max_sites);
+                    int nsites = (int)gf_filter_sites(ix, ldg_filter(ix.filter + gf_filter_word(key, ix.filter_words), pol), key, ix.max_sites);
                     if (nsites) atomicAdd(&t_sh[wib][q_own[wib][j]], nsites);
                 }
                 __syncwarp();

@@ -285,7 +285,7 @@ __device__ __forceinline__ void build_r2_forward(const Col& c, int len2) {
 }
 
 __device__ __forceinline__ uint32_t filter_sites(const GfDevIndex& ix, uint32_t key, unsigned long long pol, uint32_t max_sites) {
-    return gf_filter_sites(ldg_filter(ix.filter + gf_filter_word(key, ix.filter_words), pol), key, max_sites);
+    return gf_filter_sites(ix, ldg_filter(ix.filter + gf_filter_word(key, ix.filter_words), pol), key, max_sites);
 }
 
 /* conservative first pass over one sequence whose planes start at (LO, HI, V) in the private column */
@@ -388,7 +388,7 @@ __device__ __forceinline__ bool screen_sequence(const GfDevIndex& ix, const COL&
             }
 #pragma unroll
             for (int u = 0; u < 4; u++)
-                if (ok[u]) T += (int)gf_filter_sites(w[u], key[u], ix.max_sites);
+                if (ok[u]) T += (int)gf_filter_sites(ix, w[u], key[u], ix.max_sites);
         }
         e_cur = e_nxt; cnt_a = na; cnt_b = nb; cnt_c = nc;
         v_cur = nv; lo_cur = nlo; hi_cur = nhi;
