@@ -56,7 +56,7 @@ struct PrepParams {
 
 /* ---------------------------------------------------------------------------------------------- k_prep */
 template <int W, bool PAIRED>
-__global__ void __launch_bounds__(tpp::WARPS * 32) k_prep(PrepParams P) {
+__global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* sm = reinterpret_cast<uint32_t*>(smem_raw);
     const uint32_t lane = gf_lane(), wib = threadIdx.x >> 5;

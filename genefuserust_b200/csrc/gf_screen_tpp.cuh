@@ -54,9 +54,13 @@ __device__ __forceinline__ uint32_t load4_guarded(const uint8_t* p, const uint8_
         if (p + t >= lo && p + t < hi) w |= (uint32_t)__ldg(p + t) << (8 * t);
     return w;
 }
-__device__ __forceinline__ uint32_t rev4(uint32_t n) { return __brev(n) >> 28; }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+/* the block straddles an end of the arena (first / last read of a batch only): byte by byte, kept out of line */
+__device__ __noinline__ uint4 load16_slow(const uint8_t* p, const uint8_t* lo, const uint8_t* hi) {
+    return make_uint4(load4_guarded(p, lo, hi), load4_guarded(p + 4, lo, hi), load4_guarded(p + 8, lo, hi),
+                      load4_guarded(p + 12, lo, hi));
+}
 /* 16-aligned 128-bit load, streaming (evict_first: the reads must not push the filter / gene planes out of L2);
  * bytes outside [lo, hi) read as 0 */
 __device__ __forceinline__ uint4 load16_guarded(const uint8_t* p, const uint8_t* lo, const uint8_t* hi, unsigned long long pol_stream) {
@@ -66,8 +70,18 @@ __device__ __forceinline__ uint4 load16_guarded(const uint8_t* p, const uint8_t*
                      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol_stream));
         return v;
     }
-    return make_uint4(load4_guarded(p, lo, hi), load4_guarded(p + 4, lo, hi), load4_guarded(p + 8, lo, hi),
-                      load4_guarded(p + 12, lo, hi));
+    return load16_slow(p, lo, hi);
+}
+/* same, when the caller has already checked that the whole aligned span of the read lies inside the arena */
+__device__ __forceinline__ uint4 load16_span(const uint8_t* p, bool span_inside, const uint8_t* lo, const uint8_t* hi,
+                                             unsigned long long pol_stream) {
+    if (span_inside) {
+        uint4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol_stream));
+        return v;
+    }
+    return load16_slow(p, lo, hi);
 }
 __device__ __forceinline__ unsigned long long make_policy_normal() {
     unsigned long long pol;
@@ -80,110 +94,141 @@ __device__ __forceinline__ unsigned long long make_policy_stream() {
     return pol;
 }
 
-/* Both converters read 16 aligned bytes per step.  With a = misalignment of the read w.r.t. the 16-byte blocks,
- * a = 4q + r: the r bytes are removed by funnel-shifting adjacent words, the 4q bases by building the planes at
- * bit position u = p + 4q and emitting word w of the aligned plane as funnelshift(U[w], U[w+1], 4q). */
+/* Both converters read two aligned 16-byte blocks per step and turn each into 16 plane bits with a handful of SWAR
+ * operations (no per-base work):
+ *   - the code bits (bit 2 / bit 1 of the ASCII byte = A0 T1 C2 G3) of 8 bytes are gathered by ONE multiply:
+ *     z = low nibbles of word 0 | low nibbles of word 1 << 4, (z & 0x44444444) * 0x00408102 has the eight bit-2 values in
+ *     base order in its top byte (0x00810204 for bit 1); the partial products never collide, so there are no carries;
+ *   - validity: the expected letter is looked up with PRMT from the low 3 bits of each byte (A 001, C 011, T 100, G 111)
+ *     and xor-ed with the byte; a block whose 16 differences are all zero takes the fast path (valid = 0xFFFF);
+ *   - misalignment a (0..15) of the read w.r.t. the blocks is removed in the bit domain: planes are built at bit position
+ *     u = p + a and aligned word w = funnelshift(U[w], U[w+1], a). */
+__device__ __forceinline__ uint32_t expect4(uint32_t x) {
+    const uint32_t t = x & 0x07070707u;
+    const uint32_t u = t | (t >> 4);
+    return __byte_perm(0x43414141u, 0x47414154u, __byte_perm(u, 0u, 0x4420u));
+}
+/* One 16-byte block -> 16 plane bits in the LOW half of each result (the upper halves are garbage):
+ *   lo / hi = code bits, v = valid (ACGT; either case when CI), ex = !CI: the byte is 'N';  CI: valid AND upper case */
+template <bool CI>
+__device__ __forceinline__ void block16(const uint4& x, uint32_t* lo, uint32_t* hi, uint32_t* v, uint32_t* ex) {
+    const uint32_t z0 = (x.x & 0x0F0F0F0Fu) | ((x.y << 4) & 0xF0F0F0F0u);
+    const uint32_t z1 = (x.z & 0x0F0F0F0Fu) | ((x.w << 4) & 0xF0F0F0F0u);
+    uint32_t l = __byte_perm((z0 & 0x44444444u) * 0x00408102u, (z1 & 0x44444444u) * 0x00408102u, 0x7373u);
+    uint32_t h = __byte_perm((z0 & 0x22222222u) * 0x00810204u, (z1 & 0x22222222u) * 0x00810204u, 0x7373u);
+    constexpr uint32_t CM = CI ? 0xDFDFDFDFu : 0xFFFFFFFFu;
+    const uint32_t d0 = (x.x ^ expect4(x.x)) & CM, d1 = (x.y ^ expect4(x.y)) & CM;
+    const uint32_t d2 = (x.z ^ expect4(x.z)) & CM, d3 = (x.w ^ expect4(x.w)) & CM;
+    uint32_t bad = d0 | d1 | d2 | d3;
+    if (CI) bad |= (x.x | x.y | x.z | x.w) & 0x20202020u; /* a lower-case letter: ex differs from v */
+    uint32_t vv = 0xFFFFu, e = CI ? 0xFFFFu : 0u;
+    if (bad) { /* rare: N, lower case, bytes outside the arena */
+        const uint32_t y0 = (zero_bytes(d0) >> 5) | (zero_bytes(d1) >> 1);
+        const uint32_t y1 = (zero_bytes(d2) >> 5) | (zero_bytes(d3) >> 1);
+        vv = __byte_perm(y0 * 0x00408102u, y1 * 0x00408102u, 0x7373u);
+        if (CI) {
+            const uint32_t w0 = ((x.x >> 3) & 0x04040404u) | ((x.y << 1) & 0x40404040u);
+            const uint32_t w1 = ((x.z >> 3) & 0x04040404u) | ((x.w << 1) & 0x40404040u);
+            e = vv & ~__byte_perm(w0 * 0x00408102u, w1 * 0x00408102u, 0x7373u);
+        } else {
+            const uint32_t n0 = (zero_bytes(x.x ^ 0x4E4E4E4Eu) >> 5) | (zero_bytes(x.y ^ 0x4E4E4E4Eu) >> 1);
+            const uint32_t n1 = (zero_bytes(x.z ^ 0x4E4E4E4Eu) >> 5) | (zero_bytes(x.w ^ 0x4E4E4E4Eu) >> 1);
+            e = __byte_perm(n0 * 0x00408102u, n1 * 0x00408102u, 0x7373u);
+        }
+        l &= vv; h &= vv;
+    }
+    *lo = l; *hi = h; *v = vv; *ex = e;
+}
+__device__ __forceinline__ uint4 fill16() { return make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u); }
+__device__ __forceinline__ uint32_t tailmask(int rem) { /* bits of a plane word that lie inside the read */
+    return rem >= 32 ? 0xFFFFFFFFu : (rem > 0 ? (1u << rem) - 1u : 0u);
+}
 
 /* R1 -> forward planes lo, hi, valid (upper-case ACGT), N */
 template <int W>
 __device__ __forceinline__ void convert_r1(const Col& c, const uint8_t* seq, int len, const uint8_t* lo, const uint8_t* hi,
                                            unsigned long long pol_stream) {
-    const uint32_t a = (uint32_t)((uintptr_t)seq & 15u), q4 = a & ~3u /* 4q */, r8 = 8u * (a & 3u);
-    const uint8_t* bp = seq - a;
-    const int nu = len + (int)q4;           /* u positions in use: [4q, nu) */
-    const int nblocks = (nu + 15) >> 4;
-    uint4 cur = load16_guarded(bp, lo, hi, pol_stream);
-    uint32_t alo = 0, ahi = 0, av = 0, an = 0; /* U word being filled */
-    uint32_t plo = 0, phi = 0, pv = 0, pn = 0; /* previous U word */
-    int m = 0;                                 /* index of the U word being filled */
+    const uint32_t a = (uint32_t)((uintptr_t)seq & 15u);
+    const uint8_t* bp = seq - a; /* advanced by 32 per step */
+    const int nu = len + (int)a;                      /* u positions in use: [a, nu) */
+    const int nwords = len > 0 ? (nu + 31) >> 5 : 0;  /* U words, <= W + 1 */
+    uint32_t plo = 0, phi = 0, pv = 0, pn = 0;        /* previous U word */
+    const bool inside = bp >= lo && bp + 32 * nwords <= hi; /* false only for the first / last reads of the arena */
+    uint4 A = fill16(), B = fill16();
+    if (nwords > 0) A = load16_span(bp, inside, lo, hi, pol_stream);
+    if (16 < nu) B = load16_span(bp + 16, inside, lo, hi, pol_stream);
 #pragma unroll 1
-    for (int b = 0; b < nblocks; b++) {
-        uint4 nxt = load16_guarded(bp + 16 * (b + 1), lo, hi, pol_stream);
-        uint32_t x[4] = {__funnelshift_r(cur.x, cur.y, r8), __funnelshift_r(cur.y, cur.z, r8),
-                         __funnelshift_r(cur.z, cur.w, r8), __funnelshift_r(cur.w, nxt.x, r8)};
-        cur = nxt;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int u0 = 16 * b + 4 * j; /* u of the first base of this group */
-            uint32_t l, h, v, n = 0;
-            classify4(x[j], false, &l, &h, &v);
-            if (v != 0xFu) n = gather4(zero_bytes(x[j] ^ 0x4E4E4E4Eu) >> 7); /* an 'N' can only sit in an invalid slot */
-            if (b == 0 || b == nblocks - 1) { /* only the first / last block holds positions outside the read */
-                int rem = nu - u0;
-                uint32_t msk = u0 < (int)q4 ? 0u : (rem >= 4 ? 0xFu : (rem > 0 ? (1u << rem) - 1u : 0u));
-                l &= msk; h &= msk; v &= msk; n &= msk;
-            }
-            uint32_t sh = (uint32_t)u0 & 31u;
-            alo |= l << sh; ahi |= h << sh; av |= v << sh; an |= n << sh;
+    for (int m = 0; m < nwords; m++) {
+        uint4 nA = fill16(), nB = fill16();
+        bp += 32;
+        if (32 * (m + 1) < nu) nA = load16_span(bp, inside, lo, hi, pol_stream);
+        if (32 * (m + 1) + 16 < nu) nB = load16_span(bp + 16, inside, lo, hi, pol_stream);
+        uint32_t l0, h0, v0, n0, l1, h1, v1, n1;
+        block16<false>(A, &l0, &h0, &v0, &n0);
+        block16<false>(B, &l1, &h1, &v1, &n1);
+        const uint32_t ulo = __byte_perm(l0, l1, 0x5410u), uhi = __byte_perm(h0, h1, 0x5410u);
+        const uint32_t uv = __byte_perm(v0, v1, 0x5410u), un = __byte_perm(n0, n1, 0x5410u);
+        if (m > 0) {
+            const uint32_t tm = tailmask(len - 32 * (m - 1));
+            c(Lay<W>::R1LO, m - 1) = __funnelshift_r(plo, ulo, a) & tm; c(Lay<W>::R1HI, m - 1) = __funnelshift_r(phi, uhi, a) & tm;
+            c(Lay<W>::R1V, m - 1) = __funnelshift_r(pv, uv, a) & tm;    c(Lay<W>::R1N, m - 1) = __funnelshift_r(pn, un, a) & tm;
         }
-        if ((b & 1) || b == nblocks - 1) { /* U word m complete */
-            if (m > 0 && m - 1 <= W) {
-                c(Lay<W>::R1LO, m - 1) = __funnelshift_r(plo, alo, q4); c(Lay<W>::R1HI, m - 1) = __funnelshift_r(phi, ahi, q4);
-                c(Lay<W>::R1V, m - 1) = __funnelshift_r(pv, av, q4);    c(Lay<W>::R1N, m - 1) = __funnelshift_r(pn, an, q4);
-            }
-            plo = alo; phi = ahi; pv = av; pn = an;
-            alo = ahi = av = an = 0;
-            m++;
-        }
+        plo = ulo; phi = uhi; pv = uv; pn = un;
+        A = nA; B = nB;
     }
-    if (m > 0 && m - 1 <= W) {
-        c(Lay<W>::R1LO, m - 1) = plo >> q4; c(Lay<W>::R1HI, m - 1) = phi >> q4; c(Lay<W>::R1V, m - 1) = pv >> q4; c(Lay<W>::R1N, m - 1) = pn >> q4;
+    if (nwords > 0) {
+        const uint32_t tm = tailmask(len - 32 * (nwords - 1));
+        c(Lay<W>::R1LO, nwords - 1) = (plo >> a) & tm; c(Lay<W>::R1HI, nwords - 1) = (phi >> a) & tm;
+        c(Lay<W>::R1V, nwords - 1) = (pv >> a) & tm;   c(Lay<W>::R1N, nwords - 1) = (pn >> a) & tm;
     }
-    for (int w = m; w <= W; w++) { c(Lay<W>::R1LO, w) = 0; c(Lay<W>::R1HI, w) = 0; c(Lay<W>::R1V, w) = 0; c(Lay<W>::R1N, w) = 0; }
+    for (int w = nwords; w <= W; w++) { c(Lay<W>::R1LO, w) = 0; c(Lay<W>::R1HI, w) = 0; c(Lay<W>::R1V, w) = 0; c(Lay<W>::R1N, w) = 0; }
 }
 
 /* R2 -> planes of reverse_complement(R2) (case-insensitive, sequence.rs:52-60) + the case-sensitive validity of
- * the same bases (VCS, in rc orientation), produced by walking R2 from its last byte downwards */
+ * the same bases (VCS, in rc orientation), produced by walking R2 from its last byte downwards: the 32 bytes below
+ * `top - 32 m` give rc positions u' = 32 m .. 32 m + 31 in reversed bit order, so one BREV per plane word */
 template <int W>
 __device__ __forceinline__ void convert_r2_rc(const Col& c, const uint8_t* seq, int len, const uint8_t* lo, const uint8_t* hi,
                                               unsigned long long pol_stream) {
     const uint8_t* end = seq + len;
     const uint32_t pad = (uint32_t)((16u - ((uintptr_t)end & 15u)) & 15u); /* garbage bytes above the last base */
-    const uint32_t q4 = pad & ~3u, r = pad & 3u;
-    const uint8_t* top = end + pad;           /* 16-aligned */
-    const int nu = len + (int)q4;
-    const int nblocks = (nu + 15) >> 4;
-    uint4 cur = load16_guarded(top - 16, lo, hi, pol_stream);
-    uint32_t alo = 0, ahi = 0, av = 0, ac = 0, plo = 0, phi = 0, pv = 0, pc = 0;
-    int m = 0;
-    const uint32_t s8 = 8u * (4u - r); /* 32 when r == 0: __funnelshift_rc clamps and returns the upper word */
+    const uint8_t* top = end + pad;           /* 16-aligned, lowered by 32 per step */
+    const int nu = len + (int)pad;
+    const int nwords = len > 0 ? (nu + 31) >> 5 : 0;
+    uint32_t plo = 0, phi = 0, pv = 0, pc = 0;
+    const bool inside = top <= hi && top - 32 * nwords >= lo;
+    uint4 A = fill16(), B = fill16();         /* A: rc positions u' 0..15 of the word, B: 16..31 */
+    if (nwords > 0) A = load16_span(top - 16, inside, lo, hi, pol_stream);
+    if (16 < nu) B = load16_span(top - 32, inside, lo, hi, pol_stream);
 #pragma unroll 1
-    for (int b = 0; b < nblocks; b++) {
-        uint4 nxt = load16_guarded(top - 16 * (b + 2), lo, hi, pol_stream);
-        uint32_t x[4] = {__funnelshift_rc(cur.z, cur.w, s8), __funnelshift_rc(cur.y, cur.z, s8),
-                         __funnelshift_rc(cur.x, cur.y, s8), __funnelshift_rc(nxt.w, cur.x, s8)};
-        cur = nxt;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int u0 = 16 * b + 4 * j;
-            uint32_t l, h, v;
-            classify4(x[j], true, &l, &h, &v);
-            /* case-sensitive validity: a valid letter is upper case iff bit 5 of its byte is clear */
-            uint32_t vcs = v & ~gather4((x[j] >> 5) & 0x01010101u);
-            /* byte t of x[j] has u = u0 + 3 - t: reverse the nibbles; complement = code ^ 1 */
-            uint32_t rv = rev4(v), rl = ~rev4(l) & rv, rh = rev4(h), rcs = rev4(vcs);
-            if (b == 0 || b == nblocks - 1) {
-                int rem = nu - u0;
-                uint32_t msk = u0 < (int)q4 ? 0u : (rem >= 4 ? 0xFu : (rem > 0 ? (1u << rem) - 1u : 0u));
-                rl &= msk; rh &= msk; rv &= msk; rcs &= msk;
-            }
-            uint32_t sh = (uint32_t)u0 & 31u;
-            alo |= rl << sh; ahi |= rh << sh; av |= rv << sh; ac |= rcs << sh;
+    for (int m = 0; m < nwords; m++) {
+        uint4 nA = fill16(), nB = fill16();
+        top -= 32;
+        if (32 * (m + 1) < nu) nA = load16_span(top - 16, inside, lo, hi, pol_stream);
+        if (32 * (m + 1) + 16 < nu) nB = load16_span(top - 32, inside, lo, hi, pol_stream);
+        uint32_t l0, h0, v0, e0, l1, h1, v1, e1;
+        block16<true>(A, &l0, &h0, &v0, &e0);
+        block16<true>(B, &l1, &h1, &v1, &e1);
+        const uint32_t ulo = __brev(__byte_perm(l1, l0, 0x5410u)), uhi = __brev(__byte_perm(h1, h0, 0x5410u));
+        const uint32_t uv = __brev(__byte_perm(v1, v0, 0x5410u)), uc = __brev(__byte_perm(e1, e0, 0x5410u));
+        if (m > 0) {
+            const uint32_t tm = tailmask(len - 32 * (m - 1));
+            const uint32_t sv = __funnelshift_r(pv, uv, pad) & tm;
+            c(Lay<W>::C2LO, m - 1) = ~__funnelshift_r(plo, ulo, pad) & sv; /* complement = code ^ 1 */
+            c(Lay<W>::C2HI, m - 1) = __funnelshift_r(phi, uhi, pad) & sv;
+            c(Lay<W>::C2V, m - 1) = sv;
+            c(Lay<W>::VCS, m - 1) = __funnelshift_r(pc, uc, pad) & tm;
         }
-        if ((b & 1) || b == nblocks - 1) {
-            if (m > 0 && m - 1 <= W) {
-                c(Lay<W>::C2LO, m - 1) = __funnelshift_r(plo, alo, q4); c(Lay<W>::C2HI, m - 1) = __funnelshift_r(phi, ahi, q4);
-                c(Lay<W>::C2V, m - 1) = __funnelshift_r(pv, av, q4);    c(Lay<W>::VCS, m - 1) = __funnelshift_r(pc, ac, q4);
-            }
-            plo = alo; phi = ahi; pv = av; pc = ac;
-            alo = ahi = av = ac = 0;
-            m++;
-        }
+        plo = ulo; phi = uhi; pv = uv; pc = uc;
+        A = nA; B = nB;
     }
-    if (m > 0 && m - 1 <= W) {
-        c(Lay<W>::C2LO, m - 1) = plo >> q4; c(Lay<W>::C2HI, m - 1) = phi >> q4; c(Lay<W>::C2V, m - 1) = pv >> q4; c(Lay<W>::VCS, m - 1) = pc >> q4;
+    if (nwords > 0) {
+        const uint32_t tm = tailmask(len - 32 * (nwords - 1));
+        const uint32_t sv = (pv >> pad) & tm;
+        c(Lay<W>::C2LO, nwords - 1) = ~(plo >> pad) & sv; c(Lay<W>::C2HI, nwords - 1) = (phi >> pad) & sv;
+        c(Lay<W>::C2V, nwords - 1) = sv;                  c(Lay<W>::VCS, nwords - 1) = (pc >> pad) & tm;
     }
-    for (int w = m; w <= W; w++) { c(Lay<W>::C2LO, w) = 0; c(Lay<W>::C2HI, w) = 0; c(Lay<W>::C2V, w) = 0; c(Lay<W>::VCS, w) = 0; }
+    for (int w = nwords; w <= W; w++) { c(Lay<W>::C2LO, w) = 0; c(Lay<W>::C2HI, w) = 0; c(Lay<W>::C2V, w) = 0; c(Lay<W>::VCS, w) = 0; }
 }
 
 /* mismatch mask of overlap chunk k for overlap length olen (read.rs:346) */
@@ -201,33 +246,61 @@ __device__ __forceinline__ bool low_qual_pair(const uint8_t* q1, const uint8_t* 
     *r1_wins = a >= '?' && b <= '0';
     return *r1_wins || (a <= '0' && b >= '?');
 }
-/* smallest passing overlap length (read.rs:323-367) or -1 */
+/* the full test of one overlap length (read.rs:339-367): <= 2 mismatches, each one a "low quality" pair */
+template <int W>
+__device__ __forceinline__ bool overlap_passes(const Col& c, int len1, int len2, int o, const uint8_t* q1, const uint8_t* q2, int* diff_out) {
+    const int offset = len1 - o;
+    int cnt = 0;
+    for (int k = 0; 32 * k < o; k++) {
+        uint32_t mism = overlap_mism<W>(c, offset, o, len2, k);
+        if (!mism) continue;
+        cnt += __popc(mism);
+        if (cnt > 2) return false;
+        while (mism) {
+            int b = __ffs(mism) - 1;
+            mism &= mism - 1;
+            bool r1w;
+            if (!low_qual_pair(q1, q2, offset, len2, 32 * k + b, &r1w)) return false;
+        }
+    }
+    *diff_out = cnt;
+    return true;
+}
+/* smallest passing overlap length (read.rs:323-367) or -1.
+ * Cheap reject per overlap length o: the low code-bit plane of R1 at offset len1 - o against the first 32 bases of rc(R2)
+ * must differ in <= 2 positions.  The R1 window slides by one bit per o, so the plane words are loaded once per 32 overlap
+ * lengths and every o costs funnel shift + xor + popc + 2 (candidate bit shifted into a mask, no branch). */
 template <int W>
 __device__ __forceinline__ int find_overlap(const Col& c, int len1, int len2, const uint8_t* q1, const uint8_t* q2, int* diff_out) {
     const int minlen = min(len1, len2);
+    *diff_out = 0;
+    /* o = 30, 31: fewer than 32 positions */
+    for (int o = 30; o <= min(31, minlen); o++)
+        if (overlap_passes<W>(c, len1, len2, o, q1, q2, diff_out)) return o;
+    if (minlen < 32) return -1;
+    const uint32_t c0 = c(Lay<W>::C2LO, 0);
+    const int w_hi = (len1 - 32) >> 5, w_lo = (len1 - minlen) >> 5;
+    uint32_t b = c(Lay<W>::R1LO, w_hi + 1);
 #pragma unroll 1
-    for (int o = 30; o <= minlen; o++) {
-        const int offset = len1 - o;
-        /* cheap reject: low code-bit plane of the first chunk */
-        {
-            uint32_t x = (c.fs(Lay<W>::R1LO, (uint32_t)offset) ^ c(Lay<W>::C2LO, 0)) & lowmask(o);
-            if (__popc(x) > 2) continue;
+    for (int w = w_hi; w >= w_lo; w--) {
+        const uint32_t a = c(Lay<W>::R1LO, w);
+        uint32_t cand = 0; /* bit 31 - j <-> offset 32 w + 31 - j, i.e. o = o_base + j */
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const uint32_t x = __funnelshift_r(a, b, 31 - j) ^ c0;
+            cand = __funnelshift_l((uint32_t)(__popc(x) - 3), cand, 1);
         }
-        int cnt = 0;
-        bool ok = true;
-        for (int k = 0; ok && 32 * k < o; k++) {
-            uint32_t mism = overlap_mism<W>(c, offset, o, len2, k);
-            if (!mism) continue;
-            cnt += __popc(mism);
-            if (cnt > 2) { ok = false; break; }
-            while (mism) {
-                int b = __ffs(mism) - 1;
-                mism &= mism - 1;
-                bool r1w;
-                if (!low_qual_pair(q1, q2, offset, len2, 32 * k + b, &r1w)) { ok = false; break; }
-            }
+        b = a;
+        const int o_base = len1 - 32 * w - 31;
+        /* keep 32 <= o <= minlen */
+        const int j_lo = max(0, 32 - o_base), j_hi = min(31, minlen - o_base);
+        if (j_hi < j_lo) continue;
+        cand &= (0xFFFFFFFFu >> j_lo) & (0xFFFFFFFFu << (31 - j_hi));
+        while (cand) { /* rare: candidates in increasing o */
+            const int j = __clz(cand);
+            cand &= ~(0x80000000u >> j);
+            if (overlap_passes<W>(c, len1, len2, o_base + j, q1, q2, diff_out)) return o_base + j;
         }
-        if (ok) { *diff_out = cnt; return o; }
     }
     *diff_out = 0;
     return -1;
