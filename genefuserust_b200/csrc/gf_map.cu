@@ -1207,14 +1207,13 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
             GF_CUDA_TRY(idx->ws_seq_words.reserve(groups * NW3 * 32 * sizeof(uint32_t)));
             GF_CUDA_TRY(idx->ws_seq_meta.reserve((size_t)cap * sizeof(uint4)));
             GF_CUDA_TRY(idx->ws_seq_seed.reserve((size_t)cap * sizeof(uint2)));
-            GF_CUDA_TRY(idx->ws_seq_lists.reserve((size_t)cap * 2 * sizeof(uint32_t) + 64));
+            GF_CUDA_TRY(idx->ws_seq_lists.reserve((size_t)cap * 4 * sizeof(uint32_t) + 64));
             split::SeqStore ss;
             ss.words = idx->ws_seq_words.as<uint32_t>();
             ss.meta = idx->ws_seq_meta.as<uint4>();
             ss.seed = idx->ws_seq_seed.as<uint2>();
             ss.counters = idx->ws_seq_lists.as<unsigned int>();
-            ss.list_seeded = idx->ws_seq_lists.as<uint32_t>() + 16;
-            ss.list_unseeded = ss.list_seeded + cap;
+            for (int l = 0; l < 4; l++) ss.lists[l] = idx->ws_seq_lists.as<uint32_t>() + 16 + (size_t)l * cap;
             ss.cap = cap;
             GF_CUDA_TRY(cudaMemsetAsync(ss.counters, 0, 64, st));
             split::PrepParams pp;

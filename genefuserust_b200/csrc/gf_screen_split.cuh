@@ -26,9 +26,9 @@ struct SeqStore {
     uint32_t* words;
     uint4* meta;
     uint2* seed;              /* per slot: {seed_val, seed_i} */
-    uint32_t* list_seeded;    /* slot indices */
-    uint32_t* list_unseeded;
-    unsigned int* counters;   /* [0] slots, [1] seeded, [2] unseeded */
+    uint32_t* lists[4];       /* slot indices: seeded short / seeded long / unseeded short / unseeded long, where
+                                 short = at most 32 W bases (every unmerged read); warps then run one length class */
+    unsigned int* counters;   /* [0] slots, [1..4] entries of lists[0..3] */
     uint32_t cap;
 };
 template <int W>
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepPa
                         if (r1w) { if (fix0 < 0) fix0 = offset + 32 * k + b; else fix1 = offset + 32 * k + b; }
                     }
                 }
-                for (int k = 0; k < NW; k++) {
+                for (int k = 0; k <= nwm; k++) { /* words 0 .. ceil(len/32): nothing beyond is ever read */
                     uint32_t lo = 0, hi = 0, v = 0;
                     if (k < nwm) {
                         int pos0 = 32 * k;
@@ -162,18 +162,18 @@ __global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepPa
                 c_merged++;
             } else if (sq == 0) {
                 len = len1;
-                for (int k = 0; k < NW; k++) {
-                    bool in = k <= W;
-                    w[(size_t)k * 32] = in ? c(Lay<W>::R1LO, k) : 0u;
-                    w[(size_t)(NW + k) * 32] = in ? c(Lay<W>::R1HI, k) : 0u;
-                    w[(size_t)(2 * NW + k) * 32] = in ? c(Lay<W>::R1V, k) : 0u;
+                const int nw = (len1 + 31) >> 5; /* <= W; plane word nw is zero */
+                for (int k = 0; k <= nw; k++) {
+                    w[(size_t)k * 32] = c(Lay<W>::R1LO, k);
+                    w[(size_t)(NW + k) * 32] = c(Lay<W>::R1HI, k);
+                    w[(size_t)(2 * NW + k) * 32] = c(Lay<W>::R1V, k);
                 }
                 info = 1u;
             } else {
                 /* forward R2 (upper-case validity) from the rc planes */
                 len = len2;
                 const int nw = (len2 + 31) >> 5;
-                for (int k = 0; k < NW; k++) {
+                for (int k = 0; k <= nw; k++) {
                     uint32_t lo = 0, hi = 0, v = 0;
                     if (k < nw) {
                         int pos = len2 - 32 * k - 32;
@@ -221,11 +221,12 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t s0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); s0 < n_slots; s0 += stride) {
         const uint32_t s = s0 + lane;
-        bool have = s < n_slots, seeded = false;
+        bool have = s < n_slots, seeded = false, is_long = false;
         uint32_t seed_val = GF_EMPTY_VAL, seed_i = 0;
         if (have) {
             const uint4 m = P.st.meta[s];
             const int len = (int)m.z;
+            is_long = len > 32 * W;
             const int nprobe = len >= 16 ? ((len - 16) >> 1) + 1 : 0;
             if (nprobe == 0 && P.need_total > 0) have = false; /* cannot reach the gate: dropped here */
             if (have && nprobe > 0) {
@@ -259,17 +260,18 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
             }
             if (have) P.st.seed[s] = make_uint2(seed_val, seed_i);
         }
-        /* class lists, warp-aggregated */
-        const uint32_t ms = __ballot_sync(FULL, have && seeded), mu = __ballot_sync(FULL, have && !seeded);
-        uint32_t bs = 0, bu = 0;
-        if (lane == 0) {
-            if (ms) bs = atomicAdd(&P.st.counters[1], (unsigned)__popc(ms));
-            if (mu) bu = atomicAdd(&P.st.counters[2], (unsigned)__popc(mu));
+        /* class lists, warp-aggregated: lane c reserves the entries of class c */
+        const int cls = have ? (seeded ? 0 : 2) + (is_long ? 1 : 0) : -1;
+        const uint32_t mine = __match_any_sync(FULL, cls);
+        uint32_t m4 = 0, base = 0;
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+            const uint32_t mc = __ballot_sync(FULL, cls == cc);
+            if (lane == (uint32_t)cc) m4 = mc;
         }
-        bs = __shfl_sync(FULL, bs, 0);
-        bu = __shfl_sync(FULL, bu, 0);
-        if (have && seeded) P.st.list_seeded[bs + __popc(ms & gf_lanemask_lt())] = s;
-        if (have && !seeded) P.st.list_unseeded[bu + __popc(mu & gf_lanemask_lt())] = s;
+        if (lane < 4 && m4) base = atomicAdd(&P.st.counters[1 + lane], (unsigned)__popc(m4));
+        base = __shfl_sync(FULL, base, cls < 0 ? 0 : cls);
+        if (cls >= 0) P.st.lists[cls][base + __popc(mine & gf_lanemask_lt())] = s;
     }
 }
 
@@ -316,10 +318,12 @@ __device__ __forceinline__ int probe_offsets(const GfDevIndex& ix, uint32_t om, 
 template <int W>
 __global__ void __launch_bounds__(256) k_scan(ClassParams P) {
     constexpr int NW = SL<W>::NW;
-    const uint32_t n = P.st.counters[2];
     const unsigned long long pol = make_policy_keep();
+    for (int cls = 2; cls < 4; cls++) {
+    const uint32_t n = P.st.counters[1 + cls];
+    const uint32_t* list = P.st.lists[cls];
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-        const uint32_t s = P.st.list_unseeded[t];
+        const uint32_t s = list[t];
         const uint4 m = P.st.meta[s];
         const int len = (int)m.z, nch = (len + 31) >> 5;
         const uint32_t* col = slot_words<W>(P.st, s);
@@ -333,24 +337,51 @@ __global__ void __launch_bounds__(256) k_scan(ClassParams P) {
         }
         if (P.need_total <= 0 || (T >= P.need_total && T >= P.need_minor)) push_survivor(P, m);
     }
+    }
 }
 
 /* seeded sequences: compare with the gene along the seed diagonal; exact votes where the 16-mer equals an indexed window.
- * The few offsets the diagonal does not explain (reads with a sequencing error) are queued per warp and probed by all
- * 32 lanes together, so the probe code does not run at 1-2 active threads. */
+ * Chunks with offsets the diagonal does not explain (reads with a sequencing error) are appended to a per-warp queue as ONE
+ * entry {plane words, offset mask, owner} (no per-offset loop in the diverged code); when the queue fills up or the warp's
+ * sequences are done, all 32 lanes expand the entries together: 16 lanes per entry, one even offset each. */
+constexpr int DIAG_Q = 128; /* queue entries per warp; flushed above DIAG_Q - 32 (a chunk adds <= 32) */
 template <int W>
-__global__ void __launch_bounds__(256) k_diag(ClassParams P) {
+__global__ void __launch_bounds__(256, 4) k_diag(ClassParams P) {
     constexpr int NW = SL<W>::NW;
-    __shared__ uint32_t q_key[8][512];
-    __shared__ uint8_t q_own[8][512];
+    __shared__ uint32_t q_lo0[8][DIAG_Q], q_lo1[8][DIAG_Q], q_hi0[8][DIAG_Q], q_hi1[8][DIAG_Q], q_om[8][DIAG_Q], q_meta[8][DIAG_Q];
     __shared__ int t_sh[8][32];
+    __shared__ unsigned q_cnt[8];
     const uint32_t lane = gf_lane(), wib = threadIdx.x >> 5;
-    const uint32_t n = P.st.counters[1];
     const unsigned long long pol = make_policy_keep();
     const GfDevIndex& ix = P.ix;
+    auto flush = [&]() {
+        __syncwarp();
+        const int total = (int)q_cnt[wib];
+#pragma unroll 2
+        for (int base = 0; base < total; base += 2) {
+            const int e = base + (int)(lane >> 4);
+            if (e < total) {
+                const uint32_t om = q_om[wib][e], meta = q_meta[wib][e];
+                const uint32_t b = 2u * (lane & 15u) + ((meta >> 9) & 1u);
+                if ((om >> b) & 1u) {
+                    const uint32_t kk = ((__funnelshift_r(q_hi0[wib][e], q_hi1[wib][e], b) & 0xFFFFu) << 16) |
+                                        (__funnelshift_r(q_lo0[wib][e], q_lo1[wib][e], b) & 0xFFFFu);
+                    const uint32_t key = ((meta >> 8) & 1u) ? gf_key_revcomp(kk) : kk;
+                    const int nsites = (int)gf_filter_sites(ix, ldg_filter(ix.filter + gf_filter_word(key, ix.filter_words), pol), key, ix.max_sites);
+                    if (nsites) atomicAdd(&t_sh[wib][meta & 31u], nsites);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) q_cnt[wib] = 0;
+        __syncwarp();
+    };
+    for (int cls = 0; cls < 2; cls++) {
+    const uint32_t n = P.st.counters[1 + cls];
+    const uint32_t* list = P.st.lists[cls];
     for (uint32_t t0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); t0 < n; t0 += gridDim.x * blockDim.x) {
         const bool have = t0 + lane < n;
-        const uint32_t s = have ? P.st.list_seeded[t0 + lane] : 0u;
+        const uint32_t s = have ? list[t0 + lane] : 0u;
         const uint4 m = have ? P.st.meta[s] : make_uint4(0, 0, 0, 0);
         const uint2 sd = have ? P.st.seed[s] : make_uint2(0, 0);
         const int len = (int)m.z, nch = have ? (len + 31) >> 5 : 0;
@@ -362,6 +393,8 @@ __global__ void __launch_bounds__(256) k_diag(ClassParams P) {
         const uint32_t wbase = D >> 5, sh = D & 31u;
         const uint32_t* gc = rc ? ix.g_cr : ix.g_cf;
         t_sh[wib][lane] = 0;
+        if (lane == 0) q_cnt[wib] = 0;
+        __syncwarp();
         /* read chunk k in the orientation of the comparison */
         auto read_chunk = [&](int k, uint32_t* lo, uint32_t* hi, uint32_t* v) {
             if (k >= nch) { *lo = *hi = *v = 0; return; }
@@ -395,8 +428,8 @@ __global__ void __launch_bounds__(256) k_diag(ClassParams P) {
         const int max_nch = (int)__reduce_max_sync(FULL, (unsigned)nch);
 #pragma unroll 1
         for (int k = 0; k < max_nch; k++) {
-            uint32_t om = 0, nlo = 0, nhi = 0, nv = 0;
             if (k < nch) {
+                uint32_t nlo, nhi, nv;
                 read_chunk(k + 1, &nlo, &nhi, &nv);
                 uint32_t e_nxt = 0, na = 0, nb = 0, nc = 0;
                 if (k + 1 < nch) {
@@ -414,40 +447,25 @@ __global__ void __launch_bounds__(256) k_diag(ClassParams P) {
                 uint32_t hit = c0 | c1 | c2;
                 c_d += __popc(hit);
                 T += __popc(c0) + 2 * __popc(c1) + 4 * __popc(c2);
-                om = run16(v_cur, nv) & parity & ~hit;
+                uint32_t om = run16(v_cur, nv) & parity & ~hit;
                 e_cur = e_nxt; cnt_a = na; cnt_b = nb; cnt_c = nc;
-            }
-            /* queue this chunk's unexplained offsets of all lanes, then probe them with the whole warp */
-            int cnt = __popc(om), incl = cnt;
-            for (int o = 1; o < 32; o <<= 1) {
-                int tt = __shfl_up_sync(FULL, incl, o);
-                if ((int)lane >= o) incl += tt;
-            }
-            const int total = __shfl_sync(FULL, incl, 31);
-            if (total) {
-                int pos = incl - cnt;
-                while (om) {
-                    uint32_t b = (uint32_t)(__ffs(om) - 1);
-                    om &= om - 1u;
-                    uint32_t kk = ((__funnelshift_r(hi_cur, nhi, b) & 0xFFFFu) << 16) | (__funnelshift_r(lo_cur, nlo, b) & 0xFFFFu);
-                    q_key[wib][pos] = rc ? gf_key_revcomp(kk) : kk;
-                    q_own[wib][pos] = (uint8_t)lane;
-                    pos++;
+                /* queue this chunk's unexplained offsets (one entry) */
+                if (om) {
+                    const unsigned pos = atomicAdd(&q_cnt[wib], 1u);
+                    q_lo0[wib][pos] = lo_cur; q_lo1[wib][pos] = nlo; q_hi0[wib][pos] = hi_cur; q_hi1[wib][pos] = nhi;
+                    q_om[wib][pos] = om;
+                    q_meta[wib][pos] = lane | (rc ? 0x100u : 0u) | ((parity & 1u) ? 0u : 0x200u);
                 }
-                __syncwarp();
-                for (int j = (int)lane; j < total; j += 32) {
-                    uint32_t key = q_key[wib][j];
-                    int nsites = (int)gf_filter_sites(ix, ldg_filter(ix.filter + gf_filter_word(key, ix.filter_words), pol), key, ix.max_sites);
-                    if (nsites) atomicAdd(&t_sh[wib][q_own[wib][j]], nsites);
-                }
-                __syncwarp();
+                v_cur = nv; lo_cur = nlo; hi_cur = nhi;
             }
-            if (k < nch) { v_cur = nv; lo_cur = nlo; hi_cur = nhi; }
+            __syncwarp();
+            if (q_cnt[wib] > (unsigned)(DIAG_Q - 32)) flush();
         }
-        __syncwarp();
+        flush();
         T += t_sh[wib][lane];
         if (have && (P.need_total <= 0 || P.need_minor <= 0 || (T >= P.need_total && (T - c_d) >= P.need_minor))) push_survivor(P, m);
         __syncwarp();
+    }
     }
 }
 
