@@ -61,27 +61,18 @@ __device__ __noinline__ uint4 load16_slow(const uint8_t* p, const uint8_t* lo, c
     return make_uint4(load4_guarded(p, lo, hi), load4_guarded(p + 4, lo, hi), load4_guarded(p + 8, lo, hi),
                       load4_guarded(p + 12, lo, hi));
 }
-/* 16-aligned 128-bit load, streaming (evict_first: the reads must not push the filter / gene planes out of L2);
- * bytes outside [lo, hi) read as 0 */
-__device__ __forceinline__ uint4 load16_guarded(const uint8_t* p, const uint8_t* lo, const uint8_t* hi, unsigned long long pol_stream) {
-    if (p >= lo && p + 16 <= hi) {
-        uint4 v;
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol_stream));
-        return v;
-    }
-    return load16_slow(p, lo, hi);
-}
-/* same, when the caller has already checked that the whole aligned span of the read lies inside the arena */
-__device__ __forceinline__ uint4 load16_span(const uint8_t* p, bool span_inside, const uint8_t* lo, const uint8_t* hi,
-                                             unsigned long long pol_stream) {
+/* 32-aligned 256-bit load (one full sector per request), streaming; `span_inside` = the caller has checked that the whole
+ * aligned span of the read lies inside the arena (false only for the first / last reads of a batch) */
+__device__ __forceinline__ void load32_span(const uint8_t* p, bool span_inside, const uint8_t* lo, const uint8_t* hi,
+                                            unsigned long long pol_stream, uint4* a, uint4* b) {
     if (span_inside) {
-        uint4 v;
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol_stream));
-        return v;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                     : "=r"(a->x), "=r"(a->y), "=r"(a->z), "=r"(a->w), "=r"(b->x), "=r"(b->y), "=r"(b->z), "=r"(b->w)
+                     : "l"(p), "l"(pol_stream));
+        return;
     }
-    return load16_slow(p, lo, hi);
+    *a = load16_slow(p, lo, hi);
+    *b = load16_slow(p + 16, lo, hi);
 }
 __device__ __forceinline__ unsigned long long make_policy_normal() {
     unsigned long long pol;
@@ -94,14 +85,14 @@ __device__ __forceinline__ unsigned long long make_policy_stream() {
     return pol;
 }
 
-/* Both converters read two aligned 16-byte blocks per step and turn each into 16 plane bits with a handful of SWAR
+/* Both converters read one aligned 32-byte sector (two 16-byte blocks) per step and turn each block into 16 plane bits with a handful of SWAR
  * operations (no per-base work):
  *   - the code bits (bit 2 / bit 1 of the ASCII byte = A0 T1 C2 G3) of 8 bytes are gathered by ONE multiply:
  *     z = low nibbles of word 0 | low nibbles of word 1 << 4, (z & 0x44444444) * 0x00408102 has the eight bit-2 values in
  *     base order in its top byte (0x00810204 for bit 1); the partial products never collide, so there are no carries;
  *   - validity: the expected letter is looked up with PRMT from the low 3 bits of each byte (A 001, C 011, T 100, G 111)
  *     and xor-ed with the byte; a block whose 16 differences are all zero takes the fast path (valid = 0xFFFF);
- *   - misalignment a (0..15) of the read w.r.t. the blocks is removed in the bit domain: planes are built at bit position
+ *   - misalignment a (0..31) of the read w.r.t. the sectors is removed in the bit domain: planes are built at bit position
  *     u = p + a and aligned word w = funnelshift(U[w], U[w+1], a). */
 __device__ __forceinline__ uint32_t expect4(uint32_t x) {
     const uint32_t t = x & 0x07070707u;
@@ -148,21 +139,19 @@ __device__ __forceinline__ uint32_t tailmask(int rem) { /* bits of a plane word 
 template <int W>
 __device__ __forceinline__ void convert_r1(const Col& c, const uint8_t* seq, int len, const uint8_t* lo, const uint8_t* hi,
                                            unsigned long long pol_stream) {
-    const uint32_t a = (uint32_t)((uintptr_t)seq & 15u);
-    const uint8_t* bp = seq - a; /* advanced by 32 per step */
+    const uint32_t a = (uint32_t)((uintptr_t)seq & 31u);
+    const uint8_t* bp = seq - a; /* 32-aligned, advanced by 32 per step */
     const int nu = len + (int)a;                      /* u positions in use: [a, nu) */
     const int nwords = len > 0 ? (nu + 31) >> 5 : 0;  /* U words, <= W + 1 */
     uint32_t plo = 0, phi = 0, pv = 0, pn = 0;        /* previous U word */
-    const bool inside = bp >= lo && bp + 32 * nwords <= hi; /* false only for the first / last reads of the arena */
+    const bool inside = bp >= lo && bp + 32 * nwords <= hi;
     uint4 A = fill16(), B = fill16();
-    if (nwords > 0) A = load16_span(bp, inside, lo, hi, pol_stream);
-    if (16 < nu) B = load16_span(bp + 16, inside, lo, hi, pol_stream);
+    if (nwords > 0) load32_span(bp, inside, lo, hi, pol_stream, &A, &B);
 #pragma unroll 1
     for (int m = 0; m < nwords; m++) {
         uint4 nA = fill16(), nB = fill16();
         bp += 32;
-        if (32 * (m + 1) < nu) nA = load16_span(bp, inside, lo, hi, pol_stream);
-        if (32 * (m + 1) + 16 < nu) nB = load16_span(bp + 16, inside, lo, hi, pol_stream);
+        if (m + 1 < nwords) load32_span(bp, inside, lo, hi, pol_stream, &nA, &nB);
         uint32_t l0, h0, v0, n0, l1, h1, v1, n1;
         block16<false>(A, &l0, &h0, &v0, &n0);
         block16<false>(B, &l1, &h1, &v1, &n1);
@@ -191,21 +180,19 @@ template <int W>
 __device__ __forceinline__ void convert_r2_rc(const Col& c, const uint8_t* seq, int len, const uint8_t* lo, const uint8_t* hi,
                                               unsigned long long pol_stream) {
     const uint8_t* end = seq + len;
-    const uint32_t pad = (uint32_t)((16u - ((uintptr_t)end & 15u)) & 15u); /* garbage bytes above the last base */
-    const uint8_t* top = end + pad;           /* 16-aligned, lowered by 32 per step */
+    const uint32_t pad = (uint32_t)((32u - ((uintptr_t)end & 31u)) & 31u); /* garbage bytes above the last base */
+    const uint8_t* top = end + pad;           /* 32-aligned, lowered by 32 per step */
     const int nu = len + (int)pad;
     const int nwords = len > 0 ? (nu + 31) >> 5 : 0;
     uint32_t plo = 0, phi = 0, pv = 0, pc = 0;
     const bool inside = top <= hi && top - 32 * nwords >= lo;
-    uint4 A = fill16(), B = fill16();         /* A: rc positions u' 0..15 of the word, B: 16..31 */
-    if (nwords > 0) A = load16_span(top - 16, inside, lo, hi, pol_stream);
-    if (16 < nu) B = load16_span(top - 32, inside, lo, hi, pol_stream);
+    uint4 A = fill16(), B = fill16();         /* A: rc positions u' 0..15 of the word (upper 16 bytes), B: 16..31 */
+    if (nwords > 0) load32_span(top - 32, inside, lo, hi, pol_stream, &B, &A);
 #pragma unroll 1
     for (int m = 0; m < nwords; m++) {
         uint4 nA = fill16(), nB = fill16();
         top -= 32;
-        if (32 * (m + 1) < nu) nA = load16_span(top - 16, inside, lo, hi, pol_stream);
-        if (32 * (m + 1) + 16 < nu) nB = load16_span(top - 32, inside, lo, hi, pol_stream);
+        if (m + 1 < nwords) load32_span(top - 32, inside, lo, hi, pol_stream, &nB, &nA);
         uint32_t l0, h0, v0, e0, l1, h1, v1, e1;
         block16<true>(A, &l0, &h0, &v0, &e0);
         block16<true>(B, &l1, &h1, &v1, &e1);
