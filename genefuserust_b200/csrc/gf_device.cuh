@@ -53,6 +53,10 @@ struct GfDevIndex {
                                    site or its key is HIGH */
     const uint32_t* g_cr;       /* same for the reverse-complement k-mer of that window */
     uint32_t g_cstride;
+    const uint32_t* g_if;       /* the same planes interleaved, 8 words (one 32-byte sector) per arena word w:
+                                   {lo, hi, valid, cf bit0, cf bit1, cf bit2, 0, 0} — k_diag fetches everything it needs
+                                   about 32 gene positions with ONE 256-bit load (one L1 wavefront instead of six) */
+    const uint32_t* g_ir;       /* {lo, hi, valid, cr bit0, cr bit1, cr bit2, 0, 0} for reverse-strand diagonals */
     const unsigned long long* filter; /* blocked Bloom filter over all non-HIGH keys, 64-bit blocks */
     uint32_t filter_words;
     const unsigned long long* filter_multi; /* second-level filter: NORMAL (dupe) keys only */

@@ -402,6 +402,20 @@ struct BuildWorkspace {
         return p;
     }
 };
+/* planes lo, hi, valid, cf[3], cr[3] (each `stride` words) -> two interleaved arrays of 8 words per arena word */
+__global__ void k_interleave_planes(const uint32_t* __restrict__ pl, uint32_t stride, uint32_t* __restrict__ g_if,
+                                    uint32_t* __restrict__ g_ir) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= stride) return;
+    const uint32_t lo = pl[w], hi = pl[(size_t)stride + w], v = pl[2ull * stride + w];
+    uint4* f = reinterpret_cast<uint4*>(g_if + 8ull * w);
+    uint4* r = reinterpret_cast<uint4*>(g_ir + 8ull * w);
+    f[0] = make_uint4(lo, hi, v, pl[3ull * stride + w]);
+    f[1] = make_uint4(pl[4ull * stride + w], pl[5ull * stride + w], 0u, 0u);
+    r[0] = make_uint4(lo, hi, v, pl[6ull * stride + w]);
+    r[1] = make_uint4(pl[7ull * stride + w], pl[8ull * stride + w], 0u, 0u);
+}
+
 }  // namespace
 
 int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_genes) {
@@ -595,9 +609,9 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
 
     /* gene bit-planes (lo, hi, valid) + per-window site-count planes (3 bits x 2 strands) */
     const uint32_t n_pw = (uint32_t)((arena_len + 31) / 32);
-    const size_t plane_stride = (size_t)n_pw + 72;
-    GF_CUDA_TRY(cudaMalloc(&idx->d_planes, sizeof(uint32_t) * plane_stride * 9));
-    GF_CUDA_TRY(cudaMemsetAsync(idx->d_planes, 0, sizeof(uint32_t) * plane_stride * 9, st));
+    const size_t plane_stride = ((size_t)n_pw + 72 + 7) & ~(size_t)7;
+    GF_CUDA_TRY(cudaMalloc(&idx->d_planes, sizeof(uint32_t) * plane_stride * 25));
+    GF_CUDA_TRY(cudaMemsetAsync(idx->d_planes, 0, sizeof(uint32_t) * plane_stride * 25, st));
     uint32_t* pl = (uint32_t*)idx->d_planes;
     idx->dev.g_lo = pl;
     idx->dev.g_hi = pl + plane_stride;
@@ -610,6 +624,12 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     k_window_class<<<ex_blocks, EX_THREADS, 0, st>>>(idx->dev, (const uint8_t*)idx->d_gene_ascii, arena_len,
                                                      pl + 3 * plane_stride, pl + 6 * plane_stride,
                                                      (uint32_t)plane_stride);
+    /* interleaved copies for k_diag: one sector per arena word and strand (9 planes + 2 x 8 words = 25 strides; the
+     * allocation is 256-byte aligned and 9 * plane_stride is a multiple of 8 words, so every entry is 32-byte aligned) */
+    idx->dev.g_if = pl + 9 * plane_stride;
+    idx->dev.g_ir = pl + 17 * plane_stride;
+    k_interleave_planes<<<(unsigned)((plane_stride + 255) / 256), 256, 0, st>>>(pl, (uint32_t)plane_stride, pl + 9 * plane_stride,
+                                                                                  pl + 17 * plane_stride);
     GF_CUDA_TRY(cudaGetLastError());
     GF_CUDA_TRY(cudaEventRecord(e1, st));
     GF_CUDA_TRY(cudaStreamSynchronize(st));
@@ -630,7 +650,7 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     inf.max_displacement = h_maxdisp;
     inf.gene_bytes = gene_bytes;
     inf.device_bytes = n_buckets * 32 + sizeof(uint32_t) * ((size_t)n_dupes + 8) + arena_len + 9ull * (n_genes + 1) +
-                       sizeof(uint32_t) * plane_stride * 9 + sizeof(unsigned long long) * ((size_t)filter_words + filter_multi_words);
+                       sizeof(uint32_t) * plane_stride * 25 + sizeof(unsigned long long) * ((size_t)filter_words + filter_multi_words);
     inf.build_ms = ms;
     return GF_OK;
 }

@@ -1157,6 +1157,14 @@ cudaError_t set_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
+/* blocks of `kernel` that are resident on one SM at once (registers / shared memory / threads) */
+template <class K>
+static unsigned resident_blocks(K kernel, int threads, size_t smem) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
+    return (unsigned)nb;
+}
+
 /* ================================================================================================== */
 int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uint64_t out_cap,
                         unsigned long long* d_n_out, cudaStream_t st, bool record_events) {
@@ -1226,10 +1234,12 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
             if (const char* e = getenv("GF_PREFETCH")) pp.prefetch = atoi(e) != 0;
             const size_t psm = sizeof(uint32_t) * tpp::WARPS * (w5 ? tpp::Lay<5>::MLO : tpp::Lay<8>::MLO) * 32;
             const uint64_t want_b = (b.n + tpp::WARPS * 32 - 1) / (tpp::WARPS * 32);
-            const unsigned pgrid = (unsigned)std::min<uint64_t>(want_b, (uint64_t)idx->sm_count * (w5 ? 8 : 5));
+            /* persistent grids: exactly as many blocks as are resident at once (a partial second wave would idle SMs) */
 #define GF_LAUNCH_PREP(WW, PE)                                                             \
     do {                                                                                   \
         GF_CUDA_TRY(set_smem(split::k_prep<WW, PE>, psm));                                 \
+        const unsigned pgrid = (unsigned)std::min<uint64_t>(                               \
+            want_b, (uint64_t)idx->sm_count * resident_blocks(split::k_prep<WW, PE>, tpp::WARPS * 32, psm)); \
         split::k_prep<WW, PE><<<pgrid, tpp::WARPS * 32, psm, st>>>(pp);                    \
     } while (0)
             if (w5) { if (paired) GF_LAUNCH_PREP(5, true); else GF_LAUNCH_PREP(5, false); }
@@ -1248,15 +1258,15 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
             cp.counters = d_cnt;
             cp.need_total = sp.need_total;
             cp.need_minor = sp.need_minor;
-            const unsigned cgrid = (unsigned)idx->sm_count * 8;
+            const unsigned smc = (unsigned)idx->sm_count;
             if (w5) {
-                split::k_seed<5><<<cgrid, 256, 0, st>>>(sdp);
-                split::k_diag<5><<<cgrid, 256, 0, st>>>(cp);
-                split::k_scan<5><<<cgrid, 256, 0, st>>>(cp);
+                split::k_seed<5><<<smc * resident_blocks(split::k_seed<5>, 256, 0), 256, 0, st>>>(sdp);
+                split::k_diag<5><<<smc * resident_blocks(split::k_diag<5>, 256, 0), 256, 0, st>>>(cp);
+                split::k_scan<5><<<smc * resident_blocks(split::k_scan<5>, 256, 0), 256, 0, st>>>(cp);
             } else {
-                split::k_seed<8><<<cgrid, 256, 0, st>>>(sdp);
-                split::k_diag<8><<<cgrid, 256, 0, st>>>(cp);
-                split::k_scan<8><<<cgrid, 256, 0, st>>>(cp);
+                split::k_seed<8><<<smc * resident_blocks(split::k_seed<8>, 256, 0), 256, 0, st>>>(sdp);
+                split::k_diag<8><<<smc * resident_blocks(split::k_diag<8>, 256, 0), 256, 0, st>>>(cp);
+                split::k_scan<8><<<smc * resident_blocks(split::k_scan<8>, 256, 0), 256, 0, st>>>(cp);
             }
             idx->launches += 3;
         } else if (idx->screen_version >= 3 && small) {

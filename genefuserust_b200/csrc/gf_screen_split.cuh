@@ -230,15 +230,34 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
             const int nprobe = len >= 16 ? ((len - 16) >> 1) + 1 : 0;
             if (nprobe == 0 && P.need_total > 0) have = false; /* cannot reach the gate: dropped here */
             if (have && nprobe > 0) {
-                /* all 8 candidate k-mers go to the filter at once (independent L2 loads); the
-                 * HBM table is asked only for candidates the filter calls present-and-unique, in read order */
+                /* 8 candidate 16-mers at half-word aligned offsets (a candidate is then one shift + mask of a plane word, and
+                 * two candidates share the three plane loads): words k_j = (j * nwc) / 4, j = 0..3, halves 0 and 1.  Every
+                 * candidate offset is even and inside the read (its 16 valid bits), i.e. one of pass 1's probe offsets; which
+                 * ones are tried only decides the diagonal, never the bound.  All go to the L2 filter at once; the HBM table
+                 * is asked only for candidates the filter calls present-and-unique, in read order, and the bucket of the first
+                 * valid candidate is prefetched into L2 while the filter words are in flight. */
                 const uint32_t* col = slot_words<W>(P.st, s);
+                const int nwc = max(1, len >> 5);
                 uint32_t key[8], okm = 0;
+                int kprev = -1;
 #pragma unroll
-                for (int t = 0; t < 8; t++) {
-                    uint32_t i = (uint32_t)(((long long)t * nprobe) >> 3) * 2u;
-                    if ((fs_col(col, 2 * NW, i) & 0xFFFFu) == 0xFFFFu) okm |= 1u << t;
-                    key[t] = ((fs_col(col, NW, i) & 0xFFFFu) << 16) | (fs_col(col, 0, i) & 0xFFFFu);
+                for (int j = 0; j < 4; j++) {
+                    const int k = (j * nwc) >> 2;
+                    const uint32_t lo = col[(size_t)k * 32], hi = col[(size_t)(NW + k) * 32], v = col[(size_t)(2 * NW + k) * 32];
+                    key[2 * j] = (hi << 16) | (lo & 0xFFFFu);
+                    key[2 * j + 1] = (hi & 0xFFFF0000u) | (lo >> 16);
+                    if (k != kprev) {
+                        if ((v & 0xFFFFu) == 0xFFFFu) okm |= 1u << (2 * j);
+                        if ((v >> 16) == 0xFFFFu) okm |= 2u << (2 * j);
+                    }
+                    kprev = k;
+                }
+                if (okm) {
+                    const uint32_t t0 = (uint32_t)__ffs(okm) - 1u;
+                    uint32_t k0 = key[0];
+#pragma unroll
+                    for (int t = 1; t < 8; t++) if (t0 == (uint32_t)t) k0 = key[t];
+                    tpp::prefetch_l2(P.ix.table + 2ull * gf_home_bucket(k0, P.ix.bucket_shift));
                 }
                 unsigned long long fw[8];
 #pragma unroll
@@ -253,7 +272,7 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
                     uint32_t val = gf_table_find(P.ix, key[t]);
                     if (val != GF_EMPTY_VAL && (val >> 30) == GF_KIND_UNIQUE) {
                         seed_val = val;
-                        seed_i = (uint32_t)(((long long)t * nprobe) >> 3) * 2u;
+                        seed_i = 32u * (uint32_t)(((t >> 1) * nwc) >> 2) + 16u * (uint32_t)(t & 1);
                         seeded = true;
                     }
                 }
@@ -289,36 +308,18 @@ __device__ __forceinline__ void push_survivor(const ClassParams& P, const uint4&
     if (slot < P.survivors_cap) P.survivors[slot] = make_uint2(m.x, m.y);
     else atomicOr(&P.counters->error_flags, 2u);
 }
-/* filter probes for the set bits of `om` (offsets inside the current chunk), 4 in flight; returns the vote bound */
-__device__ __forceinline__ int probe_offsets(const GfDevIndex& ix, uint32_t om, uint32_t lo_cur, uint32_t lo_nxt, uint32_t hi_cur,
-                                             uint32_t hi_nxt, bool rc, unsigned long long pol) {
-    int T = 0;
-    while (om) {
-        uint32_t key[4];
-        unsigned long long w[4];
-        bool ok[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            ok[u] = om != 0u;
-            uint32_t b = ok[u] ? (uint32_t)(__ffs(om) - 1) : 0u;
-            om &= om - 1u;
-            uint32_t kk = ((__funnelshift_r(hi_cur, hi_nxt, b) & 0xFFFFu) << 16) | (__funnelshift_r(lo_cur, lo_nxt, b) & 0xFFFFu);
-            key[u] = rc ? gf_key_revcomp(kk) : kk;
-            w[u] = 0;
-            if (ok[u]) w[u] = ldg_filter(ix.filter + gf_filter_word(key[u], ix.filter_words), pol);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-            if (ok[u]) T += (int)gf_filter_sites(ix, w[u], key[u], ix.max_sites);
-    }
-    return T;
-}
-
-/* unseeded sequences: every valid even offset gets a filter probe; survive iff the bound reaches the gate */
+/* unseeded sequences: the valid even offsets get a filter probe until the outcome is decided.
+ * Bound (indexer.rs:286-360): a k-mer votes at most ONCE for any one diagonal (the sites of a key are distinct), so with
+ * s_i = sites of the k-mer at offset i:  count1 <= P = #{i : s_i >= 1}  and  count1 + count2 <= T = sum min(s_i, 2).
+ * The gate needs count1 >= need_major and count2 >= need_minor, hence P >= need_major and T >= need_major + need_minor;
+ * probing stops as soon as the offsets that are left cannot lift P or T over its threshold (off-target reads: after ~3/4
+ * of their offsets). */
 template <int W>
 __global__ void __launch_bounds__(256) k_scan(ClassParams P) {
     constexpr int NW = SL<W>::NW;
     const unsigned long long pol = make_policy_keep();
+    const GfDevIndex& ix = P.ix;
+    const int need_major = P.need_total - P.need_minor;
     for (int cls = 2; cls < 4; cls++) {
     const uint32_t n = P.st.counters[1 + cls];
     const uint32_t* list = P.st.lists[cls];
@@ -328,22 +329,53 @@ __global__ void __launch_bounds__(256) k_scan(ClassParams P) {
         const int len = (int)m.z, nch = (len + 31) >> 5;
         const uint32_t* col = slot_words<W>(P.st, s);
         uint32_t lo = col[0], hi = col[(size_t)NW * 32], v = col[(size_t)2 * NW * 32];
-        int T = 0;
+        int T = 0, Pn = 0;
+        bool dead = false;
 #pragma unroll 1
-        for (int k = 0; k < nch; k++) {
-            uint32_t nlo = col[(size_t)(k + 1) * 32], nhi = col[(size_t)(NW + k + 1) * 32], nv = col[(size_t)(2 * NW + k + 1) * 32];
-            T += probe_offsets(P.ix, run16(v, nv) & 0x55555555u, lo, nlo, hi, nhi, false, pol);
+        for (int k = 0; k < nch && !dead; k++) {
+            const uint32_t nlo = col[(size_t)(k + 1) * 32], nhi = col[(size_t)(NW + k + 1) * 32], nv = col[(size_t)(2 * NW + k + 1) * 32];
+            uint32_t om = run16(v, nv) & 0x55555555u;
+            const int beyond = len - 16 - 32 * (k + 1);            /* last probe offset relative to the next chunk */
+            const int rem_after = beyond >= 0 ? (beyond >> 1) + 1 : 0;
+            while (om) {
+                uint32_t key[4];
+                unsigned long long w[4];
+                bool ok[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    ok[u] = om != 0u;
+                    const uint32_t b = ok[u] ? (uint32_t)(__ffs(om) - 1) : 0u;
+                    om &= om - 1u;
+                    key[u] = ((__funnelshift_r(hi, nhi, b) & 0xFFFFu) << 16) | (__funnelshift_r(lo, nlo, b) & 0xFFFFu);
+                    w[u] = 0;
+                    if (ok[u]) w[u] = ldg_filter(ix.filter + gf_filter_word(key[u], ix.filter_words), pol);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (ok[u]) {
+                        const int si = (int)gf_filter_sites(ix, w[u], key[u], 2u);
+                        T += si;
+                        Pn += si != 0;
+                    }
+                const int rem = __popc(om) + rem_after;
+                if (P.need_total > 0 && (Pn + rem < need_major || T + 2 * rem < P.need_total)) { dead = true; break; }
+            }
             lo = nlo; hi = nhi; v = nv;
         }
-        if (P.need_total <= 0 || (T >= P.need_total && T >= P.need_minor)) push_survivor(P, m);
+        if (P.need_total <= 0 || (!dead && T >= P.need_total && Pn >= need_major && T >= P.need_minor)) push_survivor(P, m);
     }
     }
 }
 
-/* seeded sequences: compare with the gene along the seed diagonal; exact votes where the 16-mer equals an indexed window.
- * Chunks with offsets the diagonal does not explain (reads with a sequencing error) are appended to a per-warp queue as ONE
- * entry {plane words, offset mask, owner} (no per-offset loop in the diverged code); when the queue fills up or the warp's
- * sequences are done, all 32 lanes expand the entries together: 16 lanes per entry, one even offset each. */
+/* one interleaved gene-plane entry {lo, hi, valid, count bit 0, 1, 2, -, -}: a single 256-bit L2 load, kept in L2 */
+struct GeneWord { uint32_t lo, hi, v, a, b, c, pad0, pad1; };
+__device__ __forceinline__ GeneWord ldg_gene_word(const uint32_t* base, uint32_t w, unsigned long long pol) {
+    GeneWord g;
+    asm volatile("ld.global.nc.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(g.lo), "=r"(g.hi), "=r"(g.v), "=r"(g.a), "=r"(g.b), "=r"(g.c), "=r"(g.pad0), "=r"(g.pad1)
+                 : "l"(base + 8ull * w), "l"(pol));
+    return g;
+}
 constexpr int DIAG_Q = 128; /* queue entries per warp; flushed above DIAG_Q - 32 (a chunk adds <= 32) */
 template <int W>
 __global__ void __launch_bounds__(256, 4) k_diag(ClassParams P) {
@@ -367,7 +399,7 @@ __global__ void __launch_bounds__(256, 4) k_diag(ClassParams P) {
                     const uint32_t kk = ((__funnelshift_r(q_hi0[wib][e], q_hi1[wib][e], b) & 0xFFFFu) << 16) |
                                         (__funnelshift_r(q_lo0[wib][e], q_lo1[wib][e], b) & 0xFFFFu);
                     const uint32_t key = ((meta >> 8) & 1u) ? gf_key_revcomp(kk) : kk;
-                    const int nsites = (int)gf_filter_sites(ix, ldg_filter(ix.filter + gf_filter_word(key, ix.filter_words), pol), key, ix.max_sites);
+                    const int nsites = (int)gf_filter_sites(ix, ldg_filter(ix.filter + gf_filter_word(key, ix.filter_words), pol), key, 2u);
                     if (nsites) atomicAdd(&t_sh[wib][meta & 31u], nsites);
                 }
             }
@@ -391,7 +423,7 @@ __global__ void __launch_bounds__(256, 4) k_diag(ClassParams P) {
         const uint32_t D = rc ? goff + sd.y - (uint32_t)len + 1u : goff - sd.y;
         const uint32_t parity = (rc && (len & 1)) ? 0xAAAAAAAAu : 0x55555555u;
         const uint32_t wbase = D >> 5, sh = D & 31u;
-        const uint32_t* gc = rc ? ix.g_cr : ix.g_cf;
+        const uint32_t* gi = rc ? ix.g_ir : ix.g_if;
         t_sh[wib][lane] = 0;
         if (lane == 0) q_cnt[wib] = 0;
         __syncwarp();
@@ -408,21 +440,16 @@ __global__ void __launch_bounds__(256, 4) k_diag(ClassParams P) {
             *lo = ~__brev(a) & vv;
             *hi = __brev(b);
         };
-        uint32_t glo0 = 0, ghi0 = 0, gv0 = 0, gca0 = 0, gcb0 = 0, gcc0 = 0;
+        GeneWord g0 = {0, 0, 0, 0, 0, 0, 0, 0};
         uint32_t lo_cur = 0, hi_cur = 0, v_cur = 0, e_cur = 0, cnt_a = 0, cnt_b = 0, cnt_c = 0;
         if (have) {
-            glo0 = ldg_plane(ix.g_lo + wbase, pol); ghi0 = ldg_plane(ix.g_hi + wbase, pol); gv0 = ldg_plane(ix.g_v + wbase, pol);
-            gca0 = ldg_plane(gc + wbase, pol); gcb0 = ldg_plane(gc + ix.g_cstride + wbase, pol);
-            gcc0 = ldg_plane(gc + 2 * ix.g_cstride + wbase, pol);
+            g0 = ldg_gene_word(gi, wbase, pol);
+            const GeneWord g1 = ldg_gene_word(gi, wbase + 1, pol);
             read_chunk(0, &lo_cur, &hi_cur, &v_cur);
-            uint32_t glo1 = ldg_plane(ix.g_lo + wbase + 1, pol), ghi1 = ldg_plane(ix.g_hi + wbase + 1, pol),
-                     gv1 = ldg_plane(ix.g_v + wbase + 1, pol);
-            uint32_t gca1 = ldg_plane(gc + wbase + 1, pol), gcb1 = ldg_plane(gc + ix.g_cstride + wbase + 1, pol),
-                     gcc1 = ldg_plane(gc + 2 * ix.g_cstride + wbase + 1, pol);
-            e_cur = ~((lo_cur ^ __funnelshift_r(glo0, glo1, sh)) | (hi_cur ^ __funnelshift_r(ghi0, ghi1, sh))) & v_cur &
-                    __funnelshift_r(gv0, gv1, sh);
-            cnt_a = __funnelshift_r(gca0, gca1, sh); cnt_b = __funnelshift_r(gcb0, gcb1, sh); cnt_c = __funnelshift_r(gcc0, gcc1, sh);
-            glo0 = glo1; ghi0 = ghi1; gv0 = gv1; gca0 = gca1; gcb0 = gcb1; gcc0 = gcc1;
+            e_cur = ~((lo_cur ^ __funnelshift_r(g0.lo, g1.lo, sh)) | (hi_cur ^ __funnelshift_r(g0.hi, g1.hi, sh))) & v_cur &
+                    __funnelshift_r(g0.v, g1.v, sh);
+            cnt_a = __funnelshift_r(g0.a, g1.a, sh); cnt_b = __funnelshift_r(g0.b, g1.b, sh); cnt_c = __funnelshift_r(g0.c, g1.c, sh);
+            g0 = g1;
         }
         int T = 0, c_d = 0;
         const int max_nch = (int)__reduce_max_sync(FULL, (unsigned)nch);
@@ -433,20 +460,17 @@ __global__ void __launch_bounds__(256, 4) k_diag(ClassParams P) {
                 read_chunk(k + 1, &nlo, &nhi, &nv);
                 uint32_t e_nxt = 0, na = 0, nb = 0, nc = 0;
                 if (k + 1 < nch) {
-                    uint32_t glo1 = ldg_plane(ix.g_lo + wbase + k + 2, pol), ghi1 = ldg_plane(ix.g_hi + wbase + k + 2, pol),
-                             gv1 = ldg_plane(ix.g_v + wbase + k + 2, pol);
-                    uint32_t gca1 = ldg_plane(gc + wbase + k + 2, pol), gcb1 = ldg_plane(gc + ix.g_cstride + wbase + k + 2, pol),
-                             gcc1 = ldg_plane(gc + 2 * ix.g_cstride + wbase + k + 2, pol);
-                    e_nxt = ~((nlo ^ __funnelshift_r(glo0, glo1, sh)) | (nhi ^ __funnelshift_r(ghi0, ghi1, sh))) & nv &
-                            __funnelshift_r(gv0, gv1, sh);
-                    na = __funnelshift_r(gca0, gca1, sh); nb = __funnelshift_r(gcb0, gcb1, sh); nc = __funnelshift_r(gcc0, gcc1, sh);
-                    glo0 = glo1; ghi0 = ghi1; gv0 = gv1; gca0 = gca1; gcb0 = gcb1; gcc0 = gcc1;
+                    const GeneWord g1 = ldg_gene_word(gi, wbase + k + 2, pol);
+                    e_nxt = ~((nlo ^ __funnelshift_r(g0.lo, g1.lo, sh)) | (nhi ^ __funnelshift_r(g0.hi, g1.hi, sh))) & nv &
+                            __funnelshift_r(g0.v, g1.v, sh);
+                    na = __funnelshift_r(g0.a, g1.a, sh); nb = __funnelshift_r(g0.b, g1.b, sh); nc = __funnelshift_r(g0.c, g1.c, sh);
+                    g0 = g1;
                 }
                 uint32_t mm = run16(e_cur, e_nxt) & parity;
                 uint32_t c0 = cnt_a & mm, c1 = cnt_b & mm, c2 = cnt_c & mm;
                 uint32_t hit = c0 | c1 | c2;
                 c_d += __popc(hit);
-                T += __popc(c0) + 2 * __popc(c1) + 4 * __popc(c2);
+                T += __popc(hit) + __popc(c1 | c2); /* min(sites, 2) per offset: a k-mer votes once per diagonal */
                 uint32_t om = run16(v_cur, nv) & parity & ~hit;
                 e_cur = e_nxt; cnt_a = na; cnt_b = nb; cnt_c = nc;
                 /* queue this chunk's unexplained offsets (one entry) */

@@ -1,10 +1,11 @@
 #!/usr/bin/env python3
 """Aggregates an ncu report's per-instruction counters by source function / line (needs -lineinfo builds).
-usage: ncu_by_function.py report.ncu-rep [n_units]   (n_units: divide instruction counts, e.g. pairs per launch)"""
+usage: ncu_by_function.py report.ncu-rep [n_units] [kernel-regex]   (n_units: divide instruction counts, e.g. pairs per launch)"""
 import collections, csv, re, subprocess, sys, os
 rep = sys.argv[1]
 units = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+kf = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + kf, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = None; cur = None
 agg = collections.defaultdict(lambda: [0, 0, ""])
