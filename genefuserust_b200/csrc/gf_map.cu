@@ -762,18 +762,27 @@ __device__ void revcomp_inplace(uint8_t* seq, int len) {
 /* ------------------------------------------------------------------------------------------------ */
 /* k_exact                                                                                           */
 constexpr int EX_SEQ_CAP = 2048 + 64;
-constexpr int EX_TBL_SMEM = 1024;       /* vote-table slots in shared memory (reads up to ~320 bases) */
-constexpr int EX_TBL_GLOBAL = 8192;     /* per-warp global fallback (long reads / many dupes) */
 constexpr int EX_WARPS = 4;
 constexpr long long EX_EMPTY_KEY = LLONG_MIN;
 
-struct ExactWarp {
-    long long tkeys[EX_TBL_SMEM];
-    int tcnt[EX_TBL_SMEM];
-    uint8_t seq[EX_SEQ_CAP];
-    uint8_t flag[EX_SEQ_CAP];
-    uint8_t mask[EX_SEQ_CAP];
+/* per-warp state of the exact path.  Two sizes: reads of up to 256 bases (merged <= 482) use a 256-slot vote table and
+ * 544-byte sequence buffers, 4.7 KB per warp, so that 40+ warps are resident per SM (the kernel is a chain of dependent
+ * HBM / shared-memory round trips: throughput = survivors in flight); longer reads use 1024 slots and 2112 bytes.  A read
+ * whose votes do not fit the shared table (distinct diagonals > 3/4 of the slots: repeats) redoes pass 1 with the warp's
+ * table in global memory (GT slots >= the most votes a read of that class can cast). */
+template <int TBL, int CAP, int GT>
+struct ExactWarpT {
+    static constexpr int TBL_SLOTS = TBL, SEQ_CAP = CAP, GLOBAL_SLOTS = GT;
+    long long tkeys[TBL];
+    int tcnt[TBL];
+    uint8_t seq[CAP];
+    uint8_t flag[CAP];
+    uint8_t mask[CAP];
+    int distinct;  /* keys in the shared table */
+    int overflow;  /* the shared table is too small for this read */
 };
+using ExactWarpSmall = ExactWarpT<256, 544, 2048>;
+using ExactWarpLarge = ExactWarpT<1024, EX_SEQ_CAP, 8192>;
 
 struct ExactParams {
     GfDevIndex ix;
@@ -784,7 +793,7 @@ struct ExactParams {
     gf_match* out;
     unsigned long long out_cap;
     unsigned long long* n_out;
-    long long* gtbl_keys; /* [n_warps_total][EX_TBL_GLOBAL] */
+    long long* gtbl_keys; /* [n_warps_total][GLOBAL_SLOTS] */
     int* gtbl_cnt;
 };
 
@@ -795,18 +804,21 @@ struct Top2 { long long k1, k2; int c1, c2; };
 __device__ __forceinline__ bool vote_better(int ca, long long ka, int cb, long long kb) {
     return ca > cb || (ca == cb && ca > 0 && ka < kb);
 }
-__device__ __forceinline__ void vote_insert(long long* tk, int* tc, uint32_t tmask, long long g) {
+__device__ __forceinline__ void vote_insert(long long* tk, int* tc, uint32_t tmask, long long g, int* distinct, int limit,
+                                            int* overflow) {
     if (g == 0) return; /* key 0 is the "no hit" bucket and is never a candidate (k != 0, indexer.rs:337) */
     uint32_t h = (uint32_t)(((unsigned long long)g * 0x9E3779B97F4A7C15ull) >> 40) & tmask;
-    for (;;) {
+    for (uint32_t tries = 0; tries <= tmask; tries++) {
         long long old = (long long)atomicCAS((unsigned long long*)&tk[h], (unsigned long long)EX_EMPTY_KEY,
                                              (unsigned long long)g);
         if (old == EX_EMPTY_KEY || old == g) {
             atomicAdd(&tc[h], 1);
+            if (old == EX_EMPTY_KEY && atomicAdd(distinct, 1) >= limit) *overflow = 1;
             return;
         }
         h = (h + 1) & tmask;
     }
+    *overflow = 1; /* table full */
 }
 /* visit every (contig, position) the k-mer at seq[i..i+16) maps to */
 template <class F>
@@ -833,7 +845,8 @@ __device__ __forceinline__ void for_each_site(const GfDevIndex& ix, const uint8_
 struct SegResult { int n; int s0, e0, s1, e1; long long gp0, gp1; }; /* entries in TOP, SECOND order */
 
 /* Indexer::map_read (indexer.rs:252-538) on the ASCII sequence in W.seq.  All lanes return the same result. */
-__device__ SegResult exact_map_read(const GfDevIndex& ix, ExactWarp& W, int len, long long* gkeys, int* gcnt) {
+template <class EW>
+__device__ SegResult exact_map_read(const GfDevIndex& ix, EW& W, int len, long long* gkeys, int* gcnt) {
     const uint32_t lane = gf_lane();
     SegResult R;
     R.n = 0; R.s0 = R.e0 = R.s1 = R.e1 = 0; R.gp0 = R.gp1 = 0;
@@ -841,18 +854,26 @@ __device__ SegResult exact_map_read(const GfDevIndex& ix, ExactWarp& W, int len,
     const int nprobe = ((len - 16) >> 1) + 1;
     long long* tk = W.tkeys;
     int* tc = W.tcnt;
-    uint32_t tsize = EX_TBL_SMEM;
-    /* at most nprobe * max_sites distinct votes: shared-memory table while it stays <= 75% full */
-    if ((uint32_t)nprobe * ix.max_sites * 4u > 3u * EX_TBL_SMEM) { tk = gkeys; tc = gcnt; tsize = EX_TBL_GLOBAL; }
-    const uint32_t tmask = tsize - 1;
-    for (uint32_t s = lane; s < tsize; s += 32) { tk[s] = EX_EMPTY_KEY; tc[s] = 0; }
-    __syncwarp();
-    /* first pass: every 2nd offset votes for pack(contig, position - i)  (:277-321) */
-    for (int j = (int)lane; j < nprobe; j += 32) {
-        int i = 2 * j;
-        for_each_site(ix, W.seq, i, [&](int32_t c, int32_t p) { vote_insert(tk, tc, tmask, gf_gp_pack(c, p - i)); });
+    uint32_t tsize = EW::TBL_SLOTS;
+    /* first pass: every 2nd offset votes for pack(contig, position - i)  (:277-321); shared table first, the global
+     * one when the read casts more distinct votes than 3/4 of the shared slots */
+    for (int round = 0; round < 2; round++) {
+        const uint32_t tmask = tsize - 1;
+        for (uint32_t s = lane; s < tsize; s += 32) { tk[s] = EX_EMPTY_KEY; tc[s] = 0; }
+        if (lane == 0) { W.distinct = 0; W.overflow = 0; }
+        __syncwarp();
+        const int limit = (int)(tsize - tsize / 4);
+        for (int j = (int)lane; j < nprobe; j += 32) {
+            int i = 2 * j;
+            for_each_site(ix, W.seq, i, [&](int32_t c, int32_t p) {
+                vote_insert(tk, tc, tmask, gf_gp_pack(c, p - i), &W.distinct, limit, &W.overflow);
+            });
+        }
+        __syncwarp();
+        if (!W.overflow || round == 1) break;
+        __syncwarp();
+        tk = gkeys; tc = gcnt; tsize = EW::GLOBAL_SLOTS;
     }
-    __syncwarp();
     /* top-2 (:324-346) */
     long long k1 = 0, k2 = 0;
     int c1 = 0, c2 = 0;
@@ -953,16 +974,17 @@ __device__ bool in_required_direction(const GfDevIndex& ix, int32_t lc, int32_t 
     return false; /* :597-599 compares left with left -> never true */
 }
 
+template <class EW>
 __global__ void __launch_bounds__(EX_WARPS * 32) k_exact(ExactParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ExactWarp* Wall = reinterpret_cast<ExactWarp*>(smem_raw);
+    EW* Wall = reinterpret_cast<EW*>(smem_raw);
     const uint32_t lane = gf_lane();
     const uint32_t wib = threadIdx.x >> 5;
-    ExactWarp& W = Wall[wib];
+    EW& W = Wall[wib];
     const uint64_t gwarp = (uint64_t)blockIdx.x * EX_WARPS + wib;
     const uint64_t n_warps = (uint64_t)gridDim.x * EX_WARPS;
-    long long* gkeys = P.gtbl_keys + gwarp * EX_TBL_GLOBAL;
-    int* gcnt = P.gtbl_cnt + gwarp * EX_TBL_GLOBAL;
+    long long* gkeys = P.gtbl_keys + gwarp * EW::GLOBAL_SLOTS;
+    int* gcnt = P.gtbl_cnt + gwarp * EW::GLOBAL_SLOTS;
     const uint32_t n_surv = min(P.counters->n_survivors, P.survivors_cap);
 
     for (uint64_t sidx = gwarp; sidx < n_surv; sidx += n_warps) {
@@ -971,7 +993,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) k_exact(ExactParams P) {
         const int olen = (int)((sv.y >> 2) & 0xFFFu), diff = (int)((sv.y >> 14) & 3u);
         __syncwarp();
         int len = load_sequence(P.b, pair, source, olen, W.seq);
-        if (len + 16 > EX_SEQ_CAP) continue;
+        if (len + 16 > EW::SEQ_CAP) { if (lane == 0) atomicOr(&P.counters->error_flags, 1u); continue; }
         if (lane == 0) for (int k = 0; k < 16; k++) W.seq[len + k] = 0;
         __syncwarp();
         for (int attempt = 0; attempt < 2; attempt++) {
@@ -1299,12 +1321,19 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
     if (record_events) GF_CUDA_TRY(cudaEventRecord(idx->ev_screen, st));
 
     if (b.n) {
-        /* exact path over the (device-side) survivor count: fixed persistent grid, no host round trip */
-        const unsigned ex_grid = (unsigned)idx->sm_count * 3;
+        /* exact path over the (device-side) survivor count: persistent grid of all resident warps, no host round trip */
+        const bool ex_small = b.max_len != 0 && b.max_len <= 256;
+        const size_t ex_smem = (ex_small ? sizeof(ExactWarpSmall) : sizeof(ExactWarpLarge)) * EX_WARPS;
+        const int ex_gslots = ex_small ? ExactWarpSmall::GLOBAL_SLOTS : ExactWarpLarge::GLOBAL_SLOTS;
+        if (ex_small) GF_CUDA_TRY(set_smem(k_exact<ExactWarpSmall>, ex_smem));
+        else GF_CUDA_TRY(set_smem(k_exact<ExactWarpLarge>, ex_smem));
+        const unsigned ex_res = ex_small ? resident_blocks(k_exact<ExactWarpSmall>, EX_WARPS * 32, ex_smem)
+                                         : resident_blocks(k_exact<ExactWarpLarge>, EX_WARPS * 32, ex_smem);
+        const unsigned ex_grid = (unsigned)idx->sm_count * std::min(ex_res, 10u);
         const size_t n_ex_warps = (size_t)ex_grid * EX_WARPS;
         static_assert(sizeof(long long) == 8, "");
-        GfBuf& gt = idx->ws_gtbl; /* per-warp global vote tables (long reads only) */
-        GF_CUDA_TRY(gt.reserve(n_ex_warps * EX_TBL_GLOBAL * (sizeof(long long) + sizeof(int))));
+        GfBuf& gt = idx->ws_gtbl; /* per-warp global vote tables (reads whose votes overflow the shared table) */
+        GF_CUDA_TRY(gt.reserve(n_ex_warps * ex_gslots * (sizeof(long long) + sizeof(int))));
         ExactParams ep;
         ep.ix = idx->dev;
         ep.b = b;
@@ -1315,10 +1344,9 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
         ep.out_cap = out_cap;
         ep.n_out = d_n_out;
         ep.gtbl_keys = gt.as<long long>();
-        ep.gtbl_cnt = (int*)(gt.as<long long>() + n_ex_warps * EX_TBL_GLOBAL);
-        const size_t ex_smem = sizeof(ExactWarp) * EX_WARPS;
-        GF_CUDA_TRY(set_smem(k_exact, ex_smem));
-        k_exact<<<ex_grid, EX_WARPS * 32, ex_smem, st>>>(ep);
+        ep.gtbl_cnt = (int*)(gt.as<long long>() + n_ex_warps * ex_gslots);
+        if (ex_small) k_exact<ExactWarpSmall><<<ex_grid, EX_WARPS * 32, ex_smem, st>>>(ep);
+        else k_exact<ExactWarpLarge><<<ex_grid, EX_WARPS * 32, ex_smem, st>>>(ep);
         GF_CUDA_TRY(cudaGetLastError());
         VerifyParams vp;
         vp.ix = idx->dev;
@@ -1327,7 +1355,7 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
         vp.out = d_out;
         vp.out_cap = out_cap;
         vp.n_out = d_n_out;
-        k_verify<<<(unsigned)idx->sm_count * 2, VF_WARPS * 32, 0, st>>>(vp);
+        k_verify<<<(unsigned)idx->sm_count * std::min(resident_blocks(k_verify, VF_WARPS * 32, 0), 12u), VF_WARPS * 32, 0, st>>>(vp);
         GF_CUDA_TRY(cudaGetLastError());
         idx->launches += 2;
     }

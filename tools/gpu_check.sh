@@ -2,7 +2,7 @@
 # one GPU round trip: parity tests, a short bench, and per-kernel time / instruction counts of one step
 # usage (under gpurun): bash tools/gpu_check.sh <tag>
 tag=${1:-chk}
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; tail -3 gpurun_out/${tag}_pytest.log
 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/${tag}.json 2> gpurun_out/${tag}.err
 python - <<PY
 import json
