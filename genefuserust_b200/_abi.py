@@ -129,6 +129,10 @@ class gf_map_stats(C.Structure):
         ("d2h_bytes", C.c_uint64),
         ("zero_copy_qual", C.c_uint32),
         ("reserved", C.c_uint32),
+        ("ms_prep", C.c_float),
+        ("ms_seed", C.c_float),
+        ("ms_diag", C.c_float),
+        ("ms_scan", C.c_float),
     ]
 
 

@@ -67,10 +67,13 @@ void destroy_handle(gf_index* idx) {
         if (s.done) cudaEventDestroy(s.done);
     }
     if (idx->h_slots) cudaFreeHost(idx->h_slots);
-    for (cudaEvent_t e : {idx->ev_start, idx->ev_screen, idx->ev_exact, idx->ev_end})
+    for (cudaEvent_t e : {idx->ev_start, idx->ev_screen, idx->ev_exact, idx->ev_end, idx->ev_prep, idx->ev_seed, idx->ev_diag})
         if (e) cudaEventDestroy(e);
     if (idx->stream) cudaStreamDestroy(idx->stream);
     if (idx->copy_stream) cudaStreamDestroy(idx->copy_stream);
+    if (idx->side_stream) cudaStreamDestroy(idx->side_stream);
+    if (idx->ev_fork) cudaEventDestroy(idx->ev_fork);
+    if (idx->ev_join) cudaEventDestroy(idx->ev_join);
     delete idx;
 }
 
@@ -131,6 +134,9 @@ int gf_index_create(const gf_gene_span* genes, uint32_t n_genes, const gf_params
     idx->device = device;
     idx->params = p;
     if (const char* e = getenv("GF_SCREEN")) { int v = atoi(e); if (v >= 1 && v <= 4) idx->screen_version = v; }
+    if (const char* e = getenv("GF_CONCURRENT")) idx->concurrent = atoi(e) != 0;
+    if (const char* e = getenv("GF_CC_DIAG")) { int v = atoi(e); if (v >= 1 && v <= 8) idx->cc_diag = v; }
+    if (const char* e = getenv("GF_CC_SCAN")) { int v = atoi(e); if (v >= 1 && v <= 8) idx->cc_scan = v; }
     int rc = GF_OK;
     do {
         cudaDeviceProp prop;
@@ -142,7 +148,9 @@ int gf_index_create(const gf_gene_span* genes, uint32_t n_genes, const gf_params
             break;
         }
         bool ok = cudaEventCreate(&idx->ev_start) == cudaSuccess && cudaEventCreate(&idx->ev_screen) == cudaSuccess &&
-                  cudaEventCreate(&idx->ev_exact) == cudaSuccess && cudaEventCreate(&idx->ev_end) == cudaSuccess;
+                  cudaEventCreate(&idx->ev_exact) == cudaSuccess && cudaEventCreate(&idx->ev_end) == cudaSuccess &&
+                  cudaEventCreate(&idx->ev_prep) == cudaSuccess && cudaEventCreate(&idx->ev_seed) == cudaSuccess &&
+                  cudaEventCreate(&idx->ev_diag) == cudaSuccess;
         for (auto& s : idx->stage)
             ok = ok && cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) == cudaSuccess;
@@ -457,6 +465,7 @@ int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8
     return GF_OK;
 }
 
+static_assert(sizeof(gf_map_stats) == 112 && sizeof(gf_match) == 48, "ABI layout (include/genefuse_gpu.h, _abi.py)");
 int gf_get_map_stats(const gf_index* cidx, gf_map_stats* out) {
     gf_index* idx = const_cast<gf_index*>(cidx);
     if (!idx || !out) return fail(GF_E_INVALID, "NULL argument");
@@ -475,6 +484,13 @@ int gf_get_map_stats(const gf_index* cidx, gf_map_stats* out) {
         idx->stats.ms_exact = b;
         idx->stats.ms_total = c;
         idx->stats.ms_merge = 0; /* fast_merge is fused into the screen kernel */
+        idx->stats.ms_prep = idx->stats.ms_seed = idx->stats.ms_diag = idx->stats.ms_scan = 0;
+        if (idx->split_events) {
+            GF_CUDA_TRY(cudaEventElapsedTime(&idx->stats.ms_prep, idx->ev_start, idx->ev_prep));
+            GF_CUDA_TRY(cudaEventElapsedTime(&idx->stats.ms_seed, idx->ev_prep, idx->ev_seed));
+            GF_CUDA_TRY(cudaEventElapsedTime(&idx->stats.ms_diag, idx->ev_seed, idx->ev_diag));
+            GF_CUDA_TRY(cudaEventElapsedTime(&idx->stats.ms_scan, idx->ev_diag, idx->ev_screen));
+        }
         idx->stats_pending = false;
         rc = check_flags(h);
         if (rc == GF_OK && h.counters.n_ref_panic)

@@ -89,7 +89,12 @@ struct gf_index {
 
     std::mutex mu; /* serialises calls on one handle */
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t side_stream = nullptr;                 /* k_scan next to k_diag (GF_CONCURRENT) */
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int concurrent = 0, cc_diag = 2, cc_scan = 3;       /* blocks per SM of k_diag / k_scan when they run side by side */
     cudaEvent_t ev_start = nullptr, ev_screen = nullptr, ev_exact = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_prep = nullptr, ev_seed = nullptr, ev_diag = nullptr; /* between the launches of the split screen */
+    bool split_events = false;                                           /* the last batch recorded them */
     bool ev_valid = false;
 
     /* mapping workspace (grow-only) */

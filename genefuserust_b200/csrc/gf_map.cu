@@ -1203,7 +1203,7 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
     GfMapCounters* d_cnt = idx->ws_counters.as<GfMapCounters>();
     GF_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(GfMapCounters), st));
     GF_CUDA_TRY(cudaMemsetAsync(d_n_out, 0, sizeof(unsigned long long), st));
-    if (record_events) GF_CUDA_TRY(cudaEventRecord(idx->ev_start, st));
+    if (record_events) { GF_CUDA_TRY(cudaEventRecord(idx->ev_start, st)); idx->split_events = false; }
 
     const int need_major = (idx->params.major_gene_key_requirement + 1) / 2;
     const int need_minor = (idx->params.minor_gene_key_requirement + 1) / 2;
@@ -1267,6 +1267,7 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
             if (w5) { if (paired) GF_LAUNCH_PREP(5, true); else GF_LAUNCH_PREP(5, false); }
             else { if (paired) GF_LAUNCH_PREP(8, true); else GF_LAUNCH_PREP(8, false); }
 #undef GF_LAUNCH_PREP
+            if (record_events) GF_CUDA_TRY(cudaEventRecord(idx->ev_prep, st));
             split::SeedParams sdp;
             sdp.ix = idx->dev;
             sdp.st = ss;
@@ -1281,15 +1282,35 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
             cp.need_total = sp.need_total;
             cp.need_minor = sp.need_minor;
             const unsigned smc = (unsigned)idx->sm_count;
-            if (w5) {
-                split::k_seed<5><<<smc * resident_blocks(split::k_seed<5>, 256, 0), 256, 0, st>>>(sdp);
-                split::k_diag<5><<<smc * resident_blocks(split::k_diag<5>, 256, 0), 256, 0, st>>>(cp);
-                split::k_scan<5><<<smc * resident_blocks(split::k_scan<5>, 256, 0), 256, 0, st>>>(cp);
-            } else {
-                split::k_seed<8><<<smc * resident_blocks(split::k_seed<8>, 256, 0), 256, 0, st>>>(sdp);
-                split::k_diag<8><<<smc * resident_blocks(split::k_diag<8>, 256, 0), 256, 0, st>>>(cp);
-                split::k_scan<8><<<smc * resident_blocks(split::k_scan<8>, 256, 0), 256, 0, st>>>(cp);
+#define GF_EV(e) do { if (record_events) GF_CUDA_TRY(cudaEventRecord(idx->e, st)); } while (0)
+            bool cc = idx->concurrent != 0;
+            if (cc && !idx->side_stream) {
+                cc = cudaStreamCreateWithFlags(&idx->side_stream, cudaStreamNonBlocking) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&idx->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&idx->ev_join, cudaEventDisableTiming) == cudaSuccess;
             }
+#define GF_LAUNCH_CLASSES(WW)                                                                                         \
+    do {                                                                                                              \
+        split::k_seed<WW><<<smc * resident_blocks(split::k_seed<WW>, 256, 0), 256, 0, st>>>(sdp);                     \
+        GF_EV(ev_seed);                                                                                               \
+        if (cc) { /* k_diag (latency / issue) and k_scan (L1TEX gathers) side by side, each on part of every SM */     \
+            GF_CUDA_TRY(cudaEventRecord(idx->ev_fork, st));                                                           \
+            GF_CUDA_TRY(cudaStreamWaitEvent(idx->side_stream, idx->ev_fork, 0));                                      \
+            split::k_diag<WW><<<smc * (unsigned)idx->cc_diag, 256, 0, st>>>(cp);                                      \
+            split::k_scan<WW><<<smc * (unsigned)idx->cc_scan, 256, 0, idx->side_stream>>>(cp);                        \
+            GF_CUDA_TRY(cudaEventRecord(idx->ev_join, idx->side_stream));                                             \
+            GF_EV(ev_diag);                                                                                           \
+            GF_CUDA_TRY(cudaStreamWaitEvent(st, idx->ev_join, 0));                                                    \
+        } else {                                                                                                      \
+            split::k_diag<WW><<<smc * resident_blocks(split::k_diag<WW>, 256, 0), 256, 0, st>>>(cp);                  \
+            GF_EV(ev_diag);                                                                                           \
+            split::k_scan<WW><<<smc * resident_blocks(split::k_scan<WW>, 256, 0), 256, 0, st>>>(cp);                  \
+        }                                                                                                             \
+    } while (0)
+            if (w5) GF_LAUNCH_CLASSES(5); else GF_LAUNCH_CLASSES(8);
+#undef GF_LAUNCH_CLASSES
+#undef GF_EV
+            if (record_events) idx->split_events = true;
             idx->launches += 3;
         } else if (idx->screen_version >= 3 && small) {
             /* thread per pair: 4 warps x (81 | 123) private words x 32 lanes of shared memory per block */

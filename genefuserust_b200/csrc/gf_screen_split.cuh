@@ -265,15 +265,28 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
                     fw[t] = 0;
                     if ((okm >> t) & 1u) fw[t] = ldg_filter(P.ix.filter + gf_filter_word(key[t], P.ix.filter_words), pol);
                 }
+                /* candidates the main filter calls present (the NORMAL / unique distinction is left to the table: asking
+                 * the second-level filter would cost another dependent L2 gather per candidate) */
+                uint32_t pm = 0;
 #pragma unroll
                 for (int t = 0; t < 8; t++) {
-                    if (seeded || !((okm >> t) & 1u)) continue;
-                    if (gf_filter_sites(P.ix, fw[t], key[t], 2u) != 1u) continue;
-                    uint32_t val = gf_table_find(P.ix, key[t]);
+                    uint32_t al, ah;
+                    gf_filter_masks(key[t], &al, &ah);
+                    const uint32_t wl = (uint32_t)fw[t], wh = (uint32_t)(fw[t] >> 32);
+                    if (((okm >> t) & 1u) && (wl & al) == al && (wh & ah) == ah) pm |= 1u << t;
+                }
+                while (pm) { /* usually one iteration: the first present candidate of an on-target read is unique */
+                    const int t = __ffs(pm) - 1;
+                    pm &= pm - 1u;
+                    uint32_t kt = key[0];
+#pragma unroll
+                    for (int u = 1; u < 8; u++) if (t == u) kt = key[u];
+                    const uint32_t val = gf_table_find(P.ix, kt);
                     if (val != GF_EMPTY_VAL && (val >> 30) == GF_KIND_UNIQUE) {
                         seed_val = val;
                         seed_i = 32u * (uint32_t)(((t >> 1) * nwc) >> 2) + 16u * (uint32_t)(t & 1);
                         seeded = true;
+                        break;
                     }
                 }
             }

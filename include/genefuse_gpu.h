@@ -172,6 +172,12 @@ typedef struct gf_map_stats {
     uint32_t zero_copy_qual; /* 1 = the quality arenas were pinned host memory and were NOT copied: the kernels
                                 read the few quality bytes fast_merge depends on directly over PCIe */
     uint32_t reserved;
+    /* the four launches ms_screen is made of (split screen, reads <= 256 bases; 0 otherwise).  gf_map_pairs (chunked
+     * host path): the last chunk only, like every other ms_* field there. */
+    float ms_prep;           /* k_prep: ASCII -> bit-planes, fast_merge, sequence store */
+    float ms_seed;           /* k_seed: seed k-mers -> filter -> one table lookup, class lists */
+    float ms_diag;           /* k_diag: seeded sequences against the gene planes */
+    float ms_scan;           /* k_scan: unseeded sequences, filter probes */
 } gf_map_stats;
 
 const char* gf_last_error(void);

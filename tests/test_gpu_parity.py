@@ -164,6 +164,49 @@ def test_scan_pair_end_noisy_fusions(mappers, small_panel):
     assert_same_matches(got, want, "noisy")
 
 
+def _repeat_rich_panel():
+    """genes that share long blocks (2, 3, 5 = NORMAL dupes; 6 copies = HIGH; one copy reverse-complemented), with
+    fusion breakpoints inside and at the edges of the shared blocks: votes spread over several diagonals per k-mer,
+    which is what the screen's bound  count1 + count2 <= sum min(sites, 2),  count1 <= #present  has to survive"""
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    genes = [synth.random_bases(4000 + g, 6000) for g in range(24)]
+    def put(g, pos, blk):
+        genes[g][pos:pos + len(blk)] = blk
+    a, b, c, d = (synth.random_bases(900 + k, n) for k, n in enumerate((1500, 1200, 800, 700)))
+    for g in (0, 1, 2):
+        put(g, 1000 + 500 * g, a)
+    put(3, 2000, b); put(4, 700, b)
+    put(5, 3000, np.frombuffer(b.tobytes()[::-1].translate(comp), dtype=np.uint8))
+    for g in (6, 7, 8, 9, 10):
+        put(g, 400 * (g - 5), c)
+    for g in (11, 12, 13, 14, 15, 16):
+        put(g, 2500, d)
+    fusions = [(0, 1700, 1, 3, 2500, 1), (1, 1500, 1, 20, 3000, -1), (2, 2000, -1, 4, 1200, 1), (5, 3600, 1, 21, 1000, 1),
+               (6, 600, 1, 7, 1100, -1), (8, 1500, -1, 22, 4000, -1), (11, 2800, 1, 23, 500, 1), (12, 2500, 1, 9, 1900, 1),
+               (3, 1999, 1, 0, 999, 1), (10, 2400, -1, 1, 3001, 1), (17, 3000, 1, 18, 3000, 1), (19, 100, 1, 17, 5900, -1)]
+    revs = [g % 3 == 0 for g in range(24)]
+    return synth.Panel([f"G{g}" for g in range(24)], genes, [int(r) for r in revs], fusions)
+
+
+@pytest.mark.parametrize("read_len,seed", [(150, 5), (100, 6), (250, 7)])
+def test_repeat_rich_panel(host, read_len, seed):
+    panel = _repeat_rich_panel()
+    m = host.FusionMapper.from_gene_spans(panel.genes(), device=0)
+    o = orc.OracleIndex(panel.genes())
+    c = o.counts()
+    assert c["n_normal"] > 3000 and c["n_high"] > 500
+    b = synth.generate_pairs(panel, 40000, read_len=read_len, seed=seed, p_target=0.45, p_fusion=0.5, sub_rate=0.004,
+                             n_rate=0.001)
+    got = m.scan_pair_end(b)
+    want = o.scan(b, threads=8)
+    assert len(want) > 3000
+    assert_same_matches(got, want, f"repeat-rich L={read_len}")
+    se = ReadBatch(b.seq2, b.qual2, b.off2)
+    assert_same_matches(m.scan_single_end(se), o.scan(se, threads=8), f"repeat-rich SE L={read_len}")
+    m.close()
+    o.close()
+
+
 def test_scan_single_end_parity(mappers, small_panel):
     m, o = mappers
     b = synth.generate_pairs(small_panel, 40000, read_len=150, seed=21, p_fusion=0.05)
