@@ -28,7 +28,7 @@ struct SeqStore {
     uint2* seed;              /* per slot: {seed_val, seed_i} */
     uint32_t* lists[4];       /* slot indices: seeded short / seeded long / unseeded short / unseeded long, where
                                  short = at most 32 W bases (every unmerged read); warps then run one length class */
-    unsigned int* counters;   /* [0] slots, [1..4] entries of lists[0..3] */
+    unsigned int* counters;   /* [0] short slots (from 0 up), [5] long slots (from cap - 1 down), [1..4] entries of lists[0..3] */
     uint32_t cap;
 };
 template <int W>
@@ -100,19 +100,27 @@ __global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepPa
                 nseq = olen >= 0 ? 1 : (PAIRED ? 2 : 1);
             }
         }
-        /* slots: warp-aggregated allocation, one atomic per warp (all lanes take part) */
-        int incl = nseq;
+        /* slots: warp-aggregated allocation (all lanes take part).  Short sequences (<= 32 W bases: every unmerged read)
+         * fill the store from slot 0 upwards, long ones (merged reads) from slot cap - 1 downwards, so that the class lists
+         * k_seed builds refer to nearly contiguous slots and the plane-word loads of k_diag / k_scan stay coalesced. */
+        const bool lng = olen >= 0 && (len1 - olen + len2) > 32 * W;
+        const int mine = lng ? (1 << 16) : nseq;
+        int incl = mine;
         for (int o = 1; o < 32; o <<= 1) {
             int t = __shfl_up_sync(FULL, incl, o);
             if ((int)lane >= o) incl += t;
         }
         const int total = __shfl_sync(FULL, incl, 31);
-        uint32_t slot0 = 0;
-        if (total) {
-            if (lane == 0) slot0 = atomicAdd(&P.st.counters[0], (unsigned)total);
-            slot0 = __shfl_sync(FULL, slot0, 0) + (uint32_t)(incl - nseq);
+        uint32_t base_s = 0, base_l = 0;
+        if (lane == 0) {
+            if (total & 0xFFFF) base_s = atomicAdd(&P.st.counters[0], (unsigned)(total & 0xFFFF));
+            if (total >> 16) base_l = atomicAdd(&P.st.counters[5], (unsigned)(total >> 16));
         }
-        if (nseq && slot0 + (uint32_t)nseq > P.st.cap) { err |= 2u; nseq = 0; }
+        base_s = __shfl_sync(FULL, base_s, 0);
+        base_l = __shfl_sync(FULL, base_l, 0);
+        const int excl = incl - mine;
+        uint32_t slot0 = lng ? P.st.cap - 1u - (base_l + (uint32_t)(excl >> 16)) : base_s + (uint32_t)(excl & 0xFFFF);
+        if (nseq && (lng ? base_l + (uint32_t)(excl >> 16) >= P.st.cap : slot0 + (uint32_t)nseq > P.st.cap)) { err |= 2u; nseq = 0; }
         for (int sq = 0; sq < nseq; sq++) {
             const uint32_t s = slot0 + (uint32_t)sq;
             uint32_t* w = slot_words<W>(P.st, s);
@@ -216,12 +224,14 @@ template <int W>
 __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
     constexpr int NW = SL<W>::NW;
     const uint32_t lane = gf_lane();
-    const uint32_t n_slots = min(P.st.counters[0], P.st.cap);
+    const uint32_t n_short = min(P.st.counters[0], P.st.cap), n_long = min(P.st.counters[5], P.st.cap - n_short);
+    const uint32_t n_slots = n_short + n_long; /* virtual index v: short slots, then the long ones in ascending order */
     const unsigned long long pol = make_policy_keep();
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t s0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); s0 < n_slots; s0 += stride) {
-        const uint32_t s = s0 + lane;
-        bool have = s < n_slots, seeded = false, is_long = false;
+        const uint32_t vi = s0 + lane;
+        const uint32_t s = vi < n_short ? vi : P.st.cap - n_long + (vi - n_short);
+        bool have = vi < n_slots, seeded = false, is_long = false;
         uint32_t seed_val = GF_EMPTY_VAL, seed_i = 0;
         if (have) {
             const uint4 m = P.st.meta[s];
