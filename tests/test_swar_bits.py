@@ -1,0 +1,110 @@
+"""CPU model of the 16-base SWAR step of the read converters (csrc/gf_screen_tpp.cuh: expect4 / block16): the multiply
+gathers, the PRMT validity lookup and the slow path, checked against the plain definition of the planes
+(make_kmer_bytes' code A0 T1 C2 G3, src/core/indexer.rs:888-904; reverse_complement's case rule, src/core/sequence.rs:52-60).
+The constants are read from the CUDA source so that the model cannot drift from the kernel."""
+import os
+import random
+import re
+
+SRC = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "genefuserust_b200", "csrc", "gf_screen_tpp.cuh")).read()
+M32 = 0xFFFFFFFF
+
+
+def _const(pattern):
+    m = re.search(pattern, SRC)
+    assert m, pattern
+    return [int(x, 16) for x in m.groups()]
+
+
+LUT_LO, LUT_HI, PACK = _const(r"__byte_perm\((0x[0-9A-Fa-f]+)u, (0x[0-9A-Fa-f]+)u, __byte_perm\(u, 0u, (0x[0-9A-Fa-f]+)u\)\)")
+MUL_LO, = _const(r"\(z0 & 0x44444444u\) \* (0x[0-9A-Fa-f]+)u")
+MUL_HI, = _const(r"\(z0 & 0x22222222u\) \* (0x[0-9A-Fa-f]+)u")
+
+
+def byte_perm(x, y, s):
+    b = [(x >> (8 * i)) & 0xFF for i in range(4)] + [(y >> (8 * i)) & 0xFF for i in range(4)]
+    return sum(b[(s >> (4 * i)) & 7] << (8 * i) for i in range(4))
+
+
+def expect4(x):
+    t = x & 0x07070707
+    return byte_perm(LUT_LO, LUT_HI, byte_perm(t | (t >> 4), 0, PACK))
+
+
+def zero_bytes(y):
+    return (~((((y & 0x7F7F7F7F) + 0x7F7F7F7F) | y)) & 0x80808080) & M32
+
+
+def block16(x, ci):
+    z0 = (x[0] & 0x0F0F0F0F) | ((x[1] << 4) & 0xF0F0F0F0)
+    z1 = (x[2] & 0x0F0F0F0F) | ((x[3] << 4) & 0xF0F0F0F0)
+    lo = byte_perm(((z0 & 0x44444444) * MUL_LO) & M32, ((z1 & 0x44444444) * MUL_LO) & M32, 0x7373)
+    hi = byte_perm(((z0 & 0x22222222) * MUL_HI) & M32, ((z1 & 0x22222222) * MUL_HI) & M32, 0x7373)
+    cm = 0xDFDFDFDF if ci else M32
+    d = [(x[j] ^ expect4(x[j])) & cm for j in range(4)]
+    bad = d[0] | d[1] | d[2] | d[3]
+    if ci:
+        bad |= (x[0] | x[1] | x[2] | x[3]) & 0x20202020
+    v, ex = 0xFFFF, (0xFFFF if ci else 0)
+    if bad:
+        y0 = (zero_bytes(d[0]) >> 5) | (zero_bytes(d[1]) >> 1)
+        y1 = (zero_bytes(d[2]) >> 5) | (zero_bytes(d[3]) >> 1)
+        v = byte_perm((y0 * MUL_LO) & M32, (y1 * MUL_LO) & M32, 0x7373)
+        if ci:
+            w0 = ((x[0] >> 3) & 0x04040404) | ((x[1] << 1) & 0x40404040)
+            w1 = ((x[2] >> 3) & 0x04040404) | ((x[3] << 1) & 0x40404040)
+            ex = v & ~byte_perm((w0 * MUL_LO) & M32, (w1 * MUL_LO) & M32, 0x7373)
+        else:
+            n0 = (zero_bytes(x[0] ^ 0x4E4E4E4E) >> 5) | (zero_bytes(x[1] ^ 0x4E4E4E4E) >> 1)
+            n1 = (zero_bytes(x[2] ^ 0x4E4E4E4E) >> 5) | (zero_bytes(x[3] ^ 0x4E4E4E4E) >> 1)
+            ex = byte_perm((n0 * MUL_LO) & M32, (n1 * MUL_LO) & M32, 0x7373)
+        lo &= v
+        hi &= v
+    return lo & 0xFFFF, hi & 0xFFFF, v & 0xFFFF, ex & 0xFFFF
+
+
+def planes(bs, ci):
+    lo = hi = v = ex = 0
+    for p, b in enumerate(bs):
+        ch = chr(b)
+        up = ch.upper() if ci else ch
+        if up in "ACGT":
+            code = "ATCG".index(up)
+            lo |= (code & 1) << p
+            hi |= (code >> 1) << p
+            v |= 1 << p
+            if ci and ch in "ACGT":
+                ex |= 1 << p
+        if not ci and ch == "N":
+            ex |= 1 << p
+    return lo, hi, v, ex
+
+
+def _words(bs):
+    return [int.from_bytes(bs[4 * j:4 * j + 4], "little") for j in range(4)]
+
+
+def test_block16_random_blocks():
+    rng = random.Random(1)
+    alpha = b"ACGTACGTACGTACGTNacgtnRY\x00\xff@BDEFPQSUVW"
+    for it in range(40000):
+        mode = it % 4
+        if mode == 0:
+            bs = bytes(rng.choice(b"ACGT") for _ in range(16))
+        elif mode == 1:
+            bs = bytes(rng.choice(alpha) for _ in range(16))
+        elif mode == 2:
+            bs = bytes(rng.randrange(256) for _ in range(16))
+        else:
+            bs = bytes(rng.choice(b"ACGTacgt") for _ in range(16))
+        for ci in (False, True):
+            assert block16(_words(bs), ci) == planes(bs, ci), (bs, ci)
+
+
+def test_block16_every_byte_value_in_every_position():
+    for pos in range(16):
+        for b in range(256):
+            bs = bytearray(b"ACGTTGCAACGTTGCA")
+            bs[pos] = b
+            for ci in (False, True):
+                assert block16(_words(bytes(bs)), ci) == planes(bytes(bs), ci), (pos, b, ci)
