@@ -136,12 +136,25 @@ class gf_map_stats(C.Structure):
     ]
 
 
+class gf_break_ref(C.Structure):
+    _fields_ = [("left_off", C.c_uint64), ("right_off", C.c_uint64), ("left_len", C.c_uint32), ("right_len", C.c_uint32)]
+
+
+class gf_break_job(C.Structure):
+    _fields_ = [("seq_off", C.c_uint64), ("seq_len", C.c_uint32), ("read_break", C.c_int32), ("result", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class gf_break_out(C.Structure):
+    _fields_ = [("shift", C.c_int32), ("left_distance", C.c_int32), ("right_distance", C.c_int32), ("status", C.c_int32)]
+
+
 # every symbol include/genefuse_gpu.h declares (tests check the .so exports all of them)
 EXPORTS = (
     "gf_last_error", "gf_abi_version", "gf_device_count", "gf_default_params", "gf_index_create",
     "gf_index_destroy", "gf_index_get_info", "gf_index_lookup", "gf_map_pairs", "gf_map_pairs_device",
     "gf_sort_matches", "gf_get_map_stats", "gf_fast_merge", "gf_map_fastq", "gf_multi_create", "gf_multi_destroy",
-    "gf_multi_map_pairs",
+    "gf_multi_map_pairs", "gf_adjust_fusion_break",
 )
 
 _lib = None
@@ -191,5 +204,8 @@ def load_library():
     lib.gf_multi_map_pairs.restype = C.c_int
     lib.gf_fast_merge.argtypes = [C.c_void_p, P(gf_batch), P(gf_merge_info)]
     lib.gf_fast_merge.restype = C.c_int
+    lib.gf_adjust_fusion_break.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, P(gf_break_ref), C.c_uint32, P(gf_break_job),
+                                           C.c_uint64, P(gf_break_out)]
+    lib.gf_adjust_fusion_break.restype = C.c_int
     _lib = lib
     return lib

@@ -500,6 +500,47 @@ int gf_get_map_stats(const gf_index* cidx, gf_map_stats* out) {
     return rc;
 }
 
+/* FusionResult::adjust_fusion_break for a set of clustered matches (src/core/fusion_result.rs:299-397) */
+int gf_adjust_fusion_break(gf_index* idx, const uint8_t* bytes, uint64_t n_bytes, const gf_break_ref* refs, uint32_t n_refs,
+                           const gf_break_job* jobs, uint64_t n_jobs, gf_break_out* out) {
+    if (!idx || (n_jobs && (!jobs || !out || !refs)) || (n_bytes && !bytes)) return fail(GF_E_INVALID, "NULL argument");
+    if (n_jobs == 0) return GF_OK;
+    for (uint64_t j = 0; j < n_jobs; j++) {
+        const gf_break_job& b = jobs[j];
+        if (b.result >= n_refs) return fail(GF_E_INVALID, "gf_break_job.result out of range");
+        if (b.seq_off > n_bytes || b.seq_len > n_bytes - b.seq_off) return fail(GF_E_INVALID, "gf_break_job sequence outside the arena");
+        if (b.seq_len > GF_MAX_SEQ_LEN) return fail(GF_E_LIMIT, "gf_break_job sequence longer than GF_MAX_SEQ_LEN");
+    }
+    for (uint32_t r = 0; r < n_refs; r++) {
+        const gf_break_ref& f = refs[r];
+        if (f.left_off > n_bytes || f.left_len > n_bytes - f.left_off || f.right_off > n_bytes || f.right_len > n_bytes - f.right_off)
+            return fail(GF_E_INVALID, "gf_break_ref string outside the arena");
+    }
+    std::lock_guard<std::mutex> lk(idx->mu);
+    GF_CUDA_TRY(cudaSetDevice(idx->device));
+    GfStage& s = idx->stage[0];
+    GF_CUDA_TRY(s.seq1.reserve(n_bytes + 16));
+    GF_CUDA_TRY(s.off1.reserve(sizeof(gf_break_ref) * (size_t)n_refs));
+    GF_CUDA_TRY(s.off2.reserve(sizeof(gf_break_job) * n_jobs));
+    GF_CUDA_TRY(s.out.reserve(sizeof(gf_break_out) * n_jobs + 16));
+    GF_CUDA_TRY(idx->ws_counters.reserve(sizeof(GfMapCounters)));
+    cudaStream_t st = idx->stream;
+    unsigned int* d_undef = &idx->ws_counters.as<GfMapCounters>()->n_ref_panic;
+    GF_CUDA_TRY(cudaMemsetAsync(idx->ws_counters.p, 0, sizeof(GfMapCounters), st));
+    if (n_bytes) GF_CUDA_TRY(cudaMemcpyAsync(s.seq1.p, bytes, n_bytes, cudaMemcpyHostToDevice, st));
+    GF_CUDA_TRY(cudaMemcpyAsync(s.off1.p, refs, sizeof(gf_break_ref) * (size_t)n_refs, cudaMemcpyHostToDevice, st));
+    GF_CUDA_TRY(cudaMemcpyAsync(s.off2.p, jobs, sizeof(gf_break_job) * n_jobs, cudaMemcpyHostToDevice, st));
+    int rc = gf_adjust_break_device(idx, s.seq1.as<uint8_t>(), s.off1.as<gf_break_ref>(), s.off2.as<gf_break_job>(), n_jobs,
+                                    s.out.as<gf_break_out>(), d_undef, st);
+    if (rc != GF_OK) return rc;
+    GF_CUDA_TRY(cudaMemcpyAsync(out, s.out.p, sizeof(gf_break_out) * n_jobs, cudaMemcpyDeviceToHost, st));
+    unsigned int n_undef = 0;
+    GF_CUDA_TRY(cudaMemcpyAsync(&n_undef, d_undef, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    GF_CUDA_TRY(cudaStreamSynchronize(st));
+    if (n_undef) return fail(GF_E_REF_PANIC, "a shifted break point lies outside its read (gf_break_out.status)");
+    return GF_OK;
+}
+
 int gf_fast_merge(gf_index* idx, const gf_batch* in, gf_merge_info* out) {
     if (!idx || !out) return fail(GF_E_INVALID, "NULL argument");
     int rc = validate_batch(in);

@@ -1171,6 +1171,58 @@ __global__ void __launch_bounds__(VF_WARPS * 32) k_verify(VerifyParams P) {
     }
 }
 
+/* ------------------------------------------------------------------------------------------------ */
+/* k_adjust_break: FusionResult::adjust_fusion_break / calc_ed (fusion_result.rs:299-397), warp per match */
+struct AdjustParams {
+    const uint8_t* bytes;
+    const gf_break_ref* refs;
+    const gf_break_job* jobs;
+    unsigned long long n_jobs;
+    gf_break_out* out;
+    unsigned int* n_undefined;
+};
+__device__ __forceinline__ int ed_equal_len(const uint8_t* a, const uint8_t* b, int m) { /* both of length m */
+    return m > 0 ? warp_edit_distance(a, m, false, b) : 0;
+}
+__global__ void __launch_bounds__(VF_WARPS * 32) k_adjust_break(AdjustParams P) {
+    const uint32_t lane = gf_lane();
+    const uint64_t n_warps = (uint64_t)gridDim.x * VF_WARPS;
+    for (uint64_t j = (uint64_t)blockIdx.x * VF_WARPS + (threadIdx.x >> 5); j < P.n_jobs; j += n_warps) {
+        const gf_break_job job = P.jobs[j];
+        const gf_break_ref ref = P.refs[job.result];
+        const uint8_t* seq = P.bytes + job.seq_off;
+        const uint8_t* lref = P.bytes + ref.left_off;
+        const uint8_t* rref = P.bytes + ref.right_off;
+        const int len = (int)job.seq_len, nl = (int)ref.left_len, nr = (int)ref.right_len;
+        int smallest = 0xFFFF, shift = 0, best_l = 0, best_r = 0;
+        bool undefined = false;
+        for (int s = -3; s <= 3; s++) {
+            const int left_len = job.read_break + s + 1, right_len = len - left_len;
+            if (left_len < 0 || right_len < 0) { undefined = true; break; }
+            const uint8_t* right_seq = seq + left_len;
+            /* the 20 bases on either side of the break decide (:340-372) */
+            const int lc = min(min(left_len, nl), 20), rc = min(min(right_len, nr), 20);
+            const int total = ed_equal_len(seq + left_len - lc, lref + nl - lc, lc) + ed_equal_len(right_seq, rref, rc);
+            if (total < smallest) { /* strict: the first (most negative) best shift wins (:307-313) */
+                const int lc2 = min(left_len, nl), rc2 = min(right_len, nr);
+                best_l = ed_equal_len(seq + left_len - lc2, lref + nl - lc2, lc2);
+                best_r = ed_equal_len(right_seq, rref, rc2);
+                smallest = total;
+                shift = s;
+            }
+        }
+        if (lane == 0) {
+            gf_break_out o;
+            o.shift = undefined ? 0 : shift;
+            o.left_distance = undefined ? 0 : best_l;
+            o.right_distance = undefined ? 0 : best_r;
+            o.status = undefined ? 1 : 0;
+            P.out[j] = o;
+            if (undefined) atomicAdd(P.n_undefined, 1u);
+        }
+    }
+}
+
 template <class K>
 cudaError_t set_smem(K kernel, size_t bytes) {
     if (bytes <= 48 * 1024) return cudaSuccess;
@@ -1408,5 +1460,25 @@ int gf_fast_merge_device(gf_index* idx, const GfDevBatch& b, gf_merge_info* d_ou
     unsigned grid = (unsigned)std::min<uint64_t>((b.n + warps - 1) / warps, (uint64_t)idx->sm_count * 4);
     k_merge_only<32><<<grid, threads, smem, st>>>(b, d_out, idx->ws_counters.as<GfMapCounters>());
     GF_CUDA_TRY(cudaGetLastError());
+    return GF_OK;
+}
+
+/* report stage: adjust_fusion_break for n_jobs matches, everything already on the device; *d_n_undefined counts jobs whose
+ * shifted break leaves the read */
+int gf_adjust_break_device(gf_index* idx, const uint8_t* d_bytes, const gf_break_ref* d_refs, const gf_break_job* d_jobs,
+                           uint64_t n_jobs, gf_break_out* d_out, unsigned int* d_n_undefined, cudaStream_t st) {
+    if (!n_jobs) return GF_OK;
+    AdjustParams ap;
+    ap.bytes = d_bytes;
+    ap.refs = d_refs;
+    ap.jobs = d_jobs;
+    ap.n_jobs = n_jobs;
+    ap.out = d_out;
+    ap.n_undefined = d_n_undefined;
+    const uint64_t want = (n_jobs + VF_WARPS - 1) / VF_WARPS;
+    const unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)idx->sm_count * resident_blocks(k_adjust_break, VF_WARPS * 32, 0));
+    k_adjust_break<<<grid, VF_WARPS * 32, 0, st>>>(ap);
+    GF_CUDA_TRY(cudaGetLastError());
+    idx->launches++;
     return GF_OK;
 }

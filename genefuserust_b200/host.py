@@ -12,8 +12,8 @@ import os
 
 import numpy as np
 
-from ._abi import (GF_E_CAPACITY, GF_E_REF_PANIC, GF_OK, gf_index_info, gf_lookup, gf_map_stats, gf_match,
-                   gf_merge_info, gf_gene_span, gf_params, load_library)
+from ._abi import (GF_E_CAPACITY, GF_E_REF_PANIC, GF_OK, gf_break_job, gf_break_out, gf_break_ref, gf_index_info, gf_lookup,
+                   gf_map_stats, gf_match, gf_merge_info, gf_gene_span, gf_params, load_library)
 from .batch import ReadBatch
 
 
@@ -295,6 +295,36 @@ class FusionMapper:
         out = gf_map_stats()
         _check(self.lib, self.lib.gf_get_map_stats(self.m_indexer.h, C.byref(out)), allow=(GF_E_REF_PANIC,))
         return out
+
+    def adjust_fusion_break(self, results):
+        """FusionResult::adjust_fusion_break (fusion_result.rs:299-397) for clustered matches.
+        `results` = [(m_left_ref, m_right_ref, [(m_read.m_seq, m_read_break), ...]), ...] (bytes; the two reference strings
+        are what make_reference builds, :242-297).  Returns, per result, [(shift, m_left_distance, m_right_distance), ...];
+        the caller adds `shift` to m_read_break and to both gene positions (:317-319)."""
+        arena = bytearray()
+        refs = (gf_break_ref * max(1, len(results)))()
+        jobs_l = []
+        for r, (lref, rref, matches) in enumerate(results):
+            refs[r].left_off, refs[r].left_len = len(arena), len(lref)
+            arena += lref
+            refs[r].right_off, refs[r].right_len = len(arena), len(rref)
+            arena += rref
+            for seq, rb in matches:
+                jobs_l.append((len(arena), len(seq), rb, r))
+                arena += seq
+        jobs = (gf_break_job * max(1, len(jobs_l)))()
+        for j, (off, ln, rb, r) in enumerate(jobs_l):
+            jobs[j].seq_off, jobs[j].seq_len, jobs[j].read_break, jobs[j].result = off, ln, rb, r
+        out = (gf_break_out * max(1, len(jobs_l)))()
+        rc = self.lib.gf_adjust_fusion_break(self.m_indexer.h, bytes(arena), len(arena), refs, len(results), jobs, len(jobs_l), out)
+        _check(self.lib, rc, allow=(GF_E_REF_PANIC,))
+        self.last_rc = rc
+        res, j = [], 0
+        for _l, _r, matches in results:
+            res.append([(out[j + k].shift, out[j + k].left_distance, out[j + k].right_distance, out[j + k].status)
+                        for k in range(len(matches))])
+            j += len(matches)
+        return res
 
     # -- fusion_mapper.rs:253-275 / 379-392
     def add_match(self, m):

@@ -229,6 +229,36 @@ int gf_get_map_stats(const gf_index* idx, gf_map_stats* out);
 /* Parity hook: run only the device fast_merge on a HOST batch. */
 int gf_fast_merge(gf_index* idx, const gf_batch* in, gf_merge_info* out);
 
+/* ---- report stage, per clustered match: FusionResult::adjust_fusion_break (src/core/fusion_result.rs:299-397) ----
+ * SURVEY 8(f) #4.  After clustering, the reference slides every match's break point by -3..+3 and keeps the shift with
+ * the smallest edit distance of the 20 bases on either side against FusionResult::m_left_ref / m_right_ref
+ * (make_reference, :242-297 — built by the host exactly as today, get_ref_seq :770-798), 7 x 4 Levenshtein distances
+ * per match; the winning shift's full-length left / right distances overwrite m_left_distance / m_right_distance.
+ * `bytes` is one arena holding every read sequence and every reference string; jobs and refs index into it. */
+typedef struct gf_break_ref {   /* one FusionResult */
+    uint64_t left_off;          /* m_left_ref  = bytes[left_off  .. left_off  + left_len)  (may be empty) */
+    uint64_t right_off;         /* m_right_ref = bytes[right_off .. right_off + right_len) */
+    uint32_t left_len;
+    uint32_t right_len;
+} gf_break_ref;
+typedef struct gf_break_job {   /* one ReadMatch of that FusionResult */
+    uint64_t seq_off;           /* m_read.m_seq = bytes[seq_off .. seq_off + seq_len) */
+    uint32_t seq_len;
+    int32_t read_break;         /* m_read_break before the adjustment */
+    uint32_t result;            /* index into refs */
+    uint32_t reserved;
+} gf_break_job;
+typedef struct gf_break_out {
+    int32_t shift;              /* add to m_read_break, m_left_gp.position and m_right_gp.position (:317-319) */
+    int32_t left_distance;      /* new m_left_distance */
+    int32_t right_distance;     /* new m_right_distance */
+    int32_t status;             /* 0 ok; 1 = a shifted break lies outside the read (the reference's usize casts wrap there;
+                                   not reachable from make_match's breaks) — shift / distances are 0 and the call returns
+                                   GF_E_REF_PANIC */
+} gf_break_out;
+int gf_adjust_fusion_break(gf_index* idx, const uint8_t* bytes, uint64_t n_bytes, const gf_break_ref* refs, uint32_t n_refs,
+                           const gf_break_job* jobs, uint64_t n_jobs, gf_break_out* out);
+
 /* ---- several GPUs of one box from ONE process (what the Rust binary needs; bench.py uses one process per GPU) ----
  * The index is replicated on every listed device (built there, ~12 ms each, in parallel); every batch is cut into
  * n_devices contiguous shards of pairs, each mapped by its own host thread on its own device (no device-to-device

@@ -561,6 +561,49 @@ static int fast_merge(const uint8_t* s1, const uint8_t* q1, int32_t len1, const 
 }
 
 /* ------------------------------------------------------------------ C API */
+/* ---- report stage, per clustered match: src/core/fusion_result.rs ---- */
+/* :770-798 get_ref_seq */
+static std::string fr_get_ref_seq(const std::string& ref_s, int32_t start, int32_t end) {
+    if ((start >= 0 && end <= 0) || (start <= 0 && end >= 0)) return "";
+    if (std::abs(start) >= (int32_t)ref_s.size() || std::abs(end) >= (int32_t)ref_s.size()) return "";
+    size_t len = (size_t)(std::abs(end - start) + 1);
+    if (start < 0) return reverse_complement(ref_s.substr((size_t)(-end), len));
+    return ref_s.substr((size_t)start, len);
+}
+/* :324-397 FusionResult::calc_ed.  `undefined` is set where the Rust code's `as usize` casts would wrap
+ * (left_len < 0 or > seq length: not reachable from make_match's read_break +-3, segments are > 20 long). */
+static int32_t fr_calc_ed(const std::string& seq, int32_t m_read_break, int32_t shift, const std::string& m_left_ref,
+                          const std::string& m_right_ref, int32_t* left_ed, int32_t* right_ed, bool* undefined) {
+    int32_t read_break = m_read_break + shift;
+    int32_t left_len = read_break + 1;
+    int32_t right_len = (int32_t)seq.size() - left_len;
+    if (left_len < 0 || right_len < 0) { *undefined = true; return 0; }
+    std::string left_seq = seq.substr(0, (size_t)left_len);
+    std::string right_seq = seq.substr((size_t)left_len, (size_t)right_len);
+    /* use the sequence near the break point to adjust */
+    int32_t left_comp = (int32_t)std::min(std::min(left_seq.size(), m_left_ref.size()), (size_t)20);
+    int32_t right_comp = (int32_t)std::min(std::min(right_seq.size(), m_right_ref.size()), (size_t)20);
+    bool wp = false;
+    std::string a = left_seq.substr(left_seq.size() - (size_t)left_comp, (size_t)left_comp);
+    std::string b = m_left_ref.substr(m_left_ref.size() - (size_t)left_comp, (size_t)left_comp);
+    int32_t left_part_ed = (int32_t)edit_distance((const uint8_t*)a.data(), a.size(), (const uint8_t*)b.data(), b.size(), &wp);
+    a = right_seq.substr(0, (size_t)right_comp);
+    b = m_right_ref.substr(0, (size_t)right_comp);
+    int32_t right_part_ed = (int32_t)edit_distance((const uint8_t*)a.data(), a.size(), (const uint8_t*)b.data(), b.size(), &wp);
+    int32_t total_ed = left_part_ed + right_part_ed;
+    /* recalculate the left and right edit distance */
+    left_comp = std::min(left_len, (int32_t)m_left_ref.size());
+    right_comp = std::min(right_len, (int32_t)m_right_ref.size());
+    a = left_seq.substr(left_seq.size() - (size_t)left_comp, (size_t)left_comp);
+    b = m_left_ref.substr(m_left_ref.size() - (size_t)left_comp, (size_t)left_comp);
+    *left_ed = (int32_t)edit_distance((const uint8_t*)a.data(), a.size(), (const uint8_t*)b.data(), b.size(), &wp);
+    a = right_seq.substr(0, (size_t)right_comp);
+    b = m_right_ref.substr(0, (size_t)right_comp);
+    *right_ed = (int32_t)edit_distance((const uint8_t*)a.data(), a.size(), (const uint8_t*)b.data(), b.size(), &wp);
+    if (wp) *undefined = true;
+    return total_ed;
+}
+
 extern "C" {
 
 orc_index* orc_index_create(const gf_gene_span* genes, uint32_t n_genes, const gf_params* p) {
@@ -810,6 +853,35 @@ uint64_t orc_scan_pairs(const orc_index* idx, const gf_batch* in, gf_match* out,
 
 void orc_last_scan_counters(uint64_t out[6]) {
     for (int k = 0; k < 6; k++) out[k] = g_counters[k];
+}
+
+
+int32_t orc_get_ref_seq(const uint8_t* ref, int32_t ref_len, int32_t start, int32_t end, uint8_t* out) {
+    std::string r = fr_get_ref_seq(std::string((const char*)ref, (size_t)ref_len), start, end);
+    memcpy(out, r.data(), r.size());
+    return (int32_t)r.size();
+}
+
+/* FusionResult::adjust_fusion_break for one match (src/core/fusion_result.rs:299-321): out = {shift, left, right} */
+int orc_adjust_fusion_break(const uint8_t* seq, int32_t len, int32_t read_break, const uint8_t* left_ref, int32_t left_len,
+                            const uint8_t* right_ref, int32_t right_len, int32_t out[3]) {
+    std::string sq((const char*)seq, (size_t)len), lr((const char*)left_ref, (size_t)left_len),
+        rr((const char*)right_ref, (size_t)right_len);
+    int32_t smallest_ed = 0xFFFF, shift = 0, l = 0, r = 0;
+    bool undefined = false;
+    for (int32_t s = -3; s <= 3; s++) {
+        int32_t left_ed = 0, right_ed = 0;
+        int32_t ed = fr_calc_ed(sq, read_break, s, lr, rr, &left_ed, &right_ed, &undefined);
+        if (undefined) return 1;
+        if (ed < smallest_ed) {
+            smallest_ed = ed;
+            shift = s;
+            l = left_ed;
+            r = right_ed;
+        }
+    }
+    out[0] = shift; out[1] = l; out[2] = r;
+    return 0;
 }
 
 } /* extern "C" */

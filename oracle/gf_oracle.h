@@ -69,6 +69,13 @@ uint64_t orc_scan_pairs(const orc_index*, const gf_batch* in, gf_match* out, uin
  * [5] edit distances that would have panicked in the reference */
 void orc_last_scan_counters(uint64_t out[6]);
 
+/* report stage: get_ref_seq (src/core/fusion_result.rs:770-798) and FusionResult::adjust_fusion_break
+ * for one match (:299-397): out = {shift, m_left_distance, m_right_distance}; returns 1 where the reference's usize casts
+ * would wrap (break outside the read), 0 otherwise */
+int32_t orc_get_ref_seq(const uint8_t* ref, int32_t ref_len, int32_t start, int32_t end, uint8_t* out);
+int orc_adjust_fusion_break(const uint8_t* seq, int32_t len, int32_t read_break, const uint8_t* left_ref, int32_t left_len,
+                            const uint8_t* right_ref, int32_t right_len, int32_t out[3]);
+
 #ifdef __cplusplus
 }
 #endif

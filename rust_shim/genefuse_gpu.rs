@@ -50,7 +50,18 @@ extern "C" {
     fn gf_index_destroy(idx: *mut gf_index);
     fn gf_map_pairs(idx: *mut gf_index, batch: *const gf_batch, out: *mut gf_match, out_cap: u64,
                     n_out: *mut u64) -> c_int;
+    fn gf_adjust_fusion_break(idx: *mut gf_index, bytes: *const u8, n_bytes: u64, refs: *const gf_break_ref, n_refs: u32,
+                              jobs: *const gf_break_job, n_jobs: u64, out: *mut gf_break_out) -> c_int;
 }
+
+/// include/genefuse_gpu.h: one FusionResult's m_left_ref / m_right_ref inside the byte arena
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct gf_break_ref { pub left_off: u64, pub right_off: u64, pub left_len: u32, pub right_len: u32 }
+/// one ReadMatch of that FusionResult: m_read.m_seq inside the arena + m_read_break
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct gf_break_job { pub seq_off: u64, pub seq_len: u32, pub read_break: i32, pub result: u32, pub reserved: u32 }
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct gf_break_out { pub shift: i32, pub left_distance: i32, pub right_distance: i32, pub status: i32 }
 
 pub const GF_E_CAPACITY: c_int = -3;
 
@@ -87,6 +98,21 @@ impl GpuIndex {
             out.truncate(n as usize);
             return Ok(out);
         }
+    }
+}
+
+impl GpuIndex {
+    /// FusionResult::adjust_fusion_break (src/core/fusion_result.rs:299-321) for every match of every result of one
+    /// mapper: call it from cluster_matches right after fr.make_reference(..) (src/core/fusion_mapper.rs:438-456)
+    /// instead of fr.adjust_fusion_break(); then for each match: m_read_break += shift, both positions += shift,
+    /// m_left_distance / m_right_distance = the returned distances.
+    pub fn adjust_fusion_break(&self, arena: &[u8], refs: &[gf_break_ref], jobs: &[gf_break_job])
+        -> Result<Vec<gf_break_out>, String> {
+        let mut out = vec![gf_break_out::default(); jobs.len()];
+        let rc = unsafe { gf_adjust_fusion_break(self.h, arena.as_ptr(), arena.len() as u64, refs.as_ptr(), refs.len() as u32,
+                                                 jobs.as_ptr(), jobs.len() as u64, out.as_mut_ptr()) };
+        if rc != 0 { return Err(last_error()); }
+        Ok(out)
     }
 }
 

@@ -64,6 +64,11 @@ def lib():
     L.orc_scan_pairs.argtypes = [C.c_void_p, P(gf_batch), P(gf_match), C.c_uint64, C.c_int]
     L.orc_scan_pairs.restype = C.c_uint64
     L.orc_last_scan_counters.argtypes = [P(C.c_uint64)]
+    L.orc_get_ref_seq.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_char_p]
+    L.orc_get_ref_seq.restype = C.c_int32
+    L.orc_adjust_fusion_break.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32,
+                                          P(C.c_int32)]
+    L.orc_adjust_fusion_break.restype = C.c_int
     _lib = L
     return L
 
@@ -172,3 +177,17 @@ def segment_mask(mask, gp1, gp2):
     out = (orc_seqmatch * 2)()
     n = lib().orc_segment_mask(bytes(mask), len(mask), gp1, gp2, out)
     return [out[i].astuple() for i in range(n)]
+
+
+def get_ref_seq(ref, start, end):
+    """get_ref_seq (fusion_result.rs:770-798)"""
+    out = C.create_string_buffer(len(ref) + 1)
+    n = lib().orc_get_ref_seq(ref, len(ref), start, end, out)
+    return out.raw[:n]
+
+
+def adjust_fusion_break(seq, read_break, left_ref, right_ref):
+    """FusionResult::adjust_fusion_break for one match -> (shift, left_distance, right_distance, status)"""
+    out = (C.c_int32 * 3)()
+    st = lib().orc_adjust_fusion_break(seq, len(seq), read_break, left_ref, len(left_ref), right_ref, len(right_ref), out)
+    return (0, 0, 0, 1) if st else (out[0], out[1], out[2], 0)

@@ -520,3 +520,46 @@ def test_multi_device_handle(host, small_panel):
     assert len(want) > 100 and got == want
     mm.close()
     o.close()
+
+
+def test_adjust_fusion_break_parity(mappers, small_panel):
+    """FusionResult::adjust_fusion_break on the device vs the oracle — real matches of a noisy fusion
+    batch grouped per gene pair like cluster_matches does, references built with get_ref_seq like make_reference
+    (fusion_result.rs:242-297), plus breaks pushed to the edges of the reads and empty references."""
+    m, o = mappers
+    b = synth.generate_pairs(small_panel, 30000, read_len=150, seed=78, p_target=0.3, p_fusion=0.6, sub_rate=0.01, n_rate=0.002)
+    recs = o.scan(b, threads=8)
+    assert len(recs) > 2000
+    genes = [g for g, _ in small_panel.genes()]
+    groups = {}
+    for r in recs:
+        pair, source, used_rc, _rev, rb, lc, lp, rc_, rp, *_ = r
+        s1, q1 = b.read(pair, 1)
+        s2, q2 = b.read(pair, 2)
+        seq = orc.fast_merge(s1, q1, s2, q2)[0] if source == 0 else (s1 if source == 1 else s2)
+        if used_rc:
+            seq = orc.reverse_complement(seq)
+        groups.setdefault((lc, rc_), []).append((seq, rb, lp, rp))
+    results, rng = [], random.Random(4)
+    for (lc, rc_), ms in sorted(groups.items()):
+        # calc_fusion_point's "first match" flavour + make_reference
+        lp, rp = ms[0][2], ms[0][3]
+        longest_left = max(rb + 1 for _s, rb, _l, _r in ms)
+        longest_right = max(len(sq) - (rb + 1) for sq, rb, _l, _r in ms)
+        lref = orc.get_ref_seq(genes[lc], lp - longest_left + 1, lp)
+        rref = orc.get_ref_seq(genes[rc_], rp, rp + longest_right - 1)
+        jobs = [(sq, rb) for sq, rb, _l, _r in ms]
+        jobs += [(sq, rng.choice((0, 2, 3, len(sq) - 4, len(sq) - 2, len(sq) + 5))) for sq, _rb, _l, _r in ms[:2]]   # edges
+        results.append((lref, rref, jobs))
+    results.append((b"", b"", [(results[0][2][0][0], 60)]))
+    got = m.adjust_fusion_break(results)
+    n_jobs = n_shift = n_undef = 0
+    for (lref, rref, jobs), g in zip(results, got):
+        for (sq, rb), gg in zip(jobs, g):
+            want = orc.adjust_fusion_break(sq, rb, lref, rref)
+            assert gg == want, (rb, len(sq), len(lref), len(rref), gg, want)
+            n_jobs += 1
+            n_shift += want[0] != 0
+            n_undef += want[3]
+    assert n_jobs > 2000 and n_shift > 20 and n_undef > 5
+    assert m.last_rc == -5      # GF_E_REF_PANIC: some breaks were pushed outside their reads on purpose

@@ -107,3 +107,29 @@ def test_make_kmer_code():
     assert L.orc_make_kmer(b"AAAAAAAANAAAAAAA", 0) == -1
     assert L.orc_make_kmer(b"AAAAAAAAaAAAAAAA", 0) == -1
     assert L.orc_make_kmer(b"NACGTACGTACGTACGT", 1) == L.orc_make_kmer(b"ACGTACGTACGTACGT", 0)
+
+
+def test_adjust_fusion_break_hand_cases():
+    """FusionResult::adjust_fusion_break (fusion_result.rs:299-397) on cases small enough to verify by hand"""
+    left_gene = b"ACGTTGCAAGGCTTAACCGGATCGATCGTTAGC"      # 33 bases
+    right_gene = b"TTGACCATGGCAATCGGATTACAGGCTTACGAT"     # 33 bases
+    # a read that is exactly left_gene[3:33] + right_gene[0:28]: break at 29, no shift needed, both distances 0
+    read = left_gene[3:] + right_gene[:28]
+    assert orc.adjust_fusion_break(read, 29, left_gene[3:], right_gene[:28]) == (0, 0, 0, 0)
+    # the caller's break is 2 too far left: the best shift is +2 and the distances return to 0
+    assert orc.adjust_fusion_break(read, 27, left_gene[3:], right_gene[:28]) == (2, 0, 0, 0)
+    # ... 3 too far right: shift -3
+    assert orc.adjust_fusion_break(read, 32, left_gene[3:], right_gene[:28]) == (-3, 0, 0, 0)
+    # one substitution on the right side, 5 bases after the break: shift 0, right distance 1
+    mut = bytearray(read)
+    mut[35] = ord("A") if mut[35] != ord("A") else ord("C")
+    assert orc.adjust_fusion_break(bytes(mut), 29, left_gene[3:], right_gene[:28]) == (0, 0, 1, 0)
+    # empty references (get_ref_seq returned ""): every shift scores 0, the first one (-3) wins (strict '<' from 0xFFFF)
+    assert orc.adjust_fusion_break(read, 29, b"", b"") == (-3, 0, 0, 0)
+    # a shifted break outside the read is outside the reference's defined behaviour
+    assert orc.adjust_fusion_break(read, 1, left_gene[3:], right_gene[:28])[3] == 1
+    # get_ref_seq: forward slice, reverse strand = reverse complement of [-end, -start], straddling / overflow -> ""
+    assert orc.get_ref_seq(left_gene, 3, 7) == left_gene[3:8]
+    assert orc.get_ref_seq(left_gene, -7, -3) == orc.reverse_complement(left_gene[3:8])
+    assert orc.get_ref_seq(left_gene, -2, 3) == b"" and orc.get_ref_seq(left_gene, 0, 5) == b""
+    assert orc.get_ref_seq(left_gene, 30, 33) == b""
