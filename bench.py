@@ -142,8 +142,18 @@ def run_cpu_oracle(panel, batch, threads, sample_pairs):
     return sample.n / dt, dt, len(res), t_index
 
 
+def _only_json_on_stdout():
+    """Libraries (NCCL's version banner, nvcc) write to the C-level stdout; the contract is ONE JSON line there.
+    Everything else goes to stderr; the JSON line is written to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def main():
     a = parse_args()
+    json_out = _only_json_on_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -182,7 +192,8 @@ def main():
                                        "CPU path (oracle/), packs of 1000 pairs over all host threads"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
         return
 
     # ------------------------------------------------------------------ our arm
@@ -390,7 +401,8 @@ def main():
         "setup": {"index_create_s": t_index, "first_index_create_s_incl_cuda_init": t_first, "generate_s": t_gen,
                   "host_threads": threads},
     }
-    print(json.dumps(line))
+    json_out.write(json.dumps(line) + "\n")
+    json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 
