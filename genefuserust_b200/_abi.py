@@ -133,6 +133,8 @@ class gf_map_stats(C.Structure):
         ("ms_seed", C.c_float),
         ("ms_diag", C.c_float),
         ("ms_scan", C.c_float),
+        ("ms_ingest", C.c_float),
+        ("reserved2", C.c_float),
     ]
 
 

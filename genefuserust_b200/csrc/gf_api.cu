@@ -415,6 +415,7 @@ int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8
     int rc = gf_fastq_parse_device(sg.seq1.as<uint8_t>(), bytes1, &idx->fq[0], st);
     if (rc == GF_OK && pe) rc = gf_fastq_parse_device(sg.seq2.as<uint8_t>(), bytes2, &idx->fq[1], st);
     if (rc != GF_OK) return rc;
+    GF_CUDA_TRY(cudaEventRecord(idx->ev_prep, st)); /* end of the ingest (the parse synchronises on its record count) */
     const uint64_t n = pe ? std::min(idx->fq[0].n_records, idx->fq[1].n_records) : idx->fq[0].n_records;
     *n_records = n;
     idx->stats.n_pairs = n;
@@ -454,6 +455,7 @@ int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8
     float ms = 0;
     GF_CUDA_TRY(cudaEventElapsedTime(&ms, idx->ev_start, idx->ev_end));
     idx->stats.ms_total = ms;
+    GF_CUDA_TRY(cudaEventElapsedTime(&idx->stats.ms_ingest, idx->ev_start, idx->ev_prep));
     idx->stats.kernel_launches = idx->launches - launches0 + 3;
     *n_out = h->n_out;
     if (h->n_out > out_cap) return fail(GF_E_CAPACITY, "out_cap too small; *n_out holds the required count");
@@ -465,7 +467,7 @@ int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8
     return GF_OK;
 }
 
-static_assert(sizeof(gf_map_stats) == 112 && sizeof(gf_match) == 48, "ABI layout (include/genefuse_gpu.h, _abi.py)");
+static_assert(sizeof(gf_map_stats) == 120 && sizeof(gf_match) == 48, "ABI layout (include/genefuse_gpu.h, _abi.py)");
 int gf_get_map_stats(const gf_index* cidx, gf_map_stats* out) {
     gf_index* idx = const_cast<gf_index*>(cidx);
     if (!idx || !out) return fail(GF_E_INVALID, "NULL argument");

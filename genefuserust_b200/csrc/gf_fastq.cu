@@ -101,10 +101,10 @@ int gf_fastq_parse_device(const uint8_t* d_text, uint64_t bytes, GfFastqTable* o
     out->max_len = 0;
     if (bytes == 0) return GF_OK;
     const uint64_t n_tiles = (bytes + NL_TILE - 1) / NL_TILE;
-    uint32_t *d_cnt = nullptr, *d_off = nullptr, *d_tmp = nullptr;
-    GF_CUDA_TRY(cudaMalloc(&d_cnt, sizeof(uint32_t) * (n_tiles + 2)));
-    GF_CUDA_TRY(cudaMalloc(&d_off, sizeof(uint32_t) * (n_tiles + 1)));
-    GF_CUDA_TRY(cudaMalloc(&d_tmp, sizeof(uint32_t) * gf_scan_tmp_elems(n_tiles)));
+    GF_CUDA_TRY(out->cnt.reserve(sizeof(uint32_t) * (n_tiles + 2)));
+    GF_CUDA_TRY(out->off.reserve(sizeof(uint32_t) * (n_tiles + 1)));
+    GF_CUDA_TRY(out->tmp.reserve(sizeof(uint32_t) * gf_scan_tmp_elems(n_tiles)));
+    uint32_t *d_cnt = out->cnt.as<uint32_t>(), *d_off = out->off.as<uint32_t>(), *d_tmp = out->tmp.as<uint32_t>();
     k_nl_count<<<(unsigned)n_tiles, NL_THREADS, 0, st>>>(d_text, bytes, d_cnt);
     GF_CUDA_TRY(gf_exclusive_scan_u32(d_cnt, d_off, n_tiles, d_tmp, st));
     uint32_t n_nl = 0;
@@ -141,15 +141,11 @@ int gf_fastq_parse_device(const uint8_t* d_text, uint64_t bytes, GfFastqTable* o
         GF_CUDA_TRY(cudaStreamSynchronize(st));
         out->max_len = h[0];
         if (h[1] & 1u) {
-            cudaFree(d_cnt); cudaFree(d_off); cudaFree(d_tmp);
             gf_set_error("FASTQ: a quality line and its sequence line differ in length (the reference indexes qualities by "
                          "sequence position and panics when they are shorter, src/core/read.rs:349)");
             return GF_E_INVALID;
         }
     }
     GF_CUDA_TRY(cudaGetLastError());
-    GF_CUDA_TRY(cudaFree(d_cnt));
-    GF_CUDA_TRY(cudaFree(d_off));
-    GF_CUDA_TRY(cudaFree(d_tmp));
     return GF_OK;
 }

@@ -73,7 +73,8 @@ struct GfFastqTable {
     uint64_t n_records = 0;
     uint32_t max_len = 0;
     GfBuf nl, s, e, qs; /* newline positions; sequence start / end; quality start (u64 each) */
-    void release() { nl.release(); s.release(); e.release(); qs.release(); }
+    GfBuf cnt, off, tmp; /* per-tile newline counts, their exclusive scan, scan workspace (kept between calls) */
+    void release() { nl.release(); s.release(); e.release(); qs.release(); cnt.release(); off.release(); tmp.release(); }
 };
 
 struct gf_index {

@@ -178,6 +178,8 @@ typedef struct gf_map_stats {
     float ms_seed;           /* k_seed: seed k-mers -> filter -> one table lookup, class lists */
     float ms_diag;           /* k_diag: seeded sequences against the gene planes */
     float ms_scan;           /* k_scan: unseeded sequences, filter probes */
+    float ms_ingest;         /* gf_map_fastq only: H2D of the text + newline scan + record tables (before the mapping) */
+    float reserved2;
 } gf_map_stats;
 
 const char* gf_last_error(void);

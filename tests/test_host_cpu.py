@@ -40,7 +40,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_abi.gf_match) == 48
     assert C.sizeof(_abi.gf_batch) == 80
     assert C.sizeof(_abi.gf_params) == 20
-    assert C.sizeof(_abi.gf_map_stats) == 112
+    assert C.sizeof(_abi.gf_map_stats) == 120
 
 
 def test_no_device_fails_loudly(built):

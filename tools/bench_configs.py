@@ -4,6 +4,7 @@ multi-CSV list mode (config 4), device-timed on one B200, each checked against t
 
   python tools/bench_configs.py --sweep 75:50000000 250:50000000     # read_len:pairs
   python tools/bench_configs.py --list 16 --pairs 10000000
+  python tools/bench_configs.py --fastq 4000000                      # raw FASTQ text, record splitting on the device
 Prints one JSON line per config."""
 import argparse
 import ctypes as C
@@ -31,6 +32,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sweep", nargs="*", default=[])
     ap.add_argument("--list", type=int, default=0)
+    ap.add_argument("--fastq", type=int, default=0, help="pairs of raw FASTQ text through gf_map_fastq (device-side ingest)")
     ap.add_argument("--pairs", type=int, default=10_000_000)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--oracle-sample", type=int, default=300_000)
@@ -105,6 +107,68 @@ def main():
         o.close()
         del d, d_off, batch
         torch.cuda.empty_cache()
+
+    if a.fastq:
+        # raw FASTQ text (pinned host memory) -> gf_map_fastq: H2D of the text, newline scan and record
+        # tables on the device, mapping straight from the text.  Fixed-width records built with numpy.
+        import numpy as np
+        P, L = a.fastq, 150
+        batch = synth.generate_pairs(panel, P, read_len=L, seed=12, threads=threads)
+
+        def fastq_text(seq, qual, mate):
+            name = np.frombuffer(b"@SYN:12:000000000 %d:N:0:ACGT\n" % mate, dtype=np.uint8)
+            rec = len(name) + L + 1 + 2 + L + 1
+            t = torch.empty(P * rec, dtype=torch.uint8, pin_memory=True)
+            out = t.numpy().reshape(P, rec)
+            out[:, :len(name)] = name
+            idx = np.arange(P, dtype=np.int64)
+            for k in range(9):                                   # zero-padded decimal pair index
+                out[:, 8 + 8 - k] = 48 + (idx // 10 ** k) % 10
+            o = len(name)
+            out[:, o:o + L] = seq.reshape(P, L)
+            out[:, o + L] = 10
+            out[:, o + L + 1] = 43
+            out[:, o + L + 2] = 10
+            out[:, o + L + 3:o + 2 * L + 3] = qual.reshape(P, L)
+            out[:, o + 2 * L + 3] = 10
+            return t
+        t1 = fastq_text(batch.seq1, batch.qual1, 1)
+        t2 = fastq_text(batch.seq2, batch.qual2, 2)
+        m = FusionMapper.from_gene_spans(genes)
+        lib = m.lib
+        cap = max(1 << 16, P // 4)
+        out = (gf_match * cap)()
+        n, nrec = C.c_uint64(0), C.c_uint64(0)
+
+        def call():
+            rc = lib.gf_map_fastq(m.m_indexer.h, C.cast(t1.data_ptr(), C.c_char_p), t1.numel(), C.cast(t2.data_ptr(), C.c_char_p),
+                                  t2.numel(), out, cap, C.byref(n), C.byref(nrec))
+            assert rc == 0, lib.gf_last_error()
+        call()
+        walls = []
+        s = gf_map_stats()
+        for _ in range(a.steps):
+            t0 = time.perf_counter()
+            call()
+            walls.append(time.perf_counter() - t0)
+            lib.gf_get_map_stats(m.m_indexer.h, C.byref(s))
+            print(f"  call {len(walls)}: wall {walls[-1] * 1e3:.1f} ms, device total {s.ms_total:.1f} ms, ingest {s.ms_ingest:.1f} ms",
+                  file=sys.stderr)
+        dt = min(walls)
+        got = [out[i].astuple() for i in range(n.value)]
+        sample = batch.slice(0, min(a.oracle_sample, P))
+        o = _oracle.OracleIndex(genes)
+        want = o.scan(sample, threads=threads)
+        ok = [g for g in got if g[0] < sample.n] == want
+        text_bytes = t1.numel() + t2.numel()
+        print(json.dumps({"config": f"FASTQ ingest on the device: {P} pairs 2x150 as raw text ({text_bytes} bytes, pinned host), 1 B200",
+                          "records": int(nrec.value), "pairs_per_s_e2e": P / dt, "ms_per_call": dt * 1e3, "device_ms_total": s.ms_total,
+                          "ingest_ms (H2D + newline scan + record tables)": s.ms_ingest,
+                          "h2d_GBps_if_ingest_were_copy_only": text_bytes / (s.ms_ingest / 1e3) / 1e9,
+                          "matches": int(n.value), "parity_ok_on_sample": ok}), flush=True)
+        assert ok and nrec.value == P
+        m.close()
+        o.close()
 
     if a.list:
         # list mode: K fusion CSVs = K independent indices over the same reads (fusion_scan.rs:62-188); alternate the
