@@ -46,6 +46,20 @@ for h in want:
     if h not in hdr: continue
     i = hdr.index(h)
     md.append(f"| {h} [{units[i]}] | " + " | ".join(r[i] for r in krows) + " |")
+# derived: achieved DRAM bandwidth of each launch against the measured copy peak (MEASURED_PEAKS.json)
+try:
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    peak = 6538.3
+gbs = []
+for r in krows:
+    rd, _, s1 = val(r, "dram__bytes_read.sum"); wr, _, s2 = val(r, "dram__bytes_write.sum"); t, _, st = val(r, "gpu__time_duration.sum")
+    gbs.append((rd * s1 + wr * s2) / (t * st / 1e3) / 1e9)
+md.append("| **derived: DRAM read+write [GB/s]** | " + " | ".join(f"{g:.0f}" for g in gbs) + " |")
+md.append(f"| **derived: fraction of the measured HBM peak ({peak:.1f} GB/s)** | " + " | ".join(f"{g / peak:.2f}" for g in gbs) + " |")
+reading = os.path.join(ROOT, "profiles", f"{tag}_reading.md")
+if os.path.exists(reading):
+    md += ["", open(reading).read().rstrip()]
 kern = {}
 for r, n in zip(krows, names):
     base = [b for b in ("k_prep", "k_seed", "k_diag", "k_scan", "k_exact", "k_verify") if b in r[hdr.index("Kernel Name")]]
