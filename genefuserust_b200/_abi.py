@@ -156,7 +156,7 @@ EXPORTS = (
     "gf_last_error", "gf_abi_version", "gf_device_count", "gf_default_params", "gf_index_create",
     "gf_index_destroy", "gf_index_get_info", "gf_index_lookup", "gf_map_pairs", "gf_map_pairs_device",
     "gf_sort_matches", "gf_get_map_stats", "gf_fast_merge", "gf_map_fastq", "gf_multi_create", "gf_multi_destroy",
-    "gf_multi_map_pairs", "gf_adjust_fusion_break",
+    "gf_multi_map_pairs", "gf_adjust_fusion_break", "gf_list_map_pairs", "gf_map_pairs_device_list",
 )
 
 _lib = None
@@ -206,6 +206,11 @@ def load_library():
     lib.gf_multi_map_pairs.restype = C.c_int
     lib.gf_fast_merge.argtypes = [C.c_void_p, P(gf_batch), P(gf_merge_info)]
     lib.gf_fast_merge.restype = C.c_int
+    lib.gf_list_map_pairs.argtypes = [P(C.c_void_p), C.c_uint32, P(gf_batch), P(P(gf_match)), P(C.c_uint64), P(C.c_uint64)]
+    lib.gf_list_map_pairs.restype = C.c_int
+    lib.gf_map_pairs_device_list.argtypes = [P(C.c_void_p), C.c_uint32, P(gf_batch), P(C.c_void_p), C.c_uint64, P(C.c_void_p),
+                                             C.c_void_p]
+    lib.gf_map_pairs_device_list.restype = C.c_int
     lib.gf_adjust_fusion_break.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, P(gf_break_ref), C.c_uint32, P(gf_break_job),
                                            C.c_uint64, P(gf_break_out)]
     lib.gf_adjust_fusion_break.restype = C.c_int

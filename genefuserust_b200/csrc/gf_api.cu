@@ -201,18 +201,20 @@ static int validate_batch(const gf_batch* in) {
     return GF_OK;
 }
 
-/* Host batch: chunked double-buffered pipeline (H2D of chunk k+1 overlaps the kernels of chunk k). */
-int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_cap, uint64_t* n_out) {
-    if (!idx || !n_out) return fail(GF_E_INVALID, "NULL argument");
-    *n_out = 0;
-    int rc = validate_batch(in);
-    if (rc != GF_OK) return rc;
-    if (out_cap && !out) return fail(GF_E_INVALID, "out is NULL");
-    std::lock_guard<std::mutex> lk(idx->mu);
+/* Host batch: chunked double-buffered pipeline (H2D of chunk k+1 overlaps the kernels of chunk k).
+ * nh > 1 = list mode: the same reads against several indices.  hs[0] owns the staging buffers, the streams and the
+ * sequence store; every chunk is copied ONCE, converted / merged ONCE (k_prep) and then seeded, screened and verified
+ * against each index in turn, on hs[0]'s stream. */
+static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, gf_match* const* outs, const uint64_t* caps,
+                          uint64_t* n_outs) {
+    gf_index* idx = hs[0];
     GF_CUDA_TRY(cudaSetDevice(idx->device));
-    idx->stats = gf_map_stats{};
-    idx->stats.n_pairs = in->n;
-    idx->stats_pending = false;
+    for (uint32_t h = 0; h < nh; h++) {
+        hs[h]->stats = gf_map_stats{};
+        hs[h]->stats.n_pairs = in->n;
+        hs[h]->stats_pending = false;
+        n_outs[h] = 0;
+    }
     if (in->n == 0) return GF_OK;
     const bool pe = in->seq2 != nullptr;
     const uint64_t n = in->n;
@@ -220,14 +222,18 @@ int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_
     const uint64_t* off2 = in->off2;
     if (off1[n] < off1[0] || (pe && off2[n] < off2[0])) return fail(GF_E_INVALID, "offsets are not ascending");
     const uint64_t total_bytes = (off1[n] - off1[0]) + (pe ? off2[n] - off2[0] : 0);
-    uint64_t n_chunks = std::max<uint64_t>(1, (2 * total_bytes + CHUNK_TARGET_BYTES - 1) / CHUNK_TARGET_BYTES);
+    /* list mode: a chunk costs nh rounds of launches, so chunks are larger (the upload is a smaller share of a chunk anyway) */
+    const uint64_t chunk_bytes = CHUNK_TARGET_BYTES * std::min<uint32_t>(nh, 4u);
+    uint64_t n_chunks = std::max<uint64_t>(1, (2 * total_bytes + chunk_bytes - 1) / chunk_bytes);
     n_chunks = std::min<uint64_t>(n_chunks, n);
     const uint64_t per = (n + n_chunks - 1) / n_chunks;
     n_chunks = (n + per - 1) / per;
 
-    const unsigned long long launches0 = idx->launches;
-    uint64_t total_out = 0, h2d = 0, d2h = 0;
-    bool panic = false;
+    std::vector<unsigned long long> launches0(nh);
+    for (uint32_t h = 0; h < nh; h++) launches0[h] = hs[h]->launches;
+    std::vector<uint64_t> total_out(nh, 0), d2h(nh, 0);
+    uint64_t h2d = 0;
+    std::vector<char> panic(nh, 0);
     GF_CUDA_TRY(cudaEventRecord(idx->ev_start, idx->stream));
 
     /* qualities: zero-copy when they live in pinned host memory and the on-demand kernel (thread per pair) runs */
@@ -247,7 +253,7 @@ int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_
         }
     }
     const bool zc = zq1 != nullptr;
-    idx->stats.zero_copy_qual = zc ? 1u : 0u;
+    for (uint32_t h = 0; h < nh; h++) hs[h]->stats.zero_copy_qual = zc ? 1u : 0u;
 
     auto issue = [&](uint64_t k) -> int {
         GfStage& s = idx->stage[k & 1];
@@ -294,40 +300,45 @@ int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_
         GF_CUDA_TRY(cudaEventRecord(s.copied, cs));
         s.n = cn;
         s.pair_base = lo;
-        s.out_cap = (pe ? 2 : 1) * cn;
-        GF_CUDA_TRY(s.out.reserve(sizeof(gf_match) * s.out_cap));
-        GF_CUDA_TRY(s.nout.reserve(sizeof(unsigned long long)));
         GF_CUDA_TRY(cudaStreamWaitEvent(idx->stream, s.copied, 0));
-        int r = gf_map_device_batch(idx, db, s.out.as<gf_match>(), s.out_cap, s.nout.as<unsigned long long>(),
-                                    idx->stream, false);
-        if (r != GF_OK) return r;
-        GfHostSlot* h = &idx->h_slots[k & 1];
-        GF_CUDA_TRY(cudaMemcpyAsync(&h->counters, idx->ws_counters.p, sizeof(GfMapCounters), cudaMemcpyDeviceToHost,
-                                    idx->stream));
-        GF_CUDA_TRY(cudaMemcpyAsync(&h->n_out, s.nout.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                                    idx->stream));
+        for (uint32_t h = 0; h < nh; h++) {
+            GfStage& sh = hs[h]->stage[k & 1];
+            sh.out_cap = (pe ? 2 : 1) * cn;
+            GF_CUDA_TRY(sh.out.reserve(sizeof(gf_match) * sh.out_cap));
+            GF_CUDA_TRY(sh.nout.reserve(sizeof(unsigned long long)));
+            int r = gf_map_device_batch(hs[h], db, sh.out.as<gf_match>(), sh.out_cap, sh.nout.as<unsigned long long>(),
+                                        idx->stream, false, h ? idx : nullptr);
+            if (r != GF_OK) return r;
+            GfHostSlot* hsl = &hs[h]->h_slots[k & 1];
+            GF_CUDA_TRY(cudaMemcpyAsync(&hsl->counters, hs[h]->ws_counters.p, sizeof(GfMapCounters), cudaMemcpyDeviceToHost,
+                                        idx->stream));
+            GF_CUDA_TRY(cudaMemcpyAsync(&hsl->n_out, sh.nout.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                        idx->stream));
+        }
         GF_CUDA_TRY(cudaEventRecord(s.done, idx->stream));
         return GF_OK;
     };
     auto collect = [&](uint64_t k) -> int {
-        GfStage& s = idx->stage[k & 1];
-        GfHostSlot* h = &idx->h_slots[k & 1];
-        GF_CUDA_TRY(cudaEventSynchronize(s.done));
-        int r = check_flags(*h);
-        if (r != GF_OK) return r;
-        accumulate(idx->stats, *h);
-        if (h->counters.n_ref_panic) panic = true;
-        const uint64_t cnt = h->n_out; /* <= s.out_cap by construction */
-        if (cnt && total_out + cnt <= out_cap) {
-            GF_CUDA_TRY(cudaMemcpy(out + total_out, s.out.p, sizeof(gf_match) * cnt, cudaMemcpyDeviceToHost));
-            d2h += sizeof(gf_match) * cnt;
+        GF_CUDA_TRY(cudaEventSynchronize(idx->stage[k & 1].done));
+        for (uint32_t h = 0; h < nh; h++) {
+            GfStage& sh = hs[h]->stage[k & 1];
+            GfHostSlot* hsl = &hs[h]->h_slots[k & 1];
+            int r = check_flags(*hsl);
+            if (r != GF_OK) return r;
+            accumulate(hs[h]->stats, *hsl);
+            if (hsl->counters.n_ref_panic) panic[h] = 1;
+            const uint64_t cnt = hsl->n_out; /* <= sh.out_cap by construction */
+            if (cnt && total_out[h] + cnt <= caps[h]) {
+                GF_CUDA_TRY(cudaMemcpy(outs[h] + total_out[h], sh.out.p, sizeof(gf_match) * cnt, cudaMemcpyDeviceToHost));
+                d2h[h] += sizeof(gf_match) * cnt;
+            }
+            d2h[h] += sizeof(GfMapCounters) + sizeof(unsigned long long);
+            total_out[h] += cnt;
         }
-        d2h += sizeof(GfMapCounters) + sizeof(unsigned long long);
-        total_out += cnt;
         return GF_OK;
     };
 
-    rc = issue(0);
+    int rc = issue(0);
     for (uint64_t k = 0; rc == GF_OK && k < n_chunks; k++) {
         if (k + 1 < n_chunks) rc = issue(k + 1);
         if (rc == GF_OK) rc = collect(k);
@@ -341,17 +352,108 @@ int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_
     GF_CUDA_TRY(cudaEventSynchronize(idx->ev_end));
     float ms = 0;
     GF_CUDA_TRY(cudaEventElapsedTime(&ms, idx->ev_start, idx->ev_end));
-    idx->stats.ms_total = ms;
-    idx->stats.kernel_launches = idx->launches - launches0;
-    idx->stats.h2d_bytes = h2d;
-    idx->stats.d2h_bytes = d2h;
-    *n_out = total_out;
-    if (total_out > out_cap) return fail(GF_E_CAPACITY, "out_cap too small; *n_out holds the required count");
-    gf_sort_matches(out, total_out);
-    if (panic)
-        return fail(GF_E_REF_PANIC,
-                    "a candidate needs an edit distance over more than 640 columns: the reference panics here "
-                    "(src/core/edit_distance.rs:94-100,177-196); records were still written with exact distances");
+    rc = GF_OK;
+    for (uint32_t h = 0; h < nh; h++) {
+        gf_map_stats& st = hs[h]->stats;
+        st.ms_total = ms; /* of the whole call (all indices) */
+        st.kernel_launches = hs[h]->launches - launches0[h];
+        st.h2d_bytes = h ? 0 : h2d;
+        st.d2h_bytes = d2h[h];
+        if (h) { /* k_prep ran once, on hs[0] */
+            st.n_sequences = hs[0]->stats.n_sequences;
+            st.n_probes_pass1 = hs[0]->stats.n_probes_pass1;
+            st.seq_bytes = hs[0]->stats.seq_bytes;
+        }
+        n_outs[h] = total_out[h];
+        if (total_out[h] > caps[h]) { rc = fail(GF_E_CAPACITY, "out_cap too small; *n_out holds the required count"); continue; }
+        gf_sort_matches(outs[h], total_out[h]);
+        if (panic[h] && rc == GF_OK)
+            rc = fail(GF_E_REF_PANIC,
+                      "a candidate needs an edit distance over more than 640 columns: the reference panics here "
+                      "(src/core/edit_distance.rs:94-100,177-196); records were still written with exact distances");
+    }
+    return rc;
+}
+
+int gf_map_pairs(gf_index* idx, const gf_batch* in, gf_match* out, uint64_t out_cap, uint64_t* n_out) {
+    if (!idx || !n_out) return fail(GF_E_INVALID, "NULL argument");
+    *n_out = 0;
+    int rc = validate_batch(in);
+    if (rc != GF_OK) return rc;
+    if (out_cap && !out) return fail(GF_E_INVALID, "out is NULL");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    return map_host_batch(&idx, 1, in, &out, &out_cap, n_out);
+}
+
+/* list mode: all handles are locked in address order (two list calls sharing handles cannot deadlock) */
+struct ListLock {
+    std::vector<gf_index*> order;
+    explicit ListLock(gf_index* const* hs, uint32_t nh) : order(hs, hs + nh) {
+        std::sort(order.begin(), order.end());
+        for (gf_index* h : order) h->mu.lock();
+    }
+    ~ListLock() { for (auto it = order.rbegin(); it != order.rend(); ++it) (*it)->mu.unlock(); }
+};
+static int validate_list(gf_index* const* hs, uint32_t nh) {
+    if (!hs || nh == 0) return fail(GF_E_INVALID, "empty index list");
+    for (uint32_t h = 0; h < nh; h++) {
+        if (!hs[h]) return fail(GF_E_INVALID, "NULL index in the list");
+        if (hs[h]->device != hs[0]->device) return fail(GF_E_INVALID, "all indices of a list must live on one device");
+        for (uint32_t g = 0; g < h; g++)
+            if (hs[g] == hs[h]) return fail(GF_E_INVALID, "the same index is listed twice");
+    }
+    return GF_OK;
+}
+
+int gf_list_map_pairs(gf_index* const* idx, uint32_t n_idx, const gf_batch* in, gf_match* const* out, const uint64_t* out_cap,
+                      uint64_t* n_out) {
+    if (!n_out || !out_cap || !out) return fail(GF_E_INVALID, "NULL argument");
+    int rc = validate_list(idx, n_idx);
+    if (rc != GF_OK) return rc;
+    rc = validate_batch(in);
+    if (rc != GF_OK) return rc;
+    for (uint32_t h = 0; h < n_idx; h++)
+        if (out_cap[h] && !out[h]) return fail(GF_E_INVALID, "out is NULL");
+    ListLock lk(idx, n_idx);
+    return map_host_batch(idx, n_idx, in, out, out_cap, n_out);
+}
+
+int gf_map_pairs_device_list(gf_index* const* idx, uint32_t n_idx, const gf_batch* in_dev, gf_match* const* d_out,
+                             uint64_t out_cap, uint64_t* const* d_n_out, void* cuda_stream) {
+    if (!d_out || !d_n_out) return fail(GF_E_INVALID, "NULL argument");
+    int rc = validate_list(idx, n_idx);
+    if (rc != GF_OK) return rc;
+    rc = validate_batch(in_dev);
+    if (rc != GF_OK) return rc;
+    ListLock lk(idx, n_idx);
+    GF_CUDA_TRY(cudaSetDevice(idx[0]->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    GfDevBatch db{};
+    db.n = in_dev->n;
+    db.seq1 = in_dev->seq1;
+    db.qual1 = in_dev->qual1;
+    db.s1 = in_dev->off1; db.e1 = db.s1 + 1; db.qs1 = db.s1;
+    db.seq2 = in_dev->seq2;
+    db.qual2 = in_dev->qual2;
+    db.s2 = in_dev->off2; db.e2 = db.s2 ? db.s2 + 1 : nullptr; db.qs2 = db.s2;
+    db.bytes1 = in_dev->bytes1;
+    db.bytes2 = in_dev->bytes2;
+    db.max_len = in_dev->max_len;
+    for (uint32_t h = 0; h < n_idx; h++) {
+        gf_index* x = idx[h];
+        if (!d_n_out[h]) return fail(GF_E_INVALID, "NULL argument");
+        const unsigned long long launches0 = x->launches;
+        rc = gf_map_device_batch(x, db, d_out[h], out_cap, (unsigned long long*)d_n_out[h], st, true, h ? idx[0] : nullptr);
+        if (rc != GF_OK) return rc;
+        GfHostSlot* hsl = &x->h_slots[2];
+        GF_CUDA_TRY(cudaMemcpyAsync(&hsl->counters, x->ws_counters.p, sizeof(GfMapCounters), cudaMemcpyDeviceToHost, st));
+        GF_CUDA_TRY(cudaMemcpyAsync(&hsl->n_out, d_n_out[h], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        GF_CUDA_TRY(cudaEventRecord(x->ev_end, st));
+        x->stats = gf_map_stats{};
+        x->stats.n_pairs = in_dev->n;
+        x->stats.kernel_launches = x->launches - launches0;
+        x->stats_pending = true;
+    }
     return GF_OK;
 }
 

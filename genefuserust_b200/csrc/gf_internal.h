@@ -135,8 +135,10 @@ struct GfDevBatch {
     uint64_t pair_base;      /* added to the local pair index in emitted records */
     uint32_t max_len;        /* upper bound of any read length (selects the kernel capacity) */
 };
+/* store_owner != nullptr (list mode): reuse the sequence store `store_owner` filled for the SAME batch just before on the same
+ * stream instead of running k_prep again (only taken on the split-screen path, reads <= 256 bases; ignored otherwise) */
 int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uint64_t out_cap,
-                        unsigned long long* d_n_out, cudaStream_t stream, bool record_events);
+                        unsigned long long* d_n_out, cudaStream_t stream, bool record_events, gf_index* store_owner = nullptr);
 int gf_fast_merge_device(gf_index* idx, const GfDevBatch& b, gf_merge_info* d_out, cudaStream_t stream);
 int gf_adjust_break_device(gf_index* idx, const uint8_t* d_bytes, const gf_break_ref* d_refs, const gf_break_job* d_jobs,
                            uint64_t n_jobs, gf_break_out* d_out, unsigned int* d_n_undefined, cudaStream_t stream);

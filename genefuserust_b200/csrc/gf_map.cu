@@ -1241,7 +1241,7 @@ static unsigned resident_blocks(K kernel, int threads, size_t smem) {
 
 /* ================================================================================================== */
 int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uint64_t out_cap,
-                        unsigned long long* d_n_out, cudaStream_t st, bool record_events) {
+                        unsigned long long* d_n_out, cudaStream_t st, bool record_events, gf_index* store_owner) {
     const bool paired = b.seq2 != nullptr;
     if (b.n > 0xFFFFFFFFull) {
         gf_set_error("batch too large (n > 2^32-1 pairs): split it");
@@ -1286,18 +1286,28 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
             const int NW3 = w5 ? split::SL<5>::NW3 : split::SL<8>::NW3;
             const uint32_t cap = surv_cap;
             const size_t groups = ((size_t)cap + 31) / 32;
-            GF_CUDA_TRY(idx->ws_seq_words.reserve(groups * NW3 * 32 * sizeof(uint32_t)));
-            GF_CUDA_TRY(idx->ws_seq_meta.reserve((size_t)cap * sizeof(uint4)));
+            /* list mode (several indices, one batch): k_prep's output does not depend on the index, so only the first
+             * handle of the list (`store_owner`) converts / merges / stores the sequences; the others read its store */
+            gf_index* own = store_owner ? store_owner : idx;
+            if (!store_owner) {
+                GF_CUDA_TRY(idx->ws_seq_words.reserve(groups * NW3 * 32 * sizeof(uint32_t)));
+                GF_CUDA_TRY(idx->ws_seq_meta.reserve((size_t)cap * sizeof(uint4)));
+            }
             GF_CUDA_TRY(idx->ws_seq_seed.reserve((size_t)cap * sizeof(uint2)));
             GF_CUDA_TRY(idx->ws_seq_lists.reserve((size_t)cap * 4 * sizeof(uint32_t) + 64));
             split::SeqStore ss;
-            ss.words = idx->ws_seq_words.as<uint32_t>();
-            ss.meta = idx->ws_seq_meta.as<uint4>();
+            ss.words = own->ws_seq_words.as<uint32_t>();
+            ss.meta = own->ws_seq_meta.as<uint4>();
             ss.seed = idx->ws_seq_seed.as<uint2>();
             ss.counters = idx->ws_seq_lists.as<unsigned int>();
             for (int l = 0; l < 4; l++) ss.lists[l] = idx->ws_seq_lists.as<uint32_t>() + 16 + (size_t)l * cap;
             ss.cap = cap;
             GF_CUDA_TRY(cudaMemsetAsync(ss.counters, 0, 64, st));
+            if (store_owner) { /* the slot counts of the shared store */
+                const unsigned int* oc = store_owner->ws_seq_lists.as<unsigned int>();
+                GF_CUDA_TRY(cudaMemcpyAsync(ss.counters, oc, sizeof(unsigned int), cudaMemcpyDeviceToDevice, st));
+                GF_CUDA_TRY(cudaMemcpyAsync(ss.counters + 5, oc + 5, sizeof(unsigned int), cudaMemcpyDeviceToDevice, st));
+            }
             split::PrepParams pp;
             pp.b = b;
             pp.st = ss;
@@ -1316,8 +1326,10 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
             want_b, (uint64_t)idx->sm_count * resident_blocks(split::k_prep<WW, PE>, tpp::WARPS * 32, psm)); \
         split::k_prep<WW, PE><<<pgrid, tpp::WARPS * 32, psm, st>>>(pp);                    \
     } while (0)
-            if (w5) { if (paired) GF_LAUNCH_PREP(5, true); else GF_LAUNCH_PREP(5, false); }
-            else { if (paired) GF_LAUNCH_PREP(8, true); else GF_LAUNCH_PREP(8, false); }
+            if (!store_owner) {
+                if (w5) { if (paired) GF_LAUNCH_PREP(5, true); else GF_LAUNCH_PREP(5, false); }
+                else { if (paired) GF_LAUNCH_PREP(8, true); else GF_LAUNCH_PREP(8, false); }
+            }
 #undef GF_LAUNCH_PREP
             if (record_events) GF_CUDA_TRY(cudaEventRecord(idx->ev_prep, st));
             split::SeedParams sdp;

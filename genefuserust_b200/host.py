@@ -407,3 +407,27 @@ class MultiGpuMapper:
         if getattr(self, "h", None):
             self.lib.gf_multi_destroy(self.h)
             self.h = None
+
+
+def scan_list(mappers, batch):
+    """List mode (fusion_scan.rs:62-188): the same reads against several FusionMappers (one per fusion CSV, all on one
+    device) in ONE call — the batch is uploaded and converted once, then mapped per index (gf_list_map_pairs).
+    Returns one record list per mapper, each identical to mapper.scan_pair_end(batch) / scan_single_end(batch)."""
+    lib = mappers[0].lib
+    n = len(mappers)
+    hs = (C.c_void_p * n)(*[m.m_indexer.h.value for m in mappers])
+    caps = [max(4096, batch.n // 64)] * n
+    st = batch.as_struct()
+    while True:
+        bufs = [(gf_match * c)() for c in caps]
+        outs = (C.POINTER(gf_match) * n)(*[C.cast(b, C.POINTER(gf_match)) for b in bufs])
+        ccaps = (C.c_uint64 * n)(*caps)
+        nout = (C.c_uint64 * n)()
+        rc = lib.gf_list_map_pairs(hs, n, C.byref(st), outs, ccaps, nout)
+        if rc == GF_E_CAPACITY:
+            caps = [max(c, int(k)) for c, k in zip(caps, nout)]
+            continue
+        _check(lib, rc, allow=(GF_E_REF_PANIC,))
+        for m in mappers:
+            m.last_rc = rc
+        return [[bufs[h][i] for i in range(nout[h])] for h in range(n)]

@@ -261,6 +261,18 @@ typedef struct gf_break_out {
 int gf_adjust_fusion_break(gf_index* idx, const uint8_t* bytes, uint64_t n_bytes, const gf_break_ref* refs, uint32_t n_refs,
                            const gf_break_job* jobs, uint64_t n_jobs, gf_break_out* out);
 
+/* ---- list mode: the same reads against several fusion CSVs (src/core/fusion_scan.rs:62-188) ----
+ * The reference scans its preloaded reads once per CSV with a fresh FusionMapper.  Here every CSV is one index handle, all on
+ * one device, and one call maps a batch against all of them: the batch is uploaded ONCE and converted / merged ONCE
+ * (fast_merge and the bit-plane conversion do not depend on the index), then seeded, screened and verified per index.
+ * out[h] / out_cap[h] / n_out[h] belong to idx[h]; each output is identical to gf_map_pairs(idx[h], in, ...) on its own.
+ * Returns the first error; GF_E_CAPACITY when any out_cap[h] is too small (n_out[] holds the required counts). */
+int gf_list_map_pairs(gf_index* const* idx, uint32_t n_idx, const gf_batch* in, gf_match* const* out, const uint64_t* out_cap,
+                      uint64_t* n_out);
+/* the same on a DEVICE-resident batch, asynchronous on `cuda_stream` like gf_map_pairs_device (one capacity for all) */
+int gf_map_pairs_device_list(gf_index* const* idx, uint32_t n_idx, const gf_batch* in_dev, gf_match* const* d_out,
+                             uint64_t out_cap, uint64_t* const* d_n_out, void* cuda_stream);
+
 /* ---- several GPUs of one box from ONE process (what the Rust binary needs; bench.py uses one process per GPU) ----
  * The index is replicated on every listed device (built there, ~12 ms each, in parallel); every batch is cut into
  * n_devices contiguous shards of pairs, each mapped by its own host thread on its own device (no device-to-device

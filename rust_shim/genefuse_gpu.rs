@@ -50,6 +50,8 @@ extern "C" {
     fn gf_index_destroy(idx: *mut gf_index);
     fn gf_map_pairs(idx: *mut gf_index, batch: *const gf_batch, out: *mut gf_match, out_cap: u64,
                     n_out: *mut u64) -> c_int;
+    fn gf_list_map_pairs(idx: *const *mut gf_index, n_idx: u32, batch: *const gf_batch, out: *const *mut gf_match,
+                         out_cap: *const u64, n_out: *mut u64) -> c_int;
     fn gf_adjust_fusion_break(idx: *mut gf_index, bytes: *const u8, n_bytes: u64, refs: *const gf_break_ref, n_refs: u32,
                               jobs: *const gf_break_job, n_jobs: u64, out: *mut gf_break_out) -> c_int;
 }
@@ -113,6 +115,24 @@ impl GpuIndex {
                                                  jobs.as_ptr(), jobs.len() as u64, out.as_mut_ptr()) };
         if rc != 0 { return Err(last_error()); }
         Ok(out)
+    }
+}
+
+/// List mode (src/core/fusion_scan.rs:62-188): one batch against every CSV's index in one call — one upload, one
+/// conversion / fast_merge pass, then per-index seeding, screening and verification.  Returns one record vector per index,
+/// each identical to `indices[h].map_pairs(batch)`.
+pub fn list_map_pairs(indices: &[&GpuIndex], batch: &gf_batch) -> Result<Vec<Vec<gf_match>>, String> {
+    let hs: Vec<*mut gf_index> = indices.iter().map(|g| g.h).collect();
+    let mut caps: Vec<u64> = vec![(batch.n / 8).max(1024); hs.len()];
+    loop {
+        let mut bufs: Vec<Vec<gf_match>> = caps.iter().map(|c| vec![gf_match::default(); *c as usize]).collect();
+        let ptrs: Vec<*mut gf_match> = bufs.iter_mut().map(|b| b.as_mut_ptr()).collect();
+        let mut n = vec![0u64; hs.len()];
+        let rc = unsafe { gf_list_map_pairs(hs.as_ptr(), hs.len() as u32, batch, ptrs.as_ptr(), caps.as_ptr(), n.as_mut_ptr()) };
+        if rc == GF_E_CAPACITY { for (c, k) in caps.iter_mut().zip(&n) { *c = (*c).max(*k); } continue; }
+        if rc != 0 { return Err(last_error()); }
+        for (b, k) in bufs.iter_mut().zip(&n) { b.truncate(*k as usize); }
+        return Ok(bufs);
     }
 }
 

@@ -563,3 +563,26 @@ def test_adjust_fusion_break_parity(mappers, small_panel):
             n_undef += want[3]
     assert n_jobs > 2000 and n_shift > 20 and n_undef > 5
     assert m.last_rc == -5      # GF_E_REF_PANIC: some breaks were pushed outside their reads on purpose
+
+
+def test_list_mode_shared_prep(host, small_panel):
+    """BASELINE config 4 / fusion_scan.rs:62-188: one batch against several indices in one call (upload and k_prep once):
+    every per-index record list must equal the one that index produces on its own, and the oracle's."""
+    genes = small_panel.genes()
+    subsets = [genes, genes[:40], genes[20:90], genes[:3]]
+    mappers = [host.FusionMapper.from_gene_spans(g, device=0) for g in subsets]
+    for L, seed in ((150, 41), (250, 42), (300, 43)):          # split screen (W = 5, 8) and the long-read path
+        b = synth.generate_pairs(small_panel, 60000, read_len=L, seed=seed, p_fusion=0.1)
+        got = host.scan_list(mappers, b)
+        for g, m, k in zip(subsets, mappers, range(len(subsets))):
+            alone = [r.astuple() for r in m.scan_pair_end(b)]
+            assert [r.astuple() for r in got[k]] == alone, (L, k)
+        o = orc.OracleIndex(subsets[1])
+        assert [r.astuple() for r in got[1]] == o.scan(b, threads=8)
+        o.close()
+        assert len(got[0]) > 100
+    se = ReadBatch(b.seq1, b.qual1, b.off1)
+    got = host.scan_list(mappers[:2], se)
+    assert [r.astuple() for r in got[1]] == [r.astuple() for r in mappers[1].scan_single_end(se)]
+    for m in mappers:
+        m.close()

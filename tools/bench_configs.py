@@ -41,7 +41,7 @@ def main():
     import __graft_entry__ as ge
     ge.build()
     import _oracle
-    from genefuserust_b200 import synth
+    from genefuserust_b200 import synth, ReadBatch
     from genefuserust_b200._abi import gf_batch, gf_map_stats, gf_match
     from genefuserust_b200.host import FusionMapper
     threads = os.cpu_count() or 8
@@ -177,17 +177,76 @@ def main():
         batch, d, d_off = device_batch(torch, synth, panel, P, L, 12, threads)
         sub = genes[:40]
         mappers = [FusionMapper.from_gene_spans(genes if k % 2 == 0 else sub) for k in range(a.list)]
-        ms, s, _ = run(mappers, d, d_off, P, L, a.steps)
-        sample = batch.slice(0, min(a.oracle_sample, P))
-        ok = True
+        ms_sep, s, _ = run(mappers, d, d_off, P, L, a.steps)      # one gf_map_pairs_device per CSV (k_prep per CSV)
+        # one gf_map_pairs_device_list call: upload / k_prep once, then per index
+        K = a.list
+        lib = mappers[0].lib
+        out_cap = max(1 << 16, P // 4)
+        d_outs = [torch.empty(out_cap * C.sizeof(gf_match), dtype=torch.uint8, device="cuda") for _ in range(K)]
+        d_ns = torch.zeros(K, dtype=torch.int64, device="cuda")
+        hs = (C.c_void_p * K)(*[m.m_indexer.h.value for m in mappers])
+        outs = (C.c_void_p * K)(*[t.data_ptr() for t in d_outs])
+        nouts = (C.c_void_p * K)(*[d_ns.data_ptr() + 8 * k for k in range(K)])
+        db = gf_batch()
+        db.n = P
+        db.seq1, db.qual1, db.seq2, db.qual2 = (t.data_ptr() for t in d)
+        db.off1 = db.off2 = d_off.data_ptr()
+        db.bytes1 = db.bytes2 = P * L
+        db.max_len = L
+        st = torch.cuda.current_stream()
+
+        def list_pass():
+            rc = lib.gf_map_pairs_device_list(hs, K, C.byref(db), outs, out_cap, nouts, C.c_void_p(st.cuda_stream))
+            assert rc == 0, lib.gf_last_error()
+        for _ in range(3):
+            list_pass()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(a.steps):
+            list_pass()
+        e1.record(st)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.steps
+        n_list = [int(x) for x in d_ns.tolist()]
+        # end to end from pinned host memory: gf_list_map_pairs (one upload) vs one gf_map_pairs per CSV
+        from genefuserust_b200 import host as H
+        import numpy as np
+        hb = ReadBatch(batch.seq1, batch.qual1, batch.off1, batch.seq2, batch.qual2, batch.off2)
+        got_list = H.scan_list(mappers, hb)                        # first call: grows every handle's chunk buffers
+        got_sep = [m.scan_pair_end(hb) for m in mappers[:2]]
+        # timed: the C ABI calls themselves (preallocated outputs), pinned host arenas
+        cap_h = max(4096, P // 64)
+        bufs = [(gf_match * cap_h)() for _ in range(K)]
+        outs_h = (C.POINTER(gf_match) * K)(*[C.cast(b_, C.POINTER(gf_match)) for b_ in bufs])
+        caps_h = (C.c_uint64 * K)(*([cap_h] * K))
+        nout_h = (C.c_uint64 * K)()
+        hst = hb.as_struct()
         t0 = time.perf_counter()
-        for gset, m in ((genes, mappers[0]), (sub, mappers[1] if a.list > 1 else mappers[0])):
+        rc = lib.gf_list_map_pairs(hs, K, C.byref(hst), outs_h, caps_h, nout_h)
+        e2e_list = time.perf_counter() - t0
+        assert rc == 0, lib.gf_last_error()
+        one = C.c_uint64(0)
+        t0 = time.perf_counter()
+        for k in range(2):
+            rc = lib.gf_map_pairs(mappers[k].m_indexer.h, C.byref(hst), bufs[k], cap_h, C.byref(one))
+            assert rc == 0, lib.gf_last_error()
+        e2e_sep2 = time.perf_counter() - t0
+        same = all([r.astuple() for r in got_list[k]] == [r.astuple() for r in got_sep[k]] for k in range(2))
+        same = same and [len(g) for g in got_list] == n_list
+        sample = batch.slice(0, min(a.oracle_sample, P))
+        ok = same
+        for gset, k in ((genes, 0), (sub, 1 if a.list > 1 else 0)):
             o = _oracle.OracleIndex(gset)
-            ok = ok and [r.astuple() for r in m.scan_pair_end(sample)] == o.scan(sample, threads=threads)
+            ok = ok and [r.astuple() for r in got_list[k] if r.pair_idx < sample.n] == o.scan(sample, threads=threads)
             o.close()
         print(json.dumps({"config": f"list mode: {a.list} fusion CSVs (alternating 136-gene / 40-gene panels) x {P} pairs 2x150, 1 B200",
                           "ms_per_list_job": ms, "pairs_per_s_whole_list": P / (ms / 1e3),
-                          "pair_x_csv_per_s": P * a.list / (ms / 1e3), "parity_ok_on_sample": ok,
+                          "pair_x_csv_per_s": P * a.list / (ms / 1e3),
+                          "ms_per_list_job_one_call_per_csv": ms_sep, "pair_x_csv_per_s_one_call_per_csv": P * a.list / (ms_sep / 1e3),
+                          "e2e_s_list_call (one upload, pinned host)": e2e_list, "e2e_pair_x_csv_per_s": P * a.list / e2e_list,
+                          "e2e_s_per_csv_separate_calls": e2e_sep2 / 2,
+                          "parity_ok_on_sample": ok,
                           "index_bytes_total": sum(int(m.m_indexer.info().device_bytes) for m in mappers)}), flush=True)
         assert ok
         for m in mappers:
