@@ -223,7 +223,8 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
     if (off1[n] < off1[0] || (pe && off2[n] < off2[0])) return fail(GF_E_INVALID, "offsets are not ascending");
     const uint64_t total_bytes = (off1[n] - off1[0]) + (pe ? off2[n] - off2[0] : 0);
     /* list mode: a chunk costs nh rounds of launches, so chunks are larger (the upload is a smaller share of a chunk anyway) */
-    const uint64_t chunk_bytes = CHUNK_TARGET_BYTES * std::min<uint32_t>(nh, 4u);
+    uint64_t chunk_bytes = CHUNK_TARGET_BYTES * std::min<uint32_t>(nh, 4u);
+    if (const char* e = getenv("GF_CHUNK_MB")) { long v = atol(e); if (v >= 1 && v <= 65536) chunk_bytes = (uint64_t)v << 20; }
     uint64_t n_chunks = std::max<uint64_t>(1, (2 * total_bytes + chunk_bytes - 1) / chunk_bytes);
     n_chunks = std::min<uint64_t>(n_chunks, n);
     const uint64_t per = (n + n_chunks - 1) / n_chunks;

@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepPa
     for (uint64_t base = ((uint64_t)blockIdx.x * tpp::WARPS + wib) * 32; base < B.n; base += n_warps * 32) {
         const uint64_t p = base + lane;
         int len1 = 0, len2 = 0, olen = -1, diff = 0, nseq = 0;
+        uint32_t r1_bits = 0; /* which of the (<= 2) overlap mismatches keep the R1 base */
         const uint8_t *q1 = nullptr, *q2 = nullptr;
         if (p < B.n) {
             const uint64_t o1 = __ldg(B.s1 + p);
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepPa
                 tpp::convert_r1<W>(c, s1, len1, B.seq1, bound1, pol_stream);
                 if (PAIRED) {
                     tpp::convert_r2_rc<W>(c, s2, len2, B.seq2, bound2, pol_stream);
-                    olen = tpp::find_overlap<W>(c, len1, len2, q1, q2, &diff);
+                    olen = tpp::find_overlap<W>(c, len1, len2, q1, q2, &diff, &r1_bits);
                 }
                 nseq = olen >= 0 ? 1 : (PAIRED ? 2 : 1);
             }
@@ -136,12 +137,11 @@ __global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepPa
                 int fix0 = -1, fix1 = -1;
                 for (int k = 0; 32 * k < olen; k++) {
                     uint32_t mism = tpp::overlap_mism<W>(c, offset, olen, len2, k);
-                    while (mism) {
+                    while (mism) { /* the qualities were looked at in find_overlap: r1_bits */
                         int b = __ffs(mism) - 1;
                         mism &= mism - 1;
-                        bool r1w;
-                        tpp::low_qual_pair(q1, q2, offset, len2, 32 * k + b, &r1w);
-                        if (r1w) { if (fix0 < 0) fix0 = offset + 32 * k + b; else fix1 = offset + 32 * k + b; }
+                        if (r1_bits & 1u) { if (fix0 < 0) fix0 = offset + 32 * k + b; else fix1 = offset + 32 * k + b; }
+                        r1_bits >>= 1;
                     }
                 }
                 for (int k = 0; k <= nwm; k++) { /* words 0 .. ceil(len/32): nothing beyond is ever read */

@@ -233,11 +233,16 @@ __device__ __forceinline__ bool low_qual_pair(const uint8_t* q1, const uint8_t* 
     *r1_wins = a >= '?' && b <= '0';
     return *r1_wins || (a <= '0' && b >= '?');
 }
-/* the full test of one overlap length (read.rs:339-367): <= 2 mismatches, each one a "low quality" pair */
+/* the full test of one overlap length (read.rs:339-367): <= 2 mismatches, each one a "low quality" pair.
+ * *r1_bits: bit i set <=> at the i-th mismatch (in position order) the R1 base wins (q1 >= '?' and q2 <= '0',
+ * read.rs:401-428) — kept so that the merged read can be built without fetching the quality bytes a second time
+ * (they may live in pinned host memory) */
 template <int W>
-__device__ __forceinline__ bool overlap_passes(const Col& c, int len1, int len2, int o, const uint8_t* q1, const uint8_t* q2, int* diff_out) {
+__device__ __forceinline__ bool overlap_passes(const Col& c, int len1, int len2, int o, const uint8_t* q1, const uint8_t* q2, int* diff_out,
+                                               uint32_t* r1_bits) {
     const int offset = len1 - o;
     int cnt = 0;
+    uint32_t bits = 0, nm = 0;
     for (int k = 0; 32 * k < o; k++) {
         uint32_t mism = overlap_mism<W>(c, offset, o, len2, k);
         if (!mism) continue;
@@ -248,9 +253,12 @@ __device__ __forceinline__ bool overlap_passes(const Col& c, int len1, int len2,
             mism &= mism - 1;
             bool r1w;
             if (!low_qual_pair(q1, q2, offset, len2, 32 * k + b, &r1w)) return false;
+            bits |= (r1w ? 1u : 0u) << nm;
+            nm++;
         }
     }
     *diff_out = cnt;
+    *r1_bits = bits;
     return true;
 }
 /* smallest passing overlap length (read.rs:323-367) or -1.
@@ -258,12 +266,14 @@ __device__ __forceinline__ bool overlap_passes(const Col& c, int len1, int len2,
  * must differ in <= 2 positions.  The R1 window slides by one bit per o, so the plane words are loaded once per 32 overlap
  * lengths and every o costs funnel shift + xor + popc + 2 (candidate bit shifted into a mask, no branch). */
 template <int W>
-__device__ __forceinline__ int find_overlap(const Col& c, int len1, int len2, const uint8_t* q1, const uint8_t* q2, int* diff_out) {
+__device__ __forceinline__ int find_overlap(const Col& c, int len1, int len2, const uint8_t* q1, const uint8_t* q2, int* diff_out,
+                                            uint32_t* r1_bits) {
     const int minlen = min(len1, len2);
     *diff_out = 0;
+    *r1_bits = 0;
     /* o = 30, 31: fewer than 32 positions */
     for (int o = 30; o <= min(31, minlen); o++)
-        if (overlap_passes<W>(c, len1, len2, o, q1, q2, diff_out)) return o;
+        if (overlap_passes<W>(c, len1, len2, o, q1, q2, diff_out, r1_bits)) return o;
     if (minlen < 32) return -1;
     const uint32_t c0 = c(Lay<W>::C2LO, 0);
     const int w_hi = (len1 - 32) >> 5, w_lo = (len1 - minlen) >> 5;
@@ -286,7 +296,7 @@ __device__ __forceinline__ int find_overlap(const Col& c, int len1, int len2, co
         while (cand) { /* rare: candidates in increasing o */
             const int j = __clz(cand);
             cand &= ~(0x80000000u >> j);
-            if (overlap_passes<W>(c, len1, len2, o_base + j, q1, q2, diff_out)) return o_base + j;
+            if (overlap_passes<W>(c, len1, len2, o_base + j, q1, q2, diff_out, r1_bits)) return o_base + j;
         }
     }
     *diff_out = 0;
@@ -495,7 +505,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_screen_tpp(ScreenParams P) {
                 int olen = -1, diff = 0;
                 if (PAIRED) {
                     convert_r2_rc<W>(c, s2, len2, B.seq2, bound2, pol_stream);
-                    olen = find_overlap<W>(c, len1, len2, q1, q2, &diff);
+                    uint32_t r1_bits_unused;
+                    olen = find_overlap<W>(c, len1, len2, q1, q2, &diff, &r1_bits_unused);
                 }
                 const int nseq = olen >= 0 ? 1 : (PAIRED ? 2 : 1);
                 for (int sq = 0; sq < nseq; sq++) {
@@ -559,7 +570,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_merge_only_tpp(GfDevBatch B, gf_
         convert_r1<W>(c, B.seq1 + (o1 - B.base1), len1, B.seq1, B.seq1 + B.bytes1, make_policy_stream());
         convert_r2_rc<W>(c, B.seq2 + (o2 - B.base2), len2, B.seq2, B.seq2 + B.bytes2, make_policy_stream());
         int diff = 0;
-        int olen = find_overlap<W>(c, len1, len2, B.qual1 + (B.qs1[p] - B.base1), B.qual2 + (B.qs2[p] - B.base2), &diff);
+        uint32_t r1_bits_unused;
+        int olen = find_overlap<W>(c, len1, len2, B.qual1 + (B.qs1[p] - B.base1), B.qual2 + (B.qs2[p] - B.base2), &diff, &r1_bits_unused);
         gf_merge_info mi;
         mi.merged = olen >= 0;
         mi.olen = olen >= 0 ? olen : 0;
