@@ -234,33 +234,32 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
         bool have = vi < n_slots, seeded = false, is_long = false;
         uint32_t seed_val = GF_EMPTY_VAL, seed_i = 0;
         if (have) {
+            /* 8 candidate 16-mers at half-word aligned offsets of the first 128 bases (a candidate is one shift + mask of a
+             * plane word, two candidates share the three plane loads).  The plane words are requested together with the
+             * slot's meta record (one memory round trip less on the critical path); a candidate counts only if it lies inside
+             * the read (words beyond the read were never written) and its 16 bases are valid.  Every candidate offset is even
+             * and inside the read, i.e. one of pass 1's probe offsets; which ones are tried only decides the diagonal, never
+             * the bound.  All go to the L2 filter at once; the HBM table is asked only for candidates the level-1 filter calls
+             * present, in read order, and the bucket of the first valid candidate is prefetched into L2 meanwhile. */
+            const uint32_t* col = slot_words<W>(P.st, s);
+            uint32_t plo[4], phi[4], pv[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                plo[j] = col[(size_t)j * 32]; phi[j] = col[(size_t)(NW + j) * 32]; pv[j] = col[(size_t)(2 * NW + j) * 32];
+            }
             const uint4 m = P.st.meta[s];
             const int len = (int)m.z;
             is_long = len > 32 * W;
             const int nprobe = len >= 16 ? ((len - 16) >> 1) + 1 : 0;
             if (nprobe == 0 && P.need_total > 0) have = false; /* cannot reach the gate: dropped here */
             if (have && nprobe > 0) {
-                /* 8 candidate 16-mers at half-word aligned offsets (a candidate is then one shift + mask of a plane word, and
-                 * two candidates share the three plane loads): words k_j = (j * nwc) / 4, j = 0..3, halves 0 and 1.  Every
-                 * candidate offset is even and inside the read (its 16 valid bits), i.e. one of pass 1's probe offsets; which
-                 * ones are tried only decides the diagonal, never the bound.  All go to the L2 filter at once; the HBM table
-                 * is asked only for candidates the filter calls present-and-unique, in read order, and the bucket of the first
-                 * valid candidate is prefetched into L2 while the filter words are in flight. */
-                const uint32_t* col = slot_words<W>(P.st, s);
-                const int nwc = max(1, len >> 5);
                 uint32_t key[8], okm = 0;
-                int kprev = -1;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const int k = (j * nwc) >> 2;
-                    const uint32_t lo = col[(size_t)k * 32], hi = col[(size_t)(NW + k) * 32], v = col[(size_t)(2 * NW + k) * 32];
-                    key[2 * j] = (hi << 16) | (lo & 0xFFFFu);
-                    key[2 * j + 1] = (hi & 0xFFFF0000u) | (lo >> 16);
-                    if (k != kprev) {
-                        if ((v & 0xFFFFu) == 0xFFFFu) okm |= 1u << (2 * j);
-                        if ((v >> 16) == 0xFFFFu) okm |= 2u << (2 * j);
-                    }
-                    kprev = k;
+                    key[2 * j] = (phi[j] << 16) | (plo[j] & 0xFFFFu);
+                    key[2 * j + 1] = (phi[j] & 0xFFFF0000u) | (plo[j] >> 16);
+                    if (32 * j + 16 <= len && (pv[j] & 0xFFFFu) == 0xFFFFu) okm |= 1u << (2 * j);
+                    if (32 * j + 32 <= len && (pv[j] >> 16) == 0xFFFFu) okm |= 2u << (2 * j);
                 }
                 if (okm) {
                     const uint32_t t0 = (uint32_t)__ffs(okm) - 1u;
@@ -294,7 +293,7 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
                     const uint32_t val = gf_table_find(P.ix, kt);
                     if (val != GF_EMPTY_VAL && (val >> 30) == GF_KIND_UNIQUE) {
                         seed_val = val;
-                        seed_i = 32u * (uint32_t)(((t >> 1) * nwc) >> 2) + 16u * (uint32_t)(t & 1);
+                        seed_i = 16u * (uint32_t)t;
                         seeded = true;
                         break;
                     }
