@@ -187,6 +187,15 @@ __device__ __forceinline__ uint32_t gf_filter_sites(const GfDevIndex& ix, unsign
     return (mw & mm) == mm ? max_sites : 1u;
 }
 
+/* level 1 only: may the key vote at all?  (A present key is then counted with the cap of the bound, min(sites, 2) = 2:
+ * asking level 2 for the unique / dupe distinction would put a second, dependent L2 gather behind every hit.) */
+__device__ __forceinline__ bool gf_filter_present(unsigned long long w, uint32_t key) {
+    uint32_t al, ah;
+    gf_filter_masks(key, &al, &ah);
+    const uint32_t wl = (uint32_t)w, wh = (uint32_t)(w >> 32);
+    return (wl & al) == al && (wh & ah) == ah;
+}
+
 /* site decoding ---------------------------------------------------------------------------- */
 /* goff -> contig: one table load */
 __device__ __forceinline__ uint32_t gf_contig_of(const GfDevIndex& ix, uint32_t goff) {

@@ -333,9 +333,10 @@ __device__ __forceinline__ void push_survivor(const ClassParams& P, const uint4&
 /* unseeded sequences: the valid even offsets get a filter probe until the outcome is decided.
  * Bound (indexer.rs:286-360): a k-mer votes at most ONCE for any one diagonal (the sites of a key are distinct), so with
  * s_i = sites of the k-mer at offset i:  count1 <= P = #{i : s_i >= 1}  and  count1 + count2 <= T = sum min(s_i, 2).
- * The gate needs count1 >= need_major and count2 >= need_minor, hence P >= need_major and T >= need_major + need_minor;
- * probing stops as soon as the offsets that are left cannot lift P or T over its threshold (off-target reads: after ~3/4
- * of their offsets). */
+ * The gate needs count1 >= need_major and count2 >= need_minor, hence P >= need_major and T >= need_major + need_minor.
+ * Only the level-1 filter is asked here (present / absent), i.e. T is bounded by 2 P and the test is P >= need_major (and
+ * 2 P >= need_major + need_minor); probing stops as soon as the offsets that are left cannot lift P over the threshold
+ * (off-target reads: after ~3/4 of their offsets). */
 template <int W>
 __global__ void __launch_bounds__(256) k_scan(ClassParams P) {
     constexpr int NW = SL<W>::NW;
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(256) k_scan(ClassParams P) {
         const int len = (int)m.z, nch = (len + 31) >> 5;
         const uint32_t* col = slot_words<W>(P.st, s);
         uint32_t lo = col[0], hi = col[(size_t)NW * 32], v = col[(size_t)2 * NW * 32];
-        int T = 0, Pn = 0;
+        int Pn = 0;
         bool dead = false;
 #pragma unroll 1
         for (int k = 0; k < nch && !dead; k++) {
@@ -374,17 +375,15 @@ __global__ void __launch_bounds__(256) k_scan(ClassParams P) {
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++)
-                    if (ok[u]) {
-                        const int si = (int)gf_filter_sites(ix, w[u], key[u], 2u);
-                        T += si;
-                        Pn += si != 0;
-                    }
+                    if (ok[u] && gf_filter_present(w[u], key[u])) Pn++;
                 const int rem = __popc(om) + rem_after;
-                if (P.need_total > 0 && (Pn + rem < need_major || T + 2 * rem < P.need_total)) { dead = true; break; }
+                if (P.need_total > 0 && Pn + rem < need_major) { dead = true; break; }
             }
             lo = nlo; hi = nhi; v = nv;
         }
-        if (P.need_total <= 0 || (!dead && T >= P.need_total && Pn >= need_major && T >= P.need_minor)) push_survivor(P, m);
+        /* T <= 2 Pn without the unique / dupe distinction: the T conditions follow from Pn >= need_major when
+         * need_minor <= need_major (checked by the host; otherwise 2 Pn is compared) */
+        if (P.need_total <= 0 || (!dead && Pn >= need_major && 2 * Pn >= P.need_total)) push_survivor(P, m);
     }
     }
 }
@@ -421,8 +420,8 @@ __global__ void __launch_bounds__(256, 4) k_diag(ClassParams P) {
                     const uint32_t kk = ((__funnelshift_r(q_hi0[wib][e], q_hi1[wib][e], b) & 0xFFFFu) << 16) |
                                         (__funnelshift_r(q_lo0[wib][e], q_lo1[wib][e], b) & 0xFFFFu);
                     const uint32_t key = ((meta >> 8) & 1u) ? gf_key_revcomp(kk) : kk;
-                    const int nsites = (int)gf_filter_sites(ix, ldg_filter(ix.filter + gf_filter_word(key, ix.filter_words), pol), key, 2u);
-                    if (nsites) atomicAdd(&t_sh[wib][meta & 31u], nsites);
+                    if (gf_filter_present(ldg_filter(ix.filter + gf_filter_word(key, ix.filter_words), pol), key))
+                        atomicAdd(&t_sh[wib][meta & 31u], 2); /* min(sites, 2) <= 2 */
                 }
             }
         }
