@@ -228,8 +228,11 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
     const uint32_t n_slots = n_short + n_long; /* virtual index v: short slots, then the long ones in ascending order */
     const unsigned long long pol = make_policy_keep();
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t s0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); s0 < n_slots; s0 += stride) {
-        const uint32_t vi = s0 + lane;
+    const uint32_t wib = threadIdx.x >> 5;
+    __shared__ uint32_t cls_cnt[8][4], cls_base[8][4];
+    /* block-uniform trip count: the list entries are reserved once per block and iteration (below) */
+    for (uint32_t b0 = blockIdx.x * blockDim.x; b0 < n_slots; b0 += stride) {
+        const uint32_t vi = b0 + threadIdx.x;
         const uint32_t s = vi < n_short ? vi : P.st.cap - n_long + (vi - n_short);
         bool have = vi < n_slots, seeded = false, is_long = false;
         uint32_t seed_val = GF_EMPTY_VAL, seed_i = 0;
@@ -301,18 +304,26 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
             }
             if (have) P.st.seed[s] = make_uint2(seed_val, seed_i);
         }
-        /* class lists, warp-aggregated: lane c reserves the entries of class c */
+        /* class lists, aggregated over the block: one atomic per class, block and iteration (the four list counters are
+         * single hot addresses; a per-warp atomic on them serialises in L2) */
         const int cls = have ? (seeded ? 0 : 2) + (is_long ? 1 : 0) : -1;
         const uint32_t mine = __match_any_sync(FULL, cls);
-        uint32_t m4 = 0, base = 0;
 #pragma unroll
         for (int cc = 0; cc < 4; cc++) {
             const uint32_t mc = __ballot_sync(FULL, cls == cc);
-            if (lane == (uint32_t)cc) m4 = mc;
+            if (lane == (uint32_t)cc) cls_cnt[wib][cc] = (uint32_t)__popc(mc);
         }
-        if (lane < 4 && m4) base = atomicAdd(&P.st.counters[1 + lane], (unsigned)__popc(m4));
-        base = __shfl_sync(FULL, base, cls < 0 ? 0 : cls);
-        if (cls >= 0) P.st.lists[cls][base + __popc(mine & gf_lanemask_lt())] = s;
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) tot += cls_cnt[w][threadIdx.x];
+            uint32_t bb = tot ? atomicAdd(&P.st.counters[1 + threadIdx.x], tot) : 0u;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { cls_base[w][threadIdx.x] = bb; bb += cls_cnt[w][threadIdx.x]; }
+        }
+        __syncthreads();
+        if (cls >= 0) P.st.lists[cls][cls_base[wib][cls] + __popc(mine & gf_lanemask_lt())] = s;
     }
 }
 
