@@ -935,6 +935,16 @@ __device__ SegResult exact_map_read(const GfDevIndex& ix, EW& W, int len, long l
         uint32_t best = 0;
         for (int s = (int)lane; s < len - 1; s += 32) {
             if (W.mask[s] != target) continue;
+            /* The walk below is memoryless, so a start that an earlier start's walk passes through ends at the same `end`
+             * and scores strictly less: only the first start of each walk can win.  s is such a first start unless a
+             * target position lies within the 10 positions before it with nothing higher in between. */
+            bool first = true;
+            for (int q = s - 1; q >= 0 && q >= s - 10; q--) {
+                const int mq = W.mask[q];
+                if (mq > target) break;
+                if (mq == target) { first = false; break; }
+            }
+            if (!first) continue;
             int end = s + 1, g = 0;
             while (g < 10 && end + g < len) {
                 int m = W.mask[end + g];
