@@ -1125,21 +1125,91 @@ __device__ int warp_edit_distance(const uint8_t* part, int m, bool a_rc, const u
     return __shfl_sync(FULL, d, tmax);
 }
 
-/* FusionMapper::calc_ed (fusion_mapper.rs:224-251) */
-__device__ int calc_ed(const GfDevIndex& ix, const uint8_t* part, int plen, int32_t contig, int32_t start, int32_t end,
-                       uint32_t* panic) {
-    if ((start >= 0 && end <= 0) || (start <= 0 && end >= 0)) return -1;
+/* Two equal-length edit distances at once, one per half-warp (lanes 0-15: job 0, lanes 16-31: job 1): the same systolic
+ * recurrences as warp_edit_distance with the block index = lane & 15, so a candidate's left and right distances cost
+ * max(m0, m1) + blocks steps instead of their sum.  Needs <= 16 blocks (m <= 1024) per job; m == 0 = no job (result 0). */
+__device__ void warp_edit_distance_dual(const uint8_t* part0, int m0, bool rc0, const uint8_t* __restrict__ text0,
+                                        const uint8_t* part1, int m1, bool rc1, const uint8_t* __restrict__ text1, int* d0,
+                                        int* d1) {
+    const uint32_t lane = gf_lane(), hl = lane & 15u;
+    const bool side = lane >= 16;
+    const uint8_t* part = side ? part1 : part0;
+    const uint8_t* text = side ? text1 : text0;
+    const int m = side ? m1 : m0;
+    const bool a_rc = side ? rc1 : rc0;
+    const int nb = m > 0 ? ((m - 1) >> 6) + 1 : 0, tmax = nb - 1, tlen = m - 64 * tmax;
+    auto a_at = [&](int k) -> uint8_t { return a_rc ? gf_complement_ascii(part[m - 1 - k]) : part[k]; };
+    unsigned long long pA = 0, pC = 0, pG = 0, pT = 0, pN = 0, pO = 0;
+    if ((int)hl < nb) {
+        for (int j = 0; j < 64; j++) {
+            int k = 64 * (int)hl + j;
+            if (k >= m) break;
+            uint8_t ch = a_at(k);
+            unsigned long long bit = 1ull << j;
+            if (ch == 'A') pA |= bit; else if (ch == 'C') pC |= bit; else if (ch == 'G') pG |= bit;
+            else if (ch == 'T') pT |= bit; else if (ch == 'N') pN |= bit; else pO |= bit;
+        }
+    }
+    unsigned long long vp = 0, vn = 0;
+    if ((int)hl < tmax) vp = ~0ull;
+    else if ((int)hl == tmax) vp = tlen >= 64 ? ~0ull : ((1ull << tlen) - 1ull);
+    const unsigned long long top = nb > 0 ? 1ull << (tlen - 1) : 0ull, lmb = 1ull << 63;
+    int d = m;
+    uint32_t hp_out = 0, hn_out = 0;
+    const int my_steps = m > 0 ? m + nb - 1 : 0;
+    const int steps = (int)__reduce_max_sync(FULL, (unsigned)my_steps);
+    for (int t = 0; t < steps; t++) {
+        uint32_t hp_in = __shfl_up_sync(FULL, hp_out, 1, 16);
+        uint32_t hn_in = __shfl_up_sync(FULL, hn_out, 1, 16);
+        int j = t - (int)hl;
+        if ((int)hl < nb && j >= 0 && j < m) {
+            uint8_t ch = __ldg(text + j);
+            unsigned long long x;
+            if (ch == 'A') x = pA; else if (ch == 'C') x = pC; else if (ch == 'G') x = pG;
+            else if (ch == 'T') x = pT; else if (ch == 'N') x = pN;
+            else {
+                x = 0;
+                if (pO) for (int q = 0; q < 64; q++) { int k = 64 * (int)hl + q; if (k < m && ((pO >> q) & 1ull) && a_at(k) == ch) x |= 1ull << q; }
+            }
+            if (hl > 0 && hn_in) x |= 1ull;
+            unsigned long long dd0 = (((x & vp) + vp) ^ vp) | x | vn;
+            unsigned long long hp = vn | ~(dd0 | vp);
+            unsigned long long hn = dd0 & vp;
+            unsigned long long x2 = hp << 1;
+            if (hl == 0 || hp_in) x2 |= 1ull;
+            vp = (hn << 1) | ~(dd0 | x2);
+            if (hl > 0 && hn_in) vp |= 1ull;
+            vn = dd0 & x2;
+            hp_out = (hp & lmb) ? 1u : 0u;
+            hn_out = (hn & lmb) ? 1u : 0u;
+            if ((int)hl == tmax) {
+                if (hp & top) d++;
+                else if (hn & top) d--;
+            }
+        }
+    }
+    const int r0 = __shfl_sync(FULL, d, m0 > 0 ? ((m0 - 1) >> 6) : 0);
+    const int r1 = __shfl_sync(FULL, d, 16 + (m1 > 0 ? ((m1 - 1) >> 6) : 0));
+    *d0 = m0 > 0 ? r0 : 0;
+    *d1 = m1 > 0 ? r1 : 0;
+}
+
+/* the checks of FusionMapper::calc_ed (fusion_mapper.rs:224-251) that come before the edit distance: returns true when
+ * `*res` already is the answer (-1 / -2 sentinels, empty side), otherwise the equal-length job (text, rc) */
+__device__ bool calc_ed_setup(const GfDevIndex& ix, int plen, int32_t contig, int32_t start, int32_t end, int* res,
+                              const uint8_t** text, bool* rc, uint32_t* panic) {
+    if ((start >= 0 && end <= 0) || (start <= 0 && end >= 0)) { *res = -1; return true; }
     const int32_t glen = (int32_t)ix.gene_len[contig];
     const int32_t as = start < 0 ? -start : start, ae = end < 0 ? -end : end;
-    if (as >= glen || ae >= glen) return -2;
-    bool rc = start < 0;
-    if (rc) { int32_t tmp = start; start = -end; end = -tmp; }
+    if (as >= glen || ae >= glen) { *res = -2; return true; }
+    *rc = start < 0;
+    if (*rc) { int32_t tmp = start; start = -end; end = -tmp; }
     const int reflen = end - start + 1;
-    if (plen == 0) return reflen;      /* edit_distance: asize == 0 -> bsize */
-    if (reflen == 0) return plen;
-    /* plen == reflen by construction (calc_distance, fusion_mapper.rs:196-222) */
+    if (plen == 0) { *res = reflen; return true; }      /* edit_distance: asize == 0 -> bsize */
+    if (reflen == 0) { *res = plen; return true; }
     if (((plen - 1) >> 6) + 1 > 10) *panic = 1; /* the reference falls into its panicking DP branch (>640) */
-    return warp_edit_distance(part, plen, rc, ix.gene_ascii + ix.gene_start[contig] + start);
+    *text = ix.gene_ascii + ix.gene_start[contig] + start;
+    return false;
 }
 
 __global__ void __launch_bounds__(VF_WARPS * 32) k_verify(VerifyParams P) {
@@ -1158,8 +1228,23 @@ __global__ void __launch_bounds__(VF_WARPS * 32) k_verify(VerifyParams P) {
         const int rb = m.read_break;
         const int left_len = rb + 1, right_len = len - (rb + 1);
         uint32_t panic = 0;
-        int ld = calc_ed(P.ix, W.seq, left_len, m.l_contig, m.l_pos - left_len + 1, m.l_pos, &panic);
-        int rd = calc_ed(P.ix, W.seq + rb + 1, right_len, m.r_contig, m.r_pos, m.r_pos + right_len - 1, &panic);
+        int ld = 0, rd = 0;
+        {
+            const uint8_t *tl = nullptr, *tr = nullptr;
+            bool rcl = false, rcr = false;
+            const bool dl = calc_ed_setup(P.ix, left_len, m.l_contig, m.l_pos - left_len + 1, m.l_pos, &ld, &tl, &rcl, &panic);
+            const bool dr = calc_ed_setup(P.ix, right_len, m.r_contig, m.r_pos, m.r_pos + right_len - 1, &rd, &tr, &rcr, &panic);
+            if (left_len <= 1024 && right_len <= 1024) { /* both distances side by side, one per half-warp */
+                int a = 0, b = 0;
+                if (!dl || !dr)
+                    warp_edit_distance_dual(W.seq, dl ? 0 : left_len, rcl, tl, W.seq + rb + 1, dr ? 0 : right_len, rcr, tr, &a, &b);
+                if (!dl) ld = a;
+                if (!dr) rd = b;
+            } else {
+                if (!dl) ld = warp_edit_distance(W.seq, left_len, rcl, tl);
+                if (!dr) rd = warp_edit_distance(W.seq + rb + 1, right_len, rcr, tr);
+            }
+        }
         /* what filter_matches would decide (fusion_mapper.rs:298-377); the record is kept either way */
         int chg_l = 0, chg_r = 0; /* dis_connected_count (src/utils/mod.rs:48-56) of both sides of the break */
         for (int i = (int)lane; i + 1 < left_len; i += 32) chg_l += W.seq[i] != W.seq[i + 1];
