@@ -410,7 +410,7 @@ __device__ __forceinline__ GeneWord ldg_gene_word(const uint32_t* base, uint32_t
 }
 constexpr int DIAG_Q = 128; /* queue entries per warp; flushed above DIAG_Q - 32 (a chunk adds <= 32) */
 template <int W>
-__global__ void __launch_bounds__(256, 4) k_diag(ClassParams P) {
+__global__ void __launch_bounds__(256, 5) k_diag(ClassParams P) {
     constexpr int NW = SL<W>::NW;
     __shared__ uint32_t q_lo0[8][DIAG_Q], q_lo1[8][DIAG_Q], q_hi0[8][DIAG_Q], q_hi1[8][DIAG_Q], q_om[8][DIAG_Q], q_meta[8][DIAG_Q];
     __shared__ int t_sh[8][32];
