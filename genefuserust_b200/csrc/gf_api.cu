@@ -230,6 +230,28 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
     const uint64_t per = (n + n_chunks - 1) / n_chunks;
     n_chunks = (n + per - 1) / per;
 
+    /* max_len hint missing: the host offsets are at hand, so the longest read is found here (several threads; ~1 ms per
+     * 10 M reads) instead of falling back to the long-read kernels */
+    uint32_t max_len = in->max_len;
+    if (max_len == 0) {
+        const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        std::vector<uint64_t> part(nt, 0);
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++)
+            th.emplace_back([&, t]() {
+                uint64_t mx = 0;
+                for (uint64_t i = n * t / nt; i < n * (t + 1) / nt; i++) {
+                    mx = std::max(mx, off1[i + 1] - off1[i]);
+                    if (pe) mx = std::max(mx, off2[i + 1] - off2[i]);
+                }
+                part[t] = mx;
+            });
+        for (auto& x : th) x.join();
+        uint64_t mx = 1;
+        for (uint64_t v : part) mx = std::max(mx, v);
+        max_len = (uint32_t)std::min<uint64_t>(mx, 0xFFFFFFFFull);
+    }
+
     std::vector<unsigned long long> launches0(nh);
     for (uint32_t h = 0; h < nh; h++) launches0[h] = hs[h]->launches;
     std::vector<uint64_t> total_out(nh, 0), d2h(nh, 0);
@@ -241,7 +263,7 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
     const uint8_t *zq1 = nullptr, *zq2 = nullptr;
     {
         const char* e = getenv("GF_ZEROCOPY_QUAL");
-        bool want = !(e && atoi(e) == 0) && idx->screen_version >= 3 && in->max_len != 0 && in->max_len <= 256;
+        bool want = !(e && atoi(e) == 0) && idx->screen_version >= 3 && max_len != 0 && max_len <= 256;
         auto mapped = [](const void* p) -> const uint8_t* {
             cudaPointerAttributes at;
             if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -279,7 +301,7 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
         db.base1 = b1;
         db.bytes1 = e1 - b1;
         db.pair_base = lo;
-        db.max_len = in->max_len;
+        db.max_len = max_len;
         if (pe) {
             const uint64_t b2 = off2[lo], e2 = off2[hi];
             GF_CUDA_TRY(s.seq2.reserve(e2 - b2 + 16));

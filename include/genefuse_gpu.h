@@ -88,8 +88,10 @@ typedef struct gf_batch {
     uint64_t bytes1; /* == off1[n] - off1[0] */
     uint64_t bytes2; /* == off2[n] - off2[0] (0 for SE) */
     uint32_t max_len; /* hint: upper bound of any read's length in this batch, 0 = unknown.  Selects the
-                         kernel capacity (<= 256: 8-word bit-planes, else 32-word).  A read longer than the
-                         hint (or than 1024) makes the call fail with GF_E_INVALID; it is never truncated. */
+                         kernel capacity (<= 160 / <= 256: thread-per-pair kernels, else warp-per-pair).  A read longer
+                         than the hint (or than 1024) makes the call fail with GF_E_INVALID; it is never truncated.
+                         0: gf_map_pairs / gf_list_map_pairs find the longest read themselves (host offsets);
+                         gf_map_pairs_device cannot without a synchronisation and takes the long-read kernels. */
     uint32_t reserved;
 } gf_batch;
 

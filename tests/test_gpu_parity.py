@@ -267,6 +267,21 @@ def test_max_len_hint_is_enforced(mappers, small_panel, host):
         m.scan_pair_end(b)
 
 
+def test_missing_max_len_hint(mappers, small_panel):
+    """max_len = 0 (no hint): gf_map_pairs finds the longest read itself; same records, and the thread-per-pair kernels
+    (zero-copy qualities are only offered by them) still run"""
+    import torch
+    m, o = mappers
+    b = synth.generate_pairs(small_panel, 30000, read_len=150, seed=33, p_fusion=0.1)
+    want = [r.astuple() for r in m.scan_pair_end(b)]
+    pinned = [torch.from_numpy(a.copy()).pin_memory() for a in (b.seq1, b.qual1, b.seq2, b.qual2)]
+    pb = ReadBatch(pinned[0].numpy(), pinned[1].numpy(), b.off1, pinned[2].numpy(), pinned[3].numpy(), b.off2)
+    pb.max_len = 0
+    assert [r.astuple() for r in m.scan_pair_end(pb)] == want
+    assert m.map_stats().zero_copy_qual == 1
+    assert want == o.scan(b, threads=8)
+
+
 def test_capacity_protocol(mappers, small_panel):
     import ctypes as C
     from genefuserust_b200._abi import gf_match
