@@ -328,30 +328,41 @@ class FusionMapper:
 
     # -- fusion_mapper.rs:253-275 / 379-392
     def add_match(self, m):
-        index = self.n_genes * m.r_contig + m.l_contig
-        self.fusion_matches.setdefault(index, []).append(m)
+        self.fusion_matches.setdefault(fusion_bucket(self.n_genes, m), []).append(m)
 
     def sort_matches(self, read_name_of):
         """sort_by(|a, b| b.partial_cmp(a)) with ReadMatch's order (read_match.rs:203-229): read_break desc,
         read length asc, read name desc; stable.  `read_name_of(m)` supplies m_read.m_name."""
-        import functools
-
-        def cmp(a, b):
-            # partial_cmp(self=b, other=a): break asc on (b, a) -> desc on (a, b); len compared other-vs-self
-            if a.read_break != b.read_break:
-                return -1 if b.read_break < a.read_break else 1
-            if a.seq_len != b.seq_len:
-                return -1 if a.seq_len < b.seq_len else 1
-            na, nb = read_name_of(a), read_name_of(b)
-            if na != nb:
-                return -1 if nb < na else 1
-            return 0
-
         for v in self.fusion_matches.values():
-            v.sort(key=functools.cmp_to_key(cmp))
+            sort_read_matches(v, read_name_of)
 
     def close(self):
         self.m_indexer.close()
+
+
+def fusion_bucket(n_genes, m):
+    """FusionMapper::add_match (fusion_mapper.rs:253-275): index of the n_genes x n_genes bucket a match goes to"""
+    return n_genes * m.r_contig + m.l_contig
+
+
+def sort_read_matches(matches, read_name_of):
+    """FusionMapper::sort_matches (fusion_mapper.rs:379-385) = sort_by(|a, b| b.partial_cmp(a)) with ReadMatch's order
+    (read_match.rs:203-229): read_break descending, read length ascending, read name descending; stable, so exact ties
+    keep the push order ((pair_idx, source) = the reference's order at -t 1)."""
+    import functools
+
+    def cmp(a, b):
+        # partial_cmp(self=b, other=a): break asc on (b, a) -> desc on (a, b); len compared other-vs-self
+        if a.read_break != b.read_break:
+            return -1 if b.read_break < a.read_break else 1
+        if a.seq_len != b.seq_len:
+            return -1 if a.seq_len < b.seq_len else 1
+        na, nb = read_name_of(a), read_name_of(b)
+        if na != nb:
+            return -1 if nb < na else 1
+        return 0
+
+    matches.sort(key=functools.cmp_to_key(cmp))
 
 
 class PairEndScanner:

@@ -184,3 +184,22 @@ def test_sharding_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert len(want) > 5 and got == want
+
+
+def test_add_match_bucket_and_sort_order():
+    """bucket = n_genes * right.contig + left.contig (fusion_mapper.rs:263); sort_matches orders a
+    bucket by read_break desc, read length asc, read name desc, stable (read_match.rs:203-229, fusion_mapper.rs:379-385)"""
+    from genefuserust_b200 import host
+    from genefuserust_b200._abi import gf_match
+
+    def mk(pair, rb, slen, lc=1, rc=2):
+        m = gf_match()
+        m.pair_idx, m.read_break, m.seq_len, m.l_contig, m.r_contig = pair, rb, slen, lc, rc
+        return m
+    assert host.fusion_bucket(136, mk(0, 10, 100, lc=3, rc=7)) == 136 * 7 + 3
+    names = {0: "r0", 1: "r1", 2: "r2", 3: "r3", 4: "r4", 5: "r5", 6: "r5"}
+    ms = [mk(0, 50, 150), mk(1, 70, 150), mk(2, 70, 120), mk(3, 70, 120), mk(4, 50, 150), mk(5, 60, 99), mk(6, 60, 99)]
+    host.sort_read_matches(ms, lambda m: names[m.pair_idx])
+    # break 70 first (len 120 before 150; among the two 120s the larger name first), then 60 (equal names: push order kept),
+    # then 50 (r4 before r0)
+    assert [m.pair_idx for m in ms] == [3, 2, 1, 5, 6, 4, 0]
