@@ -128,8 +128,10 @@ __device__ __forceinline__ uint32_t gf_home_bucket(uint32_t key, uint32_t shift)
 /* 32-byte (one sector) read-only bucket load */
 __device__ __forceinline__ void gf_load_bucket(const uint4* table, uint32_t b, uint4& a, uint4& c) {
     const uint4* p = table + 2ull * b;
-    a = __ldg(p);
-    c = __ldg(p + 1);
+    /* one 256-bit load of the 32-byte bucket; L2::64B = smallest L2 prefetch size: a random probe should not drag a whole
+     * 128-byte line out of HBM */
+    asm volatile("ld.global.nc.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "l"(p));
 }
 /* match `key` inside a loaded bucket: returns val, or GF_EMPTY_VAL with *stop telling whether the probe ends */
 __device__ __forceinline__ uint32_t gf_match_bucket(const uint4& a, const uint4& c, uint32_t key, bool* stop) {
