@@ -276,7 +276,7 @@ int gf_map_pairs_device_list(gf_index* const* idx, uint32_t n_idx, const gf_batc
                              uint64_t out_cap, uint64_t* const* d_n_out, void* cuda_stream);
 
 /* ---- several GPUs of one box from ONE process (what the Rust binary needs; bench.py uses one process per GPU) ----
- * The index is replicated on every listed device (built there, ~12 ms each, in parallel); every batch is cut into
+ * The index is replicated on every listed device (built there, ~19 ms each, in parallel); every batch is cut into
  * n_devices contiguous shards of pairs, each mapped by its own host thread on its own device (no device-to-device
  * traffic: reads are independent, map_read(&self), src/core/fusion_mapper.rs:93), and the records are gathered on
  * the host.  The result is identical to a single-device gf_map_pairs on the whole batch, including the order.
