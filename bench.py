@@ -69,9 +69,12 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """clocks of the samples that arrived inside [t_begin, t_end] (host clock); when the timed region is shorter than
+        the sampling period the samples of the whole loaded phase (warm-up .. extra steps, the same kernels) are used and
+        `window` says so"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -80,23 +83,32 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
+
+        def summarise(lines):
+            sm, mx, reasons = [], [], set()
+            for _t, ln in lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            sm.sort()
+            return sm, mx, sorted(reasons)
+        window = "timed region"
+        inside = [x for x in self.lines if t_begin is None or (t_begin - 0.01 <= x[0] <= t_end + 0.03)]
+        sm, mx, reasons = summarise(inside)
+        if len(sm) < 2:
+            window = "warm-up + timed region + per-kernel steps (timed region shorter than the sampling period)"
+            sm, mx, reasons = summarise(self.lines)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": reasons, "window": window}
 
 
 def measured_peak():
@@ -271,21 +283,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()          # before the warm-up: nvidia-smi needs ~100 ms to deliver its first line
     for _ in range(max(a.warmup, 3)):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     screen_ms = []
     exact_ms = []
     parts_ms = []
     barrier()
+    t_begin = time.perf_counter()
     ev0.record(stream)
     for _ in range(a.steps):
         step_device()
     ev1.record(stream)
     barrier()
+    t_end = time.perf_counter()
     ms_total = ev0.elapsed_time(ev1)
     # per-kernel duration of the last step from the library's own events on the launching stream
     st = gf_map_stats()
@@ -301,7 +315,7 @@ def main():
         screen_ms.append(s2.ms_screen)
         exact_ms.append(s2.ms_exact)
         parts_ms.append((s2.ms_prep, s2.ms_seed, s2.ms_diag, s2.ms_scan))
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, t_end)
     n_matches = int(d_nout.item())
 
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
