@@ -105,7 +105,7 @@ class ClockSampler:
         inside = [x for x in self.lines if t_begin is None or (t_begin - 0.01 <= x[0] <= t_end + 0.03)]
         sm, mx, reasons = summarise(inside)
         if len(sm) < 2:
-            window = "warm-up + timed region + per-kernel steps (timed region shorter than the sampling period)"
+            window = "warm-up + timed region + further identical steps (timed region shorter than the sampling period)"
             sm, mx, reasons = summarise(self.lines)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": reasons, "window": window}
@@ -315,6 +315,12 @@ def main():
         screen_ms.append(s2.ms_screen)
         exact_ms.append(s2.ms_exact)
         parts_ms.append((s2.ms_prep, s2.ms_seed, s2.ms_diag, s2.ms_scan))
+    # a short timed region (small --steps) can end before nvidia-smi has delivered a line: keep the same kernels running
+    # until a few samples exist (outside the timed numbers; `clocks.window` says which samples were used)
+    t_extra = time.perf_counter()
+    while len(sampler.lines) < 4 and time.perf_counter() - t_extra < 1.0:
+        step_device()
+        torch.cuda.synchronize()
     clocks = sampler.stop(t_begin, t_end)
     n_matches = int(d_nout.item())
 
