@@ -132,6 +132,33 @@ def ncu_traffic():
     return None
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Several ranks on one box: run this rank (and therefore first-touch / pin its host buffers) on the CPUs of the NUMA
+    node its GPU hangs off, so that the H2D streams of the ranks do not all cross the socket interconnect.  Best effort:
+    returns the node, or None when the topology cannot be read (GF_BENCH_NUMA=0 disables it)."""
+    if os.environ.get("GF_BENCH_NUMA", "1") == "0":
+        return None
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def cpu_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -214,13 +241,19 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ge.build()
     from genefuserust_b200._abi import gf_batch, gf_map_stats, gf_match
     from genefuserust_b200.host import FusionMapper
 
-    threads = max(1, cpu_threads() // max(1, world))
+    if numa is not None:   # the affinity now covers one NUMA node: share it among the ranks bound to that node
+        import glob
+        n_nodes = max(1, len(glob.glob("/sys/devices/system/node/node[0-9]*")))
+        threads = max(1, cpu_threads() // max(1, -(-world // n_nodes)))
+    else:
+        threads = max(1, cpu_threads() // max(1, world))
     panel = synth.make_panel(scale=a.panel_scale)
     # the first create also pays CUDA context + module load; time a second one for the steady-state index build
     genes = panel.genes()
@@ -431,7 +464,7 @@ def main():
         "survivors_per_step": int(st.n_survivors),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(st.kernel_launches) * a.steps,
         "roofline": roofline, "cpu_baseline": cpu,
-        "setup": {"index_create_s": t_index, "first_index_create_s_incl_cuda_init": t_first, "generate_s": t_gen,
+        "setup": {"numa_node": numa, "index_create_s": t_index, "first_index_create_s_incl_cuda_init": t_first, "generate_s": t_gen,
                   "host_threads": threads},
     }
     json_out.write(json.dumps(line) + "\n")
