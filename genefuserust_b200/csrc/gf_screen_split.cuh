@@ -1,19 +1,27 @@
 /*
  * gf_screen_split.cuh — screen v4: the thread-per-pair screen of gf_screen_tpp.cuh cut into four kernels so that every
- * warp runs ONE class of work (profiles/r01_final_summary.md: the fused kernel averages 15 of 32 active threads because
- * merged/unmerged, seeded/unseeded and forward/reverse pairs diverge inside a warp).
+ * warp runs ONE class of work (the fused kernel averaged 15 of 32 active threads because merged/unmerged,
+ * seeded/unseeded, short/long and forward/reverse pairs diverge inside a warp).
  *
  *   k_prep   thread per pair      convert R1 / rc(R2) to bit-planes, fast_merge (read.rs:313-440), write the 1-2 sequences
- *                                 that will be mapped (merged, or R1 and R2) as bit-planes into a sequence store
- *   k_seed   thread per sequence  8 spread 16-mers -> L2 filter -> first unique one -> ONE HBM table lookup;
- *                                 appends the sequence to the "seeded" or the "unseeded" list
- *   k_diag   thread per seeded sequence    compare with the gene planes along the seed diagonal (exact votes), filter
- *                                          probes for the offsets the diagonal does not explain
- *   k_scan   thread per unseeded sequence  filter probe for every valid even offset
+ *                                 that will be mapped (merged, or R1 and R2) as bit-planes into a sequence store: short
+ *                                 sequences from slot 0 upwards, long (merged) ones from the top downwards
+ *   k_seed   thread per sequence  8 half-word aligned 16-mers of the first 128 bases -> level-1 filter (L2) -> the first
+ *                                 present one -> ONE HBM table lookup; appends the sequence to one of four lists
+ *                                 (seeded / unseeded x short / long), entries reserved once per block
+ *   k_diag   thread per seeded sequence    compare with the interleaved gene planes along the seed diagonal (exact
+ *                                          votes); chunks with offsets the diagonal does not explain are queued per warp
+ *                                          and probed in the filter by all lanes together
+ *   k_scan   thread per unseeded sequence  level-1 filter probe for the valid even offsets until the outcome is decided
  *
- * The drop rule is the one documented in gf_map.cu (count2 <= T - c_d).  Sequence store layout: slot s, plane word k
- * (lo: 0..NW-1, hi: NW.., valid: 2NW..) at words[((s >> 5) * 3*NW + k) * 32 + (s & 31)] — column-major per group of 32
- * slots, so a warp reading consecutive slots is coalesced; meta[s] = {pair, source|olen<<2|diff<<14, len, 0}.
+ * Drop rule (indexer.rs:286-360; a k-mer votes at most once per diagonal): with s_i = sites of the k-mer at even offset i,
+ * P = #{s_i >= 1}, T = sum min(s_i, 2), c_d = votes on the seed diagonal:  count1 <= P,  count1 + count2 <= T,
+ * count2 <= T - c_d.  k_diag drops iff T < need_total or T - c_d < need_minor; k_scan iff P < need_major (T <= 2 P).
+ * Survivors re-run the literal algorithm in k_exact, so the screen only has to be conservative.
+ *
+ * Sequence store layout: slot s, plane word k (lo: 0..NW-1, hi: NW.., valid: 2NW..) at
+ * words[((s >> 5) * 3*NW + k) * 32 + (s & 31)] — column-major per group of 32 slots, so a warp reading consecutive slots is
+ * coalesced; only words 0 .. ceil(len/32) are written; meta[s] = {pair, source|olen<<2|diff<<14, len, 0}.
  */
 #pragma once
 
