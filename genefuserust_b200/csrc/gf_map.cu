@@ -9,11 +9,12 @@
  *   Indexer::map_read / in_required_direction / segment_mask       src/core/indexer.rs:252-679
  *   edit_distance                   src/core/edit_distance.rs:12-197
  *
- * Three kernels:
- *   k_screen  (warp per pair, every pair)   fast_merge decision + a CONSERVATIVE form of map_read's first pass.
- *             Reads are turned into bit-planes with __ballot_sync (1 bit per base and plane), the overlap test
- *             of fast_merge is 32 bases per funnel-shift/xor/popc, 16-mers are cut out of the planes with funnel
- *             shifts, and every even-offset 16-mer is probed in the HBM table (one 32-byte sector per probe).
+ * Kernels:
+ *   screen    every pair: fast_merge decision + a CONSERVATIVE form of map_read's first pass.  Default (reads <= 256 bases):
+ *             the split pipeline k_prep -> k_seed -> k_diag / k_scan of gf_screen_split.cuh (thread per pair / per
+ *             sequence, bit-planes, L2-resident filter + gene planes; the bound is documented there).  Kept for A/B and for
+ *             longer reads: k_screen<.., 2> (warp per pair, same structures), k_screen<.., 1> (one HBM table probe per
+ *             k-mer), k_screen_tpp (the split steps fused in one thread-per-pair kernel), selected by GF_SCREEN.
  *             A sequence is dropped only when it provably fails the vote gate of indexer.rs:353-360:
  *                 T = sum of sites voted, c_d = votes of unique keys on one diagonal d (any d)
  *                 count1 >= c_d and count1 + count2 <= T   =>   count2 <= T - c_d
@@ -23,8 +24,10 @@
  *             gate, second pass mask, mismatch gate, segment_mask, direction gate, make_match, and the
  *             reverse-complement retry of scan_pair_end.  Emits candidate records.
  *   k_verify  (warp per candidate)          calc_distance/calc_ed: bit-parallel (Myers/Hyyro) Levenshtein with
- *             one 64-column block per lane, carries passed lane to lane in a systolic pipeline; exact for any
- *             distance, so the -1/-2 sentinels and the ">= 5" filter downstream see the reference's values.
+ *             one 64-column block per lane, carries passed lane to lane in a systolic pipeline (left and right
+ *             distance side by side in the two half-warps); exact for any distance, so the -1/-2 sentinels and the
+ *             ">= 5" filter downstream see the reference's values.  Also sets the post-filter flags.
+ *   k_adjust_break (warp per clustered match)  FusionResult::adjust_fusion_break, src/core/fusion_result.rs:299-397.
  */
 #include <climits>
 #include <cstdlib>

@@ -8,7 +8,7 @@
  *
  *  - each thread keeps its planes in a private shared-memory column: word k of thread t lives at [k][t], so any
  *    data-dependent index still hits the thread's own bank (never a conflict);
- *  - reads are converted 4 bases at a time (one aligned 32-bit load + funnel shift, PRMT-based classification);
+ *  - reads are converted 32 bases per step: one aligned 256-bit sector load, two 16-base SWAR blocks (block16 below);
  *  - reverse_complement(R2) is produced directly by walking R2 backwards;
  *  - qualities are NOT converted: fast_merge only looks at them where R1 and rc(R2) disagree inside a candidate
  *    overlap that has <= 2 mismatches, so the two bytes are fetched from global memory only then;
