@@ -295,6 +295,9 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
                     const uint32_t wl = (uint32_t)fw[t], wh = (uint32_t)(fw[t] >> 32);
                     if (((okm >> t) & 1u) && (wl & al) == al && (wh & ah) == ah) pm |= 1u << t;
                 }
+                /* an unseeded sequence goes to k_scan, which need not probe these candidates again: it starts from their
+                 * count (bits 0-7 of seed.y) and skips the offsets (bits 8-15: which were valid) */
+                seed_i = pm | (okm << 8);
                 while (pm) { /* usually one iteration: the first present candidate of an on-target read is unique */
                     const int t = __ffs(pm) - 1;
                     pm &= pm - 1u;
@@ -371,14 +374,18 @@ __global__ void __launch_bounds__(256) k_scan(ClassParams P) {
         const int len = (int)m.z, nch = (len + 31) >> 5;
         const uint32_t* col = slot_words<W>(P.st, s);
         uint32_t lo = col[0], hi = col[(size_t)NW * 32], v = col[(size_t)2 * NW * 32];
-        int Pn = 0;
+        /* k_seed already asked the filter about the 16-mers at offsets 0, 16, ..., 112 (seed.y: bits 0-7 present,
+         * bits 8-15 valid = probed) */
+        const uint32_t pre = P.st.seed[s].y, pre_valid = (pre >> 8) & 0xFFu;
+        int Pn = __popc(pre & 0xFFu);
         bool dead = false;
 #pragma unroll 1
         for (int k = 0; k < nch && !dead; k++) {
             const uint32_t nlo = col[(size_t)(k + 1) * 32], nhi = col[(size_t)(NW + k + 1) * 32], nv = col[(size_t)(2 * NW + k + 1) * 32];
             uint32_t om = run16(v, nv) & 0x55555555u;
+            if (k < 4) om &= ~0x00010001u;                          /* offsets 32 k and 32 k + 16: probed by k_seed */
             const int beyond = len - 16 - 32 * (k + 1);            /* last probe offset relative to the next chunk */
-            const int rem_after = beyond >= 0 ? (beyond >> 1) + 1 : 0;
+            const int rem_after = (beyond >= 0 ? (beyond >> 1) + 1 : 0) - (k < 3 ? __popc(pre_valid >> (2 * (k + 1))) : 0);
             while (om) {
                 uint32_t key[4];
                 unsigned long long w[4];
