@@ -281,3 +281,39 @@ def scan_pair(ix: "RefIndexer", s1, q1, s2, q2):
     try_read(s1, 1, True)
     try_read(s2, 2, True)
     return out
+
+
+# ---- report stage: src/core/fusion_result.rs (second, independent restatement; the C++ one is oracle/gf_oracle.cpp) ----
+def get_ref_seq(ref: bytes, start: int, end: int) -> bytes:
+    """fusion_result.rs:770-798"""
+    if (start >= 0 and end <= 0) or (start <= 0 and end >= 0):
+        return b""
+    if abs(start) >= len(ref) or abs(end) >= len(ref):
+        return b""
+    n = abs(end - start) + 1
+    if start < 0:
+        return reverse_complement(ref[-end:-end + n])
+    return ref[start:start + n]
+
+
+def adjust_fusion_break(seq: bytes, read_break: int, left_ref: bytes, right_ref: bytes):
+    """FusionResult::adjust_fusion_break + calc_ed (fusion_result.rs:299-397) for one match ->
+    (shift, left_distance, right_distance), or None where a shifted break leaves the read"""
+    best, shift, out_l, out_r = 0xFFFF, 0, 0, 0
+    for s in range(-3, 4):
+        left_len = read_break + s + 1
+        right_len = len(seq) - left_len
+        if left_len < 0 or right_len < 0:
+            return None
+        left_seq, right_seq = seq[:left_len], seq[left_len:]
+        lc = min(len(left_seq), len(left_ref), 20)
+        rc = min(len(right_seq), len(right_ref), 20)
+        total = levenshtein(left_seq[len(left_seq) - lc:], left_ref[len(left_ref) - lc:]) + \
+            levenshtein(right_seq[:rc], right_ref[:rc])
+        lc = min(left_len, len(left_ref))
+        rc = min(right_len, len(right_ref))
+        le = levenshtein(left_seq[len(left_seq) - lc:], left_ref[len(left_ref) - lc:])
+        re_ = levenshtein(right_seq[:rc], right_ref[:rc])
+        if total < best:
+            best, shift, out_l, out_r = total, s, le, re_
+    return shift, out_l, out_r

@@ -115,3 +115,39 @@ def test_scan_pair_end_policy_in_both_restatements():
     assert [g[:13] for g in got] == want
     assert len(want) > 60 and any(w[2] for w in want) and any(w[1] == 0 for w in want) and any(w[1] == 2 for w in want)
     idx.close()
+
+
+def test_adjust_fusion_break_in_both_restatements():
+    """FusionResult::adjust_fusion_break / get_ref_seq (fusion_result.rs:299-397, 770-798): C++ oracle vs the independent
+    Python port on randomised junction reads (substitutions, indels near the break, wrong breaks, short / empty references)"""
+    import random
+    rng = random.Random(17)
+    rnd = lambda n: bytes(rng.choice(b"ACGT") for _ in range(n))
+    n_shift = 0
+    for it in range(400):
+        gl, gr = rnd(400), rnd(400)
+        ll, rl = rng.randint(25, 140), rng.randint(25, 140)
+        a, b = rng.randint(0, 400 - ll), rng.randint(0, 400 - rl)
+        read = bytearray(gl[a:a + ll] + gr[b:b + rl])
+        for _ in range(rng.choice((0, 0, 1, 2, 3))):
+            p = rng.randrange(len(read))
+            r = rng.random()
+            if r < 0.6:
+                read[p] = rng.choice(b"ACGTN")
+            elif r < 0.8:
+                del read[p]
+            else:
+                read.insert(p, rng.choice(b"ACGT"))
+        read = bytes(read)
+        rb = max(0, min(len(read) - 1, ll - 1 + rng.choice((0, 0, 0, -1, 1, -2, 2, -3, 3, -5, 5))))
+        lref = gl[max(0, a - rng.randint(0, 30)):a + ll] if it % 7 else b""
+        rref = gr[b:b + rl + rng.randint(0, 30)] if it % 11 else gr[b:b + 5]
+        want = ref_port.adjust_fusion_break(read, rb, lref, rref)
+        got = orc.adjust_fusion_break(read, rb, lref, rref)
+        assert got == ((0, 0, 0, 1) if want is None else want + (0,)), (it, rb, len(read), got, want)
+        n_shift += want is not None and want[0] != 0
+        # get_ref_seq on both strands and at the edges
+        s0 = rng.randint(-420, 420)
+        e0 = s0 + rng.randint(-5, 60)
+        assert orc.get_ref_seq(gl, s0, e0) == ref_port.get_ref_seq(gl, s0, e0) or e0 < s0, (s0, e0)
+    assert n_shift > 50
