@@ -1,0 +1,43 @@
+"""Randomised parity fuzz on the GPU: many small panels / read lengths / error rates / fusion rates, the CUDA path
+(PE, SE, list mode) against the CPU oracle.  usage: python tools/fuzz_parity.py [iterations] [seed]"""
+import os, random, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import __graft_entry__ as ge
+ge.build()
+from genefuserust_b200 import synth, ReadBatch
+from genefuserust_b200 import host
+import _oracle as orc
+
+iters = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+t0 = time.time()
+n_pairs = n_matches = 0
+for it in range(iters):
+    scale = rng.choice((0.004, 0.01, 0.02, 0.05))
+    max_genes = rng.choice((None, 8, 24, 60))
+    panel = synth.make_panel(seed=20240201 + it, scale=scale, max_genes=max_genes, n_fusions=rng.choice((4, 20, 60)))
+    L = rng.choice((36, 50, 75, 100, 125, 150, 151, 160, 161, 200, 250, 256, 257, 300))
+    n = rng.choice((2000, 20000, 60000))
+    kw = dict(read_len=L, seed=rng.randrange(1 << 30), p_target=rng.choice((0.2, 0.5, 0.8)), p_fusion=rng.choice((0.001, 0.05, 0.3, 0.7)),
+              sub_rate=rng.choice((0.0, 0.002, 0.01, 0.03)), n_rate=rng.choice((0.0, 0.0005, 0.005)))
+    b = synth.generate_pairs(panel, n, **kw)
+    genes = panel.genes()
+    m = host.FusionMapper.from_gene_spans(genes, device=0)
+    o = orc.OracleIndex(genes)
+    want = o.scan(b, threads=os.cpu_count() or 8)
+    got = [r.astuple() for r in m.scan_pair_end(b)]
+    assert got == want, ("PE", it, scale, max_genes, L, n, kw, len(got), len(want))
+    se = ReadBatch(b.seq2, b.qual2, b.off2)
+    assert [r.astuple() for r in m.scan_single_end(se)] == o.scan(se, threads=os.cpu_count() or 8), ("SE", it, L, kw)
+    if it % 5 == 0:
+        sub = genes[: max(2, len(genes) // 2)]
+        m2 = host.FusionMapper.from_gene_spans(sub, device=0)
+        lst = host.scan_list([m, m2], b)
+        o2 = orc.OracleIndex(sub)
+        assert [r.astuple() for r in lst[0]] == want and [r.astuple() for r in lst[1]] == o2.scan(b, threads=os.cpu_count() or 8), ("list", it)
+        m2.close(); o2.close()
+    n_pairs += n; n_matches += len(want)
+    m.close(); o.close()
+print(f"fuzz ok: {iters} configurations, {n_pairs} pairs, {n_matches} matches, {time.time() - t0:.1f} s")
