@@ -23,6 +23,21 @@ for it in range(iters):
     kw = dict(read_len=L, seed=rng.randrange(1 << 30), p_target=rng.choice((0.2, 0.5, 0.8)), p_fusion=rng.choice((0.001, 0.05, 0.3, 0.7)),
               sub_rate=rng.choice((0.0, 0.002, 0.01, 0.03)), n_rate=rng.choice((0.0, 0.0005, 0.005)))
     b = synth.generate_pairs(panel, n, **kw)
+    if it % 3 == 2:
+        # ragged lengths + lower case / IUPAC / N characters (the converters' slow paths, every alignment class)
+        n = min(n, 20000)
+        alpha = b"acgtnNRYKM."
+        def mutate(seq, qual, off, i):
+            a, e = int(off[i]), int(off[i + 1])
+            cut = rng.randint(0, min(40, e - a)) if rng.random() < 0.7 else 0
+            s_ = bytearray(seq[a:e - cut].tobytes())
+            for _ in range(rng.choice((0, 0, 1, 2, 5))):
+                if s_:
+                    s_[rng.randrange(len(s_))] = rng.choice(alpha)
+            return bytes(s_), qual[a:e - cut].tobytes()
+        r1 = [mutate(b.seq1, b.qual1, b.off1, i) for i in range(n)]
+        r2 = [mutate(b.seq2, b.qual2, b.off2, i) for i in range(n)]
+        b = ReadBatch.from_reads(r1, r2)
     genes = panel.genes()
     m = host.FusionMapper.from_gene_spans(genes, device=0)
     o = orc.OracleIndex(genes)
