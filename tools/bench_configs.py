@@ -5,7 +5,10 @@ multi-CSV list mode (config 4), device-timed on one B200, each checked against t
   python tools/bench_configs.py --sweep 75:50000000 250:50000000     # read_len:pairs
   python tools/bench_configs.py --list 16 --pairs 10000000
   python tools/bench_configs.py --fastq 4000000                      # raw FASTQ text, record splitting on the device
-Prints one JSON line per config."""
+Prints one JSON line per config.
+
+Developer tool (test / measurement infrastructure, not product code): the CPU oracle is loaded here only as the checker of
+the CUDA path's records and as the reported CPU rate; the package under genefuserust_b200/ never touches it."""
 import argparse
 import ctypes as C
 import json

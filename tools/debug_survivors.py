@@ -1,4 +1,5 @@
-"""GPU debug: categorise the screen's survivors (kind of read, merged?, true gate passers per the oracle)."""
+"""GPU debug: categorise the screen's survivors (kind of read, merged?, true gate passers per the oracle).
+Developer tool (test infrastructure): the oracle is used only as the checker."""
 import collections, ctypes as C, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))

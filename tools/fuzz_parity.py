@@ -1,5 +1,8 @@
 """Randomised parity fuzz on the GPU: many small panels / read lengths / error rates / fusion rates, the CUDA path
-(PE, SE, list mode) against the CPU oracle.  usage: python tools/fuzz_parity.py [iterations] [seed]"""
+(PE, SE, list mode) against the CPU oracle.  usage: python tools/fuzz_parity.py [iterations] [seed]
+
+Developer tool (test / measurement infrastructure, not product code): the CPU oracle is loaded here only as the checker of
+the CUDA path's records and as the reported CPU rate; the package under genefuserust_b200/ never touches it."""
 import os, random, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
