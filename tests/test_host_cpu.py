@@ -203,3 +203,19 @@ def test_add_match_bucket_and_sort_order():
     # break 70 first (len 120 before 150; among the two 120s the larger name first), then 60 (equal names: push order kept),
     # then 50 (r4 before r0)
     assert [m.pair_idx for m in ms] == [3, 2, 1, 5, 6, 4, 0]
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/genefuse_gpu.h is the drop-in boundary: it must compile as C99 (plain pointers and sizes, no C++) and agree
+    with the ctypes mirror on the struct sizes"""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "genefuse_gpu.h"\n#include <stdio.h>\nint main(void){ printf("%zu %zu %zu %zu %zu %zu %zu\\n", '
+                   'sizeof(gf_match), sizeof(gf_batch), sizeof(gf_params), sizeof(gf_map_stats), sizeof(gf_break_ref), '
+                   'sizeof(gf_break_job), sizeof(gf_break_out)); return 0; }\n')
+    exe = tmp_path / "hdr"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert sizes == [C.sizeof(_abi.gf_match), C.sizeof(_abi.gf_batch), C.sizeof(_abi.gf_params), C.sizeof(_abi.gf_map_stats),
+                     C.sizeof(_abi.gf_break_ref), C.sizeof(_abi.gf_break_job), C.sizeof(_abi.gf_break_out)]
