@@ -151,12 +151,32 @@ class gf_break_out(C.Structure):
     _fields_ = [("shift", C.c_int32), ("left_distance", C.c_int32), ("right_distance", C.c_int32), ("status", C.c_int32)]
 
 
+class gf_ref_contig(C.Structure):
+    _fields_ = [("seq", C.c_void_p), ("len", C.c_uint64)]
+
+
+class gf_reference_info(C.Structure):
+    _fields_ = [("n_contigs", C.c_uint64), ("n_bases", C.c_uint64), ("key_positions", C.c_uint64 * 4),
+                ("short_contigs", C.c_uint64), ("h2d_bytes", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("ms_total", C.c_float), ("ms_scan", C.c_float)]
+
+
+class gf_alignable_result(C.Structure):
+    _fields_ = [("key_positions", C.c_uint64 * 4), ("n_removed", C.c_uint64), ("panic_seq", C.c_int64),
+                ("bloom_bits", C.c_uint32), ("panic_stage", C.c_int32)]
+
+    def astuple(self):
+        return (tuple(int(x) for x in self.key_positions), int(self.n_removed), int(self.panic_seq), int(self.bloom_bits),
+                int(self.panic_stage))
+
+
 # every symbol include/genefuse_gpu.h declares (tests check the .so exports all of them)
 EXPORTS = (
     "gf_last_error", "gf_abi_version", "gf_device_count", "gf_default_params", "gf_index_create",
     "gf_index_destroy", "gf_index_get_info", "gf_index_lookup", "gf_map_pairs", "gf_map_pairs_device",
     "gf_sort_matches", "gf_get_map_stats", "gf_fast_merge", "gf_map_fastq", "gf_multi_create", "gf_multi_destroy",
     "gf_multi_map_pairs", "gf_adjust_fusion_break", "gf_list_map_pairs", "gf_map_pairs_device_list",
+    "gf_reference_create", "gf_reference_destroy", "gf_reference_get_info", "gf_alignable_filter",
 )
 
 _lib = None
@@ -214,5 +234,13 @@ def load_library():
     lib.gf_adjust_fusion_break.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, P(gf_break_ref), C.c_uint32, P(gf_break_job),
                                            C.c_uint64, P(gf_break_out)]
     lib.gf_adjust_fusion_break.restype = C.c_int
+    lib.gf_reference_create.argtypes = [P(gf_ref_contig), C.c_uint32, C.c_int, P(C.c_void_p)]
+    lib.gf_reference_create.restype = C.c_int
+    lib.gf_reference_destroy.argtypes = [C.c_void_p]
+    lib.gf_reference_destroy.restype = None
+    lib.gf_reference_get_info.argtypes = [C.c_void_p, P(gf_reference_info)]
+    lib.gf_reference_get_info.restype = C.c_int
+    lib.gf_alignable_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, P(gf_alignable_result)]
+    lib.gf_alignable_filter.restype = C.c_int
     _lib = lib
     return lib

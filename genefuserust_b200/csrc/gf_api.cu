@@ -36,9 +36,61 @@ int check_flags(const GfHostSlot& h) {
     return GF_OK;
 }
 
+/* gf_map_pairs_device* return with work in flight on the caller's stream; that work uses the handle's workspace
+ * (counters, survivor list, sequence store, vote tables, the pinned result slot).  Every entry point that touches the
+ * workspace first makes its own stream wait for it. */
+int wait_prior_device_work(gf_index* idx, cudaStream_t st) {
+    if (idx->busy) GF_CUDA_TRY(cudaStreamWaitEvent(st, idx->ev_busy, 0));
+    return GF_OK;
+}
+int mark_device_work(gf_index* idx, cudaStream_t st) {
+    GF_CUDA_TRY(cudaEventRecord(idx->ev_busy, st));
+    idx->busy = true;
+    return GF_OK;
+}
+
+/* Host offsets of one mate: ascending, every record at most `limit` long.  Returns the longest record in *max_len.
+ * (Several threads: ~1 ms per 10 M reads.) */
+int scan_offsets(const uint64_t* off1, const uint64_t* off2, uint64_t n, uint64_t limit, uint64_t* max_len) {
+    const unsigned nt = n < (1u << 16) ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<uint64_t> part(nt, 0);
+    std::vector<char> bad(nt, 0);
+    auto work = [&](unsigned t) {
+        uint64_t mx = 0;
+        bool b = false;
+        for (uint64_t i = n * t / nt; i < n * (t + 1) / nt; i++) {
+            const uint64_t a = off1[i], e = off1[i + 1];
+            b |= e < a;
+            mx = std::max(mx, e - a);
+            if (off2) {
+                const uint64_t a2 = off2[i], e2 = off2[i + 1];
+                b |= e2 < a2;
+                mx = std::max(mx, e2 - a2);
+            }
+        }
+        part[t] = mx;
+        bad[t] = b;
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    uint64_t mx = 0;
+    for (unsigned t = 0; t < nt; t++) {
+        if (bad[t]) return fail(GF_E_INVALID, "offsets are not ascending");
+        mx = std::max(mx, part[t]);
+    }
+    if (mx > limit) return fail(GF_E_INVALID, "a read is longer than the kernel capacity (max_len hint too small, or > 1024 bases)");
+    *max_len = mx;
+    return GF_OK;
+}
+
 void destroy_handle(gf_index* idx) {
     if (!idx) return;
     cudaSetDevice(idx->device);
+    if (idx->busy && idx->ev_busy) cudaEventSynchronize(idx->ev_busy); /* device-batch work still in flight on a caller's stream */
     if (idx->stream) cudaStreamSynchronize(idx->stream);
     if (idx->copy_stream) cudaStreamSynchronize(idx->copy_stream);
     cudaFree(idx->d_table);
@@ -71,9 +123,7 @@ void destroy_handle(gf_index* idx) {
         if (e) cudaEventDestroy(e);
     if (idx->stream) cudaStreamDestroy(idx->stream);
     if (idx->copy_stream) cudaStreamDestroy(idx->copy_stream);
-    if (idx->side_stream) cudaStreamDestroy(idx->side_stream);
-    if (idx->ev_fork) cudaEventDestroy(idx->ev_fork);
-    if (idx->ev_join) cudaEventDestroy(idx->ev_join);
+    if (idx->ev_busy) cudaEventDestroy(idx->ev_busy);
     delete idx;
 }
 
@@ -119,24 +169,18 @@ int gf_index_create(const gf_gene_span* genes, uint32_t n_genes, const gf_params
     if (device < 0 || device >= ndev) return fail(GF_E_INVALID, "device index out of range");
     GF_CUDA_TRY(cudaSetDevice(device));
 
-    /* Index probes are random 32-byte sectors.  The default L2 fetch granularity pulls the whole 128-byte line
-     * from HBM on a miss (ncu: 4 DRAM sectors per probe, profiles/r01_screen_v1_summary.md); ask for 32 bytes.
-     * It is a per-context performance hint only.  GF_L2_FETCH_GRANULARITY=0 leaves the limit untouched. */
-    {
-        size_t gran = 32;
-        if (const char* e = getenv("GF_L2_FETCH_GRANULARITY")) gran = (size_t)atoi(e);
-        if (gran == 32 || gran == 64 || gran == 128) {
+    /* GF_L2_FETCH_GRANULARITY=32|64|128 (opt-in, experiments only): sets cudaLimitMaxL2FetchGranularity for the whole
+     * primary context.  Measured: it does not change the DRAM sectors fetched per random bucket probe
+     * (profiles/r01_screen_v1_summary.md), so the library leaves the context's limit alone by default. */
+    if (const char* e = getenv("GF_L2_FETCH_GRANULARITY")) {
+        const size_t gran = (size_t)atoi(e);
+        if (gran == 32 || gran == 64 || gran == 128)
             if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) cudaGetLastError();
-        }
     }
 
     gf_index* idx = new gf_index();
     idx->device = device;
     idx->params = p;
-    if (const char* e = getenv("GF_SCREEN")) { int v = atoi(e); if (v >= 1 && v <= 4) idx->screen_version = v; }
-    if (const char* e = getenv("GF_CONCURRENT")) idx->concurrent = atoi(e) != 0;
-    if (const char* e = getenv("GF_CC_DIAG")) { int v = atoi(e); if (v >= 1 && v <= 8) idx->cc_diag = v; }
-    if (const char* e = getenv("GF_CC_SCAN")) { int v = atoi(e); if (v >= 1 && v <= 8) idx->cc_scan = v; }
     int rc = GF_OK;
     do {
         cudaDeviceProp prop;
@@ -150,7 +194,8 @@ int gf_index_create(const gf_gene_span* genes, uint32_t n_genes, const gf_params
         bool ok = cudaEventCreate(&idx->ev_start) == cudaSuccess && cudaEventCreate(&idx->ev_screen) == cudaSuccess &&
                   cudaEventCreate(&idx->ev_exact) == cudaSuccess && cudaEventCreate(&idx->ev_end) == cudaSuccess &&
                   cudaEventCreate(&idx->ev_prep) == cudaSuccess && cudaEventCreate(&idx->ev_seed) == cudaSuccess &&
-                  cudaEventCreate(&idx->ev_diag) == cudaSuccess;
+                  cudaEventCreate(&idx->ev_diag) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&idx->ev_busy, cudaEventDisableTiming) == cudaSuccess;
         for (auto& s : idx->stage)
             ok = ok && cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) == cudaSuccess;
@@ -230,26 +275,19 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
     const uint64_t per = (n + n_chunks - 1) / n_chunks;
     n_chunks = (n + per - 1) / per;
 
-    /* max_len hint missing: the host offsets are at hand, so the longest read is found here (several threads; ~1 ms per
-     * 10 M reads) instead of falling back to the long-read kernels */
-    uint32_t max_len = in->max_len;
-    if (max_len == 0) {
-        const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-        std::vector<uint64_t> part(nt, 0);
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; t++)
-            th.emplace_back([&, t]() {
-                uint64_t mx = 0;
-                for (uint64_t i = n * t / nt; i < n * (t + 1) / nt; i++) {
-                    mx = std::max(mx, off1[i + 1] - off1[i]);
-                    if (pe) mx = std::max(mx, off2[i + 1] - off2[i]);
-                }
-                part[t] = mx;
-            });
-        for (auto& x : th) x.join();
-        uint64_t mx = 1;
-        for (uint64_t v : part) mx = std::max(mx, v);
-        max_len = (uint32_t)std::min<uint64_t>(mx, 0xFFFFFFFFull);
+    /* the host offsets are at hand: check that they ascend and find the longest read here (it selects the kernel
+     * capacity; a read longer than the caller's hint, or than 1024 bases, fails the call before anything is launched) */
+    uint32_t max_len;
+    {
+        uint64_t mx = 0;
+        const uint64_t limit = in->max_len ? std::min<uint64_t>(in->max_len, 1024) : 1024;
+        int r = scan_offsets(off1, pe ? off2 : nullptr, n, limit, &mx);
+        if (r != GF_OK) return r;
+        max_len = (uint32_t)std::max<uint64_t>(mx, 1);
+    }
+    for (uint32_t h = 0; h < nh; h++) {
+        int r = wait_prior_device_work(hs[h], idx->stream);
+        if (r != GF_OK) return r;
     }
 
     std::vector<unsigned long long> launches0(nh);
@@ -263,7 +301,7 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
     const uint8_t *zq1 = nullptr, *zq2 = nullptr;
     {
         const char* e = getenv("GF_ZEROCOPY_QUAL");
-        bool want = !(e && atoi(e) == 0) && idx->screen_version >= 3 && max_len != 0 && max_len <= 256;
+        bool want = !(e && atoi(e) == 0) && max_len != 0 && max_len <= 256;
         auto mapped = [](const void* p) -> const uint8_t* {
             cudaPointerAttributes at;
             if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -376,6 +414,7 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
     float ms = 0;
     GF_CUDA_TRY(cudaEventElapsedTime(&ms, idx->ev_start, idx->ev_end));
     rc = GF_OK;
+    for (uint32_t h = 0; h < nh; h++) hs[h]->busy = false; /* the stream waited for it and has drained */
     for (uint32_t h = 0; h < nh; h++) {
         gf_map_stats& st = hs[h]->stats;
         st.ms_total = ms; /* of the whole call (all indices) */
@@ -463,8 +502,12 @@ int gf_map_pairs_device_list(gf_index* const* idx, uint32_t n_idx, const gf_batc
     db.bytes2 = in_dev->bytes2;
     db.max_len = in_dev->max_len;
     for (uint32_t h = 0; h < n_idx; h++) {
-        gf_index* x = idx[h];
         if (!d_n_out[h]) return fail(GF_E_INVALID, "NULL argument");
+        rc = wait_prior_device_work(idx[h], st);
+        if (rc != GF_OK) return rc;
+    }
+    for (uint32_t h = 0; h < n_idx; h++) {
+        gf_index* x = idx[h];
         const unsigned long long launches0 = x->launches;
         rc = gf_map_device_batch(x, db, d_out[h], out_cap, (unsigned long long*)d_n_out[h], st, true, h ? idx[0] : nullptr);
         if (rc != GF_OK) return rc;
@@ -476,6 +519,10 @@ int gf_map_pairs_device_list(gf_index* const* idx, uint32_t n_idx, const gf_batc
         x->stats.n_pairs = in_dev->n;
         x->stats.kernel_launches = x->launches - launches0;
         x->stats_pending = true;
+    }
+    for (uint32_t h = 0; h < n_idx; h++) { /* after the LAST handle's work: the shared sequence store is read by all of them */
+        rc = mark_device_work(idx[h], st);
+        if (rc != GF_OK) return rc;
     }
     return GF_OK;
 }
@@ -502,6 +549,8 @@ int gf_map_pairs_device(gf_index* idx, const gf_batch* in_dev, gf_match* d_out, 
     db.pair_base = 0;
     db.max_len = in_dev->max_len;
     const unsigned long long launches0 = idx->launches;
+    rc = wait_prior_device_work(idx, st);
+    if (rc != GF_OK) return rc;
     rc = gf_map_device_batch(idx, db, d_out, out_cap, (unsigned long long*)d_n_out, st, true);
     if (rc != GF_OK) return rc;
     GfHostSlot* h = &idx->h_slots[2];
@@ -512,7 +561,7 @@ int gf_map_pairs_device(gf_index* idx, const gf_batch* in_dev, gf_match* d_out, 
     idx->stats.n_pairs = in_dev->n;
     idx->stats.kernel_launches = idx->launches - launches0;
     idx->stats_pending = true;
-    return GF_OK;
+    return mark_device_work(idx, st);
 }
 
 int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8_t* fq2, uint64_t bytes2, gf_match* out,
@@ -529,6 +578,7 @@ int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8
     const bool pe = fq2 != nullptr;
     cudaStream_t st = idx->stream;
     GfStage& sg = idx->stage[0];
+    { int r = wait_prior_device_work(idx, st); if (r != GF_OK) return r; }
     GF_CUDA_TRY(cudaEventRecord(idx->ev_start, st));
     /* raw text -> device (the sequence and quality "arenas" are the text itself) */
     GF_CUDA_TRY(sg.seq1.reserve(bytes1 + 32));
@@ -574,6 +624,7 @@ int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8
     GF_CUDA_TRY(cudaMemcpyAsync(&h->n_out, sg.nout.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     GF_CUDA_TRY(cudaEventRecord(idx->ev_end, st));
     GF_CUDA_TRY(cudaEventSynchronize(idx->ev_end));
+    idx->busy = false;
     rc = check_flags(*h);
     if (rc != GF_OK) return rc;
     accumulate(idx->stats, *h);
@@ -619,6 +670,7 @@ int gf_get_map_stats(const gf_index* cidx, gf_map_stats* out) {
             GF_CUDA_TRY(cudaEventElapsedTime(&idx->stats.ms_scan, idx->ev_diag, idx->ev_screen));
         }
         idx->stats_pending = false;
+        idx->busy = false; /* ev_end was recorded after the work ev_busy stands for */
         rc = check_flags(h);
         if (rc == GF_OK && h.counters.n_ref_panic)
             rc = fail(GF_E_REF_PANIC, "a candidate needs an edit distance over more than 640 columns (reference panics)");
@@ -652,6 +704,7 @@ int gf_adjust_fusion_break(gf_index* idx, const uint8_t* bytes, uint64_t n_bytes
     GF_CUDA_TRY(s.out.reserve(sizeof(gf_break_out) * n_jobs + 16));
     GF_CUDA_TRY(idx->ws_counters.reserve(sizeof(GfMapCounters)));
     cudaStream_t st = idx->stream;
+    { int r = wait_prior_device_work(idx, st); if (r != GF_OK) return r; }
     unsigned int* d_undef = &idx->ws_counters.as<GfMapCounters>()->n_ref_panic;
     GF_CUDA_TRY(cudaMemsetAsync(idx->ws_counters.p, 0, sizeof(GfMapCounters), st));
     if (n_bytes) GF_CUDA_TRY(cudaMemcpyAsync(s.seq1.p, bytes, n_bytes, cudaMemcpyHostToDevice, st));
@@ -678,6 +731,11 @@ int gf_fast_merge(gf_index* idx, const gf_batch* in, gf_merge_info* out) {
     GF_CUDA_TRY(cudaSetDevice(idx->device));
     const uint64_t n = in->n;
     const uint64_t b1 = in->off1[0], e1 = in->off1[n], b2 = in->off2[0], e2 = in->off2[n];
+    uint64_t mx = 0;
+    rc = scan_offsets(in->off1, in->off2, n, in->max_len ? std::min<uint64_t>(in->max_len, 1024) : 1024, &mx);
+    if (rc != GF_OK) return rc;
+    rc = wait_prior_device_work(idx, idx->stream);
+    if (rc != GF_OK) return rc;
     GfStage& s = idx->stage[0];
     GF_CUDA_TRY(s.seq1.reserve(e1 - b1 + 16));
     GF_CUDA_TRY(s.qual1.reserve(e1 - b1 + 16));
@@ -705,7 +763,7 @@ int gf_fast_merge(gf_index* idx, const gf_batch* in, gf_merge_info* out) {
     db.base2 = b2;
     db.bytes1 = e1 - b1;
     db.bytes2 = e2 - b2;
-    db.max_len = in->max_len;
+    db.max_len = (uint32_t)std::max<uint64_t>(mx, 1);
     rc = gf_fast_merge_device(idx, db, s.out.as<gf_merge_info>(), st);
     if (rc != GF_OK) return rc;
     GF_CUDA_TRY(cudaMemcpyAsync(out, s.out.p, sizeof(gf_merge_info) * n, cudaMemcpyDeviceToHost, st));

@@ -44,19 +44,14 @@ struct GfDevIndex {
     const uint8_t* gene_rev;    /* Gene::is_reversed() per gene */
     const uint16_t* granule_contig; /* contig owning arena granule (goff >> 11); genes are >= 2304 bytes apart, so a
                                        2048-byte granule never holds bases of two genes */
-    /* L2-resident screen structures (gf_index.cu: k_gene_planes, k_window_class, filter bits in k_build_table) */
-    const uint32_t* g_lo;       /* gene arena as bit-planes, bit (goff & 31) of word (goff >> 5): low code bit */
-    const uint32_t* g_hi;       /* high code bit */
-    const uint32_t* g_v;        /* base is upper-case ACGT */
-    const uint32_t* g_cf;       /* 3 planes (stride g_cstride): bit b of the number of sites (1..7) the forward k-mer
-                                   of the window starting at goff votes for, 0 when that window is not an indexed
-                                   site or its key is HIGH */
-    const uint32_t* g_cr;       /* same for the reverse-complement k-mer of that window */
-    uint32_t g_cstride;
-    const uint32_t* g_if;       /* the same planes interleaved, 8 words (one 32-byte sector) per arena word w:
-                                   {lo, hi, valid, cf bit0, cf bit1, cf bit2, 0, 0} — k_diag fetches everything it needs
-                                   about 32 gene positions with ONE 256-bit load (one L1 wavefront instead of six) */
-    const uint32_t* g_ir;       /* {lo, hi, valid, cr bit0, cr bit1, cr bit2, 0, 0} for reverse-strand diagonals */
+    /* L2-resident screen structures (gf_index.cu: k_gene_planes, k_window_class, filter bits in k_build_table).
+     * The gene arena as interleaved bit-plane entries, 8 words (one 32-byte sector) per 32 arena positions (word w =
+     * goff >> 5, bit goff & 31): {lo, hi, valid, cnt bit0, cnt bit1, cnt bit2, 0, 0}; lo / hi = code bit planes, valid =
+     * upper-case ACGT, cnt = the number of sites (1..7) the forward k-mer of the window STARTING there votes for (0 when
+     * that window is not an indexed site or its key is HIGH).  One 256-bit load fetches everything the diagonal
+     * comparison needs about 32 gene positions. */
+    const uint32_t* g_if;       /* counts of the forward k-mer */
+    const uint32_t* g_ir;       /* {lo, hi, valid, ...} with the counts of the reverse-complement k-mer of that window */
     const unsigned long long* filter; /* blocked Bloom filter over all non-HIGH keys, 64-bit blocks */
     uint32_t filter_words;
     const unsigned long long* filter_multi; /* second-level filter: NORMAL (dupe) keys only */

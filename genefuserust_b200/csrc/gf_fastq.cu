@@ -36,7 +36,8 @@ __device__ __forceinline__ uint32_t newline_mask16(const uint8_t* __restrict__ t
     }
     return m;
 }
-__global__ void k_nl_count(const uint8_t* __restrict__ text, uint64_t bytes, uint32_t* __restrict__ tile_counts) {
+__global__ void k_nl_count(const uint8_t* __restrict__ text, uint64_t bytes, uint32_t* __restrict__ tile_counts,
+                           unsigned long long* __restrict__ total) {
     __shared__ uint32_t ws[NL_THREADS / 32];
     uint64_t pos = (uint64_t)blockIdx.x * NL_TILE + (uint64_t)threadIdx.x * 16;
     uint32_t c = pos < bytes ? __popc(newline_mask16(text, bytes, pos)) : 0u;
@@ -47,6 +48,7 @@ __global__ void k_nl_count(const uint8_t* __restrict__ text, uint64_t bytes, uin
         uint32_t t = 0;
         for (int w = 0; w < NL_THREADS / 32; w++) t += ws[w];
         tile_counts[blockIdx.x] = t;
+        if (t) atomicAdd(total, (unsigned long long)t); /* 64-bit: the u32 scan below must not wrap unnoticed */
     }
 }
 __global__ void k_nl_write(const uint8_t* __restrict__ text, uint64_t bytes, const uint32_t* __restrict__ tile_off,
@@ -101,17 +103,27 @@ int gf_fastq_parse_device(const uint8_t* d_text, uint64_t bytes, GfFastqTable* o
     out->max_len = 0;
     if (bytes == 0) return GF_OK;
     const uint64_t n_tiles = (bytes + NL_TILE - 1) / NL_TILE;
-    GF_CUDA_TRY(out->cnt.reserve(sizeof(uint32_t) * (n_tiles + 2)));
+    if (n_tiles > 0x7FFFFFFFull) { gf_set_error("FASTQ buffer too large for one call (> 8 TiB)"); return GF_E_LIMIT; }
+    GF_CUDA_TRY(out->cnt.reserve(sizeof(uint32_t) * (n_tiles + 2) + 16));
     GF_CUDA_TRY(out->off.reserve(sizeof(uint32_t) * (n_tiles + 1)));
     GF_CUDA_TRY(out->tmp.reserve(sizeof(uint32_t) * gf_scan_tmp_elems(n_tiles)));
     uint32_t *d_cnt = out->cnt.as<uint32_t>(), *d_off = out->off.as<uint32_t>(), *d_tmp = out->tmp.as<uint32_t>();
-    k_nl_count<<<(unsigned)n_tiles, NL_THREADS, 0, st>>>(d_text, bytes, d_cnt);
+    /* 64-bit newline total behind the tile counts (8-byte aligned) */
+    unsigned long long* d_total = reinterpret_cast<unsigned long long*>(d_cnt + ((n_tiles + 2 + 1) & ~1ull));
+    GF_CUDA_TRY(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
+    k_nl_count<<<(unsigned)n_tiles, NL_THREADS, 0, st>>>(d_text, bytes, d_cnt, d_total);
     GF_CUDA_TRY(gf_exclusive_scan_u32(d_cnt, d_off, n_tiles, d_tmp, st));
     uint32_t n_nl = 0;
+    unsigned long long n_nl64 = 0;
     uint8_t last = 0;
     GF_CUDA_TRY(cudaMemcpyAsync(&n_nl, d_off + n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    GF_CUDA_TRY(cudaMemcpyAsync(&n_nl64, d_total, sizeof(n_nl64), cudaMemcpyDeviceToHost, st));
     GF_CUDA_TRY(cudaMemcpyAsync(&last, d_text + bytes - 1, 1, cudaMemcpyDeviceToHost, st));
     GF_CUDA_TRY(cudaStreamSynchronize(st));
+    if (n_nl64 != (unsigned long long)n_nl) {
+        gf_set_error("FASTQ buffer holds 2^32 or more lines: pass it in pieces (gf_fastq_stream_*)");
+        return GF_E_LIMIT;
+    }
     /* a non-empty unterminated last line still counts as a line (read_line returns > 0): virtual newline at `bytes` */
     const uint64_t n_lines = (uint64_t)n_nl + (last != '\n' ? 1 : 0);
     GF_CUDA_TRY(out->nl.reserve(sizeof(unsigned long long) * (n_lines + 2)));

@@ -387,6 +387,15 @@ struct PhaseTimer { /* GF_DEBUG_TIMING=1: host wall clock per build phase on std
 }  // namespace
 
 namespace {
+/* error paths return through GF_CUDA_TRY: temporaries and events are released by these guards */
+struct DevTmp {
+    void* p = nullptr;
+    ~DevTmp() { if (p) cudaFree(p); }
+};
+struct EventGuard {
+    cudaEvent_t e = nullptr;
+    ~EventGuard() { if (e) cudaEventDestroy(e); }
+};
 /* one device allocation for every temporary of the build (cudaMalloc/cudaFree are slow, synchronising calls) */
 struct BuildWorkspace {
     char* base = nullptr;
@@ -463,9 +472,10 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
         if (genes[g].len)
             for (uint64_t q = idx->gene_start[g] >> 11; q <= ((uint64_t)idx->gene_start[g] + genes[g].len - 1) >> 11; q++)
                 granule[q] = (uint16_t)g;
-    cudaEvent_t e0, e1;
-    GF_CUDA_TRY(cudaEventCreate(&e0));
-    GF_CUDA_TRY(cudaEventCreate(&e1));
+    EventGuard g0, g1;
+    GF_CUDA_TRY(cudaEventCreate(&g0.e));
+    GF_CUDA_TRY(cudaEventCreate(&g1.e));
+    const cudaEvent_t e0 = g0.e, e1 = g1.e;
     GF_CUDA_TRY(cudaMalloc(&idx->d_gene_ascii, arena_len));
     GF_CUDA_TRY(cudaMalloc(&idx->d_gene_start, sizeof(uint32_t) * (n_genes + 1)));
     GF_CUDA_TRY(cudaMalloc(&idx->d_gene_len, sizeof(uint32_t) * (n_genes + 1)));
@@ -566,9 +576,9 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     GF_CUDA_TRY(cudaMemsetAsync(idx->d_table, 0xFF, n_buckets * 32, st));
     GF_CUDA_TRY(cudaMalloc(&idx->d_dupes, sizeof(uint32_t) * ((size_t)n_dupes + 8)));
     unsigned int* d_maxdisp = (unsigned int*)(d_stats + 6);
-    /* blocked Bloom filter, GF_FILTER_BITS (default 8: the filter must stay L2-resident next to the gene planes) bits per key, whole 64-bit words, at least 1024 words */
-    int filter_bits = 8;
-    if (const char* e = getenv("GF_FILTER_BITS")) { int v = atoi(e); if (v >= 4 && v <= 32) filter_bits = v; }
+    /* blocked Bloom filter, 8 bits per key (the filter must stay L2-resident next to the gene planes), whole 64-bit words,
+     * at least 1024 words */
+    const int filter_bits = 8;
     const uint32_t filter_words = (uint32_t)std::max<uint64_t>(1024, (n_keys * (uint64_t)filter_bits + 63) / 64);
     /* + the multi filter behind it: 16 bits per NORMAL key */
     const uint32_t filter_multi_words = (uint32_t)std::max<uint64_t>(1024, (h_stats[2] * 16 + 63) / 64);
@@ -607,36 +617,31 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     idx->dev.filter_multi = d_filter_multi;
     idx->dev.filter_multi_words = filter_multi_words;
 
-    /* gene bit-planes (lo, hi, valid) + per-window site-count planes (3 bits x 2 strands) */
+    /* gene bit-planes (lo, hi, valid) + per-window site-count planes (3 bits x 2 strands), built as 9 separate planes in a
+     * temporary and interleaved into the two resident arrays g_if / g_ir (one 32-byte entry per arena word and strand; the
+     * allocation is 256-byte aligned, so every entry is sector aligned).  72 pad words: the longest diagonal walk reads
+     * (2048 + 64) / 32 + 2 words beyond its start. */
     const uint32_t n_pw = (uint32_t)((arena_len + 31) / 32);
     const size_t plane_stride = ((size_t)n_pw + 72 + 7) & ~(size_t)7;
-    GF_CUDA_TRY(cudaMalloc(&idx->d_planes, sizeof(uint32_t) * plane_stride * 25));
-    GF_CUDA_TRY(cudaMemsetAsync(idx->d_planes, 0, sizeof(uint32_t) * plane_stride * 25, st));
-    uint32_t* pl = (uint32_t*)idx->d_planes;
-    idx->dev.g_lo = pl;
-    idx->dev.g_hi = pl + plane_stride;
-    idx->dev.g_v = pl + 2 * plane_stride;
-    idx->dev.g_cf = pl + 3 * plane_stride;
-    idx->dev.g_cr = pl + 6 * plane_stride;
-    idx->dev.g_cstride = (uint32_t)plane_stride;
+    DevTmp tmp_planes;
+    GF_CUDA_TRY(cudaMalloc(&tmp_planes.p, sizeof(uint32_t) * plane_stride * 9));
+    GF_CUDA_TRY(cudaMemsetAsync(tmp_planes.p, 0, sizeof(uint32_t) * plane_stride * 9, st));
+    GF_CUDA_TRY(cudaMalloc(&idx->d_planes, sizeof(uint32_t) * plane_stride * 16));
+    uint32_t* pl = (uint32_t*)tmp_planes.p;
+    uint32_t* gi = (uint32_t*)idx->d_planes;
     k_gene_planes<<<(n_pw + 255) / 256, 256, 0, st>>>((const uint8_t*)idx->d_gene_ascii, arena_len, n_pw, pl,
                                                       pl + plane_stride, pl + 2 * plane_stride);
     k_window_class<<<ex_blocks, EX_THREADS, 0, st>>>(idx->dev, (const uint8_t*)idx->d_gene_ascii, arena_len,
                                                      pl + 3 * plane_stride, pl + 6 * plane_stride,
                                                      (uint32_t)plane_stride);
-    /* interleaved copies for k_diag: one sector per arena word and strand (9 planes + 2 x 8 words = 25 strides; the
-     * allocation is 256-byte aligned and 9 * plane_stride is a multiple of 8 words, so every entry is 32-byte aligned) */
-    idx->dev.g_if = pl + 9 * plane_stride;
-    idx->dev.g_ir = pl + 17 * plane_stride;
-    k_interleave_planes<<<(unsigned)((plane_stride + 255) / 256), 256, 0, st>>>(pl, (uint32_t)plane_stride, pl + 9 * plane_stride,
-                                                                                  pl + 17 * plane_stride);
+    idx->dev.g_if = gi;
+    idx->dev.g_ir = gi + 8 * plane_stride;
+    k_interleave_planes<<<(unsigned)((plane_stride + 255) / 256), 256, 0, st>>>(pl, (uint32_t)plane_stride, gi, gi + 8 * plane_stride);
     GF_CUDA_TRY(cudaGetLastError());
     GF_CUDA_TRY(cudaEventRecord(e1, st));
     GF_CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0;
     GF_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
 
     pt.mark("gene planes + window class");
     gf_index_info& inf = idx->info;
@@ -650,23 +655,20 @@ int gf_build_index_device(gf_index* idx, const gf_gene_span* genes, uint32_t n_g
     inf.max_displacement = h_maxdisp;
     inf.gene_bytes = gene_bytes;
     inf.device_bytes = n_buckets * 32 + sizeof(uint32_t) * ((size_t)n_dupes + 8) + arena_len + 9ull * (n_genes + 1) +
-                       sizeof(uint32_t) * plane_stride * 25 + sizeof(unsigned long long) * ((size_t)filter_words + filter_multi_words);
+                       sizeof(uint32_t) * plane_stride * 16 + sizeof(unsigned long long) * ((size_t)filter_words + filter_multi_words);
     inf.build_ms = ms;
     return GF_OK;
 }
 
 int gf_lookup_device(gf_index* idx, const uint32_t* kmers, uint64_t n, gf_lookup* out) {
     if (n == 0) return GF_OK;
-    uint32_t* d_k = nullptr;
-    gf_lookup* d_o = nullptr;
-    GF_CUDA_TRY(cudaMalloc(&d_k, sizeof(uint32_t) * n));
-    GF_CUDA_TRY(cudaMalloc(&d_o, sizeof(gf_lookup) * n));
-    GF_CUDA_TRY(cudaMemcpyAsync(d_k, kmers, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, idx->stream));
-    k_lookup<<<(unsigned)((n + 127) / 128), 128, 0, idx->stream>>>(idx->dev, d_k, n, d_o);
+    DevTmp k, o;
+    GF_CUDA_TRY(cudaMalloc(&k.p, sizeof(uint32_t) * n));
+    GF_CUDA_TRY(cudaMalloc(&o.p, sizeof(gf_lookup) * n));
+    GF_CUDA_TRY(cudaMemcpyAsync(k.p, kmers, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, idx->stream));
+    k_lookup<<<(unsigned)((n + 127) / 128), 128, 0, idx->stream>>>(idx->dev, (const uint32_t*)k.p, n, (gf_lookup*)o.p);
     GF_CUDA_TRY(cudaGetLastError());
-    GF_CUDA_TRY(cudaMemcpyAsync(out, d_o, sizeof(gf_lookup) * n, cudaMemcpyDeviceToHost, idx->stream));
+    GF_CUDA_TRY(cudaMemcpyAsync(out, o.p, sizeof(gf_lookup) * n, cudaMemcpyDeviceToHost, idx->stream));
     GF_CUDA_TRY(cudaStreamSynchronize(idx->stream));
-    GF_CUDA_TRY(cudaFree(d_k));
-    GF_CUDA_TRY(cudaFree(d_o));
     return GF_OK;
 }

@@ -90,9 +90,9 @@ struct gf_index {
 
     std::mutex mu; /* serialises calls on one handle */
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaStream_t side_stream = nullptr;                 /* k_scan next to k_diag (GF_CONCURRENT) */
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int concurrent = 0, cc_diag = 2, cc_scan = 3;       /* blocks per SM of k_diag / k_scan when they run side by side */
+    cudaEvent_t ev_busy = nullptr; /* recorded at the end of every unsynchronised device-batch call (gf_map_pairs_device*):
+                                      the next entry point that touches the handle's workspace waits for it on its stream */
+    bool busy = false;
     cudaEvent_t ev_start = nullptr, ev_screen = nullptr, ev_exact = nullptr, ev_end = nullptr;
     cudaEvent_t ev_prep = nullptr, ev_seed = nullptr, ev_diag = nullptr; /* between the launches of the split screen */
     bool split_events = false;                                           /* the last batch recorded them */
@@ -109,9 +109,6 @@ struct gf_index {
     gf_map_stats stats{};
     unsigned long long launches = 0;
     int sm_count = 148;
-    int screen_version = 4; /* GF_SCREEN: 1 = HBM hash probe per k-mer (warp per pair), 2 = L2-resident filter + gene
-                               planes (warp per pair), 3 = same, thread per pair for reads <= 256 bases (else falls back to 2),
-                               4 = thread per pair split into prep / seed / diag / scan kernels (default) */
 };
 
 /* gf_index.cu */

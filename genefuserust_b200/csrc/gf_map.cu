@@ -10,11 +10,10 @@
  *   edit_distance                   src/core/edit_distance.rs:12-197
  *
  * Kernels:
- *   screen    every pair: fast_merge decision + a CONSERVATIVE form of map_read's first pass.  Default (reads <= 256 bases):
- *             the split pipeline k_prep -> k_seed -> k_diag / k_scan of gf_screen_split.cuh (thread per pair / per
- *             sequence, bit-planes, L2-resident filter + gene planes; the bound is documented there).  Kept for A/B and for
- *             longer reads: k_screen<.., 2> (warp per pair, same structures), k_screen<.., 1> (one HBM table probe per
- *             k-mer), k_screen_tpp (the split steps fused in one thread-per-pair kernel), selected by GF_SCREEN.
+ *   screen    every pair: fast_merge decision + a CONSERVATIVE form of map_read's first pass.  Reads <= 256 bases: the
+ *             split pipeline k_prep -> k_seed -> k_diag / k_scan of gf_screen_split.cuh (thread per pair / per sequence,
+ *             bit-planes, L2-resident filter + gene planes; the bound is documented there).  Longer reads (up to 1024
+ *             bases): k_screen (warp per pair, same structures).
  *             A sequence is dropped only when it provably fails the vote gate of indexer.rs:353-360:
  *                 T = sum of sites voted, c_d = votes of unique keys on one diagonal d (any d)
  *                 count1 >= c_d and count1 + count2 <= T   =>   count2 <= T - c_d
@@ -34,10 +33,12 @@
 #include <cstdio>
 
 #include "gf_internal.h"
+#include "gf_swar.cuh"
 
 namespace {
 
 #define FULL 0xFFFFFFFFu
+using swar::zero_bytes;
 
 __device__ __forceinline__ uint32_t fsr(const uint32_t* plane, uint32_t bitpos) {
     uint32_t w = bitpos >> 5;
@@ -45,6 +46,12 @@ __device__ __forceinline__ uint32_t fsr(const uint32_t* plane, uint32_t bitpos) 
 }
 __device__ __forceinline__ uint32_t lowmask(int nbits) { /* nbits >= 1 */
     return nbits >= 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u);
+}
+/* record [s, e) of an arena (offsets relative to `base`, `bytes` readable; 0 = extent unknown, not checked) lies inside the
+ * arena and is at most max_len long — offsets that are not ascending or wrap fail here */
+__device__ __forceinline__ bool record_ok(uint64_t s, uint64_t e, uint64_t base, uint64_t bytes, int max_len) {
+    if (e < s || e - s > (uint64_t)max_len || s < base) return false;
+    return bytes == 0 || (s - base <= bytes && e - s <= bytes - (s - base));
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -74,9 +81,6 @@ struct ScreenWarp {
 /* ---- SWAR plane construction: 8 ASCII bytes per lane and load --------------------------------------- */
 __device__ __forceinline__ uint32_t gather4(uint32_t t) { /* bits 0,8,16,24 -> bits 0..3 */
     return ((t * 0x01020408u) >> 24) & 0xFu;
-}
-__device__ __forceinline__ uint32_t zero_bytes(uint32_t y) { /* bit 7 of every byte that is 0 */
-    return ~(((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y) & 0x80808080u;
 }
 /* 4 bases -> 4-bit masks: code bits (A0 T1 C2 G3), valid = one of ACGT (upper case, or either case when ci) */
 __device__ __forceinline__ void classify4(uint32_t x, bool ci, uint32_t* lo, uint32_t* hi, uint32_t* v) {
@@ -311,90 +315,14 @@ struct ScreenParams {
     int need_total, need_minor;
 };
 
-/* Conservative first pass over one sequence given as planes.  Returns true when the sequence may pass the
- * vote gate (indexer.rs:353-360) and must go through the exact kernel. */
-constexpr int SCREEN_ROUNDS = 4;
-__device__ __forceinline__ bool screen_sequence(const GfDevIndex& ix, const uint32_t* lo, const uint32_t* hi,
-                                                const uint32_t* v, int len, int need_total, int need_minor,
-                                                unsigned long long* probes) {
-    const uint32_t lane = gf_lane();
-    const int nprobe = len >= 16 ? ((len - 16) >> 1) + 1 : 0; /* indexer.rs:277, step 2 */
-    *probes += (unsigned long long)nprobe;
-    int T = 0, cntd = 0;
-    bool have_d = false;
-    uint32_t d = 0;
-    for (int base = 0; base < nprobe; base += 32 * SCREEN_ROUNDS) {
-        uint32_t key[SCREEN_ROUNDS], bkt[SCREEN_ROUNDS];
-        bool ok[SCREEN_ROUNDS];
-        uint4 a[SCREEN_ROUNDS], c[SCREEN_ROUNDS];
-#pragma unroll
-        for (int r = 0; r < SCREEN_ROUNDS; r++) {
-            int j = base + 32 * r + (int)lane;
-            ok[r] = j < nprobe;
-            uint32_t i = ok[r] ? 2u * (uint32_t)j : 0u;
-            uint32_t vb = fsr(v, i) & 0xFFFFu;
-            ok[r] = ok[r] && vb == 0xFFFFu;
-            key[r] = ((fsr(hi, i) & 0xFFFFu) << 16) | (fsr(lo, i) & 0xFFFFu);
-            bkt[r] = gf_home_bucket(key[r], ix.bucket_shift);
-            if (ok[r]) gf_load_bucket(ix.table, bkt[r], a[r], c[r]);
-        }
-#pragma unroll
-        for (int r = 0; r < SCREEN_ROUNDS; r++) {
-            if (base + 32 * r >= nprobe) break; /* warp-uniform */
-            uint32_t val = GF_EMPTY_VAL;
-            if (ok[r]) {
-                bool stop;
-                val = gf_match_bucket(a[r], c[r], key[r], &stop);
-                uint32_t bb = bkt[r];
-                while (!stop) {
-                    bb = (bb + 1) & ix.bucket_mask;
-                    uint4 a2, c2;
-                    gf_load_bucket(ix.table, bb, a2, c2);
-                    val = gf_match_bucket(a2, c2, key[r], &stop);
-                }
-            }
-            bool is_u = false;
-            uint32_t dcode = 0xC0000000u | lane; /* never equals a real diagonal code (< 2^30) */
-            if (val != GF_EMPTY_VAL) {
-                uint32_t kind = val >> 30;
-                if (kind == GF_KIND_UNIQUE) {
-                    uint32_t i = 2u * (uint32_t)(base + 32 * r + (int)lane);
-                    uint32_t goff = val & GF_SITE_GOFF_MASK;
-                    /* forward site: position - i ; reverse site: -(P) - i = -(P + i) */
-                    dcode = (val & GF_SITE_STRAND) ? (GF_SITE_STRAND | ((goff + i) & GF_SITE_GOFF_MASK))
-                                                   : ((goff - i) & GF_SITE_GOFF_MASK);
-                    is_u = true;
-                    T += 1;
-                } else if (kind == GF_KIND_NORMAL) {
-                    T += (int)(val & 7u);
-                }
-            }
-            if (!have_d) {
-                uint32_t um = __ballot_sync(FULL, is_u);
-                if (um) {
-                    uint32_t peers = __match_any_sync(FULL, dcode);
-                    uint32_t score = is_u ? (((uint32_t)__popc(peers) << 5) | (31u - lane)) : 0u;
-                    uint32_t best = __reduce_max_sync(FULL, score);
-                    d = __shfl_sync(FULL, dcode, 31 - (int)(best & 31u));
-                    have_d = true;
-                }
-            }
-            if (have_d) cntd += __popc(__ballot_sync(FULL, is_u && dcode == d));
-        }
-    }
-    T = (int)__reduce_add_sync(FULL, (unsigned)T);
-    return T >= need_total && (T - cntd) >= need_minor;
-}
-
-
-/* ---- screen v2: L2-resident working set ------------------------------------------------------------
+/* ---- warp-per-pair screen (reads longer than 256 bases): L2-resident working set ---------------------
  * Same conservative bound as screen_sequence (count2 <= T - c_d), but T and c_d are obtained without
  * touching the HBM table for every k-mer:
  *   1. seed: up to 8 spread k-mers are tested in the Bloom filter (L2); the first present one is looked up
  *      in the HBM table; a UNIQUE key gives a site, i.e. a diagonal d of the read against one gene strand.
  *   2. the whole read is compared with the 2-bit gene planes along d (32 bases per xor), a 16-wide run
  *      detector yields every offset whose 16-mer equals the gene window; where that window is an indexed
- *      voting site (site-count planes g_cf / g_cr) the votes are known exactly: +nsites to T, +1 to c_d.
+ *      voting site (count bits of the interleaved gene entries g_if / g_ir) the votes are known exactly: +nsites to T, +1 to c_d.
  *   3. every other valid even offset is probed in the filter: contributes an UPPER bound of its votes to T.
  * No false negatives anywhere => T_ub >= T and c_d <= true votes on d => the drop rule stays safe. */
 __device__ __forceinline__ uint32_t run16(uint32_t w0, uint32_t w1) {
@@ -416,11 +344,6 @@ __device__ __forceinline__ unsigned long long make_policy_keep() {
 __device__ __forceinline__ unsigned long long ldg_filter(const unsigned long long* p, unsigned long long pol) {
     unsigned long long v;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ uint32_t ldg_plane(const uint32_t* p, unsigned long long pol) {
-    uint32_t v;
-    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
     return v;
 }
 
@@ -487,16 +410,13 @@ __device__ __forceinline__ bool screen_sequence2(const GfDevIndex& ix, ScreenWar
             if (len & 1) parity = 0xAAAAAAAAu; /* i' = len-16-i: even i <=> i' has the parity of len */
             __syncwarp();
         }
-        /* 2. gene planes along the diagonal */
+        /* 2. gene planes along the diagonal: one interleaved 32-byte entry {lo, hi, valid, count bits 0..2} per 32 positions */
         const uint32_t wbase = D >> 5, sh = D & 31u;
-        const uint32_t* gc = rc ? ix.g_cr : ix.g_cf;
+        const uint4* gi = reinterpret_cast<const uint4*>(rc ? ix.g_ir : ix.g_if);
         for (int k = (int)lane; k <= nch + 1; k += 32) {
-            S.glo[k] = ldg_plane(ix.g_lo + wbase + k, pol);
-            S.ghi[k] = ldg_plane(ix.g_hi + wbase + k, pol);
-            S.gv[k] = ldg_plane(ix.g_v + wbase + k, pol);
-            S.gc[0][k] = ldg_plane(gc + wbase + k, pol);
-            S.gc[1][k] = ldg_plane(gc + ix.g_cstride + wbase + k, pol);
-            S.gc[2][k] = ldg_plane(gc + 2 * ix.g_cstride + wbase + k, pol);
+            const uint4 a = __ldg(gi + 2ull * (wbase + k)), b = __ldg(gi + 2ull * (wbase + k) + 1);
+            S.glo[k] = a.x; S.ghi[k] = a.y; S.gv[k] = a.z;
+            S.gc[0][k] = a.w; S.gc[1][k] = b.x; S.gc[2][k] = b.y;
         }
         __syncwarp();
         for (int k = (int)lane; k <= nch; k += 32) {
@@ -587,7 +507,7 @@ __device__ __forceinline__ bool screen_sequence2(const GfDevIndex& ix, ScreenWar
 #include "gf_screen_tpp.cuh"
 #include "gf_screen_split.cuh"
 
-template <int MAXW, bool PAIRED, int VERSION>
+template <int MAXW, bool PAIRED>
 __global__ void __launch_bounds__(256, 3) k_screen(ScreenParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScreenWarp<MAXW>* Sall = reinterpret_cast<ScreenWarp<MAXW>*>(smem_raw);
@@ -619,7 +539,8 @@ __global__ void __launch_bounds__(256, 3) k_screen(ScreenParams P) {
             s2 = B.seq2 + (o2 - B.base2);
             q2 = B.qual2 + (B.qs2[p] - B.base2);
         }
-        if (len1 > 32 * MAXW || len2 > 32 * MAXW || len1 < 0 || len2 < 0) {
+        if (!record_ok(o1, e1, B.base1, B.bytes1, 32 * MAXW) ||
+            (PAIRED && !record_ok(__ldg(B.s2 + p), __ldg(B.e2 + p), B.base2, B.bytes2, 32 * MAXW))) {
             err |= 1u;
             continue;
         }
@@ -655,9 +576,7 @@ __global__ void __launch_bounds__(256, 3) k_screen(ScreenParams P) {
             }
             c_seq++;
             c_bytes += (unsigned long long)len;
-            bool sv = VERSION == 1
-                          ? screen_sequence(P.ix, plo, phi, pv, len, P.need_total, P.need_minor, &c_probes)
-                          : screen_sequence2<MAXW>(P.ix, S, plo, phi, pv, len, P.need_total, P.need_minor, &c_probes);
+            const bool sv = screen_sequence2<MAXW>(P.ix, S, plo, phi, pv, len, P.need_total, P.need_minor, &c_probes);
             if (sv && lane == 0) {
                 uint32_t slot = atomicAdd(&P.counters->n_survivors, 1u);
                 if (slot < P.survivors_cap) P.survivors[slot] = make_uint2((uint32_t)p, meta);
@@ -712,28 +631,33 @@ __global__ void __launch_bounds__(256) k_merge_only(GfDevBatch B, gf_merge_info*
 /* ------------------------------------------------------------------------------------------------ */
 /* raw (ASCII) sequence reconstruction for the exact / verify kernels                                */
 
-/* Loads the sequence a survivor stands for into `seq` (shared memory), returns its length.
+/* Loads the sequence a survivor stands for into `seq` (shared memory, `cap` bytes), returns its length, or -1 without
+ * writing anything when the record offsets are inconsistent (outside the arena, negative or longer than the buffer).
  * source 0 = merged read (literal read.rs:369-428 given the overlap length), 1 = R1, 2 = R2. */
-__device__ int load_sequence(const GfDevBatch& B, uint32_t pair, uint32_t source, int olen, uint8_t* seq) {
+__device__ int load_sequence(const GfDevBatch& B, uint32_t pair, uint32_t source, int olen, uint8_t* seq, int cap) {
     const uint32_t lane = gf_lane();
-    const uint64_t o1 = B.s1[pair];
-    const int len1 = (int)(B.e1[pair] - o1);
+    const uint64_t o1 = B.s1[pair], e1 = B.e1[pair];
+    if (!record_ok(o1, e1, B.base1, B.bytes1, cap)) return -1;
+    const int len1 = (int)(e1 - o1);
     const uint8_t* s1 = B.seq1 + (o1 - B.base1);
     int len;
     if (source == 1) {
         for (int j = (int)lane; j < len1; j += 32) seq[j] = s1[j];
         len = len1;
     } else {
-        const uint64_t o2 = B.s2[pair];
-        const int len2 = (int)(B.e2[pair] - o2);
+        if (!B.seq2) return -1;
+        const uint64_t o2 = B.s2[pair], e2 = B.e2[pair];
+        if (!record_ok(o2, e2, B.base2, B.bytes2, cap)) return -1;
+        const int len2 = (int)(e2 - o2);
         const uint8_t* s2 = B.seq2 + (o2 - B.base2);
         if (source == 2) {
             for (int j = (int)lane; j < len2; j += 32) seq[j] = s2[j];
             len = len2;
         } else {
+            const int offset = len1 - olen;
+            if (olen < 0 || offset < 0 || olen > len2 || offset + len2 > cap) return -1;
             const uint8_t* q1 = B.qual1 + (B.qs1[pair] - B.base1);
             const uint8_t* q2 = B.qual2 + (B.qs2[pair] - B.base2);
-            const int offset = len1 - olen;
             for (int j = (int)lane; j < offset; j += 32) seq[j] = s1[j];
             for (int i = (int)lane; i < len2; i += 32) {
                 uint8_t c2 = gf_complement_ascii(s2[len2 - 1 - i]);
@@ -1005,8 +929,8 @@ __global__ void __launch_bounds__(EX_WARPS * 32) k_exact(ExactParams P) {
         const uint32_t pair = sv.x, source = sv.y & 3u;
         const int olen = (int)((sv.y >> 2) & 0xFFFu), diff = (int)((sv.y >> 14) & 3u);
         __syncwarp();
-        int len = load_sequence(P.b, pair, source, olen, W.seq);
-        if (len + 16 > EW::SEQ_CAP) { if (lane == 0) atomicOr(&P.counters->error_flags, 1u); continue; }
+        const int len = load_sequence(P.b, pair, source, olen, W.seq, EW::SEQ_CAP - 16);
+        if (len < 0) { if (lane == 0) atomicOr(&P.counters->error_flags, 1u); continue; }
         if (lane == 0) for (int k = 0; k < 16; k++) W.seq[len + k] = 0;
         __syncwarp();
         for (int attempt = 0; attempt < 2; attempt++) {
@@ -1226,7 +1150,8 @@ __global__ void __launch_bounds__(VF_WARPS * 32) k_verify(VerifyParams P) {
     for (uint64_t ci = (uint64_t)blockIdx.x * VF_WARPS + wib; ci < n; ci += n_warps) {
         gf_match m = P.out[ci];
         __syncwarp();
-        int len = load_sequence(P.b, (uint32_t)(m.pair_idx - P.b.pair_base), m.source, m.merge_olen, W.seq);
+        const int len = load_sequence(P.b, (uint32_t)(m.pair_idx - P.b.pair_base), m.source, m.merge_olen, W.seq, EX_SEQ_CAP - 16);
+        if (len < 0) { if (lane == 0) atomicOr(&P.counters->error_flags, 1u); continue; }
         if (m.used_rc) revcomp_inplace(W.seq, len);
         const int rb = m.read_break;
         const int left_len = rb + 1, right_len = len - (rb + 1);
@@ -1373,12 +1298,7 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
         const int blocks_per_sm = 3; /* 80 registers x 256 threads -> 3 resident blocks per SM */
         uint64_t want = (b.n + warps - 1) / warps;
         unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)idx->sm_count * blocks_per_sm);
-#define GF_LAUNCH_SCREEN(W, PE, VER)                                         \
-    do {                                                                     \
-        GF_CUDA_TRY(set_smem(k_screen<W, PE, VER>, smem));                   \
-        k_screen<W, PE, VER><<<grid, threads, smem, st>>>(sp);               \
-    } while (0)
-        if (idx->screen_version == 4 && small) {
+        if (small) {
             /* split pipeline: prep -> seed -> diag / scan (gf_screen_split.cuh) */
             const bool w5 = b.max_len <= 160;
             const int NW3 = w5 ? split::SL<5>::NW3 : split::SL<8>::NW3;
@@ -1410,11 +1330,7 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
             pp.b = b;
             pp.st = ss;
             pp.counters = d_cnt;
-            pp.stream_policy = 0; /* measured: evict_first on the read bytes and L2 prefetch both cost ~2 % (gpurun_out) */
-            pp.prefetch = 0;
-            if (const char* e = getenv("GF_STREAM_POLICY")) pp.stream_policy = atoi(e) != 0;
-            if (const char* e = getenv("GF_PREFETCH")) pp.prefetch = atoi(e) != 0;
-            const size_t psm = sizeof(uint32_t) * tpp::WARPS * (w5 ? tpp::Lay<5>::MLO : tpp::Lay<8>::MLO) * 32;
+            const size_t psm = sizeof(uint32_t) * tpp::WARPS * (w5 ? tpp::Lay<5>::NWORDS : tpp::Lay<8>::NWORDS) * 32;
             const uint64_t want_b = (b.n + tpp::WARPS * 32 - 1) / (tpp::WARPS * 32);
             /* persistent grids: exactly as many blocks as are resident at once (a partial second wave would idle SMs) */
 #define GF_LAUNCH_PREP(WW, PE)                                                             \
@@ -1445,59 +1361,28 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
             cp.need_minor = sp.need_minor;
             const unsigned smc = (unsigned)idx->sm_count;
 #define GF_EV(e) do { if (record_events) GF_CUDA_TRY(cudaEventRecord(idx->e, st)); } while (0)
-            bool cc = idx->concurrent != 0;
-            if (cc && !idx->side_stream) {
-                cc = cudaStreamCreateWithFlags(&idx->side_stream, cudaStreamNonBlocking) == cudaSuccess &&
-                     cudaEventCreateWithFlags(&idx->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-                     cudaEventCreateWithFlags(&idx->ev_join, cudaEventDisableTiming) == cudaSuccess;
-            }
+            /* k_diag and k_scan back to back: running them side by side on two streams with split grids measured the same
+             * (2.8 vs 2.9 ms), so there is one path */
 #define GF_LAUNCH_CLASSES(WW)                                                                                         \
     do {                                                                                                              \
         split::k_seed<WW><<<smc * resident_blocks(split::k_seed<WW>, 256, 0), 256, 0, st>>>(sdp);                     \
         GF_EV(ev_seed);                                                                                               \
-        if (cc) { /* k_diag (latency / issue) and k_scan (L1TEX gathers) side by side, each on part of every SM */     \
-            GF_CUDA_TRY(cudaEventRecord(idx->ev_fork, st));                                                           \
-            GF_CUDA_TRY(cudaStreamWaitEvent(idx->side_stream, idx->ev_fork, 0));                                      \
-            split::k_diag<WW><<<smc * (unsigned)idx->cc_diag, 256, 0, st>>>(cp);                                      \
-            split::k_scan<WW><<<smc * (unsigned)idx->cc_scan, 256, 0, idx->side_stream>>>(cp);                        \
-            GF_CUDA_TRY(cudaEventRecord(idx->ev_join, idx->side_stream));                                             \
-            GF_EV(ev_diag);                                                                                           \
-            GF_CUDA_TRY(cudaStreamWaitEvent(st, idx->ev_join, 0));                                                    \
-        } else {                                                                                                      \
-            split::k_diag<WW><<<smc * resident_blocks(split::k_diag<WW>, 256, 0), 256, 0, st>>>(cp);                  \
-            GF_EV(ev_diag);                                                                                           \
-            split::k_scan<WW><<<smc * resident_blocks(split::k_scan<WW>, 256, 0), 256, 0, st>>>(cp);                  \
-        }                                                                                                             \
+        split::k_diag<WW><<<smc * resident_blocks(split::k_diag<WW>, 256, 0), 256, 0, st>>>(cp);                      \
+        GF_EV(ev_diag);                                                                                               \
+        split::k_scan<WW><<<smc * resident_blocks(split::k_scan<WW>, 256, 0), 256, 0, st>>>(cp);                      \
     } while (0)
             if (w5) GF_LAUNCH_CLASSES(5); else GF_LAUNCH_CLASSES(8);
 #undef GF_LAUNCH_CLASSES
 #undef GF_EV
             if (record_events) idx->split_events = true;
             idx->launches += 3;
-        } else if (idx->screen_version >= 3 && small) {
-            /* thread per pair: 4 warps x (81 | 123) private words x 32 lanes of shared memory per block */
-            const bool w5 = b.max_len <= 160;
-            const size_t tsm = sizeof(uint32_t) * tpp::WARPS * (w5 ? tpp::Lay<5>::NWORDS : tpp::Lay<8>::NWORDS) * 32;
-            const uint64_t want_b = (b.n + tpp::WARPS * 32 - 1) / (tpp::WARPS * 32);
-            int bps = w5 ? 5 : 3; /* resident blocks per SM the shared-memory columns allow */
-            if (const char* e = getenv("GF_TPP_BLOCKS")) { int v = atoi(e); if (v >= 1 && v <= bps) bps = v; }
-            const unsigned tgrid = (unsigned)std::min<uint64_t>(want_b, (uint64_t)idx->sm_count * bps);
-#define GF_LAUNCH_TPP(WW, PE)                                                              \
-    do {                                                                                   \
-        GF_CUDA_TRY(set_smem(tpp::k_screen_tpp<WW, PE>, tsm));                             \
-        tpp::k_screen_tpp<WW, PE><<<tgrid, tpp::WARPS * 32, tsm, st>>>(sp);                \
-    } while (0)
-            if (w5) { if (paired) GF_LAUNCH_TPP(5, true); else GF_LAUNCH_TPP(5, false); }
-            else { if (paired) GF_LAUNCH_TPP(8, true); else GF_LAUNCH_TPP(8, false); }
-#undef GF_LAUNCH_TPP
-        } else if (idx->screen_version == 1) {
-            if (small) { if (paired) GF_LAUNCH_SCREEN(8, true, 1); else GF_LAUNCH_SCREEN(8, false, 1); }
-            else { if (paired) GF_LAUNCH_SCREEN(32, true, 1); else GF_LAUNCH_SCREEN(32, false, 1); }
         } else {
-            if (small) { if (paired) GF_LAUNCH_SCREEN(8, true, 2); else GF_LAUNCH_SCREEN(8, false, 2); }
-            else { if (paired) GF_LAUNCH_SCREEN(32, true, 2); else GF_LAUNCH_SCREEN(32, false, 2); }
+            /* reads longer than 256 bases: warp per pair, same filter + gene-plane structures */
+            GF_CUDA_TRY(set_smem(k_screen<32, true>, smem));
+            GF_CUDA_TRY(set_smem(k_screen<32, false>, smem));
+            if (paired) k_screen<32, true><<<grid, threads, smem, st>>>(sp);
+            else k_screen<32, false><<<grid, threads, smem, st>>>(sp);
         }
-#undef GF_LAUNCH_SCREEN
         GF_CUDA_TRY(cudaGetLastError());
         idx->launches++;
     }
@@ -1550,7 +1435,7 @@ int gf_fast_merge_device(gf_index* idx, const GfDevBatch& b, gf_merge_info* d_ou
     if (!b.n) return GF_OK;
     GF_CUDA_TRY(idx->ws_counters.reserve(sizeof(GfMapCounters)));
     GF_CUDA_TRY(cudaMemsetAsync(idx->ws_counters.p, 0, sizeof(GfMapCounters), st));
-    if (idx->screen_version >= 3 && b.max_len != 0 && b.max_len <= 256) {
+    if (b.max_len != 0 && b.max_len <= 256) {
         const bool w5 = b.max_len <= 160;
         const size_t tsm = sizeof(uint32_t) * tpp::WARPS * (w5 ? tpp::Lay<5>::NWORDS : tpp::Lay<8>::NWORDS) * 32;
         unsigned tgrid = (unsigned)std::min<uint64_t>((b.n + tpp::WARPS * 32 - 1) / (tpp::WARPS * 32), (uint64_t)idx->sm_count * 3);

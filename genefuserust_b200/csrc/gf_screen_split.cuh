@@ -1,7 +1,7 @@
 /*
- * gf_screen_split.cuh — screen v4: the thread-per-pair screen of gf_screen_tpp.cuh cut into four kernels so that every
- * warp runs ONE class of work (the fused kernel averaged 15 of 32 active threads because merged/unmerged,
- * seeded/unseeded, short/long and forward/reverse pairs diverge inside a warp).
+ * gf_screen_split.cuh — the screen for reads <= 256 bases: thread per pair / per sequence, cut into four kernels so that
+ * every warp runs ONE class of work (a fused thread-per-pair kernel averaged 15 of 32 active threads because
+ * merged/unmerged, seeded/unseeded, short/long and forward/reverse pairs diverge inside a warp).
  *
  *   k_prep   thread per pair      convert R1 / rc(R2) to bit-planes, fast_merge (read.rs:313-440), write the 1-2 sequences
  *                                 that will be mapped (merged, or R1 and R2) as bit-planes into a sequence store: short
@@ -58,8 +58,6 @@ struct PrepParams {
     GfDevBatch b;
     SeqStore st;
     GfMapCounters* counters;
-    int stream_policy; /* 0 = evict_normal, 1 = evict_first for the read bytes (GF_STREAM_POLICY) */
-    int prefetch;      /* 1 = prefetch the next pair's bases into L2 (GF_PREFETCH) */
 };
 
 /* ---------------------------------------------------------------------------------------------- k_prep */
@@ -68,12 +66,12 @@ __global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepPa
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* sm = reinterpret_cast<uint32_t*>(smem_raw);
     const uint32_t lane = gf_lane(), wib = threadIdx.x >> 5;
-    constexpr int PW = Lay<W>::MLO; /* private words actually used here: R1 + C2 arrays only */
+    constexpr int PW = Lay<W>::NWORDS; /* R1 + rc(R2) plane arrays */
     Col c;
     c.base = sm + (size_t)wib * PW * 32 + lane;
     const GfDevBatch& B = P.b;
     const uint64_t n_warps = (uint64_t)gridDim.x * tpp::WARPS;
-    const unsigned long long pol_stream = P.stream_policy ? tpp::make_policy_stream() : tpp::make_policy_normal();
+    const unsigned long long pol_stream = tpp::make_policy_normal(); /* measured: evict_first on the read bytes costs ~2 % */
     const uint8_t* const NOBOUND = reinterpret_cast<const uint8_t*>(~(uintptr_t)0);
     const uint8_t* bound1 = B.bytes1 ? B.seq1 + B.bytes1 : NOBOUND;
     const uint8_t* bound2 = (PAIRED && B.bytes2) ? B.seq2 + B.bytes2 : NOBOUND;
@@ -87,19 +85,22 @@ __global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepPa
         uint32_t r1_bits = 0; /* which of the (<= 2) overlap mismatches keep the R1 base */
         const uint8_t *q1 = nullptr, *q2 = nullptr;
         if (p < B.n) {
-            const uint64_t o1 = __ldg(B.s1 + p);
-            len1 = (int)(__ldg(B.e1 + p) - o1);
+            const uint64_t o1 = __ldg(B.s1 + p), e1 = __ldg(B.e1 + p);
+            bool ok = record_ok(o1, e1, B.base1, B.bytes1, 32 * W);
+            len1 = (int)(e1 - o1);
             const uint8_t* s1 = B.seq1 + (o1 - B.base1);
             q1 = B.qual1 + (B.qs1[p] - B.base1);
             const uint8_t* s2 = nullptr;
             if (PAIRED) {
-                const uint64_t o2 = __ldg(B.s2 + p);
-                len2 = (int)(__ldg(B.e2 + p) - o2);
+                const uint64_t o2 = __ldg(B.s2 + p), e2 = __ldg(B.e2 + p);
+                ok = ok && record_ok(o2, e2, B.base2, B.bytes2, 32 * W);
+                len2 = (int)(e2 - o2);
                 s2 = B.seq2 + (o2 - B.base2);
                 q2 = B.qual2 + (B.qs2[p] - B.base2);
             }
-            if (len1 > 32 * W || len2 > 32 * W || len1 < 0 || len2 < 0) {
+            if (!ok) { /* longer than the kernel capacity, or offsets that are not ascending / leave the arena */
                 err |= 1u;
+                len1 = len2 = 0;
             } else {
                 tpp::convert_r1<W>(c, s1, len1, B.seq1, bound1, pol_stream);
                 if (PAIRED) {

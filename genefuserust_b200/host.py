@@ -12,8 +12,9 @@ import os
 
 import numpy as np
 
-from ._abi import (GF_E_CAPACITY, GF_E_REF_PANIC, GF_OK, gf_break_job, gf_break_out, gf_break_ref, gf_index_info, gf_lookup,
-                   gf_map_stats, gf_match, gf_merge_info, gf_gene_span, gf_params, load_library)
+from ._abi import (GF_E_CAPACITY, GF_E_REF_PANIC, GF_OK, gf_alignable_result, gf_break_job, gf_break_out, gf_break_ref,
+                   gf_index_info, gf_lookup, gf_map_stats, gf_match, gf_merge_info, gf_gene_span, gf_params, gf_ref_contig,
+                   gf_reference_info, load_library)
 from .batch import ReadBatch
 
 
@@ -363,6 +364,62 @@ def sort_read_matches(matches, read_name_of):
         return 0
 
     matches.sort(key=functools.cmp_to_key(cmp))
+
+
+class Matcher:
+    """matcher.rs as FusionMapper::remove_alignables uses it (fusion_mapper.rs:488-542): built ONCE per reference (the
+    reference streams through the GPU scan once, gf_reference_create), then asked per set of surviving read sequences."""
+
+    def __init__(self, contigs, device=0):
+        """contigs: FastaReader.m_all_contigs (dict name -> bytes; iterated in ascending name order like the BTreeMap), or
+        a list of bytes / numpy uint8 arrays already in that order, or (device_pointer, length) tuples."""
+        self.lib = load_library()
+        if isinstance(contigs, dict):
+            contigs = [contigs[k] for k in sorted(contigs)]
+        arr = (gf_ref_contig * max(1, len(contigs)))()
+        self._keep = []
+        for i, c in enumerate(contigs):
+            if isinstance(c, tuple):
+                arr[i].seq, arr[i].len = c
+                continue
+            a = np.frombuffer(c, dtype=np.uint8) if isinstance(c, (bytes, bytearray)) else np.ascontiguousarray(c, dtype=np.uint8)
+            self._keep.append(a)
+            arr[i].seq = a.ctypes.data if len(a) else None
+            arr[i].len = len(a)
+        h = C.c_void_p()
+        _check(self.lib, self.lib.gf_reference_create(arr, len(contigs), device, C.byref(h)))
+        self.h = h
+        self._keep = []
+
+    def info(self):
+        out = gf_reference_info()
+        _check(self.lib, self.lib.gf_reference_get_info(self.h, C.byref(out)))
+        return out
+
+    def remove_alignables(self, seqs):
+        """seqs: list of bytes (ReadMatch::get_read().m_seq in bucket order).  Returns (alignable flags, result struct, rc);
+        rc is GF_E_REF_PANIC where the reference's Matcher would abort the run."""
+        off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        if seqs:
+            np.cumsum([len(s) for s in seqs], out=off[1:])
+        arena = np.frombuffer(b"".join(seqs), dtype=np.uint8) if seqs else np.zeros(0, np.uint8)
+        flags = np.zeros(max(1, len(seqs)), dtype=np.uint8)
+        res = gf_alignable_result()
+        rc = self.lib.gf_alignable_filter(self.h, arena.ctypes.data if len(arena) else None, off.ctypes.data, len(seqs),
+                                          flags.ctypes.data, C.byref(res))
+        _check(self.lib, rc, allow=(GF_E_REF_PANIC,))
+        return flags[:len(seqs)], res, rc
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gf_reference_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class PairEndScanner:

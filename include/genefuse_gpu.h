@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GF_ABI_VERSION 1
+#define GF_ABI_VERSION 2
 
 /* status codes (0 = ok, negative = error; text via gf_last_error()) */
 enum gf_status {
@@ -262,6 +262,59 @@ typedef struct gf_break_out {
 } gf_break_out;
 int gf_adjust_fusion_break(gf_index* idx, const uint8_t* bytes, uint64_t n_bytes, const gf_break_ref* refs, uint32_t n_refs,
                            const gf_break_job* jobs, uint64_t n_jobs, gf_break_out* out);
+
+/* ---- Matcher pass: FusionMapper::remove_alignables (src/core/fusion_mapper.rs:488-542), SURVEY 8(a) row M / 8(f) #4 ----
+ * After the per-record filters the reference builds a `Matcher` over the WHOLE reference (Matcher::from_ref_and_seqs,
+ * src/core/matcher.rs:44-169) and drops every match whose read `do_match`es it (:662-689).  As ported, the Matcher is
+ * degenerate: its make_kmer* helpers `break` after the first base (:778-793,818-834,855-869), so a "k-mer" is the 2-bit code
+ * of one base, the 512 MiB bloom array only ever has bits 0..3 of byte 0 set (:73-88), index_contig_bytes (:227-289) keeps a
+ * reference position only where its rolling 32-bit value is < 4 (the start of every ACGT run, and any base preceded by
+ * 15 'A's or by nothing but 'A's since the run start), and map_to_index (:388-529) can only return None or panic at
+ * `.get(&kmer).unwrap()` (:490-491).  So remove_alignables removes nothing — but it costs one pass over the reference
+ * (13-18 s of the reference's wall clock on hg19/hg38) and it can abort the run.  This call reproduces both observable
+ * outcomes: the per-key position counts of m_kmer_positions and the panic pre-condition, from one streaming scan of the
+ * reference on the GPU.
+ *
+ * gf_reference_create streams the contigs (host OR device pointers, ASCII, any case: to_ascii_uppercase, :143-148) through
+ * the scan kernel once and keeps the result (4 counters and, for a key with <= 50 positions, the positions themselves) in
+ * the handle; no reference bytes stay on the device.  List mode builds it once for all CSVs.  Contigs must be given in
+ * FastaReader::m_all_contigs order (BTreeMap: ascending name), which defines the contig ids. */
+typedef struct gf_ref_contig {
+    const uint8_t* seq;
+    uint64_t len;
+} gf_ref_contig;
+typedef struct gf_reference gf_reference; /* opaque */
+typedef struct gf_reference_info {
+    uint64_t n_contigs;
+    uint64_t n_bases;
+    uint64_t key_positions[4]; /* positions index_contig_bytes keeps for rolling key 0..3 (A, T, C, G) when the key's bloom
+                                  bit is set */
+    uint64_t short_contigs;    /* contigs shorter than 16 bases: Matcher::make_index panics on them (:240-243) */
+    uint64_t h2d_bytes;        /* reference bytes copied host -> device (0 for device-resident contigs) */
+    uint64_t kernel_launches;
+    float ms_total;            /* device time of the whole pass (copies + scan), events on the handle's stream */
+    float ms_scan;             /* scan kernels only */
+} gf_reference_info;
+int gf_reference_create(const gf_ref_contig* contigs, uint32_t n_contigs, int device, gf_reference** out);
+void gf_reference_destroy(gf_reference* ref);
+int gf_reference_get_info(const gf_reference* ref, gf_reference_info* out);
+
+typedef struct gf_alignable_result {
+    uint64_t key_positions[4]; /* Matcher::m_kmer_positions[k].len() for THIS set of sequences (0 when bloom bit k is unset) */
+    uint64_t n_removed;        /* matches do_match returns Some for: always 0 (see above) */
+    int64_t panic_seq;         /* index of the first sequence whose do_match panics, -1 = none */
+    uint32_t bloom_bits;       /* m_bloom_filter_array[0] (bits 0..3 = base codes seen at a k-mer start of any sequence or
+                                  of its reverse complement) */
+    int32_t panic_stage;       /* 0 = the reference completes; 1 = Matcher::make_index panics (a contig shorter than 16
+                                  bases); 2 / 3 = do_match panics in map_to_index of the sequence / of its reverse complement
+                                  (:490-491); 4 = a sequence shorter than 15 bases (the reference's usize arithmetic wraps,
+                                  :77, :414) */
+} gf_alignable_result;
+/* seqs[seq_off[j] .. seq_off[j+1]) = ReadMatch::get_read().m_seq of the j-th surviving match, in bucket order (the order
+ * remove_alignables' retain() visits them).  alignable[j] = 1 where the match would be removed (always 0).  Returns GF_OK,
+ * or GF_E_REF_PANIC when res->panic_stage != 0 (the result struct is still filled). */
+int gf_alignable_filter(gf_reference* ref, const uint8_t* seqs, const uint64_t* seq_off, uint64_t n_seqs, uint8_t* alignable,
+                        gf_alignable_result* res);
 
 /* ---- list mode: the same reads against several fusion CSVs (src/core/fusion_scan.rs:62-188) ----
  * The reference scans its preloaded reads once per CSV with a fresh FusionMapper.  Here every CSV is one index handle, all on

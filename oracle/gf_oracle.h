@@ -76,6 +76,17 @@ int32_t orc_get_ref_seq(const uint8_t* ref, int32_t ref_len, int32_t start, int3
 int orc_adjust_fusion_break(const uint8_t* seq, int32_t len, int32_t read_break, const uint8_t* left_ref, int32_t left_len,
                             const uint8_t* right_ref, int32_t right_len, int32_t out[3]);
 
+/* ---- Matcher (src/core/matcher.rs) as called from FusionMapper::remove_alignables (src/core/fusion_mapper.rs:488-542);
+ * gf_oracle_matcher.cpp.  Places where the Rust code panics are returned as codes. ---- */
+typedef struct orc_matcher orc_matcher;
+orc_matcher* orc_matcher_create(const gf_ref_contig* contigs, uint32_t n_contigs, const uint8_t* seqs, const uint64_t* seq_off,
+                                uint64_t n_seqs, int* status);
+void orc_matcher_destroy(orc_matcher*);
+void orc_matcher_counts(const orc_matcher*, uint64_t key_positions[4], uint32_t* bloom_bits, uint64_t* other_keys);
+int orc_matcher_do_match(orc_matcher*, const uint8_t* seq, int32_t len);
+int orc_remove_alignables(const gf_ref_contig* contigs, uint32_t n_contigs, const uint8_t* seqs, const uint64_t* seq_off,
+                          uint64_t n_seqs, uint8_t* alignable, gf_alignable_result* res);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,7 +5,8 @@ import subprocess
 
 import numpy as np
 
-from genefuserust_b200._abi import gf_batch, gf_gene_span, gf_lookup, gf_match, gf_params
+from genefuserust_b200._abi import (gf_alignable_result, gf_batch, gf_gene_span, gf_lookup, gf_match, gf_params,
+                                    gf_ref_contig)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
@@ -23,8 +24,8 @@ _lib = None
 
 
 def build_oracle():
-    src = os.path.join(ORACLE_DIR, "gf_oracle.cpp")
-    if (not os.path.exists(ORACLE_SO)) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("gf_oracle.cpp", "gf_oracle_matcher.cpp", "gf_oracle.h")]
+    if (not os.path.exists(ORACLE_SO)) or os.path.getmtime(ORACLE_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return ORACLE_SO
 
@@ -69,6 +70,9 @@ def lib():
     L.orc_adjust_fusion_break.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32,
                                           P(C.c_int32)]
     L.orc_adjust_fusion_break.restype = C.c_int
+    L.orc_remove_alignables.argtypes = [P(gf_ref_contig), C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                        P(gf_alignable_result)]
+    L.orc_remove_alignables.restype = C.c_int
     _lib = L
     return L
 
@@ -191,3 +195,23 @@ def adjust_fusion_break(seq, read_break, left_ref, right_ref):
     out = (C.c_int32 * 3)()
     st = lib().orc_adjust_fusion_break(seq, len(seq), read_break, left_ref, len(left_ref), right_ref, len(right_ref), out)
     return (0, 0, 0, 1) if st else (out[0], out[1], out[2], 0)
+
+
+def remove_alignables(contigs, seqs):
+    """FusionMapper::remove_alignables (fusion_mapper.rs:488-542) on the CPU: contigs = list of bytes in name order, seqs =
+    list of bytes.  Returns (flags, gf_alignable_result, rc) like genefuserust_b200.host.Matcher.remove_alignables."""
+    L = lib()
+    keep = [np.frombuffer(c, dtype=np.uint8) for c in contigs]
+    arr = (gf_ref_contig * max(1, len(contigs)))()
+    for i, a in enumerate(keep):
+        arr[i].seq = a.ctypes.data if len(a) else None
+        arr[i].len = len(a)
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    if seqs:
+        np.cumsum([len(s) for s in seqs], out=off[1:])
+    arena = np.frombuffer(b"".join(seqs), dtype=np.uint8) if seqs else np.zeros(0, np.uint8)
+    flags = np.zeros(max(1, len(seqs)), dtype=np.uint8)
+    res = gf_alignable_result()
+    rc = L.orc_remove_alignables(arr, len(contigs), arena.ctypes.data if len(arena) else None, off.ctypes.data, len(seqs),
+                                 flags.ctypes.data, C.byref(res))
+    return flags[:len(seqs)], res, rc

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(built):
     assert declared == set(_abi.EXPORTS), declared ^ set(_abi.EXPORTS)
     for name in declared:
         assert getattr(built, name) is not None
-    assert built.gf_abi_version() == 1
+    assert built.gf_abi_version() == 2
     p = _abi.gf_params()
     built.gf_default_params(C.byref(p))
     assert (p.skip_key_dup_threshold, p.major_gene_key_requirement, p.minor_gene_key_requirement,

@@ -1,4 +1,4 @@
-"""CPU model of the 16-base SWAR step of the read converters (csrc/gf_screen_tpp.cuh: expect4 / block16): the multiply
+"""CPU model of the 16-base SWAR step of the read converters (csrc/gf_swar.cuh: expect4 / block16): the multiply
 gathers, the PRMT validity lookup and the slow path, checked against the plain definition of the planes
 (make_kmer_bytes' code A0 T1 C2 G3, src/core/indexer.rs:888-904; reverse_complement's case rule, src/core/sequence.rs:52-60).
 The constants are read from the CUDA source so that the model cannot drift from the kernel."""
@@ -6,7 +6,7 @@ import os
 import random
 import re
 
-SRC = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "genefuserust_b200", "csrc", "gf_screen_tpp.cuh")).read()
+SRC = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "genefuserust_b200", "csrc", "gf_swar.cuh")).read()
 M32 = 0xFFFFFFFF
 
 
