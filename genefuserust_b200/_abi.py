@@ -177,7 +177,16 @@ EXPORTS = (
     "gf_sort_matches", "gf_get_map_stats", "gf_fast_merge", "gf_map_fastq", "gf_multi_create", "gf_multi_destroy",
     "gf_multi_map_pairs", "gf_adjust_fusion_break", "gf_list_map_pairs", "gf_map_pairs_device_list",
     "gf_reference_create", "gf_reference_destroy", "gf_reference_get_info", "gf_alignable_filter",
+    "gf_index_set_output_mode",
 )
+GF_OUT_DROP_FILTERED, GF_OUT_BUCKET_ORDER = 1, 2
+
+
+def gf_match_order_key(n_genes, m):
+    """static inline gf_match_order_key of the header"""
+    bucket = n_genes * m.r_contig + m.l_contig
+    brk = 2047 - min(max(m.read_break, 0), 2047)
+    return (bucket << 23) | (brk << 12) | (m.seq_len & 0xFFF)
 
 _lib = None
 
@@ -234,6 +243,8 @@ def load_library():
     lib.gf_adjust_fusion_break.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, P(gf_break_ref), C.c_uint32, P(gf_break_job),
                                            C.c_uint64, P(gf_break_out)]
     lib.gf_adjust_fusion_break.restype = C.c_int
+    lib.gf_index_set_output_mode.argtypes = [C.c_void_p, C.c_uint32]
+    lib.gf_index_set_output_mode.restype = C.c_int
     lib.gf_reference_create.argtypes = [P(gf_ref_contig), C.c_uint32, C.c_int, P(C.c_void_p)]
     lib.gf_reference_create.restype = C.c_int
     lib.gf_reference_destroy.argtypes = [C.c_void_p]

@@ -114,7 +114,7 @@ void destroy_handle(gf_index* idx) {
     for (auto& s : idx->stage) {
         s.seq1.release(); s.qual1.release(); s.off1.release();
         s.seq2.release(); s.qual2.release(); s.off2.release();
-        s.out.release(); s.nout.release();
+        s.out.release(); s.nout.release(); s.out2.release(); s.keys.release();
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.done) cudaEventDestroy(s.done);
     }
@@ -237,6 +237,27 @@ void gf_sort_matches(gf_match* m, uint64_t n) {
     });
 }
 
+/* GF_OUT_BUCKET_ORDER: records by (device-computed key, pair_idx, source) */
+static void order_by_keys(gf_match* m, const std::vector<unsigned long long>& keys, uint64_t n) {
+    std::vector<uint64_t> perm(n);
+    for (uint64_t i = 0; i < n; i++) perm[i] = i;
+    std::sort(perm.begin(), perm.end(), [&](uint64_t a, uint64_t b) {
+        if (keys[a] != keys[b]) return keys[a] < keys[b];
+        if (m[a].pair_idx != m[b].pair_idx) return m[a].pair_idx < m[b].pair_idx;
+        return m[a].source < m[b].source;
+    });
+    std::vector<gf_match> tmp(m, m + n);
+    for (uint64_t i = 0; i < n; i++) m[i] = tmp[perm[i]];
+}
+
+int gf_index_set_output_mode(gf_index* idx, uint32_t mode) {
+    if (!idx) return fail(GF_E_INVALID, "NULL argument");
+    if (mode & ~(GF_OUT_DROP_FILTERED | GF_OUT_BUCKET_ORDER)) return fail(GF_E_INVALID, "unknown output mode bits");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    idx->out_mode = mode;
+    return GF_OK;
+}
+
 static int validate_batch(const gf_batch* in) {
     if (!in) return fail(GF_E_INVALID, "batch is NULL");
     if (in->n == 0) return GF_OK;
@@ -293,6 +314,7 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
     std::vector<unsigned long long> launches0(nh);
     for (uint32_t h = 0; h < nh; h++) launches0[h] = hs[h]->launches;
     std::vector<uint64_t> total_out(nh, 0), d2h(nh, 0);
+    std::vector<std::vector<unsigned long long>> keys(nh); /* GF_OUT_BUCKET_ORDER: device-computed order keys */
     uint64_t h2d = 0;
     std::vector<char> panic(nh, 0);
     GF_CUDA_TRY(cudaEventRecord(idx->ev_start, idx->stream));
@@ -366,11 +388,21 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
             GfStage& sh = hs[h]->stage[k & 1];
             sh.out_cap = (pe ? 2 : 1) * cn;
             GF_CUDA_TRY(sh.out.reserve(sizeof(gf_match) * sh.out_cap));
-            GF_CUDA_TRY(sh.nout.reserve(sizeof(unsigned long long)));
+            GF_CUDA_TRY(sh.nout.reserve(2 * sizeof(unsigned long long)));
             int r = gf_map_device_batch(hs[h], db, sh.out.as<gf_match>(), sh.out_cap, sh.nout.as<unsigned long long>(),
                                         idx->stream, false, h ? idx : nullptr);
             if (r != GF_OK) return r;
             GfHostSlot* hsl = &hs[h]->h_slots[k & 1];
+            if (hs[h]->out_mode) { /* per-record filters + order keys on the device, before the records leave it */
+                GF_CUDA_TRY(sh.out2.reserve(sizeof(gf_match) * sh.out_cap));
+                GF_CUDA_TRY(sh.keys.reserve(sizeof(unsigned long long) * sh.out_cap));
+                r = gf_finish_records_device(hs[h], sh.out.as<gf_match>(), sh.nout.as<unsigned long long>(), sh.out_cap,
+                                             sh.out2.as<gf_match>(), sh.keys.as<unsigned long long>(),
+                                             sh.nout.as<unsigned long long>() + 1, hs[h]->out_mode, idx->stream);
+                if (r != GF_OK) return r;
+                GF_CUDA_TRY(cudaMemcpyAsync(&hsl->n_out2, sh.nout.as<unsigned long long>() + 1, sizeof(unsigned long long),
+                                            cudaMemcpyDeviceToHost, idx->stream));
+            }
             GF_CUDA_TRY(cudaMemcpyAsync(&hsl->counters, hs[h]->ws_counters.p, sizeof(GfMapCounters), cudaMemcpyDeviceToHost,
                                         idx->stream));
             GF_CUDA_TRY(cudaMemcpyAsync(&hsl->n_out, sh.nout.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
@@ -388,10 +420,18 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
             if (r != GF_OK) return r;
             accumulate(hs[h]->stats, *hsl);
             if (hsl->counters.n_ref_panic) panic[h] = 1;
-            const uint64_t cnt = hsl->n_out; /* <= sh.out_cap by construction */
+            const uint32_t mode = hs[h]->out_mode;
+            const uint64_t cnt = mode ? hsl->n_out2 : hsl->n_out; /* <= sh.out_cap by construction */
             if (cnt && total_out[h] + cnt <= caps[h]) {
-                GF_CUDA_TRY(cudaMemcpy(outs[h] + total_out[h], sh.out.p, sizeof(gf_match) * cnt, cudaMemcpyDeviceToHost));
+                GF_CUDA_TRY(cudaMemcpy(outs[h] + total_out[h], mode ? sh.out2.p : sh.out.p, sizeof(gf_match) * cnt,
+                                       cudaMemcpyDeviceToHost));
                 d2h[h] += sizeof(gf_match) * cnt;
+                if (mode & GF_OUT_BUCKET_ORDER) {
+                    keys[h].resize(total_out[h] + cnt);
+                    GF_CUDA_TRY(cudaMemcpy(keys[h].data() + total_out[h], sh.keys.p, sizeof(unsigned long long) * cnt,
+                                           cudaMemcpyDeviceToHost));
+                    d2h[h] += sizeof(unsigned long long) * cnt;
+                }
             }
             d2h[h] += sizeof(GfMapCounters) + sizeof(unsigned long long);
             total_out[h] += cnt;
@@ -428,7 +468,8 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
         }
         n_outs[h] = total_out[h];
         if (total_out[h] > caps[h]) { rc = fail(GF_E_CAPACITY, "out_cap too small; *n_out holds the required count"); continue; }
-        gf_sort_matches(outs[h], total_out[h]);
+        if (hs[h]->out_mode & GF_OUT_BUCKET_ORDER) order_by_keys(outs[h], keys[h], total_out[h]);
+        else gf_sort_matches(outs[h], total_out[h]);
         if (panic[h] && rc == GF_OK)
             rc = fail(GF_E_REF_PANIC,
                       "a candidate needs an edit distance over more than 640 columns: the reference panics here "
@@ -615,11 +656,21 @@ int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8
     if (db.max_len == 0) db.max_len = 1;
     const uint64_t cap = (pe ? 2 : 1) * n;
     GF_CUDA_TRY(sg.out.reserve(sizeof(gf_match) * cap));
-    GF_CUDA_TRY(sg.nout.reserve(sizeof(unsigned long long)));
+    GF_CUDA_TRY(sg.nout.reserve(2 * sizeof(unsigned long long)));
     const unsigned long long launches0 = idx->launches;
     rc = gf_map_device_batch(idx, db, sg.out.as<gf_match>(), cap, sg.nout.as<unsigned long long>(), st, false);
     if (rc != GF_OK) return rc;
     GfHostSlot* h = &idx->h_slots[0];
+    const uint32_t mode = idx->out_mode;
+    if (mode) {
+        GF_CUDA_TRY(sg.out2.reserve(sizeof(gf_match) * cap));
+        GF_CUDA_TRY(sg.keys.reserve(sizeof(unsigned long long) * cap));
+        rc = gf_finish_records_device(idx, sg.out.as<gf_match>(), sg.nout.as<unsigned long long>(), cap, sg.out2.as<gf_match>(),
+                                      sg.keys.as<unsigned long long>(), sg.nout.as<unsigned long long>() + 1, mode, st);
+        if (rc != GF_OK) return rc;
+        GF_CUDA_TRY(cudaMemcpyAsync(&h->n_out2, sg.nout.as<unsigned long long>() + 1, sizeof(unsigned long long),
+                                    cudaMemcpyDeviceToHost, st));
+    }
     GF_CUDA_TRY(cudaMemcpyAsync(&h->counters, idx->ws_counters.p, sizeof(GfMapCounters), cudaMemcpyDeviceToHost, st));
     GF_CUDA_TRY(cudaMemcpyAsync(&h->n_out, sg.nout.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     GF_CUDA_TRY(cudaEventRecord(idx->ev_end, st));
@@ -633,11 +684,19 @@ int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8
     idx->stats.ms_total = ms;
     GF_CUDA_TRY(cudaEventElapsedTime(&idx->stats.ms_ingest, idx->ev_start, idx->ev_prep));
     idx->stats.kernel_launches = idx->launches - launches0 + 3;
-    *n_out = h->n_out;
-    if (h->n_out > out_cap) return fail(GF_E_CAPACITY, "out_cap too small; *n_out holds the required count");
-    if (h->n_out) GF_CUDA_TRY(cudaMemcpy(out, sg.out.p, sizeof(gf_match) * h->n_out, cudaMemcpyDeviceToHost));
-    idx->stats.d2h_bytes = sizeof(gf_match) * h->n_out + sizeof(GfMapCounters) + 8;
-    gf_sort_matches(out, h->n_out);
+    const uint64_t n_rec = mode ? h->n_out2 : h->n_out;
+    *n_out = n_rec;
+    if (n_rec > out_cap) return fail(GF_E_CAPACITY, "out_cap too small; *n_out holds the required count");
+    if (n_rec) GF_CUDA_TRY(cudaMemcpy(out, mode ? sg.out2.p : sg.out.p, sizeof(gf_match) * n_rec, cudaMemcpyDeviceToHost));
+    idx->stats.d2h_bytes = sizeof(gf_match) * n_rec + sizeof(GfMapCounters) + 8;
+    if (mode & GF_OUT_BUCKET_ORDER) {
+        std::vector<unsigned long long> keys(n_rec);
+        if (n_rec) GF_CUDA_TRY(cudaMemcpy(keys.data(), sg.keys.p, sizeof(unsigned long long) * n_rec, cudaMemcpyDeviceToHost));
+        idx->stats.d2h_bytes += sizeof(unsigned long long) * n_rec;
+        order_by_keys(out, keys, n_rec);
+    } else {
+        gf_sort_matches(out, n_rec);
+    }
     if (h->counters.n_ref_panic)
         return fail(GF_E_REF_PANIC, "a candidate needs an edit distance over more than 640 columns (reference panics)");
     return GF_OK;

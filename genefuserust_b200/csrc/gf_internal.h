@@ -59,13 +59,15 @@ struct GfMapCounters {
 
 struct GfStage { /* one in-flight chunk of a host batch */
     GfBuf seq1, qual1, off1, seq2, qual2, off2, out, nout;
+    GfBuf out2, keys; /* output mode != 0: compacted records + their order keys (nout holds two counters then) */
     cudaEvent_t copied = nullptr, done = nullptr;
     uint64_t n = 0, pair_base = 0, out_cap = 0;
 };
 struct GfHostSlot { /* pinned host memory the device writes results of one call/chunk into */
     GfMapCounters counters;
     unsigned long long n_out;
-    unsigned long long pad[15];
+    unsigned long long n_out2; /* records left after the device-side filter (output mode != 0) */
+    unsigned long long pad[14];
 };
 
 /* gf_fastq.cu: FASTQ text already on the device -> per-record start/end/quality-start tables */
@@ -109,6 +111,7 @@ struct gf_index {
     gf_map_stats stats{};
     unsigned long long launches = 0;
     int sm_count = 148;
+    uint32_t out_mode = 0; /* GF_OUT_* (gf_index_set_output_mode) */
 };
 
 /* gf_index.cu */
@@ -136,6 +139,10 @@ struct GfDevBatch {
  * stream instead of running k_prep again (only taken on the split-screen path, reads <= 256 bases; ignored otherwise) */
 int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uint64_t out_cap,
                         unsigned long long* d_n_out, cudaStream_t stream, bool record_events, gf_index* store_owner = nullptr);
+/* output mode: drop flagged records / compute the bucket-order keys of the records k_verify finished (d_in[0 .. *d_n_in)) */
+int gf_finish_records_device(gf_index* idx, const gf_match* d_in, const unsigned long long* d_n_in, uint64_t in_cap,
+                             gf_match* d_out2, unsigned long long* d_keys, unsigned long long* d_n_out2, uint32_t mode,
+                             cudaStream_t stream);
 int gf_fast_merge_device(gf_index* idx, const GfDevBatch& b, gf_merge_info* d_out, cudaStream_t stream);
 int gf_adjust_break_device(gf_index* idx, const uint8_t* d_bytes, const gf_break_ref* d_refs, const gf_break_job* d_jobs,
                            uint64_t n_jobs, gf_break_out* d_out, unsigned int* d_n_undefined, cudaStream_t stream);

@@ -1246,6 +1246,25 @@ __global__ void __launch_bounds__(VF_WARPS * 32) k_adjust_break(AdjustParams P) 
     }
 }
 
+/* ------------------------------------------------------------------------------------------------ */
+/* k_finish: the per-record part of FusionMapper::filter_matches (fusion_mapper.rs:298-377: a record with any filter flag is
+ * removed) and the key sort_matches orders by (add_match bucket :263, read_break descending, read length ascending,
+ * read_match.rs:203-229; the name tie-break stays with the host, which owns the names).  Thread per record. */
+__global__ void k_finish(const gf_match* __restrict__ in, const unsigned long long* __restrict__ n_in, unsigned long long in_cap,
+                         gf_match* __restrict__ out, unsigned long long* __restrict__ keys, unsigned long long* __restrict__ n_out,
+                         uint32_t n_genes, uint32_t mode) {
+    unsigned long long n = *n_in;
+    if (n > in_cap) n = in_cap;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const gf_match m = in[i];
+        if ((mode & GF_OUT_DROP_FILTERED) && m.filter_flags) continue;
+        const unsigned long long slot = atomicAdd(n_out, 1ull);
+        out[slot] = m;
+        keys[slot] = gf_match_order_key(n_genes, &m);
+    }
+}
+
 template <class K>
 cudaError_t set_smem(K kernel, size_t bytes) {
     if (bytes <= 48 * 1024) return cudaSuccess;
@@ -1428,6 +1447,16 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
         idx->launches += 2;
     }
     if (record_events) GF_CUDA_TRY(cudaEventRecord(idx->ev_exact, st));
+    return GF_OK;
+}
+
+int gf_finish_records_device(gf_index* idx, const gf_match* d_in, const unsigned long long* d_n_in, uint64_t in_cap,
+                             gf_match* d_out2, unsigned long long* d_keys, unsigned long long* d_n_out2, uint32_t mode,
+                             cudaStream_t st) {
+    GF_CUDA_TRY(cudaMemsetAsync(d_n_out2, 0, sizeof(unsigned long long), st));
+    k_finish<<<(unsigned)idx->sm_count, 256, 0, st>>>(d_in, d_n_in, in_cap, d_out2, d_keys, d_n_out2, idx->n_genes, mode);
+    GF_CUDA_TRY(cudaGetLastError());
+    idx->launches++;
     return GF_OK;
 }
 

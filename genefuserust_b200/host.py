@@ -292,6 +292,29 @@ class FusionMapper:
         _check(self.lib, self.lib.gf_fast_merge(self.m_indexer.h, C.byref(st), out))
         return [(o.merged, o.olen, o.diff, o.merged_len) for o in out[:batch.n]]
 
+    def set_output_mode(self, mode):
+        """GF_OUT_DROP_FILTERED | GF_OUT_BUCKET_ORDER: the per-record filters of filter_matches and the bucket / sort_matches
+        key order are applied on the device (include/genefuse_gpu.h); finish_order() then settles the read-name ties."""
+        _check(self.lib, self.lib.gf_index_set_output_mode(self.m_indexer.h, mode))
+
+    def finish_order(self, records, read_name_of):
+        """records in GF_OUT_BUCKET_ORDER order -> the reference's final order: inside every run of equal
+        gf_match_order_key (same bucket, read_break and read length) sort by read name descending, stable
+        (read_match.rs:228, fusion_mapper.rs:384)."""
+        from ._abi import gf_match_order_key
+        out, i = [], 0
+        while i < len(records):
+            k = gf_match_order_key(self.n_genes, records[i])
+            j = i
+            while j < len(records) and gf_match_order_key(self.n_genes, records[j]) == k:
+                j += 1
+            run = records[i:j]
+            if j - i > 1:
+                sort_read_matches(run, read_name_of)
+            out.extend(run)
+            i = j
+        return out
+
     def map_stats(self):
         out = gf_map_stats()
         _check(self.lib, self.lib.gf_get_map_stats(self.m_indexer.h, C.byref(out)), allow=(GF_E_REF_PANIC,))

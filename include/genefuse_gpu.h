@@ -228,6 +228,33 @@ void gf_sort_matches(gf_match* m, uint64_t n); /* by (pair_idx, source), host */
 int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8_t* fq2, uint64_t bytes2,
                  gf_match* out, uint64_t out_cap, uint64_t* n_out, uint64_t* n_records);
 
+/* ---- post-filters and bucket order on the device ----
+ * What the reference does with the records after the scan: add_match drops each into bucket n_genes * right.contig +
+ * left.contig (src/core/fusion_mapper.rs:253-275), filter_matches removes records by three per-record predicates (:298-377,
+ * = gf_match.filter_flags), sort_matches orders every bucket by read_break descending, read length ascending, read name
+ * descending, stable (:379-385, src/core/read_match.rs:203-229).  With an output mode set, the HOST-batch entry points
+ * (gf_map_pairs, gf_list_map_pairs, gf_map_fastq, gf_multi_map_pairs) do the first steps on the device, next to k_verify:
+ *   GF_OUT_DROP_FILTERED  records with filter_flags != 0 are dropped before the device -> host copy;
+ *   GF_OUT_BUCKET_ORDER   a 53-bit sort key (bucket, 2047 - read_break, seq_len) is computed per record on the device and the
+ *                         records come back ordered by (key, pair_idx, source): bucket order, and inside a bucket the
+ *                         reference's order up to the read-name tie-break.  Records with equal gf_match_order_key() form a
+ *                         run in push order; the caller, who owns the names, orders such a run by name descending (stable).
+ * Mode 0 (default): every record, ordered by (pair_idx, source).  gf_map_pairs_device* ignore the mode. */
+#define GF_OUT_DROP_FILTERED 1u
+#define GF_OUT_BUCKET_ORDER 2u
+int gf_index_set_output_mode(gf_index* idx, uint32_t mode);
+/* the key GF_OUT_BUCKET_ORDER sorts by (smaller first); n_genes = the index's gene count */
+#ifdef __CUDACC__
+#define GF_HOST_DEVICE __host__ __device__
+#else
+#define GF_HOST_DEVICE
+#endif
+static inline GF_HOST_DEVICE uint64_t gf_match_order_key(uint32_t n_genes, const gf_match* m) {
+    const uint64_t bucket = (uint64_t)((int64_t)n_genes * m->r_contig + m->l_contig);
+    const uint64_t brk = (uint64_t)(2047 - (m->read_break < 0 ? 0 : (m->read_break > 2047 ? 2047 : m->read_break)));
+    return (bucket << 23) | (brk << 12) | (uint64_t)(m->seq_len & 0xFFF);
+}
+
 int gf_get_map_stats(const gf_index* idx, gf_map_stats* out);
 
 /* Parity hook: run only the device fast_merge on a HOST batch. */

@@ -753,6 +753,52 @@ int orc_segment_mask(const uint8_t* mask, int32_t seqlen, int64_t gp1, int64_t g
 
 int64_t orc_make_kmer(const uint8_t* seq, int32_t pos) { return make_kmer(seq, pos, -1, 1); }
 
+
+/* ---- FusionMapper::add_match (src/core/fusion_mapper.rs:253-275), the per-record filters of filter_matches (:298-377, as
+ * already decided in gf_match.filter_flags by orc_scan_pairs) and sort_matches (:379-385) with ReadMatch's order
+ * (src/core/read_match.rs:203-229).  `names[i]` = m_read.m_name of record i (NUL-terminated).  Records are pushed in input
+ * order (= the reference's push order at -t 1), flagged ones are dropped when drop_filtered != 0 (the three retain() passes),
+ * every bucket is sorted with sort_by(|a, b| b.partial_cmp(a)) (stable), and the buckets are written out in index order.
+ * out_index[k] = position in `in` of the k-th output record.  Returns the number written. ---- */
+namespace {
+struct RmLite {
+    int32_t m_read_break;
+    size_t seq_len;       /* m_read.m_seq.m_str.len() */
+    const char* m_name;   /* m_read.m_name */
+    uint64_t src;         /* index in the input */
+};
+/* impl PartialOrd for ReadMatch (read_match.rs:203-229): -1 Less, 0 Equal, 1 Greater */
+int rm_partial_cmp(const RmLite& self, const RmLite& other) {
+    if (self.m_read_break != other.m_read_break) return self.m_read_break < other.m_read_break ? -1 : 1;
+    /* other.len().partial_cmp(&self.len()) */
+    if (other.seq_len != self.seq_len) return other.seq_len < self.seq_len ? -1 : 1;
+    const int c = strcmp(self.m_name, other.m_name); /* String's order = byte-wise, like strcmp on NUL-free names */
+    return c < 0 ? -1 : (c > 0 ? 1 : 0);
+}
+}  // namespace
+
+uint64_t orc_bucket_sort(const gf_match* in, uint64_t n, uint32_t n_genes, const char* const* names, int drop_filtered,
+                         uint64_t* out_index, int64_t* out_bucket) {
+    std::vector<std::vector<RmLite>> fusion_matches((size_t)n_genes * n_genes); /* fusion_mapper.rs:47-49 */
+    for (uint64_t i = 0; i < n; i++) {
+        if (drop_filtered && in[i].filter_flags) continue;
+        const int32_t index = (int32_t)n_genes * (int32_t)in[i].r_contig + (int32_t)in[i].l_contig; /* :263 */
+        fusion_matches[(size_t)index].push_back(RmLite{in[i].read_break, (size_t)in[i].seq_len, names[i], i});
+    }
+    uint64_t w = 0;
+    for (size_t b = 0; b < fusion_matches.size(); b++) {
+        auto& v = fusion_matches[b];
+        /* rmv.sort_by(|a, b| b.partial_cmp(a).unwrap()): a goes first iff b.partial_cmp(a) == Less; slice::sort_by is stable */
+        std::stable_sort(v.begin(), v.end(), [](const RmLite& a, const RmLite& bb) { return rm_partial_cmp(bb, a) < 0; });
+        for (const RmLite& r : v) {
+            out_index[w] = r.src;
+            if (out_bucket) out_bucket[w] = (int64_t)b;
+            w++;
+        }
+    }
+    return w;
+}
+
 static thread_local uint64_t g_counters[6];
 
 /* src/core/pescanner.rs:427-518 (PE) / src/core/sescanner.rs:183-205 (SE) */

@@ -76,6 +76,11 @@ int32_t orc_get_ref_seq(const uint8_t* ref, int32_t ref_len, int32_t start, int3
 int orc_adjust_fusion_break(const uint8_t* seq, int32_t len, int32_t read_break, const uint8_t* left_ref, int32_t left_len,
                             const uint8_t* right_ref, int32_t right_len, int32_t out[3]);
 
+/* add_match buckets (src/core/fusion_mapper.rs:253-275) + sort_matches (:379-385) with ReadMatch::partial_cmp
+ * (src/core/read_match.rs:203-229); see gf_oracle.cpp.  out_index / out_bucket need n entries. */
+uint64_t orc_bucket_sort(const gf_match* in, uint64_t n, uint32_t n_genes, const char* const* names, int drop_filtered,
+                         uint64_t* out_index, int64_t* out_bucket);
+
 /* ---- Matcher (src/core/matcher.rs) as called from FusionMapper::remove_alignables (src/core/fusion_mapper.rs:488-542);
  * gf_oracle_matcher.cpp.  Places where the Rust code panics are returned as codes. ---- */
 typedef struct orc_matcher orc_matcher;

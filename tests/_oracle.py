@@ -70,6 +70,8 @@ def lib():
     L.orc_adjust_fusion_break.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32,
                                           P(C.c_int32)]
     L.orc_adjust_fusion_break.restype = C.c_int
+    L.orc_bucket_sort.argtypes = [P(gf_match), C.c_uint64, C.c_uint32, P(C.c_char_p), C.c_int, P(C.c_uint64), P(C.c_int64)]
+    L.orc_bucket_sort.restype = C.c_uint64
     L.orc_remove_alignables.argtypes = [P(gf_ref_contig), C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                         P(gf_alignable_result)]
     L.orc_remove_alignables.restype = C.c_int
@@ -215,3 +217,16 @@ def remove_alignables(contigs, seqs):
     rc = L.orc_remove_alignables(arr, len(contigs), arena.ctypes.data if len(arena) else None, off.ctypes.data, len(seqs),
                                  flags.ctypes.data, C.byref(res))
     return flags[:len(seqs)], res, rc
+
+
+def bucket_sort(records, n_genes, names, drop_filtered=True):
+    """add_match + per-record filters + sort_matches (fusion_mapper.rs:253-275, 298-385; read_match.rs:203-229).
+    records: list of gf_match (push order), names: list of bytes.  Returns [(index into records, bucket), ...]."""
+    L = lib()
+    n = len(records)
+    arr = (gf_match * max(1, n))(*records)
+    nm = (C.c_char_p * max(1, n))(*names)
+    oi = (C.c_uint64 * max(1, n))()
+    ob = (C.c_int64 * max(1, n))()
+    k = L.orc_bucket_sort(arr, n, n_genes, nm, 1 if drop_filtered else 0, oi, ob)
+    return [(int(oi[i]), int(ob[i])) for i in range(k)]

@@ -26,6 +26,9 @@ def built():
 def test_library_exports_every_declared_symbol(built):
     hdr = open(os.path.join(ROOT, "include", "genefuse_gpu.h")).read()
     declared = set(re.findall(r"\b(gf_[a-z_]+)\s*\(", hdr))
+    inline = set(re.findall(r"static inline [A-Z_ ]*\w+ (gf_[a-z_]+)\s*\(", hdr))   # defined in the header itself
+    assert inline == {"gf_match_order_key"}
+    declared -= inline
     assert declared == set(_abi.EXPORTS), declared ^ set(_abi.EXPORTS)
     for name in declared:
         assert getattr(built, name) is not None
@@ -210,12 +213,16 @@ def test_header_is_plain_c(tmp_path):
     with the ctypes mirror on the struct sizes"""
     import subprocess
     src = tmp_path / "hdr.c"
-    src.write_text('#include "genefuse_gpu.h"\n#include <stdio.h>\nint main(void){ printf("%zu %zu %zu %zu %zu %zu %zu\\n", '
+    src.write_text('#include "genefuse_gpu.h"\n#include <stdio.h>\nint main(void){ gf_match m = {0}; '
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %llu\\n", '
                    'sizeof(gf_match), sizeof(gf_batch), sizeof(gf_params), sizeof(gf_map_stats), sizeof(gf_break_ref), '
-                   'sizeof(gf_break_job), sizeof(gf_break_out)); return 0; }\n')
+                   'sizeof(gf_break_job), sizeof(gf_break_out), sizeof(gf_ref_contig), sizeof(gf_reference_info), '
+                   'sizeof(gf_alignable_result), (unsigned long long)gf_match_order_key(136, &m)); return 0; }\n')
     exe = tmp_path / "hdr"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
                            str(src), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     assert sizes == [C.sizeof(_abi.gf_match), C.sizeof(_abi.gf_batch), C.sizeof(_abi.gf_params), C.sizeof(_abi.gf_map_stats),
-                     C.sizeof(_abi.gf_break_ref), C.sizeof(_abi.gf_break_job), C.sizeof(_abi.gf_break_out)]
+                     C.sizeof(_abi.gf_break_ref), C.sizeof(_abi.gf_break_job), C.sizeof(_abi.gf_break_out),
+                     C.sizeof(_abi.gf_ref_contig), C.sizeof(_abi.gf_reference_info), C.sizeof(_abi.gf_alignable_result),
+                     _abi.gf_match_order_key(136, _abi.gf_match())]
