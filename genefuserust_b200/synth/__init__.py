@@ -85,8 +85,10 @@ class Panel:
         return [(s.tobytes(), bool(r)) for s, r in zip(self.seqs, self.reversed)]
 
 
-def make_panel(seed=20240201, scale=1.0, max_genes=None, n_fusions=20, plant=True):
-    """cancer.csv-shaped panel.  `scale` shrinks every gene length (tests); 1.0 = 15.1 Mbases."""
+def make_panel(seed=20240201, scale=1.0, max_genes=None, n_fusions=20, plant=True, repeat_frac=0.0):
+    """cancer.csv-shaped panel.  `scale` shrinks every gene length (tests); 1.0 = 15.1 Mbases.  repeat_frac > 0 plants
+    blocks of 300..3000 bases in 2..5 copies each (either strand) over random genes until that fraction of the panel's
+    bases belongs to a copy: NORMAL dupe keys, the shape of interspersed repeats in real genes."""
     table = load_gene_table()
     if max_genes:
         table = table[:max_genes]
@@ -111,6 +113,25 @@ def make_panel(seed=20240201, scale=1.0, max_genes=None, n_fusions=20, plant=Tru
         put(1, len(seqs[1]) // 2, np.frombuffer(b"AT" * 200, dtype=np.uint8))
         put(2, len(seqs[2]) // 2, np.frombuffer(b"A" * 100, dtype=np.uint8))
         put(4, len(seqs[4]) // 2, np.frombuffer(b"N" * 500, dtype=np.uint8))
+    if repeat_frac > 0:
+        rr = np.random.RandomState((seed + 4242) & 0x7FFFFFFF)
+        total = sum(len(s) for s in seqs)
+        planted = 0
+        comp = np.zeros(256, dtype=np.uint8)
+        for a_, b_ in zip(b"ACGTN", b"TGCAN"):
+            comp[a_] = b_
+        k = 0
+        while planted < repeat_frac * total:
+            blk = random_bases(seed + 100000 + k, int(rr.randint(300, 3001)))
+            k += 1
+            for _ in range(int(rr.randint(2, 6))):
+                gi = int(rr.randint(0, len(seqs)))
+                s = seqs[gi]
+                if len(s) <= len(blk) + 2:
+                    continue
+                pos = int(rr.randint(0, len(s) - len(blk)))
+                s[pos:pos + len(blk)] = blk if rr.rand() < 0.5 else comp[blk[::-1]]
+                planted += len(blk)
     fusions = []
     ng = len(seqs)
     for k in range(n_fusions):

@@ -54,6 +54,17 @@ def main():
     # tinyref contigs — src/core/fasta_reader.rs:237-238
     s = strings_in("src/core/fasta_reader.rs", 232, 245)
     kat["tinyref"] = {"cite": "src/core/fasta_reader.rs:232-279", "strings": s}
+    # Gene::pos2str strings of testdata/fusions.csv — src/core/fusion.rs:116-141 (the test compares against these literals)
+    lines = open(os.path.join(REF, "src/core/fusion.rs")).read().split("\n")[115:141]
+    cases, gene = [], None
+    for ln in lines:
+        g = re.search(r'm_name == "([A-Z0-9]+)"', ln)
+        if g:
+            gene = g.group(1)
+        c = re.search(r'pos2str\((-?\d+)\)\.unwrap\(\) != "([^"]*)"', ln)
+        if c:
+            cases.append([gene, int(c.group(1)), c.group(2)])
+    kat["pos2str"] = {"cite": "src/core/fusion.rs:116-141 (over testdata/fusions.csv)", "cases": cases}
     json.dump(kat, open(os.path.join(HERE, "kat.json"), "w"), indent=1)
 
     td = os.path.join(HERE, "testdata")
