@@ -24,7 +24,7 @@ int fail(int code, const std::string& msg) {
 void accumulate(gf_map_stats& st, const GfHostSlot& h) {
     st.n_sequences += h.counters.n_sequences;
     st.n_probes_pass1 += h.counters.n_probes;
-    st.n_survivors += h.counters.n_survivors;
+    st.n_survivors += h.counters.n_survivors + h.counters.n_survivors_total;
     st.n_matches += h.n_out;
     st.seq_bytes += h.counters.seq_bytes;
 }
@@ -105,9 +105,7 @@ void destroy_handle(gf_index* idx) {
     idx->ws_survivors.release();
     idx->ws_counters.release();
     idx->ws_gtbl.release();
-    idx->ws_seq_words.release();
-    idx->ws_seq_meta.release();
-    idx->ws_seq_seed.release();
+    idx->ws_seq_chunks.release();
     idx->ws_seq_lists.release();
     idx->fq[0].release();
     idx->fq[1].release();
@@ -119,8 +117,11 @@ void destroy_handle(gf_index* idx) {
         if (s.done) cudaEventDestroy(s.done);
     }
     if (idx->h_slots) cudaFreeHost(idx->h_slots);
-    for (cudaEvent_t e : {idx->ev_start, idx->ev_screen, idx->ev_exact, idx->ev_end, idx->ev_prep, idx->ev_seed, idx->ev_diag})
+    for (cudaEvent_t e : {idx->ev_start, idx->ev_end, idx->ev_ingest})
         if (e) cudaEventDestroy(e);
+    for (GfChunkEvents& ce : idx->chunk_events)
+        for (cudaEvent_t e : ce.e)
+            if (e) cudaEventDestroy(e);
     if (idx->stream) cudaStreamDestroy(idx->stream);
     if (idx->copy_stream) cudaStreamDestroy(idx->copy_stream);
     if (idx->ev_busy) cudaEventDestroy(idx->ev_busy);
@@ -191,10 +192,8 @@ int gf_index_create(const gf_gene_span* genes, uint32_t n_genes, const gf_params
             rc = fail(GF_E_CUDA, "cudaStreamCreate failed");
             break;
         }
-        bool ok = cudaEventCreate(&idx->ev_start) == cudaSuccess && cudaEventCreate(&idx->ev_screen) == cudaSuccess &&
-                  cudaEventCreate(&idx->ev_exact) == cudaSuccess && cudaEventCreate(&idx->ev_end) == cudaSuccess &&
-                  cudaEventCreate(&idx->ev_prep) == cudaSuccess && cudaEventCreate(&idx->ev_seed) == cudaSuccess &&
-                  cudaEventCreate(&idx->ev_diag) == cudaSuccess &&
+        bool ok = cudaEventCreate(&idx->ev_start) == cudaSuccess && cudaEventCreate(&idx->ev_end) == cudaSuccess &&
+                  cudaEventCreate(&idx->ev_ingest) == cudaSuccess &&
                   cudaEventCreateWithFlags(&idx->ev_busy, cudaEventDisableTiming) == cudaSuccess;
         for (auto& s : idx->stage)
             ok = ok && cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming) == cudaSuccess &&
@@ -296,13 +295,18 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
     const uint64_t per = (n + n_chunks - 1) / n_chunks;
     n_chunks = (n + per - 1) / per;
 
-    /* the host offsets are at hand: check that they ascend and find the longest read here (it selects the kernel
-     * capacity; a read longer than the caller's hint, or than 1024 bases, fails the call before anything is launched) */
+    /* The host offsets are at hand: they must ascend, and no read may be longer than the caller's hint (or than 1024 bases);
+     * the longest read selects the kernel capacity.  Without a hint the whole table is scanned here, before anything is
+     * launched (several threads).  With a hint every pipeline chunk is checked against it just before it is issued (below),
+     * while the device works on the chunk before: a violation fails the call before that chunk's kernels read anything. */
     uint32_t max_len;
-    {
+    const bool check_per_chunk = in->max_len != 0;
+    if (check_per_chunk) {
+        if (in->max_len > 1024) return fail(GF_E_INVALID, "max_len hint above the kernel capacity of 1024 bases");
+        max_len = in->max_len;
+    } else {
         uint64_t mx = 0;
-        const uint64_t limit = in->max_len ? std::min<uint64_t>(in->max_len, 1024) : 1024;
-        int r = scan_offsets(off1, pe ? off2 : nullptr, n, limit, &mx);
+        int r = scan_offsets(off1, pe ? off2 : nullptr, n, 1024, &mx);
         if (r != GF_OK) return r;
         max_len = (uint32_t)std::max<uint64_t>(mx, 1);
     }
@@ -341,6 +345,11 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
     auto issue = [&](uint64_t k) -> int {
         GfStage& s = idx->stage[k & 1];
         const uint64_t lo = k * per, hi = std::min(n, lo + per), cn = hi - lo;
+        if (check_per_chunk) {
+            uint64_t mx = 0;
+            int r = scan_offsets(off1 + lo, pe ? off2 + lo : nullptr, cn, max_len, &mx);
+            if (r != GF_OK) return r;
+        }
         const uint64_t b1 = off1[lo], e1 = off1[hi];
         GF_CUDA_TRY(s.seq1.reserve(e1 - b1 + 16));
         GF_CUDA_TRY(s.off1.reserve(sizeof(uint64_t) * (cn + 1)));
@@ -390,7 +399,7 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
             GF_CUDA_TRY(sh.out.reserve(sizeof(gf_match) * sh.out_cap));
             GF_CUDA_TRY(sh.nout.reserve(2 * sizeof(unsigned long long)));
             int r = gf_map_device_batch(hs[h], db, sh.out.as<gf_match>(), sh.out_cap, sh.nout.as<unsigned long long>(),
-                                        idx->stream, false, h ? idx : nullptr);
+                                        idx->stream, nullptr, true, h ? idx : nullptr);
             if (r != GF_OK) return r;
             GfHostSlot* hsl = &hs[h]->h_slots[k & 1];
             if (hs[h]->out_mode) { /* per-record filters + order keys on the device, before the records leave it */
@@ -547,18 +556,22 @@ int gf_map_pairs_device_list(gf_index* const* idx, uint32_t n_idx, const gf_batc
         rc = wait_prior_device_work(idx[h], st);
         if (rc != GF_OK) return rc;
     }
+    std::vector<unsigned long long> launches0(n_idx);
+    std::vector<gf_match*> outs(d_out, d_out + n_idx);
+    std::vector<unsigned long long*> nouts(n_idx);
+    for (uint32_t h = 0; h < n_idx; h++) { launches0[h] = idx[h]->launches; nouts[h] = (unsigned long long*)d_n_out[h]; }
+    for (uint32_t h = 0; h < n_idx; h++) GF_CUDA_TRY(cudaEventRecord(idx[h]->ev_start, st));
+    rc = gf_map_device_batches(idx, n_idx, db, outs.data(), out_cap, nouts.data(), st);
+    if (rc != GF_OK) return rc;
     for (uint32_t h = 0; h < n_idx; h++) {
         gf_index* x = idx[h];
-        const unsigned long long launches0 = x->launches;
-        rc = gf_map_device_batch(x, db, d_out[h], out_cap, (unsigned long long*)d_n_out[h], st, true, h ? idx[0] : nullptr);
-        if (rc != GF_OK) return rc;
         GfHostSlot* hsl = &x->h_slots[2];
         GF_CUDA_TRY(cudaMemcpyAsync(&hsl->counters, x->ws_counters.p, sizeof(GfMapCounters), cudaMemcpyDeviceToHost, st));
         GF_CUDA_TRY(cudaMemcpyAsync(&hsl->n_out, d_n_out[h], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         GF_CUDA_TRY(cudaEventRecord(x->ev_end, st));
         x->stats = gf_map_stats{};
         x->stats.n_pairs = in_dev->n;
-        x->stats.kernel_launches = x->launches - launches0;
+        x->stats.kernel_launches = x->launches - launches0[h];
         x->stats_pending = true;
     }
     for (uint32_t h = 0; h < n_idx; h++) { /* after the LAST handle's work: the shared sequence store is read by all of them */
@@ -592,7 +605,9 @@ int gf_map_pairs_device(gf_index* idx, const gf_batch* in_dev, gf_match* d_out, 
     const unsigned long long launches0 = idx->launches;
     rc = wait_prior_device_work(idx, st);
     if (rc != GF_OK) return rc;
-    rc = gf_map_device_batch(idx, db, d_out, out_cap, (unsigned long long*)d_n_out, st, true);
+    GF_CUDA_TRY(cudaEventRecord(idx->ev_start, st));
+    unsigned long long* nout1 = (unsigned long long*)d_n_out;
+    rc = gf_map_device_batches(&idx, 1, db, &d_out, out_cap, &nout1, st);
     if (rc != GF_OK) return rc;
     GfHostSlot* h = &idx->h_slots[2];
     GF_CUDA_TRY(cudaMemcpyAsync(&h->counters, idx->ws_counters.p, sizeof(GfMapCounters), cudaMemcpyDeviceToHost, st));
@@ -631,7 +646,7 @@ int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8
     int rc = gf_fastq_parse_device(sg.seq1.as<uint8_t>(), bytes1, &idx->fq[0], st);
     if (rc == GF_OK && pe) rc = gf_fastq_parse_device(sg.seq2.as<uint8_t>(), bytes2, &idx->fq[1], st);
     if (rc != GF_OK) return rc;
-    GF_CUDA_TRY(cudaEventRecord(idx->ev_prep, st)); /* end of the ingest (the parse synchronises on its record count) */
+    GF_CUDA_TRY(cudaEventRecord(idx->ev_ingest, st)); /* end of the ingest (the parse synchronises on its record count) */
     const uint64_t n = pe ? std::min(idx->fq[0].n_records, idx->fq[1].n_records) : idx->fq[0].n_records;
     *n_records = n;
     idx->stats.n_pairs = n;
@@ -658,7 +673,7 @@ int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8
     GF_CUDA_TRY(sg.out.reserve(sizeof(gf_match) * cap));
     GF_CUDA_TRY(sg.nout.reserve(2 * sizeof(unsigned long long)));
     const unsigned long long launches0 = idx->launches;
-    rc = gf_map_device_batch(idx, db, sg.out.as<gf_match>(), cap, sg.nout.as<unsigned long long>(), st, false);
+    rc = gf_map_device_batch(idx, db, sg.out.as<gf_match>(), cap, sg.nout.as<unsigned long long>(), st, nullptr, true);
     if (rc != GF_OK) return rc;
     GfHostSlot* h = &idx->h_slots[0];
     const uint32_t mode = idx->out_mode;
@@ -682,7 +697,7 @@ int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8
     float ms = 0;
     GF_CUDA_TRY(cudaEventElapsedTime(&ms, idx->ev_start, idx->ev_end));
     idx->stats.ms_total = ms;
-    GF_CUDA_TRY(cudaEventElapsedTime(&idx->stats.ms_ingest, idx->ev_start, idx->ev_prep));
+    GF_CUDA_TRY(cudaEventElapsedTime(&idx->stats.ms_ingest, idx->ev_start, idx->ev_ingest));
     idx->stats.kernel_launches = idx->launches - launches0 + 3;
     const uint64_t n_rec = mode ? h->n_out2 : h->n_out;
     *n_out = n_rec;
@@ -713,21 +728,22 @@ int gf_get_map_stats(const gf_index* cidx, gf_map_stats* out) {
         GF_CUDA_TRY(cudaEventSynchronize(idx->ev_end));
         const GfHostSlot& h = idx->h_slots[2];
         accumulate(idx->stats, h);
-        float a = 0, b = 0, c = 0;
-        GF_CUDA_TRY(cudaEventElapsedTime(&a, idx->ev_start, idx->ev_screen));
-        GF_CUDA_TRY(cudaEventElapsedTime(&b, idx->ev_screen, idx->ev_exact));
-        GF_CUDA_TRY(cudaEventElapsedTime(&c, idx->ev_start, idx->ev_end));
-        idx->stats.ms_screen = a;
-        idx->stats.ms_exact = b;
-        idx->stats.ms_total = c;
-        idx->stats.ms_merge = 0; /* fast_merge is fused into the screen kernel */
-        idx->stats.ms_prep = idx->stats.ms_seed = idx->stats.ms_diag = idx->stats.ms_scan = 0;
-        if (idx->split_events) {
-            GF_CUDA_TRY(cudaEventElapsedTime(&idx->stats.ms_prep, idx->ev_start, idx->ev_prep));
-            GF_CUDA_TRY(cudaEventElapsedTime(&idx->stats.ms_seed, idx->ev_prep, idx->ev_seed));
-            GF_CUDA_TRY(cudaEventElapsedTime(&idx->stats.ms_diag, idx->ev_seed, idx->ev_diag));
-            GF_CUDA_TRY(cudaEventElapsedTime(&idx->stats.ms_scan, idx->ev_diag, idx->ev_screen));
+        /* per-stage device time: the sum over the chunks of the call, from the events between the launches */
+        gf_map_stats& S = idx->stats;
+        S.ms_screen = S.ms_exact = S.ms_merge = S.ms_prep = S.ms_seed = S.ms_diag = S.ms_scan = 0; /* fast_merge is fused into k_prep */
+        for (uint32_t c = 0; c < idx->n_chunks_timed && c < idx->chunk_events.size(); c++) {
+            const GfChunkEvents& ce = idx->chunk_events[c];
+            float t = 0;
+            GF_CUDA_TRY(cudaEventElapsedTime(&t, ce.e[0], ce.e[4])); S.ms_screen += t;
+            GF_CUDA_TRY(cudaEventElapsedTime(&t, ce.e[4], ce.e[5])); S.ms_exact += t;
+            if (idx->split_events) {
+                GF_CUDA_TRY(cudaEventElapsedTime(&t, ce.e[0], ce.e[1])); S.ms_prep += t;
+                GF_CUDA_TRY(cudaEventElapsedTime(&t, ce.e[1], ce.e[2])); S.ms_seed += t;
+                GF_CUDA_TRY(cudaEventElapsedTime(&t, ce.e[2], ce.e[3])); S.ms_diag += t;
+                GF_CUDA_TRY(cudaEventElapsedTime(&t, ce.e[3], ce.e[4])); S.ms_scan += t;
+            }
         }
+        GF_CUDA_TRY(cudaEventElapsedTime(&S.ms_total, idx->ev_start, idx->ev_end));
         idx->stats_pending = false;
         idx->busy = false; /* ev_end was recorded after the work ev_busy stands for */
         rc = check_flags(h);

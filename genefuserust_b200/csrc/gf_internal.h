@@ -54,7 +54,9 @@ struct GfMapCounters {
     unsigned int n_candidates;        /* candidates appended by the exact kernel */
     unsigned int n_ref_panic;         /* edit distances beyond the reference's 640-column limit */
     unsigned int error_flags;         /* bit 0: a read is longer than the kernel capacity; bit 1: survivor list overflow */
-    unsigned long long pad[9];
+    unsigned long long n_survivors_total; /* survivors of the chunks before the current one (device batches run in chunks) */
+    unsigned long long verify_from;       /* records [verify_from, *n_out) belong to the current chunk (k_verify's range) */
+    unsigned long long pad[7];
 };
 
 struct GfStage { /* one in-flight chunk of a host batch */
@@ -79,6 +81,10 @@ struct GfFastqTable {
     void release() { nl.release(); s.release(); e.release(); qs.release(); cnt.release(); off.release(); tmp.release(); }
 };
 
+struct GfChunkEvents { /* start, after k_prep, k_seed, k_diag, the whole screen, exact + verify */
+    cudaEvent_t e[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
 struct gf_index {
     int device = 0;
     gf_params params{};
@@ -95,15 +101,17 @@ struct gf_index {
     cudaEvent_t ev_busy = nullptr; /* recorded at the end of every unsynchronised device-batch call (gf_map_pairs_device*):
                                       the next entry point that touches the handle's workspace waits for it on its stream */
     bool busy = false;
-    cudaEvent_t ev_start = nullptr, ev_screen = nullptr, ev_exact = nullptr, ev_end = nullptr;
-    cudaEvent_t ev_prep = nullptr, ev_seed = nullptr, ev_diag = nullptr; /* between the launches of the split screen */
-    bool split_events = false;                                           /* the last batch recorded them */
+    cudaEvent_t ev_start = nullptr, ev_end = nullptr;  /* whole call */
+    cudaEvent_t ev_ingest = nullptr;                   /* gf_map_fastq: end of the text ingest */
+    std::vector<GfChunkEvents> chunk_events;           /* device-batch path: per chunk, between the launches (created on demand) */
+    uint32_t n_chunks_timed = 0;                       /* chunks of the last device-batch call */
+    bool split_events = false;                         /* the last device batch ran the split screen (prep / seed / diag / scan) */
     bool ev_valid = false;
 
     /* mapping workspace (grow-only) */
     GfBuf ws_survivors, ws_counters, ws_gtbl;
     GfFastqTable fq[2];
-    GfBuf ws_seq_words, ws_seq_meta, ws_seq_seed, ws_seq_lists; /* split screen pipeline (gf_screen_split.cuh) */
+    GfBuf ws_seq_chunks, ws_seq_lists; /* split screen pipeline (gf_screen_split.cuh): sequence store; counters + class lists */
     GfStage stage[2];
     GfHostSlot* h_slots = nullptr; /* [3]: two pipeline stages + the device-batch path */
     bool stats_pending = false;    /* h_slots[2] is being written by an unsynchronised device-batch call */
@@ -137,8 +145,15 @@ struct GfDevBatch {
 };
 /* store_owner != nullptr (list mode): reuse the sequence store `store_owner` filled for the SAME batch just before on the same
  * stream instead of running k_prep again (only taken on the split-screen path, reads <= 256 bases; ignored otherwise) */
+/* ONE chunk.  first: zero the handle's counters and *d_n_out (later chunks of one call accumulate); ev: events to record
+ * between the launches, or nullptr */
 int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uint64_t out_cap,
-                        unsigned long long* d_n_out, cudaStream_t stream, bool record_events, gf_index* store_owner = nullptr);
+                        unsigned long long* d_n_out, cudaStream_t stream, GfChunkEvents* ev, bool first,
+                        gf_index* store_owner = nullptr);
+/* a device-resident batch of any size against nh indices (nh > 1 = list mode): cut into chunks whose workspace stays below
+ * ~5 GB, every chunk converted once (hs[0]) and mapped against each index; records accumulate in d_outs[h] / d_n_outs[h] */
+int gf_map_device_batches(gf_index* const* hs, uint32_t nh, const GfDevBatch& b, gf_match* const* d_outs, uint64_t out_cap,
+                          unsigned long long* const* d_n_outs, cudaStream_t stream);
 /* output mode: drop flagged records / compute the bucket-order keys of the records k_verify finished (d_in[0 .. *d_n_in)) */
 int gf_finish_records_device(gf_index* idx, const gf_match* d_in, const unsigned long long* d_n_in, uint64_t in_cap,
                              gf_match* d_out2, unsigned long long* d_keys, unsigned long long* d_n_out2, uint32_t mode,

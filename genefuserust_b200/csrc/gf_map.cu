@@ -1147,7 +1147,7 @@ __global__ void __launch_bounds__(VF_WARPS * 32) k_verify(VerifyParams P) {
     const uint64_t n_warps = (uint64_t)gridDim.x * VF_WARPS;
     unsigned long long n = *P.n_out;
     if (n > P.out_cap) n = P.out_cap;
-    for (uint64_t ci = (uint64_t)blockIdx.x * VF_WARPS + wib; ci < n; ci += n_warps) {
+    for (uint64_t ci = P.counters->verify_from + (uint64_t)blockIdx.x * VF_WARPS + wib; ci < n; ci += n_warps) {
         gf_match m = P.out[ci];
         __syncwarp();
         const int len = load_sequence(P.b, (uint32_t)(m.pair_idx - P.b.pair_base), m.source, m.merge_olen, W.seq, EX_SEQ_CAP - 16);
@@ -1282,8 +1282,19 @@ static unsigned resident_blocks(K kernel, int threads, size_t smem) {
 }
 
 /* ================================================================================================== */
+/* later chunks of one call: the survivor list starts again at 0, its count so far moves to the running total */
+__global__ void k_roll_counters(GfMapCounters* c, const unsigned long long* n_out, unsigned long long out_cap) {
+    c->n_survivors_total += c->n_survivors;
+    c->n_survivors = 0;
+    c->verify_from = min(*n_out, out_cap); /* records before this index were verified with their own chunk */
+}
+
 int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uint64_t out_cap,
-                        unsigned long long* d_n_out, cudaStream_t st, bool record_events, gf_index* store_owner) {
+                        unsigned long long* d_n_out, cudaStream_t st, GfChunkEvents* ev, bool first, gf_index* store_owner) {
+    const bool record_events = ev != nullptr;
+    if (ev)
+        for (cudaEvent_t& e : ev->e)
+            if (!e) GF_CUDA_TRY(cudaEventCreate(&e));
     const bool paired = b.seq2 != nullptr;
     if (b.n > 0xFFFFFFFFull) {
         gf_set_error("batch too large (n > 2^32-1 pairs): split it");
@@ -1295,9 +1306,13 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
     GF_CUDA_TRY(idx->ws_survivors.reserve(sizeof(uint2) * (size_t)surv_cap));
     GF_CUDA_TRY(idx->ws_counters.reserve(sizeof(GfMapCounters)));
     GfMapCounters* d_cnt = idx->ws_counters.as<GfMapCounters>();
-    GF_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(GfMapCounters), st));
-    GF_CUDA_TRY(cudaMemsetAsync(d_n_out, 0, sizeof(unsigned long long), st));
-    if (record_events) { GF_CUDA_TRY(cudaEventRecord(idx->ev_start, st)); idx->split_events = false; }
+    if (first) {
+        GF_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(GfMapCounters), st));
+        GF_CUDA_TRY(cudaMemsetAsync(d_n_out, 0, sizeof(unsigned long long), st));
+    } else {
+        k_roll_counters<<<1, 1, 0, st>>>(d_cnt, d_n_out, out_cap);
+    }
+    if (record_events) { GF_CUDA_TRY(cudaEventRecord(ev->e[0], st)); idx->split_events = false; }
 
     const int need_major = (idx->params.major_gene_key_requirement + 1) / 2;
     const int need_minor = (idx->params.minor_gene_key_requirement + 1) / 2;
@@ -1320,24 +1335,18 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
         if (small) {
             /* split pipeline: prep -> seed -> diag / scan (gf_screen_split.cuh) */
             const bool w5 = b.max_len <= 160;
-            const int NW3 = w5 ? split::SL<5>::NW3 : split::SL<8>::NW3;
+            const int NCH = w5 ? split::SL<5>::NCH : split::SL<8>::NCH;
             const uint32_t cap = surv_cap;
-            const size_t groups = ((size_t)cap + 31) / 32;
             /* list mode (several indices, one batch): k_prep's output does not depend on the index, so only the first
-             * handle of the list (`store_owner`) converts / merges / stores the sequences; the others read its store */
+             * handle of the list (`store_owner`) converts / merges / stores the sequences; the others read its store (and
+             * overwrite the seed words in it: the handles of one list call run one after the other on one stream) */
             gf_index* own = store_owner ? store_owner : idx;
-            if (!store_owner) {
-                GF_CUDA_TRY(idx->ws_seq_words.reserve(groups * NW3 * 32 * sizeof(uint32_t)));
-                GF_CUDA_TRY(idx->ws_seq_meta.reserve((size_t)cap * sizeof(uint4)));
-            }
-            GF_CUDA_TRY(idx->ws_seq_seed.reserve((size_t)cap * sizeof(uint2)));
-            GF_CUDA_TRY(idx->ws_seq_lists.reserve((size_t)cap * 4 * sizeof(uint32_t) + 64));
+            if (!store_owner) GF_CUDA_TRY(idx->ws_seq_chunks.reserve((size_t)cap * NCH * sizeof(uint4)));
+            GF_CUDA_TRY(idx->ws_seq_lists.reserve((size_t)cap * sizeof(uint32_t) + 64));
             split::SeqStore ss;
-            ss.words = own->ws_seq_words.as<uint32_t>();
-            ss.meta = own->ws_seq_meta.as<uint4>();
-            ss.seed = idx->ws_seq_seed.as<uint2>();
+            ss.chunks = own->ws_seq_chunks.as<uint4>();
             ss.counters = idx->ws_seq_lists.as<unsigned int>();
-            for (int l = 0; l < 4; l++) ss.lists[l] = idx->ws_seq_lists.as<uint32_t>() + 16 + (size_t)l * cap;
+            ss.list = idx->ws_seq_lists.as<uint32_t>() + 16;
             ss.cap = cap;
             GF_CUDA_TRY(cudaMemsetAsync(ss.counters, 0, 64, st));
             if (store_owner) { /* the slot counts of the shared store */
@@ -1364,7 +1373,7 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
                 else { if (paired) GF_LAUNCH_PREP(8, true); else GF_LAUNCH_PREP(8, false); }
             }
 #undef GF_LAUNCH_PREP
-            if (record_events) GF_CUDA_TRY(cudaEventRecord(idx->ev_prep, st));
+            if (record_events) GF_CUDA_TRY(cudaEventRecord(ev->e[1], st));
             split::SeedParams sdp;
             sdp.ix = idx->dev;
             sdp.st = ss;
@@ -1379,15 +1388,15 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
             cp.need_total = sp.need_total;
             cp.need_minor = sp.need_minor;
             const unsigned smc = (unsigned)idx->sm_count;
-#define GF_EV(e) do { if (record_events) GF_CUDA_TRY(cudaEventRecord(idx->e, st)); } while (0)
+#define GF_EV(k) do { if (record_events) GF_CUDA_TRY(cudaEventRecord(ev->e[k], st)); } while (0)
             /* k_diag and k_scan back to back: running them side by side on two streams with split grids measured the same
              * (2.8 vs 2.9 ms), so there is one path */
 #define GF_LAUNCH_CLASSES(WW)                                                                                         \
     do {                                                                                                              \
         split::k_seed<WW><<<smc * resident_blocks(split::k_seed<WW>, 256, 0), 256, 0, st>>>(sdp);                     \
-        GF_EV(ev_seed);                                                                                               \
+        GF_EV(2);                                                                                                     \
         split::k_diag<WW><<<smc * resident_blocks(split::k_diag<WW>, 256, 0), 256, 0, st>>>(cp);                      \
-        GF_EV(ev_diag);                                                                                               \
+        GF_EV(3);                                                                                                     \
         split::k_scan<WW><<<smc * resident_blocks(split::k_scan<WW>, 256, 0), 256, 0, st>>>(cp);                      \
     } while (0)
             if (w5) GF_LAUNCH_CLASSES(5); else GF_LAUNCH_CLASSES(8);
@@ -1405,7 +1414,7 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
         GF_CUDA_TRY(cudaGetLastError());
         idx->launches++;
     }
-    if (record_events) GF_CUDA_TRY(cudaEventRecord(idx->ev_screen, st));
+    if (record_events) GF_CUDA_TRY(cudaEventRecord(ev->e[4], st));
 
     if (b.n) {
         /* exact path over the (device-side) survivor count: persistent grid of all resident warps, no host round trip */
@@ -1446,7 +1455,36 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
         GF_CUDA_TRY(cudaGetLastError());
         idx->launches += 2;
     }
-    if (record_events) GF_CUDA_TRY(cudaEventRecord(idx->ev_exact, st));
+    if (record_events) GF_CUDA_TRY(cudaEventRecord(ev->e[5], st));
+    return GF_OK;
+}
+
+int gf_map_device_batches(gf_index* const* hs, uint32_t nh, const GfDevBatch& b, gf_match* const* d_outs, uint64_t out_cap,
+                          unsigned long long* const* d_n_outs, cudaStream_t st) {
+    /* workspace per pair of a chunk: two store slots (reads <= 256 bases) + list + survivor entries */
+    const bool small = b.max_len != 0 && b.max_len <= 256;
+    const uint64_t per_pair = (small ? 2ull * (b.max_len <= 160 ? split::SL<5>::NCH : split::SL<8>::NCH) * sizeof(uint4) : 0ull) + 8 + 16;
+    uint64_t chunk = std::max<uint64_t>(1u << 20, (5ull << 30) / per_pair);
+    if (const char* e = getenv("GF_DEVICE_CHUNK_PAIRS")) { long long v = atoll(e); if (v >= 1024) chunk = (uint64_t)v; }
+    const uint64_t n_chunks = b.n ? (b.n + chunk - 1) / chunk : 1;
+    const uint64_t per = b.n ? (b.n + n_chunks - 1) / n_chunks : 0;
+    for (uint32_t h = 0; h < nh; h++) {
+        if (hs[h]->chunk_events.size() < n_chunks) hs[h]->chunk_events.resize(n_chunks);
+        hs[h]->n_chunks_timed = (uint32_t)n_chunks;
+    }
+    for (uint64_t c = 0; c < n_chunks; c++) {
+        const uint64_t lo = c * per, hi = std::min(b.n, lo + per);
+        GfDevBatch cb = b;
+        cb.n = hi - lo;
+        cb.s1 += lo; cb.e1 += lo; cb.qs1 += lo;
+        if (cb.s2) { cb.s2 += lo; cb.e2 += lo; cb.qs2 += lo; }
+        cb.pair_base = b.pair_base + lo;
+        for (uint32_t h = 0; h < nh; h++) {
+            int rc = gf_map_device_batch(hs[h], cb, d_outs[h], out_cap, d_n_outs[h], st, &hs[h]->chunk_events[c], c == 0,
+                                         h ? hs[0] : nullptr);
+            if (rc != GF_OK) return rc;
+        }
+    }
     return GF_OK;
 }
 

@@ -601,3 +601,85 @@ def test_list_mode_shared_prep(host, small_panel):
     assert [r.astuple() for r in got[1]] == [r.astuple() for r in mappers[1].scan_single_end(se)]
     for m in mappers:
         m.close()
+
+
+def _device_batch(torch, b):
+    """gf_batch whose pointers are DEVICE pointers (torch owns the memory); returns (struct, keepalive)"""
+    from genefuserust_b200._abi import gf_batch
+    d = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (b.seq1, b.qual1, b.seq2, b.qual2)]
+    o1 = torch.from_numpy(b.off1.view(np.int64)).cuda()
+    o2 = torch.from_numpy(b.off2.view(np.int64)).cuda()
+    db = gf_batch()
+    db.n = b.n
+    db.seq1, db.qual1, db.seq2, db.qual2 = (t.data_ptr() for t in d)
+    db.off1, db.off2 = o1.data_ptr(), o2.data_ptr()
+    db.bytes1, db.bytes2 = int(b.off1[-1]), int(b.off2[-1])
+    db.max_len = b.max_len
+    return db, (d, o1, o2)
+
+
+def _device_records(torch, d_out, d_n, k=0):
+    import ctypes as C
+    from genefuserust_b200._abi import gf_match
+    n = int(d_n[k].item())
+    raw = d_out[:n * C.sizeof(gf_match)].cpu().numpy().tobytes()
+    recs = (gf_match * n).from_buffer_copy(raw)
+    return sorted((r.astuple() for r in recs), key=lambda t: (t[0], t[1]))
+
+
+@pytest.mark.parametrize("read_len,seed", [(150, 51), (250, 52), (300, 53)])
+def test_device_batch_entry_points(host, small_panel, read_len, seed):
+    """gf_map_pairs_device / gf_map_pairs_device_list on device-resident arenas: one chunk and many chunks
+    (GF_DEVICE_CHUNK_PAIRS) give the host path's records; a host-path call issued right behind an unsynchronised device call
+    on the same handle waits for it (the handle's workspace is shared)"""
+    import ctypes as C
+    import torch
+    from genefuserust_b200._abi import gf_map_stats, gf_match
+    genes = small_panel.genes()
+    mappers = [host.FusionMapper.from_gene_spans(g, device=0) for g in (genes, genes[:40], genes[10:70])]
+    b = synth.generate_pairs(small_panel, 50000, read_len=read_len, seed=seed, p_fusion=0.1)
+    want = [[r.astuple() for r in m.scan_pair_end(b)] for m in mappers]
+    assert len(want[0]) > 100
+    lib = mappers[0].lib
+    db, keep = _device_batch(torch, b)
+    cap = 2 * b.n
+    K = len(mappers)
+    d_outs = [torch.empty(cap * C.sizeof(gf_match), dtype=torch.uint8, device="cuda") for _ in range(K)]
+    d_ns = torch.zeros(K, dtype=torch.int64, device="cuda")
+    side = torch.cuda.Stream()
+    for chunk_env in (None, "7000"):
+        if chunk_env:
+            os.environ["GF_DEVICE_CHUNK_PAIRS"] = chunk_env
+        try:
+            # single-index call on a side stream, then (no synchronisation) a host-path call on the same handle
+            rc = lib.gf_map_pairs_device(mappers[0].m_indexer.h, C.byref(db), d_outs[0].data_ptr(), cap, d_ns.data_ptr(),
+                                         C.c_void_p(side.cuda_stream))
+            assert rc == 0, lib.gf_last_error()
+            again = [r.astuple() for r in mappers[0].scan_pair_end(b)]
+            side.synchronize()
+            assert again == want[0]
+            assert _device_records(torch, d_outs[0], d_ns, 0) == want[0]
+            st = gf_map_stats()
+            # two device calls back to back on different streams of one handle
+            rc = lib.gf_map_pairs_device(mappers[0].m_indexer.h, C.byref(db), d_outs[0].data_ptr(), cap, d_ns.data_ptr(),
+                                         C.c_void_p(side.cuda_stream))
+            rc2 = lib.gf_map_pairs_device(mappers[0].m_indexer.h, C.byref(db), d_outs[1].data_ptr(), cap, d_ns.data_ptr() + 8,
+                                          C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            assert rc == 0 and rc2 == 0, lib.gf_last_error()
+            torch.cuda.synchronize()
+            assert _device_records(torch, d_outs[0], d_ns, 0) == want[0] and _device_records(torch, d_outs[1], d_ns, 1) == want[0]
+            assert lib.gf_get_map_stats(mappers[0].m_indexer.h, C.byref(st)) == 0
+            assert st.n_matches == len(want[0]) and st.n_pairs == b.n and st.n_survivors >= len(want[0])
+            # list call
+            hs = (C.c_void_p * K)(*[m.m_indexer.h.value for m in mappers])
+            outs = (C.c_void_p * K)(*[t.data_ptr() for t in d_outs])
+            nouts = (C.c_void_p * K)(*[d_ns.data_ptr() + 8 * k for k in range(K)])
+            rc = lib.gf_map_pairs_device_list(hs, K, C.byref(db), outs, cap, nouts, C.c_void_p(side.cuda_stream))
+            assert rc == 0, lib.gf_last_error()
+            side.synchronize()
+            for k in range(K):
+                assert _device_records(torch, d_outs[k], d_ns, k) == want[k], (chunk_env, k)
+        finally:
+            os.environ.pop("GF_DEVICE_CHUNK_PAIRS", None)
+    for m in mappers:
+        m.close()
