@@ -51,8 +51,8 @@ int mark_device_work(gf_index* idx, cudaStream_t st) {
 
 /* Host offsets of one mate: ascending, every record at most `limit` long.  Returns the longest record in *max_len.
  * (Several threads: ~1 ms per 10 M reads.) */
-int scan_offsets(const uint64_t* off1, const uint64_t* off2, uint64_t n, uint64_t limit, uint64_t* max_len) {
-    const unsigned nt = n < (1u << 16) ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+int scan_offsets(const uint64_t* off1, const uint64_t* off2, uint64_t n, uint64_t limit, uint64_t* max_len, unsigned max_threads = 16) {
+    const unsigned nt = n < (1u << 16) ? 1u : std::max(1u, std::min(max_threads, std::thread::hardware_concurrency()));
     std::vector<uint64_t> part(nt, 0);
     std::vector<char> bad(nt, 0);
     auto work = [&](unsigned t) {
@@ -105,7 +105,9 @@ void destroy_handle(gf_index* idx) {
     idx->ws_survivors.release();
     idx->ws_counters.release();
     idx->ws_gtbl.release();
-    idx->ws_seq_chunks.release();
+    idx->ws_seq_words.release();
+    idx->ws_seq_meta.release();
+    idx->ws_seq_seed.release();
     idx->ws_seq_lists.release();
     idx->fq[0].release();
     idx->fq[1].release();
@@ -347,7 +349,7 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
         const uint64_t lo = k * per, hi = std::min(n, lo + per), cn = hi - lo;
         if (check_per_chunk) {
             uint64_t mx = 0;
-            int r = scan_offsets(off1 + lo, pe ? off2 + lo : nullptr, cn, max_len, &mx);
+            int r = scan_offsets(off1 + lo, pe ? off2 + lo : nullptr, cn, max_len, &mx, 1); /* inline: ~0.3 ms per chunk */
             if (r != GF_OK) return r;
         }
         const uint64_t b1 = off1[lo], e1 = off1[hi];
@@ -622,9 +624,18 @@ int gf_map_pairs_device(gf_index* idx, const gf_batch* in_dev, gf_match* d_out, 
 
 int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8_t* fq2, uint64_t bytes2, gf_match* out,
                  uint64_t out_cap, uint64_t* n_out, uint64_t* n_records) {
+    uint64_t consumed[2];
+    return gf_map_fastq_text(idx, fq1, bytes1, fq2, bytes2, true, out, out_cap, n_out, n_records, consumed);
+}
+
+} /* extern "C" */
+
+int gf_map_fastq_text(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8_t* fq2, uint64_t bytes2, bool final_chunk,
+                      gf_match* out, uint64_t out_cap, uint64_t* n_out, uint64_t* n_records, uint64_t consumed[2]) {
     if (!idx || !n_out || !n_records) return fail(GF_E_INVALID, "NULL argument");
     *n_out = 0;
     *n_records = 0;
+    consumed[0] = consumed[1] = 0;
     if ((bytes1 && !fq1) || (bytes2 && !fq2)) return fail(GF_E_INVALID, "NULL FASTQ buffer");
     if (out_cap && !out) return fail(GF_E_INVALID, "out is NULL");
     std::lock_guard<std::mutex> lk(idx->mu);
@@ -643,8 +654,8 @@ int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8
         GF_CUDA_TRY(sg.seq2.reserve(bytes2 + 32));
         GF_CUDA_TRY(cudaMemcpyAsync(sg.seq2.p, fq2, bytes2, cudaMemcpyHostToDevice, st));
     }
-    int rc = gf_fastq_parse_device(sg.seq1.as<uint8_t>(), bytes1, &idx->fq[0], st);
-    if (rc == GF_OK && pe) rc = gf_fastq_parse_device(sg.seq2.as<uint8_t>(), bytes2, &idx->fq[1], st);
+    int rc = gf_fastq_parse_device(sg.seq1.as<uint8_t>(), bytes1, &idx->fq[0], st, final_chunk);
+    if (rc == GF_OK && pe) rc = gf_fastq_parse_device(sg.seq2.as<uint8_t>(), bytes2, &idx->fq[1], st, final_chunk);
     if (rc != GF_OK) return rc;
     GF_CUDA_TRY(cudaEventRecord(idx->ev_ingest, st)); /* end of the ingest (the parse synchronises on its record count) */
     const uint64_t n = pe ? std::min(idx->fq[0].n_records, idx->fq[1].n_records) : idx->fq[0].n_records;
@@ -652,6 +663,13 @@ int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8
     idx->stats.n_pairs = n;
     idx->stats.h2d_bytes = bytes1 + (pe ? bytes2 : 0);
     if (n == 0) return GF_OK;
+    /* bytes the n whole records cover = one past the newline that ends record n - 1's quality line (shifted table: nl[4 n]) */
+    for (int k = 0; k < (pe ? 2 : 1); k++) {
+        unsigned long long end = 0;
+        GF_CUDA_TRY(cudaMemcpyAsync(&end, idx->fq[k].nl.as<unsigned long long>() + 4 * n, sizeof(end), cudaMemcpyDeviceToHost, st));
+        GF_CUDA_TRY(cudaStreamSynchronize(st));
+        consumed[k] = std::min<uint64_t>(end + 1, k ? bytes2 : bytes1);
+    }
     GfDevBatch db{};
     db.n = n;
     db.seq1 = db.qual1 = sg.seq1.as<uint8_t>();
@@ -716,6 +734,8 @@ int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8
         return fail(GF_E_REF_PANIC, "a candidate needs an edit distance over more than 640 columns (reference panics)");
     return GF_OK;
 }
+
+extern "C" {
 
 static_assert(sizeof(gf_map_stats) == 120 && sizeof(gf_match) == 48, "ABI layout (include/genefuse_gpu.h, _abi.py)");
 int gf_get_map_stats(const gf_index* cidx, gf_map_stats* out) {

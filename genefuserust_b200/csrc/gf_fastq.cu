@@ -98,7 +98,7 @@ __global__ void k_records(const unsigned long long* __restrict__ nl, uint64_t n_
 
 }  // namespace
 
-int gf_fastq_parse_device(const uint8_t* d_text, uint64_t bytes, GfFastqTable* out, cudaStream_t st) {
+int gf_fastq_parse_device(const uint8_t* d_text, uint64_t bytes, GfFastqTable* out, cudaStream_t st, bool final_chunk) {
     out->n_records = 0;
     out->max_len = 0;
     if (bytes == 0) return GF_OK;
@@ -124,7 +124,9 @@ int gf_fastq_parse_device(const uint8_t* d_text, uint64_t bytes, GfFastqTable* o
         gf_set_error("FASTQ buffer holds 2^32 or more lines: pass it in pieces (gf_fastq_stream_*)");
         return GF_E_LIMIT;
     }
-    /* a non-empty unterminated last line still counts as a line (read_line returns > 0): virtual newline at `bytes` */
+    /* a non-empty unterminated last line still counts as a line (read_line returns > 0): virtual newline at `bytes` — but
+     * only at the end of the file: in a streamed chunk the rest of that line has not arrived yet */
+    if (!final_chunk) last = '\n';
     const uint64_t n_lines = (uint64_t)n_nl + (last != '\n' ? 1 : 0);
     GF_CUDA_TRY(out->nl.reserve(sizeof(unsigned long long) * (n_lines + 2)));
     unsigned long long* nl = out->nl.as<unsigned long long>();

@@ -111,7 +111,8 @@ struct gf_index {
     /* mapping workspace (grow-only) */
     GfBuf ws_survivors, ws_counters, ws_gtbl;
     GfFastqTable fq[2];
-    GfBuf ws_seq_chunks, ws_seq_lists; /* split screen pipeline (gf_screen_split.cuh): sequence store; counters + class lists */
+    GfBuf ws_seq_words, ws_seq_meta, ws_seq_seed, ws_seq_lists; /* split screen pipeline (gf_screen_split.cuh): sequence store
+                                                                  (plane words, meta, seeds); counters + the two class lists */
     GfStage stage[2];
     GfHostSlot* h_slots = nullptr; /* [3]: two pipeline stages + the device-batch path */
     bool stats_pending = false;    /* h_slots[2] is being written by an unsynchronised device-batch call */
@@ -129,7 +130,12 @@ int gf_lookup_device(gf_index* idx, const uint32_t* kmers, uint64_t n, gf_lookup
 size_t gf_scan_tmp_elems(uint64_t n);
 cudaError_t gf_exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* tmp, cudaStream_t st);
 
-int gf_fastq_parse_device(const uint8_t* d_text, uint64_t bytes, GfFastqTable* out, cudaStream_t st);
+/* final_chunk: the text ends the file (an unterminated last line is a line); otherwise it is ignored (streamed chunks) */
+int gf_fastq_parse_device(const uint8_t* d_text, uint64_t bytes, GfFastqTable* out, cudaStream_t st, bool final_chunk = true);
+/* gf_api.cu: gf_map_fastq's body.  final_chunk = false (gf_fastq_stream_*): only whole records are mapped and consumed[k]
+ * returns how many bytes of buffer k they covered (the caller carries the rest over); pair_idx counts from 0. */
+int gf_map_fastq_text(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8_t* fq2, uint64_t bytes2, bool final_chunk,
+                      gf_match* out, uint64_t out_cap, uint64_t* n_out, uint64_t* n_records, uint64_t consumed[2]);
 
 /* gf_map.cu */
 struct GfDevBatch {

@@ -1335,16 +1335,22 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
         if (small) {
             /* split pipeline: prep -> seed -> diag / scan (gf_screen_split.cuh) */
             const bool w5 = b.max_len <= 160;
-            const int NCH = w5 ? split::SL<5>::NCH : split::SL<8>::NCH;
+            const int NW3 = w5 ? split::SL<5>::NW3 : split::SL<8>::NW3;
             const uint32_t cap = surv_cap;
+            const size_t groups = ((size_t)cap + 31) / 32;
             /* list mode (several indices, one batch): k_prep's output does not depend on the index, so only the first
-             * handle of the list (`store_owner`) converts / merges / stores the sequences; the others read its store (and
-             * overwrite the seed words in it: the handles of one list call run one after the other on one stream) */
+             * handle of the list (`store_owner`) converts / merges / stores the sequences; the others read its store */
             gf_index* own = store_owner ? store_owner : idx;
-            if (!store_owner) GF_CUDA_TRY(idx->ws_seq_chunks.reserve((size_t)cap * NCH * sizeof(uint4)));
+            if (!store_owner) {
+                GF_CUDA_TRY(idx->ws_seq_words.reserve(groups * NW3 * 32 * sizeof(uint32_t)));
+                GF_CUDA_TRY(idx->ws_seq_meta.reserve((size_t)cap * sizeof(uint4)));
+            }
+            GF_CUDA_TRY(idx->ws_seq_seed.reserve((size_t)cap * sizeof(uint2)));
             GF_CUDA_TRY(idx->ws_seq_lists.reserve((size_t)cap * sizeof(uint32_t) + 64));
             split::SeqStore ss;
-            ss.chunks = own->ws_seq_chunks.as<uint4>();
+            ss.words = own->ws_seq_words.as<uint32_t>();
+            ss.meta = own->ws_seq_meta.as<uint4>();
+            ss.seed = idx->ws_seq_seed.as<uint2>();
             ss.counters = idx->ws_seq_lists.as<unsigned int>();
             ss.list = idx->ws_seq_lists.as<uint32_t>() + 16;
             ss.cap = cap;
@@ -1463,7 +1469,7 @@ int gf_map_device_batches(gf_index* const* hs, uint32_t nh, const GfDevBatch& b,
                           unsigned long long* const* d_n_outs, cudaStream_t st) {
     /* workspace per pair of a chunk: two store slots (reads <= 256 bases) + list + survivor entries */
     const bool small = b.max_len != 0 && b.max_len <= 256;
-    const uint64_t per_pair = (small ? 2ull * (b.max_len <= 160 ? split::SL<5>::NCH : split::SL<8>::NCH) * sizeof(uint4) : 0ull) + 8 + 16;
+    const uint64_t per_pair = (small ? 2ull * ((b.max_len <= 160 ? split::SL<5>::NW3 : split::SL<8>::NW3) * 4 + 16 + 8) : 0ull) + 8 + 16;
     uint64_t chunk = std::max<uint64_t>(1u << 20, (5ull << 30) / per_pair);
     if (const char* e = getenv("GF_DEVICE_CHUNK_PAIRS")) { long long v = atoll(e); if (v >= 1024) chunk = (uint64_t)v; }
     const uint64_t n_chunks = b.n ? (b.n + chunk - 1) / chunk : 1;

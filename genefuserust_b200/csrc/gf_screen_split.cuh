@@ -4,8 +4,8 @@
  * merged/unmerged, seeded/unseeded, short/long and forward/reverse pairs diverge inside a warp).
  *
  *   k_prep   thread per pair      convert R1 / rc(R2) to bit-planes, fast_merge (read.rs:313-440), write the 1-2 sequences
- *                                 that will be mapped (merged, or R1 and R2) into the sequence store: short sequences from
- *                                 slot 0 upwards, long (merged) ones from the top downwards
+ *                                 that will be mapped (merged, or R1 and R2) as bit-planes into a sequence store: short
+ *                                 sequences from slot 0 upwards, long (merged) ones from the top downwards
  *   k_seed   thread per sequence  8 half-word aligned 16-mers of the first 128 bases -> level-1 filter (L2) -> the first
  *                                 present one -> ONE HBM table lookup; appends the sequence to the seeded list (from the
  *                                 front of one array) or the unseeded list (from its back), entries reserved once per block
@@ -19,13 +19,12 @@
  * count2 <= T - c_d.  k_diag drops iff T < need_total or T - c_d < need_minor; k_scan iff P < need_major (T <= 2 P).
  * Survivors re-run the literal algorithm in k_exact, so the screen only has to be conservative.
  *
- * Sequence store layout: ROW-major, one 16-byte entry per 32 bases: slot s, chunk k at chunks[s * NCH + k] =
- * {lo word, hi word, valid word, aux}.  A thread reads its own sequence with 128-bit loads that use whole 32-byte sectors,
- * whatever order the class lists put the slots in (the earlier column-major store was only coalesced for consecutive slots:
- * k_diag / k_scan re-read 5 GB for 1.6 GB written).  aux carries what used to be separate arrays:
- *   chunk 0: len << 16 | source | olen << 2 | diff << 14      chunk 1: pair index
- *   chunk 2: seed value (k_seed)                              chunk 3: seed offset / probed-candidate masks (k_seed)
- * Chunks 0 .. max(ceil(len / 32), 3) are written (the one after the last base is zero: readers look one chunk ahead).
+ * Sequence store layout: slot s, plane word k (lo: 0..NW-1, hi: NW.., valid: 2NW..) at
+ * words[((s >> 5) * 3*NW + k) * 32 + (s & 31)] — column-major per group of 32 slots, so a warp reading consecutive slots is
+ * coalesced; only words 0 .. ceil(len/32) are written; meta[s] = {pair, source|olen<<2|diff<<14, len, 0}.
+ * (A row-major store — one 16-byte {lo, hi, valid, aux} entry per 32 bases, meta and seed folded into the aux words — was
+ * measured in round 2: it cuts the DRAM bytes k_diag / k_scan re-read, but every 128-bit load of a warp then touches 32
+ * lines instead of 1-3, and k_seed, whose slots ARE consecutive, went from 0.93 to 1.27 ms; the step got 5 % slower.)
  */
 #pragma once
 
@@ -35,20 +34,30 @@ using tpp::Col;
 using tpp::Lay;
 
 struct SeqStore {
-    uint4* chunks;
+    uint32_t* words;
+    uint4* meta;
+    uint2* seed;              /* per slot: {seed_val, seed_i} */
     uint32_t* list;           /* slot indices: seeded sequences from entry 0 upwards, unseeded ones from entry cap - 1 downwards.
-                                 k_seed walks the short slots first, then the long ones, and every block appends once per
-                                 iteration, so each list keeps the two length classes apart except in a few warps */
+                                 k_seed walks the short slots (at most 32 W bases: every unmerged read) first, then the long
+                                 ones, and every block appends once per iteration, so each list keeps the two length classes
+                                 apart except in a few warps */
     unsigned int* counters;   /* [0] short slots (from 0 up), [5] long slots (from cap - 1 down), [1] seeded, [2] unseeded entries */
     uint32_t cap;
 };
 template <int W>
 struct SL {
-    static constexpr int NCH = 2 * W + 2;  /* chunks per slot: merged reads (<= 2 W words) + zero pad, rounded to whole sectors */
+    static constexpr int NW = 2 * W + 1;   /* plane words per sequence (merged reads, + zero pad word) */
+    static constexpr int NW3 = 3 * NW;
 };
 template <int W>
-__device__ __forceinline__ uint4* slot_chunks(const SeqStore& st, uint32_t s) { return st.chunks + (size_t)s * SL<W>::NCH; }
-__device__ __forceinline__ uint4 ldg_chunk(const uint4* p) { return __ldg(p); }
+__device__ __forceinline__ uint32_t* slot_words(const SeqStore& st, uint32_t s) {
+    return st.words + (size_t)(s >> 5) * SL<W>::NW3 * 32 + (s & 31u);
+}
+
+__device__ __forceinline__ uint32_t fs_col(const uint32_t* col, int arr_base, uint32_t bitpos) {
+    uint32_t wi = bitpos >> 5;
+    return __funnelshift_r(col[(size_t)(arr_base + (int)wi) * 32], col[(size_t)(arr_base + (int)wi + 1) * 32], bitpos & 31u);
+}
 
 struct PrepParams {
     GfDevBatch b;
@@ -71,6 +80,7 @@ __global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepPa
     const uint8_t* const NOBOUND = reinterpret_cast<const uint8_t*>(~(uintptr_t)0);
     const uint8_t* bound1 = B.bytes1 ? B.seq1 + B.bytes1 : NOBOUND;
     const uint8_t* bound2 = (PAIRED && B.bytes2) ? B.seq2 + B.bytes2 : NOBOUND;
+    constexpr int NW = SL<W>::NW;
     unsigned c_seq = 0, c_probes = 0, c_bytes = 0, c_merged = 0;
     uint32_t err = 0;
 
@@ -112,7 +122,7 @@ __global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepPa
         const int len0 = merged ? offset + len2 : len1;
         /* slots: warp-aggregated allocation (all lanes take part).  Short sequences (<= 32 W bases: every unmerged read)
          * fill the store from slot 0 upwards, long ones (merged reads) from slot cap - 1 downwards, so that the lists
-         * k_seed builds keep the two length classes apart. */
+         * k_seed builds refer to nearly contiguous slots and the plane-word loads of k_diag / k_scan stay coalesced. */
         const bool lng = merged && len0 > 32 * W;
         const int mine = lng ? (1 << 16) : nseq;
         int incl = mine;
@@ -146,10 +156,9 @@ __global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepPa
                     }
                 }
             }
-            uint4* dst = slot_chunks<W>(P.st, slot0);
-            const int nw = (len0 + 31) >> 5, last = max(nw, 3);
-            const uint32_t info = merged ? (0u | ((uint32_t)olen << 2) | ((uint32_t)diff << 14)) : 1u;
-            for (int k = 0; k <= last; k++) {
+            uint32_t* w = slot_words<W>(P.st, slot0);
+            const int nw = (len0 + 31) >> 5;
+            for (int k = 0; k <= nw; k++) { /* words 0 .. ceil(len/32): nothing beyond is ever read */
                 uint32_t lo = 0, hi = 0, v = 0;
                 if (k < nw) {
                     const int pos0 = 32 * k;
@@ -171,9 +180,10 @@ __global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepPa
                         }
                     }
                 }
-                const uint32_t aux = k == 0 ? (((uint32_t)len0 << 16) | info) : (k == 1 ? (uint32_t)p : 0u);
-                dst[k] = make_uint4(lo, hi, v, aux);
+                w[(size_t)k * 32] = lo; w[(size_t)(NW + k) * 32] = hi; w[(size_t)(2 * NW + k) * 32] = v;
             }
+            const uint32_t info = merged ? (0u | ((uint32_t)olen << 2) | ((uint32_t)diff << 14)) : 1u;
+            P.st.meta[slot0] = make_uint4((uint32_t)p, info, (uint32_t)len0, 0u);
             c_seq++;
             c_merged += merged ? 1u : 0u;
             c_bytes += (unsigned)len0;
@@ -181,9 +191,9 @@ __global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepPa
         }
         if (nseq == 2) {
             /* forward R2 (upper-case validity) from the rc planes */
-            uint4* dst = slot_chunks<W>(P.st, slot0 + 1u);
-            const int nw = (len2 + 31) >> 5, last = max(nw, 3);
-            for (int k = 0; k <= last; k++) {
+            uint32_t* w = slot_words<W>(P.st, slot0 + 1u);
+            const int nw = (len2 + 31) >> 5;
+            for (int k = 0; k <= nw; k++) {
                 uint32_t lo = 0, hi = 0, v = 0;
                 if (k < nw) {
                     const int pos = len2 - 32 * k - 32;
@@ -191,9 +201,9 @@ __global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepPa
                     lo = ~__brev(c.win(Lay<W>::C2LO, pos)) & v;
                     hi = __brev(c.win(Lay<W>::C2HI, pos)) & v;
                 }
-                const uint32_t aux = k == 0 ? (((uint32_t)len2 << 16) | 2u) : (k == 1 ? (uint32_t)p : 0u);
-                dst[k] = make_uint4(lo, hi, v, aux);
+                w[(size_t)k * 32] = lo; w[(size_t)(NW + k) * 32] = hi; w[(size_t)(2 * NW + k) * 32] = v;
             }
+            P.st.meta[slot0 + 1u] = make_uint4((uint32_t)p, 2u, (uint32_t)len2, 0u);
             c_seq++;
             c_bytes += (unsigned)len2;
             c_probes += (unsigned)(len2 >= 16 ? ((len2 - 16) >> 1) + 1 : 0);
@@ -222,6 +232,7 @@ struct SeedParams {
 };
 template <int W>
 __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
+    constexpr int NW = SL<W>::NW;
     const uint32_t lane = gf_lane();
     const uint32_t n_short = min(P.st.counters[0], P.st.cap), n_long = min(P.st.counters[5], P.st.cap - n_short);
     const uint32_t n_slots = n_short + n_long; /* virtual index v: short slots, then the long ones in ascending order */
@@ -237,27 +248,30 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
         uint32_t seed_val = GF_EMPTY_VAL, seed_i = 0;
         if (have) {
             /* 8 candidate 16-mers at half-word aligned offsets of the first 128 bases (a candidate is one shift + mask of a
-             * plane word, two candidates share a chunk).  The first four chunks (two sectors) hold them and the slot's length;
-             * a candidate counts only if it lies inside the read and its 16 bases are valid.  Every candidate offset is even
+             * plane word, two candidates share the three plane loads).  The plane words are requested together with the
+             * slot's meta record (one memory round trip less on the critical path); a candidate counts only if it lies inside
+             * the read (words beyond the read were never written) and its 16 bases are valid.  Every candidate offset is even
              * and inside the read, i.e. one of pass 1's probe offsets; which ones are tried only decides the diagonal, never
              * the bound.  All go to the L2 filter at once; the HBM table is asked only for candidates the level-1 filter calls
              * present, in read order, and the bucket of the first valid candidate is prefetched into L2 meanwhile. */
-            uint4* ch = slot_chunks<W>(P.st, s);
-            uint4 c4[4];
+            const uint32_t* col = slot_words<W>(P.st, s);
+            uint32_t plo[4], phi[4], pv[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) c4[j] = ch[j];
-            const int len = (int)(c4[0].w >> 16);
+            for (int j = 0; j < 4; j++) {
+                plo[j] = col[(size_t)j * 32]; phi[j] = col[(size_t)(NW + j) * 32]; pv[j] = col[(size_t)(2 * NW + j) * 32];
+            }
+            const uint4 m = P.st.meta[s];
+            const int len = (int)m.z;
             const int nprobe = len >= 16 ? ((len - 16) >> 1) + 1 : 0;
             if (nprobe == 0 && P.need_total > 0) have = false; /* cannot reach the gate: dropped here */
             if (have && nprobe > 0) {
                 uint32_t key[8], okm = 0;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const uint32_t plo = c4[j].x, phi = c4[j].y, pv = c4[j].z;
-                    key[2 * j] = (phi << 16) | (plo & 0xFFFFu);
-                    key[2 * j + 1] = (phi & 0xFFFF0000u) | (plo >> 16);
-                    if (32 * j + 16 <= len && (pv & 0xFFFFu) == 0xFFFFu) okm |= 1u << (2 * j);
-                    if (32 * j + 32 <= len && (pv >> 16) == 0xFFFFu) okm |= 2u << (2 * j);
+                    key[2 * j] = (phi[j] << 16) | (plo[j] & 0xFFFFu);
+                    key[2 * j + 1] = (phi[j] & 0xFFFF0000u) | (plo[j] >> 16);
+                    if (32 * j + 16 <= len && (pv[j] & 0xFFFFu) == 0xFFFFu) okm |= 1u << (2 * j);
+                    if (32 * j + 32 <= len && (pv[j] >> 16) == 0xFFFFu) okm |= 2u << (2 * j);
                 }
                 if (okm) {
                     const uint32_t t0 = (uint32_t)__ffs(okm) - 1u;
@@ -283,7 +297,7 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
                     if (((okm >> t) & 1u) && (wl & al) == al && (wh & ah) == ah) pm |= 1u << t;
                 }
                 /* an unseeded sequence goes to k_scan, which need not probe these candidates again: it starts from their
-                 * count (bits 0-7) and skips the offsets (bits 8-15: which were valid) */
+                 * count (bits 0-7 of seed.y) and skips the offsets (bits 8-15: which were valid) */
                 seed_i = pm | (okm << 8);
                 while (pm) { /* usually one iteration: the first present candidate of an on-target read is unique */
                     const int t = __ffs(pm) - 1;
@@ -300,11 +314,7 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
                     }
                 }
             }
-            if (have) { /* aux words of chunks 2 and 3 (one sector) */
-                uint32_t* aux = reinterpret_cast<uint32_t*>(ch);
-                aux[2 * 4 + 3] = seed_val;
-                aux[3 * 4 + 3] = seed_i;
-            }
+            if (have) P.st.seed[s] = make_uint2(seed_val, seed_i);
         }
         /* the two lists, aggregated over the block: one atomic per class, block and iteration (the list counters are
          * single hot addresses; a per-warp atomic on them serialises in L2) */
@@ -335,9 +345,9 @@ struct ClassParams {
     GfMapCounters* counters;
     int need_total, need_minor;
 };
-__device__ __forceinline__ void push_survivor(const ClassParams& P, uint32_t pair, uint32_t info) {
+__device__ __forceinline__ void push_survivor(const ClassParams& P, const uint4& m) {
     uint32_t slot = atomicAdd(&P.counters->n_survivors, 1u);
-    if (slot < P.survivors_cap) P.survivors[slot] = make_uint2(pair, info);
+    if (slot < P.survivors_cap) P.survivors[slot] = make_uint2(m.x, m.y);
     else atomicOr(&P.counters->error_flags, 2u);
 }
 /* unseeded sequences: the valid even offsets get a filter probe until the outcome is decided.
@@ -349,27 +359,25 @@ __device__ __forceinline__ void push_survivor(const ClassParams& P, uint32_t pai
  * (off-target reads: after ~3/4 of their offsets). */
 template <int W>
 __global__ void __launch_bounds__(256) k_scan(ClassParams P) {
+    constexpr int NW = SL<W>::NW;
     const unsigned long long pol = make_policy_keep();
     const GfDevIndex& ix = P.ix;
     const int need_major = P.need_total - P.need_minor;
     const uint32_t n = P.st.counters[2];
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
         const uint32_t s = P.st.list[P.st.cap - 1u - t];
-        const uint4* ch = slot_chunks<W>(P.st, s);
-        const uint4 c0 = ldg_chunk(ch);
-        const int len = (int)(c0.w >> 16), nch = (len + 31) >> 5;
-        uint32_t lo = c0.x, hi = c0.y, v = c0.z;
-        /* k_seed already asked the filter about the 16-mers at offsets 0, 16, ..., 112 (aux of chunk 3: bits 0-7 present,
-         * bits 8-15 valid = probed); chunk 3 is in the sector after chunk 0's */
-        const uint32_t pre = __ldg(&ch[3].w), pre_valid = (pre >> 8) & 0xFFu;
-        uint32_t pair = 0;
+        const uint4 m = P.st.meta[s];
+        const int len = (int)m.z, nch = (len + 31) >> 5;
+        const uint32_t* col = slot_words<W>(P.st, s);
+        uint32_t lo = col[0], hi = col[(size_t)NW * 32], v = col[(size_t)2 * NW * 32];
+        /* k_seed already asked the filter about the 16-mers at offsets 0, 16, ..., 112 (seed.y: bits 0-7 present,
+         * bits 8-15 valid = probed) */
+        const uint32_t pre = P.st.seed[s].y, pre_valid = (pre >> 8) & 0xFFu;
         int Pn = __popc(pre & 0xFFu);
         bool dead = false;
 #pragma unroll 1
         for (int k = 0; k < nch && !dead; k++) {
-            const uint4 cn = ldg_chunk(ch + k + 1);
-            if (k == 0) pair = cn.w;
-            const uint32_t nlo = cn.x, nhi = cn.y, nv = cn.z;
+            const uint32_t nlo = col[(size_t)(k + 1) * 32], nhi = col[(size_t)(NW + k + 1) * 32], nv = col[(size_t)(2 * NW + k + 1) * 32];
             uint32_t om = run16(v, nv) & 0x55555555u;
             if (k < 4) om &= ~0x00010001u;                          /* offsets 32 k and 32 k + 16: probed by k_seed */
             const int beyond = len - 16 - 32 * (k + 1);            /* last probe offset relative to the next chunk */
@@ -395,10 +403,9 @@ __global__ void __launch_bounds__(256) k_scan(ClassParams P) {
             }
             lo = nlo; hi = nhi; v = nv;
         }
-        if (nch == 0) pair = __ldg(&ch[1].w);
         /* T <= 2 Pn without the unique / dupe distinction: the T conditions follow from Pn >= need_major when
          * need_minor <= need_major (checked by the host; otherwise 2 Pn is compared) */
-        if (P.need_total <= 0 || (!dead && Pn >= need_major && 2 * Pn >= P.need_total)) push_survivor(P, pair, c0.w & 0xFFFFu);
+        if (P.need_total <= 0 || (!dead && Pn >= need_major && 2 * Pn >= P.need_total)) push_survivor(P, m);
     }
 }
 
@@ -414,6 +421,7 @@ __device__ __forceinline__ GeneWord ldg_gene_word(const uint32_t* base, uint32_t
 constexpr int DIAG_Q = 128; /* queue entries per warp; flushed above DIAG_Q - 32 (a chunk adds <= 32) */
 template <int W>
 __global__ void __launch_bounds__(256, 5) k_diag(ClassParams P) {
+    constexpr int NW = SL<W>::NW;
     __shared__ uint32_t q_lo0[8][DIAG_Q], q_lo1[8][DIAG_Q], q_hi0[8][DIAG_Q], q_hi1[8][DIAG_Q], q_om[8][DIAG_Q], q_meta[8][DIAG_Q];
     __shared__ int t_sh[8][32];
     __shared__ unsigned q_cnt[8];
@@ -446,40 +454,28 @@ __global__ void __launch_bounds__(256, 5) k_diag(ClassParams P) {
     for (uint32_t t0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); t0 < n; t0 += gridDim.x * blockDim.x) {
         const bool have = t0 + lane < n;
         const uint32_t s = have ? P.st.list[t0 + lane] : 0u;
-        const uint4* ch = slot_chunks<W>(P.st, s);
-        const uint4 c0 = have ? ldg_chunk(ch) : make_uint4(0, 0, 0, 0);
-        const uint32_t pair = have ? __ldg(&ch[1].w) : 0u;
-        const uint32_t sd_x = have ? __ldg(&ch[2].w) : 0u, sd_y = have ? __ldg(&ch[3].w) : 0u;
-        const int len = (int)(c0.w >> 16), nch = have ? (len + 31) >> 5 : 0;
-        const bool rc = (sd_x & GF_SITE_STRAND) != 0;
-        const uint32_t goff = sd_x & GF_SITE_GOFF_MASK;
-        const uint32_t D = rc ? goff + sd_y - (uint32_t)len + 1u : goff - sd_y;
+        const uint4 m = have ? P.st.meta[s] : make_uint4(0, 0, 0, 0);
+        const uint2 sd = have ? P.st.seed[s] : make_uint2(0, 0);
+        const int len = (int)m.z, nch = have ? (len + 31) >> 5 : 0;
+        const uint32_t* col = slot_words<W>(P.st, s);
+        const bool rc = (sd.x & GF_SITE_STRAND) != 0;
+        const uint32_t goff = sd.x & GF_SITE_GOFF_MASK;
+        const uint32_t D = rc ? goff + sd.y - (uint32_t)len + 1u : goff - sd.y;
         const uint32_t parity = (rc && (len & 1)) ? 0xAAAAAAAAu : 0x55555555u;
         const uint32_t wbase = D >> 5, sh = D & 31u;
         const uint32_t* gi = rc ? ix.g_ir : ix.g_if;
         t_sh[wib][lane] = 0;
         if (lane == 0) q_cnt[wib] = 0;
         __syncwarp();
-        /* read chunk k in the orientation of the comparison.  Reverse strand: the read is walked from its end, bit-reversed
-         * and complemented; chunk k needs store words w and w + 1 (w falls by one per step, so the upper one is kept). */
-        uint4 up = make_uint4(0, 0, 0, 0);
-        int up_w = -2;
+        /* read chunk k in the orientation of the comparison */
         auto read_chunk = [&](int k, uint32_t* lo, uint32_t* hi, uint32_t* v) {
             if (k >= nch) { *lo = *hi = *v = 0; return; }
-            if (!rc) { const uint4 c = k == 0 ? c0 : ldg_chunk(ch + k); *lo = c.x; *hi = c.y; *v = c.z; return; }
-            const int pos = len - 32 * k - 32;
+            if (!rc) { *lo = col[(size_t)k * 32]; *hi = col[(size_t)(NW + k) * 32]; *v = col[(size_t)(2 * NW + k) * 32]; return; }
+            int pos = len - 32 * k - 32;
             uint32_t a, b, cc;
-            if (pos >= 0) {
-                const int w = pos >> 5;
-                const uint32_t r = (uint32_t)pos & 31u;
-                const uint4 cw = w == 0 ? c0 : ldg_chunk(ch + w);
-                const uint4 cu = up_w == w + 1 ? up : ldg_chunk(ch + w + 1);
-                a = __funnelshift_r(cw.x, cu.x, r); b = __funnelshift_r(cw.y, cu.y, r); cc = __funnelshift_r(cw.z, cu.z, r);
-                up = cw; up_w = w;
-            } else {
-                a = c0.x << (-pos); b = c0.y << (-pos); cc = c0.z << (-pos);
-            }
-            const uint32_t vv = __brev(cc);
+            if (pos >= 0) { a = fs_col(col, 0, (uint32_t)pos); b = fs_col(col, NW, (uint32_t)pos); cc = fs_col(col, 2 * NW, (uint32_t)pos); }
+            else { a = col[0] << (-pos); b = col[(size_t)NW * 32] << (-pos); cc = col[(size_t)2 * NW * 32] << (-pos); }
+            uint32_t vv = __brev(cc);
             *v = vv;
             *lo = ~__brev(a) & vv;
             *hi = __brev(b);
@@ -511,8 +507,8 @@ __global__ void __launch_bounds__(256, 5) k_diag(ClassParams P) {
                     g0 = g1;
                 }
                 uint32_t mm = run16(e_cur, e_nxt) & parity;
-                uint32_t c0m = cnt_a & mm, c1 = cnt_b & mm, c2 = cnt_c & mm;
-                uint32_t hit = c0m | c1 | c2;
+                uint32_t c0 = cnt_a & mm, c1 = cnt_b & mm, c2 = cnt_c & mm;
+                uint32_t hit = c0 | c1 | c2;
                 c_d += __popc(hit);
                 T += __popc(hit) + __popc(c1 | c2); /* min(sites, 2) per offset: a k-mer votes once per diagonal */
                 uint32_t om = run16(v_cur, nv) & parity & ~hit;
@@ -531,8 +527,7 @@ __global__ void __launch_bounds__(256, 5) k_diag(ClassParams P) {
         }
         flush();
         T += t_sh[wib][lane];
-        if (have && (P.need_total <= 0 || P.need_minor <= 0 || (T >= P.need_total && (T - c_d) >= P.need_minor)))
-            push_survivor(P, pair, c0.w & 0xFFFFu);
+        if (have && (P.need_total <= 0 || P.need_minor <= 0 || (T >= P.need_total && (T - c_d) >= P.need_minor))) push_survivor(P, m);
         __syncwarp();
     }
 }
