@@ -178,7 +178,11 @@ EXPORTS = (
     "gf_multi_map_pairs", "gf_adjust_fusion_break", "gf_list_map_pairs", "gf_map_pairs_device_list",
     "gf_reference_create", "gf_reference_destroy", "gf_reference_get_info", "gf_alignable_filter",
     "gf_index_set_output_mode",
+    "gf_stream_create", "gf_stream_destroy", "gf_stream_push", "gf_stream_flush", "gf_stream_take", "gf_stream_get_counts",
+    "gf_fastq_stream_create", "gf_fastq_stream_destroy", "gf_fastq_stream_feed", "gf_fastq_stream_finish",
+    "gf_fastq_stream_take", "gf_fastq_stream_get_counts",
 )
+GF_FQ_PLAIN, GF_FQ_GZIP = 0, 1
 GF_OUT_DROP_FILTERED, GF_OUT_BUCKET_ORDER = 1, 2
 
 
@@ -243,6 +247,31 @@ def load_library():
     lib.gf_adjust_fusion_break.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, P(gf_break_ref), C.c_uint32, P(gf_break_job),
                                            C.c_uint64, P(gf_break_out)]
     lib.gf_adjust_fusion_break.restype = C.c_int
+    lib.gf_stream_create.argtypes = [C.c_void_p, C.c_int, C.c_uint64, P(C.c_void_p)]
+    lib.gf_stream_create.restype = C.c_int
+    lib.gf_stream_destroy.argtypes = [C.c_void_p]
+    lib.gf_stream_destroy.restype = None
+    lib.gf_stream_push.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]
+    lib.gf_stream_push.restype = C.c_int
+    lib.gf_stream_flush.argtypes = [C.c_void_p]
+    lib.gf_stream_flush.restype = C.c_int
+    lib.gf_stream_take.argtypes = [C.c_void_p, P(gf_match), C.c_uint64, P(C.c_uint64)]
+    lib.gf_stream_take.restype = C.c_int
+    lib.gf_stream_get_counts.argtypes = [C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
+    lib.gf_stream_get_counts.restype = C.c_int
+    lib.gf_fastq_stream_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, P(C.c_void_p)]
+    lib.gf_fastq_stream_create.restype = C.c_int
+    lib.gf_fastq_stream_destroy.argtypes = [C.c_void_p]
+    lib.gf_fastq_stream_destroy.restype = None
+    lib.gf_fastq_stream_feed.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
+    lib.gf_fastq_stream_feed.restype = C.c_int
+    lib.gf_fastq_stream_finish.argtypes = [C.c_void_p]
+    lib.gf_fastq_stream_finish.restype = C.c_int
+    lib.gf_fastq_stream_take.argtypes = [C.c_void_p, P(gf_match), C.c_uint64, P(C.c_uint64)]
+    lib.gf_fastq_stream_take.restype = C.c_int
+    lib.gf_fastq_stream_get_counts.argtypes = [C.c_void_p, P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)]
+    lib.gf_fastq_stream_get_counts.restype = C.c_int
     lib.gf_index_set_output_mode.argtypes = [C.c_void_p, C.c_uint32]
     lib.gf_index_set_output_mode.restype = C.c_int
     lib.gf_reference_create.argtypes = [P(gf_ref_contig), C.c_uint32, C.c_int, P(C.c_void_p)]

@@ -1,0 +1,402 @@
+/*
+ * gf_stream.cu — host-side staging in front of the mapping entry points (no kernels here):
+ *
+ *   gf_stream_*        the batched shim.  The reference's consumers call scan_pair_end once per pack of 1000 pairs
+ *                      (/root/reference/src/core/pescanner.rs:350-425, src/core/common.rs:20-23); one gf_map_pairs call per
+ *                      pack would pay 6 launches, 2 synchronisations and a tiny H2D for 1000 pairs.  A gf_stream takes packs
+ *                      as they are (arrays of string pointers + lengths = what a ReadPairPack holds), copies them into
+ *                      pinned arenas and maps them in batches of >= 2^20 pairs; records come back with the caller's own pair
+ *                      numbering.
+ *   gf_fastq_stream_*  FastqReader / FastqReaderPair (src/core/fastq_reader.rs:39-69, 75-147, 149-179) as a
+ *                      stream of raw file bytes: buffers may end anywhere (the incomplete tail is carried over), gzip input
+ *                      (multi-member, like flate2's MultiGzDecoder, chosen by the caller from the file extension like
+ *                      FastqReader::new) is inflated on host threads — one per mate — straight into the pinned text buffers,
+ *                      and whole records are mapped on the device (gf_map_fastq_text: record splitting there too).
+ */
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "gf_internal.h"
+
+namespace {
+
+int sfail(int code, const std::string& msg) {
+    gf_set_error(msg);
+    return code;
+}
+
+/* grow-only pinned host buffer */
+struct PinnedArena {
+    uint8_t* p = nullptr;
+    size_t cap = 0, fill = 0;
+    ~PinnedArena() { if (p) cudaFreeHost(p); }
+    cudaError_t reserve(size_t need) {
+        if (need <= cap) return cudaSuccess;
+        size_t want = std::max(need, cap * 2);
+        uint8_t* q = nullptr;
+        cudaError_t e = cudaMallocHost((void**)&q, want);
+        if (e != cudaSuccess) return e;
+        if (fill) memcpy(q, p, fill);
+        if (p) cudaFreeHost(p);
+        p = q;
+        cap = want;
+        return cudaSuccess;
+    }
+};
+
+/* (pair_idx, source), or bucket order when the index's output mode asks for it (the same key the device computes) */
+void sort_records(const gf_index* idx, std::vector<gf_match>& v) {
+    if (!(idx->out_mode & GF_OUT_BUCKET_ORDER)) { gf_sort_matches(v.data(), v.size()); return; }
+    const uint32_t ng = idx->n_genes;
+    std::sort(v.begin(), v.end(), [ng](const gf_match& a, const gf_match& b) {
+        const uint64_t ka = gf_match_order_key(ng, &a), kb = gf_match_order_key(ng, &b);
+        if (ka != kb) return ka < kb;
+        if (a.pair_idx != b.pair_idx) return a.pair_idx < b.pair_idx;
+        return a.source < b.source;
+    });
+}
+
+/* gf_map_pairs with the capacity protocol into a vector */
+int map_into(gf_index* idx, const gf_batch* b, std::vector<gf_match>& tmp, uint64_t* n) {
+    if (tmp.size() < 4096) tmp.resize(4096);
+    for (;;) {
+        int rc = gf_map_pairs(idx, b, tmp.data(), tmp.size(), n);
+        if (rc == GF_E_CAPACITY) { tmp.resize(*n); continue; }
+        return rc;
+    }
+}
+
+}  // namespace
+
+/* ================================================================================================== packs */
+struct gf_stream {
+    gf_index* idx = nullptr;
+    uint64_t batch_pairs = 1u << 20;
+    bool paired = true;
+    PinnedArena seq[2], qual[2], off[2]; /* off: uint64 entries */
+    std::vector<uint64_t> ids;           /* the caller's number of every buffered pair */
+    uint32_t max_len = 0;
+    std::vector<gf_match> done, tmp;
+    uint64_t n_pushed = 0, n_calls = 0;
+    bool panic = false;
+    std::mutex mu;
+};
+
+namespace {
+
+int stream_flush_locked(gf_stream* s) {
+    const uint64_t n = s->ids.size();
+    if (!n) return GF_OK;
+    gf_batch b{};
+    b.n = n;
+    b.seq1 = s->seq[0].p; b.qual1 = s->qual[0].p; b.off1 = (const uint64_t*)s->off[0].p;
+    b.bytes1 = s->seq[0].fill;
+    if (s->paired) {
+        b.seq2 = s->seq[1].p; b.qual2 = s->qual[1].p; b.off2 = (const uint64_t*)s->off[1].p;
+        b.bytes2 = s->seq[1].fill;
+    }
+    b.max_len = std::max<uint32_t>(s->max_len, 1);
+    uint64_t got = 0;
+    int rc = map_into(s->idx, &b, s->tmp, &got);
+    if (rc != GF_OK && rc != GF_E_REF_PANIC) return rc;
+    if (rc == GF_E_REF_PANIC) s->panic = true;
+    for (uint64_t i = 0; i < got; i++) {
+        gf_match m = s->tmp[i];
+        m.pair_idx = s->ids[m.pair_idx];
+        s->done.push_back(m);
+    }
+    s->n_calls++;
+    s->ids.clear();
+    for (int k = 0; k < 2; k++) s->seq[k].fill = s->qual[k].fill = s->off[k].fill = 0;
+    s->max_len = 0;
+    return GF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gf_stream_create(gf_index* idx, int paired, uint64_t batch_pairs, gf_stream** out) {
+    if (!idx || !out) return sfail(GF_E_INVALID, "NULL argument");
+    gf_stream* s = new gf_stream();
+    s->idx = idx;
+    s->paired = paired != 0;
+    if (batch_pairs) s->batch_pairs = batch_pairs;
+    *out = s;
+    return GF_OK;
+}
+
+void gf_stream_destroy(gf_stream* s) { delete s; }
+
+int gf_stream_push(gf_stream* s, uint64_t first_pair, uint64_t n, const uint8_t* const* seq1, const uint8_t* const* qual1,
+                   const uint32_t* len1, const uint8_t* const* seq2, const uint8_t* const* qual2, const uint32_t* len2) {
+    if (!s || (n && (!seq1 || !qual1 || !len1))) return sfail(GF_E_INVALID, "NULL argument");
+    if (s->paired && n && (!seq2 || !qual2 || !len2)) return sfail(GF_E_INVALID, "a paired stream needs both mates");
+    std::lock_guard<std::mutex> lk(s->mu);
+    GF_CUDA_TRY(cudaSetDevice(s->idx->device));
+    for (uint64_t i = 0; i < n; i++) {
+        const uint8_t* const* sq[2] = {seq1, seq2};
+        const uint8_t* const* ql[2] = {qual1, qual2};
+        const uint32_t* ln[2] = {len1, len2};
+        for (int k = 0; k < (s->paired ? 2 : 1); k++) {
+            const uint32_t L = ln[k][i];
+            if (L > GF_MAX_READ_LEN + 24) return sfail(GF_E_INVALID, "a read is longer than the kernel capacity of 1024 bases");
+            GF_CUDA_TRY(s->seq[k].reserve(s->seq[k].fill + L + 64));
+            GF_CUDA_TRY(s->qual[k].reserve(s->qual[k].fill + L + 64));
+            GF_CUDA_TRY(s->off[k].reserve(s->off[k].fill + 16));
+            if (s->off[k].fill == 0) { ((uint64_t*)s->off[k].p)[0] = 0; s->off[k].fill = 8; }
+            if (L) { memcpy(s->seq[k].p + s->seq[k].fill, sq[k][i], L); memcpy(s->qual[k].p + s->qual[k].fill, ql[k][i], L); }
+            s->seq[k].fill += L;
+            s->qual[k].fill += L;
+            ((uint64_t*)s->off[k].p)[s->off[k].fill / 8] = s->seq[k].fill;
+            s->off[k].fill += 8;
+            s->max_len = std::max(s->max_len, L);
+        }
+        s->ids.push_back(first_pair + i);
+        s->n_pushed++;
+        if (s->ids.size() >= s->batch_pairs) {
+            int rc = stream_flush_locked(s);
+            if (rc != GF_OK) return rc;
+        }
+    }
+    return GF_OK;
+}
+
+int gf_stream_flush(gf_stream* s) {
+    if (!s) return sfail(GF_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    GF_CUDA_TRY(cudaSetDevice(s->idx->device));
+    return stream_flush_locked(s);
+}
+
+int gf_stream_take(gf_stream* s, gf_match* out, uint64_t out_cap, uint64_t* n_out) {
+    if (!s || !n_out) return sfail(GF_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    *n_out = s->done.size();
+    if (s->done.size() > out_cap) return sfail(GF_E_CAPACITY, "out_cap too small; *n_out holds the required count");
+    if (out_cap && !out && !s->done.empty()) return sfail(GF_E_INVALID, "out is NULL");
+    sort_records(s->idx, s->done);
+    if (!s->done.empty()) memcpy(out, s->done.data(), sizeof(gf_match) * s->done.size());
+    s->done.clear();
+    if (s->panic) {
+        s->panic = false;
+        return sfail(GF_E_REF_PANIC, "a candidate needs an edit distance over more than 640 columns (reference panics)");
+    }
+    return GF_OK;
+}
+
+int gf_stream_get_counts(const gf_stream* s, uint64_t* pairs_pushed, uint64_t* map_calls) {
+    if (!s) return sfail(GF_E_INVALID, "NULL argument");
+    if (pairs_pushed) *pairs_pushed = s->n_pushed;
+    if (map_calls) *map_calls = s->n_calls;
+    return GF_OK;
+}
+
+} /* extern "C" */
+
+/* ================================================================================================== FASTQ text */
+struct gf_fastq_stream {
+    gf_index* idx = nullptr;
+    bool paired = true;
+    int format = GF_FQ_PLAIN;
+    uint64_t chunk_bytes = 256ull << 20;
+    PinnedArena text[2];
+    z_stream z[2];
+    bool z_open[2] = {false, false}, z_member_done[2] = {true, true};
+    bool eof_seen[2] = {false, false};
+    uint64_t records = 0, text_bytes = 0, n_calls = 0;
+    std::vector<gf_match> done, tmp;
+    bool panic = false;
+    std::mutex mu;
+    ~gf_fastq_stream() {
+        for (int k = 0; k < 2; k++)
+            if (z_open[k]) inflateEnd(&z[k]);
+    }
+};
+
+namespace {
+
+/* maps the whole records buffered so far; final_chunk: the files have ended */
+int fq_map_locked(gf_fastq_stream* s, bool final_chunk) {
+    const int nm = s->paired ? 2 : 1;
+    if (s->text[0].fill == 0 && (!s->paired || s->text[1].fill == 0)) return GF_OK;
+    if (s->tmp.size() < 4096) s->tmp.resize(4096);
+    uint64_t got = 0, nrec = 0, consumed[2] = {0, 0};
+    int rc;
+    for (;;) {
+        rc = gf_map_fastq_text(s->idx, s->text[0].p, s->text[0].fill, s->paired ? s->text[1].p : nullptr,
+                               s->paired ? s->text[1].fill : 0, final_chunk, s->tmp.data(), s->tmp.size(), &got, &nrec, consumed);
+        if (rc == GF_E_CAPACITY) { s->tmp.resize(got); continue; }
+        break;
+    }
+    if (rc != GF_OK && rc != GF_E_REF_PANIC) return rc;
+    if (rc == GF_E_REF_PANIC) s->panic = true;
+    for (uint64_t i = 0; i < got; i++) {
+        gf_match m = s->tmp[i];
+        m.pair_idx += s->records;
+        s->done.push_back(m);
+    }
+    s->records += nrec;
+    s->n_calls++;
+    for (int k = 0; k < nm; k++) {
+        PinnedArena& t = s->text[k];
+        const size_t c = (size_t)std::min<uint64_t>(consumed[k], t.fill);
+        s->text_bytes += c;
+        if (final_chunk) { t.fill = 0; continue; }
+        memmove(t.p, t.p + c, t.fill - c);
+        t.fill -= c;
+    }
+    return GF_OK;
+}
+
+/* append decoded text of mate k from `in`; returns the input bytes consumed.  Stops early when the buffer reached
+ * chunk_bytes (the caller maps and calls again). */
+int fq_append(gf_fastq_stream* s, int k, const uint8_t* in, uint64_t n, uint64_t* used, std::string* err) {
+    PinnedArena& t = s->text[k];
+    *used = 0;
+    if (s->format == GF_FQ_PLAIN) {
+        const uint64_t room = t.fill < s->chunk_bytes ? s->chunk_bytes - t.fill : 0;
+        const uint64_t c = std::min(n, room);
+        if (c) {
+            if (t.reserve(t.fill + c + 64) != cudaSuccess) { *err = "pinned allocation failed"; return GF_E_CUDA; }
+            memcpy(t.p + t.fill, in, c);
+            t.fill += c;
+        }
+        *used = c;
+        return GF_OK;
+    }
+    z_stream& z = s->z[k];
+    if (!s->z_open[k]) {
+        memset(&z, 0, sizeof(z));
+        if (inflateInit2(&z, 15 + 32) != Z_OK) { *err = "inflateInit2 failed"; return GF_E_INVALID; }
+        s->z_open[k] = true;
+        s->z_member_done[k] = true;
+    }
+    z.next_in = const_cast<Bytef*>(in);
+    uint64_t left = n;
+    while (left && t.fill < s->chunk_bytes) {
+        if (t.reserve(std::min<uint64_t>(s->chunk_bytes, t.fill + (4u << 20)) + 64) != cudaSuccess) { *err = "pinned allocation failed"; return GF_E_CUDA; }
+        const uint64_t room = std::min<uint64_t>(t.cap - 64, s->chunk_bytes) - t.fill;
+        if (!room) break;
+        z.avail_in = (uInt)std::min<uint64_t>(left, 1u << 30);
+        const uInt in0 = z.avail_in;
+        z.next_out = t.p + t.fill;
+        z.avail_out = (uInt)std::min<uint64_t>(room, 1u << 30);
+        const uInt out0 = z.avail_out;
+        s->z_member_done[k] = false;
+        const int zr = inflate(&z, Z_NO_FLUSH);
+        left -= in0 - z.avail_in;
+        t.fill += out0 - z.avail_out;
+        if (zr == Z_STREAM_END) { /* next member of a multi-member file (MultiGzDecoder, fastq_reader.rs:49-55) */
+            s->z_member_done[k] = true;
+            if (inflateReset(&z) != Z_OK) { *err = "inflateReset failed"; return GF_E_INVALID; }
+        } else if (zr != Z_OK && zr != Z_BUF_ERROR) {
+            *err = std::string("gzip stream of mate ") + (k ? "2" : "1") + " is corrupt: " + (z.msg ? z.msg : "inflate error");
+            return GF_E_INVALID;
+        } else if (zr == Z_BUF_ERROR && in0 == z.avail_in && out0 == z.avail_out) {
+            break; /* no progress possible with this input */
+        }
+    }
+    *used = n - left;
+    return GF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gf_fastq_stream_create(gf_index* idx, int paired, int format, uint64_t chunk_bytes, gf_fastq_stream** out) {
+    if (!idx || !out) return sfail(GF_E_INVALID, "NULL argument");
+    if (format != GF_FQ_PLAIN && format != GF_FQ_GZIP) return sfail(GF_E_INVALID, "unknown FASTQ format");
+    gf_fastq_stream* s = new gf_fastq_stream();
+    s->idx = idx;
+    s->paired = paired != 0;
+    s->format = format;
+    if (chunk_bytes) s->chunk_bytes = std::max<uint64_t>(chunk_bytes, 4096);
+    *out = s;
+    return GF_OK;
+}
+
+void gf_fastq_stream_destroy(gf_fastq_stream* s) { delete s; }
+
+int gf_fastq_stream_feed(gf_fastq_stream* s, const uint8_t* fq1, uint64_t n1, const uint8_t* fq2, uint64_t n2) {
+    if (!s || (n1 && !fq1) || (n2 && !fq2)) return sfail(GF_E_INVALID, "NULL argument");
+    if (!s->paired && n2) return sfail(GF_E_INVALID, "single-end stream fed with a second file");
+    std::lock_guard<std::mutex> lk(s->mu);
+    GF_CUDA_TRY(cudaSetDevice(s->idx->device));
+    const uint8_t* in[2] = {fq1, fq2};
+    uint64_t left[2] = {n1, n2};
+    while (left[0] || left[1]) {
+        /* decode both mates side by side (inflate is the host-side cost of .fq.gz input: one thread per mate) */
+        uint64_t used[2] = {0, 0};
+        int rcs[2] = {GF_OK, GF_OK};
+        std::string errs[2];
+        std::thread other;
+        if (s->paired && left[1] && s->format == GF_FQ_GZIP)
+            other = std::thread([&] { rcs[1] = fq_append(s, 1, in[1], left[1], &used[1], &errs[1]); });
+        else if (s->paired && left[1])
+            rcs[1] = fq_append(s, 1, in[1], left[1], &used[1], &errs[1]);
+        if (left[0]) rcs[0] = fq_append(s, 0, in[0], left[0], &used[0], &errs[0]);
+        if (other.joinable()) other.join();
+        for (int k = 0; k < 2; k++) {
+            if (rcs[k] != GF_OK) return sfail(rcs[k], errs[k]);
+            in[k] += used[k];
+            left[k] -= used[k];
+        }
+        const bool full0 = s->text[0].fill >= s->chunk_bytes, full1 = s->paired && s->text[1].fill >= s->chunk_bytes;
+        if (full0 || full1) {
+            const size_t f0 = s->text[0].fill, f1 = s->text[1].fill;
+            int rc = fq_map_locked(s, false);
+            if (rc != GF_OK) return rc;
+            if (s->text[0].fill == f0 && s->text[1].fill == f1) {
+                /* a full buffer without one whole record in BOTH files (the other file is far behind, or a line is longer
+                 * than the chunk): let the buffers grow instead of spinning */
+                s->chunk_bytes *= 2;
+            }
+        } else if (!used[0] && !used[1]) {
+            break; /* nothing could be consumed (cannot happen with room in the buffers) */
+        }
+    }
+    return GF_OK;
+}
+
+int gf_fastq_stream_finish(gf_fastq_stream* s) {
+    if (!s) return sfail(GF_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    GF_CUDA_TRY(cudaSetDevice(s->idx->device));
+    if (s->format == GF_FQ_GZIP)
+        for (int k = 0; k < (s->paired ? 2 : 1); k++)
+            if (s->z_open[k] && !s->z_member_done[k])
+                return sfail(GF_E_INVALID, std::string("gzip stream of mate ") + (k ? "2" : "1") + " ends inside a member (truncated file)");
+    return fq_map_locked(s, true);
+}
+
+int gf_fastq_stream_take(gf_fastq_stream* s, gf_match* out, uint64_t out_cap, uint64_t* n_out) {
+    if (!s || !n_out) return sfail(GF_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    *n_out = s->done.size();
+    if (s->done.size() > out_cap) return sfail(GF_E_CAPACITY, "out_cap too small; *n_out holds the required count");
+    if (!out && !s->done.empty()) return sfail(GF_E_INVALID, "out is NULL");
+    sort_records(s->idx, s->done);
+    if (!s->done.empty()) memcpy(out, s->done.data(), sizeof(gf_match) * s->done.size());
+    s->done.clear();
+    if (s->panic) {
+        s->panic = false;
+        return sfail(GF_E_REF_PANIC, "a candidate needs an edit distance over more than 640 columns (reference panics)");
+    }
+    return GF_OK;
+}
+
+int gf_fastq_stream_get_counts(const gf_fastq_stream* s, uint64_t* records, uint64_t* text_bytes, uint64_t* map_calls) {
+    if (!s) return sfail(GF_E_INVALID, "NULL argument");
+    if (records) *records = s->records;
+    if (text_bytes) *text_bytes = s->text_bytes;
+    if (map_calls) *map_calls = s->n_calls;
+    return GF_OK;
+}
+
+} /* extern "C" */

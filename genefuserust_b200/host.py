@@ -389,6 +389,116 @@ def sort_read_matches(matches, read_name_of):
     matches.sort(key=functools.cmp_to_key(cmp))
 
 
+class PackStream:
+    """The batched shim (gf_stream_*): packs of reads in — as lists of (seq, qual) byte strings, the shape of the reference's
+    ReadPairPack (pescanner.rs:350-425) — large batches to the device; records come back numbered by the caller."""
+
+    def __init__(self, mapper, paired=True, batch_pairs=0):
+        self.lib, self.mapper, self.paired = mapper.lib, mapper, paired
+        h = C.c_void_p()
+        _check(self.lib, self.lib.gf_stream_create(mapper.m_indexer.h, 1 if paired else 0, batch_pairs, C.byref(h)))
+        self.h = h
+
+    def push(self, first_pair, r1, r2=None):
+        n = len(r1)
+
+        def arrays(reads):
+            ptrs = (C.c_char_p * n)(*[s for s, _ in reads])
+            qptr = (C.c_char_p * n)(*[q for _, q in reads])
+            lens = (C.c_uint32 * n)(*[len(s) for s, _ in reads])
+            return ptrs, qptr, lens
+        a1 = arrays(r1)
+        a2 = arrays(r2) if r2 is not None else (None, None, None)
+        _check(self.lib, self.lib.gf_stream_push(self.h, first_pair, n, a1[0], a1[1], a1[2], a2[0], a2[1], a2[2]))
+
+    def flush(self):
+        _check(self.lib, self.lib.gf_stream_flush(self.h))
+
+    def take(self):
+        cap = 4096
+        while True:
+            out = (gf_match * cap)()
+            n = C.c_uint64(0)
+            rc = self.lib.gf_stream_take(self.h, out, cap, C.byref(n))
+            if rc == GF_E_CAPACITY:
+                cap = int(n.value)
+                continue
+            _check(self.lib, rc, allow=(GF_E_REF_PANIC,))
+            return [out[i] for i in range(n.value)]
+
+    def counts(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        _check(self.lib, self.lib.gf_stream_get_counts(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gf_stream_destroy(self.h)
+            self.h = None
+
+
+class FastqStream:
+    """FastqReader / FastqReaderPair as a byte stream (gf_fastq_stream_*): feed raw file bytes (plain or gzip, pieces may end
+    anywhere), whole records are split and mapped on the device; records are numbered from the start of the files."""
+
+    def __init__(self, mapper, paired=True, gz=False, chunk_bytes=0):
+        self.lib = mapper.lib
+        h = C.c_void_p()
+        _check(self.lib, self.lib.gf_fastq_stream_create(mapper.m_indexer.h, 1 if paired else 0, 1 if gz else 0, chunk_bytes, C.byref(h)))
+        self.h = h
+
+    def feed(self, fq1=b"", fq2=b""):
+        _check(self.lib, self.lib.gf_fastq_stream_feed(self.h, fq1 if fq1 else None, len(fq1), fq2 if fq2 else None, len(fq2)))
+
+    def finish(self):
+        _check(self.lib, self.lib.gf_fastq_stream_finish(self.h))
+
+    def take(self):
+        cap = 4096
+        while True:
+            out = (gf_match * cap)()
+            n = C.c_uint64(0)
+            rc = self.lib.gf_fastq_stream_take(self.h, out, cap, C.byref(n))
+            if rc == GF_E_CAPACITY:
+                cap = int(n.value)
+                continue
+            _check(self.lib, rc, allow=(GF_E_REF_PANIC,))
+            return [out[i] for i in range(n.value)]
+
+    def counts(self):
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _check(self.lib, self.lib.gf_fastq_stream_get_counts(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return int(a.value), int(b.value), int(c.value)
+
+    @classmethod
+    def scan_files(cls, mapper, path1, path2=None, piece=8 << 20, chunk_bytes=0):
+        """the whole FastqReaderPair loop: format by file extension (fastq_reader.rs:149-166), files read in `piece`-byte
+        reads and fed as they come"""
+        gz = path1.endswith(".gz")
+        st = cls(mapper, paired=path2 is not None, gz=gz, chunk_bytes=chunk_bytes)
+        f1 = open(path1, "rb")
+        f2 = open(path2, "rb") if path2 else None
+        try:
+            while True:
+                a = f1.read(piece)
+                b = f2.read(piece) if f2 else b""
+                if not a and not b:
+                    break
+                st.feed(a, b)
+            st.finish()
+            return st.take(), st.counts()
+        finally:
+            f1.close()
+            if f2:
+                f2.close()
+            st.close()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gf_fastq_stream_destroy(self.h)
+            self.h = None
+
+
 class Matcher:
     """matcher.rs as FusionMapper::remove_alignables uses it (fusion_mapper.rs:488-542): built ONCE per reference (the
     reference streams through the GPU scan once, gf_reference_create), then asked per set of surviving read sequences."""

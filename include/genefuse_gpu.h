@@ -355,6 +355,43 @@ int gf_list_map_pairs(gf_index* const* idx, uint32_t n_idx, const gf_batch* in, 
 int gf_map_pairs_device_list(gf_index* const* idx, uint32_t n_idx, const gf_batch* in_dev, gf_match* const* d_out,
                              uint64_t out_cap, uint64_t* const* d_n_out, void* cuda_stream);
 
+/* ---- batched shim: packs in, large batches to the device (src/core/pescanner.rs:350-425, src/core/common.rs:20-23) ----
+ * The reference's consumers call scan_pair_end once per pack of 1000 pairs.  A gf_stream takes the packs as they are — arrays
+ * of pointers to the reads' sequence / quality strings with their lengths, which is what a ReadPairPack holds — copies them
+ * into pinned arenas and maps them in batches of `batch_pairs` (0 = 2^20) pairs with gf_map_pairs.  Pair k of a push is
+ * numbered first_pair + k in the records (the caller's own numbering, e.g. the running pair count of the producer), so
+ * several consumer threads may push packs in any order.  Records of completed batches are collected with gf_stream_take
+ * (sorted by (pair_idx, source), GF_E_CAPACITY protocol as in gf_map_pairs); gf_stream_flush maps what is still buffered
+ * (end of input).  The strings may be released as soon as the push returns.  seq2 / qual2 / len2 = NULL for a single-end
+ * stream.  Pushes on one stream are serialised internally. */
+typedef struct gf_stream gf_stream;
+int gf_stream_create(gf_index* idx, int paired, uint64_t batch_pairs, gf_stream** out);
+void gf_stream_destroy(gf_stream* s);
+int gf_stream_push(gf_stream* s, uint64_t first_pair, uint64_t n, const uint8_t* const* seq1, const uint8_t* const* qual1,
+                   const uint32_t* len1, const uint8_t* const* seq2, const uint8_t* const* qual2, const uint32_t* len2);
+int gf_stream_flush(gf_stream* s);
+int gf_stream_take(gf_stream* s, gf_match* out, uint64_t out_cap, uint64_t* n_out);
+int gf_stream_get_counts(const gf_stream* s, uint64_t* pairs_pushed, uint64_t* map_calls);
+
+/* ---- FASTQ files as a byte stream, plain or gzip (src/core/fastq_reader.rs:39-69, 75-147, 149-179) ----
+ * gf_map_fastq needs the whole text of both files in one buffer each.  A gf_fastq_stream is fed with the raw bytes of the
+ * two files as they are read, in pieces that may end anywhere: whole records are mapped on the device as soon as
+ * `chunk_bytes` (0 = 256 MiB) of text per mate have accumulated, the incomplete tail is carried over, and records are numbered
+ * from the start of the files.  format = GF_FQ_GZIP (the caller decides from the file extension like FastqReader::new, :39-69):
+ * the bytes are a gzip stream, possibly of several members (MultiGzDecoder, :49-55), inflated on the host (zlib, one thread
+ * per mate) straight into the pinned text buffers.  gf_fastq_stream_finish ends the files (a last line without '\n' counts,
+ * an incomplete last record is dropped, the shorter file decides the pair count: FastqReaderPair); records are collected
+ * with gf_fastq_stream_take at any time. */
+#define GF_FQ_PLAIN 0
+#define GF_FQ_GZIP 1
+typedef struct gf_fastq_stream gf_fastq_stream;
+int gf_fastq_stream_create(gf_index* idx, int paired, int format, uint64_t chunk_bytes, gf_fastq_stream** out);
+void gf_fastq_stream_destroy(gf_fastq_stream* s);
+int gf_fastq_stream_feed(gf_fastq_stream* s, const uint8_t* fq1, uint64_t n1, const uint8_t* fq2, uint64_t n2);
+int gf_fastq_stream_finish(gf_fastq_stream* s);
+int gf_fastq_stream_take(gf_fastq_stream* s, gf_match* out, uint64_t out_cap, uint64_t* n_out);
+int gf_fastq_stream_get_counts(const gf_fastq_stream* s, uint64_t* records, uint64_t* text_bytes, uint64_t* map_calls);
+
 /* ---- several GPUs of one box from ONE process (what the Rust binary needs; bench.py uses one process per GPU) ----
  * The index is replicated on every listed device (built there, ~19 ms each, in parallel); every batch is cut into
  * n_devices contiguous shards of pairs, each mapped by its own host thread on its own device (no device-to-device

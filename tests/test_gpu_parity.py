@@ -683,3 +683,90 @@ def test_device_batch_entry_points(host, small_panel, read_len, seed):
             os.environ.pop("GF_DEVICE_CHUNK_PAIRS", None)
     for m in mappers:
         m.close()
+
+
+@pytest.mark.parametrize("gz", [False, True])
+def test_fastq_stream_chunked_and_gzip(mappers, small_panel, host, gz, tmp_path):
+    """the two FASTQ files as byte streams (gf_fastq_stream_*): pieces that end anywhere (mid-line, mid-record,
+    different piece sizes per mate), small device chunks with the tail carried over, plain and multi-member gzip; the records
+    must equal one gf_map_fastq call on the whole text and the oracle on the reference reader's records"""
+    import gzip
+    m, o = mappers
+    rng = random.Random(19)
+    b = synth.generate_pairs(small_panel, 30000, read_len=150, seed=71, p_fusion=0.05)
+    fq1 = _to_fastq(b, 1, rng, final_newline=False)
+    fq2 = _to_fastq(b, 2, rng, extra_tail=b"@incomplete\nACGT\n+\n")
+    r1, r2 = _fastq_reader_reference(fq1), _fastq_reader_reference(fq2)
+    n = min(len(r1), len(r2))
+    want = o.scan(ReadBatch.from_reads(r1[:n], r2[:n]), threads=8)
+    whole, nrec = m.scan_fastq(fq1, fq2)
+    assert nrec == n and [r.astuple() for r in whole] == want and len(want) > 50
+
+    def enc(data, members):
+        if not gz:
+            return data
+        cuts = sorted(rng.sample(range(1, len(data)), members - 1)) if members > 1 else []
+        parts = [data[a:c] for a, c in zip([0] + cuts, cuts + [len(data)])]
+        return b"".join(gzip.compress(p, compresslevel=1) for p in parts)     # several members, cut anywhere
+    e1, e2 = enc(fq1, 3), enc(fq2, 1)
+    for chunk_bytes, piece1, piece2 in ((1 << 20, 300_001, 77_777), (4096, 1 << 16, 1 << 20), (0, len(e1), len(e2))):
+        st = host.FastqStream(m, paired=True, gz=gz, chunk_bytes=chunk_bytes)
+        p1 = p2 = 0
+        got = []
+        while p1 < len(e1) or p2 < len(e2):
+            st.feed(e1[p1:p1 + piece1], e2[p2:p2 + piece2])
+            p1 += piece1
+            p2 += piece2
+            if rng.random() < 0.3:
+                got += st.take()          # records may be collected at any time
+        st.finish()
+        got += st.take()
+        recs, text_bytes, calls = st.counts()
+        st.close()
+        assert recs == n
+        assert sorted(r.astuple() for r in got) == want, (gz, chunk_bytes)
+        if chunk_bytes and chunk_bytes <= (1 << 20):
+            assert calls > 3
+    # files on disk, format by extension (FastqReader::new), single end too
+    ext = ".fq.gz" if gz else ".fq"
+    f1, f2 = str(tmp_path / ("a_R1" + ext)), str(tmp_path / ("a_R2" + ext))
+    open(f1, "wb").write(e1)
+    open(f2, "wb").write(e2)
+    got, (recs, _tb, _calls) = host.FastqStream.scan_files(m, f1, f2, piece=1 << 18, chunk_bytes=1 << 21)
+    assert recs == n and [r.astuple() for r in got] == want
+    got, (recs, _tb, _calls) = host.FastqStream.scan_files(m, f1, None, piece=1 << 18, chunk_bytes=1 << 21)
+    assert recs == len(r1) and [r.astuple() for r in got] == o.scan(ReadBatch.from_reads(r1), threads=8)
+    if gz:      # a truncated gzip file is an error, not a silent short read
+        st = host.FastqStream(m, paired=False, gz=True)
+        st.feed(e1[:len(e1) // 2])
+        with pytest.raises(host.GeneFuseError):
+            st.finish()
+        st.close()
+
+
+def test_pack_stream_batched_shim(mappers, small_panel, host):
+    """gf_stream_*: packs of 1000 pairs (the reference's granularity, common.rs:23) pushed out of order with the caller's pair
+    numbering, mapped in batches; same records as one gf_map_pairs call over all pairs"""
+    m, o = mappers
+    b = synth.generate_pairs(small_panel, 24500, read_len=150, seed=81, p_fusion=0.05)
+    want = o.scan(b, threads=8)
+    assert len(want) > 50
+    packs = [(lo, min(lo + 1000, b.n)) for lo in range(0, b.n, 1000)]
+    random.Random(5).shuffle(packs)
+    for batch_pairs in (4000, 0):
+        st = host.PackStream(m, paired=True, batch_pairs=batch_pairs)
+        for lo, hi in packs:
+            st.push(lo, [b.read(i, 1) for i in range(lo, hi)], [b.read(i, 2) for i in range(lo, hi)])
+        st.flush()
+        got = st.take()
+        pushed, calls = st.counts()
+        st.close()
+        assert pushed == b.n and calls == (7 if batch_pairs else 1)
+        assert [r.astuple() for r in got] == want
+    st = host.PackStream(m, paired=False, batch_pairs=3000)
+    for lo, hi in packs:
+        st.push(lo, [b.read(i, 1) for i in range(lo, hi)])
+    st.flush()
+    se = ReadBatch(b.seq1, b.qual1, b.off1)
+    assert [r.astuple() for r in st.take()] == o.scan(se, threads=8)
+    st.close()
