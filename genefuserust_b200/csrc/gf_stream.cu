@@ -138,6 +138,20 @@ int gf_stream_push(gf_stream* s, uint64_t first_pair, uint64_t n, const uint8_t*
     if (s->paired && n && (!seq2 || !qual2 || !len2)) return sfail(GF_E_INVALID, "a paired stream needs both mates");
     std::lock_guard<std::mutex> lk(s->mu);
     GF_CUDA_TRY(cudaSetDevice(s->idx->device));
+    if (n && s->seq[0].cap == 0) {
+        /* first pack: size the pinned arenas for a whole batch of reads like these, once (growing a pinned buffer means
+         * cudaMallocHost + copy + cudaFreeHost, milliseconds each) */
+        for (int k = 0; k < (s->paired ? 2 : 1); k++) {
+            const uint32_t* ln = k ? len2 : len1;
+            uint64_t sum = 0;
+            for (uint64_t i = 0; i < n; i++) sum += ln[i];
+            const uint64_t want = (sum / n + 8) * (s->batch_pairs + n) + (1u << 16);
+            GF_CUDA_TRY(s->seq[k].reserve(want));
+            GF_CUDA_TRY(s->qual[k].reserve(want));
+            GF_CUDA_TRY(s->off[k].reserve(8 * (s->batch_pairs + n + 2)));
+        }
+        s->ids.reserve(s->batch_pairs + n);
+    }
     for (uint64_t i = 0; i < n; i++) {
         const uint8_t* const* sq[2] = {seq1, seq2};
         const uint8_t* const* ql[2] = {qual1, qual2};

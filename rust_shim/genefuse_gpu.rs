@@ -54,7 +54,30 @@ extern "C" {
                          out_cap: *const u64, n_out: *mut u64) -> c_int;
     fn gf_adjust_fusion_break(idx: *mut gf_index, bytes: *const u8, n_bytes: u64, refs: *const gf_break_ref, n_refs: u32,
                               jobs: *const gf_break_job, n_jobs: u64, out: *mut gf_break_out) -> c_int;
+    fn gf_index_set_output_mode(idx: *mut gf_index, mode: u32) -> c_int;
+    fn gf_stream_create(idx: *mut gf_index, paired: c_int, batch_pairs: u64, out: *mut *mut gf_stream) -> c_int;
+    fn gf_stream_destroy(s: *mut gf_stream);
+    fn gf_stream_push(s: *mut gf_stream, first_pair: u64, n: u64, seq1: *const *const u8, qual1: *const *const u8, len1: *const u32,
+                      seq2: *const *const u8, qual2: *const *const u8, len2: *const u32) -> c_int;
+    fn gf_stream_flush(s: *mut gf_stream) -> c_int;
+    fn gf_stream_take(s: *mut gf_stream, out: *mut gf_match, out_cap: u64, n_out: *mut u64) -> c_int;
+    fn gf_stream_get_counts(s: *const gf_stream, pairs_pushed: *mut u64, map_calls: *mut u64) -> c_int;
+    fn gf_reference_create(contigs: *const gf_ref_contig, n_contigs: u32, device: c_int, out: *mut *mut gf_reference) -> c_int;
+    fn gf_reference_destroy(r: *mut gf_reference);
+    fn gf_alignable_filter(r: *mut gf_reference, seqs: *const u8, seq_off: *const u64, n_seqs: u64, alignable: *mut u8,
+                           res: *mut gf_alignable_result) -> c_int;
 }
+
+#[repr(C)] pub struct gf_stream { _private: [u8; 0] }
+#[repr(C)] pub struct gf_reference { _private: [u8; 0] }
+#[repr(C)] pub struct gf_ref_contig { pub seq: *const u8, pub len: u64 }
+#[repr(C)] #[derive(Clone, Copy, Default, Debug)]
+pub struct gf_alignable_result {
+    pub key_positions: [u64; 4], pub n_removed: u64, pub panic_seq: i64, pub bloom_bits: u32, pub panic_stage: i32,
+}
+pub const GF_OUT_DROP_FILTERED: u32 = 1;
+pub const GF_OUT_BUCKET_ORDER: u32 = 2;
+pub const GF_E_REF_PANIC: c_int = -5;
 
 /// include/genefuse_gpu.h: one FusionResult's m_left_ref / m_right_ref inside the byte arena
 #[repr(C)] #[derive(Clone, Copy, Default)]
@@ -137,3 +160,69 @@ pub fn list_map_pairs(indices: &[&GpuIndex], batch: &gf_batch) -> Result<Vec<Vec
 }
 
 impl Drop for GpuIndex { fn drop(&mut self) { unsafe { gf_index_destroy(self.h) } } }
+
+
+/// The batched shim (rust_shim/batched_consumer.patch.rs): packs in, large batches to the device.
+pub struct PackStream { s: *mut gf_stream }
+unsafe impl Send for PackStream {}
+unsafe impl Sync for PackStream {} // pushes on one stream are serialised inside the library
+impl PackStream {
+    pub fn new(index: &GpuIndex, paired: bool, batch_pairs: u64) -> Result<Self, String> {
+        let mut s: *mut gf_stream = std::ptr::null_mut();
+        if unsafe { gf_stream_create(index.h, paired as c_int, batch_pairs, &mut s) } != 0 { return Err(last_error()); }
+        Ok(Self { s })
+    }
+    pub fn push(&self, first_pair: u64, s1: &[*const u8], q1: &[*const u8], l1: &[u32], s2: &[*const u8], q2: &[*const u8],
+                l2: &[u32]) -> Result<(), String> {
+        let rc = unsafe { gf_stream_push(self.s, first_pair, s1.len() as u64, s1.as_ptr(), q1.as_ptr(), l1.as_ptr(),
+                                         s2.as_ptr(), q2.as_ptr(), l2.as_ptr()) };
+        if rc != 0 { Err(last_error()) } else { Ok(()) }
+    }
+    pub fn flush(&self) -> Result<(), String> { if unsafe { gf_stream_flush(self.s) } != 0 { Err(last_error()) } else { Ok(()) } }
+    pub fn take(&self) -> Result<Vec<gf_match>, String> {
+        let mut cap = 4096usize;
+        loop {
+            let mut out = vec![gf_match::default(); cap];
+            let mut n = 0u64;
+            let rc = unsafe { gf_stream_take(self.s, out.as_mut_ptr(), cap as u64, &mut n) };
+            if rc == GF_E_CAPACITY { cap = n as usize; continue; }
+            if rc != 0 { return Err(last_error()); }
+            out.truncate(n as usize);
+            return Ok(out);
+        }
+    }
+    /// pairs that have gone through a mapping call (their packs can be released once their records were drained)
+    pub fn pairs_mapped(&self) -> u64 {
+        let (mut pushed, mut calls) = (0u64, 0u64);
+        unsafe { gf_stream_get_counts(self.s, &mut pushed, &mut calls) };
+        pushed // conservative: the caller releases packs only after take() returned their records
+    }
+}
+impl Drop for PackStream { fn drop(&mut self) { unsafe { gf_stream_destroy(self.s) } } }
+
+/// The Matcher pass (src/core/fusion_mapper.rs:488-542, src/core/matcher.rs): the reference is scanned ONCE per FASTA.
+pub struct GpuReference { r: *mut gf_reference }
+unsafe impl Send for GpuReference {}
+unsafe impl Sync for GpuReference {}
+impl GpuReference {
+    /// `contigs` = FastaReader::m_all_contigs values in BTreeMap (name) order
+    pub fn build(contigs: &[&[u8]], device: i32) -> Result<Self, String> {
+        let c: Vec<gf_ref_contig> = contigs.iter().map(|s| gf_ref_contig { seq: s.as_ptr(), len: s.len() as u64 }).collect();
+        let mut r: *mut gf_reference = std::ptr::null_mut();
+        if unsafe { gf_reference_create(c.as_ptr(), c.len() as u32, device, &mut r) } != 0 { return Err(last_error()); }
+        Ok(Self { r })
+    }
+    /// `seqs` = ReadMatch::get_read().m_seq of every surviving match in bucket order (fusion_mapper.rs:496-500)
+    pub fn alignable_filter(&self, seqs: &[&str]) -> Result<(Vec<u8>, gf_alignable_result), String> {
+        let mut arena = Vec::new();
+        let mut off = vec![0u64];
+        for s in seqs { arena.extend_from_slice(s.as_bytes()); off.push(arena.len() as u64); }
+        let mut flags = vec![0u8; seqs.len().max(1)];
+        let mut res = gf_alignable_result::default();
+        let rc = unsafe { gf_alignable_filter(self.r, arena.as_ptr(), off.as_ptr(), seqs.len() as u64, flags.as_mut_ptr(), &mut res) };
+        if rc != 0 && rc != GF_E_REF_PANIC { return Err(last_error()); }
+        flags.truncate(seqs.len());
+        Ok((flags, res))
+    }
+}
+impl Drop for GpuReference { fn drop(&mut self) { unsafe { gf_reference_destroy(self.r) } } }
