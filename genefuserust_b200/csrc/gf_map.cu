@@ -1194,6 +1194,160 @@ __global__ void __launch_bounds__(VF_WARPS * 32) k_verify(VerifyParams P) {
     }
 }
 
+/* ---- k_verify_tpj: THREAD per edit distance (reads <= 256 bases) ----------------------------------------------------
+ * The systolic kernel above keeps one 64-column block per lane: a candidate's two distances use 2-8 of a warp's 32 lanes
+ * (ncu, round 2: 7.5 active threads per instruction, 13.8 k warp instructions per candidate, 0.22 ms per 10 M pairs).
+ * Here a warp takes 16 candidates: their sequences are loaded cooperatively into shared memory, then lane 2c / 2c + 1
+ * computes the left / right distance of candidate c on its own — the same Myers / Hyyro recurrences
+ * (edit_distance.rs:12-92), all NB blocks of a column in one thread, NB a compile-time bound chosen per warp. */
+constexpr int VT_CAND = 16;      /* candidates per warp */
+constexpr int VT_SEQ = 544;      /* >= 2 * 256 - 30 + 16, like ExactWarpSmall */
+struct VerifyTpjWarp { uint8_t seq[VT_CAND][VT_SEQ]; };
+
+template <int NB>
+__device__ int thread_edit_distance(const uint8_t* part, int m, bool a_rc, const uint8_t* __restrict__ text) {
+    /* pattern a[0..m) = part (or its reverse complement), text b[0..m); returns the Levenshtein distance, m >= 1 */
+    unsigned long long plo[NB], phi[NB], pacgt[NB], pn[NB], vp[NB], vn[NB];
+    const int nb = ((m - 1) >> 6) + 1, tlen = m - 64 * (nb - 1);
+    bool other = false;
+#pragma unroll
+    for (int r = 0; r < NB; r++) {
+        plo[r] = phi[r] = pacgt[r] = pn[r] = 0ull;
+        vn[r] = 0ull;
+        vp[r] = r < nb - 1 ? ~0ull : (r == nb - 1 ? (tlen >= 64 ? ~0ull : ((1ull << tlen) - 1ull)) : 0ull);
+    }
+#pragma unroll
+    for (int r = 0; r < NB; r++) {
+        if (r < nb) {
+            const int cnt = min(64, m - 64 * r);
+            for (int q = 0; q < cnt; q++) {
+                const int k = 64 * r + q;
+                const uint32_t ch = a_rc ? gf_complement_ascii(part[m - 1 - k]) : part[k];
+                const unsigned long long bit = 1ull << q;
+                if (gf_is_acgt_upper(ch)) {
+                    pacgt[r] |= bit;
+                    if (gf_code_lo(ch)) plo[r] |= bit;
+                    if (gf_code_hi(ch)) phi[r] |= bit;
+                } else if (ch == 'N') pn[r] |= bit;
+                else other = true;
+            }
+        }
+    }
+    const unsigned long long top = 1ull << (tlen - 1);
+    int d = m;
+    for (int j = 0; j < m; j++) {
+        const uint32_t ch = __ldg(text + j);
+        const bool is_base = gf_is_acgt_upper(ch);
+        const unsigned long long tl = gf_code_lo(ch) ? ~0ull : 0ull, th = gf_code_hi(ch) ? ~0ull : 0ull;
+        uint32_t hp_in = 1u, hn_in = 0u; /* the top boundary row: D[0][j] - D[0][j-1] = +1 */
+#pragma unroll
+        for (int r = 0; r < NB; r++) {
+            if (r < nb) {
+                unsigned long long x;
+                if (is_base) x = pacgt[r] & ~(plo[r] ^ tl) & ~(phi[r] ^ th);
+                else if (ch == 'N') x = pn[r];
+                else {
+                    x = 0ull;
+                    if (other) { /* a byte outside ACGTN on both sides: plain comparison (rare) */
+                        const int cnt = min(64, m - 64 * r);
+                        for (int q = 0; q < cnt; q++) {
+                            const int k = 64 * r + q;
+                            const uint32_t pc = a_rc ? gf_complement_ascii(part[m - 1 - k]) : part[k];
+                            if (pc == ch) x |= 1ull << q;
+                        }
+                    }
+                }
+                if (hn_in) x |= 1ull;
+                const unsigned long long d0 = (((x & vp[r]) + vp[r]) ^ vp[r]) | x | vn[r];
+                const unsigned long long hp = vn[r] | ~(d0 | vp[r]);
+                const unsigned long long hn = d0 & vp[r];
+                if (r == nb - 1) {
+                    if (hp & top) d++;
+                    else if (hn & top) d--;
+                }
+                const unsigned long long x2 = (hp << 1) | (unsigned long long)hp_in;
+                vp[r] = (hn << 1) | (unsigned long long)hn_in | ~(d0 | x2);
+                vn[r] = d0 & x2;
+                hp_in = (uint32_t)(hp >> 63);
+                hn_in = (uint32_t)(hn >> 63);
+            }
+        }
+    }
+    return d;
+}
+
+__global__ void __launch_bounds__(VF_WARPS * 32) k_verify_tpj(VerifyParams P) {
+    __shared__ VerifyTpjWarp Wall[VF_WARPS];
+    const uint32_t lane = gf_lane(), wib = threadIdx.x >> 5;
+    VerifyTpjWarp& W = Wall[wib];
+    const uint64_t n_warps = (uint64_t)gridDim.x * VF_WARPS;
+    unsigned long long n = *P.n_out;
+    if (n > P.out_cap) n = P.out_cap;
+    const unsigned long long from = P.counters->verify_from;
+    for (uint64_t c0 = from + ((uint64_t)blockIdx.x * VF_WARPS + wib) * VT_CAND; c0 < n; c0 += n_warps * VT_CAND) {
+        __syncwarp();
+        const int cnt = (int)min((unsigned long long)VT_CAND, n - c0);
+        int my_len = -1;
+        for (int c = 0; c < cnt; c++) { /* cooperative loads, one candidate after the other */
+            const gf_match m = P.out[c0 + c];
+            int len = load_sequence(P.b, (uint32_t)(m.pair_idx - P.b.pair_base), m.source, m.merge_olen, W.seq[c], VT_SEQ - 16);
+            if (len >= 0 && m.used_rc) revcomp_inplace(W.seq[c], len);
+            if ((int)(lane >> 1) == c) my_len = len;
+        }
+        __syncwarp();
+        const int c = (int)(lane >> 1);
+        const bool right = (lane & 1u) != 0;
+        const bool have = c < cnt && my_len >= 0;
+        gf_match m;
+        int res = 0, plen = 0;
+        const uint8_t* text = nullptr;
+        const uint8_t* part = W.seq[c < VT_CAND ? c : 0];
+        bool rc = false, job = false;
+        uint32_t panic = 0;
+        if (have) {
+            m = P.out[c0 + c];
+            const int rb = m.read_break, left_len = rb + 1, right_len = my_len - (rb + 1);
+            plen = right ? right_len : left_len;
+            if (right) part += rb + 1;
+            const bool done = right ? calc_ed_setup(P.ix, right_len, m.r_contig, m.r_pos, m.r_pos + right_len - 1, &res, &text, &rc, &panic)
+                                    : calc_ed_setup(P.ix, left_len, m.l_contig, m.l_pos - left_len + 1, m.l_pos, &res, &text, &rc, &panic);
+            job = !done;
+        } else if (c < cnt && lane == (uint32_t)(2 * c)) {
+            atomicOr(&P.counters->error_flags, 1u);
+        }
+        /* one instantiation per warp: the smallest block count that fits every job of these 16 candidates */
+        const int nb = job ? ((plen - 1) >> 6) + 1 : 0;
+        const int nb_max = (int)__reduce_max_sync(FULL, (unsigned)nb);
+        if (nb_max > 0) {
+            int dd = 0;
+            if (nb_max <= 1) { if (job) dd = thread_edit_distance<1>(part, plen, rc, text); }
+            else if (nb_max <= 2) { if (job) dd = thread_edit_distance<2>(part, plen, rc, text); }
+            else if (nb_max <= 4) { if (job) dd = thread_edit_distance<4>(part, plen, rc, text); }
+            else { if (job) dd = thread_edit_distance<8>(part, plen, rc, text); }
+            if (job) res = dd;
+        }
+        /* what filter_matches would decide (fusion_mapper.rs:298-377): dis_connected_count of this side (src/utils/mod.rs:48-56) */
+        int chg = 0;
+        if (have)
+            for (int i = 0; i + 1 < plen; i++) chg += part[i] != part[i + 1];
+        const int o_res = __shfl_xor_sync(FULL, res, 1), o_chg = __shfl_xor_sync(FULL, chg, 1), o_len = __shfl_xor_sync(FULL, plen, 1);
+        const uint32_t o_panic = __shfl_xor_sync(FULL, panic, 1);
+        if (have && !right) {
+            const int ld = res, rd = o_res;
+            uint32_t ff = 0;
+            if (plen < 20 || chg < 7 || o_len < 20 || o_chg < 7) ff |= GF_FILTER_COMPLEXITY;
+            if (ld + rd >= 5) ff |= GF_FILTER_DISTANCE;
+            int dpos = m.l_pos - m.r_pos;
+            if (dpos < 0) dpos = -dpos;
+            if (m.l_contig == m.r_contig && dpos < P.ix.deletion_thr) ff |= GF_FILTER_INDEL;
+            P.out[c0 + c].l_dist = ld;
+            P.out[c0 + c].r_dist = rd;
+            P.out[c0 + c].filter_flags = (uint8_t)ff;
+            if (panic | o_panic) atomicAdd(&P.counters->n_ref_panic, 1u);
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* k_adjust_break: FusionResult::adjust_fusion_break / calc_ed (fusion_result.rs:299-397), warp per match */
 struct AdjustParams {
@@ -1457,7 +1611,10 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
         vp.out = d_out;
         vp.out_cap = out_cap;
         vp.n_out = d_n_out;
-        k_verify<<<(unsigned)idx->sm_count * std::min(resident_blocks(k_verify, VF_WARPS * 32, 0), 12u), VF_WARPS * 32, 0, st>>>(vp);
+        if (ex_small) /* thread per edit distance, 16 candidates per warp */
+            k_verify_tpj<<<(unsigned)idx->sm_count * std::min(resident_blocks(k_verify_tpj, VF_WARPS * 32, 0), 4u), VF_WARPS * 32, 0, st>>>(vp);
+        else
+            k_verify<<<(unsigned)idx->sm_count * std::min(resident_blocks(k_verify, VF_WARPS * 32, 0), 12u), VF_WARPS * 32, 0, st>>>(vp);
         GF_CUDA_TRY(cudaGetLastError());
         idx->launches += 2;
     }

@@ -106,14 +106,21 @@ __global__ void __launch_bounds__(RS_THREADS) k_ref_scan(const RefSeg* __restric
         const unsigned long long v64 = ((unsigned long long)v << 32) | s_v[threadIdx.x];
         const unsigned long long lo64 = ((unsigned long long)lo << 32) | s_lo[threadIdx.x];
         const unsigned long long hi64 = ((unsigned long long)hi << 32) | s_hi[threadIdx.x];
-        const unsigned long long isA = v64 & ~lo64 & ~hi64, inv = ~v64;
-        unsigned long long allA = ~0ull, ok = 0ull;
-#pragma unroll
-        for (int d = 1; d <= 15; d++) {
-            ok |= allA & (inv << d);  /* the base d back is not ACGT and everything nearer is 'A': a run starts in between */
-            allA &= isA << d;
-        }
-        ok |= allA;                   /* 15 'A's: everything older has left the 32-bit rolling value */
+        /* blocked[i] <=> some valid non-'A' base (a generate G) lies d <= 15 positions behind i with nothing but 'A's (propagate
+         * P) in between: a carry look-ahead over a window of 15, in 3 doubling steps + 3 combines (bit b of X << d = position
+         * i - d).  Non-ACGT bytes neither generate nor propagate, so a run start is never blocked; 15 'A's are a window without
+         * a generate.  kept = valid & ~blocked. */
+        const unsigned long long P1 = v64 & ~lo64 & ~hi64, G1 = v64 & ~P1;
+        const unsigned long long G2 = G1 | (P1 & (G1 << 1)), P2 = P1 & (P1 << 1);       /* window of 2 positions ending at j */
+        const unsigned long long G4 = G2 | (P2 & (G2 << 2)), P4 = P2 & (P2 << 2);       /* 4 */
+        const unsigned long long G8 = G4 | (P4 & (G4 << 4)), P8 = P4 & (P4 << 4);       /* 8 */
+        /* window of 15 = 8 + 4 + 2 + 1 positions ending at j */
+        unsigned long long G15 = G8 | (P8 & (G4 << 8));
+        const unsigned long long P12 = P8 & (P4 << 8);
+        G15 |= P12 & (G2 << 12);
+        const unsigned long long P14 = P12 & (P2 << 12);
+        G15 |= P14 & (G1 << 14);
+        const unsigned long long ok = ~(G15 << 1); /* blocked[i] = window ending at i - 1 holds a connected generate */
         /* counted positions of this sector: inside [p, p + n) and i < contig_len - 16 (`0..len-16`, :237-243) */
         const long long first = (long long)(sec - sg.p); /* index of byte 0 of the sector relative to p */
         long long lim = (long long)sg.n;
@@ -248,8 +255,8 @@ int scan_reference(gf_reference* ref, const gf_ref_contig* contigs, uint32_t n_c
     GF_CUDA_TRY(cudaEventCreate(&ev_k0.e));
     GF_CUDA_TRY(cudaEventCreate(&ev_k1.e));
     /* upper bounds of the per-buffer tables: a tile covers 4096 bytes; segments are >= 1 byte but a buffer holds at most
-     * RS_CHUNK / 64 of them (each occupies >= 64 staged bytes: 32-byte aligned start + lead) — capped below */
-    const size_t max_tiles = (size_t)(RS_CHUNK / (32 * RS_THREADS)) + 2 * 65536 + 16, max_segs = 65536;
+     * max_segs of them (the buffer is flushed when the table is full) */
+    const size_t max_segs = 4096, max_tiles = (size_t)(RS_CHUNK / (32 * RS_THREADS)) + 2 * max_segs + 16;
     bool any_host = false;
     for (uint32_t c = 0; c < n_contigs; c++) {
         if (!contigs[c].len) continue;
@@ -377,9 +384,7 @@ int gf_reference_create(const gf_ref_contig* contigs, uint32_t n_contigs, int de
     gf_reference* ref = new gf_reference();
     ref->device = device;
     struct Cleanup { gf_reference* r; ~Cleanup() { if (r) { if (r->stream) cudaStreamDestroy(r->stream); delete r; } } } guard{ref};
-    cudaDeviceProp prop;
-    GF_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    ref->sm_count = prop.multiProcessorCount;
+    GF_CUDA_TRY(cudaDeviceGetAttribute(&ref->sm_count, cudaDevAttrMultiProcessorCount, device));
     GF_CUDA_TRY(cudaStreamCreateWithFlags(&ref->stream, cudaStreamNonBlocking));
     EvGuard e0, e1;
     GF_CUDA_TRY(cudaEventCreate(&e0.e));
