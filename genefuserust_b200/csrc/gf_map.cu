@@ -22,10 +22,11 @@
  *   k_exact   (warp per survivor)           the literal algorithm: exact vote table, top-2 in BTreeMap order,
  *             gate, second pass mask, mismatch gate, segment_mask, direction gate, make_match, and the
  *             reverse-complement retry of scan_pair_end.  Emits candidate records.
- *   k_verify  (warp per candidate)          calc_distance/calc_ed: bit-parallel (Myers/Hyyro) Levenshtein with
- *             one 64-column block per lane, carries passed lane to lane in a systolic pipeline (left and right
- *             distance side by side in the two half-warps); exact for any distance, so the -1/-2 sentinels and the
- *             ">= 5" filter downstream see the reference's values.  Also sets the post-filter flags.
+ *   k_verify  (warp per 4 candidates)       calc_distance/calc_ed: bit-parallel (Myers/Hyyro) Levenshtein with
+ *             one 64-column block per lane, carries passed lane to lane in a systolic pipeline; the 8 distances of 4
+ *             candidates run side by side in groups of 4 lanes (8 / 16 lanes for longer parts); exact for any distance,
+ *             so the -1/-2 sentinels and the ">= 5" filter downstream see the reference's values.  Also sets the
+ *             post-filter flags.
  *   k_adjust_break (warp per clustered match)  FusionResult::adjust_fusion_break, src/core/fusion_result.rs:299-397.
  */
 #include <climits>
@@ -704,7 +705,8 @@ struct ExactWarpT {
     int tcnt[TBL];
     uint8_t seq[CAP];
     uint8_t flag[CAP];
-    uint8_t mask[CAP];
+    uint32_t plo[CAP / 32 + 2], phi[CAP / 32 + 2], pv[CAP / 32 + 2]; /* the sequence as code / validity bit-planes */
+    uint32_t m3[CAP / 32 + 2], m2[CAP / 32 + 2];                     /* mask == MATCH_TOP / == MATCH_SECOND per position */
     int distinct;  /* keys in the shared table */
     int overflow;  /* the shared table is too small for this read */
 };
@@ -747,11 +749,27 @@ __device__ __forceinline__ void vote_insert(long long* tk, int* tc, uint32_t tma
     }
     *overflow = 1; /* table full */
 }
-/* visit every (contig, position) the k-mer at seq[i..i+16) maps to */
-template <class F>
-__device__ __forceinline__ void for_each_site(const GfDevIndex& ix, const uint8_t* seq, int i, F f) {
-    uint32_t key;
-    if (!gf_kmer_from_ascii(seq + i, &key)) return;
+/* W.seq (ASCII, len bytes) -> bit-planes: one ballot per plane and 32 bases (make_kmer_bytes: upper-case ACGT only,
+ * indexer.rs:888-904); one zero word behind the last base */
+template <class EW>
+__device__ void exact_planes(EW& W, int len) {
+    const uint32_t lane = gf_lane();
+    const int nw = (len + 31) >> 5;
+    for (int w = 0; w <= nw; w++) {
+        const int j = 32 * w + (int)lane;
+        const uint32_t c = j < len ? W.seq[j] : 0u;
+        const bool ok = gf_is_acgt_upper(c);
+        const uint32_t v = __ballot_sync(FULL, ok), lo = __ballot_sync(FULL, ok && gf_code_lo(c)), hi = __ballot_sync(FULL, ok && gf_code_hi(c));
+        if (lane == 0) { W.pv[w] = v; W.plo[w] = lo; W.phi[w] = hi; }
+    }
+    __syncwarp();
+}
+/* visit every (contig, position) the k-mer at offset i maps to */
+template <class EW, class F>
+__device__ __forceinline__ void for_each_site(const GfDevIndex& ix, const EW& W, int i, F f) {
+    const uint32_t bp = (uint32_t)i;
+    if ((fsr(W.pv, bp) & 0xFFFFu) != 0xFFFFu) return;
+    const uint32_t key = ((fsr(W.phi, bp) & 0xFFFFu) << 16) | (fsr(W.plo, bp) & 0xFFFFu);
     uint32_t val = gf_table_find(ix, key);
     if (val == GF_EMPTY_VAL) return;
     uint32_t kind = val >> 30;
@@ -769,6 +787,29 @@ __device__ __forceinline__ void for_each_site(const GfDevIndex& ix, const uint8_
     }
 }
 
+/* next set bit of plane `pl` (nw words) at position >= from, or `none` */
+__device__ __forceinline__ int next_bit(const uint32_t* pl, int nw, int from, int none) {
+    if (from < 0) from = 0;
+    int w = from >> 5;
+    if (w >= nw) return none;
+    uint32_t x = pl[w] & (0xFFFFFFFFu << (from & 31));
+    while (!x) {
+        if (++w >= nw) return none;
+        x = pl[w];
+    }
+    return 32 * w + __ffs(x) - 1;
+}
+__device__ __forceinline__ int next_zero(const uint32_t* pl, int nw, int from, int none) {
+    int w = from >> 5;
+    if (w >= nw) return none;
+    uint32_t x = ~pl[w] & (0xFFFFFFFFu << (from & 31));
+    while (!x) {
+        if (++w >= nw) return none;
+        x = ~pl[w];
+    }
+    return 32 * w + __ffs(x) - 1;
+}
+
 struct SegResult { int n; int s0, e0, s1, e1; long long gp0, gp1; }; /* entries in TOP, SECOND order */
 
 /* Indexer::map_read (indexer.rs:252-538) on the ASCII sequence in W.seq.  All lanes return the same result. */
@@ -778,6 +819,7 @@ __device__ SegResult exact_map_read(const GfDevIndex& ix, EW& W, int len, long l
     SegResult R;
     R.n = 0; R.s0 = R.e0 = R.s1 = R.e1 = 0; R.gp0 = R.gp1 = 0;
     if (len < 16) return R;
+    exact_planes(W, len);
     const int nprobe = ((len - 16) >> 1) + 1;
     long long* tk = W.tkeys;
     int* tc = W.tcnt;
@@ -792,7 +834,7 @@ __device__ SegResult exact_map_read(const GfDevIndex& ix, EW& W, int len, long l
         const int limit = (int)(tsize - tsize / 4);
         for (int j = (int)lane; j < nprobe; j += 32) {
             int i = 2 * j;
-            for_each_site(ix, W.seq, i, [&](int32_t c, int32_t p) {
+            for_each_site(ix, W, i, [&](int32_t c, int32_t p) {
                 vote_insert(tk, tc, tmask, gf_gp_pack(c, p - i), &W.distinct, limit, &W.overflow);
             });
         }
@@ -832,7 +874,7 @@ __device__ SegResult exact_map_read(const GfDevIndex& ix, EW& W, int len, long l
     const int nwin = len - 15;
     for (int i = (int)lane; i < nwin; i += 32) {
         int f = 0;
-        for_each_site(ix, W.seq, i, [&](int32_t c, int32_t p) {
+        for_each_site(ix, W, i, [&](int32_t c, int32_t p) {
             long long g = gf_gp_pack(c, p - i);
             long long d1 = g - gp1, d2 = g - gp2;
             if (d1 < 0) d1 = -d1;
@@ -843,51 +885,50 @@ __device__ SegResult exact_map_read(const GfDevIndex& ix, EW& W, int len, long l
         W.flag[i] = (uint8_t)f;
     }
     __syncwarp();
+    /* mask[p] = max flag of the (<= 16) windows covering p, kept as two planes: == MATCH_TOP (3), == MATCH_SECOND (2) */
     int mism = 0;
-    for (int p = (int)lane; p < len; p += 32) {
-        int lo = max(0, p - 15), hi = min(p, nwin - 1);
+    const int nwm = (len + 31) >> 5;
+    for (int w = 0; w < nwm; w++) {
+        const int p = 32 * w + (int)lane;
         int m = 0;
-        for (int i = lo; i <= hi; i++) m = max(m, (int)W.flag[i]);
-        W.mask[p] = (uint8_t)m;
-        if (m <= 1) mism++; /* MATCH_NONE or MATCH_UNKNOWN (:523-528) */
+        if (p < len) {
+            const int lo = max(0, p - 15), hi = min(p, nwin - 1);
+            for (int i = lo; i <= hi; i++) m = max(m, (int)W.flag[i]);
+            if (m <= 1) mism++; /* MATCH_NONE or MATCH_UNKNOWN (:523-528) */
+        }
+        const uint32_t b3 = __ballot_sync(FULL, m == 3), b2 = __ballot_sync(FULL, m == 2);
+        if (lane == 0) { W.m3[w] = b3; W.m2[w] = b2; }
     }
     mism = (int)__reduce_add_sync(FULL, (unsigned)mism);
     __syncwarp();
     if (mism > ix.mismatch_thr) return R; /* :530-535 */
 
-    /* segment_mask (:616-679): every start s < len-1 with mask[s]==target is tried; the longest run wins,
-     * the first one on ties (strict '>'), and only if end-start > 20 */
+    /* segment_mask (:616-679): every start s < len - 1 with mask[s] == target is tried, the walk tolerates gaps of up to 9
+     * lower values and stops at any higher one; the longest run wins, the first one on ties (strict '>'), and only if
+     * end - start > 20.  The walk is memoryless, so the starts fall into disjoint chains of target positions (linked when at
+     * most 9 lower values and nothing higher lie between) and only a chain's first position can win: one pass over the
+     * chains, jumping from gap to gap with bit scans. */
     for (int t = 0; t < 2; t++) {
-        const int target = t == 0 ? 3 : 2;
-        uint32_t best = 0;
-        for (int s = (int)lane; s < len - 1; s += 32) {
-            if (W.mask[s] != target) continue;
-            /* The walk below is memoryless, so a start that an earlier start's walk passes through ends at the same `end`
-             * and scores strictly less: only the first start of each walk can win.  s is such a first start unless a
-             * target position lies within the 10 positions before it with nothing higher in between. */
-            bool first = true;
-            for (int q = s - 1; q >= 0 && q >= s - 10; q--) {
-                const int mq = W.mask[q];
-                if (mq > target) break;
-                if (mq == target) { first = false; break; }
+        const uint32_t* T = t == 0 ? W.m3 : W.m2;
+        const uint32_t* H = t == 0 ? nullptr : W.m3; /* values above the target */
+        int best_len = 0, best_s = 0;
+        int s0 = next_bit(T, nwm, 0, -1);
+        while (s0 >= 0 && s0 < len - 1) {
+            int pos = s0, last_t;
+            for (;;) {
+                const int run_end = min(next_zero(T, nwm, pos, len), len); /* pos .. run_end - 1 are target */
+                last_t = run_end - 1;
+                const int nt = next_bit(T, nwm, run_end, -1);
+                if (nt < 0 || nt - run_end > 9) break;                       /* gap of >= 10 lower values: the walk gives up */
+                if (H && next_bit(H, nwm, run_end, len) < nt) break;         /* a higher value first: break (:648-650) */
+                pos = nt;
             }
-            if (!first) continue;
-            int end = s + 1, g = 0;
-            while (g < 10 && end + g < len) {
-                int m = W.mask[end + g];
-                if (m > target) break;
-                if (m == target) { end += g + 1; g = 0; continue; }
-                g++;
-            }
-            end -= 1;
-            uint32_t sc_ = ((uint32_t)(end - s) << 16) | (0xFFFFu - (uint32_t)s);
-            best = max(best, sc_);
+            if (last_t - s0 > best_len) { best_len = last_t - s0; best_s = s0; }
+            s0 = next_bit(T, nwm, last_t + 1, -1);
         }
-        best = __reduce_max_sync(FULL, best);
-        int seglen = (int)(best >> 16), s = (int)(0xFFFFu - (best & 0xFFFFu));
-        if (seglen > 20) {
-            if (R.n == 0) { R.s0 = s; R.e0 = s + seglen; R.gp0 = t == 0 ? gp1 : gp2; }
-            else { R.s1 = s; R.e1 = s + seglen; R.gp1 = t == 0 ? gp1 : gp2; }
+        if (best_len > 20) {
+            if (R.n == 0) { R.s0 = best_s; R.e0 = best_s + best_len; R.gp0 = t == 0 ? gp1 : gp2; }
+            else { R.s1 = best_s; R.e1 = best_s + best_len; R.gp1 = t == 0 ? gp1 : gp2; }
             R.n++;
         }
     }
@@ -983,7 +1024,6 @@ __global__ void __launch_bounds__(EX_WARPS * 32) k_exact(ExactParams P) {
 /* ------------------------------------------------------------------------------------------------ */
 /* k_verify: calc_distance / calc_ed / edit_distance                                                 */
 constexpr int VF_WARPS = 4;
-struct VerifyWarp { uint8_t seq[EX_SEQ_CAP]; };
 
 struct VerifyParams {
     GfDevIndex ix;
@@ -1052,18 +1092,14 @@ __device__ int warp_edit_distance(const uint8_t* part, int m, bool a_rc, const u
     return __shfl_sync(FULL, d, tmax);
 }
 
-/* Two equal-length edit distances at once, one per half-warp (lanes 0-15: job 0, lanes 16-31: job 1): the same systolic
- * recurrences as warp_edit_distance with the block index = lane & 15, so a candidate's left and right distances cost
- * max(m0, m1) + blocks steps instead of their sum.  Needs <= 16 blocks (m <= 1024) per job; m == 0 = no job (result 0). */
-__device__ void warp_edit_distance_dual(const uint8_t* part0, int m0, bool rc0, const uint8_t* __restrict__ text0,
-                                        const uint8_t* part1, int m1, bool rc1, const uint8_t* __restrict__ text1, int* d0,
-                                        int* d1) {
-    const uint32_t lane = gf_lane(), hl = lane & 15u;
-    const bool side = lane >= 16;
-    const uint8_t* part = side ? part1 : part0;
-    const uint8_t* text = side ? text1 : text0;
-    const int m = side ? m1 : m0;
-    const bool a_rc = side ? rc1 : rc0;
+/* 32 / G equal-length edit distances at once, one per group of G consecutive lanes: the same systolic recurrences as
+ * warp_edit_distance with the block index = lane % G, so 32 / G jobs cost max(m) + blocks steps instead of their sum — and
+ * 32 / G times fewer warp instructions per job than one job per warp (ncu, round 2: a candidate's two distances kept 7.5 of
+ * 32 lanes busy and k_verify was issue bound at 13.8 k warp instructions per candidate).  Every lane of a group passes the
+ * group's job; needs <= G blocks (m <= 64 G); m == 0 = no job (result 0). */
+template <int G>
+__device__ int group_edit_distance(const uint8_t* part, int m, bool a_rc, const uint8_t* __restrict__ text) {
+    const uint32_t lane = gf_lane(), hl = lane % G;
     const int nb = m > 0 ? ((m - 1) >> 6) + 1 : 0, tmax = nb - 1, tlen = m - 64 * tmax;
     auto a_at = [&](int k) -> uint8_t { return a_rc ? gf_complement_ascii(part[m - 1 - k]) : part[k]; };
     unsigned long long pA = 0, pC = 0, pG = 0, pT = 0, pN = 0, pO = 0;
@@ -1086,8 +1122,8 @@ __device__ void warp_edit_distance_dual(const uint8_t* part0, int m0, bool rc0, 
     const int my_steps = m > 0 ? m + nb - 1 : 0;
     const int steps = (int)__reduce_max_sync(FULL, (unsigned)my_steps);
     for (int t = 0; t < steps; t++) {
-        uint32_t hp_in = __shfl_up_sync(FULL, hp_out, 1, 16);
-        uint32_t hn_in = __shfl_up_sync(FULL, hn_out, 1, 16);
+        uint32_t hp_in = __shfl_up_sync(FULL, hp_out, 1, G);
+        uint32_t hn_in = __shfl_up_sync(FULL, hn_out, 1, G);
         int j = t - (int)hl;
         if ((int)hl < nb && j >= 0 && j < m) {
             uint8_t ch = __ldg(text + j);
@@ -1115,10 +1151,8 @@ __device__ void warp_edit_distance_dual(const uint8_t* part0, int m0, bool rc0, 
             }
         }
     }
-    const int r0 = __shfl_sync(FULL, d, m0 > 0 ? ((m0 - 1) >> 6) : 0);
-    const int r1 = __shfl_sync(FULL, d, 16 + (m1 > 0 ? ((m1 - 1) >> 6) : 0));
-    *d0 = m0 > 0 ? r0 : 0;
-    *d1 = m1 > 0 ? r1 : 0;
+    const int r = __shfl_sync(FULL, d, (int)(lane - hl) + (tmax > 0 ? tmax : 0));
+    return m > 0 ? r : 0;
 }
 
 /* the checks of FusionMapper::calc_ed (fusion_mapper.rs:224-251) that come before the edit distance: returns true when
@@ -1139,212 +1173,118 @@ __device__ bool calc_ed_setup(const GfDevIndex& ix, int plen, int32_t contig, in
     return false;
 }
 
+constexpr int VG_CAND = 4; /* candidates a warp verifies together */
+template <int CAP>
+struct VerifyGrpWarp {
+    uint8_t seq[VG_CAND][CAP];
+    const uint8_t* text[2 * VG_CAND]; /* per job (2 c = left, 2 c + 1 = right of candidate c): the gene bytes to compare with */
+    int m[2 * VG_CAND];               /* job length, 0 = no distance to compute (sentinel, empty side, missing candidate) */
+    int res[2 * VG_CAND];
+    int off[2 * VG_CAND];             /* where the job's part starts in seq[c] */
+    int rc[2 * VG_CAND];
+    int len[VG_CAND];
+};
+
+template <int CAP>
 __global__ void __launch_bounds__(VF_WARPS * 32) k_verify(VerifyParams P) {
-    __shared__ VerifyWarp Wall[VF_WARPS];
-    const uint32_t lane = gf_lane();
-    const uint32_t wib = threadIdx.x >> 5;
-    VerifyWarp& W = Wall[wib];
-    const uint64_t n_warps = (uint64_t)gridDim.x * VF_WARPS;
-    unsigned long long n = *P.n_out;
-    if (n > P.out_cap) n = P.out_cap;
-    for (uint64_t ci = P.counters->verify_from + (uint64_t)blockIdx.x * VF_WARPS + wib; ci < n; ci += n_warps) {
-        gf_match m = P.out[ci];
-        __syncwarp();
-        const int len = load_sequence(P.b, (uint32_t)(m.pair_idx - P.b.pair_base), m.source, m.merge_olen, W.seq, EX_SEQ_CAP - 16);
-        if (len < 0) { if (lane == 0) atomicOr(&P.counters->error_flags, 1u); continue; }
-        if (m.used_rc) revcomp_inplace(W.seq, len);
-        const int rb = m.read_break;
-        const int left_len = rb + 1, right_len = len - (rb + 1);
-        uint32_t panic = 0;
-        int ld = 0, rd = 0;
-        {
-            const uint8_t *tl = nullptr, *tr = nullptr;
-            bool rcl = false, rcr = false;
-            const bool dl = calc_ed_setup(P.ix, left_len, m.l_contig, m.l_pos - left_len + 1, m.l_pos, &ld, &tl, &rcl, &panic);
-            const bool dr = calc_ed_setup(P.ix, right_len, m.r_contig, m.r_pos, m.r_pos + right_len - 1, &rd, &tr, &rcr, &panic);
-            if (left_len <= 1024 && right_len <= 1024) { /* both distances side by side, one per half-warp */
-                int a = 0, b = 0;
-                if (!dl || !dr)
-                    warp_edit_distance_dual(W.seq, dl ? 0 : left_len, rcl, tl, W.seq + rb + 1, dr ? 0 : right_len, rcr, tr, &a, &b);
-                if (!dl) ld = a;
-                if (!dr) rd = b;
-            } else {
-                if (!dl) ld = warp_edit_distance(W.seq, left_len, rcl, tl);
-                if (!dr) rd = warp_edit_distance(W.seq + rb + 1, right_len, rcr, tr);
-            }
-        }
-        /* what filter_matches would decide (fusion_mapper.rs:298-377); the record is kept either way */
-        int chg_l = 0, chg_r = 0; /* dis_connected_count (src/utils/mod.rs:48-56) of both sides of the break */
-        for (int i = (int)lane; i + 1 < left_len; i += 32) chg_l += W.seq[i] != W.seq[i + 1];
-        for (int i = (int)lane; i + 1 < right_len; i += 32) chg_r += W.seq[rb + 1 + i] != W.seq[rb + 2 + i];
-        chg_l = (int)__reduce_add_sync(FULL, (unsigned)chg_l);
-        chg_r = (int)__reduce_add_sync(FULL, (unsigned)chg_r);
-        if (lane == 0) {
-            uint32_t ff = 0;
-            if (left_len < 20 || chg_l < 7 || right_len < 20 || chg_r < 7) ff |= GF_FILTER_COMPLEXITY;
-            if (ld + rd >= 5) ff |= GF_FILTER_DISTANCE;
-            int dpos = m.l_pos - m.r_pos;
-            if (dpos < 0) dpos = -dpos;
-            if (m.l_contig == m.r_contig && dpos < P.ix.deletion_thr) ff |= GF_FILTER_INDEL;
-            P.out[ci].l_dist = ld;
-            P.out[ci].r_dist = rd;
-            P.out[ci].filter_flags = (uint8_t)ff;
-            if (panic) atomicAdd(&P.counters->n_ref_panic, 1u);
-        }
-    }
-}
-
-/* ---- k_verify_tpj: THREAD per edit distance (reads <= 256 bases) ----------------------------------------------------
- * The systolic kernel above keeps one 64-column block per lane: a candidate's two distances use 2-8 of a warp's 32 lanes
- * (ncu, round 2: 7.5 active threads per instruction, 13.8 k warp instructions per candidate, 0.22 ms per 10 M pairs).
- * Here a warp takes 16 candidates: their sequences are loaded cooperatively into shared memory, then lane 2c / 2c + 1
- * computes the left / right distance of candidate c on its own — the same Myers / Hyyro recurrences
- * (edit_distance.rs:12-92), all NB blocks of a column in one thread, NB a compile-time bound chosen per warp. */
-constexpr int VT_CAND = 16;      /* candidates per warp */
-constexpr int VT_SEQ = 544;      /* >= 2 * 256 - 30 + 16, like ExactWarpSmall */
-struct VerifyTpjWarp { uint8_t seq[VT_CAND][VT_SEQ]; };
-
-template <int NB>
-__device__ int thread_edit_distance(const uint8_t* part, int m, bool a_rc, const uint8_t* __restrict__ text) {
-    /* pattern a[0..m) = part (or its reverse complement), text b[0..m); returns the Levenshtein distance, m >= 1 */
-    unsigned long long plo[NB], phi[NB], pacgt[NB], pn[NB], vp[NB], vn[NB];
-    const int nb = ((m - 1) >> 6) + 1, tlen = m - 64 * (nb - 1);
-    bool other = false;
-#pragma unroll
-    for (int r = 0; r < NB; r++) {
-        plo[r] = phi[r] = pacgt[r] = pn[r] = 0ull;
-        vn[r] = 0ull;
-        vp[r] = r < nb - 1 ? ~0ull : (r == nb - 1 ? (tlen >= 64 ? ~0ull : ((1ull << tlen) - 1ull)) : 0ull);
-    }
-#pragma unroll
-    for (int r = 0; r < NB; r++) {
-        if (r < nb) {
-            const int cnt = min(64, m - 64 * r);
-            for (int q = 0; q < cnt; q++) {
-                const int k = 64 * r + q;
-                const uint32_t ch = a_rc ? gf_complement_ascii(part[m - 1 - k]) : part[k];
-                const unsigned long long bit = 1ull << q;
-                if (gf_is_acgt_upper(ch)) {
-                    pacgt[r] |= bit;
-                    if (gf_code_lo(ch)) plo[r] |= bit;
-                    if (gf_code_hi(ch)) phi[r] |= bit;
-                } else if (ch == 'N') pn[r] |= bit;
-                else other = true;
-            }
-        }
-    }
-    const unsigned long long top = 1ull << (tlen - 1);
-    int d = m;
-    for (int j = 0; j < m; j++) {
-        const uint32_t ch = __ldg(text + j);
-        const bool is_base = gf_is_acgt_upper(ch);
-        const unsigned long long tl = gf_code_lo(ch) ? ~0ull : 0ull, th = gf_code_hi(ch) ? ~0ull : 0ull;
-        uint32_t hp_in = 1u, hn_in = 0u; /* the top boundary row: D[0][j] - D[0][j-1] = +1 */
-#pragma unroll
-        for (int r = 0; r < NB; r++) {
-            if (r < nb) {
-                unsigned long long x;
-                if (is_base) x = pacgt[r] & ~(plo[r] ^ tl) & ~(phi[r] ^ th);
-                else if (ch == 'N') x = pn[r];
-                else {
-                    x = 0ull;
-                    if (other) { /* a byte outside ACGTN on both sides: plain comparison (rare) */
-                        const int cnt = min(64, m - 64 * r);
-                        for (int q = 0; q < cnt; q++) {
-                            const int k = 64 * r + q;
-                            const uint32_t pc = a_rc ? gf_complement_ascii(part[m - 1 - k]) : part[k];
-                            if (pc == ch) x |= 1ull << q;
-                        }
-                    }
-                }
-                if (hn_in) x |= 1ull;
-                const unsigned long long d0 = (((x & vp[r]) + vp[r]) ^ vp[r]) | x | vn[r];
-                const unsigned long long hp = vn[r] | ~(d0 | vp[r]);
-                const unsigned long long hn = d0 & vp[r];
-                if (r == nb - 1) {
-                    if (hp & top) d++;
-                    else if (hn & top) d--;
-                }
-                const unsigned long long x2 = (hp << 1) | (unsigned long long)hp_in;
-                vp[r] = (hn << 1) | (unsigned long long)hn_in | ~(d0 | x2);
-                vn[r] = d0 & x2;
-                hp_in = (uint32_t)(hp >> 63);
-                hn_in = (uint32_t)(hn >> 63);
-            }
-        }
-    }
-    return d;
-}
-
-__global__ void __launch_bounds__(VF_WARPS * 32) k_verify_tpj(VerifyParams P) {
-    __shared__ VerifyTpjWarp Wall[VF_WARPS];
+    __shared__ VerifyGrpWarp<CAP> Wall[VF_WARPS];
     const uint32_t lane = gf_lane(), wib = threadIdx.x >> 5;
-    VerifyTpjWarp& W = Wall[wib];
+    VerifyGrpWarp<CAP>& W = Wall[wib];
     const uint64_t n_warps = (uint64_t)gridDim.x * VF_WARPS;
     unsigned long long n = *P.n_out;
     if (n > P.out_cap) n = P.out_cap;
     const unsigned long long from = P.counters->verify_from;
-    for (uint64_t c0 = from + ((uint64_t)blockIdx.x * VF_WARPS + wib) * VT_CAND; c0 < n; c0 += n_warps * VT_CAND) {
+    for (uint64_t c0 = from + ((uint64_t)blockIdx.x * VF_WARPS + wib) * VG_CAND; c0 < n; c0 += n_warps * VG_CAND) {
         __syncwarp();
-        const int cnt = (int)min((unsigned long long)VT_CAND, n - c0);
-        int my_len = -1;
-        for (int c = 0; c < cnt; c++) { /* cooperative loads, one candidate after the other */
-            const gf_match m = P.out[c0 + c];
-            int len = load_sequence(P.b, (uint32_t)(m.pair_idx - P.b.pair_base), m.source, m.merge_olen, W.seq[c], VT_SEQ - 16);
-            if (len >= 0 && m.used_rc) revcomp_inplace(W.seq[c], len);
-            if ((int)(lane >> 1) == c) my_len = len;
+        const int cnt = (int)min((unsigned long long)VG_CAND, n - c0);
+        for (int c = 0; c < VG_CAND; c++) { /* cooperative loads, one candidate after the other */
+            int len = -1;
+            if (c < cnt) {
+                const gf_match m = P.out[c0 + c];
+                len = load_sequence(P.b, (uint32_t)(m.pair_idx - P.b.pair_base), m.source, m.merge_olen, W.seq[c], CAP - 16);
+                if (len >= 0 && m.used_rc) revcomp_inplace(W.seq[c], len);
+                if (len < 0 && lane == 0) atomicOr(&P.counters->error_flags, 1u);
+            }
+            if (lane == 0) W.len[c] = len;
         }
         __syncwarp();
-        const int c = (int)(lane >> 1);
-        const bool right = (lane & 1u) != 0;
-        const bool have = c < cnt && my_len >= 0;
-        gf_match m;
-        int res = 0, plen = 0;
-        const uint8_t* text = nullptr;
-        const uint8_t* part = W.seq[c < VT_CAND ? c : 0];
-        bool rc = false, job = false;
+        /* the checks of calc_ed per job (lane j < 8 = job j) */
         uint32_t panic = 0;
-        if (have) {
-            m = P.out[c0 + c];
-            const int rb = m.read_break, left_len = rb + 1, right_len = my_len - (rb + 1);
-            plen = right ? right_len : left_len;
-            if (right) part += rb + 1;
-            const bool done = right ? calc_ed_setup(P.ix, right_len, m.r_contig, m.r_pos, m.r_pos + right_len - 1, &res, &text, &rc, &panic)
-                                    : calc_ed_setup(P.ix, left_len, m.l_contig, m.l_pos - left_len + 1, m.l_pos, &res, &text, &rc, &panic);
-            job = !done;
-        } else if (c < cnt && lane == (uint32_t)(2 * c)) {
-            atomicOr(&P.counters->error_flags, 1u);
+        if (lane < 2 * VG_CAND) {
+            const int c = (int)(lane >> 1);
+            const bool right = (lane & 1u) != 0;
+            int res = 0, m_job = 0, off = 0;
+            const uint8_t* text = nullptr;
+            bool rc = false;
+            if (c < cnt && W.len[c] >= 0) {
+                const gf_match m = P.out[c0 + c];
+                const int rb = m.read_break, left_len = rb + 1, right_len = W.len[c] - (rb + 1);
+                const int plen = right ? right_len : left_len;
+                off = right ? rb + 1 : 0;
+                const bool done = right ? calc_ed_setup(P.ix, right_len, m.r_contig, m.r_pos, m.r_pos + right_len - 1, &res, &text, &rc, &panic)
+                                        : calc_ed_setup(P.ix, left_len, m.l_contig, m.l_pos - left_len + 1, m.l_pos, &res, &text, &rc, &panic);
+                m_job = done ? 0 : plen;
+            }
+            W.res[lane] = res; W.m[lane] = m_job; W.off[lane] = off; W.text[lane] = text; W.rc[lane] = rc ? 1 : 0;
         }
-        /* one instantiation per warp: the smallest block count that fits every job of these 16 candidates */
-        const int nb = job ? ((plen - 1) >> 6) + 1 : 0;
-        const int nb_max = (int)__reduce_max_sync(FULL, (unsigned)nb);
-        if (nb_max > 0) {
-            int dd = 0;
-            if (nb_max <= 1) { if (job) dd = thread_edit_distance<1>(part, plen, rc, text); }
-            else if (nb_max <= 2) { if (job) dd = thread_edit_distance<2>(part, plen, rc, text); }
-            else if (nb_max <= 4) { if (job) dd = thread_edit_distance<4>(part, plen, rc, text); }
-            else { if (job) dd = thread_edit_distance<8>(part, plen, rc, text); }
-            if (job) res = dd;
+        __syncwarp();
+        int mx = 0;
+        for (int j = 0; j < 2 * VG_CAND; j++) mx = max(mx, W.m[j]);
+        /* all 8 jobs at once with 4 lanes each when every job fits 4 blocks (256 columns: every unmerged read), else 4 jobs
+         * of 8 lanes twice, else 2 jobs of 16 lanes four times */
+        if (mx > 0) {
+            if (mx <= 256) {
+                const int j = (int)(lane >> 2);
+                const int d = group_edit_distance<4>(W.seq[j >> 1] + W.off[j], W.m[j], W.rc[j] != 0, W.text[j]);
+                if ((lane & 3u) == 0 && W.m[j] > 0) W.res[j] = d;
+            } else if (mx <= 512) {
+                for (int r = 0; r < 2; r++) {
+                    const int j = 4 * r + (int)(lane >> 3);
+                    const int d = group_edit_distance<8>(W.seq[j >> 1] + W.off[j], W.m[j], W.rc[j] != 0, W.text[j]);
+                    if ((lane & 7u) == 0 && W.m[j] > 0) W.res[j] = d;
+                }
+            } else if (mx <= 1024) {
+                for (int r = 0; r < 4; r++) {
+                    const int j = 2 * r + (int)(lane >> 4);
+                    const int d = group_edit_distance<16>(W.seq[j >> 1] + W.off[j], W.m[j], W.rc[j] != 0, W.text[j]);
+                    if ((lane & 15u) == 0 && W.m[j] > 0) W.res[j] = d;
+                }
+            } else {
+                for (int j = 0; j < 2 * VG_CAND; j++) {
+                    if (W.m[j] == 0) continue; /* warp-uniform */
+                    const int d = warp_edit_distance(W.seq[j >> 1] + W.off[j], W.m[j], W.rc[j] != 0, W.text[j]);
+                    if (lane == 0) W.res[j] = d;
+                }
+            }
         }
-        /* what filter_matches would decide (fusion_mapper.rs:298-377): dis_connected_count of this side (src/utils/mod.rs:48-56) */
-        int chg = 0;
-        if (have)
-            for (int i = 0; i + 1 < plen; i++) chg += part[i] != part[i + 1];
-        const int o_res = __shfl_xor_sync(FULL, res, 1), o_chg = __shfl_xor_sync(FULL, chg, 1), o_len = __shfl_xor_sync(FULL, plen, 1);
-        const uint32_t o_panic = __shfl_xor_sync(FULL, panic, 1);
-        if (have && !right) {
-            const int ld = res, rd = o_res;
-            uint32_t ff = 0;
-            if (plen < 20 || chg < 7 || o_len < 20 || o_chg < 7) ff |= GF_FILTER_COMPLEXITY;
-            if (ld + rd >= 5) ff |= GF_FILTER_DISTANCE;
-            int dpos = m.l_pos - m.r_pos;
-            if (dpos < 0) dpos = -dpos;
-            if (m.l_contig == m.r_contig && dpos < P.ix.deletion_thr) ff |= GF_FILTER_INDEL;
-            P.out[c0 + c].l_dist = ld;
-            P.out[c0 + c].r_dist = rd;
-            P.out[c0 + c].filter_flags = (uint8_t)ff;
-            if (panic | o_panic) atomicAdd(&P.counters->n_ref_panic, 1u);
+        __syncwarp();
+        panic = __reduce_or_sync(FULL, panic);
+        /* what filter_matches would decide (fusion_mapper.rs:298-377); the record is kept either way */
+        for (int c = 0; c < cnt; c++) {
+            const int len = W.len[c];
+            if (len < 0) continue;
+            const gf_match m = P.out[c0 + c];
+            const int rb = m.read_break, left_len = rb + 1, right_len = len - (rb + 1);
+            const uint8_t* sq = W.seq[c];
+            int chg_l = 0, chg_r = 0; /* dis_connected_count (src/utils/mod.rs:48-56) of both sides of the break */
+            for (int i = (int)lane; i + 1 < left_len; i += 32) chg_l += sq[i] != sq[i + 1];
+            for (int i = (int)lane; i + 1 < right_len; i += 32) chg_r += sq[rb + 1 + i] != sq[rb + 2 + i];
+            chg_l = (int)__reduce_add_sync(FULL, (unsigned)chg_l);
+            chg_r = (int)__reduce_add_sync(FULL, (unsigned)chg_r);
+            if (lane == 0) {
+                const int ld = W.res[2 * c], rd = W.res[2 * c + 1];
+                uint32_t ff = 0;
+                if (left_len < 20 || chg_l < 7 || right_len < 20 || chg_r < 7) ff |= GF_FILTER_COMPLEXITY;
+                if (ld + rd >= 5) ff |= GF_FILTER_DISTANCE;
+                int dpos = m.l_pos - m.r_pos;
+                if (dpos < 0) dpos = -dpos;
+                if (m.l_contig == m.r_contig && dpos < P.ix.deletion_thr) ff |= GF_FILTER_INDEL;
+                P.out[c0 + c].l_dist = ld;
+                P.out[c0 + c].r_dist = rd;
+                P.out[c0 + c].filter_flags = (uint8_t)ff;
+            }
         }
+        if (panic && lane == 0) atomicAdd(&P.counters->n_ref_panic, 1u);
     }
 }
 
@@ -1611,10 +1551,10 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
         vp.out = d_out;
         vp.out_cap = out_cap;
         vp.n_out = d_n_out;
-        if (ex_small) /* thread per edit distance, 16 candidates per warp */
-            k_verify_tpj<<<(unsigned)idx->sm_count * std::min(resident_blocks(k_verify_tpj, VF_WARPS * 32, 0), 4u), VF_WARPS * 32, 0, st>>>(vp);
+        if (ex_small)
+            k_verify<544><<<(unsigned)idx->sm_count * std::min(resident_blocks(k_verify<544>, VF_WARPS * 32, 0), 8u), VF_WARPS * 32, 0, st>>>(vp);
         else
-            k_verify<<<(unsigned)idx->sm_count * std::min(resident_blocks(k_verify, VF_WARPS * 32, 0), 12u), VF_WARPS * 32, 0, st>>>(vp);
+            k_verify<EX_SEQ_CAP><<<(unsigned)idx->sm_count * std::min(resident_blocks(k_verify<EX_SEQ_CAP>, VF_WARPS * 32, 0), 8u), VF_WARPS * 32, 0, st>>>(vp);
         GF_CUDA_TRY(cudaGetLastError());
         idx->launches += 2;
     }
