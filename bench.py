@@ -749,10 +749,11 @@ def main():
 
     # -------------------------------------------------------------------------------------------- config 3: 100 M pairs, strong
     if "config3" in legs:
+        from genefuserust_b200.sharding import shard_range
         total = a.total_pairs
-        P3 = total // world
-        first = rank * P3
-        log(f"config3: {total} pairs over {world} rank(s), {P3} each")
+        first, hi3 = shard_range(total, rank, world)      # contiguous shards, sizes differ by at most one pair
+        P3 = hi3 - first
+        log(f"config3: {total} pairs over {world} rank(s), rank {rank}: [{first}, {hi3})")
         do_oracle = oracle if world == 1 else None
         wl = DeviceWorkload(torch, synth, panel, P3, 150, 12, first, dev, threads, do_oracle, cpu_threads())
         out_cap = max(1 << 16, P3 // 4)
@@ -764,9 +765,9 @@ def main():
         n = int(d_ns[0].item())
         n_all = all_sum(n)
         ms_step = ms_max / a.steps
-        rec = {"workload": f"synthetic 2x150bp, {total} pairs in all, split over {world} B200 ({P3} pairs per rank, index "
+        rec = {"workload": f"synthetic 2x150bp, {total} pairs in all, split over {world} B200 (~{total // world} pairs per rank, index "
                            "replicated, no exchange step) (BASELINE.json configs[2])",
-               "pairs_total": P3 * world, "n_gpus": world, "scaling": "strong", "value": P3 * world / (ms_step / 1e3), "unit": UNIT,
+               "pairs_total": total, "n_gpus": world, "scaling": "strong", "value": total / (ms_step / 1e3), "unit": UNIT,
                "ms_per_step": ms_step, "steps": a.steps, "matches": n_all, "clocks": clocks,
                "roofline": roofline_block(stats[0], parts, ms_step, P3, 150, n, peak, peak_src),
                "device_bytes_inputs_per_rank": 4 * P3 * 150}

@@ -56,6 +56,23 @@ for it in range(iters):
         o2 = orc.OracleIndex(sub)
         assert [r.astuple() for r in lst[0]] == want and [r.astuple() for r in lst[1]] == o2.scan(b, threads=os.cpu_count() or 8), ("list", it)
         m2.close(); o2.close()
+    if it % 4 == 1:
+        # device-side record filter + bucket order against the oracle twin of add_match / sort_matches (names with ties)
+        from genefuserust_b200._abi import gf_match
+        recs = []
+        for t in want:
+            r = gf_match()
+            for f, v in zip(gf_match.FIELDS, t):
+                setattr(r, f, v)
+            recs.append(r)
+        name = lambda r: b"@r%d/%d" % (r.pair_idx // 5, 0 if r.source == 0 else r.source)
+        order = orc.bucket_sort(recs, m.n_genes, [name(r) for r in recs], True)
+        m.set_output_mode(3)
+        got3 = m.finish_order(m.scan_pair_end(b), name)
+        m.set_output_mode(0)
+        assert [r.astuple() for r in got3] == [want[i] for i, _ in order], ("bucket order", it)
     n_pairs += n; n_matches += len(want)
+    print(f"  it {it:3d}: scale {scale} genes {len(genes):3d} L {L:3d} pairs {n:6d} p_fusion {kw['p_fusion']} sub {kw['sub_rate']} n {kw['n_rate']}"
+          f"{' ragged+IUPAC' if it % 3 == 2 else ''}{' +list' if it % 5 == 0 else ''}{' +order' if it % 4 == 1 else ''}: {len(want)} records identical (PE), SE identical", flush=True)
     m.close(); o.close()
 print(f"fuzz ok: {iters} configurations, {n_pairs} pairs, {n_matches} matches, {time.time() - t0:.1f} s")
