@@ -12,7 +12,7 @@ for cfg in "1 0" "2 0" "4 0" "8 0" "1 0.3"; do
       --clock-control none -k regex:'^k_(prep|seed|diag|scan)$' -s 12 -c 4 --csv --log-file $out/$tag.ncu.csv $CMD > /dev/null 2>&1
 done
 python - <<'PY'
-import csv, json, glob, os
+import csv, json, glob, os, re
 for f in sorted(glob.glob("gpurun_out/r02_panel/*.json")):
     d = json.load(open(f)); tag = os.path.basename(f)[:-5]
     line = {"panel_scale": d["config"]["panel_scale"], "repeat_frac": d["config"]["repeat_frac"], "keys": d["index"]["keys"],
@@ -23,7 +23,7 @@ for f in sorted(glob.glob("gpurun_out/r02_panel/*.json")):
         rows = [r for r in csv.reader(open(f[:-5] + ".ncu.csv", errors="replace")) if len(r) > 14 and r[0].isdigit()]
         k = {}
         for r in rows:
-            name = r[4].split("<")[0].split("::")[-1]
+            name = re.search(r"(k_\w+)", r[4]).group(1)
             k.setdefault(name, {})[r[12]] = r[14] + " " + r[13]
         line["ncu"] = k
     except Exception as e:
