@@ -3,15 +3,19 @@
  * src/core/matcher.rs) as ONE streaming scan of the reference on the GPU.  include/genefuse_gpu.h says what the (degenerate)
  * reference code computes; here is how it maps to kernels.
  *
- *   k_ref_scan     thread per aligned 32-byte sector of reference text: 32 ASCII bases -> three plane words (code lo / hi,
- *                  valid; case-insensitive = to_ascii_uppercase, matcher.rs:143-148) with the SWAR converters of gf_swar.cuh,
- *                  neighbour words exchanged through shared memory, then the keep rule of index_contig_bytes (:227-289) for
- *                  all 32 positions at once in the bit domain:
+ *   k_ref_scan     HBM streaming, 1 byte per base read, nothing written.  Thread per aligned 32-byte sector of reference text;
+ *                  a warp covers 31 consecutive sectors + the sector before them (lane 0, context only), so neighbouring
+ *                  plane words travel by shuffle: no shared memory, no barrier, one launch per resident reference (a warp
+ *                  finds its segment from a small prefix table).  32 ASCII bases -> two plane words (valid = ACGT in either
+ *                  case = to_ascii_uppercase, matcher.rs:143-148; isA) with ONE branch-free SWAR routine in the nibble domain
+ *                  (sector_va), then the keep rule of index_contig_bytes (:227-289) for all 32 positions at once:
  *                      position i is kept  <=>  base i is ACGT, i < len - 16, and walking back from i-1 over at most 15
  *                      positions the first base that is not 'A' is a non-ACGT byte (or lies before the contig start), or
  *                      all 15 are 'A'                      (<=> the rolling 32-bit value of the run is < 4)
- *                  and its key is the base's own 2-bit code.  Per block: four counters, one atomicAdd each.
- *                  HBM streaming: 1 byte per base read, nothing written.
+ *                  and its key is the base's own 2-bit code.  Almost every sector takes the short way out: all 47 bytes in
+ *                  reach are valid and no aligned byte of the isA plane is 0xFF (a run of 15 'A's always covers one), or no
+ *                  byte is valid at all — then nothing is kept.  Otherwise the rule is evaluated as a carry look-ahead over a
+ *                  15-base window and the few kept bases are fetched again for their code.
  *   k_ref_scan<EMIT> second pass, only when some key ended with 1..50 positions (never on a real genome): the same scan,
  *                  appending (contig, position) of those keys to a small list (map_to_index votes with them, :426-433).
  *   k_seq_present  warp per surviving read: which base codes occur at a k-mer start of the read (upper case only,
@@ -28,7 +32,8 @@
 
 namespace {
 
-constexpr int RS_THREADS = 128;            /* sectors (32 bases) per tile */
+constexpr int RS_THREADS = 256;
+constexpr int RS_WT_SECTORS = 31;          /* counted sectors per warp tile (lane 0 holds the sector before them) */
 constexpr uint64_t RS_CHUNK = 64ull << 20; /* staging buffer bytes (x2, double buffered) */
 constexpr int RS_LIST_CAP = 64;            /* positions kept per key (votes need at most 50) */
 
@@ -39,11 +44,8 @@ struct RefSeg {      /* a run of bases of one contig, resident at device address
     uint64_t contig_len;
     uint32_t lead;       /* readable context bytes before p (>= 16 unless pos0 == 0) */
     uint32_t contig;
-};
-struct RefTile {
-    uint64_t sector;     /* address of the tile's first 32-byte sector */
-    uint32_t seg;
-    uint32_t pad;
+    uint64_t wt0;        /* index of the segment's first warp tile in the launch (segments are in ascending wt0 order) */
+    uint64_t n_wt;       /* warp tiles: ceil(sectors / 31) */
 };
 struct RefScanOut {
     unsigned long long count[4];
@@ -52,6 +54,15 @@ struct RefScanOut {
     unsigned int list_pos[4][RS_LIST_CAP];
 };
 
+/* four bytes of a sector that straddles an end of the segment's readable bytes (first / last sector of a segment only):
+ * byte by byte, bytes outside read as 0 = invalid; kept out of line */
+__device__ __noinline__ uint32_t load_word_slow(const uint8_t* q, const uint8_t* lo, const uint8_t* hi) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+        if (q + t >= lo && q + t < hi) w |= (uint32_t)__ldg(q + t) << (8 * t);
+    return w;
+}
 __device__ __forceinline__ void load_sector(const uint8_t* sec, const uint8_t* lo, const uint8_t* hi, uint4* a, uint4* b) {
     if (sec >= lo && sec + 32 <= hi) {
         asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -59,102 +70,162 @@ __device__ __forceinline__ void load_sector(const uint8_t* sec, const uint8_t* l
                      : "l"(sec));
         return;
     }
-    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (sec + 32 > lo && sec < hi)
-        for (int t = 0; t < 32; t++)
-            if (sec + t >= lo && sec + t < hi) w[t >> 2] |= (uint32_t)__ldg(sec + t) << (8 * (t & 3));
-    *a = make_uint4(w[0], w[1], w[2], w[3]);
-    *b = make_uint4(w[4], w[5], w[6], w[7]);
+    *a = make_uint4(load_word_slow(sec, lo, hi), load_word_slow(sec + 4, lo, hi), load_word_slow(sec + 8, lo, hi), load_word_slow(sec + 12, lo, hi));
+    *b = make_uint4(load_word_slow(sec + 16, lo, hi), load_word_slow(sec + 20, lo, hi), load_word_slow(sec + 24, lo, hi), load_word_slow(sec + 28, lo, hi));
 }
-/* 32 bases -> plane words (bit t = byte t of the sector); bytes outside the segment were read as 0 = invalid */
-__device__ __forceinline__ void sector_planes(const uint4& a, const uint4& b, uint32_t* lo, uint32_t* hi, uint32_t* v) {
-    uint32_t l0, h0, v0, e0, l1, h1, v1, e1;
-    swar::block16<true>(a, &l0, &h0, &v0, &e0);
-    swar::block16<true>(b, &l1, &h1, &v1, &e1);
-    *lo = __byte_perm(l0, l1, 0x5410u);
-    *hi = __byte_perm(h0, h1, 0x5410u);
-    *v = __byte_perm(v0, v1, 0x5410u);
+__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m) { /* (a & m) | (b & ~m) as ONE logic operation */
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+    return d;
+}
+/* 8 bases (two words) -> bit 3 of every nibble of *v / *pa: valid (ACGT, either case) / 'A' or 'a'.  z holds the low nibbles
+ * (nibble 2 i = byte i of w0, nibble 2 i + 1 = byte i of w1), y the high nibbles in the same order; with L / H the nibbles of a
+ * byte:  valid <=> H = 01x?, L3 = 0, H0 = L2 & ~L1 (only 'T' = 0x54 has the 0x10 bit), L0 = ~H0
+ * (A 0x41, C 0x43, G 0x47 -> L = 0001, 0011, 0111 with H0 = 0; T -> L = 0100 with H0 = 1); 'A' <=> valid, L2 = L1 = 0.
+ * The bits are lined up at the TOP of the nibble because that takes left shifts only, which are multiplies on the FMA pipe: the
+ * kernel is bound by the ALU pipe (logic / shift / compare, one warp instruction per 2 cycles and scheduler), not by issue.
+ * tests/test_swar_bits.py models this routine on the CPU for every byte value with the constants read from THIS file. */
+__device__ __forceinline__ void group_va(uint32_t w0, uint32_t w1, uint32_t* v, uint32_t* pa) {
+    const uint32_t z = bitsel(w0, w1 << 4, 0x0F0F0F0Fu);
+    const uint32_t y = bitsel(w0 >> 4, w1, 0x0F0F0F0Fu);
+    const uint32_t l2 = z << 1, l1 = z << 2, l0 = z << 3, h2 = y << 1, h0 = y << 3; /* L2, L1, L0, H2, H0 at bit 3 */
+    const uint32_t t1 = ~y & h2 & ~z;
+    const uint32_t t2 = ~(h0 ^ (l2 & ~l1));
+    const uint32_t t3 = t1 & t2 & 0x88888888u;
+    const uint32_t vv = t3 & (l0 ^ h0);
+    *v = vv;
+    *pa = vv & ~l2 & ~l1;
+}
+constexpr uint32_t VA_ALL = 0x88888888u; /* a group_va word with all 8 bases set */
+/* 32 bases -> plane words (bit t = byte t of the sector); bytes outside the segment were read as 0 = invalid.  A nibble's
+ * bit 3 is moved to its base's place in the top byte by one multiply (the same partial-product trick as swar::block16). */
+__device__ __forceinline__ void sector_va(const uint4& a, const uint4& b, uint32_t* v, uint32_t* pa) {
+    uint32_t v0, v1, v2, v3, a0, a1, a2, a3;
+    group_va(a.x, a.y, &v0, &a0);
+    group_va(a.z, a.w, &v1, &a1);
+    group_va(b.x, b.y, &v2, &a2);
+    group_va(b.z, b.w, &v3, &a3);
+    constexpr uint32_t M = 0x00204081u;
+    *v = __byte_perm(__byte_perm(v0 * M, v1 * M, 0x0073u), __byte_perm(v2 * M, v3 * M, 0x0073u), 0x5410u);
+    *pa = __byte_perm(__byte_perm(a0 * M, a1 * M, 0x0073u), __byte_perm(a2 * M, a3 * M, 0x0073u), 0x5410u);
+}
+
+/* the keep rule of one sector in full, from memory (rare: a sector with an invalid byte in reach or with 8 aligned 'A's in
+ * reach); returns the number of kept positions per key, one byte each (A, T, C, G) */
+template <bool EMIT>
+__device__ __noinline__ uint32_t keep_rule(const uint8_t* sec, const RefSeg* __restrict__ sgp, RefScanOut* __restrict__ out, uint32_t emit_mask) {
+    const RefSeg sg = *sgp;
+    const uint8_t *lo_b = sg.p - sg.lead, *hi_b = sg.p + sg.n;
+    uint4 a, b;
+    uint32_t v, pa, v_prev, pa_prev;
+    load_sector(sec, lo_b, hi_b, &a, &b);
+    sector_va(a, b, &v, &pa);
+    load_sector(sec - 32, lo_b, hi_b, &a, &b);
+    sector_va(a, b, &v_prev, &pa_prev);
+    uint32_t cnt = 0;
+    const unsigned long long v64 = ((unsigned long long)v << 32) | v_prev;
+    /* blocked[i] <=> some valid non-'A' base (a generate G) lies d <= 15 positions behind i with nothing but 'A's (propagate
+     * P) in between: a carry look-ahead over a window of 15, in 3 doubling steps + 3 combines (bit b of X << d = position
+     * i - d).  Non-ACGT bytes neither generate nor propagate, so a run start is never blocked; 15 'A's are a window without
+     * a generate.  kept = valid & ~blocked. */
+    const unsigned long long P1 = ((unsigned long long)pa << 32) | pa_prev, G1 = v64 & ~P1;
+    const unsigned long long G2 = G1 | (P1 & (G1 << 1)), P2 = P1 & (P1 << 1);       /* window of 2 positions ending at j */
+    const unsigned long long G4 = G2 | (P2 & (G2 << 2)), P4 = P2 & (P2 << 2);       /* 4 */
+    const unsigned long long G8 = G4 | (P4 & (G4 << 4)), P8 = P4 & (P4 << 4);       /* 8 */
+    /* window of 15 = 8 + 4 + 2 + 1 positions ending at j */
+    unsigned long long G15 = G8 | (P8 & (G4 << 8));
+    const unsigned long long P12 = P8 & (P4 << 8);
+    G15 |= P12 & (G2 << 12);
+    const unsigned long long P14 = P12 & (P2 << 12);
+    G15 |= P14 & (G1 << 14);
+    const unsigned long long ok = ~(G15 << 1); /* blocked[i] = window ending at i - 1 holds a connected generate */
+    /* counted positions of this sector: inside [p, p + n) and i < contig_len - 16 (`0..len-16`, :237-243) */
+    const long long first = (long long)(sec - sg.p); /* index of byte 0 of the sector relative to p */
+    long long lim = (long long)sg.n;
+    if (sg.contig_len >= 16) lim = min(lim, (long long)(sg.contig_len - 16) - (long long)sg.pos0);
+    else lim = 0;
+    uint32_t cm = 0;
+    {
+        const long long b0 = max(0ll, -first), b1 = min(32ll, lim - first); /* bits [b0, b1) */
+        if (b1 > b0) cm = (b1 >= 32 ? 0xFFFFFFFFu : ((1u << (int)b1) - 1u)) & ~((1u << (int)b0) - 1u);
+    }
+    uint32_t kept = (uint32_t)((v64 & ok) >> 32) & cm;
+    while (kept) { /* a run start or a base behind 15 'A's; its key is its own code (A 0, T 1, C 2, G 3) */
+        const int bit = __ffs(kept) - 1;
+        kept &= kept - 1;
+        const uint32_t ch = __ldg(sec + bit);
+        const uint32_t k = ((ch >> 2) & 1u) | (ch & 2u);
+        cnt += 1u << (8 * k);
+        if (EMIT && ((emit_mask >> k) & 1u)) {
+            const unsigned slot = atomicAdd(&out->n_listed[k], 1u);
+            if (slot < (unsigned)RS_LIST_CAP) {
+                out->list_contig[k][slot] = sg.contig;
+                out->list_pos[k][slot] = (unsigned int)(sg.pos0 + (uint64_t)(first + bit));
+            }
+        }
+    }
+    return cnt;
 }
 
 template <bool EMIT>
-__global__ void __launch_bounds__(RS_THREADS) k_ref_scan(const RefSeg* __restrict__ segs, const RefTile* __restrict__ tiles,
-                                                         uint32_t n_tiles, RefScanOut* __restrict__ out, uint32_t emit_mask) {
-    __shared__ uint32_t s_lo[RS_THREADS + 1], s_hi[RS_THREADS + 1], s_v[RS_THREADS + 1];
+__global__ void __launch_bounds__(RS_THREADS, 5) k_ref_scan(const RefSeg* __restrict__ segs, uint32_t n_segs, uint64_t total_wt,
+                                                            RefScanOut* __restrict__ out, uint32_t emit_mask) {
     __shared__ unsigned int s_cnt[4];
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t stride = (uint64_t)(32 * RS_WT_SECTORS) * n_warps;
     unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    for (uint32_t ti = blockIdx.x; ti < n_tiles; ti += gridDim.x) {
-        const RefTile tile = tiles[ti];
-        const RefSeg sg = segs[tile.seg];
-        const uint8_t* lo_b = sg.p - sg.lead;
-        const uint8_t* hi_b = sg.p + sg.n;
-        const uint8_t* sec = reinterpret_cast<const uint8_t*>(tile.sector) + 32ull * threadIdx.x;
+    /* the current segment: first / one-past-last readable byte and its tile range [wt_lo, wt_end); lane l's sector of warp tile
+     * g is `sec`, advanced by `stride` per step and recomputed when the warp enters another segment (tiles are visited in
+     * ascending order: only ever forward).  Every sector of a tile strictly inside (wt_lo, wt_end - 1) is readable as a whole. */
+    uint32_t si = 0;
+    const uint8_t *lo_b = nullptr, *hi_b = nullptr, *sec = nullptr;
+    uint64_t wt_lo = 0, wt_end = 0;
+    uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    auto enter = [&]() {
+        RefSeg sg = segs[si];
+        while (g >= sg.wt0 + sg.n_wt && si + 1 < n_segs) sg = segs[++si]; /* warp-uniform */
+        lo_b = sg.p - sg.lead;
+        hi_b = sg.p + sg.n;
+        wt_lo = sg.wt0;
+        wt_end = sg.wt0 + sg.n_wt;
+        sec = reinterpret_cast<const uint8_t*>((uintptr_t)sg.p & ~(uintptr_t)31) + 32ll * ((long long)lane - 1) +
+              (long long)(32 * RS_WT_SECTORS) * (long long)(g - sg.wt0);
+    };
+    if (g < total_wt) enter();
+#pragma unroll 1
+    for (; g < total_wt; g += n_warps, sec += stride) {
+        if (g >= wt_end) enter();
         uint4 a, b;
-        uint32_t lo, hi, v;
-        load_sector(sec, lo_b, hi_b, &a, &b);
-        sector_planes(a, b, &lo, &hi, &v);
-        __syncthreads(); /* the previous tile's readers are done */
-        s_lo[threadIdx.x + 1] = lo; s_hi[threadIdx.x + 1] = hi; s_v[threadIdx.x + 1] = v;
-        if (threadIdx.x == 0) { /* the sector before the tile: context for its first 15 positions */
-            uint4 pa, pb;
-            uint32_t plo, phi, pv;
-            load_sector(sec - 32, lo_b, hi_b, &pa, &pb);
-            sector_planes(pa, pb, &plo, &phi, &pv);
-            s_lo[0] = plo; s_hi[0] = phi; s_v[0] = pv;
+        if (g > wt_lo && g + 1 < wt_end) {
+            asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                         : "l"(sec));
+        } else {
+            load_sector(sec, lo_b, hi_b, &a, &b);
         }
-        __syncthreads();
-        const unsigned long long v64 = ((unsigned long long)v << 32) | s_v[threadIdx.x];
-        const unsigned long long lo64 = ((unsigned long long)lo << 32) | s_lo[threadIdx.x];
-        const unsigned long long hi64 = ((unsigned long long)hi << 32) | s_hi[threadIdx.x];
-        /* blocked[i] <=> some valid non-'A' base (a generate G) lies d <= 15 positions behind i with nothing but 'A's (propagate
-         * P) in between: a carry look-ahead over a window of 15, in 3 doubling steps + 3 combines (bit b of X << d = position
-         * i - d).  Non-ACGT bytes neither generate nor propagate, so a run start is never blocked; 15 'A's are a window without
-         * a generate.  kept = valid & ~blocked. */
-        const unsigned long long P1 = v64 & ~lo64 & ~hi64, G1 = v64 & ~P1;
-        const unsigned long long G2 = G1 | (P1 & (G1 << 1)), P2 = P1 & (P1 << 1);       /* window of 2 positions ending at j */
-        const unsigned long long G4 = G2 | (P2 & (G2 << 2)), P4 = P2 & (P2 << 2);       /* 4 */
-        const unsigned long long G8 = G4 | (P4 & (G4 << 4)), P8 = P4 & (P4 << 4);       /* 8 */
-        /* window of 15 = 8 + 4 + 2 + 1 positions ending at j */
-        unsigned long long G15 = G8 | (P8 & (G4 << 8));
-        const unsigned long long P12 = P8 & (P4 << 8);
-        G15 |= P12 & (G2 << 12);
-        const unsigned long long P14 = P12 & (P2 << 12);
-        G15 |= P14 & (G1 << 14);
-        const unsigned long long ok = ~(G15 << 1); /* blocked[i] = window ending at i - 1 holds a connected generate */
-        /* counted positions of this sector: inside [p, p + n) and i < contig_len - 16 (`0..len-16`, :237-243) */
-        const long long first = (long long)(sec - sg.p); /* index of byte 0 of the sector relative to p */
-        long long lim = (long long)sg.n;
-        if (sg.contig_len >= 16) lim = min(lim, (long long)(sg.contig_len - 16) - (long long)sg.pos0);
-        else lim = 0;
-        uint32_t cm = 0;
-        {
-            const long long b0 = max(0ll, -first), b1 = min(32ll, lim - first); /* bits [b0, b1) */
-            if (b1 > b0) cm = (b1 >= 32 ? 0xFFFFFFFFu : ((1u << (int)b1) - 1u)) & ~((1u << (int)b0) - 1u);
-        }
-        const uint32_t kept = (uint32_t)((v64 & ok) >> 32) & cm;
-        const uint32_t kA = kept & ~lo & ~hi, kT = kept & lo & ~hi, kC = kept & ~lo & hi, kG = kept & lo & hi;
-        c0 += __popc(kA); c1 += __popc(kT); c2 += __popc(kC); c3 += __popc(kG);
-        if (EMIT) {
-            const uint32_t km[4] = {kA, kT, kC, kG};
-            for (int k = 0; k < 4; k++) {
-                if (!((emit_mask >> k) & 1u)) continue;
-                uint32_t m = km[k];
-                while (m) {
-                    const int bit = __ffs(m) - 1;
-                    m &= m - 1;
-                    const unsigned slot = atomicAdd(&out->n_listed[k], 1u);
-                    if (slot < (unsigned)RS_LIST_CAP) {
-                        out->list_contig[k][slot] = sg.contig;
-                        out->list_pos[k][slot] = (unsigned int)(sg.pos0 + (uint64_t)(first + bit));
-                    }
-                }
-            }
+        /* Everything the short way out needs is visible in the nibble domain (no gathers): nothing is kept in the context
+         * sector; in a sector without a valid base; and in a sector where all 32 bases and the 16 before them are valid and
+         * none of the aligned groups of 8 from position -8 to 31 is all 'A' (a run of 15 'A's ending at -1 .. 30 covers one
+         * of the groups -8 .. 23): every position then has a valid non-'A' base behind it within 15. */
+        uint32_t v0, v1, v2, v3, a0, a1, a2, a3;
+        group_va(a.x, a.y, &v0, &a0);
+        group_va(a.z, a.w, &v1, &a1);
+        group_va(b.x, b.y, &v2, &a2);
+        group_va(b.z, b.w, &v3, &a3);
+        const bool tail_plain = (v2 & v3) == VA_ALL && a3 != VA_ALL;                       /* what the next sector needs of this one */
+        const bool prev_plain = __shfl_up_sync(0xFFFFFFFFu, (int)tail_plain, 1) != 0;
+        const bool plain = prev_plain && (v0 & v1 & v2 & v3) == VA_ALL && a0 != VA_ALL && a1 != VA_ALL && a2 != VA_ALL && a3 != VA_ALL;
+        if (lane != 0 && (v0 | v1 | v2 | v3) != 0u && !plain) {
+            const uint32_t kc = keep_rule<EMIT>(sec, segs + si, out, emit_mask);
+            c0 += kc & 0xFFu; c1 += (kc >> 8) & 0xFFu; c2 += (kc >> 16) & 0xFFu; c3 += kc >> 24;
         }
     }
     c0 = __reduce_add_sync(0xFFFFFFFFu, c0); c1 = __reduce_add_sync(0xFFFFFFFFu, c1);
     c2 = __reduce_add_sync(0xFFFFFFFFu, c2); c3 = __reduce_add_sync(0xFFFFFFFFu, c3);
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         if (c0) atomicAdd(&s_cnt[0], c0);
         if (c1) atomicAdd(&s_cnt[1], c1);
         if (c2) atomicAdd(&s_cnt[2], c2);
@@ -226,37 +297,39 @@ struct gf_reference {
 
 namespace {
 
-/* one launch over a set of tiles; the tables are uploaded on `st` from pinned staging owned by the caller */
+/* one launch over a set of segments; the table is uploaded on `st` from pinned staging owned by the caller */
 template <bool EMIT>
-void launch_scan(const RefSeg* d_segs, const RefTile* d_tiles, uint32_t n_tiles, RefScanOut* d_out, uint32_t emit_mask, int sms,
+void launch_scan(const RefSeg* d_segs, uint32_t n_segs, uint64_t total_wt, RefScanOut* d_out, uint32_t emit_mask, int sms,
                  cudaStream_t st) {
-    if (!n_tiles) return;
-    const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)sms * 16);
-    k_ref_scan<EMIT><<<grid, RS_THREADS, 0, st>>>(d_segs, d_tiles, n_tiles, d_out, emit_mask);
+    if (!total_wt) return;
+    const uint64_t blocks_needed = (total_wt + RS_THREADS / 32 - 1) / (RS_THREADS / 32);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ref_scan<EMIT>, RS_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    const unsigned grid = (unsigned)std::min<uint64_t>(blocks_needed, (uint64_t)sms * per_sm);
+    k_ref_scan<EMIT><<<grid, RS_THREADS, 0, st>>>(d_segs, n_segs, total_wt, d_out, emit_mask);
 }
 
-void add_tiles(std::vector<RefTile>& tiles, uint32_t seg_id, const uint8_t* p, uint64_t n, uint32_t lead) {
-    (void)lead;
-    if (!n) return;
+/* warp tiles of a segment: its 32-byte sectors in groups of 31 */
+uint64_t seg_warp_tiles(const uint8_t* p, uint64_t n) {
+    if (!n) return 0;
     const uintptr_t first = (uintptr_t)p & ~(uintptr_t)31, last = ((uintptr_t)p + n + 31) & ~(uintptr_t)31;
-    for (uintptr_t s = first; s < last; s += 32ull * RS_THREADS) tiles.push_back(RefTile{(uint64_t)s, seg_id, 0});
+    const uint64_t sectors = (last - first) / 32;
+    return (sectors + RS_WT_SECTORS - 1) / RS_WT_SECTORS;
 }
 
 /* the whole pass: emit_mask == 0 counts, otherwise lists the positions of the keys in the mask */
 int scan_reference(gf_reference* ref, const gf_ref_contig* contigs, uint32_t n_contigs, uint32_t emit_mask, RefScanOut* h_out,
                    float* ms_scan, uint64_t* h2d_bytes, uint64_t* launches) {
     cudaStream_t st = ref->stream;
-    DevBuf d_out, d_stage[2], d_segs[2], d_tiles[2];
-    PinnedBuf h_segs[2], h_tiles[2], h_res;
+    DevBuf d_out, d_stage[2], d_segs[2];
+    PinnedBuf h_segs[2], h_res;
     EvGuard ev_free[2], ev_k0, ev_k1;
     GF_CUDA_TRY(cudaMalloc(&d_out.p, sizeof(RefScanOut)));
     GF_CUDA_TRY(cudaMemsetAsync(d_out.p, 0, sizeof(RefScanOut), st));
     GF_CUDA_TRY(cudaMallocHost(&h_res.p, sizeof(RefScanOut)));
     GF_CUDA_TRY(cudaEventCreate(&ev_k0.e));
     GF_CUDA_TRY(cudaEventCreate(&ev_k1.e));
-    /* upper bounds of the per-buffer tables: a tile covers 4096 bytes; segments are >= 1 byte but a buffer holds at most
-     * max_segs of them (the buffer is flushed when the table is full) */
-    const size_t max_segs = 4096, max_tiles = (size_t)(RS_CHUNK / (32 * RS_THREADS)) + 2 * max_segs + 16;
+    const size_t max_segs = 4096; /* a buffer is flushed when its segment table is full */
     bool any_host = false;
     for (uint32_t c = 0; c < n_contigs; c++) {
         if (!contigs[c].len) continue;
@@ -268,16 +341,14 @@ int scan_reference(gf_reference* ref, const gf_ref_contig* contigs, uint32_t n_c
     for (int k = 0; k < 2; k++) {
         if (any_host) GF_CUDA_TRY(cudaMalloc(&d_stage[k].p, RS_CHUNK + 256));
         GF_CUDA_TRY(cudaMalloc(&d_segs[k].p, sizeof(RefSeg) * max_segs));
-        GF_CUDA_TRY(cudaMalloc(&d_tiles[k].p, sizeof(RefTile) * max_tiles));
         GF_CUDA_TRY(cudaMallocHost(&h_segs[k].p, sizeof(RefSeg) * max_segs));
-        GF_CUDA_TRY(cudaMallocHost(&h_tiles[k].p, sizeof(RefTile) * max_tiles));
         GF_CUDA_TRY(cudaEventCreate(&ev_free[k].e));
     }
     float ms_k = 0;
     int cur = 0;
     bool used[2] = {false, false};
     std::vector<RefSeg> segs;
-    std::vector<RefTile> tiles;
+    uint64_t total_wt = 0;
     uint64_t fill = 0; /* bytes used in the current staging buffer */
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed; /* kernel start/end events, read at the end */
     std::vector<EvGuard> ev_pool;
@@ -286,26 +357,23 @@ int scan_reference(gf_reference* ref, const gf_ref_contig* contigs, uint32_t n_c
     auto flush = [&]() -> int {
         if (segs.empty()) return GF_OK;
         memcpy(h_segs[cur].p, segs.data(), sizeof(RefSeg) * segs.size());
-        memcpy(h_tiles[cur].p, tiles.data(), sizeof(RefTile) * tiles.size());
         GF_CUDA_TRY(cudaMemcpyAsync(d_segs[cur].p, h_segs[cur].p, sizeof(RefSeg) * segs.size(), cudaMemcpyHostToDevice, st));
-        GF_CUDA_TRY(cudaMemcpyAsync(d_tiles[cur].p, h_tiles[cur].p, sizeof(RefTile) * tiles.size(), cudaMemcpyHostToDevice, st));
         cudaEvent_t a = nullptr, b = nullptr;
         if (ev_pool.size() + 2 <= ev_pool.capacity()) {
             ev_pool.emplace_back(); GF_CUDA_TRY(cudaEventCreate(&ev_pool.back().e)); a = ev_pool.back().e;
             ev_pool.emplace_back(); GF_CUDA_TRY(cudaEventCreate(&ev_pool.back().e)); b = ev_pool.back().e;
             GF_CUDA_TRY(cudaEventRecord(a, st));
         }
-        if (emit_mask) launch_scan<true>((const RefSeg*)d_segs[cur].p, (const RefTile*)d_tiles[cur].p, (uint32_t)tiles.size(),
-                                         (RefScanOut*)d_out.p, emit_mask, ref->sm_count, st);
-        else launch_scan<false>((const RefSeg*)d_segs[cur].p, (const RefTile*)d_tiles[cur].p, (uint32_t)tiles.size(),
-                                (RefScanOut*)d_out.p, 0u, ref->sm_count, st);
+        if (emit_mask) launch_scan<true>((const RefSeg*)d_segs[cur].p, (uint32_t)segs.size(), total_wt, (RefScanOut*)d_out.p, emit_mask,
+                                         ref->sm_count, st);
+        else launch_scan<false>((const RefSeg*)d_segs[cur].p, (uint32_t)segs.size(), total_wt, (RefScanOut*)d_out.p, 0u, ref->sm_count, st);
         GF_CUDA_TRY(cudaGetLastError());
         if (b) { GF_CUDA_TRY(cudaEventRecord(b, st)); timed.emplace_back(a, b); }
         (*launches)++;
         GF_CUDA_TRY(cudaEventRecord(ev_free[cur].e, st));
         used[cur] = true;
         segs.clear();
-        tiles.clear();
+        total_wt = 0;
         fill = 0;
         cur ^= 1;
         /* the buffer we switch to (staging + pinned tables) may still be in use by the launch before last */
@@ -320,16 +388,10 @@ int scan_reference(gf_reference* ref, const gf_ref_contig* contigs, uint32_t n_c
         const bool dev = cudaPointerGetAttributes(&at, contigs[c].seq) == cudaSuccess && at.type == cudaMemoryTypeDevice;
         cudaGetLastError();
         if (dev) { /* resident: scanned in place, one segment */
-            if (segs.size() + 1 > max_segs || tiles.size() + len / (32 * RS_THREADS) + 2 > max_tiles) { int r = flush(); if (r) return r; }
-            uint64_t done = 0;
-            while (done < len) { /* cut only so that the tile table fits */
-                const uint64_t room = (max_tiles - tiles.size() - 2) * 32ull * RS_THREADS;
-                const uint64_t n = std::min<uint64_t>(len - done, room);
-                segs.push_back(RefSeg{contigs[c].seq + done, n, done, len, (uint32_t)std::min<uint64_t>(done, 16), c});
-                add_tiles(tiles, (uint32_t)segs.size() - 1, contigs[c].seq + done, n, 0);
-                done += n;
-                if (done < len) { int r = flush(); if (r) return r; }
-            }
+            if (segs.size() + 1 > max_segs) { int r = flush(); if (r) return r; }
+            const uint64_t nwt = seg_warp_tiles(contigs[c].seq, len);
+            segs.push_back(RefSeg{contigs[c].seq, len, 0, len, 0, c, total_wt, nwt});
+            total_wt += nwt;
             continue;
         }
         uint64_t done = 0;
@@ -337,7 +399,7 @@ int scan_reference(gf_reference* ref, const gf_ref_contig* contigs, uint32_t n_c
             const uint32_t lead = (uint32_t)std::min<uint64_t>(done, 16);
             /* staged layout: [.. fill) used; this piece goes to a 32-byte aligned start + 32 so that `lead` bytes fit before */
             uint64_t start = ((fill + 31) & ~31ull) + 32;
-            if (start + 64 > RS_CHUNK || segs.size() + 1 > max_segs || tiles.size() + 4 > max_tiles) {
+            if (start + 64 > RS_CHUNK || segs.size() + 1 > max_segs) {
                 int r = flush();
                 if (r) return r;
                 start = 32;
@@ -346,8 +408,9 @@ int scan_reference(gf_reference* ref, const gf_ref_contig* contigs, uint32_t n_c
             uint8_t* dst = (uint8_t*)d_stage[cur].p + start;
             GF_CUDA_TRY(cudaMemcpyAsync(dst - lead, contigs[c].seq + done - lead, n + lead, cudaMemcpyHostToDevice, st));
             *h2d_bytes += n + lead;
-            segs.push_back(RefSeg{dst, n, done, len, lead, c});
-            add_tiles(tiles, (uint32_t)segs.size() - 1, dst, n, lead);
+            const uint64_t nwt = seg_warp_tiles(dst, n);
+            segs.push_back(RefSeg{dst, n, done, len, lead, c, total_wt, nwt});
+            total_wt += nwt;
             fill = start + n;
             done += n;
         }

@@ -212,43 +212,71 @@ __device__ __forceinline__ bool overlap_passes(const Col& c, int len1, int len2,
     return true;
 }
 /* smallest passing overlap length (read.rs:323-367) or -1.
- * Cheap reject per overlap length o: the low code-bit plane of R1 at offset len1 - o against the first 32 bases of rc(R2)
- * must differ in <= 2 positions.  The R1 window slides by one bit per o, so the plane words are loaded once per 32 overlap
- * lengths and every o costs funnel shift + xor + popc + 2 (candidate bit shifted into a mask, no branch). */
+ * Cheap reject per overlap length o >= 32: the low code-bit plane of R1 at offset len1 - o against the first 32 bases of rc(R2)
+ * must differ in <= 2 positions (o = 30, 31: all 30 / 31 positions).  The R1 window slides by one bit per o, so the plane words
+ * are loaded once per 32 overlap lengths and every o costs funnel shift + xor + popc + 2 (candidate bit shifted into a mask, no
+ * branch).
+ * The scan runs over ALL overlap lengths first and only notes the candidates (the first two, in increasing o); the full test
+ * (overlap_passes: plane windows, quality bytes from global / pinned host memory) comes afterwards, so that the lanes of a warp
+ * that have a candidate — every pair that merges has one, at its own o — run it side by side instead of one after the other
+ * whenever their candidate happens to show up in the scan.  A third candidate (low-complexity reads) is left to
+ * find_overlap_from, the one-by-one form of the same search. */
+template <int W>
+__device__ __noinline__ int find_overlap_from(const Col& c, int len1, int len2, int o_min, const uint8_t* q1, const uint8_t* q2, int* diff_out,
+                                              uint32_t* r1_bits) {
+    const int minlen = min(len1, len2);
+    const uint32_t c0 = c(Lay<W>::C2LO, 0);
+    for (int o = max(32, o_min); o <= minlen; o++) {
+        const uint32_t x = c.fs(Lay<W>::R1LO, (uint32_t)(len1 - o)) ^ c0;
+        if (__popc(x) <= 2 && overlap_passes<W>(c, len1, len2, o, q1, q2, diff_out, r1_bits)) return o;
+    }
+    *diff_out = 0;
+    return -1;
+}
 template <int W>
 __device__ __forceinline__ int find_overlap(const Col& c, int len1, int len2, const uint8_t* q1, const uint8_t* q2, int* diff_out,
                                             uint32_t* r1_bits) {
     const int minlen = min(len1, len2);
     *diff_out = 0;
     *r1_bits = 0;
-    /* o = 30, 31: fewer than 32 positions */
-    for (int o = 30; o <= min(31, minlen); o++)
-        if (overlap_passes<W>(c, len1, len2, o, q1, q2, diff_out, r1_bits)) return o;
-    if (minlen < 32) return -1;
+    int o1 = 0, o2 = 0; /* the first two candidates */
+    bool more = false;
     const uint32_t c0 = c(Lay<W>::C2LO, 0);
-    const int w_hi = (len1 - 32) >> 5, w_lo = (len1 - minlen) >> 5;
-    uint32_t b = c(Lay<W>::R1LO, w_hi + 1);
+    /* o = 30, 31: fewer than 32 positions */
+    for (int o = 30; o <= min(31, minlen); o++) {
+        const uint32_t x = (c.fs(Lay<W>::R1LO, (uint32_t)(len1 - o)) ^ c0) & lowmask(o);
+        if (__popc(x) <= 2) { if (!o1) o1 = o; else o2 = o; }
+    }
+    if (minlen >= 32) {
+        const int w_hi = (len1 - 32) >> 5, w_lo = (len1 - minlen) >> 5;
+        uint32_t b = c(Lay<W>::R1LO, w_hi + 1);
 #pragma unroll 1
-    for (int w = w_hi; w >= w_lo; w--) {
-        const uint32_t a = c(Lay<W>::R1LO, w);
-        uint32_t cand = 0; /* bit 31 - j <-> offset 32 w + 31 - j, i.e. o = o_base + j */
+        for (int w = w_hi; w >= w_lo; w--) {
+            const uint32_t a = c(Lay<W>::R1LO, w);
+            uint32_t cand = 0; /* bit 31 - j <-> offset 32 w + 31 - j, i.e. o = o_base + j */
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-            const uint32_t x = __funnelshift_r(a, b, 31 - j) ^ c0;
-            cand = __funnelshift_l((uint32_t)(__popc(x) - 3), cand, 1);
-        }
-        b = a;
-        const int o_base = len1 - 32 * w - 31;
-        /* keep 32 <= o <= minlen */
-        const int j_lo = max(0, 32 - o_base), j_hi = min(31, minlen - o_base);
-        if (j_hi < j_lo) continue;
-        cand &= (0xFFFFFFFFu >> j_lo) & (0xFFFFFFFFu << (31 - j_hi));
-        while (cand) { /* rare: candidates in increasing o */
-            const int j = __clz(cand);
-            cand &= ~(0x80000000u >> j);
-            if (overlap_passes<W>(c, len1, len2, o_base + j, q1, q2, diff_out, r1_bits)) return o_base + j;
+            for (int j = 0; j < 32; j++) {
+                const uint32_t x = __funnelshift_r(a, b, 31 - j) ^ c0;
+                cand = __funnelshift_l((uint32_t)(__popc(x) - 3), cand, 1);
+            }
+            b = a;
+            const int o_base = len1 - 32 * w - 31;
+            /* keep 32 <= o <= minlen */
+            const int j_lo = max(0, 32 - o_base), j_hi = min(31, minlen - o_base);
+            if (j_hi < j_lo) continue;
+            cand &= (0xFFFFFFFFu >> j_lo) & (0xFFFFFFFFu << (31 - j_hi));
+            while (cand) { /* rare: candidates in increasing o */
+                const int j = __clz(cand);
+                cand &= ~(0x80000000u >> j);
+                if (!o1) o1 = o_base + j;
+                else if (!o2) o2 = o_base + j;
+                else { more = true; cand = 0; }
+            }
         }
     }
+    if (o1 && overlap_passes<W>(c, len1, len2, o1, q1, q2, diff_out, r1_bits)) return o1;
+    if (o2 && overlap_passes<W>(c, len1, len2, o2, q1, q2, diff_out, r1_bits)) return o2;
+    if (more) return find_overlap_from<W>(c, len1, len2, o2 + 1, q1, q2, diff_out, r1_bits);
     *diff_out = 0;
     return -1;
 }

@@ -108,3 +108,71 @@ def test_block16_every_byte_value_in_every_position():
             bs[pos] = b
             for ci in (False, True):
                 assert block16(_words(bytes(bs)), ci) == planes(bytes(bs), ci), (pos, b, ci)
+
+
+# ---- the reference scan's converter (csrc/gf_matcher.cu: group_va / sector_va): valid (ACGT in either case) and isA planes of
+# one 32-byte sector, branch-free in the nibble domain
+MSRC = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "genefuserust_b200", "csrc", "gf_matcher.cu")).read()
+
+
+def _mconst(pattern):
+    m = re.search(pattern, MSRC)
+    assert m, pattern
+    return [int(x, 16) for x in m.groups()]
+
+
+VA_MASK, = _mconst(r"t3 = t1 & t2 & (0x[0-9A-Fa-f]+)u;")
+VA_MUL, = _mconst(r"constexpr uint32_t M = (0x[0-9A-Fa-f]+)u;")
+VA_IN, VA_OUT = _mconst(r"\*v = __byte_perm\(__byte_perm\(v0 \* M, v1 \* M, (0x[0-9A-Fa-f]+)u\), __byte_perm\(v2 \* M, v3 \* M, 0x[0-9A-Fa-f]+u\), (0x[0-9A-Fa-f]+)u\);")
+
+
+def group_va(w0, w1):
+    z = (w0 & 0x0F0F0F0F) | ((w1 << 4) & 0xF0F0F0F0)
+    y = ((w0 >> 4) & 0x0F0F0F0F) | (w1 & 0xF0F0F0F0)
+    l2, l1, l0, h2, h0 = (z << 1) & M32, (z << 2) & M32, (z << 3) & M32, (y << 1) & M32, (y << 3) & M32
+    t1 = ~y & h2 & ~z & M32
+    t2 = ~(h0 ^ (l2 & ~l1)) & M32
+    vv = t1 & t2 & VA_MASK & (l0 ^ h0)
+    return vv, vv & ~l2 & ~l1 & M32
+
+
+def sector_va(bs):
+    w = [int.from_bytes(bs[4 * j:4 * j + 4], "little") for j in range(8)]
+    g = [group_va(w[2 * k], w[2 * k + 1]) for k in range(4)]
+    out = []
+    for sel in (0, 1):
+        m = [(g[k][sel] * VA_MUL) & M32 for k in range(4)]
+        out.append(byte_perm(byte_perm(m[0], m[1], VA_IN), byte_perm(m[2], m[3], VA_IN), VA_OUT))
+    return tuple(out)
+
+
+def va_planes(bs):
+    v = pa = 0
+    for p, b in enumerate(bs):
+        up = chr(b).upper() if b < 128 else "?"
+        if up in "ACGT":
+            v |= 1 << p
+        if up == "A":
+            pa |= 1 << p
+    return v, pa
+
+
+def test_sector_va_every_byte_value_in_every_position():
+    for pos in range(32):
+        for b in range(256):
+            bs = bytearray(b"ACGTTGCAacgtTGCAAAAACCCCGGGGTTTT")
+            bs[pos] = b
+            assert sector_va(bytes(bs)) == va_planes(bytes(bs)), (pos, b)
+
+
+def test_sector_va_random_sectors():
+    rng = random.Random(2)
+    alpha = b"ACGTACGTAAAAacgtaNnRY\x00\xff@BDEFPQSUVWdeqsuvw"
+    for it in range(20000):
+        if it % 3 == 0:
+            bs = bytes(rng.choice(b"ACGTacgt") for _ in range(32))
+        elif it % 3 == 1:
+            bs = bytes(rng.choice(alpha) for _ in range(32))
+        else:
+            bs = bytes(rng.randrange(256) for _ in range(32))
+        assert sector_va(bs) == va_planes(bs), bs
