@@ -434,6 +434,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # the ranks of one box share its host cores: each packs its uploads (csrc/gf_pack.cpp) with its share of them
+    os.environ.setdefault("GF_PACK_THREADS", str(max(1, min(64, cpu_threads() // world))))
     if a.impl == "reference":
         return reference_arm(a, json_out, rank)
 
@@ -551,11 +553,37 @@ def main():
                 failures.append(f"e2e call returned {n_out.value} records, the device path {n_matches}")
             hs_ = gf_map_stats()
             lib.gf_get_map_stats(h, C.byref(hs_))
+            # the records of the host call against the oracle's (the packed upload is a different input path into k_prep)
+            e2e_parity = None
+            if oracle is not None and wl.piece >= P:
+                import numpy as np
+                got_h = np.frombuffer(out_host, dtype=match_dtype(), count=int(n_out.value)).copy()
+                e2e_parity = parity_record(got_h, wl.oracle_all, P, f"all {P} pairs, records returned by gf_map_pairs")
+                if not e2e_parity["identical"]:
+                    failures.append("e2e leg: records of gf_map_pairs differ from the oracle's")
+            # the same call with the packed upload switched off (ASCII arenas copied as they are), for comparison
+            ascii_ms = None
+            if hs_.packed_upload:
+                os.environ["GF_HOST_PACK"] = "0"
+                step_host()
+                tt = []
+                for _ in range(5):
+                    c0 = time.perf_counter()
+                    step_host()
+                    tt.append(time.perf_counter() - c0)
+                del os.environ["GF_HOST_PACK"]
+                ascii_ms = 1e3 * sorted(tt)[len(tt) // 2]
             per_call.sort()
             med = per_call[len(per_call) // 2]
             e2e = {"value": world * wl.batch.n * e2e_steps / dt_max, "unit": UNIT,
                    "h2d_bytes_per_step": int(hs_.h2d_bytes), "d2h_bytes_per_step": int(hs_.d2h_bytes),
                    "zero_copy_qualities": bool(hs_.zero_copy_qual),
+                   "packed_upload": bool(hs_.packed_upload),
+                   "upload": ("2-bit planes built by the host threads (csrc/gf_pack.cpp), ASCII left in pinned memory for the "
+                              "survivors" if hs_.packed_upload else "ASCII sequence arenas"),
+                   "pack_threads": int(os.environ.get("GF_PACK_THREADS", 0)) or cpu_threads(),
+                   "ms_per_call_median_ascii_upload": ascii_ms,
+                   "parity": e2e_parity,
                    "host_buffer_bytes_per_step": 4 * wl.batch.n * L + 2 * 8 * (wl.batch.n + 1),
                    "pairs_per_step": int(wl.batch.n), "steps": e2e_steps,
                    "ms_per_call_min": 1e3 * per_call[0], "ms_per_call_median": 1e3 * med, "ms_per_call_max": 1e3 * per_call[-1],

@@ -128,13 +128,13 @@ class gf_map_stats(C.Structure):
         ("h2d_bytes", C.c_uint64),
         ("d2h_bytes", C.c_uint64),
         ("zero_copy_qual", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("packed_upload", C.c_uint32),
         ("ms_prep", C.c_float),
         ("ms_seed", C.c_float),
         ("ms_diag", C.c_float),
         ("ms_scan", C.c_float),
         ("ms_ingest", C.c_float),
-        ("reserved2", C.c_float),
+        ("ms_host_pack", C.c_float),
     ]
 
 
@@ -181,6 +181,7 @@ EXPORTS = (
     "gf_stream_create", "gf_stream_destroy", "gf_stream_push", "gf_stream_flush", "gf_stream_take", "gf_stream_get_counts",
     "gf_fastq_stream_create", "gf_fastq_stream_destroy", "gf_fastq_stream_feed", "gf_fastq_stream_finish",
     "gf_fastq_stream_take", "gf_fastq_stream_get_counts",
+    "gf_pack_supported", "gf_pack_reads",
 )
 GF_FQ_PLAIN, GF_FQ_GZIP = 0, 1
 GF_OUT_DROP_FILTERED, GF_OUT_BUCKET_ORDER = 1, 2
@@ -247,6 +248,10 @@ def load_library():
     lib.gf_adjust_fusion_break.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, P(gf_break_ref), C.c_uint32, P(gf_break_job),
                                            C.c_uint64, P(gf_break_out)]
     lib.gf_adjust_fusion_break.restype = C.c_int
+    lib.gf_pack_supported.restype = C.c_int
+    lib.gf_pack_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_uint64, P(C.c_uint64), P(C.c_uint64)]
+    lib.gf_pack_reads.restype = C.c_int
     lib.gf_stream_create.argtypes = [C.c_void_p, C.c_int, C.c_uint64, P(C.c_void_p)]
     lib.gf_stream_create.restype = C.c_int
     lib.gf_stream_destroy.argtypes = [C.c_void_p]

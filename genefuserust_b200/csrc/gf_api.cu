@@ -3,6 +3,7 @@
  * No CPU fallback: every compute entry point needs a CUDA device and fails with GF_E_CUDA otherwise.
  */
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -115,6 +116,10 @@ void destroy_handle(gf_index* idx) {
         s.seq1.release(); s.qual1.release(); s.off1.release();
         s.seq2.release(); s.qual2.release(); s.off2.release();
         s.out.release(); s.nout.release(); s.out2.release(); s.keys.release();
+        for (int m = 0; m < 2; m++) {
+            s.pk[m].release(); s.pko[m].release(); s.pkx[m].release(); s.pxo[m].release();
+            s.h_pk[m].release(); s.h_pko[m].release(); s.h_pkx[m].release(); s.h_pxo[m].release();
+        }
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.done) cudaEventDestroy(s.done);
     }
@@ -342,31 +347,98 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
         }
     }
     const bool zc = zq1 != nullptr;
+    /* packed upload: with the sequence arenas in pinned memory too, the host threads build the plane words and only they are
+     * copied (gf_pack.cpp); k_exact / k_verify read the survivors' bases from the mapped arenas */
+    const uint8_t *zs1 = nullptr, *zs2 = nullptr;
+    if (zc && gf_pack_available()) {
+        auto mapped = [](const void* p) -> const uint8_t* {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            return at.type == cudaMemoryTypeHost ? (const uint8_t*)at.devicePointer : nullptr;
+        };
+        zs1 = mapped(in->seq1);
+        zs2 = pe ? mapped(in->seq2) : nullptr;
+        if (!zs1 || (pe && !zs2)) zs1 = zs2 = nullptr;
+    }
+    const bool packed = zs1 != nullptr;
+    float ms_pack = 0;
+    for (uint32_t h = 0; h < nh; h++) hs[h]->stats.packed_upload = packed ? 1u : 0u;
     for (uint32_t h = 0; h < nh; h++) hs[h]->stats.zero_copy_qual = zc ? 1u : 0u;
 
     auto issue = [&](uint64_t k) -> int {
         GfStage& s = idx->stage[k & 1];
         const uint64_t lo = k * per, hi = std::min(n, lo + per), cn = hi - lo;
-        if (check_per_chunk) {
+        if (check_per_chunk && !packed) { /* (the packing threads check the offsets they read anyway) */
             uint64_t mx = 0;
             int r = scan_offsets(off1 + lo, pe ? off2 + lo : nullptr, cn, max_len, &mx, 1); /* inline: ~0.3 ms per chunk */
             if (r != GF_OK) return r;
         }
         const uint64_t b1 = off1[lo], e1 = off1[hi];
-        GF_CUDA_TRY(s.seq1.reserve(e1 - b1 + 16));
-        GF_CUDA_TRY(s.off1.reserve(sizeof(uint64_t) * (cn + 1)));
         cudaStream_t cs = idx->copy_stream;
-        GF_CUDA_TRY(cudaMemcpyAsync(s.seq1.p, in->seq1 + b1, e1 - b1, cudaMemcpyHostToDevice, cs));
+        GfPackMate pm[2];
+        if (packed) {
+            for (int m = 0; m < (pe ? 2 : 1); m++) {
+                const uint64_t* off = m ? off2 : off1;
+                const uint64_t bytes = off[hi] - off[lo];
+                const size_t wcap = sizeof(uint32_t) * 2 * (size_t)(bytes / 32 + cn + 1); /* >= 2 * sum ceil(len / 32) */
+                GF_CUDA_TRY(s.h_pk[m].reserve(wcap));
+                GF_CUDA_TRY(s.h_pkx[m].reserve(wcap));
+                GF_CUDA_TRY(s.h_pko[m].reserve(sizeof(uint32_t) * cn));
+                GF_CUDA_TRY(s.h_pxo[m].reserve(sizeof(uint32_t) * cn));
+                GF_CUDA_TRY(s.pk[m].reserve(wcap));
+                GF_CUDA_TRY(s.pkx[m].reserve(wcap));
+                GF_CUDA_TRY(s.pko[m].reserve(sizeof(uint32_t) * cn));
+                GF_CUDA_TRY(s.pxo[m].reserve(sizeof(uint32_t) * cn));
+                pm[m] = GfPackMate{};
+                pm[m].seq = (m ? in->seq2 : in->seq1) + off[lo];
+                pm[m].off = off + lo;
+                pm[m].off_base = off[lo];
+                pm[m].n = cn;
+                pm[m].mate2 = m == 1;
+                pm[m].max_len = max_len;
+                pm[m].words = s.h_pk[m].as<uint32_t>();
+                pm[m].woff = s.h_pko[m].as<uint32_t>();
+                pm[m].xwords = s.h_pkx[m].as<uint32_t>();
+                pm[m].xoff = s.h_pxo[m].as<uint32_t>();
+            }
+            const auto t_pack = std::chrono::steady_clock::now();
+            gf_pack_chunk(pm, pe ? 2 : 1); /* all host threads; the device works on the chunk before meanwhile */
+            ms_pack += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_pack).count();
+            if (pm[0].bad_offsets || (pe && pm[1].bad_offsets))
+                return fail(GF_E_INVALID, "offsets are not ascending, or a read is longer than max_len / the kernel capacity");
+            for (int m = 0; m < (pe ? 2 : 1); m++) {
+                GF_CUDA_TRY(cudaMemcpyAsync(s.pk[m].p, s.h_pk[m].p, sizeof(uint32_t) * pm[m].n_words, cudaMemcpyHostToDevice, cs));
+                GF_CUDA_TRY(cudaMemcpyAsync(s.pko[m].p, s.h_pko[m].p, sizeof(uint32_t) * cn, cudaMemcpyHostToDevice, cs));
+                GF_CUDA_TRY(cudaMemcpyAsync(s.pxo[m].p, s.h_pxo[m].p, sizeof(uint32_t) * cn, cudaMemcpyHostToDevice, cs));
+                h2d += sizeof(uint32_t) * (pm[m].n_words + 2 * cn);
+                for (int t = 0; t < pm[m].n_threads; t++) {
+                    if (!pm[m].xregion_used[t]) continue;
+                    GF_CUDA_TRY(cudaMemcpyAsync(s.pkx[m].as<uint32_t>() + pm[m].xregion_start[t],
+                                                s.h_pkx[m].as<uint32_t>() + pm[m].xregion_start[t],
+                                                sizeof(uint32_t) * pm[m].xregion_used[t], cudaMemcpyHostToDevice, cs));
+                    h2d += sizeof(uint32_t) * pm[m].xregion_used[t];
+                }
+            }
+        } else {
+            GF_CUDA_TRY(s.seq1.reserve(e1 - b1 + 16));
+            GF_CUDA_TRY(cudaMemcpyAsync(s.seq1.p, in->seq1 + b1, e1 - b1, cudaMemcpyHostToDevice, cs));
+            h2d += e1 - b1;
+        }
+        GF_CUDA_TRY(s.off1.reserve(sizeof(uint64_t) * (cn + 1)));
         if (!zc) {
             GF_CUDA_TRY(s.qual1.reserve(e1 - b1 + 16));
             GF_CUDA_TRY(cudaMemcpyAsync(s.qual1.p, in->qual1 + b1, e1 - b1, cudaMemcpyHostToDevice, cs));
             h2d += e1 - b1;
         }
         GF_CUDA_TRY(cudaMemcpyAsync(s.off1.p, off1 + lo, sizeof(uint64_t) * (cn + 1), cudaMemcpyHostToDevice, cs));
-        h2d += (e1 - b1) + sizeof(uint64_t) * (cn + 1);
+        h2d += sizeof(uint64_t) * (cn + 1);
         GfDevBatch db{};
         db.n = cn;
-        db.seq1 = s.seq1.as<uint8_t>();
+        db.seq1 = packed ? zs1 + b1 : s.seq1.as<uint8_t>();
+        if (packed) {
+            db.pk1 = s.pk[0].as<uint32_t>(); db.pko1 = s.pko[0].as<uint32_t>();
+            db.pkx1 = s.pkx[0].as<uint32_t>(); db.pxo1 = s.pxo[0].as<uint32_t>();
+        }
         db.qual1 = zc ? zq1 + b1 : s.qual1.as<uint8_t>(); /* kernels address it as qual1 + (off - base1) */
         db.s1 = s.off1.as<uint64_t>(); db.e1 = db.s1 + 1; db.qs1 = db.s1;
         db.base1 = b1;
@@ -375,17 +447,24 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
         db.max_len = max_len;
         if (pe) {
             const uint64_t b2 = off2[lo], e2 = off2[hi];
-            GF_CUDA_TRY(s.seq2.reserve(e2 - b2 + 16));
             GF_CUDA_TRY(s.off2.reserve(sizeof(uint64_t) * (cn + 1)));
-            GF_CUDA_TRY(cudaMemcpyAsync(s.seq2.p, in->seq2 + b2, e2 - b2, cudaMemcpyHostToDevice, cs));
+            if (!packed) {
+                GF_CUDA_TRY(s.seq2.reserve(e2 - b2 + 16));
+                GF_CUDA_TRY(cudaMemcpyAsync(s.seq2.p, in->seq2 + b2, e2 - b2, cudaMemcpyHostToDevice, cs));
+                h2d += e2 - b2;
+            }
             if (!zc) {
                 GF_CUDA_TRY(s.qual2.reserve(e2 - b2 + 16));
                 GF_CUDA_TRY(cudaMemcpyAsync(s.qual2.p, in->qual2 + b2, e2 - b2, cudaMemcpyHostToDevice, cs));
                 h2d += e2 - b2;
             }
             GF_CUDA_TRY(cudaMemcpyAsync(s.off2.p, off2 + lo, sizeof(uint64_t) * (cn + 1), cudaMemcpyHostToDevice, cs));
-            h2d += (e2 - b2) + sizeof(uint64_t) * (cn + 1);
-            db.seq2 = s.seq2.as<uint8_t>();
+            h2d += sizeof(uint64_t) * (cn + 1);
+            db.seq2 = packed ? zs2 + b2 : s.seq2.as<uint8_t>();
+            if (packed) {
+                db.pk2 = s.pk[1].as<uint32_t>(); db.pko2 = s.pko[1].as<uint32_t>();
+                db.pkx2 = s.pkx[1].as<uint32_t>(); db.pxo2 = s.pxo[1].as<uint32_t>();
+            }
             db.qual2 = zc ? zq2 + b2 : s.qual2.as<uint8_t>();
             db.s2 = s.off2.as<uint64_t>(); db.e2 = db.s2 ? db.s2 + 1 : nullptr; db.qs2 = db.s2;
             db.base2 = b2;
@@ -471,6 +550,7 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
         st.ms_total = ms; /* of the whole call (all indices) */
         st.kernel_launches = hs[h]->launches - launches0[h];
         st.h2d_bytes = h ? 0 : h2d;
+        st.ms_host_pack = h ? 0.f : ms_pack;
         st.d2h_bytes = d2h[h];
         if (h) { /* k_prep ran once, on hs[0] */
             st.n_sequences = hs[0]->stats.n_sequences;
@@ -973,5 +1053,52 @@ extern "C" int gf_debug_get_survivors(gf_index* idx, uint32_t* out_pairs_meta, u
     *n = c.n_survivors;
     uint64_t m = std::min<uint64_t>(cap, c.n_survivors);
     if (m) GF_CUDA_TRY(cudaMemcpy(out_pairs_meta, idx->ws_survivors.p, sizeof(uint32_t) * 2 * m, cudaMemcpyDeviceToHost));
+    return GF_OK;
+}
+
+/* ---- the host packer on its own (include/genefuse_gpu.h); no device involved ---- */
+extern "C" int gf_pack_supported(void) { return gf_pack_available() ? 1 : 0; }
+
+extern "C" int gf_pack_reads(const uint8_t* seq, const uint64_t* off, uint64_t n, int mate2, uint32_t* words, uint32_t* woff,
+                             uint32_t* xwords, uint32_t* xoff, uint64_t cap_words, uint64_t* n_words, uint64_t* n_xwords) {
+    if (!off || !n_words || !n_xwords || (n && (!seq || !woff || !xoff))) return fail(GF_E_INVALID, "NULL argument");
+    if (!gf_pack_available()) return fail(GF_E_INVALID, "the packed upload needs AVX-512BW on the host (or GF_HOST_PACK=0 is set)");
+    uint64_t need = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        if (off[i + 1] < off[i]) return fail(GF_E_INVALID, "offsets are not ascending");
+        if (off[i + 1] - off[i] > 1024) return fail(GF_E_INVALID, "a read is longer than 1024 bases");
+        need += 2 * ((off[i + 1] - off[i] + 31) >> 5);
+    }
+    *n_words = need;
+    *n_xwords = 0;
+    if (need > 0x7FFFFFFFull) return fail(GF_E_LIMIT, "more than 2^31 plane words: split the batch");
+    if (need > cap_words) return fail(GF_E_CAPACITY, "cap_words too small; *n_words holds the required count");
+    if (!n) return GF_OK;
+    if (need && (!words || !xwords)) return fail(GF_E_INVALID, "NULL argument");
+    GfPackMate pm{};
+    pm.seq = seq;
+    pm.off = off;
+    pm.off_base = off[0];
+    pm.n = n;
+    pm.mate2 = mate2 != 0;
+    pm.max_len = 1024;
+    pm.words = words;
+    pm.woff = woff;
+    pm.xwords = xwords;
+    pm.xoff = xoff;
+    gf_pack_chunk(&pm, 1);
+    /* the packing threads wrote their exception words into separate regions: close the gaps */
+    uint64_t fill = 0;
+    for (int t = 0; t < pm.n_threads; t++) {
+        const uint64_t a = n * (uint64_t)t / pm.n_threads, b = n * (uint64_t)(t + 1) / pm.n_threads;
+        const uint64_t shift = pm.xregion_start[t] - fill;
+        if (pm.xregion_used[t] && shift) {
+            memmove(xwords + fill, xwords + pm.xregion_start[t], sizeof(uint32_t) * pm.xregion_used[t]);
+            for (uint64_t i = a; i < b; i++)
+                if (xoff[i]) xoff[i] -= (uint32_t)shift;
+        }
+        fill += pm.xregion_used[t];
+    }
+    *n_xwords = fill;
     return GF_OK;
 }

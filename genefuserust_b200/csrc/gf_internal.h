@@ -8,6 +8,7 @@
 
 #include "../../include/genefuse_gpu.h"
 #include "gf_device.cuh"
+#include "gf_pack.h"
 
 void gf_set_error(const std::string& msg);
 
@@ -59,8 +60,35 @@ struct GfMapCounters {
     unsigned long long pad[7];
 };
 
+/* grow-only pinned host buffer (contents are not kept when it grows) */
+struct GfPinned {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return (T*)p; }
+};
+
 struct GfStage { /* one in-flight chunk of a host batch */
     GfBuf seq1, qual1, off1, seq2, qual2, off2, out, nout;
+    /* packed upload (gf_pack.cpp), per mate: plane words, their per-read offsets, exception words, per-read exception offsets —
+     * built in the pinned buffers by the host threads, copied to the device buffers */
+    GfBuf pk[2], pko[2], pkx[2], pxo[2];
+    GfPinned h_pk[2], h_pko[2], h_pkx[2], h_pxo[2];
     GfBuf out2, keys; /* output mode != 0: compacted records + their order keys (nout holds two counters then) */
     cudaEvent_t copied = nullptr, done = nullptr;
     uint64_t n = 0, pair_base = 0, out_cap = 0;
@@ -148,6 +176,13 @@ struct GfDevBatch {
     uint64_t bytes1, bytes2; /* readable extent of the seq/qual arenas (0 = unknown: no bounds guard) */
     uint64_t pair_base;      /* added to the local pair index in emitted records */
     uint32_t max_len;        /* upper bound of any read length (selects the kernel capacity) */
+    /* packed upload (gf_pack.cpp; host batches in pinned memory, reads <= 256 bases): k_prep takes the plane words the host
+     * built instead of converting the ASCII, and seq1 / seq2 are the MAPPED pinned arenas, read only by k_exact / k_verify
+     * for the survivors.  pk == nullptr: convert from ASCII. */
+    const uint32_t *pk1 = nullptr, *pk2 = nullptr;   /* plane words: per read nw x lo, nw x hi */
+    const uint32_t *pko1 = nullptr, *pko2 = nullptr; /* per read: where its plane words start */
+    const uint32_t *pkx1 = nullptr, *pkx2 = nullptr; /* exception words: per flagged read nw x valid, nw x aux */
+    const uint32_t *pxo1 = nullptr, *pxo2 = nullptr; /* per read: 0 = every base upper-case ACGT, else 1 + start of its exception words */
 };
 /* store_owner != nullptr (list mode): reuse the sequence store `store_owner` filled for the SAME batch just before on the same
  * stream instead of running k_prep again (only taken on the split-screen path, reads <= 256 bases; ignored otherwise) */

@@ -1461,17 +1461,19 @@ int gf_map_device_batch(gf_index* idx, const GfDevBatch& b, gf_match* d_out, uin
             const size_t psm = sizeof(uint32_t) * tpp::WARPS * (w5 ? tpp::Lay<5>::NWORDS : tpp::Lay<8>::NWORDS) * 32;
             const uint64_t want_b = (b.n + tpp::WARPS * 32 - 1) / (tpp::WARPS * 32);
             /* persistent grids: exactly as many blocks as are resident at once (a partial second wave would idle SMs) */
-#define GF_LAUNCH_PREP(WW, PE)                                                             \
+#define GF_LAUNCH_PREP2(WW, PE, PK)                                                        \
     do {                                                                                   \
-        GF_CUDA_TRY(set_smem(split::k_prep<WW, PE>, psm));                                 \
+        GF_CUDA_TRY(set_smem(split::k_prep<WW, PE, PK>, psm));                             \
         const unsigned pgrid = (unsigned)std::min<uint64_t>(                               \
-            want_b, (uint64_t)idx->sm_count * resident_blocks(split::k_prep<WW, PE>, tpp::WARPS * 32, psm)); \
-        split::k_prep<WW, PE><<<pgrid, tpp::WARPS * 32, psm, st>>>(pp);                    \
+            want_b, (uint64_t)idx->sm_count * resident_blocks(split::k_prep<WW, PE, PK>, tpp::WARPS * 32, psm)); \
+        split::k_prep<WW, PE, PK><<<pgrid, tpp::WARPS * 32, psm, st>>>(pp);                \
     } while (0)
+#define GF_LAUNCH_PREP(WW, PE) do { if (b.pk1) GF_LAUNCH_PREP2(WW, PE, true); else GF_LAUNCH_PREP2(WW, PE, false); } while (0)
             if (!store_owner) {
                 if (w5) { if (paired) GF_LAUNCH_PREP(5, true); else GF_LAUNCH_PREP(5, false); }
                 else { if (paired) GF_LAUNCH_PREP(8, true); else GF_LAUNCH_PREP(8, false); }
             }
+#undef GF_LAUNCH_PREP2
 #undef GF_LAUNCH_PREP
             if (record_events) GF_CUDA_TRY(cudaEventRecord(ev->e[1], st));
             split::SeedParams sdp;

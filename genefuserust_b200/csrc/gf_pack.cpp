@@ -1,0 +1,247 @@
+/*
+ * gf_pack.cpp — host side of the packed upload of gf_map_pairs (no CUDA here).
+ *
+ * End to end the mapping call is bound by the host -> device copy: 316 bytes per 2x150 pair at ~50 GB/s, while the device
+ * needs 0.5 ns per pair.  The kernels only ever look at bit-planes of the reads (csrc/gf_screen_tpp.cuh), so when the arenas
+ * live in pinned host memory the planes are built HERE, by all host cores at memory speed (AVX-512BW: a 64-byte load and two
+ * test-into-mask instructions give 64 plane bits each), and only they cross PCIe: 2 bits per base + 8 bytes per read
+ * (~112 bytes per pair with the offsets).  The ASCII stays where it is; the handful of reads that survive the screen are
+ * fetched from the pinned arenas by k_exact / k_verify on demand, like the quality bytes of fast_merge.
+ *
+ * Per read of mate m, forward orientation, bit j of word k = base 32 k + j:
+ *   words[woff[i] ..]           nw = ceil(len / 32) words of `lo` (bit 2 of the ASCII byte), then nw words of `hi` (bit 1),
+ *                               both cleared where the base is not valid (A0 T1 C2 G3 = hi:lo, src/core/indexer.rs:888-904)
+ *   xoff[i] == 0                every base is upper-case ACGT: the validity planes are all ones, nothing else is sent
+ *   xwords[xoff[i] - 1 ..]      otherwise nw words of `valid` then nw words of `aux`:
+ *                                 mate 1: valid = upper-case ACGT,       aux = the byte is 'N'   (fast_merge, read.rs:339-367)
+ *                                 mate 2: valid = ACGT in either case,   aux = upper-case ACGT   (reverse_complement keeps the
+ *                                         case-insensitive complement, sequence.rs:52-60; map_read wants upper case)
+ * which is exactly what convert_r1 / convert_r2_rc compute on the device from the ASCII (the device reverses mate 2 itself).
+ * tests/test_gpu_parity.py::test_packed_upload_parity runs both paths on ragged reads with N / lower case / IUPAC bytes.
+ *
+ * The packer is compiled for AVX-512BW by a function attribute and only used when the CPU has it (gf_pack_available); without
+ * it gf_map_pairs keeps uploading the ASCII arenas.
+ */
+#include <immintrin.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "gf_pack.h"
+
+namespace {
+
+/* persistent workers: a pipeline chunk is packed in ~1 ms, thread start-up would cost as much */
+class Pool {
+public:
+    explicit Pool(int n) : n_(n) {
+        for (int t = 1; t < n_; t++) th_.emplace_back([this, t] { worker(t); });
+    }
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            gen_++;
+            agen_.store(gen_, std::memory_order_release);
+        }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    int size() const { return n_; }
+    /* fn(tid) on every thread (the caller is thread 0); returns when all are done */
+    void run(const std::function<void(int)>& fn) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn;
+            left_ = n_ - 1;
+            aleft_.store(left_, std::memory_order_release);
+            gen_++;
+            agen_.store(gen_, std::memory_order_release);
+        }
+        cv_.notify_all();
+        fn(0);
+        for (int spin = 0; spin < 20000 && aleft_.load(std::memory_order_acquire) != 0; spin++) _mm_pause();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [this] { return left_ == 0; });
+        fn_ = nullptr;
+    }
+    /* all threads of the running job meet here */
+    void barrier() {
+        const int g = bar_gen_.load(std::memory_order_acquire);
+        if (bar_cnt_.fetch_add(1, std::memory_order_acq_rel) + 1 == n_) {
+            bar_cnt_.store(0, std::memory_order_relaxed);
+            bar_gen_.store(g + 1, std::memory_order_release);
+        } else {
+            while (bar_gen_.load(std::memory_order_acquire) == g) _mm_pause();
+        }
+    }
+
+private:
+    void worker(int tid) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)>* fn;
+            /* a pipeline hands out a chunk every millisecond or so: spin for a moment before going to sleep */
+            for (int spin = 0; spin < 20000 && agen_.load(std::memory_order_acquire) == seen; spin++) _mm_pause();
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                fn = fn_;
+            }
+            (*fn)(tid);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                --left_;
+                aleft_.store(left_, std::memory_order_release);
+                if (left_ == 0) done_.notify_one();
+            }
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)>* fn_ = nullptr;
+    uint64_t gen_ = 0;
+    int left_ = 0;
+    bool stop_ = false;
+    std::atomic<int> bar_cnt_{0}, bar_gen_{0};
+    std::atomic<int> aleft_{0};
+    std::atomic<uint64_t> agen_{0}; /* copy of gen_ the workers can poll without the lock */
+};
+
+std::mutex g_pool_mu; /* one job at a time (handles on several devices share the host cores) */
+Pool* g_pool = nullptr;
+
+int want_threads() {
+    if (const char* e = getenv("GF_PACK_THREADS")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= GF_PACK_MAX_THREADS) return v;
+    }
+    unsigned hc = std::thread::hardware_concurrency();
+    if (hc == 0) hc = 4;
+    return (int)std::min<unsigned>(hc, GF_PACK_MAX_THREADS);
+}
+
+/* one read -> plane words.  Returns true when some base is not upper-case ACGT (then xv / xa are meaningful). */
+__attribute__((target("avx512f,avx512bw"))) inline bool pack_read(const uint8_t* s, uint32_t len, bool mate2, uint32_t* lo,
+                                                                  uint32_t* hi, uint32_t* xv, uint32_t* xa) {
+    const __m512i b4 = _mm512_set1_epi8(4), b2 = _mm512_set1_epi8(2), m7 = _mm512_set1_epi8(7), up = _mm512_set1_epi8((char)0xDF);
+    /* the letter a valid base must be, by the low 3 bits of the byte: 1 A, 3 C, 4 T, 7 G (either case); 0xFF elsewhere: a byte
+     * with those low bits never equals it */
+    const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8(-1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1));
+    const __m512i cn = _mm512_set1_epi8('N');
+    bool flagged = false;
+    uint32_t w = 0;
+    for (uint32_t p = 0; p < len; p += 64, w += 2) {
+        const uint32_t rem = len - p;
+        const __mmask64 km = rem >= 64 ? ~0ull : ((1ull << rem) - 1ull);
+        const __m512i x = _mm512_maskz_loadu_epi8(km, s + p);
+        const __m512i e = _mm512_shuffle_epi8(lut, _mm512_and_si512(x, m7));
+        const uint64_t vcs = _mm512_mask_cmpeq_epi8_mask(km, x, e);
+        uint64_t v = vcs, a;
+        if (mate2) {
+            v = _mm512_mask_cmpeq_epi8_mask(km, _mm512_and_si512(x, up), e);
+            a = vcs;
+        } else {
+            a = _mm512_mask_cmpeq_epi8_mask(km, x, cn);
+        }
+        const uint64_t l = _mm512_test_epi8_mask(x, b4) & v, h = _mm512_test_epi8_mask(x, b2) & v;
+        flagged |= vcs != km;
+        lo[w] = (uint32_t)l; hi[w] = (uint32_t)h; xv[w] = (uint32_t)v; xa[w] = (uint32_t)a;
+        if (rem > 32) { lo[w + 1] = (uint32_t)(l >> 32); hi[w + 1] = (uint32_t)(h >> 32); xv[w + 1] = (uint32_t)(v >> 32); xa[w + 1] = (uint32_t)(a >> 32); }
+    }
+    return flagged;
+}
+
+__attribute__((target("avx512f,avx512bw"))) void pack_range(GfPackMate* m, uint64_t a, uint64_t b, uint64_t word_base, uint64_t x_base,
+                                                            uint64_t* x_used) {
+    uint64_t P = word_base, X = x_base;
+    uint32_t tv[32], ta[32]; /* validity planes of the current read (<= 1024 bases); kept only when it has exceptions */
+    for (uint64_t i = a; i < b; i++) {
+        const uint64_t o = m->off[i];
+        const uint32_t len = (uint32_t)(m->off[i + 1] - o), nw = (len + 31) >> 5;
+        uint32_t* lo = m->words + 2 * P;
+        m->woff[i] = (uint32_t)(2 * P);
+        uint32_t* xv = m->xwords + X;
+        const bool fl = pack_read(m->seq + (o - m->off_base), len, m->mate2, lo, lo + nw, tv, ta);
+        if (fl) {
+            memcpy(xv, tv, 4 * nw);
+            memcpy(xv + nw, ta, 4 * nw);
+            m->xoff[i] = (uint32_t)(X + 1);
+            X += 2 * nw;
+        } else {
+            m->xoff[i] = 0;
+        }
+        P += nw;
+    }
+    *x_used = X - x_base;
+}
+
+}  // namespace
+
+bool gf_pack_available() {
+    static const bool cpu_ok = [] {
+        __builtin_cpu_init();
+        return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
+    }();
+    const char* e = getenv("GF_HOST_PACK"); /* read per call: tests switch it */
+    return cpu_ok && !(e && atoi(e) == 0);
+}
+
+int gf_pack_threads() { return want_threads(); }
+
+void gf_pack_chunk(GfPackMate* mates, int n_mates) { /* n_mates <= 2 */
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    const int nt = want_threads();
+    if (!g_pool || g_pool->size() != nt) {
+        delete g_pool;
+        g_pool = new Pool(nt);
+    }
+    Pool* pool = g_pool;
+    std::vector<uint64_t> sums((size_t)n_mates * nt, 0);
+    std::atomic<uint32_t> bad_flag[2];
+    bad_flag[0].store(0);
+    bad_flag[1].store(0);
+    for (int k = 0; k < n_mates; k++) mates[k].n_threads = nt;
+    const std::function<void(int)> job = [&](int t) {
+        /* pass A: plane words of this thread's reads (from the offsets alone) */
+        for (int k = 0; k < n_mates; k++) {
+            const GfPackMate& m = mates[k];
+            const uint64_t a = m.n * (uint64_t)t / nt, b = m.n * (uint64_t)(t + 1) / nt;
+            uint64_t s = 0, bad = 0;
+            for (uint64_t i = a; i < b; i++) {
+                const uint64_t len = m.off[i + 1] - m.off[i]; /* wraps to a huge value when the offsets descend */
+                bad |= len > m.max_len;
+                s += (len + 31) >> 5;
+            }
+            sums[(size_t)k * nt + t] = s;
+            if (bad) bad_flag[k].store(1, std::memory_order_relaxed);
+        }
+        pool->barrier();
+        for (int k = 0; k < n_mates; k++)
+            if (bad_flag[k].load(std::memory_order_relaxed)) return; /* every thread sees the same flags after the barrier */
+        /* pass B: pack.  A thread's exception words start where its plane words would if every read had them: the regions
+         * never overlap, and only their used parts are copied to the device */
+        for (int k = 0; k < n_mates; k++) {
+            GfPackMate& m = mates[k];
+            const uint64_t a = m.n * (uint64_t)t / nt, b = m.n * (uint64_t)(t + 1) / nt;
+            uint64_t base = 0;
+            for (int u = 0; u < t; u++) base += sums[(size_t)k * nt + u];
+            m.xregion_start[t] = 2 * base;
+            pack_range(&m, a, b, base, 2 * base, &m.xregion_used[t]);
+            if (t == nt - 1) m.n_words = 2 * (base + sums[(size_t)k * nt + t]);
+        }
+    };
+    pool->run(job);
+    for (int k = 0; k < n_mates; k++) mates[k].bad_offsets = bad_flag[k].load();
+}

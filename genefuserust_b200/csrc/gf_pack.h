@@ -1,0 +1,29 @@
+/* gf_pack.h — host-side packing of ASCII reads into plane words (gf_pack.cpp); internal, not part of the ABI */
+#pragma once
+#include <stdint.h>
+
+#define GF_PACK_MAX_THREADS 64
+
+struct GfPackMate {       /* one mate of one pipeline chunk */
+    const uint8_t* seq;   /* arena; read i = seq[off[i] - off_base .. off[i + 1] - off_base) */
+    const uint64_t* off;  /* n + 1 offsets */
+    uint64_t off_base;
+    uint64_t n;
+    bool mate2;           /* validity rules of R2 (case-insensitive planes + upper-case plane) instead of R1's (+ 'N' plane) */
+    /* outputs, pinned host memory owned by the caller: words / xwords hold 2 * sum(ceil(len / 32)) entries, woff / xoff n */
+    uint32_t* words;
+    uint32_t* woff;
+    uint32_t* xwords;
+    uint32_t* xoff;
+    uint32_t max_len;                              /* in: no read may be longer (checked by the packing threads) */
+    uint32_t bad_offsets;                          /* out: != 0 = offsets that do not ascend, or a read longer than max_len:
+                                                      nothing of this chunk may be used */
+    uint64_t n_words;                              /* entries of `words` in use */
+    int n_threads;
+    uint64_t xregion_start[GF_PACK_MAX_THREADS];   /* per packing thread: its part of `xwords` (entries) */
+    uint64_t xregion_used[GF_PACK_MAX_THREADS];
+};
+
+bool gf_pack_available();                          /* AVX-512BW present and GF_HOST_PACK != 0 */
+int gf_pack_threads();                             /* GF_PACK_THREADS or the hardware threads */
+void gf_pack_chunk(GfPackMate* mates, int n_mates);

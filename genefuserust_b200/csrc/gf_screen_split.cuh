@@ -66,7 +66,7 @@ struct PrepParams {
 };
 
 /* ---------------------------------------------------------------------------------------------- k_prep */
-template <int W, bool PAIRED>
+template <int W, bool PAIRED, bool PACKED>
 __global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* sm = reinterpret_cast<uint32_t*>(smem_raw);
@@ -107,9 +107,19 @@ __global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepPa
                 err |= 1u;
                 len1 = len2 = 0;
             } else {
-                tpp::convert_r1<W>(c, s1, len1, B.seq1, bound1, pol_stream);
+                if (PACKED) { /* the host built the planes (gf_pack.cpp) */
+                    const uint32_t x1 = __ldg(B.pxo1 + p);
+                    tpp::load_r1_packed<W>(c, B.pk1 + __ldg(B.pko1 + p), x1 ? B.pkx1 + (x1 - 1u) : nullptr, len1);
+                } else {
+                    tpp::convert_r1<W>(c, s1, len1, B.seq1, bound1, pol_stream);
+                }
                 if (PAIRED) {
-                    tpp::convert_r2_rc<W>(c, s2, len2, B.seq2, bound2, pol_stream);
+                    if (PACKED) {
+                        const uint32_t x2 = __ldg(B.pxo2 + p);
+                        tpp::load_r2_rc_packed<W>(c, B.pk2 + __ldg(B.pko2 + p), x2 ? B.pkx2 + (x2 - 1u) : nullptr, len2);
+                    } else {
+                        tpp::convert_r2_rc<W>(c, s2, len2, B.seq2, bound2, pol_stream);
+                    }
                     olen = tpp::find_overlap<W>(c, len1, len2, q1, q2, &diff, &r1_bits);
                 }
                 nseq = olen >= 0 ? 1 : (PAIRED ? 2 : 1);

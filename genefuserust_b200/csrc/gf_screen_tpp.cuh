@@ -168,6 +168,45 @@ __device__ __forceinline__ void convert_r2_rc(const Col& c, const uint8_t* seq, 
     for (int w = nwords; w <= W; w++) { c(Lay<W>::C2LO, w) = 0; c(Lay<W>::C2HI, w) = 0; c(Lay<W>::C2V, w) = 0; c(Lay<W>::VCS, w) = 0; }
 }
 
+/* ---- packed upload: the host built the forward planes (gf_pack.cpp), nothing is converted here ---- */
+/* R1: nw words of lo, nw of hi; exception words (valid = upper-case ACGT, aux = 'N') only when the read has any */
+template <int W>
+__device__ __forceinline__ void load_r1_packed(const Col& c, const uint32_t* __restrict__ w, const uint32_t* __restrict__ x, int len) {
+    const int nw = (len + 31) >> 5;
+    for (int k = 0; k < nw; k++) {
+        c(Lay<W>::R1LO, k) = __ldg(w + k);
+        c(Lay<W>::R1HI, k) = __ldg(w + nw + k);
+        c(Lay<W>::R1V, k) = x ? __ldg(x + k) : tailmask(len - 32 * k);
+        c(Lay<W>::R1N, k) = x ? __ldg(x + nw + k) : 0u;
+    }
+    for (int k = nw; k <= W; k++) { c(Lay<W>::R1LO, k) = 0; c(Lay<W>::R1HI, k) = 0; c(Lay<W>::R1V, k) = 0; c(Lay<W>::R1N, k) = 0; }
+}
+/* 32 bits of a forward plane (nw words at p) starting at bit `pos` (may be negative); bits outside the plane read as 0 */
+__device__ __forceinline__ uint32_t plane_win(const uint32_t* __restrict__ p, int nw, int pos) {
+    if (pos <= -32) return 0u;
+    if (pos < 0) return __ldg(p) << (-pos);
+    const int wi = pos >> 5;
+    const uint32_t a = __ldg(p + wi), b = wi + 1 < nw ? __ldg(p + wi + 1) : 0u;
+    return __funnelshift_r(a, b, (uint32_t)pos & 31u);
+}
+/* R2: forward planes -> the planes of reverse_complement(R2): rc position u' = len - 1 - u, so word k of an rc plane is the
+ * bit-reversed forward window at len - 32 (k + 1); complement = code ^ 1 = the low plane inverted.  Exception words: valid
+ * = ACGT in either case, aux = upper-case ACGT (VCS) */
+template <int W>
+__device__ __forceinline__ void load_r2_rc_packed(const Col& c, const uint32_t* __restrict__ w, const uint32_t* __restrict__ x, int len) {
+    const int nw = (len + 31) >> 5;
+    for (int k = 0; k < nw; k++) {
+        const int pos = len - 32 * (k + 1);
+        const uint32_t tm = tailmask(len - 32 * k);
+        const uint32_t sv = x ? __brev(plane_win(x, nw, pos)) : tm;
+        c(Lay<W>::C2LO, k) = ~__brev(plane_win(w, nw, pos)) & sv;
+        c(Lay<W>::C2HI, k) = __brev(plane_win(w + nw, nw, pos)) & sv;
+        c(Lay<W>::C2V, k) = sv;
+        c(Lay<W>::VCS, k) = x ? __brev(plane_win(x + nw, nw, pos)) : tm;
+    }
+    for (int k = nw; k <= W; k++) { c(Lay<W>::C2LO, k) = 0; c(Lay<W>::C2HI, k) = 0; c(Lay<W>::C2V, k) = 0; c(Lay<W>::VCS, k) = 0; }
+}
+
 /* mismatch mask of overlap chunk k for overlap length olen (read.rs:346) */
 template <int W>
 __device__ __forceinline__ uint32_t overlap_mism(const Col& c, int offset, int olen, int len2, int k) {

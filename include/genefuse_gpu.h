@@ -173,7 +173,10 @@ typedef struct gf_map_stats {
     uint64_t d2h_bytes;      /* bytes copied device -> host */
     uint32_t zero_copy_qual; /* 1 = the quality arenas were pinned host memory and were NOT copied: the kernels
                                 read the few quality bytes fast_merge depends on directly over PCIe */
-    uint32_t reserved;
+    uint32_t packed_upload;  /* 1 = sequence AND quality arenas were pinned host memory, reads <= 256 bases and the host has
+                                AVX-512BW: the host threads built the reads' 2-bit planes and only those were copied (about a
+                                third of the bytes); the few reads that survive the screen are fetched from the pinned arenas on
+                                demand.  GF_HOST_PACK=0 disables this, GF_PACK_THREADS sets the number of packing threads. */
     /* the four launches ms_screen is made of (split screen, reads <= 256 bases; 0 otherwise).  gf_map_pairs (chunked
      * host path): the last chunk only, like every other ms_* field there. */
     float ms_prep;           /* k_prep: ASCII -> bit-planes, fast_merge, sequence store */
@@ -181,7 +184,7 @@ typedef struct gf_map_stats {
     float ms_diag;           /* k_diag: seeded sequences against the gene planes */
     float ms_scan;           /* k_scan: unseeded sequences, filter probes */
     float ms_ingest;         /* gf_map_fastq only: H2D of the text + newline scan + record tables (before the mapping) */
-    float reserved2;
+    float ms_host_pack;      /* packed upload: host wall-clock milliseconds the packing threads took (sum over the chunks) */
 } gf_map_stats;
 
 const char* gf_last_error(void);
@@ -391,6 +394,24 @@ int gf_fastq_stream_feed(gf_fastq_stream* s, const uint8_t* fq1, uint64_t n1, co
 int gf_fastq_stream_finish(gf_fastq_stream* s);
 int gf_fastq_stream_take(gf_fastq_stream* s, gf_match* out, uint64_t out_cap, uint64_t* n_out);
 int gf_fastq_stream_get_counts(const gf_fastq_stream* s, uint64_t* records, uint64_t* text_bytes, uint64_t* map_calls);
+
+/* ---- the packed upload, as a host-side utility ----
+ * With all four arenas of a batch in pinned host memory (and reads <= 256 bases) gf_map_pairs / gf_list_map_pairs do not copy
+ * the sequence bytes: the host threads turn them into the bit-planes the kernels work on — 2 bits per base — and only those
+ * cross PCIe (gf_map_stats.packed_upload, csrc/gf_pack.cpp); the reads that survive the screen are fetched from the pinned
+ * arenas on demand.  gf_pack_reads is that packer on its own (no device involved), for tests and for callers that want to
+ * look at the format.  Per read i of `n` (bytes seq[off[i] - off[0] .. off[i + 1] - off[0])), with nw = ceil(len / 32):
+ *   words[woff[i] ..]        nw words of the low code bit, nw words of the high code bit (A 0, T 1, C 2, G 3 = high:low; bit j
+ *                            of word k = base 32 k + j), cleared where the base is not valid
+ *   xoff[i] == 0             every base is upper-case ACGT; otherwise xwords[xoff[i] - 1 ..] = nw words `valid`, nw words `aux`:
+ *                            mate2 == 0: valid = upper-case ACGT, aux = the byte is 'N';
+ *                            mate2 != 0: valid = ACGT in either case, aux = upper-case ACGT.
+ * words / xwords hold cap_words entries each, woff / xoff n; *n_words / *n_xwords = entries used (GF_E_CAPACITY: needed).
+ * gf_pack_supported() == 0 (no AVX-512BW on this host, or GF_HOST_PACK=0): gf_pack_reads fails with GF_E_INVALID and
+ * gf_map_pairs uploads the ASCII arenas as before. */
+int gf_pack_supported(void);
+int gf_pack_reads(const uint8_t* seq, const uint64_t* off, uint64_t n, int mate2, uint32_t* words, uint32_t* woff,
+                  uint32_t* xwords, uint32_t* xoff, uint64_t cap_words, uint64_t* n_words, uint64_t* n_xwords);
 
 /* ---- several GPUs of one box from ONE process (what the Rust binary needs; bench.py uses one process per GPU) ----
  * The index is replicated on every listed device (built there, ~19 ms each, in parallel); every batch is cut into

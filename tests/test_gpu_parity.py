@@ -377,6 +377,72 @@ def test_zero_copy_qualities_pinned(mappers, small_panel):
     assert_same_matches(got_zc, want, "zero-copy")
 
 
+def test_packed_upload_parity(mappers, small_panel, monkeypatch):
+    """packed upload (csrc/gf_pack.cpp): with all four arenas in pinned memory the host threads build the reads' bit-planes and
+    only those are copied; k_prep takes them as they are (mate 2 reversed on the device), survivors are read from the mapped
+    arenas.  Ragged reads (0 .. 256 bases) with N / lower case / IUPAC bytes, PE and SE, several thread counts: the records must
+    equal the oracle's and the ASCII path's."""
+    import torch
+    m, o = mappers
+    rng = random.Random(5)
+    genes = small_panel.seqs
+    comp = bytes.maketrans(b"ACGTacgt", b"TGCAtgca")
+    r1s, r2s = [], []
+    for k in range(40000):
+        ga = rng.randrange(len(genes))
+        sa = rng.randrange(0, max(1, len(genes[ga]) - 700))
+        if k % 4 == 0:   # fusion-like fragment
+            gb = rng.randrange(len(genes))
+            sb = rng.randrange(0, max(1, len(genes[gb]) - 700))
+            x = rng.randint(40, 300)
+            frag = bytearray(genes[ga][sa:sa + x].tobytes() + genes[gb][sb:sb + 600 - x].tobytes())
+        else:
+            frag = bytearray(genes[ga][sa:sa + 600].tobytes())
+        if rng.random() < 0.5:
+            frag = bytearray(bytes(frag[::-1]).translate(comp))
+        flen = rng.randint(60, 500)
+        frag = frag[:flen]
+        if k % 3 == 0:
+            for _ in range(rng.randint(1, 4)):
+                frag[rng.randrange(len(frag))] = rng.choice(b"acgtNnRYK@\x00\xffACGT")
+        l1 = rng.choice((0, 1, 15, 16, 31, 32, 33, 64, 65, 100, 150, 151, 200, 256)) if k % 5 == 0 else 150
+        l2 = rng.choice((0, 16, 75, 150, 250, 256)) if k % 7 == 0 else l1
+        r1 = bytes(frag[:l1])
+        r2 = bytes(frag[::-1]).translate(comp)[:l2]
+        q = lambda n: bytes(rng.choice(b"EEEEEEA/") for _ in range(n))
+        r1s.append((r1, q(len(r1))))
+        r2s.append((r2, q(len(r2))))
+    b = ReadBatch.from_reads(r1s, r2s)
+    assert b.max_len == 256
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    bp = ReadBatch(pin(b.seq1), pin(b.qual1), pin(b.off1.view(np.int64)).view(np.uint64),
+                   pin(b.seq2), pin(b.qual2), pin(b.off2.view(np.int64)).view(np.uint64))
+    bp.max_len = b.max_len
+    want = o.scan(b, threads=8)
+    assert len(want) > 300
+    monkeypatch.setenv("GF_HOST_PACK", "0")
+    got_ascii = m.scan_pair_end(bp)
+    assert m.map_stats().packed_upload == 0
+    assert_same_matches(got_ascii, want, "ascii upload")
+    monkeypatch.setenv("GF_HOST_PACK", "1")
+    monkeypatch.setenv("GF_CHUNK_MB", "1")       # many pipeline chunks
+    for threads in ("1", "3", "16"):
+        monkeypatch.setenv("GF_PACK_THREADS", threads)
+        got = m.scan_pair_end(bp)
+        st = m.map_stats()
+        if st.packed_upload == 0:
+            pytest.skip("host without AVX-512BW: the packed upload is not offered")
+        assert st.h2d_bytes < 0.5 * (b.seq1.size + b.seq2.size)
+        assert_same_matches(got, want, f"packed upload, {threads} threads")
+    # single end
+    se = ReadBatch(bp.seq1, bp.qual1, bp.off1, None, None, None)
+    se.max_len = b.max_len
+    want_se = o.scan(ReadBatch(b.seq1, b.qual1, b.off1, None, None, None), threads=8)
+    got_se = m.scan_single_end(se)
+    assert m.map_stats().packed_upload == 1
+    assert_same_matches(got_se, want_se, "packed upload, single end")
+
+
 def test_list_mode_concurrent_handles(host, small_panel):
     """multi-CSV list mode (fusion_scan.rs:62-188): one index per CSV, used concurrently from different host
     threads over the same reads; handles are independent, every result must equal the oracle's for its panel"""

@@ -1,5 +1,5 @@
-"""CPU model of the 16-base SWAR step of the read converters (csrc/gf_swar.cuh: expect4 / block16): the multiply
-gathers, the PRMT validity lookup and the slow path, checked against the plain definition of the planes
+"""CPU model of the 16-base SWAR step of the read converters (csrc/gf_swar.cuh: block16): the multiply gathers, the
+nibble-domain validity test and the slow path, checked against the plain definition of the planes
 (make_kmer_bytes' code A0 T1 C2 G3, src/core/indexer.rs:888-904; reverse_complement's case rule, src/core/sequence.rs:52-60).
 The constants are read from the CUDA source so that the model cannot drift from the kernel."""
 import os
@@ -16,9 +16,11 @@ def _const(pattern):
     return [int(x, 16) for x in m.groups()]
 
 
-LUT_LO, LUT_HI, PACK = _const(r"__byte_perm\((0x[0-9A-Fa-f]+)u, (0x[0-9A-Fa-f]+)u, __byte_perm\(u, 0u, (0x[0-9A-Fa-f]+)u\)\)")
 MUL_LO, = _const(r"\(z0 & 0x44444444u\) \* (0x[0-9A-Fa-f]+)u")
 MUL_HI, = _const(r"\(z0 & 0x22222222u\) \* (0x[0-9A-Fa-f]+)u")
+NIB3, = _const(r"constexpr uint32_t NIB3 = (0x[0-9A-Fa-f]+)u;")
+GATHER3, = _const(r"constexpr uint32_t GATHER3 = (0x[0-9A-Fa-f]+)u;")
+FMT_XOR, FMT_AND = _const(r"\(\(y0 \^ (0x[0-9A-Fa-f]+)u\) & (0x[0-9A-Fa-f]+)u\)")
 
 
 def byte_perm(x, y, s):
@@ -26,38 +28,33 @@ def byte_perm(x, y, s):
     return sum(b[(s >> (4 * i)) & 7] << (8 * i) for i in range(4))
 
 
-def expect4(x):
-    t = x & 0x07070707
-    return byte_perm(LUT_LO, LUT_HI, byte_perm(t | (t >> 4), 0, PACK))
+def bitsel(a, b, m):
+    return (a & m) | (b & ~m & M32)
 
 
-def zero_bytes(y):
-    return (~((((y & 0x7F7F7F7F) + 0x7F7F7F7F) | y)) & 0x80808080) & M32
+def nib_code_bad(z, y):
+    l2, l1, l0, h0 = (z << 1) & M32, (z << 2) & M32, (z << 3) & M32, (y << 3) & M32
+    return ((h0 ^ (l2 & ~l1)) | (~(l0 ^ h0) & M32)) & M32
 
 
 def block16(x, ci):
-    z0 = (x[0] & 0x0F0F0F0F) | ((x[1] << 4) & 0xF0F0F0F0)
-    z1 = (x[2] & 0x0F0F0F0F) | ((x[3] << 4) & 0xF0F0F0F0)
+    z0, z1 = bitsel(x[0], (x[1] << 4) & M32, 0x0F0F0F0F), bitsel(x[2], (x[3] << 4) & M32, 0x0F0F0F0F)
+    y0, y1 = bitsel(x[0] >> 4, x[1], 0x0F0F0F0F), bitsel(x[2] >> 4, x[3], 0x0F0F0F0F)
     lo = byte_perm(((z0 & 0x44444444) * MUL_LO) & M32, ((z1 & 0x44444444) * MUL_LO) & M32, 0x7373)
     hi = byte_perm(((z0 & 0x22222222) * MUL_HI) & M32, ((z1 & 0x22222222) * MUL_HI) & M32, 0x7373)
-    cm = 0xDFDFDFDF if ci else M32
-    d = [(x[j] ^ expect4(x[j])) & cm for j in range(4)]
-    bad = d[0] | d[1] | d[2] | d[3]
-    if ci:
-        bad |= (x[0] | x[1] | x[2] | x[3]) & 0x20202020
+    c0, c1 = nib_code_bad(z0, y0) | z0, nib_code_bad(z1, y1) | z1
+    bad = ((c0 | c1) & NIB3) | ((y0 ^ FMT_XOR) & FMT_AND) | ((y1 ^ FMT_XOR) & FMT_AND)
     v, ex = 0xFFFF, (0xFFFF if ci else 0)
     if bad:
-        y0 = (zero_bytes(d[0]) >> 5) | (zero_bytes(d[1]) >> 1)
-        y1 = (zero_bytes(d[2]) >> 5) | (zero_bytes(d[3]) >> 1)
-        v = byte_perm((y0 * MUL_LO) & M32, (y1 * MUL_LO) & M32, 0x7373)
+        f0, f1 = ~y0 & (y0 << 1) & M32, ~y1 & (y1 << 1) & M32
+        vci0, vci1 = ~c0 & f0 & NIB3, ~c1 & f1 & NIB3
+        vcs0, vcs1 = vci0 & ~(y0 << 2) & M32, vci1 & ~(y1 << 2) & M32
+        g = lambda a, b: byte_perm((a * GATHER3) & M32, (b * GATHER3) & M32, 0x7373)
         if ci:
-            w0 = ((x[0] >> 3) & 0x04040404) | ((x[1] << 1) & 0x40404040)
-            w1 = ((x[2] >> 3) & 0x04040404) | ((x[3] << 1) & 0x40404040)
-            ex = v & ~byte_perm((w0 * MUL_LO) & M32, (w1 * MUL_LO) & M32, 0x7373)
+            v, ex = g(vci0, vci1), g(vcs0, vcs1)
         else:
-            n0 = (zero_bytes(x[0] ^ 0x4E4E4E4E) >> 5) | (zero_bytes(x[1] ^ 0x4E4E4E4E) >> 1)
-            n1 = (zero_bytes(x[2] ^ 0x4E4E4E4E) >> 5) | (zero_bytes(x[3] ^ 0x4E4E4E4E) >> 1)
-            ex = byte_perm((n0 * MUL_LO) & M32, (n1 * MUL_LO) & M32, 0x7373)
+            n = lambda z, y, f: f & ~(y << 2) & ~(y << 3) & z & (z << 1) & (z << 2) & ~(z << 3) & NIB3 & M32
+            v, ex = g(vcs0, vcs1), g(n(z0, y0, f0), n(z1, y1, f1))
         lo &= v
         hi &= v
     return lo & 0xFFFF, hi & 0xFFFF, v & 0xFFFF, ex & 0xFFFF

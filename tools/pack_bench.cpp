@@ -10,7 +10,7 @@
 static inline void pack_read(const uint8_t* s, int len, uint32_t* lo, uint32_t* hi, uint32_t* bad) {
     const __m512i b4 = _mm512_set1_epi8(4), b2 = _mm512_set1_epi8(2), m7 = _mm512_set1_epi8(7);
     // expected letter by low 3 bits: 1 A, 3 C, 7 G, 4 T
-    const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8(0, 'A', 0, 'C', 'T', 0, 0, 'G', 0, 0, 0, 0, 0, 0, 0, 0));
+    const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8(-1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1));
     int w = 0; uint64_t anybad = 0;
     for (int p = 0; p < len; p += 64, w += 2) {
         const int rem = len - p;
