@@ -435,7 +435,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     # the ranks of one box share its host cores: each packs its uploads (csrc/gf_pack.cpp) with its share of them
-    os.environ.setdefault("GF_PACK_THREADS", str(max(1, min(64, cpu_threads() // world))))
+    os.environ.setdefault("GF_PACK_THREADS", str(max(1, min(64, (cpu_threads() - cpu_threads() // 4) // world))))
     if a.impl == "reference":
         return reference_arm(a, json_out, rank)
 

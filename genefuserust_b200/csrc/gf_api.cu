@@ -294,14 +294,6 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
     const uint64_t* off2 = in->off2;
     if (off1[n] < off1[0] || (pe && off2[n] < off2[0])) return fail(GF_E_INVALID, "offsets are not ascending");
     const uint64_t total_bytes = (off1[n] - off1[0]) + (pe ? off2[n] - off2[0] : 0);
-    /* list mode: a chunk costs nh rounds of launches, so chunks are larger (the upload is a smaller share of a chunk anyway) */
-    uint64_t chunk_bytes = CHUNK_TARGET_BYTES * std::min<uint32_t>(nh, 4u);
-    if (const char* e = getenv("GF_CHUNK_MB")) { long v = atol(e); if (v >= 1 && v <= 65536) chunk_bytes = (uint64_t)v << 20; }
-    uint64_t n_chunks = std::max<uint64_t>(1, (2 * total_bytes + chunk_bytes - 1) / chunk_bytes);
-    n_chunks = std::min<uint64_t>(n_chunks, n);
-    const uint64_t per = (n + n_chunks - 1) / n_chunks;
-    n_chunks = (n + per - 1) / per;
-
     /* The host offsets are at hand: they must ascend, and no read may be longer than the caller's hint (or than 1024 bases);
      * the longest read selects the kernel capacity.  Without a hint the whole table is scanned here, before anything is
      * launched (several threads).  With a hint every pipeline chunk is checked against it just before it is issued (below),
@@ -362,6 +354,15 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
     }
     const bool packed = zs1 != nullptr;
     float ms_pack = 0;
+    /* pipeline chunks.  List mode: a chunk costs nh rounds of launches, so chunks are larger (the upload is a smaller share of a
+     * chunk anyway).  Packed upload: twice the size (the per-chunk work of the issuing thread is not hidden behind a copy) */
+    uint64_t chunk_bytes = CHUNK_TARGET_BYTES * std::min<uint32_t>(nh, 4u) * (packed ? 2u : 1u);
+    if (const char* e = getenv("GF_CHUNK_MB")) { long v = atol(e); if (v >= 1 && v <= 65536) chunk_bytes = (uint64_t)v << 20; }
+    uint64_t n_chunks = std::max<uint64_t>(1, (2 * total_bytes + chunk_bytes - 1) / chunk_bytes);
+    n_chunks = std::min<uint64_t>(n_chunks, n);
+    const uint64_t per = (n + n_chunks - 1) / n_chunks;
+    n_chunks = (n + per - 1) / per;
+
     for (uint32_t h = 0; h < nh; h++) hs[h]->stats.packed_upload = packed ? 1u : 0u;
     for (uint32_t h = 0; h < nh; h++) hs[h]->stats.zero_copy_qual = zc ? 1u : 0u;
 

@@ -55,8 +55,11 @@ def run(tag, hint, env):
 run("packed upload (default threads)", 150, {})
 for t in ("4", "8", "12", "16"):
     run(f"packed upload, {t} threads", 150, {"GF_PACK_THREADS": t})
+for pf in ("0", "512", "4096", "8192", "16384"):
+    for t in ("8", "12"):
+        run(f"packed upload, {t} threads, prefetch {pf} B ahead", 150, {"GF_PACK_THREADS": t, "GF_PACK_PREFETCH": pf})
 for mb in ("48", "384", "1536"):
-    run(f"packed upload, 16 threads, chunk {mb} MB", 150, {"GF_CHUNK_MB": mb})
+    run(f"packed upload, default threads, chunk {mb} MB", 150, {"GF_CHUNK_MB": mb})
 os.environ["GF_HOST_PACK"] = "0"
 run("hint=150 (per-chunk check), zero-copy qual", 150, {})
 run("hint=0 (pre-scan), zero-copy qual", 0, {})
