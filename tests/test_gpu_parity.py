@@ -434,6 +434,11 @@ def test_packed_upload_parity(mappers, small_panel, monkeypatch):
             pytest.skip("host without AVX-512BW: the packed upload is not offered")
         assert st.h2d_bytes < 0.5 * (b.seq1.size + b.seq2.size)
         assert_same_matches(got, want, f"packed upload, {threads} threads")
+    # a read longer than the hint: the packing threads notice (they read the offsets anyway) and the call fails loudly
+    bp.max_len = 200
+    with pytest.raises(Exception):
+        m.scan_pair_end(bp)
+    bp.max_len = b.max_len
     # single end
     se = ReadBatch(bp.seq1, bp.qual1, bp.off1, None, None, None)
     se.max_len = b.max_len

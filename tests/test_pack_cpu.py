@@ -64,7 +64,7 @@ def run(lib, reads, mate2):
 @pytest.mark.parametrize("threads", ["1", "4", "7"])
 def test_pack_reads_against_the_plane_definition(threads, monkeypatch):
     lib = load_library()
-    monkeypatch.delenv("GF_HOST_PACK", raising=False)
+    monkeypatch.setenv("GF_HOST_PACK", "1")        # (without it the packer is only offered with >= 8 packing threads)
     if not lib.gf_pack_supported():
         pytest.skip("no AVX-512BW on this host: the packed upload is not offered")
     monkeypatch.setenv("GF_PACK_THREADS", threads)
@@ -91,7 +91,7 @@ def test_pack_reads_against_the_plane_definition(threads, monkeypatch):
 
 def test_pack_reads_capacity_and_switch(monkeypatch):
     lib = load_library()
-    monkeypatch.delenv("GF_HOST_PACK", raising=False)
+    monkeypatch.setenv("GF_HOST_PACK", "1")
     if not lib.gf_pack_supported():
         pytest.skip("no AVX-512BW on this host")
     seq = np.frombuffer(b"ACGT" * 40, dtype=np.uint8).copy()
@@ -103,3 +103,8 @@ def test_pack_reads_capacity_and_switch(monkeypatch):
     assert rc == -3 and nw.value == 10          # GF_E_CAPACITY, needed count
     monkeypatch.setenv("GF_HOST_PACK", "0")
     assert lib.gf_pack_supported() == 0
+    monkeypatch.delenv("GF_HOST_PACK")
+    monkeypatch.setenv("GF_PACK_THREADS", "2")     # too few threads to beat the plain copy: not offered
+    assert lib.gf_pack_supported() == 0
+    monkeypatch.setenv("GF_PACK_THREADS", "12")
+    assert lib.gf_pack_supported() == 1
