@@ -579,8 +579,10 @@ def main():
                    "h2d_bytes_per_step": int(hs_.h2d_bytes), "d2h_bytes_per_step": int(hs_.d2h_bytes),
                    "zero_copy_qualities": bool(hs_.zero_copy_qual),
                    "packed_upload": bool(hs_.packed_upload),
-                   "upload": ("2-bit planes built by the host threads (csrc/gf_pack.cpp), ASCII left in pinned memory for the "
-                              "survivors" if hs_.packed_upload else "ASCII sequence arenas"),
+                   "upload": {0: "ASCII sequence arenas copied", 1: "every chunk as 2-bit planes built by the host threads",
+                              2: "some chunks as 2-bit planes built by the host threads (csrc/gf_pack.cpp) while the copy engine "
+                                 "moves the others as ASCII; the ASCII stays in pinned memory for the survivors"}[int(hs_.packed_upload)],
+                   "ms_host_pack_per_step": float(hs_.ms_host_pack),
                    "pack_threads": int(os.environ.get("GF_PACK_THREADS", 0)) or cpu_threads(),
                    "ms_per_call_median_ascii_upload": ascii_ms,
                    "parity": e2e_parity,

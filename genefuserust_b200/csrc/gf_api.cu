@@ -205,9 +205,9 @@ int gf_index_create(const gf_gene_span* genes, uint32_t n_genes, const gf_params
         for (auto& s : idx->stage)
             ok = ok && cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && cudaMallocHost((void**)&idx->h_slots, sizeof(GfHostSlot) * 3) == cudaSuccess;
+        ok = ok && cudaMallocHost((void**)&idx->h_slots, sizeof(GfHostSlot) * (GF_STAGES + 1)) == cudaSuccess;
         if (!ok) { rc = fail(GF_E_CUDA, "event / pinned allocation failed"); break; }
-        memset(idx->h_slots, 0, sizeof(GfHostSlot) * 3);
+        memset(idx->h_slots, 0, sizeof(GfHostSlot) * (GF_STAGES + 1));
         rc = gf_build_index_device(idx, genes, n_genes);
     } while (0);
     if (rc != GF_OK) {
@@ -352,33 +352,73 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
         zs2 = pe ? mapped(in->seq2) : nullptr;
         if (!zs1 || (pe && !zs2)) zs1 = zs2 = nullptr;
     }
-    const bool packed = zs1 != nullptr;
+    const bool can_pack = zs1 != nullptr;
+    const bool pack_all = can_pack && gf_pack_forced();
     float ms_pack = 0;
+    uint64_t n_packed_chunks = 0;
     /* pipeline chunks.  List mode: a chunk costs nh rounds of launches, so chunks are larger (the upload is a smaller share of a
      * chunk anyway).  Packed upload: twice the size (the per-chunk work of the issuing thread is not hidden behind a copy) */
-    uint64_t chunk_bytes = CHUNK_TARGET_BYTES * std::min<uint32_t>(nh, 4u) * (packed ? 2u : 1u);
+    uint64_t chunk_bytes = CHUNK_TARGET_BYTES * std::min<uint32_t>(nh, 4u) * (can_pack ? 2u : 1u);
     if (const char* e = getenv("GF_CHUNK_MB")) { long v = atol(e); if (v >= 1 && v <= 65536) chunk_bytes = (uint64_t)v << 20; }
     uint64_t n_chunks = std::max<uint64_t>(1, (2 * total_bytes + chunk_bytes - 1) / chunk_bytes);
     n_chunks = std::min<uint64_t>(n_chunks, n);
     const uint64_t per = (n + n_chunks - 1) / n_chunks;
     n_chunks = (n + per - 1) / per;
 
-    for (uint32_t h = 0; h < nh; h++) hs[h]->stats.packed_upload = packed ? 1u : 0u;
     for (uint32_t h = 0; h < nh; h++) hs[h]->stats.zero_copy_qual = zc ? 1u : 0u;
 
-    auto issue = [&](uint64_t k) -> int {
-        GfStage& s = idx->stage[k & 1];
-        const uint64_t lo = k * per, hi = std::min(n, lo + per), cn = hi - lo;
-        if (check_per_chunk && !packed) { /* (the packing threads check the offsets they read anyway) */
-            uint64_t mx = 0;
-            int r = scan_offsets(off1 + lo, pe ? off2 + lo : nullptr, cn, max_len, &mx, 1); /* inline: ~0.3 ms per chunk */
-            if (r != GF_OK) return r;
+    /* Which chunks are packed?  The packers (host cores, memory-bound) and the copy engine (PCIe) are two resources that can
+     * work side by side: a packed chunk costs host time and little copy time, an ASCII chunk no host time and three times the
+     * copy time.  Up to GF_STAGES chunks are in flight; a chunk is packed when the copies already queued keep the copy engine
+     * busy for at least as long as packing it takes — so the engine never waits for the packers and the packers never pack
+     * what the engine could have fetched in the meantime.  Few cores (many ranks on one host) => mostly ASCII chunks; many
+     * cores => mostly packed ones.  Times are estimates (bytes / nominal rates, packing measured as it goes): the rule corrects
+     * itself because it looks at what is actually still queued (cudaEventQuery). */
+    struct InFlight { cudaEvent_t copied; double copy_ms; };
+    std::vector<InFlight> in_flight;
+    double pack_ms_per_byte = 1.0 / (5.0e6 * std::max(1, gf_pack_threads())); /* first guess: 5 GB/s per packing thread */
+    constexpr double COPY_BYTES_PER_MS = 45.0e6;
+    auto queued_copy_ms = [&]() {
+        double t = 0;
+        for (size_t i = 0; i < in_flight.size();) {
+            if (cudaEventQuery(in_flight[i].copied) == cudaSuccess) { in_flight[i] = in_flight.back(); in_flight.pop_back(); }
+            else { t += in_flight[i].copy_ms; i++; }
         }
-        const uint64_t b1 = off1[lo], e1 = off1[hi];
-        cudaStream_t cs = idx->copy_stream;
+        cudaGetLastError(); /* cudaErrorNotReady is not an error here */
+        return t;
+    };
+
+    /* a chunk in two steps: begin_chunk decides how it is uploaded and, when it is packed, starts the packing threads;
+     * enqueue_chunk waits for them and issues its copies and launches.  begin_chunk(k + 1) comes BEFORE enqueue_chunk(k): the
+     * issuing thread's own work on chunk k (some thirty driver calls) runs while chunk k + 1 is being packed. */
+    struct ChunkPlan {
+        bool packed = false, job = false;
         GfPackMate pm[2];
-        if (packed) {
-            for (int m = 0; m < (pe ? 2 : 1); m++) {
+        uint64_t ascii_bytes = 0;
+    };
+    ChunkPlan plans[GF_STAGES];
+    auto begin_chunk = [&](uint64_t k, double copy_ms_not_yet_queued) -> int {
+        GfStage& s = idx->stage[k % GF_STAGES];
+        ChunkPlan& c = plans[k % GF_STAGES];
+        const uint64_t lo = k * per, hi = std::min(n, lo + per), cn = hi - lo;
+        c.ascii_bytes = (off1[hi] - off1[lo]) + (pe ? off2[hi] - off2[lo] : 0);
+        c.packed = can_pack && (pack_all || queued_copy_ms() + copy_ms_not_yet_queued >= pack_ms_per_byte * (double)c.ascii_bytes);
+        c.job = false;
+        const int nm = pe ? 2 : 1;
+        if (can_pack || check_per_chunk) {
+            for (int m = 0; m < nm; m++) {
+                const uint64_t* off = m ? off2 : off1;
+                c.pm[m] = GfPackMate{};
+                c.pm[m].seq = (m ? in->seq2 : in->seq1) + off[lo];
+                c.pm[m].off = off + lo;
+                c.pm[m].off_base = off[lo];
+                c.pm[m].n = cn;
+                c.pm[m].mate2 = m == 1;
+                c.pm[m].max_len = max_len;
+            }
+        }
+        if (c.packed) {
+            for (int m = 0; m < nm; m++) {
                 const uint64_t* off = m ? off2 : off1;
                 const uint64_t bytes = off[hi] - off[lo];
                 const size_t wcap = sizeof(uint32_t) * 2 * (size_t)(bytes / 32 + cn + 1); /* >= 2 * sum ceil(len / 32) */
@@ -390,23 +430,54 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
                 GF_CUDA_TRY(s.pkx[m].reserve(wcap));
                 GF_CUDA_TRY(s.pko[m].reserve(sizeof(uint32_t) * cn));
                 GF_CUDA_TRY(s.pxo[m].reserve(sizeof(uint32_t) * cn));
-                pm[m] = GfPackMate{};
-                pm[m].seq = (m ? in->seq2 : in->seq1) + off[lo];
-                pm[m].off = off + lo;
-                pm[m].off_base = off[lo];
-                pm[m].n = cn;
-                pm[m].mate2 = m == 1;
-                pm[m].max_len = max_len;
-                pm[m].words = s.h_pk[m].as<uint32_t>();
-                pm[m].woff = s.h_pko[m].as<uint32_t>();
-                pm[m].xwords = s.h_pkx[m].as<uint32_t>();
-                pm[m].xoff = s.h_pxo[m].as<uint32_t>();
+                c.pm[m].words = s.h_pk[m].as<uint32_t>();
+                c.pm[m].woff = s.h_pko[m].as<uint32_t>();
+                c.pm[m].xwords = s.h_pkx[m].as<uint32_t>();
+                c.pm[m].xoff = s.h_pxo[m].as<uint32_t>();
             }
-            const auto t_pack = std::chrono::steady_clock::now();
-            gf_pack_chunk(pm, pe ? 2 : 1); /* all host threads; the device works on the chunk before meanwhile */
-            ms_pack += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_pack).count();
-            if (pm[0].bad_offsets || (pe && pm[1].bad_offsets))
-                return fail(GF_E_INVALID, "offsets are not ascending, or a read is longer than max_len / the kernel capacity");
+            gf_pack_start(c.pm, nm, false); /* the packing threads; the device works on the chunks before meanwhile */
+            c.job = true;
+        } else if (check_per_chunk) { /* (a packed chunk is checked by the packing threads: they read the offsets anyway) */
+            if (can_pack) {
+                gf_pack_start(c.pm, nm, true);
+                c.job = true;
+            } else {
+                uint64_t mx = 0;
+                int r = scan_offsets(off1 + lo, pe ? off2 + lo : nullptr, cn, max_len, &mx, 1); /* inline: ~0.3 ms per chunk */
+                if (r != GF_OK) return r;
+            }
+        }
+        return GF_OK;
+    };
+    auto chunk_copy_ms = [&](uint64_t k) { /* estimate, for the chunk that is about to be queued */
+        const ChunkPlan& c = plans[k % GF_STAGES];
+        return (double)c.ascii_bytes * (c.packed ? 0.37 : 1.0) / COPY_BYTES_PER_MS;
+    };
+    auto finish_pack = [&](uint64_t k) -> int {
+        ChunkPlan& c = plans[k % GF_STAGES];
+        if (!c.job) return GF_OK;
+        const float ms_job = gf_pack_wait();
+        c.job = false;
+        if (c.packed) {
+            ms_pack += ms_job;
+            n_packed_chunks++;
+            pack_ms_per_byte = 0.5 * pack_ms_per_byte + 0.5 * (double)ms_job / (double)std::max<uint64_t>(c.ascii_bytes, 1);
+        }
+        if (c.pm[0].bad_offsets || (pe && c.pm[1].bad_offsets))
+            return fail(GF_E_INVALID, "offsets are not ascending, or a read is longer than max_len / the kernel capacity");
+        return GF_OK;
+    };
+
+    auto enqueue_chunk = [&](uint64_t k) -> int {
+        GfStage& s = idx->stage[k % GF_STAGES];
+        ChunkPlan& c = plans[k % GF_STAGES];
+        const bool packed = c.packed;
+        const GfPackMate* pm = c.pm;
+        const uint64_t lo = k * per, hi = std::min(n, lo + per), cn = hi - lo;
+        const uint64_t b1 = off1[lo], e1 = off1[hi];
+        const uint64_t h2d_before = h2d;
+        cudaStream_t cs = idx->copy_stream;
+        if (packed) {
             for (int m = 0; m < (pe ? 2 : 1); m++) {
                 GF_CUDA_TRY(cudaMemcpyAsync(s.pk[m].p, s.h_pk[m].p, sizeof(uint32_t) * pm[m].n_words, cudaMemcpyHostToDevice, cs));
                 GF_CUDA_TRY(cudaMemcpyAsync(s.pko[m].p, s.h_pko[m].p, sizeof(uint32_t) * cn, cudaMemcpyHostToDevice, cs));
@@ -472,18 +543,19 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
             db.bytes2 = e2 - b2;
         }
         GF_CUDA_TRY(cudaEventRecord(s.copied, cs));
+        in_flight.push_back(InFlight{s.copied, (double)(h2d - h2d_before) / COPY_BYTES_PER_MS});
         s.n = cn;
         s.pair_base = lo;
         GF_CUDA_TRY(cudaStreamWaitEvent(idx->stream, s.copied, 0));
         for (uint32_t h = 0; h < nh; h++) {
-            GfStage& sh = hs[h]->stage[k & 1];
+            GfStage& sh = hs[h]->stage[k % GF_STAGES];
             sh.out_cap = (pe ? 2 : 1) * cn;
             GF_CUDA_TRY(sh.out.reserve(sizeof(gf_match) * sh.out_cap));
             GF_CUDA_TRY(sh.nout.reserve(2 * sizeof(unsigned long long)));
             int r = gf_map_device_batch(hs[h], db, sh.out.as<gf_match>(), sh.out_cap, sh.nout.as<unsigned long long>(),
                                         idx->stream, nullptr, true, h ? idx : nullptr);
             if (r != GF_OK) return r;
-            GfHostSlot* hsl = &hs[h]->h_slots[k & 1];
+            GfHostSlot* hsl = &hs[h]->h_slots[k % GF_STAGES];
             if (hs[h]->out_mode) { /* per-record filters + order keys on the device, before the records leave it */
                 GF_CUDA_TRY(sh.out2.reserve(sizeof(gf_match) * sh.out_cap));
                 GF_CUDA_TRY(sh.keys.reserve(sizeof(unsigned long long) * sh.out_cap));
@@ -503,10 +575,10 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
         return GF_OK;
     };
     auto collect = [&](uint64_t k) -> int {
-        GF_CUDA_TRY(cudaEventSynchronize(idx->stage[k & 1].done));
+        GF_CUDA_TRY(cudaEventSynchronize(idx->stage[k % GF_STAGES].done));
         for (uint32_t h = 0; h < nh; h++) {
-            GfStage& sh = hs[h]->stage[k & 1];
-            GfHostSlot* hsl = &hs[h]->h_slots[k & 1];
+            GfStage& sh = hs[h]->stage[k % GF_STAGES];
+            GfHostSlot* hsl = &hs[h]->h_slots[k % GF_STAGES];
             int r = check_flags(*hsl);
             if (r != GF_OK) return r;
             accumulate(hs[h]->stats, *hsl);
@@ -530,11 +602,22 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
         return GF_OK;
     };
 
-    int rc = issue(0);
+    /* up to GF_STAGES chunks are in flight; a chunk's results are collected when its stage is needed again (or at the end) */
+    const uint64_t depth = GF_STAGES;
+    uint64_t collected = 0;
+    int rc = begin_chunk(0, 0.0);
     for (uint64_t k = 0; rc == GF_OK && k < n_chunks; k++) {
-        if (k + 1 < n_chunks) rc = issue(k + 1);
-        if (rc == GF_OK) rc = collect(k);
+        rc = finish_pack(k);
+        if (rc != GF_OK) break;
+        if (k + 1 < n_chunks) {
+            while (rc == GF_OK && k + 1 - collected >= depth) rc = collect(collected++); /* chunk k + 1 reuses that stage */
+            if (rc == GF_OK) rc = begin_chunk(k + 1, chunk_copy_ms(k));
+        }
+        if (rc == GF_OK) rc = enqueue_chunk(k);
     }
+    for (ChunkPlan& c : plans)
+        if (c.job) { gf_pack_wait(); c.job = false; } /* (error paths: never leave the packing threads running) */
+    while (rc == GF_OK && collected < n_chunks) rc = collect(collected++);
     if (rc != GF_OK) {
         cudaStreamSynchronize(idx->stream);
         cudaStreamSynchronize(idx->copy_stream);
@@ -552,6 +635,7 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
         st.kernel_launches = hs[h]->launches - launches0[h];
         st.h2d_bytes = h ? 0 : h2d;
         st.ms_host_pack = h ? 0.f : ms_pack;
+        st.packed_upload = n_packed_chunks == 0 ? 0u : (n_packed_chunks == n_chunks ? 1u : 2u);
         st.d2h_bytes = d2h[h];
         if (h) { /* k_prep ran once, on hs[0] */
             st.n_sequences = hs[0]->stats.n_sequences;
@@ -648,7 +732,7 @@ int gf_map_pairs_device_list(gf_index* const* idx, uint32_t n_idx, const gf_batc
     if (rc != GF_OK) return rc;
     for (uint32_t h = 0; h < n_idx; h++) {
         gf_index* x = idx[h];
-        GfHostSlot* hsl = &x->h_slots[2];
+        GfHostSlot* hsl = &x->h_slots[GF_SLOT_DEVICE];
         GF_CUDA_TRY(cudaMemcpyAsync(&hsl->counters, x->ws_counters.p, sizeof(GfMapCounters), cudaMemcpyDeviceToHost, st));
         GF_CUDA_TRY(cudaMemcpyAsync(&hsl->n_out, d_n_out[h], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         GF_CUDA_TRY(cudaEventRecord(x->ev_end, st));
@@ -692,7 +776,7 @@ int gf_map_pairs_device(gf_index* idx, const gf_batch* in_dev, gf_match* d_out, 
     unsigned long long* nout1 = (unsigned long long*)d_n_out;
     rc = gf_map_device_batches(&idx, 1, db, &d_out, out_cap, &nout1, st);
     if (rc != GF_OK) return rc;
-    GfHostSlot* h = &idx->h_slots[2];
+    GfHostSlot* h = &idx->h_slots[GF_SLOT_DEVICE];
     GF_CUDA_TRY(cudaMemcpyAsync(&h->counters, idx->ws_counters.p, sizeof(GfMapCounters), cudaMemcpyDeviceToHost, st));
     GF_CUDA_TRY(cudaMemcpyAsync(&h->n_out, d_n_out, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     GF_CUDA_TRY(cudaEventRecord(idx->ev_end, st));
@@ -827,7 +911,7 @@ int gf_get_map_stats(const gf_index* cidx, gf_map_stats* out) {
     if (idx->stats_pending) {
         GF_CUDA_TRY(cudaSetDevice(idx->device));
         GF_CUDA_TRY(cudaEventSynchronize(idx->ev_end));
-        const GfHostSlot& h = idx->h_slots[2];
+        const GfHostSlot& h = idx->h_slots[GF_SLOT_DEVICE];
         accumulate(idx->stats, h);
         /* per-stage device time: the sum over the chunks of the call, from the events between the launches */
         gf_map_stats& S = idx->stats;

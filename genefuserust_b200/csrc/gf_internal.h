@@ -83,6 +83,9 @@ struct GfPinned {
     T* as() const { return (T*)p; }
 };
 
+constexpr int GF_STAGES = 4;      /* chunks of a host batch in flight at once */
+constexpr int GF_SLOT_DEVICE = GF_STAGES;
+
 struct GfStage { /* one in-flight chunk of a host batch */
     GfBuf seq1, qual1, off1, seq2, qual2, off2, out, nout;
     /* packed upload (gf_pack.cpp), per mate: plane words, their per-read offsets, exception words, per-read exception offsets —
@@ -141,8 +144,8 @@ struct gf_index {
     GfFastqTable fq[2];
     GfBuf ws_seq_words, ws_seq_meta, ws_seq_seed, ws_seq_lists; /* split screen pipeline (gf_screen_split.cuh): sequence store
                                                                   (plane words, meta, seeds); counters + the two class lists */
-    GfStage stage[2];
-    GfHostSlot* h_slots = nullptr; /* [3]: two pipeline stages + the device-batch path */
+    GfStage stage[GF_STAGES];
+    GfHostSlot* h_slots = nullptr; /* [GF_STAGES + 1]: the pipeline stages + the device-batch path (GF_SLOT_DEVICE) */
     bool stats_pending = false;    /* h_slots[2] is being written by an unsynchronised device-batch call */
     uint64_t pending_pairs = 0;
     gf_map_stats stats{};

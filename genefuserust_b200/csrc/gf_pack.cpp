@@ -25,6 +25,7 @@
 #include <immintrin.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
@@ -42,11 +43,12 @@ int g_prefetch = 8192; /* bytes ahead of the read being packed (GF_PACK_PREFETCH
                           pack 10 M pairs in 52.7 ms without, 46.3 ms at 512, 32.4 ms at 8192: the arenas are 4 KB pages in a guest,
                           the hardware prefetchers stop at every page end) */
 
-/* persistent workers: a pipeline chunk is packed in ~1 ms, thread start-up would cost as much */
+/* persistent workers: a pipeline chunk is packed in a millisecond or two, thread start-up would cost as much.  The caller
+ * starts a job and does its own work (issuing the copies and launches of the chunk before) until it needs the result. */
 class Pool {
 public:
     explicit Pool(int n) : n_(n) {
-        for (int t = 1; t < n_; t++) th_.emplace_back([this, t] { worker(t); });
+        for (int t = 0; t < n_; t++) th_.emplace_back([this, t] { worker(t); });
     }
     ~Pool() {
         {
@@ -59,24 +61,27 @@ public:
         for (auto& t : th_) t.join();
     }
     int size() const { return n_; }
-    /* fn(tid) on every thread (the caller is thread 0); returns when all are done */
-    void run(const std::function<void(int)>& fn) {
+    /* fn(tid) on every worker; returns at once */
+    void start(const std::function<void(int)>* fn) {
         {
             std::lock_guard<std::mutex> lk(mu_);
-            fn_ = &fn;
-            left_ = n_ - 1;
+            fn_ = fn;
+            left_ = n_;
             aleft_.store(left_, std::memory_order_release);
             gen_++;
             agen_.store(gen_, std::memory_order_release);
         }
         cv_.notify_all();
-        fn(0);
+    }
+    /* until the job is done; returns the steady-clock time at which the last worker finished */
+    std::chrono::steady_clock::time_point wait() {
         for (int spin = 0; spin < 20000 && aleft_.load(std::memory_order_acquire) != 0; spin++) _mm_pause();
         std::unique_lock<std::mutex> lk(mu_);
         done_.wait(lk, [this] { return left_ == 0; });
         fn_ = nullptr;
+        return t_done_;
     }
-    /* all threads of the running job meet here */
+    /* all workers of the running job meet here */
     void barrier() {
         const int g = bar_gen_.load(std::memory_order_acquire);
         if (bar_cnt_.fetch_add(1, std::memory_order_acq_rel) + 1 == n_) {
@@ -105,6 +110,7 @@ private:
             {
                 std::lock_guard<std::mutex> lk(mu_);
                 --left_;
+                if (left_ == 0) t_done_ = std::chrono::steady_clock::now();
                 aleft_.store(left_, std::memory_order_release);
                 if (left_ == 0) done_.notify_one();
             }
@@ -118,6 +124,7 @@ private:
     uint64_t gen_ = 0;
     int left_ = 0;
     bool stop_ = false;
+    std::chrono::steady_clock::time_point t_done_{};
     std::atomic<int> bar_cnt_{0}, bar_gen_{0};
     std::atomic<int> aleft_{0};
     std::atomic<uint64_t> agen_{0}; /* copy of gen_ the workers can poll without the lock */
@@ -207,17 +214,63 @@ bool gf_pack_available() {
         return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
     }();
     const char* e = getenv("GF_HOST_PACK"); /* read per call: tests switch it */
-    if (!cpu_ok || (e && atoi(e) == 0)) return false;
-    /* with fewer than 8 packing threads the copy of the ASCII arenas is the faster way (measured on a 16-core B200 host, 10 M
-     * pairs 2x150: copy 64 ms; packed 8 threads 50 ms, 4 threads 97 ms) — e.g. many ranks sharing few cores.  GF_HOST_PACK=1
-     * forces it (tests). */
-    return (e && atoi(e) == 1) || want_threads() >= 8;
+    return cpu_ok && !(e && atoi(e) == 0);
+}
+
+bool gf_pack_forced() {
+    const char* e = getenv("GF_HOST_PACK");
+    return e && atoi(e) == 1;
 }
 
 int gf_pack_threads() { return want_threads(); }
 
-void gf_pack_chunk(GfPackMate* mates, int n_mates) { /* n_mates <= 2 */
-    std::lock_guard<std::mutex> lk(g_pool_mu);
+/* the job in flight (one at a time: g_pool_mu is held from gf_pack_start to gf_pack_wait) */
+struct PackJob {
+    GfPackMate* mates = nullptr;
+    int n_mates = 0, nt = 1;
+    bool check_only = false;
+    std::vector<uint64_t> sums;
+    std::atomic<uint32_t> bad[2];
+    std::function<void(int)> fn;
+    std::chrono::steady_clock::time_point t_start{};
+};
+static PackJob g_job;
+
+static void pack_worker(int t) {
+    PackJob& J = g_job;
+    const int nt = J.nt;
+    /* pass A: plane words of this thread's reads (from the offsets alone) + the offset check */
+    for (int k = 0; k < J.n_mates; k++) {
+        const GfPackMate& m = J.mates[k];
+        const uint64_t a = m.n * (uint64_t)t / nt, b = m.n * (uint64_t)(t + 1) / nt;
+        uint64_t s = 0, bad = 0;
+        for (uint64_t i = a; i < b; i++) {
+            const uint64_t len = m.off[i + 1] - m.off[i]; /* wraps to a huge value when the offsets descend */
+            bad |= len > m.max_len;
+            s += (len + 31) >> 5;
+        }
+        J.sums[(size_t)k * nt + t] = s;
+        if (bad) J.bad[k].store(1, std::memory_order_relaxed);
+    }
+    if (J.check_only) return;
+    g_pool->barrier();
+    for (int k = 0; k < J.n_mates; k++)
+        if (J.bad[k].load(std::memory_order_relaxed)) return; /* every thread sees the same flags after the barrier */
+    /* pass B: pack.  A thread's exception words start where its plane words would if every read had them: the regions
+     * never overlap, and only their used parts are copied to the device */
+    for (int k = 0; k < J.n_mates; k++) {
+        GfPackMate& m = J.mates[k];
+        const uint64_t a = m.n * (uint64_t)t / nt, b = m.n * (uint64_t)(t + 1) / nt;
+        uint64_t base = 0;
+        for (int u = 0; u < t; u++) base += J.sums[(size_t)k * nt + u];
+        m.xregion_start[t] = 2 * base;
+        pack_range(&m, a, b, base, 2 * base, &m.xregion_used[t]);
+        if (t == nt - 1) m.n_words = 2 * (base + J.sums[(size_t)k * nt + t]);
+    }
+}
+
+void gf_pack_start(GfPackMate* mates, int n_mates, bool check_only) { /* n_mates <= 2 */
+    g_pool_mu.lock();
     g_prefetch = 8192;
     if (const char* e = getenv("GF_PACK_PREFETCH")) { const int v = atoi(e); if (v >= 0 && v <= (1 << 20)) g_prefetch = v; }
     const int nt = want_threads();
@@ -225,41 +278,34 @@ void gf_pack_chunk(GfPackMate* mates, int n_mates) { /* n_mates <= 2 */
         delete g_pool;
         g_pool = new Pool(nt);
     }
-    Pool* pool = g_pool;
-    std::vector<uint64_t> sums((size_t)n_mates * nt, 0);
-    std::atomic<uint32_t> bad_flag[2];
-    bad_flag[0].store(0);
-    bad_flag[1].store(0);
+    PackJob& J = g_job;
+    J.mates = mates;
+    J.n_mates = n_mates;
+    J.nt = nt;
+    J.check_only = check_only;
+    J.sums.assign((size_t)n_mates * nt, 0);
+    J.bad[0].store(0);
+    J.bad[1].store(0);
     for (int k = 0; k < n_mates; k++) mates[k].n_threads = nt;
-    const std::function<void(int)> job = [&](int t) {
-        /* pass A: plane words of this thread's reads (from the offsets alone) */
-        for (int k = 0; k < n_mates; k++) {
-            const GfPackMate& m = mates[k];
-            const uint64_t a = m.n * (uint64_t)t / nt, b = m.n * (uint64_t)(t + 1) / nt;
-            uint64_t s = 0, bad = 0;
-            for (uint64_t i = a; i < b; i++) {
-                const uint64_t len = m.off[i + 1] - m.off[i]; /* wraps to a huge value when the offsets descend */
-                bad |= len > m.max_len;
-                s += (len + 31) >> 5;
-            }
-            sums[(size_t)k * nt + t] = s;
-            if (bad) bad_flag[k].store(1, std::memory_order_relaxed);
-        }
-        pool->barrier();
-        for (int k = 0; k < n_mates; k++)
-            if (bad_flag[k].load(std::memory_order_relaxed)) return; /* every thread sees the same flags after the barrier */
-        /* pass B: pack.  A thread's exception words start where its plane words would if every read had them: the regions
-         * never overlap, and only their used parts are copied to the device */
-        for (int k = 0; k < n_mates; k++) {
-            GfPackMate& m = mates[k];
-            const uint64_t a = m.n * (uint64_t)t / nt, b = m.n * (uint64_t)(t + 1) / nt;
-            uint64_t base = 0;
-            for (int u = 0; u < t; u++) base += sums[(size_t)k * nt + u];
-            m.xregion_start[t] = 2 * base;
-            pack_range(&m, a, b, base, 2 * base, &m.xregion_used[t]);
-            if (t == nt - 1) m.n_words = 2 * (base + sums[(size_t)k * nt + t]);
-        }
-    };
-    pool->run(job);
-    for (int k = 0; k < n_mates; k++) mates[k].bad_offsets = bad_flag[k].load();
+    if (!J.fn) J.fn = pack_worker;
+    J.t_start = std::chrono::steady_clock::now();
+    g_pool->start(&J.fn);
+}
+
+float gf_pack_wait() {
+    const auto t_done = g_pool->wait();
+    PackJob& J = g_job;
+    for (int k = 0; k < J.n_mates; k++) J.mates[k].bad_offsets = J.bad[k].load();
+    const float ms = std::chrono::duration<float, std::milli>(t_done - J.t_start).count();
+    g_pool_mu.unlock();
+    return ms;
+}
+
+void gf_pack_chunk(GfPackMate* mates, int n_mates) {
+    gf_pack_start(mates, n_mates, false);
+    gf_pack_wait();
+}
+void gf_pack_check_offsets(GfPackMate* mates, int n_mates) {
+    gf_pack_start(mates, n_mates, true);
+    gf_pack_wait();
 }

@@ -173,10 +173,12 @@ typedef struct gf_map_stats {
     uint64_t d2h_bytes;      /* bytes copied device -> host */
     uint32_t zero_copy_qual; /* 1 = the quality arenas were pinned host memory and were NOT copied: the kernels
                                 read the few quality bytes fast_merge depends on directly over PCIe */
-    uint32_t packed_upload;  /* 1 = sequence AND quality arenas were pinned host memory, reads <= 256 bases and the host has
-                                AVX-512BW: the host threads built the reads' 2-bit planes and only those were copied (about a
-                                third of the bytes); the few reads that survive the screen are fetched from the pinned arenas on
-                                demand.  GF_HOST_PACK=0 disables this, GF_PACK_THREADS sets the number of packing threads. */
+    uint32_t packed_upload;  /* != 0: sequence AND quality arenas were pinned host memory, reads <= 256 bases and the host has
+                                AVX-512BW: for some (2) or all (1) pipeline chunks the host threads built the reads' 2-bit planes
+                                and only those were copied (about a third of the bytes) while the copy engine was busy with
+                                other chunks; the few reads that survive the screen are fetched from the pinned arenas on
+                                demand.  GF_HOST_PACK=0 disables this, =1 packs every chunk; GF_PACK_THREADS sets the number of
+                                packing threads. */
     /* the four launches ms_screen is made of (split screen, reads <= 256 bases; 0 otherwise).  gf_map_pairs (chunked
      * host path): the last chunk only, like every other ms_* field there. */
     float ms_prep;           /* k_prep: ASCII -> bit-planes, fast_merge, sequence store */

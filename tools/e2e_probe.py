@@ -46,20 +46,18 @@ def run(tag, hint, env):
     st = gf_map_stats()
     lib.gf_get_map_stats(h, C.byref(st))
     ts.sort()
-    print(f"{tag:44s} median {1e3 * ts[4]:7.2f} ms  min {1e3 * ts[0]:7.2f}  device-span {st.ms_total:7.2f} ms  pack {st.ms_host_pack:6.2f} ms  "
+    print(f"{tag:44s} median {1e3 * ts[4]:7.2f} ms  min {1e3 * ts[0]:7.2f}  device-span {st.ms_total:7.2f} ms  pack {st.ms_host_pack:6.2f} ms (mode {st.packed_upload})  "
           f"h2d {st.h2d_bytes / 1e9:.2f} GB  -> {st.h2d_bytes / ts[4] / 1e9:5.1f} GB/s  {P / ts[4] / 1e6:6.1f} M pairs/s", flush=True)
     for k in env:
         os.environ.pop(k, None)
 
 
-run("packed upload (default threads)", 150, {})
+run("hybrid upload (default)", 150, {})
 for t in ("4", "8", "12", "16"):
-    run(f"packed upload, {t} threads", 150, {"GF_PACK_THREADS": t})
-for pf in ("0", "512", "4096", "8192", "16384"):
-    for t in ("8", "12"):
-        run(f"packed upload, {t} threads, prefetch {pf} B ahead", 150, {"GF_PACK_THREADS": t, "GF_PACK_PREFETCH": pf})
-for mb in ("48", "384", "1536"):
-    run(f"packed upload, default threads, chunk {mb} MB", 150, {"GF_CHUNK_MB": mb})
+    run(f"hybrid upload, {t} packing threads", 150, {"GF_PACK_THREADS": t})
+for mb in ("192", "768"):
+    run(f"hybrid upload, chunk {mb} MB", 150, {"GF_CHUNK_MB": mb})
+run("every chunk packed", 150, {"GF_HOST_PACK": "1"})
 os.environ["GF_HOST_PACK"] = "0"
 run("hint=150 (per-chunk check), zero-copy qual", 150, {})
 run("hint=0 (pre-scan), zero-copy qual", 0, {})
