@@ -74,3 +74,16 @@ print("matcher (device contigs)", mt.remove_alignables([b"ACGT" * 20])[1].astupl
 mt.close()
 m.close()
 print("ok")
+# packed / hybrid upload from pinned arenas (ragged reads with N and lower case), several chunks
+rng = random.Random(3)
+r1 = [(bytes(rng.choice(b"ACGTACGTACGTNacgt") for _ in range(n)), b"E" * n) for n in [0, 1, 31, 32, 33, 64, 65, 100, 150, 151, 200, 256] * 300]
+r2 = [(bytes(rng.choice(b"ACGTACGTACGTNacgt") for _ in range(n)), b"E" * n) for n in [256, 200, 151, 150, 100, 65, 64, 33, 32, 31, 1, 0] * 300]
+b = ReadBatch.from_reads(r1, r2)
+pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+bp = ReadBatch(pin(b.seq1), pin(b.qual1), pin(b.off1.view(np.int64)).view(np.uint64), pin(b.seq2), pin(b.qual2), pin(b.off2.view(np.int64)).view(np.uint64))
+bp.max_len = b.max_len
+os.environ["GF_CHUNK_MB"] = "1"
+for mode in ("0", "1", "2"):
+    os.environ["GF_HOST_PACK"] = mode
+    print("upload mode", mode, len(m.scan_pair_end(bp)), m.map_stats().packed_upload)
+del os.environ["GF_HOST_PACK"], os.environ["GF_CHUNK_MB"]
