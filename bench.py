@@ -775,6 +775,58 @@ def main():
             if not rec["parity"]["identical"] or nrec.value != P:
                 failures.append("fastq: GPU records differ from the oracle's")
         configs["fastq_text"] = rec
+        # ---- the same reads as .fq.gz files fed as byte streams (gf_fastq_stream_*, SURVEY 8(f) #2: fastq_reader.rs:39-69,149-179):
+        # one gzip member per file (inflate is sequential: one host thread per mate) and BGZF (what bgzip / bcl2fastq write:
+        # members of <= 64 KB, inflated by all host threads)
+        import gzip as _gzip
+        from genefuserust_b200.host import bgzf_compress
+        Pz = 250_000                                   # (compressing the bench input in Python is the slow part)
+        rec_bytes = t1.numel() // P
+        raw1, raw2 = bytes(t1.numpy()[:Pz * rec_bytes]), bytes(t2.numpy()[:Pz * rec_bytes])
+        want_z = None
+        if oracle is not None:
+            want_z = want[want["pair_idx"] < Pz]
+        gz_rec = {"workload": f"{Pz} pairs 2x150 as two .fq.gz byte streams through gf_fastq_stream_feed (8 MiB pieces): host "
+                              "inflate + H2D of the text + record splitting + mapping", "pairs": Pz, "unit": UNIT}
+        for kind, enc in (("gzip_single_member", lambda d: _gzip.compress(d, compresslevel=1)), ("bgzf", lambda d: bgzf_compress(d))):
+            e1, e2 = enc(raw1), enc(raw2)
+            # one stream, the files fed three times over (a gzip file may be several files concatenated: MultiGzDecoder): the
+            # first pass pays for the pinned text buffers, the passes after it are what a long file costs per record
+            sh = C.c_void_p()
+            if lib.gf_fastq_stream_create(h, 1, 1, 0, C.byref(sh)) != 0:
+                raise RuntimeError(lib.gf_last_error().decode())
+            piece = 8 << 20
+            passes = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                for p0 in range(0, max(len(e1), len(e2)), piece):
+                    a1, a2 = e1[p0:p0 + piece], e2[p0:p0 + piece]
+                    if lib.gf_fastq_stream_feed(sh, a1 if a1 else None, len(a1), a2 if a2 else None, len(a2)) != 0:
+                        raise RuntimeError(lib.gf_last_error().decode())
+                passes.append(time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            if lib.gf_fastq_stream_finish(sh) != 0:
+                raise RuntimeError(lib.gf_last_error().decode())
+            nz = C.c_uint64(0)
+            outz = np.zeros(3 * cap, dtype=match_dtype())
+            rcz = lib.gf_fastq_stream_take(sh, C.cast(outz.ctypes.data, C.POINTER(gf_match)), 3 * cap, C.byref(nz))
+            t_fin = time.perf_counter() - t0
+            lib.gf_fastq_stream_destroy(sh)
+            if rcz != 0:
+                raise RuntimeError(lib.gf_last_error().decode())
+            best = min(passes[1:]) + t_fin / 3      # (the text is mapped when 256 MiB have accumulated or at finish)
+            sub = {"value": Pz / best, "ms_per_pass": 1e3 * best, "ms_first_pass_incl_pinned_buffers": 1e3 * passes[0],
+                   "compressed_bytes": len(e1) + len(e2), "inflated_gbs": 2 * len(raw1) / best / 1e9}
+            if want_z is not None:
+                gotz = outz[:nz.value]
+                sub["parity"] = parity_record(gotz[gotz["pair_idx"] < Pz], want_z, Pz, f"all {Pz} records of the first pass; "
+                                              f"the three passes returned {int(nz.value)} records = 3 x {len(want_z)}")
+                if int(nz.value) != 3 * len(want_z):
+                    failures.append(f"fastq_gz {kind}: record count of the repeated passes")
+                if not sub["parity"]["identical"]:
+                    failures.append(f"fastq_gz {kind}: GPU records differ from the oracle's")
+            gz_rec[kind] = sub
+        configs["fastq_gz"] = gz_rec
         del t1, t2
 
     # -------------------------------------------------------------------------------------------- config 3: 100 M pairs, strong

@@ -12,10 +12,17 @@
  *                      (multi-member, like flate2's MultiGzDecoder, chosen by the caller from the file extension like
  *                      FastqReader::new) is inflated on host threads — one per mate — straight into the pinned text buffers,
  *                      and whole records are mapped on the device (gf_map_fastq_text: record splitting there too).
+ *                      BGZF input (blocked gzip: what bcl2fastq / bgzip write — every member is <= 64 KB and says its own
+ *                      compressed size in a 'BC' extra field and its uncompressed size in the trailer) is inflated by ALL
+ *                      host threads: the members that lie completely in the fed piece go to their final place in the text
+ *                      buffer side by side (the sizes give the offsets up front); a member cut by the end of the piece takes
+ *                      the streaming path like any other gzip member.
  */
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -223,6 +230,8 @@ struct gf_fastq_stream {
     bool z_open[2] = {false, false}, z_member_done[2] = {true, true};
     bool eof_seen[2] = {false, false};
     uint64_t records = 0, text_bytes = 0, n_calls = 0;
+    uint64_t bgzf_blocks = 0; /* members inflated on the parallel path */
+    double ms_bgzf = 0, ms_stream = 0, ms_map = 0; /* GF_DEBUG_TIMING: where the host time of the gzip path goes (mate 1's thread) */
     std::vector<gf_match> done, tmp;
     bool panic = false;
     std::mutex mu;
@@ -241,12 +250,14 @@ int fq_map_locked(gf_fastq_stream* s, bool final_chunk) {
     if (s->tmp.size() < 4096) s->tmp.resize(4096);
     uint64_t got = 0, nrec = 0, consumed[2] = {0, 0};
     int rc;
+    const auto tm0 = std::chrono::steady_clock::now();
     for (;;) {
         rc = gf_map_fastq_text(s->idx, s->text[0].p, s->text[0].fill, s->paired ? s->text[1].p : nullptr,
                                s->paired ? s->text[1].fill : 0, final_chunk, s->tmp.data(), s->tmp.size(), &got, &nrec, consumed);
         if (rc == GF_E_CAPACITY) { s->tmp.resize(got); continue; }
         break;
     }
+    s->ms_map += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tm0).count();
     if (rc != GF_OK && rc != GF_E_REF_PANIC) return rc;
     if (rc == GF_E_REF_PANIC) s->panic = true;
     for (uint64_t i = 0; i < got; i++) {
@@ -267,11 +278,57 @@ int fq_map_locked(gf_fastq_stream* s, bool final_chunk) {
     return GF_OK;
 }
 
+/* BGZF member at p (n bytes available)?  Returns its total size and uncompressed size when the whole member is there. */
+struct BgzfBlock { const uint8_t* data; uint32_t clen, isize, crc; uint64_t out; };
+bool bgzf_block_at(const uint8_t* p, uint64_t n, uint32_t* total, BgzfBlock* b) {
+    if (n < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return false;
+    const uint32_t xlen = p[10] | (p[11] << 8);
+    if (n < 12 + (uint64_t)xlen) return false;
+    uint32_t bsize = 0;
+    bool found = false;
+    for (uint32_t q = 12; q + 4 <= 12 + xlen;) { /* extra subfields: SI1 SI2 SLEN(2) data */
+        const uint32_t slen = p[q + 2] | (p[q + 3] << 8);
+        if (p[q] == 'B' && p[q + 1] == 'C' && slen == 2 && q + 6 <= 12 + xlen) { bsize = (p[q + 4] | (p[q + 5] << 8)) + 1u; found = true; }
+        q += 4 + slen;
+    }
+    if (!found || (p[3] & ~4u) || bsize < 12 + xlen + 8 || n < bsize) return false; /* other header flags: streaming path */
+    b->data = p + 12 + xlen;
+    b->clen = bsize - (12 + xlen) - 8;
+    b->crc = p[bsize - 8] | (p[bsize - 7] << 8) | (p[bsize - 6] << 16) | ((uint32_t)p[bsize - 5] << 24);
+    b->isize = p[bsize - 4] | (p[bsize - 3] << 8) | (p[bsize - 2] << 16) | ((uint32_t)p[bsize - 1] << 24);
+    if (b->isize > (1u << 16)) return false; /* not BGZF after all */
+    *total = bsize;
+    return true;
+}
+/* inflate blocks[lo, hi) to dst + blocks[i].out; false on a corrupt block */
+bool bgzf_inflate_range(const std::vector<BgzfBlock>& blocks, size_t lo, size_t hi, uint8_t* dst) {
+    z_stream z;
+    memset(&z, 0, sizeof(z));
+    if (inflateInit2(&z, -15) != Z_OK) return false;
+    bool ok = true;
+    for (size_t i = lo; i < hi && ok; i++) {
+        const BgzfBlock& b = blocks[i];
+        if (b.isize == 0) continue;
+        z.next_in = const_cast<Bytef*>(b.data);
+        z.avail_in = b.clen;
+        z.next_out = dst + b.out;
+        z.avail_out = b.isize;
+        const int zr = inflate(&z, Z_FINISH);
+        ok = zr == Z_STREAM_END && z.avail_out == 0 && (uint32_t)crc32(0L, dst + b.out, b.isize) == b.crc;
+        inflateReset(&z);
+    }
+    inflateEnd(&z);
+    return ok;
+}
+
 /* append decoded text of mate k from `in`; returns the input bytes consumed.  Stops early when the buffer reached
  * chunk_bytes (the caller maps and calls again). */
 int fq_append(gf_fastq_stream* s, int k, const uint8_t* in, uint64_t n, uint64_t* used, std::string* err) {
     PinnedArena& t = s->text[k];
     *used = 0;
+    /* the text buffer is pinned once at its full size: growing a pinned buffer step by step (allocate, copy, free) costs more
+     * than inflating what goes into it */
+    if (t.cap < s->chunk_bytes + 64 && t.reserve(s->chunk_bytes + 64) != cudaSuccess) { *err = "pinned allocation failed"; return GF_E_CUDA; }
     if (s->format == GF_FQ_PLAIN) {
         const uint64_t room = t.fill < s->chunk_bytes ? s->chunk_bytes - t.fill : 0;
         const uint64_t c = std::min(n, room);
@@ -290,9 +347,44 @@ int fq_append(gf_fastq_stream* s, int k, const uint8_t* in, uint64_t n, uint64_t
         s->z_open[k] = true;
         s->z_member_done[k] = true;
     }
-    z.next_in = const_cast<Bytef*>(in);
     uint64_t left = n;
     while (left && t.fill < s->chunk_bytes) {
+        if (s->z_member_done[k]) {
+            /* at a member boundary: as many whole BGZF members as lie in the piece and fit the buffer, all threads */
+            std::vector<BgzfBlock> blocks;
+            uint64_t pos = n - left, out = 0;
+            const uint64_t room = s->chunk_bytes - t.fill;
+            for (;;) {
+                uint32_t total = 0;
+                BgzfBlock b;
+                if (!bgzf_block_at(in + pos, n - pos, &total, &b) || out + b.isize > room) break;
+                b.out = out;
+                out += b.isize;
+                pos += total;
+                blocks.push_back(b);
+            }
+            if (!blocks.empty()) {
+                const auto tb0 = std::chrono::steady_clock::now();
+                if (t.reserve(t.fill + out + 64) != cudaSuccess) { *err = "pinned allocation failed"; return GF_E_CUDA; }
+                const size_t nb = blocks.size();
+                const unsigned want = s->paired ? std::max(1u, std::thread::hardware_concurrency() / 2) : std::max(1u, std::thread::hardware_concurrency());
+                const size_t nt = std::min<size_t>(want, (nb + 3) / 4);
+                std::vector<char> okv(nt, 1);
+                std::vector<std::thread> th;
+                uint8_t* dst = t.p + t.fill;
+                for (size_t u = 1; u < nt; u++)
+                    th.emplace_back([&, u] { okv[u] = bgzf_inflate_range(blocks, nb * u / nt, nb * (u + 1) / nt, dst) ? 1 : 0; });
+                okv[0] = bgzf_inflate_range(blocks, 0, nb / nt, dst) ? 1 : 0;
+                for (auto& x : th) x.join();
+                for (char o : okv)
+                    if (!o) { *err = std::string("gzip stream of mate ") + (k ? "2" : "1") + " is corrupt (BGZF block)"; return GF_E_INVALID; }
+                t.fill += out;
+                left = n - pos;
+                if (k == 0) { s->bgzf_blocks += nb; s->ms_bgzf += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count(); }
+                continue;
+            }
+        }
+        z.next_in = const_cast<Bytef*>(in + (n - left));
         if (t.reserve(std::min<uint64_t>(s->chunk_bytes, t.fill + (4u << 20)) + 64) != cudaSuccess) { *err = "pinned allocation failed"; return GF_E_CUDA; }
         const uint64_t room = std::min<uint64_t>(t.cap - 64, s->chunk_bytes) - t.fill;
         if (!room) break;
@@ -302,7 +394,9 @@ int fq_append(gf_fastq_stream* s, int k, const uint8_t* in, uint64_t n, uint64_t
         z.avail_out = (uInt)std::min<uint64_t>(room, 1u << 30);
         const uInt out0 = z.avail_out;
         s->z_member_done[k] = false;
+        const auto ts0 = std::chrono::steady_clock::now();
         const int zr = inflate(&z, Z_NO_FLUSH);
+        if (k == 0) s->ms_stream += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count();
         left -= in0 - z.avail_in;
         t.fill += out0 - z.avail_out;
         if (zr == Z_STREAM_END) { /* next member of a multi-member file (MultiGzDecoder, fastq_reader.rs:49-55) */
@@ -335,7 +429,14 @@ int gf_fastq_stream_create(gf_index* idx, int paired, int format, uint64_t chunk
     return GF_OK;
 }
 
-void gf_fastq_stream_destroy(gf_fastq_stream* s) { delete s; }
+void gf_fastq_stream_destroy(gf_fastq_stream* s) {
+    if (s && getenv("GF_DEBUG_TIMING"))
+        fprintf(stderr, "[gf_fastq_stream] records %llu, text bytes %llu, map calls %llu, BGZF members inflated side by side %llu; "
+                "ms: side-by-side inflate %.1f, streaming inflate %.1f, mapping %.1f\n",
+                (unsigned long long)s->records, (unsigned long long)s->text_bytes, (unsigned long long)s->n_calls,
+                (unsigned long long)s->bgzf_blocks, s->ms_bgzf, s->ms_stream, s->ms_map);
+    delete s;
+}
 
 int gf_fastq_stream_feed(gf_fastq_stream* s, const uint8_t* fq1, uint64_t n1, const uint8_t* fq2, uint64_t n2) {
     if (!s || (n1 && !fq1) || (n2 && !fq2)) return sfail(GF_E_INVALID, "NULL argument");

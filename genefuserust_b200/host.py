@@ -437,6 +437,21 @@ class PackStream:
             self.h = None
 
 
+def bgzf_compress(data, block=65280, level=1):
+    """`data` as BGZF (blocked gzip, what bgzip / bcl2fastq write): gzip members of <= 64 KB that carry their compressed size in
+    a 'BC' extra field, closed by the empty EOF member.  Harness utility for the tests and the bench."""
+    import struct
+    import zlib
+    out = []
+    for p in list(range(0, len(data), block)) + [None]:
+        raw = b"" if p is None else data[p:p + block]
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        body = co.compress(raw) + co.flush()
+        out.append(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(body) + 25) + body +
+                   struct.pack("<II", zlib.crc32(raw) & 0xFFFFFFFF, len(raw)))
+    return b"".join(out)
+
+
 class FastqStream:
     """FastqReader / FastqReaderPair as a byte stream (gf_fastq_stream_*): feed raw file bytes (plain or gzip, pieces may end
     anywhere), whole records are split and mapped on the device; records are numbered from the start of the files."""

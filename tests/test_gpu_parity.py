@@ -756,10 +756,11 @@ def test_device_batch_entry_points(host, small_panel, read_len, seed):
         m.close()
 
 
-@pytest.mark.parametrize("gz", [False, True])
+@pytest.mark.parametrize("gz", [False, True, "bgzf"])
 def test_fastq_stream_chunked_and_gzip(mappers, small_panel, host, gz, tmp_path):
     """the two FASTQ files as byte streams (gf_fastq_stream_*): pieces that end anywhere (mid-line, mid-record,
-    different piece sizes per mate), small device chunks with the tail carried over, plain and multi-member gzip; the records
+    different piece sizes per mate), small device chunks with the tail carried over, plain, multi-member gzip and BGZF (whose
+    whole members are inflated side by side by all host threads, the cut ones by the streaming decoder); the records
     must equal one gf_map_fastq call on the whole text and the oracle on the reference reader's records"""
     import gzip
     m, o = mappers
@@ -776,6 +777,8 @@ def test_fastq_stream_chunked_and_gzip(mappers, small_panel, host, gz, tmp_path)
     def enc(data, members):
         if not gz:
             return data
+        if gz == "bgzf":       # blocked gzip: the members that lie whole in a fed piece are inflated by all host threads
+            return host.bgzf_compress(data, block=rng.choice((4000, 65280)))
         cuts = sorted(rng.sample(range(1, len(data)), members - 1)) if members > 1 else []
         parts = [data[a:c] for a, c in zip([0] + cuts, cuts + [len(data)])]
         return b"".join(gzip.compress(p, compresslevel=1) for p in parts)     # several members, cut anywhere
