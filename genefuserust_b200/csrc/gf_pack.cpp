@@ -214,7 +214,14 @@ bool gf_pack_available() {
         return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
     }();
     const char* e = getenv("GF_HOST_PACK"); /* read per call: tests switch it */
-    return cpu_ok && !(e && atoi(e) == 0);
+    if (!cpu_ok || (e && atoi(e) == 0)) return false;
+    /* Packing trades host memory bandwidth for PCIe bandwidth: it reads every byte once to save two thirds of the copy.  That
+     * pays when this process has cores (and their share of the memory system) to spare — 12 threads on a 16-core single-GPU
+     * host: 40 ms instead of 64 per 10 M pairs; 9 threads per rank on a 24-core 2-GPU host: 56 instead of 64 — and it does
+     * NOT when many ranks share few cores and one memory system: 8 ranks with 3 threads each on a 32-core 8-GPU host, where
+     * the eight copy engines already saturate the host (237 GB/s aggregate): 178 ms instead of 146.  Fewer than 8 packing
+     * threads (GF_PACK_THREADS, or 3/4 of the hardware threads): the ASCII is copied as it is.  GF_HOST_PACK=1 forces packing. */
+    return (e && atoi(e) == 1) || want_threads() >= 8;
 }
 
 bool gf_pack_forced() {

@@ -104,4 +104,7 @@ def test_pack_reads_capacity_and_switch(monkeypatch):
     monkeypatch.setenv("GF_HOST_PACK", "0")
     assert lib.gf_pack_supported() == 0
     monkeypatch.delenv("GF_HOST_PACK")
+    monkeypatch.setenv("GF_PACK_THREADS", "3")     # many ranks on few cores: packing would cost more than it saves
+    assert lib.gf_pack_supported() == 0
+    monkeypatch.setenv("GF_PACK_THREADS", "12")
     assert lib.gf_pack_supported() == 1
