@@ -55,7 +55,7 @@ def run(tag, hint, env):
 run("hybrid upload (default)", 150, {})
 for t in ("4", "8", "12", "16"):
     run(f"hybrid upload, {t} packing threads", 150, {"GF_PACK_THREADS": t})
-for mb in ("192", "768"):
+for mb in ("96", "128", "192", "256", "768"):
     run(f"hybrid upload, chunk {mb} MB", 150, {"GF_CHUNK_MB": mb})
 run("every chunk packed", 150, {"GF_HOST_PACK": "1"})
 os.environ["GF_HOST_PACK"] = "0"

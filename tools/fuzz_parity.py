@@ -47,6 +47,22 @@ for it in range(iters):
     want = o.scan(b, threads=os.cpu_count() or 8)
     got = [r.astuple() for r in m.scan_pair_end(b)]
     assert got == want, ("PE", it, scale, max_genes, L, n, kw, len(got), len(want))
+    if b.max_len <= 256:
+        # the same batch from pinned arenas: packed upload of every chunk (GF_HOST_PACK=1), then the per-chunk mix (default),
+        # with small pipeline chunks
+        import torch
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+        bp = ReadBatch(pin(b.seq1), pin(b.qual1), pin(b.off1.view(np.int64)).view(np.uint64),
+                       pin(b.seq2), pin(b.qual2), pin(b.off2.view(np.int64)).view(np.uint64))
+        bp.max_len = b.max_len
+        os.environ["GF_CHUNK_MB"] = "1"
+        for mode in ("1", "2"):
+            os.environ["GF_HOST_PACK"] = mode
+            os.environ["GF_PACK_THREADS"] = str(rng.choice((8, 11, 16)))
+            got_p = [r.astuple() for r in m.scan_pair_end(bp)]
+            assert got_p == want, ("PE packed upload", mode, it, scale, max_genes, L, n, kw, len(got_p), len(want))
+        for k_ in ("GF_CHUNK_MB", "GF_HOST_PACK", "GF_PACK_THREADS"):
+            os.environ.pop(k_, None)
     se = ReadBatch(b.seq2, b.qual2, b.off2)
     assert [r.astuple() for r in m.scan_single_end(se)] == o.scan(se, threads=os.cpu_count() or 8), ("SE", it, L, kw)
     if it % 5 == 0:
@@ -73,6 +89,6 @@ for it in range(iters):
         assert [r.astuple() for r in got3] == [want[i] for i, _ in order], ("bucket order", it)
     n_pairs += n; n_matches += len(want)
     print(f"  it {it:3d}: scale {scale} genes {len(genes):3d} L {L:3d} pairs {n:6d} p_fusion {kw['p_fusion']} sub {kw['sub_rate']} n {kw['n_rate']}"
-          f"{' ragged+IUPAC' if it % 3 == 2 else ''}{' +list' if it % 5 == 0 else ''}{' +order' if it % 4 == 1 else ''}: {len(want)} records identical (PE), SE identical", flush=True)
+          f"{' ragged+IUPAC' if it % 3 == 2 else ''}{' +list' if it % 5 == 0 else ''}{' +order' if it % 4 == 1 else ''}: {len(want)} records identical (PE{', PE packed / mixed upload' if b.max_len <= 256 else ''}), SE identical", flush=True)
     m.close(); o.close()
 print(f"fuzz ok: {iters} configurations, {n_pairs} pairs, {n_matches} matches, {time.time() - t0:.1f} s")
