@@ -3,8 +3,8 @@
  * src/core/matcher.rs) as ONE streaming scan of the reference on the GPU.  include/genefuse_gpu.h says what the (degenerate)
  * reference code computes; here is how it maps to kernels.
  *
- *   k_ref_scan     HBM streaming, 1 byte per base read, nothing written.  Thread per aligned 32-byte sector of reference text;
- *                  a warp covers 31 consecutive sectors + the sector before them (lane 0, context only), so neighbouring
+ *   k_ref_scan     HBM streaming, 1 byte per base read, nothing written.  Two aligned 32-byte sectors of reference text per
+ *                  thread; a warp covers 63 consecutive sectors + the sector before them (context only), so neighbouring
  *                  plane words travel by shuffle: no shared memory, no barrier, one launch per resident reference (a warp
  *                  finds its segment from a small prefix table).  32 ASCII bases -> two plane words (valid = ACGT in either
  *                  case = to_ascii_uppercase, matcher.rs:143-148; isA) with ONE branch-free SWAR routine in the nibble domain
@@ -33,7 +33,7 @@
 namespace {
 
 constexpr int RS_THREADS = 256;
-constexpr int RS_WT_SECTORS = 31;          /* counted sectors per warp tile (lane 0 holds the sector before them) */
+constexpr int RS_WT_SECTORS = 63;          /* counted sectors per warp tile: two per lane, lane 0's first is the sector before them */
 constexpr uint64_t RS_CHUNK = 64ull << 20; /* staging buffer bytes (x2, double buffered) */
 constexpr int RS_LIST_CAP = 64;            /* positions kept per key (votes need at most 50) */
 
@@ -168,7 +168,7 @@ __device__ __noinline__ uint32_t keep_rule(const uint8_t* sec, const RefSeg* __r
 }
 
 template <bool EMIT>
-__global__ void __launch_bounds__(RS_THREADS, 5) k_ref_scan(const RefSeg* __restrict__ segs, uint32_t n_segs, uint64_t total_wt,
+__global__ void __launch_bounds__(RS_THREADS, 4) k_ref_scan(const RefSeg* __restrict__ segs, uint32_t n_segs, uint64_t total_wt,
                                                             RefScanOut* __restrict__ out, uint32_t emit_mask) {
     __shared__ unsigned int s_cnt[4];
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
@@ -190,20 +190,25 @@ __global__ void __launch_bounds__(RS_THREADS, 5) k_ref_scan(const RefSeg* __rest
         hi_b = sg.p + sg.n;
         wt_lo = sg.wt0;
         wt_end = sg.wt0 + sg.n_wt;
-        sec = reinterpret_cast<const uint8_t*>((uintptr_t)sg.p & ~(uintptr_t)31) + 32ll * ((long long)lane - 1) +
+        sec = reinterpret_cast<const uint8_t*>((uintptr_t)sg.p & ~(uintptr_t)31) + 32ll * (2 * (long long)lane - 1) +
               (long long)(32 * RS_WT_SECTORS) * (long long)(g - sg.wt0);
     };
     if (g < total_wt) enter();
 #pragma unroll 1
     for (; g < total_wt; g += n_warps, sec += stride) {
         if (g >= wt_end) enter();
-        uint4 a, b;
+        /* two consecutive sectors per lane (the loop's own bookkeeping is paid once for 64 bytes) */
+        uint4 a, b, c, d;
         if (g > wt_lo && g + 1 < wt_end) {
             asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                          : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
                          : "l"(sec));
+            asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w), "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w)
+                         : "l"(sec + 32));
         } else {
             load_sector(sec, lo_b, hi_b, &a, &b);
+            load_sector(sec + 32, lo_b, hi_b, &c, &d);
         }
         /* Everything the short way out needs is visible in the nibble domain (no gathers): nothing is kept in the context
          * sector; in a sector without a valid base; and in a sector where all 32 bases and the 16 before them are valid and
@@ -214,11 +219,23 @@ __global__ void __launch_bounds__(RS_THREADS, 5) k_ref_scan(const RefSeg* __rest
         group_va(a.z, a.w, &v1, &a1);
         group_va(b.x, b.y, &v2, &a2);
         group_va(b.z, b.w, &v3, &a3);
-        const bool tail_plain = (v2 & v3) == VA_ALL && a3 != VA_ALL;                       /* what the next sector needs of this one */
-        const bool prev_plain = __shfl_up_sync(0xFFFFFFFFu, (int)tail_plain, 1) != 0;
-        const bool plain = prev_plain && (v0 & v1 & v2 & v3) == VA_ALL && a0 != VA_ALL && a1 != VA_ALL && a2 != VA_ALL && a3 != VA_ALL;
-        if (lane != 0 && (v0 | v1 | v2 | v3) != 0u && !plain) {
+        const bool tail1 = (v2 & v3) == VA_ALL && a3 != VA_ALL; /* what the sector after this one needs of it */
+        const bool inner1 = (v0 & v1 & v2 & v3) == VA_ALL && a0 != VA_ALL && a1 != VA_ALL && a2 != VA_ALL && a3 != VA_ALL;
+        const bool some1 = (v0 | v1 | v2 | v3) != 0u;
+        group_va(c.x, c.y, &v0, &a0);
+        group_va(c.z, c.w, &v1, &a1);
+        group_va(d.x, d.y, &v2, &a2);
+        group_va(d.z, d.w, &v3, &a3);
+        const bool tail2 = (v2 & v3) == VA_ALL && a3 != VA_ALL;
+        const bool inner2 = (v0 & v1 & v2 & v3) == VA_ALL && a0 != VA_ALL && a1 != VA_ALL && a2 != VA_ALL && a3 != VA_ALL;
+        const bool some2 = (v0 | v1 | v2 | v3) != 0u;
+        const bool prev_tail = __shfl_up_sync(0xFFFFFFFFu, (int)tail2, 1) != 0; /* the lane before holds the two sectors before */
+        if (lane != 0 && some1 && !(prev_tail && inner1)) {
             const uint32_t kc = keep_rule<EMIT>(sec, segs + si, out, emit_mask);
+            c0 += kc & 0xFFu; c1 += (kc >> 8) & 0xFFu; c2 += (kc >> 16) & 0xFFu; c3 += kc >> 24;
+        }
+        if (some2 && !(tail1 && inner2)) {
+            const uint32_t kc = keep_rule<EMIT>(sec + 32, segs + si, out, emit_mask);
             c0 += kc & 0xFFu; c1 += (kc >> 8) & 0xFFu; c2 += (kc >> 16) & 0xFFu; c3 += kc >> 24;
         }
     }
