@@ -435,11 +435,13 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
                 c.pm[m].xwords = s.h_pkx[m].as<uint32_t>();
                 c.pm[m].xoff = s.h_pxo[m].as<uint32_t>();
             }
-            gf_pack_start(c.pm, nm, false); /* the packing threads; the device works on the chunks before meanwhile */
-            c.job = true;
-        } else if (check_per_chunk) { /* (a packed chunk is checked by the packing threads: they read the offsets anyway) */
-            if (can_pack) {
-                gf_pack_start(c.pm, nm, true);
+            /* the packing threads; the device works on the chunks before meanwhile.  When they are busy with another
+             * handle's chunk (several devices driven from one process) this chunk goes as ASCII rather than wait. */
+            if (gf_pack_start(c.pm, nm, false, pack_all)) c.job = true;
+            else c.packed = false;
+        }
+        if (!c.packed && !c.job && check_per_chunk) { /* (a packed chunk is checked by the packing threads: they read the offsets anyway) */
+            if (can_pack && gf_pack_start(c.pm, nm, true, false)) {
                 c.job = true;
             } else {
                 uint64_t mx = 0;

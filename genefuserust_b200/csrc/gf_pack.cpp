@@ -276,8 +276,9 @@ static void pack_worker(int t) {
     }
 }
 
-void gf_pack_start(GfPackMate* mates, int n_mates, bool check_only) { /* n_mates <= 2 */
-    g_pool_mu.lock();
+bool gf_pack_start(GfPackMate* mates, int n_mates, bool check_only, bool wait_if_busy) { /* n_mates <= 2 */
+    if (wait_if_busy) g_pool_mu.lock();
+    else if (!g_pool_mu.try_lock()) return false; /* another handle's chunk is being packed */
     g_prefetch = 8192;
     if (const char* e = getenv("GF_PACK_PREFETCH")) { const int v = atoi(e); if (v >= 0 && v <= (1 << 20)) g_prefetch = v; }
     const int nt = want_threads();
@@ -297,6 +298,7 @@ void gf_pack_start(GfPackMate* mates, int n_mates, bool check_only) { /* n_mates
     if (!J.fn) J.fn = pack_worker;
     J.t_start = std::chrono::steady_clock::now();
     g_pool->start(&J.fn);
+    return true;
 }
 
 float gf_pack_wait() {
@@ -309,10 +311,10 @@ float gf_pack_wait() {
 }
 
 void gf_pack_chunk(GfPackMate* mates, int n_mates) {
-    gf_pack_start(mates, n_mates, false);
+    gf_pack_start(mates, n_mates, false, true);
     gf_pack_wait();
 }
 void gf_pack_check_offsets(GfPackMate* mates, int n_mates) {
-    gf_pack_start(mates, n_mates, true);
+    gf_pack_start(mates, n_mates, true, true);
     gf_pack_wait();
 }

@@ -29,8 +29,9 @@ bool gf_pack_forced();                             /* GF_HOST_PACK=1: every chun
 int gf_pack_threads();                             /* GF_PACK_THREADS or the hardware threads */
 void gf_pack_chunk(GfPackMate* mates, int n_mates);
 /* the same in two halves: gf_pack_start returns at once (the packing threads work; `mates` must stay where it is), gf_pack_wait
- * returns when they are done, with the milliseconds they took.  One job at a time in the process. */
-void gf_pack_start(GfPackMate* mates, int n_mates, bool check_only);
+ * returns when they are done, with the milliseconds they took.  One job at a time in the process: a second caller waits, or
+ * (wait_if_busy = false) is told so and uploads its chunk as ASCII instead. */
+bool gf_pack_start(GfPackMate* mates, int n_mates, bool check_only, bool wait_if_busy); /* false: busy and !wait_if_busy */
 float gf_pack_wait();
 /* only the offset check of gf_pack_chunk (sets bad_offsets), by the same threads */
 void gf_pack_check_offsets(GfPackMate* mates, int n_mates);

@@ -448,13 +448,23 @@ def test_packed_upload_parity(mappers, small_panel, monkeypatch):
     assert_same_matches(got_se, want_se, "packed upload, single end")
 
 
-def test_list_mode_concurrent_handles(host, small_panel):
+@pytest.mark.parametrize("pinned", [False, True])
+def test_list_mode_concurrent_handles(host, small_panel, pinned, monkeypatch):
     """multi-CSV list mode (fusion_scan.rs:62-188): one index per CSV, used concurrently from different host
-    threads over the same reads; handles are independent, every result must equal the oracle's for its panel"""
+    threads over the same reads; handles are independent, every result must equal the oracle's for its panel.
+    pinned: the arenas are pinned host memory, so the calls upload chunk by chunk as planes or ASCII and share the process's
+    packing threads (a handle that finds them busy sends its chunk as ASCII)"""
     import threading
     genes = small_panel.genes()
     panels = [genes, genes[:40], genes[20:90], genes[::2]]
     b = synth.generate_pairs(small_panel, 40000, read_len=150, seed=52, p_fusion=0.05)
+    if pinned:
+        import torch
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+        b = ReadBatch(pin(b.seq1), pin(b.qual1), pin(b.off1.view(np.int64)).view(np.uint64),
+                      pin(b.seq2), pin(b.qual2), pin(b.off2.view(np.int64)).view(np.uint64))
+        monkeypatch.setenv("GF_CHUNK_MB", "1")
+        monkeypatch.setenv("GF_PACK_THREADS", "8")
     mappers = [host.FusionMapper.from_gene_spans(p, device=0) for p in panels]
     results = [None] * len(panels)
 
