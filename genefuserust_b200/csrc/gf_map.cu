@@ -764,6 +764,16 @@ __device__ void exact_planes(EW& W, int len) {
     }
     __syncwarp();
 }
+/* ask for the table bucket of the k-mer at offset i (L2 prefetch): the lookups of one read are independent of each other, the
+ * loop that makes them is a chain of dependent loads per offset (bucket -> dupe list -> site decode) with side effects, so the
+ * compiler cannot overlap them — all buckets of a pass are requested up front instead */
+template <class EW>
+__device__ __forceinline__ void prefetch_site_bucket(const GfDevIndex& ix, const EW& W, int i) {
+    const uint32_t bp = (uint32_t)i;
+    if ((fsr(W.pv, bp) & 0xFFFFu) != 0xFFFFu) return;
+    const uint32_t key = ((fsr(W.phi, bp) & 0xFFFFu) << 16) | (fsr(W.plo, bp) & 0xFFFFu);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.table + 2ull * gf_home_bucket(key, ix.bucket_shift)));
+}
 /* visit every (contig, position) the k-mer at offset i maps to */
 template <class EW, class F>
 __device__ __forceinline__ void for_each_site(const GfDevIndex& ix, const EW& W, int i, F f) {
@@ -814,7 +824,7 @@ struct SegResult { int n; int s0, e0, s1, e1; long long gp0, gp1; }; /* entries 
 
 /* Indexer::map_read (indexer.rs:252-538) on the ASCII sequence in W.seq.  All lanes return the same result. */
 template <class EW>
-__device__ SegResult exact_map_read(const GfDevIndex& ix, EW& W, int len, long long* gkeys, int* gcnt) {
+__device__ SegResult exact_map_read(const GfDevIndex& ix, EW& W, int len, long long* gkeys, int* gcnt, bool prefetch) {
     const uint32_t lane = gf_lane();
     SegResult R;
     R.n = 0; R.s0 = R.e0 = R.s1 = R.e1 = 0; R.gp0 = R.gp1 = 0;
@@ -826,6 +836,8 @@ __device__ SegResult exact_map_read(const GfDevIndex& ix, EW& W, int len, long l
     uint32_t tsize = EW::TBL_SLOTS;
     /* first pass: every 2nd offset votes for pack(contig, position - i)  (:277-321); shared table first, the global
      * one when the read casts more distinct votes than 3/4 of the shared slots */
+    if (prefetch)
+        for (int j = (int)lane; j < nprobe; j += 32) prefetch_site_bucket(ix, W, 2 * j);
     for (int round = 0; round < 2; round++) {
         const uint32_t tmask = tsize - 1;
         for (uint32_t s = lane; s < tsize; s += 32) { tk[s] = EX_EMPTY_KEY; tc[s] = 0; }
@@ -872,6 +884,9 @@ __device__ SegResult exact_map_read(const GfDevIndex& ix, EW& W, int len, long l
 
     /* second pass: per-offset flag, then mask[p] = max over the 16 windows covering p  (:362-521, :716-732) */
     const int nwin = len - 15;
+    if (prefetch)
+        for (int i = (int)lane; i < nwin; i += 32)
+            if (i & 1) prefetch_site_bucket(ix, W, i); /* (the even offsets were fetched by pass 1) */
     for (int i = (int)lane; i < nwin; i += 32) {
         int f = 0;
         for_each_site(ix, W, i, [&](int32_t c, int32_t p) {
@@ -964,6 +979,10 @@ __global__ void __launch_bounds__(EX_WARPS * 32) k_exact(ExactParams P) {
     long long* gkeys = P.gtbl_keys + gwarp * EW::GLOBAL_SLOTS;
     int* gcnt = P.gtbl_cnt + gwarp * EW::GLOBAL_SLOTS;
     const uint32_t n_surv = min(P.counters->n_survivors, P.survivors_cap);
+    /* many survivors per resident warp (repeat-rich panels): the kernel's rate is lookups in flight, so every pass asks for all
+     * its table buckets first (35 -> 26 ms for 2.5 M survivors); with a few waves of survivors the extra pass only delays each
+     * warp's own chain (+15 % measured), so it is left out */
+    const bool prefetch = (uint64_t)n_surv > 8 * n_warps;
 
     for (uint64_t sidx = gwarp; sidx < n_surv; sidx += n_warps) {
         const uint2 sv = P.survivors[sidx];
@@ -975,7 +994,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) k_exact(ExactParams P) {
         if (lane == 0) for (int k = 0; k < 16; k++) W.seq[len + k] = 0;
         __syncwarp();
         for (int attempt = 0; attempt < 2; attempt++) {
-            SegResult R = exact_map_read(P.ix, W, len, gkeys, gcnt);
+            SegResult R = exact_map_read(P.ix, W, len, gkeys, gcnt, prefetch);
             if (R.n < 2) break; /* mapable = false (fusion_mapper.rs:107-113): no retry */
             /* order by seq_start (fusion_mapper.rs:163-165 / indexer.rs:549-551) */
             int ls = R.s0, le = R.e0, rs = R.s1, re = R.e1;
