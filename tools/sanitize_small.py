@@ -72,8 +72,6 @@ dc = [torch.from_numpy(c).cuda() for c in contigs]
 mt = host.Matcher([(t.data_ptr(), t.numel()) for t in dc])
 print("matcher (device contigs)", mt.remove_alignables([b"ACGT" * 20])[1].astuple())
 mt.close()
-m.close()
-print("ok")
 # packed / hybrid upload from pinned arenas (ragged reads with N and lower case), several chunks
 rng = random.Random(3)
 r1 = [(bytes(rng.choice(b"ACGTACGTACGTNacgt") for _ in range(n)), b"E" * n) for n in [0, 1, 31, 32, 33, 64, 65, 100, 150, 151, 200, 256] * 300]
@@ -87,3 +85,5 @@ for mode in ("0", "1", "2"):
     os.environ["GF_HOST_PACK"] = mode
     print("upload mode", mode, len(m.scan_pair_end(bp)), m.map_stats().packed_upload)
 del os.environ["GF_HOST_PACK"], os.environ["GF_CHUNK_MB"]
+m.close()
+print("ok")
