@@ -221,7 +221,9 @@ bool gf_pack_available() {
      * NOT when many ranks share few cores and one memory system: 8 ranks with 3 threads each on a 32-core 8-GPU host, where
      * the eight copy engines already saturate the host (237 GB/s aggregate): 178 ms instead of 146.  Fewer than 8 packing
      * threads (GF_PACK_THREADS, or 3/4 of the hardware threads): the ASCII is copied as it is.  GF_HOST_PACK=1 forces packing. */
-    return (e && atoi(e) == 1) || want_threads() >= 8;
+    int min_threads = 8;
+    if (const char* m = getenv("GF_PACK_MIN_THREADS")) { const int v = atoi(m); if (v >= 1) min_threads = v; } /* experiments */
+    return (e && atoi(e) == 1) || want_threads() >= min_threads;
 }
 
 bool gf_pack_forced() {
