@@ -5,13 +5,23 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 #include <thread>
 
 #include "gf_internal.h"
 
 static thread_local std::string g_last_error;
 void gf_set_error(const std::string& msg) { g_last_error = msg; }
+
+/* packed upload, a chunk whose reads all have one length: off[i] = base + i * len (n + 1 entries), and where read i's plane
+ * words start: pko[i] = i * 2 * ceil(len / 32) — nothing the host would have to send */
+__global__ void k_fill_uniform(uint64_t* off, uint32_t* pko, uint64_t base, uint32_t len, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) off[i] = base + i * len;
+    if (i < n) pko[i] = (uint32_t)(i * 2u * ((len + 31u) >> 5));
+}
 
 namespace {
 
@@ -118,10 +128,13 @@ void destroy_handle(gf_index* idx) {
         s.out.release(); s.nout.release(); s.out2.release(); s.keys.release();
         for (int m = 0; m < 2; m++) {
             s.pk[m].release(); s.pko[m].release(); s.pkx[m].release(); s.pxo[m].release();
-            s.h_pk[m].release(); s.h_pko[m].release(); s.h_pkx[m].release(); s.h_pxo[m].release();
         }
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.done) cudaEventDestroy(s.done);
+    }
+    for (auto& ps : idx->pack_set) {
+        for (int m = 0; m < 2; m++) { ps.h_pk[m].release(); ps.h_pko[m].release(); ps.h_pkx[m].release(); ps.h_pxo[m].release(); }
+        if (ps.copied) cudaEventDestroy(ps.copied);
     }
     if (idx->h_slots) cudaFreeHost(idx->h_slots);
     for (cudaEvent_t e : {idx->ev_start, idx->ev_end, idx->ev_ingest})
@@ -205,6 +218,7 @@ int gf_index_create(const gf_gene_span* genes, uint32_t n_genes, const gf_params
         for (auto& s : idx->stage)
             ok = ok && cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) == cudaSuccess;
+        for (auto& ps : idx->pack_set) ok = ok && cudaEventCreateWithFlags(&ps.copied, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaMallocHost((void**)&idx->h_slots, sizeof(GfHostSlot) * (GF_STAGES + 1)) == cudaSuccess;
         if (!ok) { rc = fail(GF_E_CUDA, "event / pinned allocation failed"); break; }
         memset(idx->h_slots, 0, sizeof(GfHostSlot) * (GF_STAGES + 1));
@@ -357,8 +371,8 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
     float ms_pack = 0;
     uint64_t n_packed_chunks = 0;
     /* pipeline chunks.  List mode: a chunk costs nh rounds of launches, so chunks are larger (the upload is a smaller share of a
-     * chunk anyway).  Packed upload: twice the size (the per-chunk work of the issuing thread is not hidden behind a copy) */
-    uint64_t chunk_bytes = CHUNK_TARGET_BYTES * std::min<uint32_t>(nh, 4u) * (can_pack ? 2u : 1u);
+     * chunk anyway). */
+    uint64_t chunk_bytes = CHUNK_TARGET_BYTES * std::min<uint32_t>(nh, 4u);
     if (const char* e = getenv("GF_CHUNK_MB")) { long v = atol(e); if (v >= 1 && v <= 65536) chunk_bytes = (uint64_t)v << 20; }
     uint64_t n_chunks = std::max<uint64_t>(1, (2 * total_bytes + chunk_bytes - 1) / chunk_bytes);
     n_chunks = std::min<uint64_t>(n_chunks, n);
@@ -367,16 +381,17 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
 
     for (uint32_t h = 0; h < nh; h++) hs[h]->stats.zero_copy_qual = zc ? 1u : 0u;
 
-    /* Which chunks are packed?  The packers (host cores, memory-bound) and the copy engine (PCIe) are two resources that can
-     * work side by side: a packed chunk costs host time and little copy time, an ASCII chunk no host time and three times the
-     * copy time.  Up to GF_STAGES chunks are in flight; a chunk is packed when the copies already queued keep the copy engine
-     * busy for at least as long as packing it takes — so the engine never waits for the packers and the packers never pack
-     * what the engine could have fetched in the meantime.  Few cores (many ranks on one host) => mostly ASCII chunks; many
-     * cores => mostly packed ones.  Times are estimates (bytes / nominal rates, packing measured as it goes): the rule corrects
-     * itself because it looks at what is actually still queued (cudaEventQuery). */
+    /* Which chunks are packed?  The packers (host cores, memory-bound) and the copy engine (PCIe) are two resources that work
+     * side by side: a packed chunk costs host time and a third of the copy time, an ASCII chunk no host time.  So the batch is
+     * eaten from both ends: a driver thread keeps the packing threads busy with chunks taken from the BACK of the batch, one
+     * after the other without a pause, into GF_PACK_SETS pinned buffer sets; the issuing thread uploads every packed chunk as
+     * soon as it is ready and, whenever the copy engine is about to run dry, takes the next chunk from the FRONT and copies its
+     * ASCII.  The two meet somewhere in the middle — where depends on how many cores there are and how fast the copies go, and
+     * nothing has to be estimated beyond "how much copying is still queued" (cudaEventQuery).  Few cores => mostly ASCII chunks,
+     * many cores => mostly packed ones; the issuing thread's thirty driver calls per chunk overlap with the packing.
+     * The records of a call are sorted at the end, so the order in which chunks are issued does not matter. */
     struct InFlight { cudaEvent_t copied; double copy_ms; };
     std::vector<InFlight> in_flight;
-    double pack_ms_per_byte = 1.0 / (5.0e6 * std::max(1, gf_pack_threads())); /* first guess: 5 GB/s per packing thread */
     constexpr double COPY_BYTES_PER_MS = 45.0e6;
     auto queued_copy_ms = [&]() {
         double t = 0;
@@ -387,125 +402,178 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
         cudaGetLastError(); /* cudaErrorNotReady is not an error here */
         return t;
     };
-
-    /* a chunk in two steps: begin_chunk decides how it is uploaded and, when it is packed, starts the packing threads;
-     * enqueue_chunk waits for them and issues its copies and launches.  begin_chunk(k + 1) comes BEFORE enqueue_chunk(k): the
-     * issuing thread's own work on chunk k (some thirty driver calls) runs while chunk k + 1 is being packed. */
-    struct ChunkPlan {
-        bool packed = false, job = false;
-        GfPackMate pm[2];
-        uint64_t ascii_bytes = 0;
+    const int nm = pe ? 2 : 1;
+    uint64_t max_chunk_bytes[2] = {0, 0};
+    for (uint64_t k = 0; k < n_chunks; k++) {
+        const uint64_t lo = k * per, hi = std::min(n, lo + per);
+        max_chunk_bytes[0] = std::max(max_chunk_bytes[0], off1[hi] - off1[lo]);
+        if (pe) max_chunk_bytes[1] = std::max(max_chunk_bytes[1], off2[hi] - off2[lo]);
+    }
+    const bool use_packers = can_pack && (pack_all || n_chunks >= 2);
+    /* state shared with the driver thread */
+    enum { SET_FREE = 0, SET_PACKING, SET_READY, SET_COPYING };
+    struct SetState { int state = SET_FREE; uint64_t chunk = 0; float ms = 0; GfPackMate pm[2]; };
+    struct Shared {
+        std::mutex mu;
+        std::condition_variable cv_driver, cv_issuer;
+        uint64_t front = 0, back = 0;
+        bool stop = false, driver_done = true;
+        SetState set[GF_PACK_SETS];
+        std::vector<int> ready;
+    } sh;
+    sh.back = n_chunks;
+    auto fill_mates = [&](GfPackMate* pmv, uint64_t k) {
+        const uint64_t lo = k * per, hi = std::min(n, lo + per);
+        for (int m = 0; m < nm; m++) {
+            const uint64_t* off = m ? off2 : off1;
+            pmv[m] = GfPackMate{};
+            pmv[m].seq = (m ? in->seq2 : in->seq1) + off[lo];
+            pmv[m].off = off + lo;
+            pmv[m].off_base = off[lo];
+            pmv[m].n = hi - lo;
+            pmv[m].mate2 = m == 1;
+            pmv[m].max_len = max_len;
+        }
     };
-    ChunkPlan plans[GF_STAGES];
-    auto begin_chunk = [&](uint64_t k, double copy_ms_not_yet_queued) -> int {
-        GfStage& s = idx->stage[k % GF_STAGES];
-        ChunkPlan& c = plans[k % GF_STAGES];
-        const uint64_t lo = k * per, hi = std::min(n, lo + per), cn = hi - lo;
-        c.ascii_bytes = (off1[hi] - off1[lo]) + (pe ? off2[hi] - off2[lo] : 0);
-        c.packed = can_pack && (pack_all || queued_copy_ms() + copy_ms_not_yet_queued >= pack_ms_per_byte * (double)c.ascii_bytes);
-        c.job = false;
-        const int nm = pe ? 2 : 1;
-        if (can_pack || check_per_chunk) {
+    if (use_packers) {
+        for (GfPackSet& ps : idx->pack_set)
             for (int m = 0; m < nm; m++) {
-                const uint64_t* off = m ? off2 : off1;
-                c.pm[m] = GfPackMate{};
-                c.pm[m].seq = (m ? in->seq2 : in->seq1) + off[lo];
-                c.pm[m].off = off + lo;
-                c.pm[m].off_base = off[lo];
-                c.pm[m].n = cn;
-                c.pm[m].mate2 = m == 1;
-                c.pm[m].max_len = max_len;
+                const size_t wcap = sizeof(uint32_t) * 2 * (size_t)(max_chunk_bytes[m] / 32 + per + 1); /* >= 2 * sum ceil(len / 32) */
+                GF_CUDA_TRY(ps.h_pk[m].reserve(wcap));
+                GF_CUDA_TRY(ps.h_pkx[m].reserve(wcap));
+                GF_CUDA_TRY(ps.h_pko[m].reserve(sizeof(uint32_t) * per));
+                GF_CUDA_TRY(ps.h_pxo[m].reserve(sizeof(uint32_t) * per));
             }
-        }
-        if (c.packed) {
+    }
+    auto driver = [&]() {
+        cudaSetDevice(idx->device);
+        for (;;) {
+            int j = -1;
+            uint64_t k = 0;
+            {
+                std::unique_lock<std::mutex> lk(sh.mu);
+                for (;;) {
+                    if (sh.stop || sh.front >= sh.back) break;
+                    for (int u = 0; u < GF_PACK_SETS && j < 0; u++)
+                        if (sh.set[u].state == SET_FREE) j = u;
+                    if (j >= 0) break;
+                    /* no free set: those being copied come back when their copy is through */
+                    for (int u = 0; u < GF_PACK_SETS; u++)
+                        if (sh.set[u].state == SET_COPYING && cudaEventQuery(idx->pack_set[u].copied) == cudaSuccess) sh.set[u].state = SET_FREE;
+                    cudaGetLastError();
+                    for (int u = 0; u < GF_PACK_SETS && j < 0; u++)
+                        if (sh.set[u].state == SET_FREE) j = u;
+                    if (j >= 0) break;
+                    sh.cv_driver.wait_for(lk, std::chrono::microseconds(100));
+                }
+                if (j < 0) break;
+                k = --sh.back;
+                sh.set[j].state = SET_PACKING;
+                sh.set[j].chunk = k;
+            }
+            SetState& st = sh.set[j];
+            GfPackSet& ps = idx->pack_set[j];
+            fill_mates(st.pm, k);
             for (int m = 0; m < nm; m++) {
-                const uint64_t* off = m ? off2 : off1;
-                const uint64_t bytes = off[hi] - off[lo];
-                const size_t wcap = sizeof(uint32_t) * 2 * (size_t)(bytes / 32 + cn + 1); /* >= 2 * sum ceil(len / 32) */
-                GF_CUDA_TRY(s.h_pk[m].reserve(wcap));
-                GF_CUDA_TRY(s.h_pkx[m].reserve(wcap));
-                GF_CUDA_TRY(s.h_pko[m].reserve(sizeof(uint32_t) * cn));
-                GF_CUDA_TRY(s.h_pxo[m].reserve(sizeof(uint32_t) * cn));
-                GF_CUDA_TRY(s.pk[m].reserve(wcap));
-                GF_CUDA_TRY(s.pkx[m].reserve(wcap));
-                GF_CUDA_TRY(s.pko[m].reserve(sizeof(uint32_t) * cn));
-                GF_CUDA_TRY(s.pxo[m].reserve(sizeof(uint32_t) * cn));
-                c.pm[m].words = s.h_pk[m].as<uint32_t>();
-                c.pm[m].woff = s.h_pko[m].as<uint32_t>();
-                c.pm[m].xwords = s.h_pkx[m].as<uint32_t>();
-                c.pm[m].xoff = s.h_pxo[m].as<uint32_t>();
+                st.pm[m].compact = true;
+                st.pm[m].words = ps.h_pk[m].as<uint32_t>();
+                st.pm[m].woff = ps.h_pko[m].as<uint32_t>();
+                st.pm[m].xwords = ps.h_pkx[m].as<uint32_t>();
+                st.pm[m].xoff = ps.h_pxo[m].as<uint32_t>();
             }
-            /* the packing threads; the device works on the chunks before meanwhile.  When they are busy with another
-             * handle's chunk (several devices driven from one process) this chunk goes as ASCII rather than wait. */
-            if (gf_pack_start(c.pm, nm, false, pack_all)) c.job = true;
-            else c.packed = false;
-        }
-        if (!c.packed && !c.job && check_per_chunk) { /* (a packed chunk is checked by the packing threads: they read the offsets anyway) */
-            if (can_pack && gf_pack_start(c.pm, nm, true, false)) {
-                c.job = true;
-            } else {
-                uint64_t mx = 0;
-                int r = scan_offsets(off1 + lo, pe ? off2 + lo : nullptr, cn, max_len, &mx, 1); /* inline: ~0.3 ms per chunk */
-                if (r != GF_OK) return r;
+            gf_pack_start(st.pm, nm, false, true); /* waits while the packing threads work for another handle */
+            st.ms = gf_pack_wait();
+            {
+                std::lock_guard<std::mutex> lk(sh.mu);
+                st.state = SET_READY;
+                sh.ready.push_back(j);
             }
+            sh.cv_issuer.notify_one();
         }
-        return GF_OK;
-    };
-    auto chunk_copy_ms = [&](uint64_t k) { /* estimate, for the chunk that is about to be queued */
-        const ChunkPlan& c = plans[k % GF_STAGES];
-        return (double)c.ascii_bytes * (c.packed ? 0.37 : 1.0) / COPY_BYTES_PER_MS;
-    };
-    auto finish_pack = [&](uint64_t k) -> int {
-        ChunkPlan& c = plans[k % GF_STAGES];
-        if (!c.job) return GF_OK;
-        const float ms_job = gf_pack_wait();
-        c.job = false;
-        if (c.packed) {
-            ms_pack += ms_job;
-            n_packed_chunks++;
-            pack_ms_per_byte = 0.5 * pack_ms_per_byte + 0.5 * (double)ms_job / (double)std::max<uint64_t>(c.ascii_bytes, 1);
+        {
+            std::lock_guard<std::mutex> lk(sh.mu);
+            sh.driver_done = true;
         }
-        if (c.pm[0].bad_offsets || (pe && c.pm[1].bad_offsets))
-            return fail(GF_E_INVALID, "offsets are not ascending, or a read is longer than max_len / the kernel capacity");
-        return GF_OK;
+        sh.cv_issuer.notify_one();
+    };
+    std::thread driver_thread;
+    if (use_packers) {
+        sh.driver_done = false;
+        driver_thread = std::thread(driver);
+    }
+    auto stop_driver = [&]() {
+        if (!driver_thread.joinable()) return;
+        {
+            std::lock_guard<std::mutex> lk(sh.mu);
+            sh.stop = true;
+        }
+        sh.cv_driver.notify_one();
+        driver_thread.join();
     };
 
-    auto enqueue_chunk = [&](uint64_t k) -> int {
-        GfStage& s = idx->stage[k % GF_STAGES];
-        ChunkPlan& c = plans[k % GF_STAGES];
-        const bool packed = c.packed;
-        const GfPackMate* pm = c.pm;
+    /* issue chunk k as issue number q (stage q % GF_STAGES): its copies (plane words of pack set `set`, or the ASCII) and launches */
+    auto enqueue_chunk = [&](uint64_t q, uint64_t k, int set) -> int {
+        GfStage& s = idx->stage[q % GF_STAGES];
+        const bool packed = set >= 0;
+        const GfPackMate* pm = packed ? sh.set[set].pm : nullptr;
         const uint64_t lo = k * per, hi = std::min(n, lo + per), cn = hi - lo;
         const uint64_t b1 = off1[lo], e1 = off1[hi];
         const uint64_t h2d_before = h2d;
         cudaStream_t cs = idx->copy_stream;
         if (packed) {
-            for (int m = 0; m < (pe ? 2 : 1); m++) {
-                GF_CUDA_TRY(cudaMemcpyAsync(s.pk[m].p, s.h_pk[m].p, sizeof(uint32_t) * pm[m].n_words, cudaMemcpyHostToDevice, cs));
-                GF_CUDA_TRY(cudaMemcpyAsync(s.pko[m].p, s.h_pko[m].p, sizeof(uint32_t) * cn, cudaMemcpyHostToDevice, cs));
-                GF_CUDA_TRY(cudaMemcpyAsync(s.pxo[m].p, s.h_pxo[m].p, sizeof(uint32_t) * cn, cudaMemcpyHostToDevice, cs));
-                h2d += sizeof(uint32_t) * (pm[m].n_words + 2 * cn);
+            const GfPackSet& ps = idx->pack_set[set];
+            for (int m = 0; m < nm; m++) {
+                const size_t wcap = sizeof(uint32_t) * 2 * (size_t)(max_chunk_bytes[m] / 32 + per + 1);
+                GF_CUDA_TRY(s.pk[m].reserve(wcap));
+                GF_CUDA_TRY(s.pkx[m].reserve(wcap));
+                GF_CUDA_TRY(s.pko[m].reserve(sizeof(uint32_t) * per));
+                GF_CUDA_TRY(s.pxo[m].reserve(sizeof(uint32_t) * per));
+                GF_CUDA_TRY(cudaMemcpyAsync(s.pk[m].p, ps.h_pk[m].p, sizeof(uint32_t) * pm[m].n_words, cudaMemcpyHostToDevice, cs));
+                h2d += sizeof(uint32_t) * pm[m].n_words;
+                if (!pm[m].uniform_len) { /* (reads of one length: the device fills the table itself, below) */
+                    GF_CUDA_TRY(cudaMemcpyAsync(s.pko[m].p, ps.h_pko[m].p, sizeof(uint32_t) * cn, cudaMemcpyHostToDevice, cs));
+                    h2d += sizeof(uint32_t) * cn;
+                }
+                bool any_x = false;
+                for (int t = 0; t < pm[m].n_threads; t++) any_x = any_x || pm[m].xregion_used[t] != 0;
+                if (any_x) {
+                    for (int t = 0; t < pm[m].n_threads; t++) { /* threads without a flagged read left their part of xoff alone */
+                        const uint64_t a = cn * (uint64_t)t / pm[m].n_threads, b = cn * (uint64_t)(t + 1) / pm[m].n_threads;
+                        if (!pm[m].xoff_written[t]) memset(ps.h_pxo[m].as<uint32_t>() + a, 0, sizeof(uint32_t) * (b - a));
+                    }
+                    GF_CUDA_TRY(cudaMemcpyAsync(s.pxo[m].p, ps.h_pxo[m].p, sizeof(uint32_t) * cn, cudaMemcpyHostToDevice, cs));
+                    h2d += sizeof(uint32_t) * cn;
+                } else {
+                    GF_CUDA_TRY(cudaMemsetAsync(s.pxo[m].p, 0, sizeof(uint32_t) * cn, idx->stream));
+                }
                 for (int t = 0; t < pm[m].n_threads; t++) {
                     if (!pm[m].xregion_used[t]) continue;
                     GF_CUDA_TRY(cudaMemcpyAsync(s.pkx[m].as<uint32_t>() + pm[m].xregion_start[t],
-                                                s.h_pkx[m].as<uint32_t>() + pm[m].xregion_start[t],
+                                                ps.h_pkx[m].as<uint32_t>() + pm[m].xregion_start[t],
                                                 sizeof(uint32_t) * pm[m].xregion_used[t], cudaMemcpyHostToDevice, cs));
                     h2d += sizeof(uint32_t) * pm[m].xregion_used[t];
                 }
             }
+            GF_CUDA_TRY(cudaEventRecord(ps.copied, cs)); /* the set is free again from here on */
         } else {
-            GF_CUDA_TRY(s.seq1.reserve(e1 - b1 + 16));
+            GF_CUDA_TRY(s.seq1.reserve(max_chunk_bytes[0] + 16));
             GF_CUDA_TRY(cudaMemcpyAsync(s.seq1.p, in->seq1 + b1, e1 - b1, cudaMemcpyHostToDevice, cs));
             h2d += e1 - b1;
         }
-        GF_CUDA_TRY(s.off1.reserve(sizeof(uint64_t) * (cn + 1)));
+        GF_CUDA_TRY(s.off1.reserve(sizeof(uint64_t) * (per + 1)));
         if (!zc) {
-            GF_CUDA_TRY(s.qual1.reserve(e1 - b1 + 16));
+            GF_CUDA_TRY(s.qual1.reserve(max_chunk_bytes[0] + 16));
             GF_CUDA_TRY(cudaMemcpyAsync(s.qual1.p, in->qual1 + b1, e1 - b1, cudaMemcpyHostToDevice, cs));
             h2d += e1 - b1;
         }
-        GF_CUDA_TRY(cudaMemcpyAsync(s.off1.p, off1 + lo, sizeof(uint64_t) * (cn + 1), cudaMemcpyHostToDevice, cs));
-        h2d += sizeof(uint64_t) * (cn + 1);
+        if (packed && pm[0].uniform_len) { /* reads of one length: offsets and word offsets are made on the device */
+            k_fill_uniform<<<(unsigned)((cn + 256) / 256), 256, 0, idx->stream>>>(s.off1.as<uint64_t>(), s.pko[0].as<uint32_t>(), b1,
+                                                                                 pm[0].uniform_len, cn);
+            idx->launches++;
+        } else {
+            GF_CUDA_TRY(cudaMemcpyAsync(s.off1.p, off1 + lo, sizeof(uint64_t) * (cn + 1), cudaMemcpyHostToDevice, cs));
+            h2d += sizeof(uint64_t) * (cn + 1);
+        }
         GfDevBatch db{};
         db.n = cn;
         db.seq1 = packed ? zs1 + b1 : s.seq1.as<uint8_t>();
@@ -521,19 +589,25 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
         db.max_len = max_len;
         if (pe) {
             const uint64_t b2 = off2[lo], e2 = off2[hi];
-            GF_CUDA_TRY(s.off2.reserve(sizeof(uint64_t) * (cn + 1)));
+            GF_CUDA_TRY(s.off2.reserve(sizeof(uint64_t) * (per + 1)));
             if (!packed) {
-                GF_CUDA_TRY(s.seq2.reserve(e2 - b2 + 16));
+                GF_CUDA_TRY(s.seq2.reserve(max_chunk_bytes[1] + 16));
                 GF_CUDA_TRY(cudaMemcpyAsync(s.seq2.p, in->seq2 + b2, e2 - b2, cudaMemcpyHostToDevice, cs));
                 h2d += e2 - b2;
             }
             if (!zc) {
-                GF_CUDA_TRY(s.qual2.reserve(e2 - b2 + 16));
+                GF_CUDA_TRY(s.qual2.reserve(max_chunk_bytes[1] + 16));
                 GF_CUDA_TRY(cudaMemcpyAsync(s.qual2.p, in->qual2 + b2, e2 - b2, cudaMemcpyHostToDevice, cs));
                 h2d += e2 - b2;
             }
-            GF_CUDA_TRY(cudaMemcpyAsync(s.off2.p, off2 + lo, sizeof(uint64_t) * (cn + 1), cudaMemcpyHostToDevice, cs));
-            h2d += sizeof(uint64_t) * (cn + 1);
+            if (packed && pm[1].uniform_len) {
+                k_fill_uniform<<<(unsigned)((cn + 256) / 256), 256, 0, idx->stream>>>(s.off2.as<uint64_t>(), s.pko[1].as<uint32_t>(), b2,
+                                                                                     pm[1].uniform_len, cn);
+                idx->launches++;
+            } else {
+                GF_CUDA_TRY(cudaMemcpyAsync(s.off2.p, off2 + lo, sizeof(uint64_t) * (cn + 1), cudaMemcpyHostToDevice, cs));
+                h2d += sizeof(uint64_t) * (cn + 1);
+            }
             db.seq2 = packed ? zs2 + b2 : s.seq2.as<uint8_t>();
             if (packed) {
                 db.pk2 = s.pk[1].as<uint32_t>(); db.pko2 = s.pko[1].as<uint32_t>();
@@ -550,50 +624,50 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
         s.pair_base = lo;
         GF_CUDA_TRY(cudaStreamWaitEvent(idx->stream, s.copied, 0));
         for (uint32_t h = 0; h < nh; h++) {
-            GfStage& sh = hs[h]->stage[k % GF_STAGES];
-            sh.out_cap = (pe ? 2 : 1) * cn;
-            GF_CUDA_TRY(sh.out.reserve(sizeof(gf_match) * sh.out_cap));
-            GF_CUDA_TRY(sh.nout.reserve(2 * sizeof(unsigned long long)));
-            int r = gf_map_device_batch(hs[h], db, sh.out.as<gf_match>(), sh.out_cap, sh.nout.as<unsigned long long>(),
+            GfStage& sh_ = hs[h]->stage[q % GF_STAGES];
+            sh_.out_cap = (pe ? 2 : 1) * cn;
+            GF_CUDA_TRY(sh_.out.reserve(sizeof(gf_match) * (pe ? 2 : 1) * per));
+            GF_CUDA_TRY(sh_.nout.reserve(2 * sizeof(unsigned long long)));
+            int r = gf_map_device_batch(hs[h], db, sh_.out.as<gf_match>(), sh_.out_cap, sh_.nout.as<unsigned long long>(),
                                         idx->stream, nullptr, true, h ? idx : nullptr);
             if (r != GF_OK) return r;
-            GfHostSlot* hsl = &hs[h]->h_slots[k % GF_STAGES];
+            GfHostSlot* hsl = &hs[h]->h_slots[q % GF_STAGES];
             if (hs[h]->out_mode) { /* per-record filters + order keys on the device, before the records leave it */
-                GF_CUDA_TRY(sh.out2.reserve(sizeof(gf_match) * sh.out_cap));
-                GF_CUDA_TRY(sh.keys.reserve(sizeof(unsigned long long) * sh.out_cap));
-                r = gf_finish_records_device(hs[h], sh.out.as<gf_match>(), sh.nout.as<unsigned long long>(), sh.out_cap,
-                                             sh.out2.as<gf_match>(), sh.keys.as<unsigned long long>(),
-                                             sh.nout.as<unsigned long long>() + 1, hs[h]->out_mode, idx->stream);
+                GF_CUDA_TRY(sh_.out2.reserve(sizeof(gf_match) * (pe ? 2 : 1) * per));
+                GF_CUDA_TRY(sh_.keys.reserve(sizeof(unsigned long long) * (pe ? 2 : 1) * per));
+                r = gf_finish_records_device(hs[h], sh_.out.as<gf_match>(), sh_.nout.as<unsigned long long>(), sh_.out_cap,
+                                             sh_.out2.as<gf_match>(), sh_.keys.as<unsigned long long>(),
+                                             sh_.nout.as<unsigned long long>() + 1, hs[h]->out_mode, idx->stream);
                 if (r != GF_OK) return r;
-                GF_CUDA_TRY(cudaMemcpyAsync(&hsl->n_out2, sh.nout.as<unsigned long long>() + 1, sizeof(unsigned long long),
+                GF_CUDA_TRY(cudaMemcpyAsync(&hsl->n_out2, sh_.nout.as<unsigned long long>() + 1, sizeof(unsigned long long),
                                             cudaMemcpyDeviceToHost, idx->stream));
             }
             GF_CUDA_TRY(cudaMemcpyAsync(&hsl->counters, hs[h]->ws_counters.p, sizeof(GfMapCounters), cudaMemcpyDeviceToHost,
                                         idx->stream));
-            GF_CUDA_TRY(cudaMemcpyAsync(&hsl->n_out, sh.nout.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+            GF_CUDA_TRY(cudaMemcpyAsync(&hsl->n_out, sh_.nout.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                         idx->stream));
         }
         GF_CUDA_TRY(cudaEventRecord(s.done, idx->stream));
         return GF_OK;
     };
-    auto collect = [&](uint64_t k) -> int {
-        GF_CUDA_TRY(cudaEventSynchronize(idx->stage[k % GF_STAGES].done));
+    auto collect = [&](uint64_t q) -> int {
+        GF_CUDA_TRY(cudaEventSynchronize(idx->stage[q % GF_STAGES].done));
         for (uint32_t h = 0; h < nh; h++) {
-            GfStage& sh = hs[h]->stage[k % GF_STAGES];
-            GfHostSlot* hsl = &hs[h]->h_slots[k % GF_STAGES];
+            GfStage& sh_ = hs[h]->stage[q % GF_STAGES];
+            GfHostSlot* hsl = &hs[h]->h_slots[q % GF_STAGES];
             int r = check_flags(*hsl);
             if (r != GF_OK) return r;
             accumulate(hs[h]->stats, *hsl);
             if (hsl->counters.n_ref_panic) panic[h] = 1;
             const uint32_t mode = hs[h]->out_mode;
-            const uint64_t cnt = mode ? hsl->n_out2 : hsl->n_out; /* <= sh.out_cap by construction */
+            const uint64_t cnt = mode ? hsl->n_out2 : hsl->n_out; /* <= sh_.out_cap by construction */
             if (cnt && total_out[h] + cnt <= caps[h]) {
-                GF_CUDA_TRY(cudaMemcpy(outs[h] + total_out[h], mode ? sh.out2.p : sh.out.p, sizeof(gf_match) * cnt,
+                GF_CUDA_TRY(cudaMemcpy(outs[h] + total_out[h], mode ? sh_.out2.p : sh_.out.p, sizeof(gf_match) * cnt,
                                        cudaMemcpyDeviceToHost));
                 d2h[h] += sizeof(gf_match) * cnt;
                 if (mode & GF_OUT_BUCKET_ORDER) {
                     keys[h].resize(total_out[h] + cnt);
-                    GF_CUDA_TRY(cudaMemcpy(keys[h].data() + total_out[h], sh.keys.p, sizeof(unsigned long long) * cnt,
+                    GF_CUDA_TRY(cudaMemcpy(keys[h].data() + total_out[h], sh_.keys.p, sizeof(unsigned long long) * cnt,
                                            cudaMemcpyDeviceToHost));
                     d2h[h] += sizeof(unsigned long long) * cnt;
                 }
@@ -604,22 +678,58 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
         return GF_OK;
     };
 
-    /* up to GF_STAGES chunks are in flight; a chunk's results are collected when its stage is needed again (or at the end) */
-    const uint64_t depth = GF_STAGES;
-    uint64_t collected = 0;
-    int rc = begin_chunk(0, 0.0);
-    for (uint64_t k = 0; rc == GF_OK && k < n_chunks; k++) {
-        rc = finish_pack(k);
-        if (rc != GF_OK) break;
-        if (k + 1 < n_chunks) {
-            while (rc == GF_OK && k + 1 - collected >= depth) rc = collect(collected++); /* chunk k + 1 reuses that stage */
-            if (rc == GF_OK) rc = begin_chunk(k + 1, chunk_copy_ms(k));
+    /* The issuing thread.  An ASCII chunk is taken from the front only when less than GF_ASCII_AHEAD_MS of copying is still
+     * queued (default: half an ASCII chunk; measured 0 / 2 / 4 / 8 ms with 4 ms chunks: 39.3 / 35.8 / 36.5 / 40.9 ms per 10 M pairs), so the copy engine stays busy and nothing is committed to the slow way that the
+     * packers could still have taken.  Up to GF_STAGES chunks are in flight; a chunk's results are collected when its stage is
+     * needed again (or at the end). */
+    double ascii_ahead_ms = 0.5 * (double)(max_chunk_bytes[0] + max_chunk_bytes[1]) / COPY_BYTES_PER_MS;
+    if (const char* e = getenv("GF_ASCII_AHEAD_MS")) { const double v = atof(e); if (v >= 0) ascii_ahead_ms = v; }
+    uint64_t issued = 0, collected = 0;
+    int rc = GF_OK;
+    while (rc == GF_OK && issued < n_chunks) {
+        const bool ascii_ok = !use_packers || (!pack_all && queued_copy_ms() < ascii_ahead_ms);
+        int set = -1;
+        uint64_t k = 0;
+        bool have = false;
+        {
+            std::unique_lock<std::mutex> lk(sh.mu);
+            if (!sh.ready.empty()) {
+                set = sh.ready.front();
+                sh.ready.erase(sh.ready.begin());
+                k = sh.set[set].chunk;
+                have = true;
+            } else if (sh.front < sh.back && ascii_ok) {
+                k = sh.front++;
+                have = true;
+            } else {
+                sh.cv_issuer.wait_for(lk, std::chrono::microseconds(50));
+            }
         }
-        if (rc == GF_OK) rc = enqueue_chunk(k);
+        if (!have) continue;
+        if (set >= 0) {
+            const SetState& st = sh.set[set];
+            ms_pack += st.ms;
+            n_packed_chunks++;
+            if (st.pm[0].bad_offsets || (pe && st.pm[1].bad_offsets)) {
+                rc = fail(GF_E_INVALID, "offsets are not ascending, or a read is longer than max_len / the kernel capacity");
+                break;
+            }
+        } else if (check_per_chunk) {
+            const uint64_t lo = k * per, cn = std::min(n, lo + per) - lo;
+            uint64_t mx = 0;
+            rc = scan_offsets(off1 + lo, pe ? off2 + lo : nullptr, cn, max_len, &mx, 1); /* inline: ~0.3 ms per chunk */
+            if (rc != GF_OK) break;
+        }
+        while (rc == GF_OK && issued - collected >= (uint64_t)GF_STAGES) rc = collect(collected++); /* this issue reuses that stage */
+        if (rc == GF_OK) rc = enqueue_chunk(issued, k, set);
+        if (set >= 0) {
+            std::lock_guard<std::mutex> lk(sh.mu);
+            sh.set[set].state = rc == GF_OK ? SET_COPYING : SET_FREE;
+        }
+        issued++;
     }
-    for (ChunkPlan& c : plans)
-        if (c.job) { gf_pack_wait(); c.job = false; } /* (error paths: never leave the packing threads running) */
-    while (rc == GF_OK && collected < n_chunks) rc = collect(collected++);
+    stop_driver();
+    while (rc == GF_OK && collected < issued) rc = collect(collected++);
     if (rc != GF_OK) {
         cudaStreamSynchronize(idx->stream);
         cudaStreamSynchronize(idx->copy_stream);

@@ -83,18 +83,22 @@ struct GfPinned {
     T* as() const { return (T*)p; }
 };
 
-constexpr int GF_STAGES = 4;      /* chunks of a host batch in flight at once */
+constexpr int GF_STAGES = 6;      /* chunks of a host batch in flight at once */
+constexpr int GF_PACK_SETS = 6;   /* pinned buffer sets the packing threads fill (packed upload) */
 constexpr int GF_SLOT_DEVICE = GF_STAGES;
 
 struct GfStage { /* one in-flight chunk of a host batch */
     GfBuf seq1, qual1, off1, seq2, qual2, off2, out, nout;
     /* packed upload (gf_pack.cpp), per mate: plane words, their per-read offsets, exception words, per-read exception offsets —
-     * built in the pinned buffers by the host threads, copied to the device buffers */
+     * built in a GfPackSet's pinned buffers by the host threads, copied to these device buffers */
     GfBuf pk[2], pko[2], pkx[2], pxo[2];
-    GfPinned h_pk[2], h_pko[2], h_pkx[2], h_pxo[2];
     GfBuf out2, keys; /* output mode != 0: compacted records + their order keys (nout holds two counters then) */
     cudaEvent_t copied = nullptr, done = nullptr;
     uint64_t n = 0, pair_base = 0, out_cap = 0;
+};
+struct GfPackSet { /* packed upload: what the packing threads build for one chunk; free again once it has been copied */
+    GfPinned h_pk[2], h_pko[2], h_pkx[2], h_pxo[2];
+    cudaEvent_t copied = nullptr;
 };
 struct GfHostSlot { /* pinned host memory the device writes results of one call/chunk into */
     GfMapCounters counters;
@@ -145,6 +149,7 @@ struct gf_index {
     GfBuf ws_seq_words, ws_seq_meta, ws_seq_seed, ws_seq_lists; /* split screen pipeline (gf_screen_split.cuh): sequence store
                                                                   (plane words, meta, seeds); counters + the two class lists */
     GfStage stage[GF_STAGES];
+    GfPackSet pack_set[GF_PACK_SETS];
     GfHostSlot* h_slots = nullptr; /* [GF_STAGES + 1]: the pipeline stages + the device-batch path (GF_SLOT_DEVICE) */
     bool stats_pending = false;    /* h_slots[2] is being written by an unsynchronised device-batch call */
     uint64_t pending_pairs = 0;

@@ -180,29 +180,128 @@ __attribute__((target("avx512f,avx512bw"))) inline bool pack_read(const uint8_t*
     return flagged;
 }
 
-__attribute__((target("avx512f,avx512bw"))) void pack_range(GfPackMate* m, uint64_t a, uint64_t b, uint64_t word_base, uint64_t x_base,
-                                                            uint64_t* x_used) {
+/* The same for the read that has nothing to flag — every base upper-case ACGT, at most 256 bases — which is nearly every read:
+ * the mask words go from the registers straight to their place (8 bytes per 64 bases, 4 for an odd last word; no staging
+ * arrays, no variable-length copies), nothing is masked but the last block, and the first byte that is not ACGT sends the whole
+ * read through pack_read instead (false).  `overread`: 64 bytes may be loaded from any block start (the arena goes on behind
+ * the read); otherwise the last block is a masked load. */
+__attribute__((target("avx512f,avx512bw"))) inline bool pack_read_clean(const uint8_t* s, uint32_t len, uint32_t nw, bool overread,
+                                                                        uint32_t* lo, uint32_t* hi) {
+    const __m512i b4 = _mm512_set1_epi8(4), b2 = _mm512_set1_epi8(2), m7 = _mm512_set1_epi8(7);
+    const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8(-1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1));
+    uint32_t p = 0, w = 0;
+    for (; p + 64 <= len; p += 64, w += 2) { /* whole blocks */
+        const __m512i x = _mm512_loadu_si512((const void*)(s + p));
+        const __m512i e = _mm512_shuffle_epi8(lut, _mm512_and_si512(x, m7));
+        if (_mm512_cmpneq_epi8_mask(x, e)) return false;
+        const uint64_t l = _mm512_test_epi8_mask(x, b4), h = _mm512_test_epi8_mask(x, b2);
+        memcpy(lo + w, &l, 8);
+        memcpy(hi + w, &h, 8);
+    }
+    if (p < len) {
+        const uint32_t rem = len - p;
+        const __mmask64 km = (1ull << rem) - 1ull;
+        const __m512i x = overread ? _mm512_loadu_si512((const void*)(s + p)) : _mm512_maskz_loadu_epi8(km, s + p);
+        const __m512i e = _mm512_shuffle_epi8(lut, _mm512_and_si512(x, m7));
+        if (_mm512_mask_cmpneq_epi8_mask(km, x, e)) return false;
+        const uint64_t l = _mm512_test_epi8_mask(x, b4) & km, h = _mm512_test_epi8_mask(x, b2) & km;
+        if (nw - w >= 2) {
+            memcpy(lo + w, &l, 8);
+            memcpy(hi + w, &h, 8);
+        } else {
+            lo[w] = (uint32_t)l;
+            hi[w] = (uint32_t)h;
+        }
+    }
+    return true;
+}
+
+/* The plane words of one packing thread are one sequential stream.  They are collected in a small buffer (L1) and leave it as
+ * whole 64-byte lines with non-temporal stores: the packers are bound by the host's memory system, and an ordinary store costs
+ * a read of the line (for ownership) on top of the write; the copy engine reads the words from memory anyway. */
+struct WordStream {
+    static constexpr uint32_t CAP = 1024; /* words collected before they are flushed (a read adds <= 64) */
+    uint32_t* dst;   /* 64-byte aligned: where stage[0] belongs */
+    uint32_t fill;   /* words in stage, counting the `head` words in front */
+    uint32_t head;   /* words of the first line that belong to the thread before this one: never written */
+    bool nt;
+    alignas(64) uint32_t stage[CAP + 64 + 16];
+    __attribute__((target("avx512f,avx512bw"))) void open(uint32_t* first, bool use_nt) {
+        head = (uint32_t)(((uintptr_t)first & 63u) >> 2);
+        dst = first - head;
+        fill = head;
+        nt = use_nt;
+    }
+    uint32_t* cursor() { return stage + fill; }
+    __attribute__((target("avx512f,avx512bw"))) void flush(bool final) {
+        uint32_t done = 0;
+        if (head) {
+            if (fill < 16 && !final) return;
+            const uint32_t n0 = fill < 16 ? fill : 16;
+            memcpy(dst + head, stage + head, 4 * (size_t)(n0 - head));
+            done = n0;
+            head = 0;
+        }
+        if (nt) for (; done + 16 <= fill; done += 16) _mm512_stream_si512((__m512i*)(dst + done), _mm512_load_si512((const void*)(stage + done)));
+        else for (; done + 16 <= fill; done += 16) _mm512_store_si512((void*)(dst + done), _mm512_load_si512((const void*)(stage + done)));
+        if (final && fill > done) {
+            memcpy(dst + done, stage + done, 4 * (size_t)(fill - done));
+            done = fill;
+        }
+        const uint32_t rem = fill - done; /* < 16 */
+        if (rem) memcpy(stage, stage + done, 4 * (size_t)rem);
+        dst += done;
+        fill = rem;
+    }
+};
+bool g_nt_stores = true; /* GF_PACK_NT=0: ordinary stores (experiments) */
+
+__attribute__((target("avx512f,avx512bw"))) void pack_range(GfPackMate* m, int t, uint64_t a, uint64_t b, uint64_t word_base, uint64_t x_base,
+                                                            uint64_t* x_used, uint32_t uniform_len) {
     uint64_t P = word_base, X = x_base;
+    const uint64_t end_all = m->off[m->n] - m->off_base; /* the chunk's bytes: nothing is loaded from beyond them */
+    const uint8_t* const seq = m->seq - m->off_base;
+    const uint32_t pf = (uint32_t)g_prefetch;
+    const bool write_woff = !(m->compact && uniform_len);
+    bool write_xoff = !m->compact;
+    WordStream ws;
+    ws.open(m->words + 2 * word_base, g_nt_stores);
+    uint64_t o = a < b ? m->off[a] : 0;
     for (uint64_t i = a; i < b; i++) {
-        const uint64_t o = m->off[i];
-        const uint32_t len = (uint32_t)(m->off[i + 1] - o), nw = (len + 31) >> 5;
+        const uint64_t o_next = m->off[i + 1];
+        const uint32_t len = (uint32_t)(o_next - o), nw = (len + 31) >> 5;
+        const uint8_t* s = seq + o;
         /* the arenas stream through once: ask for the lines a few reads ahead (one core alone does not keep enough misses
          * in flight to reach its share of the memory bandwidth) */
-        const uint8_t* ahead = m->seq + (o - m->off_base) + g_prefetch;
-        _mm_prefetch((const char*)ahead, _MM_HINT_T0);
-        _mm_prefetch((const char*)(ahead + 64), _MM_HINT_T0);
-        _mm_prefetch((const char*)(ahead + 128), _MM_HINT_T0);
-        uint32_t* lo = m->words + 2 * P;
-        m->woff[i] = (uint32_t)(2 * P);
-        uint32_t* xv = m->xwords + X;
-        if (pack_read(m->seq + (o - m->off_base), len, m->mate2, lo, lo + nw, xv, xv + nw)) {
-            m->xoff[i] = (uint32_t)(X + 1);
-            X += 2 * nw;
-        } else {
-            m->xoff[i] = 0;
+        if (pf) {
+            _mm_prefetch((const char*)(s + pf), _MM_HINT_T0);
+            _mm_prefetch((const char*)(s + pf + 64), _MM_HINT_T0);
+            _mm_prefetch((const char*)(s + pf + 128), _MM_HINT_T0);
         }
+        uint32_t* lo = ws.cursor();
+        if (write_woff) m->woff[i] = (uint32_t)(2 * P);
+        uint32_t xo = 0;
+        const bool overread = (o - m->off_base) + (uint64_t)(len & ~63u) + 64 <= end_all;
+        if (!pack_read_clean(s, len, nw, overread, lo, lo + nw)) {
+            uint32_t* xv = m->xwords + X;
+            if (pack_read(s, len, m->mate2, lo, lo + nw, xv, xv + nw)) {
+                xo = (uint32_t)(X + 1);
+                X += 2 * nw;
+                if (!write_xoff) { /* the first flagged read of this thread: from here on its part of xoff is written */
+                    memset(m->xoff + a, 0, sizeof(uint32_t) * (size_t)(i - a));
+                    write_xoff = true;
+                }
+            }
+        }
+        if (write_xoff) m->xoff[i] = xo;
+        ws.fill += 2 * nw;
+        if (ws.fill >= WordStream::CAP) ws.flush(false);
         P += nw;
+        o = o_next;
     }
+    ws.flush(true);
+    _mm_sfence(); /* the non-temporal stores are visible before the job counts as done */
+    m->xoff_written[t] = write_xoff ? 1 : 0;
     *x_used = X - x_base;
 }
 
@@ -239,7 +338,7 @@ struct PackJob {
     int n_mates = 0, nt = 1;
     bool check_only = false;
     std::vector<uint64_t> sums;
-    std::atomic<uint32_t> bad[2];
+    std::atomic<uint32_t> bad[2], ragged[2];
     std::function<void(int)> fn;
     std::chrono::steady_clock::time_point t_start{};
 };
@@ -252,14 +351,17 @@ static void pack_worker(int t) {
     for (int k = 0; k < J.n_mates; k++) {
         const GfPackMate& m = J.mates[k];
         const uint64_t a = m.n * (uint64_t)t / nt, b = m.n * (uint64_t)(t + 1) / nt;
-        uint64_t s = 0, bad = 0;
+        uint64_t s = 0, bad = 0, differ = 0;
+        const uint64_t len0 = m.n ? m.off[1] - m.off[0] : 0; /* the chunk's first read: is every read as long? */
         for (uint64_t i = a; i < b; i++) {
             const uint64_t len = m.off[i + 1] - m.off[i]; /* wraps to a huge value when the offsets descend */
             bad |= len > m.max_len;
+            differ |= len ^ len0;
             s += (len + 31) >> 5;
         }
         J.sums[(size_t)k * nt + t] = s;
         if (bad) J.bad[k].store(1, std::memory_order_relaxed);
+        if (differ || len0 == 0) J.ragged[k].store(1, std::memory_order_relaxed);
     }
     if (J.check_only) return;
     g_pool->barrier();
@@ -273,7 +375,9 @@ static void pack_worker(int t) {
         uint64_t base = 0;
         for (int u = 0; u < t; u++) base += J.sums[(size_t)k * nt + u];
         m.xregion_start[t] = 2 * base;
-        pack_range(&m, a, b, base, 2 * base, &m.xregion_used[t]);
+        const uint32_t uniform_len = J.ragged[k].load(std::memory_order_relaxed) ? 0u : (uint32_t)(m.off[1] - m.off[0]);
+        if (t == 0) m.uniform_len = uniform_len;
+        pack_range(&m, t, a, b, base, 2 * base, &m.xregion_used[t], uniform_len);
         if (t == nt - 1) m.n_words = 2 * (base + J.sums[(size_t)k * nt + t]);
     }
 }
@@ -296,6 +400,9 @@ bool gf_pack_start(GfPackMate* mates, int n_mates, bool check_only, bool wait_if
     J.sums.assign((size_t)n_mates * nt, 0);
     J.bad[0].store(0);
     J.bad[1].store(0);
+    J.ragged[0].store(0);
+    J.ragged[1].store(0);
+    { const char* e = getenv("GF_PACK_NT"); g_nt_stores = !(e && atoi(e) == 0); }
     for (int k = 0; k < n_mates; k++) mates[k].n_threads = nt;
     if (!J.fn) J.fn = pack_worker;
     J.t_start = std::chrono::steady_clock::now();

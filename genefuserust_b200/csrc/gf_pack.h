@@ -16,6 +16,11 @@ struct GfPackMate {       /* one mate of one pipeline chunk */
     uint32_t* xwords;
     uint32_t* xoff;
     uint32_t max_len;                              /* in: no read may be longer (checked by the packing threads) */
+    bool compact;                                  /* in: leave out what the device can make up itself — `woff` is not written when
+                                                      every read of the chunk has the same length (uniform_len), `xoff` only by
+                                                      the threads that met a flagged read (xoff_written) */
+    uint32_t uniform_len;                          /* out: != 0 = every read has this length (woff[i] = i * 2 * ceil(len / 32)) */
+    uint8_t xoff_written[GF_PACK_MAX_THREADS];     /* out (compact): thread t wrote its part of `xoff` (reads n t / nt .. n (t + 1) / nt) */
     uint32_t bad_offsets;                          /* out: != 0 = offsets that do not ascend, or a read longer than max_len:
                                                       nothing of this chunk may be used */
     uint64_t n_words;                              /* entries of `words` in use */

@@ -448,6 +448,64 @@ def test_packed_upload_parity(mappers, small_panel, monkeypatch):
     assert_same_matches(got_se, want_se, "packed upload, single end")
 
 
+def test_packed_upload_uniform_chunks(mappers, small_panel, monkeypatch):
+    """packed upload, compact form: a chunk whose reads all have one length sends no offset tables (the device fills them,
+    k_fill_uniform) and no exception table unless a read of the chunk has a byte that is not upper-case ACGT — and then only
+    the packing threads that met one wrote their part of it.  2x100 reads, exceptions in one narrow region of the batch only,
+    every chunk packed / the hybrid mix, several thread counts and chunk sizes: records equal the oracle's."""
+    import torch
+    m, o = mappers
+    rng = random.Random(11)
+    genes = small_panel.seqs
+    comp = bytes.maketrans(b"ACGTacgt", b"TGCAtgca")
+    n = 60000
+    r1s, r2s = [], []
+    for k in range(n):
+        ga = rng.randrange(len(genes))
+        sa = rng.randrange(0, max(1, len(genes[ga]) - 400))
+        if k % 4 == 0:
+            gb = rng.randrange(len(genes))
+            sb = rng.randrange(0, max(1, len(genes[gb]) - 400))
+            x = rng.randint(40, 200)
+            frag = bytearray(genes[ga][sa:sa + x].tobytes() + genes[gb][sb:sb + 300 - x].tobytes())
+        else:
+            frag = bytearray(genes[ga][sa:sa + 300].tobytes())
+        frag = frag[:rng.randint(100, 300)]
+        if len(frag) < 100:
+            frag = frag + bytearray(b"A" * (100 - len(frag)))
+        if 20000 <= k < 20500 and k % 2 == 0:   # the only flagged reads of the batch
+            frag[rng.randrange(100)] = rng.choice(b"acgtNn@")
+            frag[len(frag) - 1 - rng.randrange(100)] = rng.choice(b"acgtNn@")
+        r1 = bytes(frag[:100])
+        r2 = bytes(frag[::-1]).translate(comp)[:100]
+        q = lambda c: bytes(rng.choice(b"EEEEEEA/") for _ in range(c))
+        r1s.append((r1, q(100)))
+        r2s.append((r2, q(100)))
+    b = ReadBatch.from_reads(r1s, r2s)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    bp = ReadBatch(pin(b.seq1), pin(b.qual1), pin(b.off1.view(np.int64)).view(np.uint64),
+                   pin(b.seq2), pin(b.qual2), pin(b.off2.view(np.int64)).view(np.uint64))
+    bp.max_len = 100
+    want = o.scan(b, threads=8)
+    assert len(want) > 300
+    for force, chunk_mb, threads in (("1", "1", "5"), ("1", "8", "16"), ("1", "64", "3"), (None, "1", "8"), (None, "2", "12")):
+        if force is None:
+            monkeypatch.delenv("GF_HOST_PACK", raising=False)
+            monkeypatch.setenv("GF_PACK_MIN_THREADS", "1")
+        else:
+            monkeypatch.setenv("GF_HOST_PACK", force)
+        monkeypatch.setenv("GF_CHUNK_MB", chunk_mb)
+        monkeypatch.setenv("GF_PACK_THREADS", threads)
+        got = m.scan_pair_end(bp)
+        st = m.map_stats()
+        if st.packed_upload == 0 and force == "1":
+            pytest.skip("host without AVX-512BW: the packed upload is not offered")
+        if force == "1":
+            assert st.packed_upload == 1
+            assert st.h2d_bytes < 0.3 * (b.seq1.size + b.seq2.size)   # plane words only: 32 of 100 bytes per read
+        assert_same_matches(got, want, f"packed upload, uniform reads, force={force} chunk={chunk_mb} MB threads={threads}")
+
+
 @pytest.mark.parametrize("pinned", [False, True])
 def test_list_mode_concurrent_handles(host, small_panel, pinned, monkeypatch):
     """multi-CSV list mode (fusion_scan.rs:62-188): one index per CSV, used concurrently from different host

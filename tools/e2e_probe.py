@@ -53,14 +53,13 @@ def run(tag, hint, env):
 
 
 run("hybrid upload (default)", 150, {})
-for t in ("4", "8", "12", "16"):
-    run(f"hybrid upload, {t} packing threads", 150, {"GF_PACK_THREADS": t})
-for mb in ("96", "128", "192", "256", "768"):
+run("hybrid upload, ordinary stores", 150, {"GF_PACK_NT": "0"})
+for mb in ("96", "128", "384"):
     run(f"hybrid upload, chunk {mb} MB", 150, {"GF_CHUNK_MB": mb})
+for t in ("6", "8", "10", "14"):
+    run(f"hybrid upload, {t} packing threads", 150, {"GF_PACK_THREADS": t, "GF_PACK_MIN_THREADS": "1"})
+for a in ("0", "2", "8"):
+    run(f"hybrid upload, ascii ahead {a} ms", 150, {"GF_ASCII_AHEAD_MS": a})
 run("every chunk packed", 150, {"GF_HOST_PACK": "1"})
-os.environ["GF_HOST_PACK"] = "0"
-run("hint=150 (per-chunk check), zero-copy qual", 150, {})
-run("hint=0 (pre-scan), zero-copy qual", 0, {})
-run("hint=150, qualities copied", 150, {"GF_ZEROCOPY_QUAL": "0"})
-for mb in ("48", "96", "384", "768"):
-    run(f"hint=150, zero-copy, chunk {mb} MB", 150, {"GF_CHUNK_MB": mb})
+run("every chunk packed, ordinary stores", 150, {"GF_HOST_PACK": "1", "GF_PACK_NT": "0"})
+run("hybrid upload (default) again", 150, {})
