@@ -777,7 +777,7 @@ def main():
         configs["fastq_text"] = rec
         # ---- the same reads as .fq.gz files fed as byte streams (gf_fastq_stream_*, SURVEY 8(f) #2: fastq_reader.rs:39-69,149-179):
         # one gzip member per file (inflate is sequential: one host thread per mate) and BGZF (what bgzip / bcl2fastq write:
-        # members of <= 64 KB, inflated by all host threads)
+        # members of <= 64 KB: their compressed payloads cross PCIe and the device inflates them, one warp per member)
         import gzip as _gzip
         from genefuserust_b200.host import bgzf_compress
         Pz = 250_000                                   # (compressing the bench input in Python is the slow part)
@@ -786,8 +786,11 @@ def main():
         want_z = None
         if oracle is not None:
             want_z = want[want["pair_idx"] < Pz]
-        gz_rec = {"workload": f"{Pz} pairs 2x150 as two .fq.gz byte streams through gf_fastq_stream_feed (8 MiB pieces): host "
-                              "inflate + H2D of the text + record splitting + mapping", "pairs": Pz, "unit": UNIT}
+        gz_rec = {"workload": f"{Pz} pairs 2x150 as two .fq.gz byte streams through gf_fastq_stream_feed (8 MiB pieces): "
+                              "gzip_single_member = host inflate (zlib, one thread per mate) + H2D of the text; bgzf = H2D of the "
+                              "compressed members + inflate on the device (k_bgzf_inflate, a warp per member; GF_BGZF_DEVICE=0: "
+                              "all host threads); then record splitting + mapping", "pairs": Pz, "unit": UNIT,
+                  "bgzf_inflate": "host" if os.environ.get("GF_BGZF_DEVICE") == "0" else "device"}
         for kind, enc in (("gzip_single_member", lambda d: _gzip.compress(d, compresslevel=1)), ("bgzf", lambda d: bgzf_compress(d))):
             e1, e2 = enc(raw1), enc(raw2)
             # one stream, the files fed three times over (a gzip file may be several files concatenated: MultiGzDecoder): the

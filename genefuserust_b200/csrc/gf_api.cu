@@ -122,6 +122,9 @@ void destroy_handle(gf_index* idx) {
     idx->ws_seq_lists.release();
     idx->fq[0].release();
     idx->fq[1].release();
+    idx->bgzf_comp[0].release(); idx->bgzf_comp[1].release();
+    idx->bgzf_members[0].release(); idx->bgzf_members[1].release();
+    idx->bgzf_status.release();
     for (auto& s : idx->stage) {
         s.seq1.release(); s.qual1.release(); s.off1.release();
         s.seq2.release(); s.qual2.release(); s.off2.release();
@@ -907,13 +910,26 @@ int gf_map_fastq(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8
 
 } /* extern "C" */
 
-int gf_map_fastq_text(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8_t* fq2, uint64_t bytes2, bool final_chunk,
-                      gf_match* out, uint64_t out_cap, uint64_t* n_out, uint64_t* n_records, uint64_t consumed[2]) {
+int gf_fastq_fetch_text(gf_index* idx, int k, uint64_t from, uint64_t len, uint8_t* dst) {
+    if (!idx || (len && !dst)) return fail(GF_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    GF_CUDA_TRY(cudaSetDevice(idx->device));
+    const GfBuf& b = k ? idx->stage[0].seq2 : idx->stage[0].seq1;
+    if (from + len > b.cap) return fail(GF_E_INVALID, "text range outside the staged chunk");
+    if (len) GF_CUDA_TRY(cudaMemcpy(dst, b.as<uint8_t>() + from, len, cudaMemcpyDeviceToHost));
+    return GF_OK;
+}
+
+int gf_map_fastq_text(gf_index* idx, const uint8_t* fq1, uint64_t host1, const uint8_t* fq2, uint64_t host2, bool final_chunk,
+                      gf_match* out, uint64_t out_cap, uint64_t* n_out, uint64_t* n_records, uint64_t consumed[2],
+                      const GfFastqMembers* members) {
+    /* the text of a mate: host bytes, then (gf_fastq_stream, blocked gzip) the text of BGZF members that are still compressed */
+    const uint64_t bytes1 = host1 + (members ? members[0].text_bytes : 0), bytes2 = host2 + (members && fq2 ? members[1].text_bytes : 0);
     if (!idx || !n_out || !n_records) return fail(GF_E_INVALID, "NULL argument");
     *n_out = 0;
     *n_records = 0;
     consumed[0] = consumed[1] = 0;
-    if ((bytes1 && !fq1) || (bytes2 && !fq2)) return fail(GF_E_INVALID, "NULL FASTQ buffer");
+    if ((host1 && !fq1) || (host2 && !fq2)) return fail(GF_E_INVALID, "NULL FASTQ buffer");
     if (out_cap && !out) return fail(GF_E_INVALID, "out is NULL");
     std::lock_guard<std::mutex> lk(idx->mu);
     GF_CUDA_TRY(cudaSetDevice(idx->device));
@@ -926,10 +942,50 @@ int gf_map_fastq_text(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const 
     GF_CUDA_TRY(cudaEventRecord(idx->ev_start, st));
     /* raw text -> device (the sequence and quality "arenas" are the text itself) */
     GF_CUDA_TRY(sg.seq1.reserve(bytes1 + 32));
-    GF_CUDA_TRY(cudaMemcpyAsync(sg.seq1.p, fq1, bytes1, cudaMemcpyHostToDevice, st));
+    if (host1) GF_CUDA_TRY(cudaMemcpyAsync(sg.seq1.p, fq1, host1, cudaMemcpyHostToDevice, st));
     if (pe) {
         GF_CUDA_TRY(sg.seq2.reserve(bytes2 + 32));
-        GF_CUDA_TRY(cudaMemcpyAsync(sg.seq2.p, fq2, bytes2, cudaMemcpyHostToDevice, st));
+        if (host2) GF_CUDA_TRY(cudaMemcpyAsync(sg.seq2.p, fq2, host2, cudaMemcpyHostToDevice, st));
+    }
+    uint64_t h2d_members = 0;
+    bool inflated = false;
+    if (members) { /* compressed bytes cross PCIe, the members are inflated here (gf_fastq.cu: k_bgzf_inflate) */
+        GF_CUDA_TRY(idx->bgzf_status.reserve(4 * sizeof(unsigned int)));
+        if (pe && members[1].n_members) { /* (mate 2's buffers may still be in use by work queued on `st` before this call) */
+            GF_CUDA_TRY(cudaEventRecord(sg.done, st));
+            GF_CUDA_TRY(cudaStreamWaitEvent(idx->copy_stream, sg.done, 0));
+        }
+        for (int k = 0; k < (pe ? 2 : 1); k++) {
+            const GfFastqMembers& mk = members[k];
+            if (!mk.n_members) continue;
+            /* the two mates side by side: mate 2's members go through the copy stream (a warp per member: one mate's members
+             * alone leave half of the SMs' warp slots empty) */
+            cudaStream_t ks = k ? idx->copy_stream : st;
+            GF_CUDA_TRY(idx->bgzf_comp[k].reserve(mk.comp_bytes + 16));
+            GF_CUDA_TRY(idx->bgzf_members[k].reserve(sizeof(GfBgzfMember) * mk.n_members));
+            GF_CUDA_TRY(cudaMemcpyAsync(idx->bgzf_comp[k].p, mk.comp, mk.comp_bytes, cudaMemcpyHostToDevice, ks));
+            GF_CUDA_TRY(cudaMemcpyAsync(idx->bgzf_members[k].p, mk.members, sizeof(GfBgzfMember) * mk.n_members, cudaMemcpyHostToDevice, ks));
+            int r = gf_bgzf_inflate_device(idx->bgzf_comp[k].as<uint8_t>(), idx->bgzf_members[k].as<GfBgzfMember>(), mk.n_members,
+                                           (k ? sg.seq2 : sg.seq1).as<uint8_t>() + (k ? host2 : host1),
+                                           idx->bgzf_status.as<unsigned int>() + 2 * k, ks);
+            if (r != GF_OK) return r;
+            if (k) {
+                GF_CUDA_TRY(cudaEventRecord(sg.copied, ks));
+                GF_CUDA_TRY(cudaStreamWaitEvent(st, sg.copied, 0));
+            }
+            idx->launches++;
+            h2d_members += mk.comp_bytes + sizeof(GfBgzfMember) * mk.n_members;
+            inflated = true;
+        }
+        if (inflated) { /* nothing of a chunk with a corrupt member is used */
+            unsigned int stt[4] = {0, 0, 0, 0};
+            GF_CUDA_TRY(cudaMemcpyAsync(stt, idx->bgzf_status.p, sizeof(stt), cudaMemcpyDeviceToHost, st));
+            GF_CUDA_TRY(cudaStreamSynchronize(st));
+            for (int k = 0; k < (pe ? 2 : 1); k++)
+                if (members[k].n_members && stt[2 * k])
+                    return fail(GF_E_INVALID, std::string("gzip stream of mate ") + (k ? "2" : "1") + " is corrupt (BGZF block " +
+                                                  std::to_string(stt[2 * k + 1] - 1) + " of the chunk, error bits " + std::to_string(stt[2 * k]) + ")");
+        }
     }
     int rc = gf_fastq_parse_device(sg.seq1.as<uint8_t>(), bytes1, &idx->fq[0], st, final_chunk);
     if (rc == GF_OK && pe) rc = gf_fastq_parse_device(sg.seq2.as<uint8_t>(), bytes2, &idx->fq[1], st, final_chunk);
@@ -938,7 +994,7 @@ int gf_map_fastq_text(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const 
     const uint64_t n = pe ? std::min(idx->fq[0].n_records, idx->fq[1].n_records) : idx->fq[0].n_records;
     *n_records = n;
     idx->stats.n_pairs = n;
-    idx->stats.h2d_bytes = bytes1 + (pe ? bytes2 : 0);
+    idx->stats.h2d_bytes = host1 + (pe ? host2 : 0) + h2d_members;
     if (n == 0) return GF_OK;
     /* bytes the n whole records cover = one past the newline that ends record n - 1's quality line (shifted table: nl[4 n]) */
     for (int k = 0; k < (pe ? 2 : 1); k++) {

@@ -12,6 +12,7 @@
  *   k_records    record i: sequence = (NL[4i], NL[4i+1]), quality = (NL[4i+2], NL[4i+3]); max length; checks
  */
 #include "gf_internal.h"
+#include "gf_inflate.cuh"
 
 namespace {
 
@@ -160,6 +161,230 @@ int gf_fastq_parse_device(const uint8_t* d_text, uint64_t bytes, GfFastqTable* o
             return GF_E_INVALID;
         }
     }
+    GF_CUDA_TRY(cudaGetLastError());
+    return GF_OK;
+}
+
+/* ---- BGZF members -> text, one WARP per member (csrc/gf_inflate.cuh holds the tables, the symbol decoder and a single-thread
+ * reference version that the CPU tests check against zlib).  Decoding a DEFLATE stream is a chain of dependent steps, so lane 0
+ * walks it alone — header, tables, symbol after symbol, literals stored as they come — and the other 31 lanes join for what is
+ * parallel: every match is copied by the whole warp (byte i of it is byte i mod dist of the `dist` bytes before it, so an
+ * overlapping match is no special case).  A thread per member was measured first: the 32 streams of a warp are never at the same
+ * instruction, the warp runs them one after the other and every copied byte costs an L2 round trip (1.1 GB/s of text per GPU);
+ * a warp per member keeps ~26 members in flight per SM, each at the speed of its own chain.  The 8 decoding tables of a block
+ * live in shared memory (2.5 KB each) next to the four CRC-32 tables.  Every member's sizes and CRC-32 are known from its header
+ * and trailer: a member that does not come out exactly is reported through `status`, never used. ---- */
+namespace {
+constexpr int INF_WARPS = 8;
+constexpr size_t INF_TABLES = (sizeof(gfinf::Tables) + 15) / 16 * 16;
+constexpr size_t INF_SMEM = INF_WARPS * INF_TABLES + (4 * 256 + 32) * sizeof(uint32_t);
+
+struct Bits32 { /* gfinf::Bits with 32-bit loads (lane 0 only) */
+    const uint8_t* in;
+    uint32_t n, pos;
+    uint64_t buf;
+    uint32_t cnt;
+    __device__ __forceinline__ bool word_ok() const { return (((uintptr_t)(in + pos)) & 3u) == 0 && pos + 4 <= n; }
+    __device__ __forceinline__ void refill() { /* >= 32 valid bits afterwards (zeros behind the input: `over` tells) */
+        if (cnt > 32) return;
+        while (cnt <= 56 && !word_ok()) { /* up to the next aligned word, or the last bytes of the input */
+            const uint64_t b = pos < n ? __ldg(in + pos) : 0u;
+            pos++;
+            buf |= b << cnt;
+            cnt += 8;
+        }
+        if (cnt <= 32) { /* (then word_ok() holds) */
+            buf |= (uint64_t)__ldg(reinterpret_cast<const uint32_t*>(in + pos)) << cnt;
+            pos += 4;
+            cnt += 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek(uint32_t k) const { return (uint32_t)(buf & ((1ull << k) - 1ull)); }
+    __device__ __forceinline__ void drop(uint32_t k) { buf >>= k; cnt -= k; }
+    __device__ __forceinline__ uint32_t take(uint32_t k) { const uint32_t v = peek(k); drop(k); return v; }
+    __device__ __forceinline__ uint32_t used_bytes() const { return pos - (cnt >> 3); }
+    __device__ __forceinline__ bool over() const { return used_bytes() > n; }
+};
+
+__constant__ uint16_t c_lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t c_lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t c_dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t c_dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ uint8_t c_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+/* lane 0: the header of the next block; returns an error code, sets *stored (a stored block was copied, no symbols follow) */
+__device__ int block_header(Bits32& b, gfinf::Tables& T, uint8_t* out, uint32_t out_len, uint32_t* op, uint32_t* last, bool* stored) {
+    using namespace gfinf;
+    b.refill();
+    *last = b.take(1);
+    const uint32_t type = b.take(2);
+    *stored = false;
+    if (type == 3) return E_BTYPE;
+    if (type == 0) {
+        b.drop(b.cnt & 7u);
+        while (b.cnt < 32) { const uint64_t x = b.pos < b.n ? __ldg(b.in + b.pos) : 0u; b.pos++; b.buf |= x << b.cnt; b.cnt += 8; }
+        const uint32_t len = b.take(16), nlen = b.take(16);
+        if ((len ^ 0xFFFFu) != nlen) return E_STORED;
+        uint32_t ip = b.used_bytes();
+        if (ip + len > b.n) return E_INPUT;
+        if (*op + len > out_len) return E_OUTPUT;
+        for (uint32_t i = 0; i < len; i++) out[*op + i] = __ldg(b.in + ip + i);
+        *op += len;
+        b.pos = ip + len; b.buf = 0; b.cnt = 0;
+        *stored = true;
+        return OK;
+    }
+    if (type == 1) {
+        fixed_lengths(T.lens);
+        build(T.lens, 288, T.lcount, T.lsym, T.lit, LBITS);
+        build(T.lens + 288, 30, T.dcount, T.dsym, T.dist, DBITS);
+        return OK;
+    }
+    const uint32_t nlen = b.take(5) + 257, ndist = b.take(5) + 1, ncode = b.take(4) + 4;
+    if (nlen > 286 || ndist > 30) return E_CODELEN;
+    uint8_t cl[19];
+    for (int i = 0; i < 19; i++) cl[i] = 0;
+    for (uint32_t i = 0; i < ncode; i++) { b.refill(); cl[c_order[i]] = (uint8_t)b.take(3); }
+    if (build(cl, 19, T.dcount, T.dsym, T.dist, 7) != 0) return E_CODELEN;
+    uint32_t i = 0;
+    while (i < nlen + ndist) {
+        b.refill();
+        const int s = decode_sym(b, T.dist, 7, T.dcount, T.dsym);
+        if (s < 0) return E_CODELEN;
+        if (s < 16) { T.lens[i++] = (uint8_t)s; continue; }
+        uint32_t rep, val = 0;
+        if (s == 16) { if (i == 0) return E_CODELEN; val = T.lens[i - 1]; rep = 3 + b.take(2); }
+        else if (s == 17) rep = 3 + b.take(3);
+        else rep = 11 + b.take(7);
+        if (i + rep > nlen + ndist) return E_CODELEN;
+        while (rep--) T.lens[i++] = (uint8_t)val;
+    }
+    if (T.lens[256] == 0) return E_CODELEN;
+    uint8_t dl[30];
+    for (uint32_t d = 0; d < 30; d++) dl[d] = d < ndist ? T.lens[nlen + d] : 0;
+    for (uint32_t s = nlen; s < 288; s++) T.lens[s] = 0;
+    const int rl = build(T.lens, 288, T.lcount, T.lsym, T.lit, LBITS);
+    if (rl < 0 || (rl > 0 && !(T.lcount[1] == 1 && T.lcount[0] == 287))) return E_CODELEN;
+    const int rd = build(dl, 30, T.dcount, T.dsym, T.dist, DBITS);
+    if (rd < 0 || (rd > 0 && !(T.dcount[1] == 1 && T.dcount[0] == 29))) return E_CODELEN;
+    return OK;
+}
+
+__global__ void __launch_bounds__(INF_WARPS * 32) k_bgzf_inflate(const uint8_t* __restrict__ comp, const GfBgzfMember* __restrict__ members,
+                                                                uint32_t n, uint8_t* text, unsigned int* __restrict__ status) {
+    using namespace gfinf;
+    extern __shared__ __align__(16) unsigned char inf_smem[];
+    uint32_t* crc_t = reinterpret_cast<uint32_t*>(inf_smem + INF_WARPS * INF_TABLES);
+    uint32_t* x2n = crc_t + 4 * 256;
+    crc_tables(crc_t, (int)threadIdx.x, INF_WARPS * 32);
+    if (threadIdx.x == INF_WARPS * 32 - 1) crc_x2n_table(x2n);
+    __syncthreads();
+    crc_tables_rest(crc_t, (int)threadIdx.x, INF_WARPS * 32);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const uint32_t i = blockIdx.x * INF_WARPS + wib;
+    if (i >= n) return;
+    Tables& T = *reinterpret_cast<Tables*>(inf_smem + wib * INF_TABLES);
+    const GfBgzfMember m = members[i];
+    uint8_t* out = text + m.out_off;
+    const uint32_t out_len = m.isize;
+    Bits32 b{comp + m.in_off, m.clen, 0, 0, 0};
+    uint32_t op = 0, last = 0; /* lane 0's: where the next decoded byte goes (the match being copied is counted already) */
+    bool in_block = false;
+    int err = OK;
+    /* The copy of a match overlaps with the decoding of what follows it: every lane asks for its source byte (an L2 round
+     * trip), lane 0 decodes on to the next match while the bytes are on their way, then they are stored. */
+    uint32_t c_len = 0, c_dist = 0, c_op = 0; /* the match being copied (c_len == 0: none) */
+    for (;;) {
+        const bool mine = lane < c_len;
+        const uint8_t* src = out + c_op - c_dist;
+        const bool apart = c_dist >= c_len; /* else byte k of the match is byte k mod dist of the `dist` bytes before it */
+        uint8_t v = 0;
+        if (mine) v = __ldcg(src + (apart ? lane : lane % c_dist));
+        /* lane 0 decodes up to the next match (state 0), the end of the member (1) or an error (2) */
+        uint32_t state = 0, len = 0, dist = 0;
+        if (lane == 0) {
+            for (;;) {
+                if (!in_block) {
+                    if (last) { state = 1; break; }
+                    bool stored = false;
+                    err = block_header(b, T, out, out_len, &op, &last, &stored);
+                    if (err == OK && b.over()) err = E_INPUT;
+                    if (err != OK) { state = 2; break; }
+                    in_block = !stored;
+                    continue;
+                }
+                b.refill();
+                int s = decode_sym(b, T.lit, LBITS, T.lcount, T.lsym);
+                if (s < 0) { err = E_SYMBOL; state = 2; break; }
+                if (s < 256) {
+                    if (op >= out_len) { err = E_OUTPUT; state = 2; break; }
+                    out[op++] = (uint8_t)s;
+                    continue;
+                }
+                if (s == 256) {
+                    in_block = false;
+                    if (b.over()) { err = E_INPUT; state = 2; break; }
+                    continue;
+                }
+                s -= 257;
+                if (s >= 29) { err = E_SYMBOL; state = 2; break; }
+                len = c_lbase[s] + b.take(c_lext[s]);
+                b.refill();
+                const int d = decode_sym(b, T.dist, DBITS, T.dcount, T.dsym);
+                if (d < 0 || d >= 30) { err = E_SYMBOL; state = 2; break; }
+                dist = c_dbase[d] + b.take(c_dext[d]);
+                if (dist > op) { err = E_DIST; state = 2; break; }
+                if (op + len > out_len) { err = E_OUTPUT; state = 2; break; }
+                break; /* state 0: a match for the whole warp */
+            }
+        }
+        if (mine) out[c_op + lane] = v;
+        for (uint32_t k = lane + 32; k < c_len; k += 32) out[c_op + k] = __ldcg(src + (apart ? k : k % c_dist));
+        const uint32_t packed = __shfl_sync(0xFFFFFFFFu, state | (len << 2) | (dist << 11), 0); /* len <= 258, dist <= 32768 */
+        const uint32_t op0 = __shfl_sync(0xFFFFFFFFu, op, 0);
+        if ((packed & 3u) != 0) break;
+        c_len = (packed >> 2) & 0x1FFu;
+        c_dist = packed >> 11;
+        c_op = op0;
+        if (lane == 0) op += c_len;
+        __syncwarp(); /* what lane 0 and the copy stored is visible to the lanes that read it next */
+    }
+    if (lane == 0) {
+        if (err == OK && op != out_len) err = E_OUTPUT;
+        if (err == OK && b.used_bytes() != m.clen) err = E_TRAILING;
+    }
+    err = __shfl_sync(0xFFFFFFFFu, err, 0);
+    __syncwarp();
+    if (err == OK) {
+        /* CRC-32 of the trailer: every lane takes one slice (the bytes were written by all lanes: read around L1), the partial
+         * values are combined as zlib's crc32_combine does: crc(A B) = crc(A) x^(8 |B|) mod P ^ crc(B) */
+        const uint32_t per = ((out_len + 31) / 32 + 3) & ~3u;
+        const uint32_t a0 = min(lane * per, out_len), b0 = min((lane + 1) * per, out_len);
+        uint32_t c = 0xFFFFFFFFu, k = a0;
+        for (; k < b0 && (((uintptr_t)(out + k)) & 3u); k++) c = crc_t[(c ^ __ldcg(out + k)) & 0xFFu] ^ (c >> 8);
+        for (; k + 4 <= b0; k += 4) {
+            c ^= __ldcg(reinterpret_cast<const uint32_t*>(out + k));
+            c = crc_t[3 * 256 + (c & 0xFFu)] ^ crc_t[2 * 256 + ((c >> 8) & 0xFFu)] ^ crc_t[256 + ((c >> 16) & 0xFFu)] ^ crc_t[c >> 24];
+        }
+        for (; k < b0; k++) c = crc_t[(c ^ __ldcg(out + k)) & 0xFFu] ^ (c >> 8);
+        const uint32_t part = b0 > a0 ? crc_multmodp(crc_x8n(out_len - b0, x2n), ~c) : 0u;
+        const uint32_t total = __reduce_xor_sync(0xFFFFFFFFu, part);
+        if (total != m.crc) err = 9;
+    }
+    if (lane == 0 && err != OK) {
+        atomicOr(&status[0], 1u << err);
+        atomicMax(&status[1], i + 1u);
+    }
+}
+}  // namespace
+
+int gf_bgzf_inflate_device(const uint8_t* d_comp, const GfBgzfMember* d_members, uint32_t n, uint8_t* d_text, unsigned int* d_status,
+                           cudaStream_t st) {
+    GF_CUDA_TRY(cudaFuncSetAttribute(k_bgzf_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INF_SMEM));
+    GF_CUDA_TRY(cudaMemsetAsync(d_status, 0, 2 * sizeof(unsigned int), st));
+    if (n == 0) return GF_OK;
+    k_bgzf_inflate<<<(n + INF_WARPS - 1) / INF_WARPS, INF_WARPS * 32, INF_SMEM, st>>>(d_comp, d_members, n, d_text, d_status);
     GF_CUDA_TRY(cudaGetLastError());
     return GF_OK;
 }

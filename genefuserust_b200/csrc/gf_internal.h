@@ -120,6 +120,25 @@ struct GfChunkEvents { /* start, after k_prep, k_seed, k_diag, the whole screen,
     cudaEvent_t e[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
+/* gf_fastq.cu: BGZF members of a .fq.gz chunk inflated on the device, one thread per member (csrc/gf_inflate.cuh) */
+struct GfBgzfMember {
+    uint64_t in_off;  /* raw DEFLATE payload inside the compressed buffer */
+    uint64_t out_off; /* where its text goes */
+    uint32_t clen, isize, crc, pad;
+};
+/* status[0]: OR of (1 << error code) over the members, status[1]: 1 + index of a failing member */
+int gf_bgzf_inflate_device(const uint8_t* d_comp, const GfBgzfMember* d_members, uint32_t n, uint8_t* d_text, unsigned int* d_status,
+                           cudaStream_t st);
+/* per mate of gf_map_fastq_text: text that is partly on the host (`prefix` bytes, passed as fq1 / fq2) and partly still
+ * compressed (BGZF members: their payloads back to back in `comp`, pinned host memory) */
+struct GfFastqMembers {
+    const uint8_t* comp = nullptr;
+    uint64_t comp_bytes = 0;
+    const GfBgzfMember* members = nullptr;
+    uint32_t n_members = 0;
+    uint64_t text_bytes = 0; /* sum of isize */
+};
+
 struct gf_index {
     int device = 0;
     gf_params params{};
@@ -150,6 +169,7 @@ struct gf_index {
                                                                   (plane words, meta, seeds); counters + the two class lists */
     GfStage stage[GF_STAGES];
     GfPackSet pack_set[GF_PACK_SETS];
+    GfBuf bgzf_comp[2], bgzf_members[2], bgzf_status; /* .fq.gz chunks inflated on the device */
     GfHostSlot* h_slots = nullptr; /* [GF_STAGES + 1]: the pipeline stages + the device-batch path (GF_SLOT_DEVICE) */
     bool stats_pending = false;    /* h_slots[2] is being written by an unsynchronised device-batch call */
     uint64_t pending_pairs = 0;
@@ -171,7 +191,10 @@ int gf_fastq_parse_device(const uint8_t* d_text, uint64_t bytes, GfFastqTable* o
 /* gf_api.cu: gf_map_fastq's body.  final_chunk = false (gf_fastq_stream_*): only whole records are mapped and consumed[k]
  * returns how many bytes of buffer k they covered (the caller carries the rest over); pair_idx counts from 0. */
 int gf_map_fastq_text(gf_index* idx, const uint8_t* fq1, uint64_t bytes1, const uint8_t* fq2, uint64_t bytes2, bool final_chunk,
-                      gf_match* out, uint64_t out_cap, uint64_t* n_out, uint64_t* n_records, uint64_t consumed[2]);
+                      gf_match* out, uint64_t out_cap, uint64_t* n_out, uint64_t* n_records, uint64_t consumed[2],
+                      const GfFastqMembers* members = nullptr /* [2]: BGZF members that follow the host text, inflated on the device */);
+/* after gf_map_fastq_text: bytes [from, from + len) of mate k's text as the device saw it (the unconsumed tail of a chunk) */
+int gf_fastq_fetch_text(gf_index* idx, int k, uint64_t from, uint64_t len, uint8_t* dst);
 
 /* gf_map.cu */
 struct GfDevBatch {

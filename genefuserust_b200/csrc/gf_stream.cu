@@ -226,6 +226,13 @@ struct gf_fastq_stream {
     int format = GF_FQ_PLAIN;
     uint64_t chunk_bytes = 256ull << 20;
     PinnedArena text[2];
+    /* blocked gzip, inflated on the device (GF_BGZF_DEVICE=0: on the host threads): the members' payloads back to back and their
+     * descriptors; their text follows text[k].fill in the mate's logical text */
+    bool device_inflate = true;
+    PinnedArena comp[2];
+    std::vector<GfBgzfMember> members[2];
+    uint64_t pending_text[2] = {0, 0};
+    std::vector<uint8_t> carry[2]; /* the first bytes of a BGZF member that the fed piece cut in two */
     z_stream z[2];
     bool z_open[2] = {false, false}, z_member_done[2] = {true, true};
     bool eof_seen[2] = {false, false};
@@ -246,14 +253,25 @@ namespace {
 /* maps the whole records buffered so far; final_chunk: the files have ended */
 int fq_map_locked(gf_fastq_stream* s, bool final_chunk) {
     const int nm = s->paired ? 2 : 1;
-    if (s->text[0].fill == 0 && (!s->paired || s->text[1].fill == 0)) return GF_OK;
+    const uint64_t total[2] = {s->text[0].fill + s->pending_text[0], s->text[1].fill + s->pending_text[1]};
+    if (total[0] == 0 && (!s->paired || total[1] == 0)) return GF_OK;
     if (s->tmp.size() < 4096) s->tmp.resize(4096);
     uint64_t got = 0, nrec = 0, consumed[2] = {0, 0};
     int rc;
     const auto tm0 = std::chrono::steady_clock::now();
+    GfFastqMembers mem[2];
+    const bool have_members = !s->members[0].empty() || !s->members[1].empty();
+    for (int k = 0; k < nm; k++) {
+        mem[k].comp = s->comp[k].p;
+        mem[k].comp_bytes = s->comp[k].fill;
+        mem[k].members = s->members[k].data();
+        mem[k].n_members = (uint32_t)s->members[k].size();
+        mem[k].text_bytes = s->pending_text[k];
+    }
     for (;;) {
         rc = gf_map_fastq_text(s->idx, s->text[0].p, s->text[0].fill, s->paired ? s->text[1].p : nullptr,
-                               s->paired ? s->text[1].fill : 0, final_chunk, s->tmp.data(), s->tmp.size(), &got, &nrec, consumed);
+                               s->paired ? s->text[1].fill : 0, final_chunk, s->tmp.data(), s->tmp.size(), &got, &nrec, consumed,
+                               have_members ? mem : nullptr);
         if (rc == GF_E_CAPACITY) { s->tmp.resize(got); continue; }
         break;
     }
@@ -269,11 +287,24 @@ int fq_map_locked(gf_fastq_stream* s, bool final_chunk) {
     s->n_calls++;
     for (int k = 0; k < nm; k++) {
         PinnedArena& t = s->text[k];
-        const size_t c = (size_t)std::min<uint64_t>(consumed[k], t.fill);
+        const uint64_t c = std::min<uint64_t>(consumed[k], total[k]);
         s->text_bytes += c;
-        if (final_chunk) { t.fill = 0; continue; }
-        memmove(t.p, t.p + c, t.fill - c);
-        t.fill -= c;
+        if (final_chunk) {
+            t.fill = 0;
+        } else if (s->members[k].empty()) {
+            memmove(t.p, t.p + c, t.fill - c);
+            t.fill -= c;
+        } else {
+            /* the unconsumed tail (usually the last, incomplete record) comes back from the device and opens the next chunk */
+            const uint64_t tail = total[k] - c;
+            if (t.reserve(tail + 64) != cudaSuccess) return sfail(GF_E_CUDA, "pinned allocation failed");
+            int r = gf_fastq_fetch_text(s->idx, k, c, tail, t.p);
+            if (r != GF_OK) return r;
+            t.fill = tail;
+        }
+        s->members[k].clear();
+        s->comp[k].fill = 0;
+        s->pending_text[k] = 0;
     }
     return GF_OK;
 }
@@ -321,14 +352,48 @@ bool bgzf_inflate_range(const std::vector<BgzfBlock>& blocks, size_t lo, size_t 
     return ok;
 }
 
-/* append decoded text of mate k from `in`; returns the input bytes consumed.  Stops early when the buffer reached
- * chunk_bytes (the caller maps and calls again). */
-int fq_append(gf_fastq_stream* s, int k, const uint8_t* in, uint64_t n, uint64_t* used, std::string* err) {
+/* how long is the BGZF member that starts with these `have` bytes?  > 0: its size; 0: cannot tell yet (so far it may be one);
+ * -1: not a BGZF member (some other gzip member: the streaming decoder takes it) */
+int64_t bgzf_member_size(const uint8_t* p, uint64_t have) {
+    static const uint8_t magic[3] = {0x1f, 0x8b, 8};
+    for (uint64_t i = 0; i < 3 && i < have; i++)
+        if (p[i] != magic[i]) return -1;
+    if (have >= 4 && (p[3] != 4)) return -1; /* FEXTRA and nothing else (other flags: streaming path) */
+    if (have < 12) return 0;
+    const uint32_t xlen = p[10] | (p[11] << 8);
+    if (have < 12 + (uint64_t)xlen) return 0;
+    for (uint32_t q = 12; q + 4 <= 12 + xlen;) {
+        const uint32_t slen = p[q + 2] | (p[q + 3] << 8);
+        if (p[q] == 'B' && p[q + 1] == 'C' && slen == 2 && q + 6 <= 12 + xlen) {
+            const int64_t bsize = (int64_t)(p[q + 4] | (p[q + 5] << 8)) + 1;
+            return bsize >= 12 + (int64_t)xlen + 8 ? bsize : -1;
+        }
+        q += 4 + slen;
+    }
+    return -1;
+}
+
+/* append decoded text of mate k from `in`; returns the input bytes consumed.  Stops early when the chunk is full: the buffer
+ * reached chunk_bytes, or (*full) the next BGZF member does not fit any more (the caller maps and calls again).
+ *
+ * Blocked gzip: whole members are never decoded here when the device inflates — only their payloads are kept, back to back in
+ * pinned memory, with the sizes and CRC-32 from their headers and trailers; a member that a piece of input cuts in two waits in
+ * `carry` for its other half, so the cut costs nothing.  Anything else (one big gzip member, members without the BGZF extra
+ * field) goes through zlib's streaming decoder into the host text buffer. */
+int fq_append(gf_fastq_stream* s, int k, const uint8_t* in, uint64_t n, uint64_t* used, bool* full, std::string* err) {
     PinnedArena& t = s->text[k];
     *used = 0;
+    *full = false;
+    const std::string corrupt = std::string("gzip stream of mate ") + (k ? "2" : "1") + " is corrupt";
     /* the text buffer is pinned once at its full size: growing a pinned buffer step by step (allocate, copy, free) costs more
      * than inflating what goes into it */
-    if (t.cap < s->chunk_bytes + 64 && t.reserve(s->chunk_bytes + 64) != cudaSuccess) { *err = "pinned allocation failed"; return GF_E_CUDA; }
+    const bool on_device = s->format == GF_FQ_GZIP && s->device_inflate; /* (then the host buffer holds little: the tail of the chunk before) */
+    if (!on_device && t.cap < s->chunk_bytes + 64 && t.reserve(s->chunk_bytes + 64) != cudaSuccess) { *err = "pinned allocation failed"; return GF_E_CUDA; }
+    if (on_device && (t.reserve(1u << 20) != cudaSuccess || /* (never NULL: a NULL second buffer means single-end to the mapping call) */
+                      (s->comp[k].cap < s->chunk_bytes / 4 && s->comp[k].reserve(s->chunk_bytes / 4 + 64) != cudaSuccess))) {
+        *err = "pinned allocation failed";
+        return GF_E_CUDA;
+    }
     if (s->format == GF_FQ_PLAIN) {
         const uint64_t room = t.fill < s->chunk_bytes ? s->chunk_bytes - t.fill : 0;
         const uint64_t c = std::min(n, room);
@@ -341,6 +406,58 @@ int fq_append(gf_fastq_stream* s, int k, const uint8_t* in, uint64_t n, uint64_t
         return GF_OK;
     }
     z_stream& z = s->z[k];
+    std::vector<uint8_t>& carry = s->carry[k];
+    /* text of this mate that is waiting to be mapped: what lies in the host buffer + what the queued members will inflate to */
+    auto logical_fill = [&]() { return (uint64_t)t.fill + s->pending_text[k]; };
+    /* queued members -> host text (the streaming inflate below appends to the host buffer, so what was queued must be there first) */
+    auto materialise = [&]() -> bool {
+        if (s->members[k].empty()) return true;
+        std::vector<BgzfBlock> blocks;
+        for (const GfBgzfMember& m : s->members[k]) blocks.push_back(BgzfBlock{s->comp[k].p + m.in_off, m.clen, m.isize, m.crc, m.out_off});
+        if (t.reserve(t.fill + s->pending_text[k] + 64) != cudaSuccess) return false;
+        if (!bgzf_inflate_range(blocks, 0, blocks.size(), t.p + t.fill)) return false;
+        t.fill += s->pending_text[k];
+        s->members[k].clear();
+        s->comp[k].fill = 0;
+        s->pending_text[k] = 0;
+        return true;
+    };
+    /* whole members (their `out` offsets count from the end of the text so far): queued for the device, or inflated here by
+     * all host threads */
+    auto take_members = [&](std::vector<BgzfBlock>& blocks, uint64_t out) -> int {
+        if (s->device_inflate) {
+            uint64_t cbytes = 0;
+            for (const BgzfBlock& b : blocks) cbytes += b.clen;
+            PinnedArena& c = s->comp[k];
+            if (c.reserve(c.fill + cbytes + 64) != cudaSuccess) { *err = "pinned allocation failed"; return GF_E_CUDA; }
+            for (const BgzfBlock& b : blocks) {
+                if (b.isize == 0) continue; /* (the empty member that ends a BGZF file) */
+                memcpy(c.p + c.fill, b.data, b.clen);
+                s->members[k].push_back(GfBgzfMember{c.fill, s->pending_text[k], b.clen, b.isize, b.crc, 0u});
+                c.fill += b.clen;
+                s->pending_text[k] += b.isize;
+            }
+            if (k == 0) s->bgzf_blocks += blocks.size();
+            return GF_OK;
+        }
+        const auto tb0 = std::chrono::steady_clock::now();
+        if (t.reserve(t.fill + out + 64) != cudaSuccess) { *err = "pinned allocation failed"; return GF_E_CUDA; }
+        const size_t nb = blocks.size();
+        const unsigned want = s->paired ? std::max(1u, std::thread::hardware_concurrency() / 2) : std::max(1u, std::thread::hardware_concurrency());
+        const size_t nt = std::max<size_t>(1, std::min<size_t>(want, (nb + 3) / 4));
+        std::vector<char> okv(nt, 1);
+        std::vector<std::thread> th;
+        uint8_t* dst = t.p + t.fill;
+        for (size_t u = 1; u < nt; u++)
+            th.emplace_back([&, u] { okv[u] = bgzf_inflate_range(blocks, nb * u / nt, nb * (u + 1) / nt, dst) ? 1 : 0; });
+        okv[0] = bgzf_inflate_range(blocks, 0, nb / nt, dst) ? 1 : 0;
+        for (auto& x : th) x.join();
+        for (char o : okv)
+            if (!o) { *err = corrupt + " (BGZF block)"; return GF_E_INVALID; }
+        t.fill += out;
+        if (k == 0) { s->bgzf_blocks += nb; s->ms_bgzf += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count(); }
+        return GF_OK;
+    };
     if (!s->z_open[k]) {
         memset(&z, 0, sizeof(z));
         if (inflateInit2(&z, 15 + 32) != Z_OK) { *err = "inflateInit2 failed"; return GF_E_INVALID; }
@@ -348,47 +465,79 @@ int fq_append(gf_fastq_stream* s, int k, const uint8_t* in, uint64_t n, uint64_t
         s->z_member_done[k] = true;
     }
     uint64_t left = n;
-    while (left && t.fill < s->chunk_bytes) {
+    while (left && logical_fill() < s->chunk_bytes) {
+        const uint8_t* zin = in + (n - left); /* what the streaming decoder would be given */
+        uint64_t zn = left;
+        bool from_carry = false;
         if (s->z_member_done[k]) {
-            /* at a member boundary: as many whole BGZF members as lie in the piece and fit the buffer, all threads */
-            std::vector<BgzfBlock> blocks;
-            uint64_t pos = n - left, out = 0;
-            const uint64_t room = s->chunk_bytes - t.fill;
-            for (;;) {
-                uint32_t total = 0;
-                BgzfBlock b;
-                if (!bgzf_block_at(in + pos, n - pos, &total, &b) || out + b.isize > room) break;
-                b.out = out;
-                out += b.isize;
-                pos += total;
-                blocks.push_back(b);
-            }
-            if (!blocks.empty()) {
-                const auto tb0 = std::chrono::steady_clock::now();
-                if (t.reserve(t.fill + out + 64) != cudaSuccess) { *err = "pinned allocation failed"; return GF_E_CUDA; }
-                const size_t nb = blocks.size();
-                const unsigned want = s->paired ? std::max(1u, std::thread::hardware_concurrency() / 2) : std::max(1u, std::thread::hardware_concurrency());
-                const size_t nt = std::min<size_t>(want, (nb + 3) / 4);
-                std::vector<char> okv(nt, 1);
-                std::vector<std::thread> th;
-                uint8_t* dst = t.p + t.fill;
-                for (size_t u = 1; u < nt; u++)
-                    th.emplace_back([&, u] { okv[u] = bgzf_inflate_range(blocks, nb * u / nt, nb * (u + 1) / nt, dst) ? 1 : 0; });
-                okv[0] = bgzf_inflate_range(blocks, 0, nb / nt, dst) ? 1 : 0;
-                for (auto& x : th) x.join();
-                for (char o : okv)
-                    if (!o) { *err = std::string("gzip stream of mate ") + (k ? "2" : "1") + " is corrupt (BGZF block)"; return GF_E_INVALID; }
-                t.fill += out;
-                left = n - pos;
-                if (k == 0) { s->bgzf_blocks += nb; s->ms_bgzf += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count(); }
-                continue;
+            if (!carry.empty()) {
+                /* the first bytes of a member came with the piece before: complete its header, then the member */
+                int64_t sz = bgzf_member_size(carry.data(), carry.size());
+                while (left && sz == 0) {
+                    carry.push_back(in[n - left]);
+                    left--;
+                    sz = bgzf_member_size(carry.data(), carry.size());
+                }
+                if (sz == 0) break; /* (input used up) */
+                if (sz > 0) {
+                    const uint64_t more = std::min<uint64_t>(left, (uint64_t)sz > carry.size() ? (uint64_t)sz - carry.size() : 0);
+                    carry.insert(carry.end(), in + (n - left), in + (n - left) + more);
+                    left -= more;
+                    if (carry.size() < (uint64_t)sz) break; /* (input used up) */
+                    uint32_t total = 0;
+                    BgzfBlock b;
+                    if (!bgzf_block_at(carry.data(), carry.size(), &total, &b)) { *err = corrupt + " (BGZF header)"; return GF_E_INVALID; }
+                    if (logical_fill() > 0 && logical_fill() + b.isize > s->chunk_bytes) { *full = true; break; } /* it opens the next chunk */
+                    b.out = 0;
+                    std::vector<BgzfBlock> one(1, b);
+                    int r = take_members(one, b.isize);
+                    if (r != GF_OK) return r;
+                    carry.clear();
+                    continue;
+                }
+                /* not BGZF after all: the streaming decoder gets the header bytes kept so far (they produce no text) */
+                zin = carry.data();
+                zn = carry.size();
+                from_carry = true;
+            } else {
+                /* at a member boundary: as many whole BGZF members as lie in the piece and fit the chunk (a chunk holds at
+                 * least one) */
+                std::vector<BgzfBlock> blocks;
+                uint64_t pos = n - left, out = 0;
+                const uint64_t room = s->chunk_bytes - logical_fill();
+                bool no_room = false;
+                for (;;) {
+                    uint32_t total = 0;
+                    BgzfBlock b;
+                    if (!bgzf_block_at(in + pos, n - pos, &total, &b)) break;
+                    if (out + b.isize > room && (logical_fill() > 0 || out > 0)) { no_room = true; break; }
+                    b.out = out;
+                    out += b.isize;
+                    pos += total;
+                    blocks.push_back(b);
+                }
+                if (!blocks.empty()) {
+                    int r = take_members(blocks, out);
+                    if (r != GF_OK) return r;
+                    left = n - pos;
+                    if (no_room) { *full = true; break; }
+                    continue;
+                }
+                if (no_room) { *full = true; break; }
+                const int64_t sz = bgzf_member_size(in + pos, n - pos);
+                if (sz == 0 || (sz > 0 && n - pos < (uint64_t)sz)) { /* a BGZF member the piece cuts in two: wait for the rest */
+                    carry.assign(in + pos, in + n);
+                    left = 0;
+                    break;
+                }
             }
         }
-        z.next_in = const_cast<Bytef*>(in + (n - left));
+        if (!materialise()) { *err = corrupt + " (BGZF block)"; return GF_E_INVALID; }
+        z.next_in = const_cast<Bytef*>(zin);
         if (t.reserve(std::min<uint64_t>(s->chunk_bytes, t.fill + (4u << 20)) + 64) != cudaSuccess) { *err = "pinned allocation failed"; return GF_E_CUDA; }
         const uint64_t room = std::min<uint64_t>(t.cap - 64, s->chunk_bytes) - t.fill;
         if (!room) break;
-        z.avail_in = (uInt)std::min<uint64_t>(left, 1u << 30);
+        z.avail_in = (uInt)std::min<uint64_t>(zn, 1u << 30);
         const uInt in0 = z.avail_in;
         z.next_out = t.p + t.fill;
         z.avail_out = (uInt)std::min<uint64_t>(room, 1u << 30);
@@ -397,13 +546,18 @@ int fq_append(gf_fastq_stream* s, int k, const uint8_t* in, uint64_t n, uint64_t
         const auto ts0 = std::chrono::steady_clock::now();
         const int zr = inflate(&z, Z_NO_FLUSH);
         if (k == 0) s->ms_stream += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count();
-        left -= in0 - z.avail_in;
+        if (from_carry) {
+            if (z.avail_in != 0) { *err = corrupt + " (gzip header)"; return GF_E_INVALID; } /* header bytes only: always taken whole */
+            carry.clear();
+        } else {
+            left -= in0 - z.avail_in;
+        }
         t.fill += out0 - z.avail_out;
         if (zr == Z_STREAM_END) { /* next member of a multi-member file (MultiGzDecoder, fastq_reader.rs:49-55) */
             s->z_member_done[k] = true;
             if (inflateReset(&z) != Z_OK) { *err = "inflateReset failed"; return GF_E_INVALID; }
         } else if (zr != Z_OK && zr != Z_BUF_ERROR) {
-            *err = std::string("gzip stream of mate ") + (k ? "2" : "1") + " is corrupt: " + (z.msg ? z.msg : "inflate error");
+            *err = corrupt + ": " + (z.msg ? z.msg : "inflate error");
             return GF_E_INVALID;
         } else if (zr == Z_BUF_ERROR && in0 == z.avail_in && out0 == z.avail_out) {
             break; /* no progress possible with this input */
@@ -425,6 +579,7 @@ int gf_fastq_stream_create(gf_index* idx, int paired, int format, uint64_t chunk
     s->paired = paired != 0;
     s->format = format;
     if (chunk_bytes) s->chunk_bytes = std::max<uint64_t>(chunk_bytes, 4096);
+    { const char* e = getenv("GF_BGZF_DEVICE"); s->device_inflate = !(e && atoi(e) == 0); }
     *out = s;
     return GF_OK;
 }
@@ -448,23 +603,24 @@ int gf_fastq_stream_feed(gf_fastq_stream* s, const uint8_t* fq1, uint64_t n1, co
     while (left[0] || left[1]) {
         /* decode both mates side by side (inflate is the host-side cost of .fq.gz input: one thread per mate) */
         uint64_t used[2] = {0, 0};
+        bool fullf[2] = {false, false};
         int rcs[2] = {GF_OK, GF_OK};
         std::string errs[2];
         std::thread other;
         if (s->paired && left[1] && s->format == GF_FQ_GZIP)
-            other = std::thread([&] { rcs[1] = fq_append(s, 1, in[1], left[1], &used[1], &errs[1]); });
+            other = std::thread([&] { rcs[1] = fq_append(s, 1, in[1], left[1], &used[1], &fullf[1], &errs[1]); });
         else if (s->paired && left[1])
-            rcs[1] = fq_append(s, 1, in[1], left[1], &used[1], &errs[1]);
-        if (left[0]) rcs[0] = fq_append(s, 0, in[0], left[0], &used[0], &errs[0]);
+            rcs[1] = fq_append(s, 1, in[1], left[1], &used[1], &fullf[1], &errs[1]);
+        if (left[0]) rcs[0] = fq_append(s, 0, in[0], left[0], &used[0], &fullf[0], &errs[0]);
         if (other.joinable()) other.join();
         for (int k = 0; k < 2; k++) {
             if (rcs[k] != GF_OK) return sfail(rcs[k], errs[k]);
             in[k] += used[k];
             left[k] -= used[k];
         }
-        const bool full0 = s->text[0].fill >= s->chunk_bytes, full1 = s->paired && s->text[1].fill >= s->chunk_bytes;
+        const uint64_t f0 = s->text[0].fill + s->pending_text[0], f1 = s->text[1].fill + s->pending_text[1];
+        const bool full0 = f0 >= s->chunk_bytes || fullf[0], full1 = s->paired && (f1 >= s->chunk_bytes || fullf[1]);
         if (full0 || full1) {
-            const size_t f0 = s->text[0].fill, f1 = s->text[1].fill;
             int rc = fq_map_locked(s, false);
             if (rc != GF_OK) return rc;
             if (s->text[0].fill == f0 && s->text[1].fill == f1) {
@@ -485,7 +641,7 @@ int gf_fastq_stream_finish(gf_fastq_stream* s) {
     GF_CUDA_TRY(cudaSetDevice(s->idx->device));
     if (s->format == GF_FQ_GZIP)
         for (int k = 0; k < (s->paired ? 2 : 1); k++)
-            if (s->z_open[k] && !s->z_member_done[k])
+            if ((s->z_open[k] && !s->z_member_done[k]) || !s->carry[k].empty())
                 return sfail(GF_E_INVALID, std::string("gzip stream of mate ") + (k ? "2" : "1") + " ends inside a member (truncated file)");
     return fq_map_locked(s, true);
 }

@@ -828,7 +828,8 @@ def test_device_batch_entry_points(host, small_panel, read_len, seed):
 def test_fastq_stream_chunked_and_gzip(mappers, small_panel, host, gz, tmp_path):
     """the two FASTQ files as byte streams (gf_fastq_stream_*): pieces that end anywhere (mid-line, mid-record,
     different piece sizes per mate), small device chunks with the tail carried over, plain, multi-member gzip and BGZF (whose
-    whole members are inflated side by side by all host threads, the cut ones by the streaming decoder); the records
+    whole members cross PCIe compressed and are inflated on the device, one warp per member — GF_BGZF_DEVICE=0: side by side by
+    all host threads —, the cut ones by the streaming decoder); the records
     must equal one gf_map_fastq call on the whole text and the oracle on the reference reader's records"""
     import gzip
     m, o = mappers
@@ -846,7 +847,7 @@ def test_fastq_stream_chunked_and_gzip(mappers, small_panel, host, gz, tmp_path)
         if not gz:
             return data
         if gz == "bgzf":       # blocked gzip: the members that lie whole in a fed piece are inflated by all host threads
-            return host.bgzf_compress(data, block=rng.choice((4000, 65280)))
+            return host.bgzf_compress(data, block=rng.choice((4000, 65280)), level=rng.choice((1, 6, 9)))
         cuts = sorted(rng.sample(range(1, len(data)), members - 1)) if members > 1 else []
         parts = [data[a:c] for a, c in zip([0] + cuts, cuts + [len(data)])]
         return b"".join(gzip.compress(p, compresslevel=1) for p in parts)     # several members, cut anywhere
@@ -882,6 +883,15 @@ def test_fastq_stream_chunked_and_gzip(mappers, small_panel, host, gz, tmp_path)
         st = host.FastqStream(m, paired=False, gz=True)
         st.feed(e1[:len(e1) // 2])
         with pytest.raises(host.GeneFuseError):
+            st.finish()
+        st.close()
+    if gz == "bgzf":   # a damaged member (inflated on the device, one warp per member) is an error as well: sizes and CRC-32 are checked
+        bad = bytearray(e1)
+        for pos in (len(bad) // 3, len(bad) // 2 + 17):
+            bad[pos] ^= 0x10
+        st = host.FastqStream(m, paired=False, gz=True)
+        with pytest.raises(host.GeneFuseError):
+            st.feed(bytes(bad))
             st.finish()
         st.close()
 
