@@ -300,7 +300,9 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_bgzf_inflate(const uint8_t* 
         const uint8_t* src = out + c_op - c_dist;
         const bool apart = c_dist >= c_len; /* else byte k of the match is byte k mod dist of the `dist` bytes before it */
         uint8_t v = 0;
-        if (mine) v = __ldcg(src + (apart ? lane : lane % c_dist));
+        uint32_t si = lane;
+        if (!apart) si = lane % c_dist; /* (warp-uniform branch: the division is only paid by overlapping matches) */
+        if (mine) v = __ldcg(src + si);
         /* lane 0 decodes up to the next match (state 0), the end of the member (1) or an error (2) */
         uint32_t state = 0, len = 0, dist = 0;
         if (lane == 0) {
@@ -340,7 +342,8 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_bgzf_inflate(const uint8_t* 
             }
         }
         if (mine) out[c_op + lane] = v;
-        for (uint32_t k = lane + 32; k < c_len; k += 32) out[c_op + k] = __ldcg(src + (apart ? k : k % c_dist));
+        if (c_len > 32)
+            for (uint32_t k = lane + 32; k < c_len; k += 32) out[c_op + k] = __ldcg(src + (apart ? k : k % c_dist));
         const uint32_t packed = __shfl_sync(0xFFFFFFFFu, state | (len << 2) | (dist << 11), 0); /* len <= 258, dist <= 32768 */
         const uint32_t op0 = __shfl_sync(0xFFFFFFFFu, op, 0);
         if ((packed & 3u) != 0) break;

@@ -502,7 +502,7 @@ def test_packed_upload_uniform_chunks(mappers, small_panel, monkeypatch):
             pytest.skip("host without AVX-512BW: the packed upload is not offered")
         if force == "1":
             assert st.packed_upload == 1
-            assert st.h2d_bytes < 0.3 * (b.seq1.size + b.seq2.size)   # plane words only: 32 of 100 bytes per read
+            assert st.h2d_bytes < 0.4 * (b.seq1.size + b.seq2.size)   # plane words only (32 bytes per 100-base read) + the few exception words
         assert_same_matches(got, want, f"packed upload, uniform reads, force={force} chunk={chunk_mb} MB threads={threads}")
 
 
