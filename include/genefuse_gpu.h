@@ -383,8 +383,12 @@ int gf_stream_get_counts(const gf_stream* s, uint64_t* pairs_pushed, uint64_t* m
  * two files as they are read, in pieces that may end anywhere: whole records are mapped on the device as soon as
  * `chunk_bytes` (0 = 256 MiB) of text per mate have accumulated, the incomplete tail is carried over, and records are numbered
  * from the start of the files.  format = GF_FQ_GZIP (the caller decides from the file extension like FastqReader::new, :39-69):
- * the bytes are a gzip stream, possibly of several members (MultiGzDecoder, :49-55), inflated on the host (zlib, one thread
- * per mate) straight into the pinned text buffers.  gf_fastq_stream_finish ends the files (a last line without '\n' counts,
+ * the bytes are a gzip stream, possibly of several members (MultiGzDecoder, :49-55).  Blocked gzip (BGZF: what bgzip and
+ * bcl2fastq write — members of <= 64 KB of text that say their own size in the header) is inflated ON THE DEVICE: only the
+ * members' compressed payloads are copied, a warp per member decodes them, and a member whose sizes or CRC-32 do not come out
+ * exactly fails the call (GF_E_INVALID); members that a fed piece cuts in two wait for their other half.  Any other gzip member
+ * is inflated on the host (zlib, one thread per mate) into the pinned text buffers.  GF_BGZF_DEVICE=0 in the environment keeps
+ * blocked gzip on the host threads too.  gf_fastq_stream_finish ends the files (a last line without '\n' counts,
  * an incomplete last record is dropped, the shorter file decides the pair count: FastqReaderPair); records are collected
  * with gf_fastq_stream_take at any time. */
 #define GF_FQ_PLAIN 0

@@ -21,3 +21,6 @@ CMD="python bench.py --steps 2 --warmup 3 --legs main --no-cpu-baseline --no-e2e
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv $CMD > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'^k_(prep|seed|diag|scan|exact|verify)$' -s 18 -c 6 -f -o $out/${tag}_kernels $CMD > $out/${tag}_ncu.log 2>&1
 ls -la $out/${tag}_*
+# the device inflate of the .fq.gz leg: its launches alone
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_bgzf --csv --log-file $out/${tag}_inflate_launches.csv python bench.py --legs fastq > /dev/null 2>&1
+grep k_bgzf $out/${tag}_inflate_launches.csv | cut -d, -f5,14- | tail -3
