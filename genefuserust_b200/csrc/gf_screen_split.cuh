@@ -33,6 +33,29 @@ namespace split {
 using tpp::Col;
 using tpp::Lay;
 
+/* The sequence store streams: written once by k_prep, read once by k_seed and once by k_diag or k_scan.  Its loads and stores carry
+ * the streaming hint (ld / st.global.cs: first in line for eviction) so that they do not push the L2-resident filter and gene
+ * planes out (GF_STORE_STREAMING 0: plain accesses, for comparison). */
+#ifndef GF_STORE_STREAMING
+#define GF_STORE_STREAMING 1
+#endif
+template <class T>
+__device__ __forceinline__ T st_ld(const T* p) {
+#if GF_STORE_STREAMING
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+template <class T>
+__device__ __forceinline__ void st_st(T* p, T v) {
+#if GF_STORE_STREAMING
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 struct SeqStore {
     uint32_t* words;
     uint4* meta;
@@ -56,7 +79,7 @@ __device__ __forceinline__ uint32_t* slot_words(const SeqStore& st, uint32_t s) 
 
 __device__ __forceinline__ uint32_t fs_col(const uint32_t* col, int arr_base, uint32_t bitpos) {
     uint32_t wi = bitpos >> 5;
-    return __funnelshift_r(col[(size_t)(arr_base + (int)wi) * 32], col[(size_t)(arr_base + (int)wi + 1) * 32], bitpos & 31u);
+    return __funnelshift_r(st_ld(&col[(size_t)(arr_base + (int)wi) * 32]), st_ld(&col[(size_t)(arr_base + (int)wi + 1) * 32]), bitpos & 31u);
 }
 
 struct PrepParams {
@@ -190,10 +213,10 @@ __global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepPa
                         }
                     }
                 }
-                w[(size_t)k * 32] = lo; w[(size_t)(NW + k) * 32] = hi; w[(size_t)(2 * NW + k) * 32] = v;
+                st_st(&w[(size_t)k * 32], lo); st_st(&w[(size_t)(NW + k) * 32], hi); st_st(&w[(size_t)(2 * NW + k) * 32], v);
             }
             const uint32_t info = merged ? (0u | ((uint32_t)olen << 2) | ((uint32_t)diff << 14)) : 1u;
-            P.st.meta[slot0] = make_uint4((uint32_t)p, info, (uint32_t)len0, 0u);
+            st_st(&P.st.meta[slot0], make_uint4((uint32_t)p, info, (uint32_t)len0, 0u));
             c_seq++;
             c_merged += merged ? 1u : 0u;
             c_bytes += (unsigned)len0;
@@ -211,9 +234,9 @@ __global__ void __launch_bounds__(tpp::WARPS * 32, W == 5 ? 8 : 5) k_prep(PrepPa
                     lo = ~__brev(c.win(Lay<W>::C2LO, pos)) & v;
                     hi = __brev(c.win(Lay<W>::C2HI, pos)) & v;
                 }
-                w[(size_t)k * 32] = lo; w[(size_t)(NW + k) * 32] = hi; w[(size_t)(2 * NW + k) * 32] = v;
+                st_st(&w[(size_t)k * 32], lo); st_st(&w[(size_t)(NW + k) * 32], hi); st_st(&w[(size_t)(2 * NW + k) * 32], v);
             }
-            P.st.meta[slot0 + 1u] = make_uint4((uint32_t)p, 2u, (uint32_t)len2, 0u);
+            st_st(&P.st.meta[slot0 + 1u], make_uint4((uint32_t)p, 2u, (uint32_t)len2, 0u));
             c_seq++;
             c_bytes += (unsigned)len2;
             c_probes += (unsigned)(len2 >= 16 ? ((len2 - 16) >> 1) + 1 : 0);
@@ -268,9 +291,9 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
             uint32_t plo[4], phi[4], pv[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                plo[j] = col[(size_t)j * 32]; phi[j] = col[(size_t)(NW + j) * 32]; pv[j] = col[(size_t)(2 * NW + j) * 32];
+                plo[j] = st_ld(&col[(size_t)j * 32]); phi[j] = st_ld(&col[(size_t)(NW + j) * 32]); pv[j] = st_ld(&col[(size_t)(2 * NW + j) * 32]);
             }
-            const uint4 m = P.st.meta[s];
+            const uint4 m = st_ld(&P.st.meta[s]);
             const int len = (int)m.z;
             const int nprobe = len >= 16 ? ((len - 16) >> 1) + 1 : 0;
             if (nprobe == 0 && P.need_total > 0) have = false; /* cannot reach the gate: dropped here */
@@ -324,7 +347,7 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
                     }
                 }
             }
-            if (have) P.st.seed[s] = make_uint2(seed_val, seed_i);
+            if (have) st_st(&P.st.seed[s], make_uint2(seed_val, seed_i));
         }
         /* the two lists, aggregated over the block: one atomic per class, block and iteration (the list counters are
          * single hot addresses; a per-warp atomic on them serialises in L2) */
@@ -341,8 +364,8 @@ __global__ void __launch_bounds__(256) k_seed(SeedParams P) {
             for (int w = 0; w < 8; w++) { cls_base[w][threadIdx.x] = bb; bb += cls_cnt[w][threadIdx.x]; }
         }
         __syncthreads();
-        if (cls == 0) P.st.list[cls_base[wib][0] + __popc(m0 & gf_lanemask_lt())] = s;
-        else if (cls == 1) P.st.list[P.st.cap - 1u - (cls_base[wib][1] + __popc(m1 & gf_lanemask_lt()))] = s;
+        if (cls == 0) st_st(&P.st.list[cls_base[wib][0] + __popc(m0 & gf_lanemask_lt())], s);
+        else if (cls == 1) st_st(&P.st.list[P.st.cap - 1u - (cls_base[wib][1] + __popc(m1 & gf_lanemask_lt()))], s);
     }
 }
 
@@ -375,19 +398,19 @@ __global__ void __launch_bounds__(256) k_scan(ClassParams P) {
     const int need_major = P.need_total - P.need_minor;
     const uint32_t n = P.st.counters[2];
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-        const uint32_t s = P.st.list[P.st.cap - 1u - t];
-        const uint4 m = P.st.meta[s];
+        const uint32_t s = st_ld(&P.st.list[P.st.cap - 1u - t]);
+        const uint4 m = st_ld(&P.st.meta[s]);
         const int len = (int)m.z, nch = (len + 31) >> 5;
         const uint32_t* col = slot_words<W>(P.st, s);
-        uint32_t lo = col[0], hi = col[(size_t)NW * 32], v = col[(size_t)2 * NW * 32];
+        uint32_t lo = st_ld(&col[0]), hi = st_ld(&col[(size_t)NW * 32]), v = st_ld(&col[(size_t)2 * NW * 32]);
         /* k_seed already asked the filter about the 16-mers at offsets 0, 16, ..., 112 (seed.y: bits 0-7 present,
          * bits 8-15 valid = probed) */
-        const uint32_t pre = P.st.seed[s].y, pre_valid = (pre >> 8) & 0xFFu;
+        const uint32_t pre = st_ld(&P.st.seed[s]).y, pre_valid = (pre >> 8) & 0xFFu;
         int Pn = __popc(pre & 0xFFu);
         bool dead = false;
 #pragma unroll 1
         for (int k = 0; k < nch && !dead; k++) {
-            const uint32_t nlo = col[(size_t)(k + 1) * 32], nhi = col[(size_t)(NW + k + 1) * 32], nv = col[(size_t)(2 * NW + k + 1) * 32];
+            const uint32_t nlo = st_ld(&col[(size_t)(k + 1) * 32]), nhi = st_ld(&col[(size_t)(NW + k + 1) * 32]), nv = st_ld(&col[(size_t)(2 * NW + k + 1) * 32]);
             uint32_t om = run16(v, nv) & 0x55555555u;
             if (k < 4) om &= ~0x00010001u;                          /* offsets 32 k and 32 k + 16: probed by k_seed */
             const int beyond = len - 16 - 32 * (k + 1);            /* last probe offset relative to the next chunk */
@@ -463,9 +486,9 @@ __global__ void __launch_bounds__(256, 5) k_diag(ClassParams P) {
     const uint32_t n = P.st.counters[1];
     for (uint32_t t0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); t0 < n; t0 += gridDim.x * blockDim.x) {
         const bool have = t0 + lane < n;
-        const uint32_t s = have ? P.st.list[t0 + lane] : 0u;
-        const uint4 m = have ? P.st.meta[s] : make_uint4(0, 0, 0, 0);
-        const uint2 sd = have ? P.st.seed[s] : make_uint2(0, 0);
+        const uint32_t s = have ? st_ld(&P.st.list[t0 + lane]) : 0u;
+        const uint4 m = have ? st_ld(&P.st.meta[s]) : make_uint4(0, 0, 0, 0);
+        const uint2 sd = have ? st_ld(&P.st.seed[s]) : make_uint2(0, 0);
         const int len = (int)m.z, nch = have ? (len + 31) >> 5 : 0;
         const uint32_t* col = slot_words<W>(P.st, s);
         const bool rc = (sd.x & GF_SITE_STRAND) != 0;
@@ -480,11 +503,11 @@ __global__ void __launch_bounds__(256, 5) k_diag(ClassParams P) {
         /* read chunk k in the orientation of the comparison */
         auto read_chunk = [&](int k, uint32_t* lo, uint32_t* hi, uint32_t* v) {
             if (k >= nch) { *lo = *hi = *v = 0; return; }
-            if (!rc) { *lo = col[(size_t)k * 32]; *hi = col[(size_t)(NW + k) * 32]; *v = col[(size_t)(2 * NW + k) * 32]; return; }
+            if (!rc) { *lo = st_ld(&col[(size_t)k * 32]); *hi = st_ld(&col[(size_t)(NW + k) * 32]); *v = st_ld(&col[(size_t)(2 * NW + k) * 32]); return; }
             int pos = len - 32 * k - 32;
             uint32_t a, b, cc;
             if (pos >= 0) { a = fs_col(col, 0, (uint32_t)pos); b = fs_col(col, NW, (uint32_t)pos); cc = fs_col(col, 2 * NW, (uint32_t)pos); }
-            else { a = col[0] << (-pos); b = col[(size_t)NW * 32] << (-pos); cc = col[(size_t)2 * NW * 32] << (-pos); }
+            else { a = st_ld(&col[0]) << (-pos); b = st_ld(&col[(size_t)NW * 32]) << (-pos); cc = st_ld(&col[(size_t)2 * NW * 32]) << (-pos); }
             uint32_t vv = __brev(cc);
             *v = vv;
             *lo = ~__brev(a) & vv;
