@@ -318,7 +318,8 @@ bool gf_pack_available() {
      * pays when this process has cores (and their share of the memory system) to spare — 12 threads on a 16-core single-GPU
      * host: 40 ms instead of 64 per 10 M pairs; 9 threads per rank on a 24-core 2-GPU host: 56 instead of 64 — and it does
      * NOT when many ranks share few cores and one memory system: 8 ranks with 3 threads each on a 32-core 8-GPU host, where
-     * the eight copy engines already saturate the host (237 GB/s aggregate): 178 ms instead of 146.  Fewer than 8 packing
+     * the eight copy engines already saturate the host (237 GB/s aggregate): 178 ms instead of 146; 4 ranks with 6 threads each
+     * (final packer, two-ended upload): 83 ms instead of 67.  Fewer than 8 packing
      * threads (GF_PACK_THREADS, or 3/4 of the hardware threads): the ASCII is copied as it is.  GF_HOST_PACK=1 forces packing. */
     int min_threads = 8;
     if (const char* m = getenv("GF_PACK_MIN_THREADS")) { const int v = atoi(m); if (v >= 1) min_threads = v; } /* experiments */
