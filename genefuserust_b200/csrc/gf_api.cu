@@ -724,6 +724,7 @@ static int map_host_batch(gf_index* const* hs, uint32_t nh, const gf_batch* in, 
             if (rc != GF_OK) break;
         }
         while (rc == GF_OK && issued - collected >= (uint64_t)GF_STAGES) rc = collect(collected++); /* this issue reuses that stage */
+        queued_copy_ms(); /* (forget the finished copies before that stage's event is recorded again) */
         if (rc == GF_OK) rc = enqueue_chunk(issued, k, set);
         if (set >= 0) {
             std::lock_guard<std::mutex> lk(sh.mu);

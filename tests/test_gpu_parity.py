@@ -488,7 +488,12 @@ def test_packed_upload_uniform_chunks(mappers, small_panel, monkeypatch):
     bp.max_len = 100
     want = o.scan(b, threads=8)
     assert len(want) > 300
-    for force, chunk_mb, threads in (("1", "1", "5"), ("1", "8", "16"), ("1", "64", "3"), (None, "1", "8"), (None, "2", "12")):
+    for force, chunk_mb, threads, parts in (("1", "1", "5", None), ("1", "8", "16", "64"), ("1", "64", "3", "1"), (None, "1", "8", None),
+                                            (None, "2", "12", "7")):
+        if parts is None:      # parts per packing job (default: one per thread): the output layout depends on them, the records must not
+            monkeypatch.delenv("GF_PACK_PARTS", raising=False)
+        else:
+            monkeypatch.setenv("GF_PACK_PARTS", parts)
         if force is None:
             monkeypatch.delenv("GF_HOST_PACK", raising=False)
             monkeypatch.setenv("GF_PACK_MIN_THREADS", "1")
