@@ -171,7 +171,10 @@ int gf_fastq_parse_device(const uint8_t* d_text, uint64_t bytes, GfFastqTable* o
  * parallel: every match is copied by the whole warp (byte i of it is byte i mod dist of the `dist` bytes before it, so an
  * overlapping match is no special case).  A thread per member was measured first: the 32 streams of a warp are never at the same
  * instruction, the warp runs them one after the other and every copied byte costs an L2 round trip (1.1 GB/s of text per GPU);
- * a warp per member keeps ~26 members in flight per SM, each at the speed of its own chain.  The 8 decoding tables of a block
+ * a warp per member keeps ~26 members in flight per SM.  With one useful lane per warp the kernel is bound by instruction issue
+ * (ncu: 65 % issue utilisation, 7.0 G warp instructions per 3831 members = 10.3 ms), so what counts is instructions per symbol.
+ * Measured and rejected: lane 0 noting up to 64 matches per round in a shared-memory list that the warp then copies in order — no
+ * fewer instructions (7.5 G) and the L2 round trips no longer overlap with the decoding: 16.9 ms.  The 8 decoding tables of a block
  * live in shared memory (2.5 KB each) next to the four CRC-32 tables.  Every member's sizes and CRC-32 are known from its header
  * and trailer: a member that does not come out exactly is reported through `status`, never used. ---- */
 namespace {
