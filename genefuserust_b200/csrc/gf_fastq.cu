@@ -174,11 +174,11 @@ int gf_fastq_parse_device(const uint8_t* d_text, uint64_t bytes, GfFastqTable* o
  * a warp per member keeps ~26 members in flight per SM.  With one useful lane per warp the kernel is bound by instruction issue
  * (ncu: 65 % issue utilisation, 7.0 G warp instructions per 3831 members = 10.3 ms), so what counts is instructions per symbol.
  * Measured and rejected: lane 0 noting up to 64 matches per round in a shared-memory list that the warp then copies in order — no
- * fewer instructions (7.5 G) and the L2 round trips no longer overlap with the decoding: 16.9 ms.  The 8 decoding tables of a block
- * live in shared memory (2.5 KB each) next to the four CRC-32 tables.  Every member's sizes and CRC-32 are known from its header
+ * fewer instructions (7.5 G) and the L2 round trips no longer overlap with the decoding: 16.9 ms.  Blocks of 4 warps at 72 registers (no spills), 7 per SM: 8.9 ms (8-warp blocks capped at 64 registers with
+ * spills: 10.3 ms).  The decoding tables of a block's warps live in shared memory (2.5 KB each) next to the four CRC-32 tables.  Every member's sizes and CRC-32 are known from its header
  * and trailer: a member that does not come out exactly is reported through `status`, never used. ---- */
 namespace {
-constexpr int INF_WARPS = 8;
+constexpr int INF_WARPS = 4;
 constexpr size_t INF_TABLES = (sizeof(gfinf::Tables) + 15) / 16 * 16;
 constexpr size_t INF_SMEM = INF_WARPS * INF_TABLES + (4 * 256 + 32) * sizeof(uint32_t);
 
@@ -273,7 +273,7 @@ __device__ int block_header(Bits32& b, gfinf::Tables& T, uint8_t* out, uint32_t 
     return OK;
 }
 
-__global__ void __launch_bounds__(INF_WARPS * 32) k_bgzf_inflate(const uint8_t* __restrict__ comp, const GfBgzfMember* __restrict__ members,
+__global__ void __launch_bounds__(INF_WARPS * 32, 7) k_bgzf_inflate(const uint8_t* __restrict__ comp, const GfBgzfMember* __restrict__ members,
                                                                 uint32_t n, uint8_t* text, unsigned int* __restrict__ status) {
     using namespace gfinf;
     extern __shared__ __align__(16) unsigned char inf_smem[];
