@@ -290,7 +290,9 @@ static int validate_batch(const gf_batch* in) {
     return GF_OK;
 }
 
-/* Host batch: chunked double-buffered pipeline (H2D of chunk k+1 overlaps the kernels of chunk k).
+/* Host batch: chunked pipeline, up to GF_STAGES chunks in flight (the upload of a chunk overlaps the kernels of the chunks before;
+ * with the arenas in pinned memory the chunks are taken from both ends of the batch: packed by the host threads from the back,
+ * copied as ASCII from the front — see below).
  * nh > 1 = list mode: the same reads against several indices.  hs[0] owns the staging buffers, the streams and the
  * sequence store; every chunk is copied ONCE, converted / merged ONCE (k_prep) and then seeded, screened and verified
  * against each index in turn, on hs[0]'s stream. */
