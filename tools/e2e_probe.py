@@ -52,11 +52,20 @@ def run(tag, hint, env):
         os.environ.pop(k, None)
 
 
-for rep in range(3):
+for rep in range(2):
     run("hybrid upload (default)", 150, {})
-    run("one part per packing thread", 150, {"GF_PACK_PARTS": "12"})
-    run("24 parts", 150, {"GF_PACK_PARTS": "24"})
-    run("64 parts", 150, {"GF_PACK_PARTS": "64"})
-    run("chunk 128 MB", 150, {"GF_CHUNK_MB": "128"})
-    run("14 packing threads", 150, {"GF_PACK_THREADS": "14"})
     run("every chunk packed", 150, {"GF_HOST_PACK": "1"})
+    run("ascii ahead 0 ms (packers only, through the driver thread)", 150, {"GF_ASCII_AHEAD_MS": "0"})
+    run("ascii ahead 1 ms", 150, {"GF_ASCII_AHEAD_MS": "1"})
+    run("ascii ahead 4 ms", 150, {"GF_ASCII_AHEAD_MS": "4"})
+    for t in ("6", "8", "10", "14"):
+        run(f"{t} packing threads", 150, {"GF_PACK_THREADS": t, "GF_PACK_MIN_THREADS": "1"})
+    for mb in ("128", "384"):
+        run(f"chunk {mb} MB", 150, {"GF_CHUNK_MB": mb})
+    for parts in ("24", "48"):
+        run(f"{parts} parts per packing job", 150, {"GF_PACK_PARTS": parts})
+    run("ordinary stores in the packers", 150, {"GF_PACK_NT": "0"})
+os.environ["GF_HOST_PACK"] = "0"
+run("ASCII upload, hint=150 (per-chunk check), zero-copy qual", 150, {})
+run("ASCII upload, hint=0 (pre-scan), zero-copy qual", 0, {})
+run("ASCII upload, qualities copied", 150, {"GF_ZEROCOPY_QUAL": "0"})
